@@ -1,0 +1,202 @@
+/*
+ * slcl.h -- C ABI of libslcl.so: the B200 (sm_100a) implementation of the SLCL
+ * contrastive-loss hot path.
+ *
+ * The reference (Dinhthixuanbinh/Soft-Labeled-Contrastive-Learning) has no FFI
+ * layer: its boundary for this path is a set of Python callables
+ * (utils/loss.py, utils/losses.py, utils/utils_.py:479-624).  Each entry point
+ * below names the reference callable (file:line) whose arithmetic it
+ * replaces; the Python package `slcl` keeps the reference signatures and
+ * calls these functions through ctypes.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in `_host`;
+ *   - the caller owns and allocates every output and the workspace; nothing
+ *     is allocated or freed inside the library;
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     no host synchronisation, no host read-back;
+ *   - return value: 0 = SLCL_OK, negative = error (slcl_strerror()); errors
+ *     are detected before any launch, outputs are then untouched;
+ *   - no global mutable state besides cached device attributes, so any thread
+ *     may call, one process per GPU;
+ *   - "pixel order" is the reference's (b, h, w) order of an NCHW map:
+ *     pixel i = b*HW + p.
+ */
+#ifndef SLCL_H_
+#define SLCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLCL_VERSION 100            /* major*100 + minor */
+#define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
+#define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
+
+enum {
+  SLCL_OK = 0,
+  SLCL_ERR_INVALID_ARGUMENT = -1,   /* null pointer, non-positive size, K out of range ... */
+  SLCL_ERR_UNSUPPORTED = -2,        /* shape/stride combination without a kernel */
+  SLCL_ERR_WORKSPACE = -3,          /* workspace_bytes smaller than slcl_*_workspace_bytes() */
+  SLCL_ERR_CUDA = -4                /* launch failed; slcl_last_cuda_error() has the text */
+};
+
+typedef void* slcl_stream_t;        /* cudaStream_t */
+
+int         slcl_version(void);
+const char* slcl_strerror(int status);
+const char* slcl_last_cuda_error(void);     /* thread-local text of the last SLCL_ERR_CUDA */
+
+/* Strided view of a feature map: element (b, c, p) lives at
+ * base[b*stride_b + c*stride_c + p*stride_p] (strides in elements).
+ * NCHW contiguous: {C*HW, HW, 1}; rows [N,C] (reference MPCL.forward input,
+ * utils/loss.py:484): B=1, HW=N, {0, 1, C}. */
+typedef struct {
+  int64_t batch;       /* B */
+  int64_t channels;    /* C */
+  int64_t pixels;      /* HW (pixels per image) */
+  int64_t stride_b, stride_c, stride_p;
+} slcl_map_t;
+
+/* ---------------------------------------------------------------------------
+ * Prototype path: pixel -> class-centre margin InfoNCE.
+ * Replaces MPCL.forward (utils/loss.py:484-573) fused with the layout and
+ * normalisation work of mpcl_loss_calc (utils/loss.py:592-601) and the
+ * autograd backward of both.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int   n_class;           /* K, 2..SLCL_MAX_CLASSES          (MPCL.num_class) */
+  float temperature;       /* T                                (utils/loss.py:472) */
+  float base_temperature;  /* T_b                              (:473) */
+  float margin;            /* m; cos_m, sin_m, th, mm derive from it (:475-480) */
+  int   easy_margin;       /* :538-541 */
+  int   normalize;         /* 1: L2-normalise pixels and centres (mpcl_loss_calc :595,:600);
+                              0: inputs are already unit vectors (direct MPCL.forward call) */
+} slcl_proto_params_t;
+
+size_t slcl_proto_workspace_bytes(int64_t n_pixels);
+
+/* Forward.  labels [N] int64 (values outside [0,K) give an all-zero positive
+ * row, as torch.eq against arange(K) does at :513) OR soft_mask [N,K] fp32
+ * row-major (:516-517); exactly one of them non-null.  sel [N] fp32 or null
+ * (pixel_sel_loc, :558-565).  centres [K,C] fp32 row-major, raw (un-normalised
+ * when params.normalize).
+ * Outputs: stash [(K+1)*N] fp32 (per-pixel backward coefficients, planar),
+ *          cstate [K*C + K] fp32 (unit centres, centre norms),
+ *          scal [4] fp32 = {loss, d loss / d (sum of weighted rows), sum(sel) or N, sum(sel*row loss)}. */
+int slcl_proto_fwd(const float* feat, const slcl_map_t* map,
+                   const int64_t* labels, const float* soft_mask, const float* sel,
+                   const float* centres, const slcl_proto_params_t* params,
+                   float* stash, float* cstate, float* scal,
+                   void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
+/* Backward w.r.t. the feature map.  grad_out: device scalar dL/dloss.
+ * dfeat uses the strides of `map`. */
+int slcl_proto_bwd(const float* feat, const slcl_map_t* map,
+                   const float* stash, const float* cstate, const float* scal, const float* grad_out,
+                   const slcl_proto_params_t* params, float* dfeat, slcl_stream_t stream);
+
+/* Backward w.r.t. the raw centres [K,C] (only when they require grad; both
+ * reference callers pass detached centres, trainer/Trainer_MPSCL.py:139,145). */
+size_t slcl_proto_bwd_centres_workspace_bytes(int64_t n_pixels, int64_t channels, int n_class);
+int slcl_proto_bwd_centres(const float* feat, const slcl_map_t* map,
+                           const float* stash, const float* cstate, const float* scal, const float* grad_out,
+                           const slcl_proto_params_t* params, float* dcentres,
+                           void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
+/* generate_pseudo_label (utils/utils_.py:597-624): label = argmax_k cos(x_i, c_k)
+ * (first index on ties), sel = (top1 - top2 > threshold) ? 1 : 0. */
+int slcl_pseudo_label(const float* feat, const slcl_map_t* map, const float* centres, int n_class,
+                      float threshold, int64_t* label, float* sel,
+                      void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Class sums: one pass over an NCHW map producing, per weight column j
+ * (j = partition*K + class), sum_i w_ij * x_i  (C values) and sum_i w_ij.
+ * Replaces the per-class masked sums of update_class_center_iter
+ * (utils/utils_.py:580-590) and cal_centroid (utils/utils_.py:509-540).
+ *
+ * Weights:  hard   w_ik = [label_i == k]                              (labels != null)
+ *           soft   w_ik = probs[b,k,p] * cert_i      (weighted != 0)  (probs  != null)
+ *           argmax w_ik = [argmax_k probs == k] * cert_i (weighted == 0)
+ *           cert_i = [max_k probs >= threshold] if 0 < threshold < 1 else 1
+ *           and, when part_id != null, times [part_id_i == partition].
+ * Output sums [P*K, C+1] fp64 row-major: columns 0..C-1 = weighted feature
+ * sums, column C = weight sum (exact integer counts for hard labels).  This is
+ * the buffer a multi-GPU caller all-reduces.
+ * ------------------------------------------------------------------------- */
+size_t slcl_class_sums_workspace_bytes(int64_t batch, int64_t channels, int64_t pixels, int n_cols);
+int slcl_class_sums(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                    const int64_t* labels, const float* probs, int weighted, float threshold,
+                    const int32_t* part_id, int n_partitions, int n_class,
+                    double* sums, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
+/* update_class_center_iter tail (utils/utils_.py:585-592): per class
+ * batch = sum/count, or the old centre when count == 0 (decided on the
+ * device, no host sync); new = m*old + (1-m)*batch. */
+int slcl_ema_finalize(const double* sums, const float* old_centres, float m, int n_class, int64_t channels,
+                      float* new_centres, slcl_stream_t stream);
+
+/* cal_centroid tail (utils/utils_.py:520-523,538,552-563): centroid = sum/(weight+1e-7),
+ * optional EMA with `previous` [K,C] (same tensor for every set) when non-null.
+ * Outputs centroids [sets*K, C] fp32 and inv_weight [sets*K] fp32 = 1/(weight+1e-7). */
+int slcl_centroid_finalize(const double* sums, const float* previous, float momentum, int n_sets, int n_class,
+                           int64_t channels, float* centroids, float* inv_weight, slcl_stream_t stream);
+
+/* Backward of the (soft / hard) centroid of cal_centroid.
+ * With gc_j = grad_centroids_j * ema_scale / (W_j + 1e-7) and mu_j = S_j / (W_j + 1e-7)
+ * (S, W from `sums`, the same -- possibly all-reduced -- buffer the forward used):
+ *   dfeat[b,c,p]  = sum_j w_ij * gc[j,c]
+ *   dprobs[b,k,p] = cert_i * [part_i] * ( x_i . gc_j - mu_j . gc_j ),  j = part_i*K + k   (soft weighted only)
+ * ema_scale = 1 - momentum when the forward applied the EMA, else 1.
+ * dprobs may be null (hard labels / arg-max weights: no gradient to the labels). */
+size_t slcl_centroid_bwd_workspace_bytes(int64_t channels, int n_cols);
+int slcl_centroid_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                      const int64_t* labels, const float* probs, int weighted, float threshold,
+                      const int32_t* part_id, int n_partitions, int n_class,
+                      const float* grad_centroids, const double* sums, float ema_scale,
+                      float* dfeat, float* dprobs, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Centroid <-> centroid InfoNCE and centroid-norm regulariser on [K,C].
+ * Replaces ContrastiveLoss.forward (utils/loss.py:241-275; `tau` is unused
+ * there and therefore absent here) and the inline CNR of
+ * trainer/Trainer_MCCL.py:303-315.  One block; writes the loss and both
+ * gradients (for dL/dloss = 1) in a single launch.
+ *   mode 0: contrastive, rows [first_row, n_rows)   (n_rows is the reference's hard-coded 4)
+ *   mode 1: contrastive, split form (:268-270)
+ *   mode 2: CNR = mean_k (||t_k|| - ||s_k||)^2
+ * ------------------------------------------------------------------------- */
+int slcl_centroid_loss(const float* centroid_s, const float* centroid_t, int n_class, int64_t channels,
+                       int mode, int first_row, int n_rows, int norm,
+                       float* loss, float* d_s, float* d_t, slcl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Sampler: per-class compaction + gather (north_star item 1).
+ * slcl_compact_by_class: stable compaction of pixel indices by label, order
+ * bit-identical to torch.nonzero(labels == k) for every k.  counts [K] int64,
+ * offsets [K+1] int64 (exclusive scan), index [N] int64 (class-major).
+ * slcl_gather_unit_rows: rows pixel_idx of an NCHW map -> [R, C] L2-normalised
+ * (eps 1e-12) bf16 and/or fp32 row-major, inverse norms [R] fp32.
+ * ------------------------------------------------------------------------- */
+size_t slcl_compact_workspace_bytes(int64_t n_pixels, int n_class);
+int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, int n_class,
+                          int64_t* counts, int64_t* offsets, int64_t* index,
+                          void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                          const int64_t* pixel_idx, int64_t n_rows, int normalize,
+                          void* rows_bf16, float* rows_f32, float* inv_norm, slcl_stream_t stream);
+/* scatter-add of row gradients back into an NCHW gradient map, through the
+ * normalisation backward: dx = (g - xhat (xhat.g)) * inv_norm. */
+int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                          const int64_t* pixel_idx, int64_t n_rows, int normalize,
+                          const float* d_rows, const float* inv_norm, float* dfeat, slcl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SLCL_H_ */

@@ -1,0 +1,600 @@
+// class_sums.cu -- per-class (and per rMC partition) weighted feature sums over an
+// NCHW map, their finalisers (EMA class centres, centroids) and the centroid
+// backward.
+//
+// Replaces (reference, file:line):
+//   update_class_center_iter   utils/utils_.py:568-594  (K masked full-map passes + K host syncs)
+//   cal_centroid               utils/utils_.py:479-565  (hard / soft / arg-max weights, partitions, EMA)
+//   autograd backward of cal_centroid (dfeat and d soft-label), SURVEY.md appendix A.3 / A.4
+//
+// Roofline: HBM.  Segmented warp reduction: a lane owns VEC (=4) consecutive
+// pixels, a warp owns CPW channels; the lane's weight row w[pixel][column] is
+// built once per tile in registers, each channel plane is read with one
+// coalesced 128-bit load per lane, and the partial sums acc[channel][column]
+// stay in registers across ALL tiles of the persistent block.  The cross-lane
+// (shuffle) reduction happens once per block at the very end, so the steady
+// state is load + FMA only: 4C + 8 bytes per pixel, one pass, no atomics.
+// Per-block partials are summed in fp64 by a second tiny kernel in block
+// order (deterministic; exact integer counts beyond 2^24).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace slcl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+enum WeightMode { kHard = 0, kSoft = 1, kPlanar = 2 };
+
+struct SumArgs {
+  const float* feat;
+  int64_t batch, channels, pixels, sb, sc, sp;
+  int mode;
+  const int64_t* labels;     // kHard: [N]
+  const float* probs;        // kSoft: [B,K,HW]
+  int weighted;              // kSoft: 1 = p_k weights, 0 = arg-max one-hot
+  float threshold;           // certainty threshold, active when 0 < t < 1
+  const int32_t* part_id;    // [N] or null
+  int n_part, n_class;
+  const float* planar;       // kPlanar: [cols][N]
+  int n_cols;                // logical columns (n_part * n_class, or planar cols)
+  int64_t tiles_per_image, n_tiles;
+  int cg_per_block, pt_per_block;   // warps = cg_per_block * pt_per_block
+  float* partial;            // [gridDim.x][KWT][C+1]
+};
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) { float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else { v[0] = ld_stream1(p); }
+}
+template <int VEC>
+__device__ __forceinline__ void ld_vec_keep(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else { v[0] = *p; }
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+  else st_stream1(p, v[0]);
+}
+
+// Weight row(s) of VEC pixels starting at image b, pixel p (flat index pix).
+// Hard labels: utils_.py:581 / :535.  Soft: :517-519 (weighted) or :524-525
+// (arg-max one-hot); certainty :511-514; partitions: SURVEY.md 8(c)-2.
+template <int KWT, int VEC>
+__device__ __forceinline__ void build_weights(const SumArgs& a, int64_t b, int64_t p, int64_t pix, float (&w)[VEC][KWT]) {
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int j = 0; j < KWT; ++j) w[v][j] = 0.f;
+
+  if (a.mode == kPlanar) {
+    const int64_t n = a.batch * a.pixels;
+#pragma unroll
+    for (int j = 0; j < KWT; ++j) {
+      if (j < a.n_cols) {
+        float t[VEC];
+        ld_vec_keep<VEC>(a.planar + (int64_t)j * n + pix, t);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v][j] = t[v];
+      }
+    }
+    return;
+  }
+  int part[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) part[v] = a.part_id ? a.part_id[pix + v] : 0;
+
+  if (a.mode == kHard) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      long long lab = a.labels[pix + v];
+      bool ok = lab >= 0 && lab < a.n_class && part[v] >= 0 && part[v] < a.n_part;
+      int col = ok ? part[v] * a.n_class + (int)lab : -1;
+#pragma unroll
+      for (int j = 0; j < KWT; ++j) w[v][j] = (j == col) ? 1.0f : 0.0f;
+    }
+    return;
+  }
+  // soft probabilities, planar per image: probs[(b*K + k)*HW + p]
+  float pr[SLCL_MAX_CLASSES][VEC];
+#pragma unroll
+  for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+    if (k < a.n_class) ld_vec_keep<VEC>(a.probs + (b * a.n_class + k) * a.pixels + p, pr[k]);
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+      if (k < a.n_class && pr[k][v] > best) { best = pr[k][v]; arg = k; }
+    }
+    float cert = (a.threshold > 0.f && a.threshold < 1.f) ? ((best >= a.threshold) ? 1.f : 0.f) : 1.f;
+    bool ok = part[v] >= 0 && part[v] < a.n_part;
+#pragma unroll
+    for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+      if (k < a.n_class) {
+        float wk = a.weighted ? pr[k][v] * cert : ((k == arg) ? cert : 0.f);
+        int col = part[v] * a.n_class + k;
+#pragma unroll
+        for (int j = 0; j < KWT; ++j) if (ok && j == col) w[v][j] = wk;
+      }
+    }
+  }
+}
+
+template <int KWT, int CPW, int VEC>
+__global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a) {
+  __shared__ float s_acc[kWarps][CPW * KWT];
+  __shared__ float s_w[kWarps][KWT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = warp % a.cg_per_block, pt = warp / a.cg_per_block;
+  const int C = (int)a.channels;
+  const int c0 = (blockIdx.y * a.cg_per_block + cg) * CPW;
+  const bool count_weights = (blockIdx.y == 0) && (cg == 0);
+
+  float acc[CPW][KWT];
+  float wacc[KWT];
+#pragma unroll
+  for (int j = 0; j < CPW; ++j)
+#pragma unroll
+    for (int q = 0; q < KWT; ++q) acc[j][q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < KWT; ++q) wacc[q] = 0.f;
+
+  const int64_t n_super = ceil_div<int64_t>(a.n_tiles, a.pt_per_block);
+  for (int64_t s = blockIdx.x; s < n_super; s += gridDim.x) {
+    const int64_t tile = s * a.pt_per_block + pt;
+    if (tile >= a.n_tiles) continue;
+    const int64_t b = tile / a.tiles_per_image;
+    const int64_t p = (tile - b * a.tiles_per_image) * (32 * VEC) + (int64_t)lane * VEC;
+    if (p >= a.pixels) continue;
+    const int64_t pix = b * a.pixels + p;
+    float w[VEC][KWT];
+    build_weights<KWT, VEC>(a, b, p, pix, w);
+    const float* base = a.feat + b * a.sb + p * a.sp;
+    float x[CPW][VEC];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) {
+      if (c0 + j < C) ld_vec<VEC>(base + (int64_t)(c0 + j) * a.sc, x[j]);
+      else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[j][v] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CPW; ++j)
+#pragma unroll
+      for (int q = 0; q < KWT; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[j][q] = fmaf(w[v][q], x[j][v], acc[j][q]);
+    if (count_weights) {
+#pragma unroll
+      for (int q = 0; q < KWT; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wacc[q] += w[v][q];
+    }
+  }
+  // one cross-lane reduction per block
+#pragma unroll
+  for (int j = 0; j < CPW; ++j)
+#pragma unroll
+    for (int q = 0; q < KWT; ++q) {
+      float r = warp_sum(acc[j][q]);
+      if (lane == 0) s_acc[warp][j * KWT + q] = r;
+    }
+#pragma unroll
+  for (int q = 0; q < KWT; ++q) {
+    float r = warp_sum(wacc[q]);
+    if (lane == 0) s_w[warp][q] = r;
+  }
+  __syncthreads();
+  // combine the pixel-tile warps that share a channel group, in fixed order
+  float* out = a.partial + (int64_t)blockIdx.x * KWT * (C + 1);
+  for (int idx = threadIdx.x; idx < a.cg_per_block * CPW * KWT; idx += kThreads) {
+    int g = idx / (CPW * KWT), r = idx % (CPW * KWT);
+    int j = r / KWT, q = r % KWT;
+    int c = (blockIdx.y * a.cg_per_block + g) * CPW + j;
+    if (c < C) {
+      float t = 0.f;
+      for (int pp = 0; pp < a.pt_per_block; ++pp) t += s_acc[pp * a.cg_per_block + g][r];
+      out[(int64_t)q * (C + 1) + c] = t;
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < KWT) {
+    float t = 0.f;
+    for (int pp = 0; pp < a.pt_per_block; ++pp) t += s_w[pp * a.cg_per_block][threadIdx.x];
+    out[(int64_t)threadIdx.x * (C + 1) + C] = t;
+  }
+}
+
+// sums[col][c] = sum over blocks (fp64, block order)
+__global__ void __launch_bounds__(kThreads) class_sums_reduce_kernel(const float* partial, int n_blocks, int kwt,
+                                                                     int n_cols, int C, double* sums) {
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  const int row = C + 1;
+  if (idx >= n_cols * row) return;
+  const int col = idx / row, c = idx % row;
+  double t = 0.0;
+  for (int b = 0; b < n_blocks; ++b) t += (double)partial[((int64_t)b * kwt + col) * row + c];
+  sums[idx] = t;
+}
+
+// utils_.py:585-592
+__global__ void __launch_bounds__(kThreads) ema_finalize_kernel(const double* sums, const float* old_c, float m, int K,
+                                                                int C, float* out) {
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= K * C) return;
+  const int k = idx / C, c = idx % C;
+  const double cnt = sums[(int64_t)k * (C + 1) + C];
+  const float old = old_c[idx];
+  float batch;
+  if (cnt == 0.0) batch = old;                                              // :585-586
+  else batch = (float)sums[(int64_t)k * (C + 1) + c] / (float)cnt;          // :588
+  out[idx] = m * old + (1.0f - m) * batch;                                  // :592
+}
+
+// utils_.py:520-523 / :538 and EMA :552-563
+__global__ void __launch_bounds__(kThreads) centroid_finalize_kernel(const double* sums, const float* prev, float mom,
+                                                                     int rows, int K, int C, float* cen, float* inv_w) {
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= rows * C) return;
+  const int r = idx / C, c = idx % C;
+  const float wsum = (float)sums[(int64_t)r * (C + 1) + C] + 1e-7f;
+  float mu = (float)sums[(int64_t)r * (C + 1) + c] / wsum;
+  if (prev != nullptr) mu = mom * prev[(r % K) * C + c] + (1.0f - mom) * mu;
+  cen[idx] = mu;
+  if (c == 0) inv_w[r] = 1.0f / wsum;
+}
+
+// ---------------------------------------------------------------------------
+// centroid backward (A.4):  dfeat = sum_j w_ij gc_j ;  dprobs_ik = cert*[part]*(x_i.gc_j - mu_j.gc_j)
+// ---------------------------------------------------------------------------
+struct CenBwdArgs {
+  SumArgs s;
+  const float* gc;          // [cols][C]
+  const float* mu_dot_gc;   // [cols]
+  float* dfeat;
+  float* dprobs;            // [B,K,HW] or null
+};
+
+// gc_j = dL/dcentroid_j * ema_scale / (W_j + 1e-7);  mu_dot_gc_j = mu_j . gc_j  with mu_j = S_j / (W_j + 1e-7)
+__global__ void __launch_bounds__(kThreads) centroid_bwd_prep_kernel(const float* grad_cen, const double* sums,
+                                                                     float ema_scale, int C, float* gc, float* mu_dot_gc) {
+  __shared__ float red[kWarps];
+  const int j = blockIdx.x;
+  const float wsum = (float)sums[(int64_t)j * (C + 1) + C] + 1e-7f;
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    const float g = grad_cen[(int64_t)j * C + c] * ema_scale / wsum;
+    const float mu = (float)sums[(int64_t)j * (C + 1) + c] / wsum;
+    gc[(int64_t)j * C + c] = g;
+    acc = fmaf(mu, g, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kWarps; ++w) t += red[w];
+    mu_dot_gc[j] = t;
+  }
+}
+
+template <int KWT> constexpr int kwpad() { return (KWT + 3) / 4 * 4; }
+
+template <int KWT, int VEC, bool HAS_DP>
+__global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs a) {
+  constexpr int KP = kwpad<KWT>();
+  extern __shared__ __align__(16) float sG[];        // [C][KP]
+  const int C = (int)a.s.channels;
+  for (int idx = threadIdx.x; idx < C * KP; idx += kThreads) {
+    int c = idx / KP, j = idx % KP;
+    sG[idx] = (j < a.s.n_cols) ? a.gc[(int64_t)j * C + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t groups = a.s.pixels / VEC;
+  if (g >= a.s.batch * groups) return;
+  const int64_t b = g / groups;
+  const int64_t p = (g - b * groups) * VEC;
+  const int64_t pix = b * a.s.pixels + p;
+  float w[VEC][KWT];
+  build_weights<KWT, VEC>(a.s, b, p, pix, w);
+  const float* src = a.s.feat + b * a.s.sb + p * a.s.sp;
+  float* dst = a.dfeat + b * a.s.sb + p * a.s.sp;
+  float dot[HAS_DP ? KWT : 1][VEC];
+#pragma unroll
+  for (int j = 0; j < (HAS_DP ? KWT : 1); ++j)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dot[j][v] = 0.f;
+
+  constexpr int U = 4;
+  for (int c = 0; c < C; c += U) {
+    float x[U][VEC];
+    if constexpr (HAS_DP) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (c + u < C) ld_vec<VEC>(src + (int64_t)(c + u) * a.s.sc, x[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c + u < C) {
+        float gj[KP];
+        const float4* row = reinterpret_cast<const float4*>(sG + (size_t)(c + u) * KP);
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q) { float4 t = row[q]; gj[4 * q] = t.x; gj[4 * q + 1] = t.y; gj[4 * q + 2] = t.z; gj[4 * q + 3] = t.w; }
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < KWT; ++j) t = fmaf(w[v][j], gj[j], t);
+          o[v] = t;
+          if constexpr (HAS_DP) {
+#pragma unroll
+            for (int j = 0; j < KWT; ++j) dot[j][v] = fmaf(x[u][v], gj[j], dot[j][v]);
+          }
+        }
+        st_vec<VEC>(dst + (int64_t)(c + u) * a.s.sc, o);
+      }
+    }
+  }
+  if constexpr (HAS_DP) {
+    // d w_ij / d p_ik = cert_i * [part_i == j / K]  (weighted soft labels only)
+    const int K = a.s.n_class;
+    const bool use_thr = a.s.threshold > 0.f && a.s.threshold < 1.f;
+    float cert[VEC];
+    int part[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { cert[v] = 1.f; part[v] = a.s.part_id ? a.s.part_id[pix + v] : 0; }
+    if (use_thr) {
+      float pr_max[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) pr_max[v] = -INFINITY;
+      for (int k = 0; k < K; ++k) {
+        float t[VEC];
+        ld_vec_keep<VEC>(a.s.probs + (b * K + k) * a.s.pixels + p, t);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) pr_max[v] = fmaxf(pr_max[v], t[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) cert[v] = (pr_max[v] >= a.s.threshold) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      if (part[v] < 0 || part[v] >= a.s.n_part) cert[v] = 0.f;
+    // statically indexed selection of column part*K + k (keeps dot[][] in registers)
+#pragma unroll
+    for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+      if (k < K) {
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int col = part[v] * K + k;
+          float val = 0.f;
+#pragma unroll
+          for (int j = 0; j < KWT; ++j) val = (j == col) ? dot[j][v] - a.mu_dot_gc[j] : val;
+          o[v] = cert[v] * val;
+        }
+        st_vec<VEC>(a.dprobs + (b * K + k) * a.s.pixels + p, o);
+      }
+    }
+  }
+}
+
+// ------------------------------ host side ----------------------------------
+int pick_kwt(int n_cols) {
+  static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
+  for (int o : opts) if (n_cols <= o) return o;
+  return -1;
+}
+
+struct SumPlan { int kwt, cpw, vec, cg_per_block, pt_per_block; dim3 grid; int64_t tiles_per_image, n_tiles; };
+
+SumPlan plan_sums(int64_t B, int64_t C, int64_t HW, int n_cols, bool vec4) {
+  SumPlan p;
+  p.kwt = pick_kwt(n_cols);
+  p.cpw = p.kwt <= 5 ? 8 : (p.kwt <= 8 ? 4 : 2);
+  p.vec = vec4 ? 4 : 1;
+  int n_groups = (int)ceil_div<int64_t>(C, p.cpw);
+  int cg = 1;
+  while (cg < n_groups && cg < kWarps) cg *= 2;
+  p.cg_per_block = cg;
+  p.pt_per_block = kWarps / cg;
+  p.tiles_per_image = ceil_div<int64_t>(HW, 32 * p.vec);
+  p.n_tiles = B * p.tiles_per_image;
+  int gy = (int)ceil_div<int64_t>(n_groups, cg);
+  int64_t n_super = ceil_div<int64_t>(p.n_tiles, p.pt_per_block);
+  int64_t gx = (int64_t)sm_count() * 2 / gy;
+  if (gx < 1) gx = 1;
+  // keep at least 4 super tiles per block so the end-of-block reduction is amortised
+  if (gx > ceil_div<int64_t>(n_super, 4)) gx = ceil_div<int64_t>(n_super, 4);
+  if (gx < 1) gx = 1;
+  p.grid = dim3((unsigned)gx, (unsigned)gy, 1);
+  return p;
+}
+
+size_t partial_bytes(const SumPlan& p, int64_t C) {
+  return align_up((size_t)p.grid.x * p.kwt * (C + 1) * sizeof(float), 256);
+}
+
+template <int KWT, int CPW>
+void launch_sums(const SumArgs& a, const SumPlan& p, cudaStream_t stream) {
+  if (p.vec == 4) class_sums_kernel<KWT, CPW, 4><<<p.grid, kThreads, 0, stream>>>(a);
+  else class_sums_kernel<KWT, CPW, 1><<<p.grid, kThreads, 0, stream>>>(a);
+}
+
+int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (a.n_cols < 1 || a.n_cols > SLCL_MAX_WEIGHT_COLS) return SLCL_ERR_INVALID_ARGUMENT;
+  SumPlan p = plan_sums(a.batch, a.channels, a.pixels, a.n_cols, vec4);
+  if (p.kwt < 0) return SLCL_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < partial_bytes(p, a.channels) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  a.tiles_per_image = p.tiles_per_image; a.n_tiles = p.n_tiles;
+  a.cg_per_block = p.cg_per_block; a.pt_per_block = p.pt_per_block;
+  a.partial = reinterpret_cast<float*>(workspace);
+  switch (p.kwt) {
+    case 2: launch_sums<2, 8>(a, p, stream); break;
+    case 3: launch_sums<3, 8>(a, p, stream); break;
+    case 4: launch_sums<4, 8>(a, p, stream); break;
+    case 5: launch_sums<5, 8>(a, p, stream); break;
+    case 6: launch_sums<6, 4>(a, p, stream); break;
+    case 8: launch_sums<8, 4>(a, p, stream); break;
+    case 10: launch_sums<10, 2>(a, p, stream); break;
+    case 12: launch_sums<12, 2>(a, p, stream); break;
+    case 16: launch_sums<16, 2>(a, p, stream); break;
+    default: return SLCL_ERR_INVALID_ARGUMENT;
+  }
+  const int total = a.n_cols * ((int)a.channels + 1);
+  class_sums_reduce_kernel<<<ceil_div(total, kThreads), kThreads, 0, stream>>>(a.partial, (int)p.grid.x, p.kwt, a.n_cols,
+                                                                              (int)a.channels, sums);
+  return check_launch("slcl_class_sums");
+}
+
+bool nchw_vec4(const float* feat, int64_t C, int64_t HW, std::initializer_list<const void*> ptrs) {
+  bool ok = (HW % 4 == 0);
+  for (const void* q : ptrs) ok = ok && (q == nullptr || aligned16(q));
+  (void)feat; (void)C;
+  return ok;
+}
+
+}  // namespace
+
+size_t class_sums_ws_bytes(int64_t batch, int64_t channels, int64_t pixels, int n_cols) {
+  if (batch <= 0 || channels <= 0 || pixels <= 0 || n_cols < 1 || n_cols > SLCL_MAX_WEIGHT_COLS) return 0;
+  // the grid never exceeds 2 blocks per SM; size for the worst case of either vector width
+  int kwt = pick_kwt(n_cols);
+  size_t blocks = (size_t)sm_count() * 2;
+  return align_up(blocks * kwt * (channels + 1) * sizeof(float), 256);
+}
+
+// used by slcl_proto_bwd_centres: weights are the planar stash rows [cols][N]
+int class_sums_planar_weights(const float* feat, const slcl_map_t* map, const float* weights, int n_cols, double* sums,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SumArgs a{};
+  a.feat = feat;
+  a.batch = map->batch; a.channels = map->channels; a.pixels = map->pixels;
+  a.sb = map->stride_b; a.sc = map->stride_c; a.sp = map->stride_p;
+  a.mode = kPlanar; a.planar = weights; a.n_cols = n_cols; a.n_part = 1; a.n_class = n_cols;
+  bool vec4 = (map->stride_p == 1) && (map->pixels % 4 == 0) && (map->stride_c % 4 == 0) && (map->stride_b % 4 == 0) &&
+              aligned16(feat) && aligned16(weights);
+  return run_class_sums(a, vec4, sums, workspace, workspace_bytes, stream);
+}
+
+}  // namespace slcl
+
+using namespace slcl;
+
+extern "C" size_t slcl_class_sums_workspace_bytes(int64_t batch, int64_t channels, int64_t pixels, int n_cols) {
+  return class_sums_ws_bytes(batch, channels, pixels, n_cols);
+}
+
+extern "C" int slcl_class_sums(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                               const int64_t* labels, const float* probs, int weighted, float threshold,
+                               const int32_t* part_id, int n_partitions, int n_class, double* sums, void* workspace,
+                               size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !sums || !workspace) return SLCL_ERR_INVALID_ARGUMENT;
+  if ((labels == nullptr) == (probs == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class < 1 || n_class > kMaxK || n_partitions < 1 || n_partitions * n_class > SLCL_MAX_WEIGHT_COLS)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_partitions > 1 && part_id == nullptr) return SLCL_ERR_INVALID_ARGUMENT;
+  SumArgs a{};
+  a.feat = feat;
+  a.batch = batch; a.channels = channels; a.pixels = pixels;
+  a.sb = channels * pixels; a.sc = pixels; a.sp = 1;
+  a.mode = labels ? kHard : kSoft;
+  a.labels = labels; a.probs = probs; a.weighted = weighted; a.threshold = threshold;
+  a.part_id = part_id; a.n_part = n_partitions; a.n_class = n_class;
+  a.n_cols = n_partitions * n_class;
+  bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id});
+  return run_class_sums(a, vec4, sums, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int slcl_ema_finalize(const double* sums, const float* old_centres, float m, int n_class, int64_t channels,
+                                 float* new_centres, slcl_stream_t stream_) {
+  if (!sums || !old_centres || !new_centres || n_class < 1 || channels <= 0) return SLCL_ERR_INVALID_ARGUMENT;
+  const int total = n_class * (int)channels;
+  ema_finalize_kernel<<<ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream_>>>(sums, old_centres, m, n_class,
+                                                                                        (int)channels, new_centres);
+  return check_launch("slcl_ema_finalize");
+}
+
+extern "C" int slcl_centroid_finalize(const double* sums, const float* previous, float momentum, int n_sets,
+                                      int n_class, int64_t channels, float* centroids, float* inv_weight,
+                                      slcl_stream_t stream_) {
+  if (!sums || !centroids || !inv_weight || n_sets < 1 || n_class < 1 || channels <= 0)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  const int rows = n_sets * n_class;
+  const int total = rows * (int)channels;
+  centroid_finalize_kernel<<<ceil_div(total, kThreads), kThreads, 0, (cudaStream_t)stream_>>>(
+      sums, previous, momentum, rows, n_class, (int)channels, centroids, inv_weight);
+  return check_launch("slcl_centroid_finalize");
+}
+
+extern "C" size_t slcl_centroid_bwd_workspace_bytes(int64_t channels, int n_cols) {
+  if (channels <= 0 || n_cols < 1) return 0;
+  return align_up((size_t)n_cols * (channels + 1) * sizeof(float), 256);
+}
+
+extern "C" int slcl_centroid_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                                 const int64_t* labels, const float* probs, int weighted, float threshold,
+                                 const int32_t* part_id, int n_partitions, int n_class, const float* grad_centroids,
+                                 const double* sums, float ema_scale, float* dfeat, float* dprobs, void* workspace,
+                                 size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !grad_centroids || !sums || !dfeat || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if ((labels == nullptr) == (probs == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class < 1 || n_class > kMaxK || n_partitions < 1 || n_partitions * n_class > SLCL_MAX_WEIGHT_COLS)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_partitions > 1 && part_id == nullptr) return SLCL_ERR_INVALID_ARGUMENT;
+  if (dprobs != nullptr && (probs == nullptr || !weighted)) return SLCL_ERR_INVALID_ARGUMENT;
+  const int n_cols = n_partitions * n_class;
+  if (workspace_bytes < slcl_centroid_bwd_workspace_bytes(channels, n_cols) || !aligned16(workspace))
+    return SLCL_ERR_WORKSPACE;
+  float* gc = reinterpret_cast<float*>(workspace);
+  float* mu_dot_gc = gc + (size_t)n_cols * channels;
+  centroid_bwd_prep_kernel<<<n_cols, kThreads, 0, (cudaStream_t)stream_>>>(grad_centroids, sums, ema_scale, (int)channels,
+                                                                           gc, mu_dot_gc);
+  CenBwdArgs a{};
+  a.s.feat = feat;
+  a.s.batch = batch; a.s.channels = channels; a.s.pixels = pixels;
+  a.s.sb = channels * pixels; a.s.sc = pixels; a.s.sp = 1;
+  a.s.mode = labels ? kHard : kSoft;
+  a.s.labels = labels; a.s.probs = probs; a.s.weighted = weighted; a.s.threshold = threshold;
+  a.s.part_id = part_id; a.s.n_part = n_partitions; a.s.n_class = n_class;
+  a.s.n_cols = n_partitions * n_class;
+  a.gc = gc; a.mu_dot_gc = mu_dot_gc; a.dfeat = dfeat; a.dprobs = dprobs;
+  const int kwt = pick_kwt(a.s.n_cols);
+  const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id, dfeat, dprobs});
+  const int vec = vec4 ? 4 : 1;
+  const size_t smem = (size_t)channels * ((kwt + 3) / 4 * 4) * sizeof(float);
+  if (smem > 200 * 1024) return SLCL_ERR_UNSUPPORTED;
+  const int blocks = (int)ceil_div<int64_t>(batch * pixels / vec, kThreads);
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define SLCL_CB(KW_)                                                                                          \
+  case KW_: {                                                                                                 \
+    auto launch = [&](auto kern) -> int {                                                                     \
+      if (smem > 48 * 1024) {                                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute"); return SLCL_ERR_CUDA; }            \
+      }                                                                                                       \
+      kern<<<blocks, kThreads, smem, stream>>>(a);                                                            \
+      return SLCL_OK;                                                                                         \
+    };                                                                                                        \
+    int st;                                                                                                   \
+    if (dprobs) st = vec4 ? launch(centroid_bwd_kernel<KW_, 4, true>) : launch(centroid_bwd_kernel<KW_, 1, true>);    \
+    else st = vec4 ? launch(centroid_bwd_kernel<KW_, 4, false>) : launch(centroid_bwd_kernel<KW_, 1, false>);         \
+    if (st != SLCL_OK) return st;                                                                             \
+  } break;
+  switch (kwt) {
+    SLCL_CB(2) SLCL_CB(3) SLCL_CB(4) SLCL_CB(5) SLCL_CB(6) SLCL_CB(8) SLCL_CB(10) SLCL_CB(12) SLCL_CB(16)
+    default: return SLCL_ERR_INVALID_ARGUMENT;
+  }
+#undef SLCL_CB
+  return check_launch("slcl_centroid_bwd");
+}

@@ -1,0 +1,49 @@
+// common.cuh -- shared device/host helpers for libslcl (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "slcl.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libslcl is written for sm_100a (B200) only"
+#endif
+
+namespace slcl {
+
+constexpr int kMaxK = SLCL_MAX_CLASSES;
+constexpr int kNumSMsDefault = 148;
+
+// thread-local text of the last CUDA launch error (slcl_last_cuda_error()).
+void set_cuda_error(cudaError_t e, const char* where);
+int  check_launch(const char* where);     // returns SLCL_OK or SLCL_ERR_CUDA
+int  sm_count();                          // cached cudaDevAttrMultiProcessorCount of the current device
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Streaming (read-once / write-once) global accesses: evict-first so a 1 GB
+// feature map does not wash the small reused state (centres, stash) out of L2.
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float  ld_stream1(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st_stream1(float* p, float v) { __stcs(p, v); }
+
+template <typename T>
+__host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace slcl

@@ -1,0 +1,619 @@
+// proto.cu -- prototype path: pixel -> class-centre margin InfoNCE (fwd + bwd)
+// and pseudo-label generation, straight from the NCHW feature map.
+//
+// Replaces (reference, file:line):
+//   MPCL.forward              utils/loss.py:484-573
+//   mpcl_loss_calc            utils/loss.py:576-605   (normalise + NCHW->NHWC copy fused away)
+//   generate_pseudo_label     utils/utils_.py:597-624
+// Closed forms: SURVEY.md appendix A.1 / A.2.
+//
+// Roofline: HBM.  One thread owns VEC (=4) consecutive pixels and walks the C
+// channel planes with 128-bit streaming loads (coalesced along HW), keeping the
+// squared norm and the K dot products in registers; the K unit centres sit in
+// shared memory and are read as warp-wide broadcasts.  Forward reads F once
+// (4C B/px) and stashes K+1 backward coefficients per pixel; backward reads F
+// and the stash and writes dF (8C B/px).  Nothing of size [N,C] or [N,K] is
+// materialised besides dF itself.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace slcl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 8;      // channel planes in flight per thread (8 x 16 B)
+
+struct MarginConst {
+  float temperature, scale /* T / T_b */, cos_m, sin_m, th, mm;
+  int easy, normalize;
+};
+
+struct ProtoArgs {
+  const float* feat;
+  int64_t batch, channels, pixels, sb, sc, sp;
+  int64_t n_total;            // batch * pixels
+  const int64_t* labels;
+  const float* soft_mask;
+  const float* sel;
+  const float* cstate;        // [K*C] unit centres, [K] norms
+  float* stash;               // [(K+1) * N]
+  double2* partial;           // per block {sum sel*row, sum sel}
+  int64_t* out_label;         // pseudo-label mode
+  float* out_sel;
+  float sel_threshold;
+  MarginConst mc;
+};
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void load_keep(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+  static __device__ __forceinline__ void store_keep(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = ld_stream1(p); }
+  static __device__ __forceinline__ void load_keep(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { st_stream1(p, v[0]); }
+  static __device__ __forceinline__ void store_keep(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+
+template <int K> constexpr int kpad() { return K <= 4 ? 4 : 8; }
+
+// Unit centres -> shared memory as sC[c][KP] so one or two 128-bit broadcast
+// loads fetch all K values of a channel.
+template <int K>
+__device__ __forceinline__ void load_centres_smem(float* sC, const float* cstate, int C) {
+  constexpr int KP = kpad<K>();
+  for (int idx = threadIdx.x; idx < C * KP; idx += blockDim.x) {
+    int c = idx / KP, k = idx % KP;
+    sC[idx] = (k < K) ? cstate[(int64_t)k * C + c] : 0.f;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void centre_row(const float* sC, int c, float (&ck)[K]) {
+  constexpr int KP = kpad<K>();
+  const float4* row = reinterpret_cast<const float4*>(sC + (size_t)c * KP);
+  float4 a = row[0];
+  float tmp[8];
+  tmp[0] = a.x; tmp[1] = a.y; tmp[2] = a.z; tmp[3] = a.w;
+  if (K > 4) { float4 b = row[1]; tmp[4] = b.x; tmp[5] = b.y; tmp[6] = b.z; tmp[7] = b.w; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) ck[k] = tmp[k];
+}
+
+// Pixel-group addressing shared by every kernel in this file.
+template <int VEC>
+__device__ __forceinline__ bool locate(const ProtoArgs& a, int64_t& pix, int64_t& offset) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t groups_per_image = a.pixels / VEC;
+  if (g >= a.batch * groups_per_image) { pix = 0; offset = 0; return false; }
+  int64_t b = g / groups_per_image;
+  int64_t p = (g - b * groups_per_image) * VEC;
+  pix = b * a.pixels + p;
+  offset = b * a.sb + p * a.sp;
+  return true;
+}
+
+// Accumulate squared norm and K dot products over all channels.
+template <int K, int VEC>
+__device__ __forceinline__ void channel_pass(const float* base, int64_t sc, int C, const float* sC,
+                                             float (&nrm)[VEC], float (&dot)[K][VEC]) {
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    nrm[v] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) dot[k][v] = 0.f;
+  }
+  int c = 0;
+  for (; c + kUnroll <= C; c += kUnroll) {
+    float x[kUnroll][VEC];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) Vec<VEC>::load(base + (int64_t)(c + u) * sc, x[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float ck[K];
+      centre_row<K>(sC, c + u, ck);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        nrm[v] = fmaf(x[u][v], x[u][v], nrm[v]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) dot[k][v] = fmaf(x[u][v], ck[k], dot[k][v]);
+      }
+    }
+  }
+  for (; c < C; ++c) {
+    float x[VEC];
+    Vec<VEC>::load(base + (int64_t)c * sc, x);
+    float ck[K];
+    centre_row<K>(sC, c, ck);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      nrm[v] = fmaf(x[v], x[v], nrm[v]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) dot[k][v] = fmaf(x[v], ck[k], dot[k][v]);
+    }
+  }
+}
+
+// One pixel of MPCL.forward (utils/loss.py:529-571) and its closed-form
+// derivative.  cosv: cosines; M: positive weights (one-hot or
+// soft row); selw: pixel_sel_loc value (1 when absent).  Returns the row loss;
+// coef[k] = selw * dl/dcos_k * inv_n, coef[K] = selw * (sum_k dl/dcos_k cos_k) * inv_n^2.
+template <int K>
+__device__ __forceinline__ float margin_row(const float (&cosv)[K], const float (&M)[K], float selw, float inv_n,
+                                            const MarginConst& mc, float (&coef)[K + 1]) {
+  float plain[K], marg[K], dphi[K];
+  float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float cs = cosv[k];
+    plain[k] = cs / mc.temperature;                                  // :530
+    float u = 1.0f - cs * cs;                                        // :534
+    float sine = sqrtf(fminf(fmaxf(u, 1e-4f), 1.0f));
+    float phi = cs * mc.cos_m - sine * mc.sin_m;                     // :536
+    bool on = mc.easy ? (cs > 0.f) : (cs > mc.th);                   // :538-541
+    float ph = on ? phi : (mc.easy ? cs : cs - mc.mm);
+    marg[k] = ph / mc.temperature;                                   // :543
+    bool unclamped = (u >= 1e-4f) && (u <= 1.0f);
+    dphi[k] = on ? (unclamped ? mc.cos_m + mc.sin_m * cs / sine : mc.cos_m) : 1.0f;
+    m1 = fmaxf(m1, plain[k]);                                        // :531 (detached)
+    m2 = fmaxf(m2, marg[k]);                                         // :545 (detached)
+  }
+  float z[K], ez[K];
+  float s = 0.f, sum_m = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    z[k] = (plain[k] - m1) * (1.0f - M[k]) + (marg[k] - m2) * M[k];  // :550-554
+    ez[k] = expf(z[k]);
+    s += ez[k];
+    sum_m += M[k];
+  }
+  float den = s + 1e-4f;                                             // :556
+  float lse = logf(den);
+  float row = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) row += M[k] * (z[k] - lse);            // :562 / :568
+  float bsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float dz = -mc.scale * (M[k] - sum_m * ez[k] / den);
+    float e = dz * ((1.0f - M[k]) + M[k] * dphi[k]) / mc.temperature;
+    coef[k] = selw * e * inv_n;
+    bsum = fmaf(e, cosv[k], bsum);
+  }
+  coef[K] = mc.normalize ? selw * bsum * inv_n * inv_n : 0.f;
+  return -mc.scale * row;
+}
+
+// ---------------------------------------------------------------------------
+// forward: loss rows + stash
+// ---------------------------------------------------------------------------
+template <int K, int VEC>
+__global__ void __launch_bounds__(kThreads) proto_fwd_kernel(const ProtoArgs a) {
+  extern __shared__ __align__(16) float sC[];
+  __shared__ double red[2][kThreads / 32];
+  const int C = (int)a.channels;
+  load_centres_smem<K>(sC, a.cstate, C);
+  __syncthreads();
+
+  int64_t pix, off;
+  const bool active = locate<VEC>(a, pix, off);
+  double loss_acc = 0.0, sel_acc = 0.0;
+  if (active) {
+    float nrm[VEC], dot[K][VEC];
+    channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot);
+
+    float selv[VEC];
+    if (a.sel != nullptr) Vec<VEC>::load_keep(a.sel + pix, selv);
+    else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) selv[v] = 1.0f;
+    }
+    long long lab[VEC];
+    if (a.labels != nullptr) {
+      if constexpr (VEC == 4) {
+        const longlong2* lp = reinterpret_cast<const longlong2*>(a.labels + pix);
+        longlong2 l0 = lp[0], l1 = lp[1];
+        lab[0] = l0.x; lab[1] = l0.y; lab[2] = l1.x; lab[3] = l1.y;
+      } else {
+        lab[0] = a.labels[pix];
+      }
+    }
+    float out[K + 1][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float n = a.mc.normalize ? fmaxf(sqrtf(nrm[v]), 1e-12f) : 1.0f;   // F.normalize eps (:595)
+      float inv_n = 1.0f / n;
+      float cosv[K], M[K], coef[K + 1];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        cosv[k] = a.mc.normalize ? dot[k][v] / n : dot[k][v];
+        if (a.labels != nullptr) M[k] = (lab[v] == (long long)k) ? 1.0f : 0.0f;      // :513
+        else M[k] = a.soft_mask[(pix + v) * K + k];                                    // :517
+      }
+      float row = margin_row<K>(cosv, M, selv[v], inv_n, a.mc, coef);
+      loss_acc += (double)(selv[v] * row);
+      sel_acc += (double)selv[v];
+#pragma unroll
+      for (int k = 0; k <= K; ++k) out[k][v] = coef[k];
+    }
+#pragma unroll
+    for (int k = 0; k <= K; ++k) Vec<VEC>::store_keep(a.stash + (int64_t)k * a.n_total + pix, out[k]);
+  }
+  // deterministic block partial
+  loss_acc = warp_sum(loss_acc);
+  sel_acc = warp_sum(sel_acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = loss_acc; red[1][warp] = sel_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0, s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { l += red[0][w]; s += red[1][w]; }
+    a.partial[blockIdx.x] = make_double2(l, s);
+  }
+}
+
+// Sums the block partials in index order (deterministic) and writes
+// scal = {loss, coefficient, weight sum, weighted row-loss sum}.
+__global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2* partial, int n_blocks, int64_t n_total,
+                                                                   int has_sel, float* scal) {
+  __shared__ double red[2][kThreads / 32];
+  double l = 0.0, s = 0.0;
+  for (int i = threadIdx.x; i < n_blocks; i += kThreads) { double2 p = partial[i]; l += p.x; s += p.y; }
+  l = warp_sum(l); s = warp_sum(s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = l; red[1][warp] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    l = 0.0; s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { l += red[0][w]; s += red[1][w]; }
+    // with pixel_sel_loc: sum / (sum(sel) + 1e-4) (:565); else mean over N (:571)
+    float coef = has_sel ? 1.0f / ((float)s + 1e-4f) : 1.0f / (float)n_total;
+    scal[0] = (float)l * coef;
+    scal[1] = coef;
+    scal[2] = has_sel ? (float)s : (float)n_total;
+    scal[3] = (float)l;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward: dF = gamma * ( sum_k a_k chat_k - b x )
+// ---------------------------------------------------------------------------
+template <int K, int VEC>
+__global__ void __launch_bounds__(kThreads) proto_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
+                                                             float* dfeat) {
+  extern __shared__ __align__(16) float sC[];
+  const int C = (int)a.channels;
+  load_centres_smem<K>(sC, a.cstate, C);
+  __syncthreads();
+  int64_t pix, off;
+  if (!locate<VEC>(a, pix, off)) return;
+  const float gamma = grad_out[0] * scal[1];
+  float coef[K + 1][VEC];
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+    Vec<VEC>::load(a.stash + (int64_t)k * a.n_total + pix, coef[k]);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) coef[k][v] *= gamma;
+  }
+  const float* src = a.feat + off;
+  float* dst = dfeat + off;
+  int c = 0;
+  for (; c + kUnroll <= C; c += kUnroll) {
+    float x[kUnroll][VEC];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) Vec<VEC>::load(src + (int64_t)(c + u) * a.sc, x[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float ck[K];
+      centre_row<K>(sC, c + u, ck);
+      float o[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float acc = -coef[K][v] * x[u][v];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(coef[k][v], ck[k], acc);
+        o[v] = acc;
+      }
+      Vec<VEC>::store(dst + (int64_t)(c + u) * a.sc, o);
+    }
+  }
+  for (; c < C; ++c) {
+    float x[VEC], ck[K], o[VEC];
+    Vec<VEC>::load(src + (int64_t)c * a.sc, x);
+    centre_row<K>(sC, c, ck);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float acc = -coef[K][v] * x[v];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc = fmaf(coef[k][v], ck[k], acc);
+      o[v] = acc;
+    }
+    Vec<VEC>::store(dst + (int64_t)c * a.sc, o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pseudo labels: argmax_k cos and (top1 - top2 > th)
+// ---------------------------------------------------------------------------
+template <int K, int VEC>
+__global__ void __launch_bounds__(kThreads) pseudo_label_kernel(const ProtoArgs a) {
+  extern __shared__ __align__(16) float sC[];
+  const int C = (int)a.channels;
+  load_centres_smem<K>(sC, a.cstate, C);
+  __syncthreads();
+  int64_t pix, off;
+  if (!locate<VEC>(a, pix, off)) return;
+  float nrm[VEC], dot[K][VEC];
+  channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot);
+  long long lab[VEC];
+  float selv[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float n = fmaxf(sqrtf(nrm[v]), 1e-12f);                      // utils_.py:615
+    float t1 = -INFINITY, t2 = -INFINITY;
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float cs = dot[k][v] / n;
+      if (cs > t1) { t2 = t1; t1 = cs; best = k; }               // strict >: first index wins ties (:621)
+      else if (cs > t2) { t2 = cs; }
+    }
+    lab[v] = best;
+    selv[v] = (t1 - t2 > a.sel_threshold) ? 1.0f : 0.0f;         // :608-609
+  }
+  if constexpr (VEC == 4) {
+    longlong2* lp = reinterpret_cast<longlong2*>(a.out_label + pix);
+    lp[0] = make_longlong2(lab[0], lab[1]);
+    lp[1] = make_longlong2(lab[2], lab[3]);
+  } else {
+    a.out_label[pix] = lab[0];
+  }
+  Vec<VEC>::store_keep(a.out_sel + pix, selv);
+}
+
+// Unit centres + norms: cstate[k*C+c] = c_k[c] / max(||c_k||, 1e-12), cstate[K*C+k] = max(||c_k||, 1e-12).
+__global__ void __launch_bounds__(kThreads) prep_centres_kernel(const float* centres, int C, int K, int normalize,
+                                                                float* cstate) {
+  __shared__ float red[kThreads / 32];
+  __shared__ float s_norm;
+  const int k = blockIdx.x;
+  const float* row = centres + (int64_t)k * C;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < C; c += kThreads) ss = fmaf(row[c], row[c], ss);
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    s_norm = normalize ? fmaxf(sqrtf(t), 1e-12f) : 1.0f;
+    cstate[(int64_t)K * C + k] = s_norm;
+  }
+  __syncthreads();
+  const float n = s_norm;
+  for (int c = threadIdx.x; c < C; c += kThreads) cstate[(int64_t)k * C + c] = row[c] / n;
+}
+
+// dcentre_k = gamma * (G_k - chat_k (chat_k . G_k)) / nu_k   (A.1), G from the class-sum kernel (fp64 [K, C+1]).
+__global__ void __launch_bounds__(kThreads) centre_grad_kernel(const double* sums, const float* cstate, const float* scal,
+                                                               const float* grad_out, int C, int K, int normalize,
+                                                               float* dcentres) {
+  __shared__ double red[kThreads / 32];
+  __shared__ double s_dot;
+  const int k = blockIdx.x;
+  const double* g = sums + (int64_t)k * (C + 1);
+  const float* ch = cstate + (int64_t)k * C;
+  double d = 0.0;
+  for (int c = threadIdx.x; c < C; c += kThreads) d += g[c] * (double)ch[c];
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    s_dot = t;
+  }
+  __syncthreads();
+  const double gamma = (double)grad_out[0] * (double)scal[1];
+  const double nu = (double)cstate[(int64_t)K * C + k];
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    double v = normalize ? (g[c] - (double)ch[c] * s_dot) / nu : g[c];
+    dcentres[(int64_t)k * C + c] = (float)(gamma * v);
+  }
+}
+
+// ------------------------------ host side ----------------------------------
+struct Plan {
+  int vec;
+  int64_t n_total;
+  int n_blocks;
+  size_t smem;
+};
+
+bool validate_map(const slcl_map_t* m) {
+  return m && m->batch > 0 && m->channels > 0 && m->pixels > 0 && m->stride_c >= 0 && m->stride_p >= 0;
+}
+
+Plan make_plan(const slcl_map_t* m, int K, std::initializer_list<const void*> ptrs16) {
+  Plan p;
+  p.n_total = m->batch * m->pixels;
+  bool vec4 = (m->stride_p == 1) && (m->pixels % 4 == 0) && (m->stride_c % 4 == 0) && (m->stride_b % 4 == 0);
+  for (const void* q : ptrs16) vec4 = vec4 && (q == nullptr || aligned16(q));
+  p.vec = vec4 ? 4 : 1;
+  p.n_blocks = (int)ceil_div<int64_t>(p.n_total / p.vec, kThreads);
+  p.smem = (size_t)m->channels * (K <= 4 ? 4 : 8) * sizeof(float);
+  return p;
+}
+
+ProtoArgs base_args(const float* feat, const slcl_map_t* m, const float* cstate) {
+  ProtoArgs a{};
+  a.feat = feat;
+  a.batch = m->batch; a.channels = m->channels; a.pixels = m->pixels;
+  a.sb = m->stride_b; a.sc = m->stride_c; a.sp = m->stride_p;
+  a.n_total = m->batch * m->pixels;
+  a.cstate = cstate;
+  return a;
+}
+
+MarginConst make_const(const slcl_proto_params_t* p) {
+  MarginConst mc;
+  mc.temperature = p->temperature;
+  mc.scale = p->temperature / p->base_temperature;
+  mc.cos_m = (float)cos((double)p->margin);
+  mc.sin_m = (float)sin((double)p->margin);
+  mc.th = (float)cos(M_PI - (double)p->margin);
+  mc.mm = (float)(sin(M_PI - (double)p->margin) * (double)p->margin);
+  mc.easy = p->easy_margin;
+  mc.normalize = p->normalize;
+  return mc;
+}
+
+template <typename Kern>
+int ensure_smem(Kern kern, size_t smem) {
+  if (smem > 200 * 1024) return SLCL_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute"); return SLCL_ERR_CUDA; }
+  }
+  return SLCL_OK;
+}
+
+#define SLCL_DISPATCH_K(K_, VEC_, ...)                                           \
+  switch (K_) {                                                                  \
+    case 2: { constexpr int KK = 2; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 3: { constexpr int KK = 3; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 4: { constexpr int KK = 4; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 5: { constexpr int KK = 5; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 6: { constexpr int KK = 6; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 7: { constexpr int KK = 7; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    case 8: { constexpr int KK = 8; if (VEC_ == 4) { constexpr int VV = 4; __VA_ARGS__ } else { constexpr int VV = 1; __VA_ARGS__ } } break; \
+    default: return SLCL_ERR_INVALID_ARGUMENT;                                   \
+  }
+
+}  // namespace
+}  // namespace slcl
+
+using namespace slcl;
+
+extern "C" size_t slcl_proto_workspace_bytes(int64_t n_pixels) {
+  if (n_pixels <= 0) return 0;
+  return (size_t)ceil_div<int64_t>(n_pixels, kThreads) * sizeof(double2) + 256;
+}
+
+extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
+                              const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
+                              float* cstate, float* scal, void* workspace, size_t workspace_bytes,
+                              slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !centres || !params || !stash || !cstate || !scal || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if ((labels == nullptr) == (soft_mask == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;   // exactly one (:502-505)
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f))
+    return SLCL_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan plan = make_plan(map, K, {feat, labels, sel, stash});
+  if (workspace_bytes < slcl_proto_workspace_bytes(plan.n_total)) return SLCL_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return SLCL_ERR_INVALID_ARGUMENT;
+
+  ProtoArgs a = base_args(feat, map, cstate);
+  a.labels = labels; a.soft_mask = soft_mask; a.sel = sel; a.stash = stash;
+  a.partial = reinterpret_cast<double2*>(workspace);
+  a.mc = make_const(params);
+
+  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, params->normalize, cstate);
+  SLCL_DISPATCH_K(K, plan.vec, {
+    int st = ensure_smem(proto_fwd_kernel<KK, VV>, plan.smem);
+    if (st != SLCL_OK) return st;
+    proto_fwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a);
+  })
+  proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, sel != nullptr, scal);
+  return check_launch("slcl_proto_fwd");
+}
+
+extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,
+                              const float* scal, const float* grad_out, const slcl_proto_params_t* params,
+                              float* dfeat, slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !stash || !cstate || !scal || !grad_out || !params || !dfeat)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan plan = make_plan(map, K, {feat, stash, dfeat});
+  ProtoArgs a = base_args(feat, map, cstate);
+  a.stash = const_cast<float*>(stash);
+  a.mc = make_const(params);
+  SLCL_DISPATCH_K(K, plan.vec, {
+    int st = ensure_smem(proto_bwd_kernel<KK, VV>, plan.smem);
+    if (st != SLCL_OK) return st;
+    proto_bwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a, scal, grad_out, dfeat);
+  })
+  return check_launch("slcl_proto_bwd");
+}
+
+extern "C" int slcl_pseudo_label(const float* feat, const slcl_map_t* map, const float* centres, int n_class,
+                                 float threshold, int64_t* label, float* sel, void* workspace, size_t workspace_bytes,
+                                 slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !centres || !label || !sel || !workspace) return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = n_class;
+  if (K < 2 || K > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
+  // workspace holds the unit centres [K*C + K]
+  if (workspace_bytes < ((size_t)K * map->channels + K) * sizeof(float)) return SLCL_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* cstate = reinterpret_cast<float*>(workspace);
+  Plan plan = make_plan(map, K, {feat, label, sel});
+  ProtoArgs a = base_args(feat, map, cstate);
+  a.out_label = label; a.out_sel = sel; a.sel_threshold = threshold;
+  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, 1, cstate);
+  SLCL_DISPATCH_K(K, plan.vec, {
+    int st = ensure_smem(pseudo_label_kernel<KK, VV>, plan.smem);
+    if (st != SLCL_OK) return st;
+    pseudo_label_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a);
+  })
+  return check_launch("slcl_pseudo_label");
+}
+
+// Weighted sums G_k = sum_i a_ik x_i come from the class-sum kernel (class_sums.cu).
+namespace slcl {
+int class_sums_planar_weights(const float* feat, const slcl_map_t* map, const float* weights, int n_cols,
+                              double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t class_sums_ws_bytes(int64_t batch, int64_t channels, int64_t pixels, int n_cols);
+}
+
+extern "C" size_t slcl_proto_bwd_centres_workspace_bytes(int64_t n_pixels, int64_t channels, int n_class) {
+  if (n_pixels <= 0 || channels <= 0 || n_class <= 0) return 0;
+  size_t sums = align_up((size_t)n_class * (channels + 1) * sizeof(double), 256);
+  return sums + class_sums_ws_bytes(1, channels, n_pixels, n_class);
+}
+
+extern "C" int slcl_proto_bwd_centres(const float* feat, const slcl_map_t* map, const float* stash,
+                                      const float* cstate, const float* scal, const float* grad_out,
+                                      const slcl_proto_params_t* params, float* dcentres, void* workspace,
+                                      size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !stash || !cstate || !scal || !grad_out || !params || !dcentres || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
+  const int64_t n = map->batch * map->pixels;
+  if (workspace_bytes < slcl_proto_bwd_centres_workspace_bytes(n, map->channels, K)) return SLCL_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  double* sums = reinterpret_cast<double*>(workspace);
+  size_t off = align_up((size_t)K * (map->channels + 1) * sizeof(double), 256);
+  int st = class_sums_planar_weights(feat, map, stash, K, sums, (char*)workspace + off, workspace_bytes - off, stream);
+  if (st != SLCL_OK) return st;
+  centre_grad_kernel<<<K, kThreads, 0, stream>>>(sums, cstate, scal, grad_out, (int)map->channels, K,
+                                                  params->normalize, dcentres);
+  return check_launch("slcl_proto_bwd_centres");
+}

@@ -1,0 +1,120 @@
+"""Autograd wiring of the slcl custom ops (fused forward + closed-form backward).
+
+Formulas: SURVEY.md appendix A; reference functions cited per class.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops  # noqa: F401  (registers torch.ops.slcl.*)
+
+_ops = torch.ops.slcl
+
+
+class _ProtoLoss(torch.autograd.Function):
+    """MPCL.forward (+ the normalise/layout work of mpcl_loss_calc): reference
+    utils/loss.py:484-573, :592-601.  Backward: appendix A.1."""
+
+    @staticmethod
+    def forward(ctx, feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature, margin,
+                easy_margin, normalize):
+        scal, stash, cstate = _ops.proto_fwd(feat.detach(), labels, None if soft_mask is None else soft_mask.detach(),
+                                             None if sel is None else sel.detach(), centres.detach(), rows_layout,
+                                             n_class, temperature, base_temperature, margin, easy_margin, normalize)
+        ctx.save_for_backward(feat, stash, cstate, scal)
+        ctx.cfg = (rows_layout, n_class, normalize)
+        ctx.soft = soft_mask is not None and soft_mask.requires_grad
+        ctx.sel_grad = sel is not None and sel.requires_grad
+        return scal[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat, stash, cstate, scal = ctx.saved_tensors
+        rows_layout, n_class, normalize = ctx.cfg
+        if ctx.soft or ctx.sel_grad:
+            raise NotImplementedError("slcl MPCL: gradients w.r.t. `mask` / `pixel_sel_loc` are not provided "
+                                      "(both reference callers pass constants)")
+        g = grad_out.reshape(1)
+        dfeat = dcen = None
+        if ctx.needs_input_grad[0]:
+            dfeat = _ops.proto_bwd(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
+        if ctx.needs_input_grad[4]:
+            dcen = _ops.proto_bwd_centres(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
+        return dfeat, None, None, None, dcen, None, None, None, None, None, None, None
+
+
+def proto_loss(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor], centres: Tensor,
+               *, rows_layout: bool, n_class: int, temperature: float, base_temperature: float, margin: float,
+               easy_margin: bool, normalize: bool) -> Tensor:
+    return _ProtoLoss.apply(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature,
+                            margin, easy_margin, normalize)
+
+
+class _Centroids(torch.autograd.Function):
+    """cal_centroid (reference utils/utils_.py:479-565, repaired; partitions per
+    SURVEY.md 8(c)-2).  Forward = class sums (+ optional cross-rank all-reduce)
+    + finalise; backward = appendix A.4."""
+
+    @staticmethod
+    def forward(ctx, feat, labels, probs, previous, weighted, threshold, part_id, n_partitions, n_class, momentum, group):
+        sums = _ops.class_sums(feat.detach(), labels, None if probs is None else probs.detach(), weighted, threshold,
+                               part_id, n_partitions, n_class)
+        if group is not None:
+            from .distributed import all_reduce_sums
+            sums = all_reduce_sums(sums, group)
+        prev = None if previous is None else previous.detach()
+        cen, _inv_w = _ops.centroid_finalize(sums, prev, momentum, n_partitions, n_class)
+        ctx.save_for_backward(feat, labels, probs, part_id, sums)
+        ctx.cfg = (weighted, threshold, n_partitions, n_class, momentum, previous is not None)
+        return cen
+
+    @staticmethod
+    def backward(ctx, grad_cen):
+        feat, labels, probs, part_id, sums = ctx.saved_tensors
+        weighted, threshold, n_partitions, n_class, momentum, has_prev = ctx.cfg
+        ema_scale = (1.0 - momentum) if has_prev else 1.0
+        dfeat = dprobs = dprev = None
+        need_dp = probs is not None and ctx.needs_input_grad[2] and weighted
+        if ctx.needs_input_grad[0] or need_dp:
+            dfeat, dp = _ops.centroid_bwd(feat.detach(), labels, None if probs is None else probs.detach(), weighted,
+                                          threshold, part_id, n_partitions, n_class, grad_cen.contiguous(), sums,
+                                          ema_scale, need_dp)
+            if need_dp:
+                dprobs = dp
+            if not ctx.needs_input_grad[0]:
+                dfeat = None
+        if has_prev and ctx.needs_input_grad[3]:
+            dprev = momentum * grad_cen.reshape(n_partitions, n_class, -1).sum(0)
+        return dfeat, None, dprobs, dprev, None, None, None, None, None, None, None
+
+
+def centroids(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], previous: Optional[Tensor], *,
+              weighted: bool, threshold: float, part_id: Optional[Tensor], n_partitions: int, n_class: int,
+              momentum: float, group=None) -> Tensor:
+    """-> [P*K, C] centroids (EMA'd with `previous` when given)."""
+    return _Centroids.apply(feat, labels, probs, previous, weighted, threshold, part_id, n_partitions, n_class, momentum,
+                            group)
+
+
+class _CentroidLoss(torch.autograd.Function):
+    """ContrastiveLoss.forward (utils/loss.py:241-275) / CNR (Trainer_MCCL.py:303-315):
+    one launch yields the loss and both gradients (appendix A.5)."""
+
+    @staticmethod
+    def forward(ctx, cs, ct, mode, first_row, n_rows, norm):
+        loss, ds, dt = _ops.centroid_loss(cs.detach(), ct.detach(), mode, first_row, n_rows, norm)
+        ctx.save_for_backward(ds, dt)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ds, dt = ctx.saved_tensors
+        return (grad_out * ds if ctx.needs_input_grad[0] else None,
+                grad_out * dt if ctx.needs_input_grad[1] else None, None, None, None, None)
+
+
+def centroid_loss(cs: Tensor, ct: Tensor, *, mode: int, first_row: int, n_rows: int, norm: bool) -> Tensor:
+    return _CentroidLoss.apply(cs, ct, mode, first_row, n_rows, norm)

@@ -1,0 +1,123 @@
+"""Drop-in for the contrastive-loss part of the reference's ``utils/loss.py``.
+
+Same class / function names, argument meaning and error behaviour as the
+reference (file:line cited per item); the arithmetic runs in libslcl.so.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as SF
+from . import p2p
+
+
+class MPCL(nn.Module):
+    """Pixel -> prototype margin InfoNCE.  Reference: utils/loss.py:469-573."""
+
+    def __init__(self, device, num_class=5, temperature=0.07, m=0.5, base_temperature=0.07, easy_margin=False):
+        super().__init__()
+        self.num_class = num_class
+        self.temperature = temperature
+        self.base_temperature = base_temperature
+        self.m = m
+        self.cos_m = math.cos(m)
+        self.sin_m = math.sin(m)
+        self.th = math.cos(math.pi - m)
+        self.mm = math.sin(math.pi - m) * m
+        self.device = device
+        self.easy_margin = easy_margin
+
+    def _kw(self, normalize):
+        return dict(n_class=self.num_class, temperature=self.temperature, base_temperature=self.base_temperature,
+                    margin=self.m, easy_margin=self.easy_margin, normalize=normalize)
+
+    def forward(self, features, labels, class_center_feas, pixel_sel_loc=None, mask=None):
+        """features [N,1,C] unit rows; labels [N]; class_center_feas [C,K] unit
+        columns; pixel_sel_loc [N]; mask [N,K] soft positives (utils/loss.py:484-573)."""
+        if len(features.shape) < 3:                                     # :494-496
+            raise ValueError('`features` needs to be [bsz, n_views, ...],'
+                             'at least 3 dimensions are required')
+        if len(features.shape) > 3:
+            features = features.view(features.shape[0], features.shape[1], -1)
+        if labels is not None and mask is not None:                     # :502-503
+            raise ValueError('Cannot define both `labels` and `mask`')
+        if features.shape[1] != 1:
+            raise NotImplementedError("slcl MPCL supports n_views == 1 (the only use in the reference trainers)")
+        n = features.shape[0]
+        if labels is None and mask is None:                             # :504-505  (eye(N) positives)
+            if n != self.num_class:
+                raise ValueError("labels=None and mask=None needs N == num_class (identity positive mask)")
+            mask = torch.eye(n, dtype=torch.float32, device=features.device)
+        if labels is not None:
+            labels = labels.contiguous().view(-1).long()
+            if labels.shape[0] != n:                                    # :511-512
+                raise ValueError('Num of labels does not match num of features')
+        else:
+            mask = mask.float()
+        rows = features[:, 0, :]
+        centres = class_center_feas.transpose(0, 1)                     # [K, C]
+        sel = None if pixel_sel_loc is None else pixel_sel_loc.view(-1)
+        return SF.proto_loss(rows, labels, mask, sel, centres, rows_layout=True, **self._kw(normalize=False))
+
+
+def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=None, tag='source'):
+    """feas [B,C,h,w]; labels [B,H,W] (source) or [N] (target); class_center_feas
+    [K,C]; loss_func an ``MPCL``.  Reference: utils/loss.py:576-605.  With an slcl
+    ``MPCL`` the normalisation, the NCHW->NHWC copy and the loss are one fused
+    kernel over the NCHW map; any other callable gets the reference call
+    sequence."""
+    n, c, fea_h, fea_w = feas.size()
+    if tag == 'source' and (labels.size()[1] != fea_h or labels.size()[2] != fea_w):     # :585-590
+        labels = labels.float()
+        labels = F.interpolate(labels, size=fea_w, mode='nearest')
+        labels = labels.permute(0, 2, 1).contiguous()
+        labels = F.interpolate(labels, size=fea_h, mode='nearest')
+        labels = labels.permute(0, 2, 1).contiguous()
+    labels = labels.to(feas.device).reshape(-1).long()                                   # :592-593
+    if isinstance(loss_func, MPCL):
+        if labels.shape[0] != n * fea_h * fea_w:
+            raise ValueError('Num of labels does not match num of features')
+        sel = None if pixel_sel_loc is None else pixel_sel_loc.view(-1)
+        return SF.proto_loss(feas, labels, None, sel, class_center_feas, rows_layout=False,
+                             **loss_func._kw(normalize=True))
+    unit = F.normalize(feas, p=2, dim=1).permute(0, 2, 3, 1).reshape(n * fea_h * fea_w, c).unsqueeze(1)
+    centres = F.normalize(class_center_feas, p=2, dim=1).transpose(0, 1)
+    return loss_func(unit, labels, centres, pixel_sel_loc=pixel_sel_loc)
+
+
+class ContrastiveLoss(nn.Module):
+    """Centroid <-> centroid InfoNCE.  Reference: utils/loss.py:233-275.
+    Bug-compatible: ``tau`` is stored and never used (:236 vs :264-265); the row
+    range ends at the reference's hard-coded 4 (:266) when K == 4 and at K otherwise
+    (the reference raises a shape error for K != 4)."""
+
+    def __init__(self, tau=5, n_class=4, bg=False, norm=True):
+        super().__init__()
+        self._tau = tau
+        self._norm = norm
+
+    def forward(self, centroid_s, centroid_t, bg=False, split=False):
+        k = centroid_s.shape[0]
+        return SF.centroid_loss(centroid_s, centroid_t, mode=1 if split else 0, first_row=0 if bg else 1, n_rows=k,
+                                norm=bool(self._norm))
+
+
+def cnr_loss(centroid_s, centroid_t_list):
+    """Centroid-norm regulariser written inline in the reference trainer
+    (trainer/Trainer_MCCL.py:303-315): sum_p MSE(||t_p||, ||s||) / P."""
+    if isinstance(centroid_t_list, torch.Tensor):
+        centroid_t_list = [centroid_t_list]
+    total = 0
+    for ct in centroid_t_list:
+        total = total + SF.centroid_loss(centroid_s, ct, mode=2, first_row=0, n_rows=centroid_s.shape[0], norm=False) \
+            / len(centroid_t_list)
+    return total
+
+
+SupConLoss = p2p.SupConLoss
+LocalConLoss = p2p.LocalConLoss
+BlockConLoss = p2p.BlockConLoss

@@ -1,0 +1,398 @@
+"""torch custom ops (``torch.ops.slcl.*``) over the C ABI of libslcl.so.
+
+Each op allocates its outputs and workspace with torch (caching allocator),
+then makes ONE call into the C ABI on the current CUDA stream.  The ops carry
+no autograd formulas; the autograd wiring lives in ``slcl.functional``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import MapT, ProtoParamsT, check, ptr, require_cuda, stream_ptr
+
+_F32 = torch.float32
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _map_nchw(feat: Tensor) -> Tuple[Tensor, MapT]:
+    """[B,C,H,W] -> (tensor actually read, strided map).  H and W must collapse
+    into one pixel stride; anything else is made contiguous first."""
+    if feat.dim() != 4:
+        raise ValueError("feature map must be [B, C, H, W]")
+    b, c, h, w = feat.shape
+    sb, sc, sh, sw = feat.stride()
+    if feat.dtype != _F32:
+        raise ValueError("slcl kernels compute in fp32; pass a float32 feature map")
+    if sw != 1 or (h > 1 and sh != w) or sc < h * w or (b > 1 and sb < c * h * w):
+        feat = feat.contiguous()
+        sb, sc = c * h * w, h * w
+    return feat, MapT(b, c, h * w, sb, sc, 1)
+
+
+def _map_rows(rows: Tensor) -> Tuple[Tensor, MapT]:
+    """[N,C] row-major rows (the layout MPCL.forward receives) as a map with B=1."""
+    if rows.dim() != 2:
+        raise ValueError("rows must be [N, C]")
+    if rows.dtype != _F32:
+        raise ValueError("slcl kernels compute in fp32; pass float32 rows")
+    rows = rows.contiguous()
+    n, c = rows.shape
+    return rows, MapT(1, c, n, 0, 1, c)
+
+
+def _params(n_class: int, temperature: float, base_temperature: float, margin: float, easy_margin: bool,
+            normalize: bool) -> ProtoParamsT:
+    return ProtoParamsT(int(n_class), float(temperature), float(base_temperature), float(margin),
+                        int(bool(easy_margin)), int(bool(normalize)))
+
+
+def _feat_map(feat: Tensor, rows_layout: bool):
+    return _map_rows(feat) if rows_layout else _map_nchw(feat)
+
+
+# ----------------------------------------------------------------------------
+# prototype path
+# ----------------------------------------------------------------------------
+@torch.library.custom_op("slcl::proto_fwd", mutates_args=(), device_types="cuda")
+def proto_fwd(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor],
+              centres: Tensor, rows_layout: bool, n_class: int, temperature: float, base_temperature: float,
+              margin: float, easy_margin: bool, normalize: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (scal[4] = {loss, coef, weight sum, row-loss sum}, stash[(K+1), N], cstate[K*C+K])"""
+    dev = require_cuda(feat, labels, soft_mask, sel, centres)
+    lib = _lib.load()
+    feat_c, m = _feat_map(feat, rows_layout)
+    n = m.batch * m.pixels
+    if labels is not None:
+        labels = labels.contiguous()
+        if labels.dtype != torch.int64:
+            raise ValueError("labels must be int64")
+    if soft_mask is not None:
+        soft_mask = soft_mask.to(_F32).contiguous()
+    if sel is not None:
+        sel = sel.to(_F32).contiguous()
+    centres = centres.to(_F32).contiguous()
+    scal = torch.empty(4, dtype=_F32, device=dev)
+    stash = torch.empty((n_class + 1, n), dtype=_F32, device=dev)
+    cstate = torch.empty(n_class * m.channels + n_class, dtype=_F32, device=dev)
+    nbytes = lib.slcl_proto_workspace_bytes(n)
+    ws = _ws(nbytes, dev)
+    p = _params(n_class, temperature, base_temperature, margin, easy_margin, normalize)
+    with torch.cuda.device(dev):
+        st = lib.slcl_proto_fwd(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(centres), C.byref(p),
+                                ptr(stash), ptr(cstate), ptr(scal), ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_proto_fwd")
+    return scal, stash, cstate
+
+
+@proto_fwd.register_fake
+def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature, margin, easy_margin,
+      normalize):
+    n = feat.shape[0] if rows_layout else feat.shape[0] * feat.shape[2] * feat.shape[3]
+    c = feat.shape[1]
+    return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class))
+
+
+@torch.library.custom_op("slcl::proto_bwd", mutates_args=(), device_types="cuda")
+def proto_bwd(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_out: Tensor, rows_layout: bool,
+              n_class: int, normalize: bool) -> Tensor:
+    dev = require_cuda(feat, stash, cstate, scal, grad_out)
+    lib = _lib.load()
+    feat_c, m = _feat_map(feat, rows_layout)
+    dfeat = torch.empty_strided(feat_c.shape, feat_c.stride(), dtype=_F32, device=dev)
+    grad_out = grad_out.to(_F32).contiguous()
+    p = _params(n_class, 1.0, 1.0, 0.0, False, normalize)
+    with torch.cuda.device(dev):
+        st = lib.slcl_proto_bwd(ptr(feat_c), C.byref(m), ptr(stash), ptr(cstate), ptr(scal), ptr(grad_out), C.byref(p),
+                                ptr(dfeat), stream_ptr(dev))
+    check(st, "slcl_proto_bwd")
+    return dfeat
+
+
+@proto_bwd.register_fake
+def _(feat, stash, cstate, scal, grad_out, rows_layout, n_class, normalize):
+    return torch.empty_like(feat)
+
+
+@torch.library.custom_op("slcl::proto_bwd_centres", mutates_args=(), device_types="cuda")
+def proto_bwd_centres(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_out: Tensor, rows_layout: bool,
+                      n_class: int, normalize: bool) -> Tensor:
+    dev = require_cuda(feat, stash, cstate, scal, grad_out)
+    lib = _lib.load()
+    feat_c, m = _feat_map(feat, rows_layout)
+    dcen = torch.empty((n_class, m.channels), dtype=_F32, device=dev)
+    grad_out = grad_out.to(_F32).contiguous()
+    ws = _ws(lib.slcl_proto_bwd_centres_workspace_bytes(m.batch * m.pixels, m.channels, n_class), dev)
+    p = _params(n_class, 1.0, 1.0, 0.0, False, normalize)
+    with torch.cuda.device(dev):
+        st = lib.slcl_proto_bwd_centres(ptr(feat_c), C.byref(m), ptr(stash), ptr(cstate), ptr(scal), ptr(grad_out),
+                                        C.byref(p), ptr(dcen), ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_proto_bwd_centres")
+    return dcen
+
+
+@proto_bwd_centres.register_fake
+def _(feat, stash, cstate, scal, grad_out, rows_layout, n_class, normalize):
+    return feat.new_empty((n_class, feat.shape[1]))
+
+
+@torch.library.custom_op("slcl::pseudo_label", mutates_args=(), device_types="cuda")
+def pseudo_label(feat: Tensor, centres: Tensor, threshold: float) -> Tuple[Tensor, Tensor]:
+    dev = require_cuda(feat, centres)
+    lib = _lib.load()
+    feat_c, m = _map_nchw(feat)
+    centres = centres.to(_F32).contiguous()
+    k = centres.shape[0]
+    n = m.batch * m.pixels
+    label = torch.empty(n, dtype=torch.int64, device=dev)
+    sel = torch.empty(n, dtype=_F32, device=dev)
+    ws = _ws((k * m.channels + k) * 4, dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_pseudo_label(ptr(feat_c), C.byref(m), ptr(centres), k, float(threshold), ptr(label), ptr(sel),
+                                   ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_pseudo_label")
+    return label, sel
+
+
+@pseudo_label.register_fake
+def _(feat, centres, threshold):
+    n = feat.shape[0] * feat.shape[2] * feat.shape[3]
+    return (torch.empty(n, dtype=torch.int64, device=feat.device), feat.new_empty(n))
+
+
+# ----------------------------------------------------------------------------
+# class sums / centroids
+# ----------------------------------------------------------------------------
+def _nchw_contig(feat: Tensor) -> Tensor:
+    if feat.dim() != 4 or feat.dtype != _F32:
+        raise ValueError("feature map must be float32 [B, C, H, W]")
+    return feat.contiguous()
+
+
+@torch.library.custom_op("slcl::class_sums", mutates_args=(), device_types="cuda")
+def class_sums(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], weighted: bool, threshold: float,
+               part_id: Optional[Tensor], n_partitions: int, n_class: int) -> Tensor:
+    """-> sums [P*K, C+1] float64 (weighted feature sums | weight sums)."""
+    dev = require_cuda(feat, labels, probs, part_id)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    if labels is not None:
+        labels = labels.contiguous()
+        if labels.dtype != torch.int64 or labels.numel() != b * h * w:
+            raise ValueError("labels must be int64 with B*H*W elements")
+    if probs is not None:
+        probs = probs.to(_F32).contiguous()
+        if probs.shape != (b, n_class, h, w):
+            raise ValueError("probs must be [B, K, H, W] at feature resolution")
+    if part_id is not None:
+        part_id = part_id.contiguous()
+        if part_id.dtype != torch.int32 or part_id.numel() != b * h * w:
+            raise ValueError("part_id must be int32 with B*H*W elements")
+    cols = n_partitions * n_class
+    sums = torch.empty((cols, c + 1), dtype=torch.float64, device=dev)
+    ws = _ws(lib.slcl_class_sums_workspace_bytes(b, c, h * w, cols), dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_class_sums(ptr(feat), b, c, h * w, ptr(labels), ptr(probs), int(weighted), float(threshold),
+                                 ptr(part_id), n_partitions, n_class, ptr(sums), ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_class_sums")
+    return sums
+
+
+@class_sums.register_fake
+def _(feat, labels, probs, weighted, threshold, part_id, n_partitions, n_class):
+    return torch.empty((n_partitions * n_class, feat.shape[1] + 1), dtype=torch.float64, device=feat.device)
+
+
+@torch.library.custom_op("slcl::ema_finalize", mutates_args=(), device_types="cuda")
+def ema_finalize(sums: Tensor, old_centres: Tensor, m: float) -> Tensor:
+    dev = require_cuda(sums, old_centres)
+    lib = _lib.load()
+    old = old_centres.to(_F32).contiguous()
+    k, c = old.shape
+    if sums.dtype != torch.float64 or sums.shape != (k, c + 1):
+        raise ValueError("sums must be float64 [K, C+1]")
+    out = torch.empty_like(old)
+    with torch.cuda.device(dev):
+        st = lib.slcl_ema_finalize(ptr(sums.contiguous()), ptr(old), float(m), k, c, ptr(out), stream_ptr(dev))
+    check(st, "slcl_ema_finalize")
+    return out
+
+
+@ema_finalize.register_fake
+def _(sums, old_centres, m):
+    return torch.empty_like(old_centres)
+
+
+@torch.library.custom_op("slcl::centroid_finalize", mutates_args=(), device_types="cuda")
+def centroid_finalize(sums: Tensor, previous: Optional[Tensor], momentum: float, n_sets: int,
+                      n_class: int) -> Tuple[Tensor, Tensor]:
+    dev = require_cuda(sums, previous)
+    lib = _lib.load()
+    sums = sums.contiguous()
+    rows, c1 = sums.shape
+    c = c1 - 1
+    if sums.dtype != torch.float64 or rows != n_sets * n_class:
+        raise ValueError("sums must be float64 [sets*K, C+1]")
+    if previous is not None:
+        previous = previous.to(_F32).contiguous()
+        if previous.shape != (n_class, c):
+            raise ValueError("previous centroid must be [K, C]")
+    cen = torch.empty((rows, c), dtype=_F32, device=dev)
+    inv_w = torch.empty(rows, dtype=_F32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_centroid_finalize(ptr(sums), ptr(previous), float(momentum), n_sets, n_class, c, ptr(cen),
+                                        ptr(inv_w), stream_ptr(dev))
+    check(st, "slcl_centroid_finalize")
+    return cen, inv_w
+
+
+@centroid_finalize.register_fake
+def _(sums, previous, momentum, n_sets, n_class):
+    return (torch.empty((sums.shape[0], sums.shape[1] - 1), dtype=_F32, device=sums.device),
+            torch.empty(sums.shape[0], dtype=_F32, device=sums.device))
+
+
+@torch.library.custom_op("slcl::centroid_bwd", mutates_args=(), device_types="cuda")
+def centroid_bwd(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], weighted: bool, threshold: float,
+                 part_id: Optional[Tensor], n_partitions: int, n_class: int, grad_centroids: Tensor, sums: Tensor,
+                 ema_scale: float, need_dprobs: bool) -> Tuple[Tensor, Tensor]:
+    dev = require_cuda(feat, labels, probs, part_id, grad_centroids, sums)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    if labels is not None:
+        labels = labels.contiguous()
+    if probs is not None:
+        probs = probs.to(_F32).contiguous()
+    if part_id is not None:
+        part_id = part_id.contiguous()
+    cols = n_partitions * n_class
+    g = grad_centroids.to(_F32).contiguous()
+    if g.shape != (cols, c):
+        raise ValueError("grad_centroids must be [P*K, C]")
+    dfeat = torch.empty_like(feat)
+    dprobs = torch.empty_like(probs) if (need_dprobs and probs is not None) else torch.empty(0, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_centroid_bwd_workspace_bytes(c, cols), dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_centroid_bwd(ptr(feat), b, c, h * w, ptr(labels), ptr(probs), int(weighted), float(threshold),
+                                   ptr(part_id), n_partitions, n_class, ptr(g), ptr(sums.contiguous()), float(ema_scale),
+                                   ptr(dfeat), ptr(dprobs) if dprobs.numel() else None, ptr(ws), ws.numel(),
+                                   stream_ptr(dev))
+    check(st, "slcl_centroid_bwd")
+    return dfeat, dprobs
+
+
+@centroid_bwd.register_fake
+def _(feat, labels, probs, weighted, threshold, part_id, n_partitions, n_class, grad_centroids, sums, ema_scale,
+      need_dprobs):
+    dp = torch.empty_like(probs) if (need_dprobs and probs is not None) else feat.new_empty(0)
+    return torch.empty_like(feat), dp
+
+
+@torch.library.custom_op("slcl::centroid_loss", mutates_args=(), device_types="cuda")
+def centroid_loss(centroid_s: Tensor, centroid_t: Tensor, mode: int, first_row: int, n_rows: int,
+                  norm: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (loss[1], dL/ds, dL/dt) for dL/dloss = 1."""
+    dev = require_cuda(centroid_s, centroid_t)
+    lib = _lib.load()
+    s = centroid_s.to(_F32).contiguous()
+    t = centroid_t.to(_F32).contiguous()
+    if s.dim() != 2 or s.shape != t.shape:
+        raise ValueError("centroids must both be [K, C]")
+    k, c = s.shape
+    loss = torch.empty(1, dtype=_F32, device=dev)
+    ds = torch.empty_like(s)
+    dt = torch.empty_like(t)
+    with torch.cuda.device(dev):
+        st = lib.slcl_centroid_loss(ptr(s), ptr(t), k, c, mode, first_row, n_rows, int(norm), ptr(loss), ptr(ds), ptr(dt),
+                                    stream_ptr(dev))
+    check(st, "slcl_centroid_loss")
+    return loss, ds, dt
+
+
+@centroid_loss.register_fake
+def _(centroid_s, centroid_t, mode, first_row, n_rows, norm):
+    return centroid_s.new_empty(1), torch.empty_like(centroid_s), torch.empty_like(centroid_t)
+
+
+# ----------------------------------------------------------------------------
+# sampler
+# ----------------------------------------------------------------------------
+@torch.library.custom_op("slcl::compact_by_class", mutates_args=(), device_types="cuda")
+def compact_by_class(labels: Tensor, n_class: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (counts[K], offsets[K+1], index[N]) int64; index[offsets[k]:offsets[k+1]] == nonzero(labels == k)."""
+    dev = require_cuda(labels)
+    lib = _lib.load()
+    lab = labels.reshape(-1).contiguous()
+    if lab.dtype != torch.int64:
+        raise ValueError("labels must be int64")
+    n = lab.numel()
+    counts = torch.empty(n_class, dtype=torch.int64, device=dev)
+    offsets = torch.empty(n_class + 1, dtype=torch.int64, device=dev)
+    index = torch.empty(n, dtype=torch.int64, device=dev)
+    ws = _ws(lib.slcl_compact_workspace_bytes(n, n_class), dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_compact_by_class(ptr(lab), n, n_class, ptr(counts), ptr(offsets), ptr(index), ptr(ws), ws.numel(),
+                                       stream_ptr(dev))
+    check(st, "slcl_compact_by_class")
+    return counts, offsets, index
+
+
+@compact_by_class.register_fake
+def _(labels, n_class):
+    dev = labels.device
+    return (torch.empty(n_class, dtype=torch.int64, device=dev), torch.empty(n_class + 1, dtype=torch.int64, device=dev),
+            torch.empty(labels.numel(), dtype=torch.int64, device=dev))
+
+
+@torch.library.custom_op("slcl::gather_unit_rows", mutates_args=(), device_types="cuda")
+def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16: bool,
+                     want_f32: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    dev = require_cuda(feat, pixel_idx)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    idx = pixel_idx.reshape(-1).contiguous()
+    if idx.dtype != torch.int64:
+        raise ValueError("pixel_idx must be int64")
+    r = idx.numel()
+    rows_bf16 = torch.empty((r, c) if want_bf16 else (0, c), dtype=torch.bfloat16, device=dev)
+    rows_f32 = torch.empty((r, c) if want_f32 else (0, c), dtype=_F32, device=dev)
+    inv_norm = torch.empty(r, dtype=_F32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.slcl_gather_unit_rows(ptr(feat), b, c, h * w, ptr(idx), r, int(normalize),
+                                       ptr(rows_bf16) if want_bf16 else None, ptr(rows_f32) if want_f32 else None,
+                                       ptr(inv_norm), stream_ptr(dev))
+    check(st, "slcl_gather_unit_rows")
+    return rows_bf16, rows_f32, inv_norm
+
+
+@gather_unit_rows.register_fake
+def _(feat, pixel_idx, normalize, want_bf16, want_f32):
+    r, c = pixel_idx.numel(), feat.shape[1]
+    return (torch.empty((r if want_bf16 else 0, c), dtype=torch.bfloat16, device=feat.device),
+            torch.empty((r if want_f32 else 0, c), dtype=_F32, device=feat.device), feat.new_empty(r))
+
+
+@torch.library.custom_op("slcl::scatter_rows_bwd", mutates_args=("dfeat",), device_types="cuda")
+def scatter_rows_bwd(feat: Tensor, pixel_idx: Tensor, normalize: bool, d_rows: Tensor, inv_norm: Tensor,
+                     dfeat: Tensor) -> None:
+    dev = require_cuda(feat, pixel_idx, d_rows, inv_norm, dfeat)
+    lib = _lib.load()
+    if not (feat.is_contiguous() and dfeat.is_contiguous() and feat.shape == dfeat.shape):
+        raise ValueError("feat and dfeat must be contiguous NCHW of equal shape")
+    b, c, h, w = feat.shape
+    idx = pixel_idx.reshape(-1).contiguous()
+    d_rows = d_rows.to(_F32).contiguous()
+    with torch.cuda.device(dev):
+        st = lib.slcl_scatter_rows_bwd(ptr(feat), b, c, h * w, ptr(idx), idx.numel(), int(normalize), ptr(d_rows),
+                                       ptr(inv_norm), ptr(dfeat), stream_ptr(dev))
+    check(st, "slcl_scatter_rows_bwd")

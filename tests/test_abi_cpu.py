@@ -1,0 +1,134 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every
+symbol include/slcl.h declares, the ctypes table mirrors the header, the Python
+package keeps the reference's names/signatures, and the product path fails
+loudly without a GPU (no CPU fallback)."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "slcl.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(slcl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from slcl import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"libslcl.so lacks {name}"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
+    assert lib.slcl_version() == 100
+    assert lib.slcl_strerror(0) == b"ok"
+    assert b"invalid" in lib.slcl_strerror(-1)
+    assert lib.slcl_proto_workspace_bytes(1 << 20) >= (1 << 20) // 256 * 16
+    assert lib.slcl_proto_workspace_bytes(0) == 0
+    assert lib.slcl_compact_workspace_bytes(10000, 4) > 0
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any launch, so it can be exercised on a GPU-less host."""
+    from slcl import _lib
+    lib = _lib.load()
+    assert lib.slcl_proto_fwd(None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.slcl_class_sums(None, 1, 1, 1, None, None, 0, 0.0, None, 1, 4, None, None, 0, None) == -1
+    assert lib.slcl_centroid_loss(None, None, 4, 32, 0, 1, 4, 1, None, None, None, None) == -1
+    assert lib.slcl_compact_by_class(None, 10, 4, None, None, None, None, 0, None) == -1
+
+
+def test_reference_signatures_are_kept():
+    from slcl import loss, losses, utils_
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(loss.MPCL.__init__) == ["self", "device", "num_class", "temperature", "m", "base_temperature", "easy_margin"]
+    assert sig(loss.MPCL.forward) == ["self", "features", "labels", "class_center_feas", "pixel_sel_loc", "mask"]
+    assert sig(loss.mpcl_loss_calc) == ["feas", "labels", "class_center_feas", "loss_func", "pixel_sel_loc", "tag"]
+    assert sig(loss.ContrastiveLoss.__init__) == ["self", "tau", "n_class", "bg", "norm"]
+    assert sig(loss.ContrastiveLoss.forward) == ["self", "centroid_s", "centroid_t", "bg", "split"]
+    assert sig(loss.SupConLoss.__init__) == ["self", "temperature", "contrast_mode", "base_temperature"]
+    assert sig(loss.SupConLoss.forward) == ["self", "features", "labels"]
+    assert sig(loss.LocalConLoss.__init__) == ["self", "temperature", "stride"]
+    assert sig(loss.BlockConLoss.__init__) == ["self", "temperature", "block_size"]
+    assert losses.SupConLoss is loss.SupConLoss
+    assert sig(utils_.cal_centroid)[:15] == ["decoder_ft", "label", "previous_centroid", "momentum", "pseudo_label", "n_class",
+                                             "partition", "threshold", "thd_w", "weighted_ave", "epoch", "max_epoch",
+                                             "low_thd", "high_thd", "stdmin"]
+    assert sig(utils_.update_class_center_iter)[:5] == ["cla_src_feas", "batch_src_labels", "class_center_feas", "m", "num_class"]
+    assert sig(utils_.generate_pseudo_label) == ["cla_feas_trg", "class_centers", "pixel_sel_th"]
+    m = loss.MPCL("cuda", num_class=4, temperature=.1, base_temperature=1, m=.4)
+    assert abs(m.th - (-0.9210609940028851)) < 1e-12 and abs(m.mm - 0.15576733692346023) < 1e-12
+    d = inspect.signature(utils_.cal_centroid).parameters
+    assert d["momentum"].default == 0.95 and d["n_class"].default == 4 and d["partition"].default == 1
+    assert inspect.signature(utils_.update_class_center_iter).parameters["m"].default == .2
+
+
+def test_product_path_has_no_cpu_fallback():
+    from slcl import loss, utils_
+    from slcl._lib import SlclError
+    feas = torch.randn(1, 8, 4, 4)
+    lab = torch.zeros(1, 4, 4, dtype=torch.long)
+    cc = torch.randn(4, 8)
+    with pytest.raises((SlclError, NotImplementedError, RuntimeError)):
+        loss.mpcl_loss_calc(feas, lab, cc, loss.MPCL("cpu", num_class=4), tag="source")
+    with pytest.raises((SlclError, NotImplementedError, RuntimeError)):
+        utils_.update_class_center_iter(feas, lab, cc)
+    with pytest.raises((SlclError, NotImplementedError, RuntimeError)):
+        utils_.generate_pseudo_label(feas, cc)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "soft-labeled-contrastive-learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle[./]", txt, re.M), \
+                    f"{f} references the oracle package"
+
+
+def test_mpcl_error_behaviour_matches_reference():
+    from slcl.loss import MPCL
+    m = MPCL("cuda", num_class=4)
+    with pytest.raises(ValueError):
+        m(torch.randn(4, 8), torch.zeros(4), torch.randn(8, 4))
+    with pytest.raises(ValueError):
+        m(torch.randn(4, 1, 8), torch.zeros(4), torch.randn(8, 4), mask=torch.ones(4, 4))
+    with pytest.raises(ValueError):
+        m(torch.randn(4, 1, 8), torch.zeros(5), torch.randn(8, 4))
+
+
+def test_class_centre_state_layout(tmp_path):
+    """a-9: NPY v1.0, '<f4', C order, (K, C); 128-byte header + 512-byte payload for (4, 32)."""
+    from slcl import state
+    src = os.path.join(ROOT, "tests", "golden", "class_center_ct_f0.npy")
+    cc = state.load_class_centers(src, device="cpu")
+    assert cc.shape == (4, 32) and cc.dtype == torch.float32
+    norms = cc.norm(dim=1).tolist()
+    assert [round(v, 2) for v in norms] == [2.98, 6.47, 6.53, 6.84]
+    out = tmp_path / state.class_center_filename("/data/mmwhs", 0)
+    assert out.name == "class_center_ct_f0.npy"
+    assert state.class_center_filename("/x/mscmrseg/y", 3) == "class_center_bssfp_f3.npy"
+    state.save_class_centers(str(out), cc)
+    raw = open(out, "rb").read()
+    assert len(raw) == 640 and raw[:8] == b"\x93NUMPY\x01\x00"
+    assert raw == open(src, "rb").read()          # byte-identical round trip
+    assert np.array_equal(np.load(out), cc.numpy())
+
+
+def test_shard_range_covers_batch():
+    from slcl.distributed import shard_range
+    for n in (1, 7, 128, 129):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,379 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+The CUDA path (called through the drop-in Python API -> torch custom ops ->
+C ABI of libslcl.so) is compared with
+
+  * the committed outputs of the reference's own functions
+    (tests/golden/reference_outputs.npz), and
+  * the CPU oracle (oracle/slcl_oracle.py) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss and gradients rtol 1e-4 in fp32;
+labels, selection masks, class counts and compacted indices bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cases
+from oracle import slcl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def close(a, b, rtol=RTOL, atol=1e-6):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def grad_close(a, b, rtol=RTOL):
+    """Gradients: rtol 1e-4 relative to the tensor's scale (elements near zero compare absolutely)."""
+    b = torch.as_tensor(b).double()
+    scale = float(b.abs().max()) + 1e-30
+    close(a, b, rtol=rtol, atol=rtol * scale * 0.1)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from slcl import loss, utils_
+    return loss, utils_
+
+
+# ---------------------------------------------------------------------------
+# prototype path
+# ---------------------------------------------------------------------------
+def test_kat1_source_loss_vs_reference_golden(api, golden):
+    loss_mod, _ = api
+    feas, labels = cases.kat1()
+    cc = cases.shipped_centres()
+    f = feas.to(dev()).requires_grad_(True)
+    c = cc.to(dev()).requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=4, temperature=.1, base_temperature=1, m=.4)
+    out = loss_mod.mpcl_loss_calc(f, labels.to(dev()), c, mp, tag='source')
+    out.backward()
+    assert abs(out.item() - 0.23589777946472168) < 0.23589777946472168 * RTOL
+    close(out, golden["kat1_loss"])
+    grad_close(f.grad, golden["kat1_dfeas"])
+    grad_close(c.grad, golden["kat1_dcentres"])
+
+
+def test_kat2_pseudo_label_and_target_loss(api, golden):
+    loss_mod, utils_mod = api
+    ft = cases.kat2().to(dev())
+    cc = cases.shipped_centres().to(dev())
+    hard, sel = utils_mod.generate_pseudo_label(ft, cc, .25)
+    assert hard.dtype == torch.int64 and sel.dtype == torch.float32
+    assert np.array_equal(hard.cpu().numpy(), golden["kat2_label"])            # bit-exact
+    assert np.array_equal(sel.cpu().numpy(), golden["kat2_sel"])
+    f = ft.clone().requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=4, temperature=.1, base_temperature=1, m=.2)
+    out = loss_mod.mpcl_loss_calc(f, hard, cc, mp, pixel_sel_loc=sel, tag='target')
+    out.backward()
+    close(out, golden["kat2_loss"], atol=1e-8)
+    grad_close(f.grad, golden["kat2_dfeas"])
+
+
+def test_kat8_direct_mpcl_forward_soft_mask(api, golden):
+    loss_mod, _ = api
+    feas, _ = cases.kat1()
+    cc = cases.shipped_centres()
+    unit = F.normalize(feas, p=2, dim=1).permute(0, 2, 3, 1).reshape(-1, 32).to(dev()).requires_grad_(True)
+    cen = F.normalize(cc, p=2, dim=1).t().to(dev())
+    mp = loss_mod.MPCL(dev(), num_class=4, temperature=.1, base_temperature=1, m=.4)
+    out = mp(unit.unsqueeze(1), None, cen, mask=cases.kat8_mask().to(dev()))
+    out.backward()
+    close(out, golden["kat8_loss"])
+    grad_close(unit.grad, golden["kat8_dunit"])
+
+
+def test_kat9_cfg1_geometry_label_downsample(api, golden):
+    """33x33 map (HW = 1089, odd: scalar path), labels 256 -> 33, K = 5, C = 128."""
+    loss_mod, _ = api
+    f9, lab9, cc9 = cases.kat9()
+    f = f9.to(dev()).requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=5, temperature=.1, base_temperature=1, m=.4)
+    out = loss_mod.mpcl_loss_calc(f, lab9.to(dev()), cc9.to(dev()), mp, tag='source')
+    out.backward()
+    close(out, golden["kat9_loss"])
+    close(f.grad.abs().sum(), golden["kat9_dfeas_abs_sum"], rtol=RTOL)
+    grad_close(f.grad[:, :4, :3, :3], golden["kat9_dfeas_head"])
+
+
+def test_ragged_out_of_range_selection_easy_margin(api, golden):
+    loss_mod, utils_mod = api
+    rf, rl, rc, rsel = cases.ragged_case()
+    f = rf.to(dev()).requires_grad_(True)
+    c = rc.to(dev()).requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=5, temperature=.07, base_temperature=.07, m=.5)
+    out = loss_mod.mpcl_loss_calc(f, rl.view(-1).to(dev()), c, mp, pixel_sel_loc=rsel.to(dev()), tag='target')
+    out.backward()
+    close(out, golden["ragged_loss"])
+    grad_close(f.grad, golden["ragged_dfeas"])
+    grad_close(c.grad, golden["ragged_dcentres"])
+    hard, sel = utils_mod.generate_pseudo_label(rf.to(dev()), rc.to(dev()), .1)
+    assert np.array_equal(hard.cpu().numpy(), golden["ragged_label"])
+    assert np.array_equal(sel.cpu().numpy(), golden["ragged_sel"])
+    f = rf.to(dev()).requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=5, temperature=.1, base_temperature=1, m=.4, easy_margin=True)
+    out = loss_mod.mpcl_loss_calc(f, rl.to(dev()), rc.to(dev()), mp, tag='source')
+    out.backward()
+    close(out, golden["ragged_easy_loss"])
+    grad_close(f.grad, golden["ragged_easy_dfeas"])
+
+
+@pytest.mark.parametrize("b,c,h,w,k,with_sel", [
+    (2, 32, 16, 16, 4, False),      # vector path, DRUNet channel count
+    (3, 128, 8, 12, 5, True),       # vector path, cfg2 channel count, selection mask
+    (2, 7, 5, 5, 3, True),          # scalar path, C not a multiple of the unroll
+    (1, 40, 4, 4, 8, False),        # K = 8 (two broadcast loads per channel)
+    (2, 16, 6, 6, 2, False),        # K = 2
+])
+def test_proto_loss_vs_oracle(api, b, c, h, w, k, with_sel):
+    loss_mod, _ = api
+    gen = cases.g(100 + c + k)
+    feas = torch.randn(b, c, h, w, generator=gen) * 2.0
+    labels = torch.randint(0, k, (b, h, w), generator=gen)
+    cc = torch.randn(k, c, generator=gen)
+    sel = (torch.rand(b * h * w, generator=gen) > 0.5).float() if with_sel else None
+    spec = O.MarginSpec(num_class=k, temperature=.1, m=.4, base_temperature=1.0)
+    fo = feas.clone().requires_grad_(True)
+    co = cc.clone().requires_grad_(True)
+    ref = O.mpcl_loss_calc(fo, labels if not with_sel else labels.view(-1), co, spec, pixel_sel_loc=sel,
+                           tag='target' if with_sel else 'source')
+    ref.backward()
+    f = feas.to(dev()).requires_grad_(True)
+    cg = cc.to(dev()).requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.4)
+    out = loss_mod.mpcl_loss_calc(f, (labels if not with_sel else labels.view(-1)).to(dev()), cg, mp,
+                                  pixel_sel_loc=None if sel is None else sel.to(dev()),
+                                  tag='target' if with_sel else 'source')
+    (out * 3.0).backward()            # non-unit upstream gradient
+    close(out, ref)
+    grad_close(f.grad / 3.0, fo.grad)
+    grad_close(cg.grad / 3.0, co.grad)
+
+
+def test_proto_loss_non_contiguous_batch_slice(api):
+    """The trainers slice the batch (dcdr_ft[:s_size], Trainer_MCCL.py:271-273) and may hand over
+    channel slices; both collapse to a strided map without a copy."""
+    loss_mod, _ = api
+    gen = cases.g(7)
+    big = torch.randn(4, 24, 8, 8, generator=gen)
+    labels = torch.randint(0, 4, (2, 8, 8), generator=gen)
+    cc = torch.randn(4, 16, generator=gen)
+    spec = O.MarginSpec(4, .1, .4, 1.0)
+    view_cpu = big[1:3, 4:20]
+    fo = view_cpu.clone().requires_grad_(True)
+    ref = O.mpcl_loss_calc(fo, labels, cc, spec)
+    ref.backward()
+    bigg = big.to(dev()).requires_grad_(True)
+    out = loss_mod.mpcl_loss_calc(bigg[1:3, 4:20], labels.to(dev()), cc.to(dev()),
+                                  loss_mod.MPCL(dev(), 4, .1, .4, 1.0))
+    out.backward()
+    close(out, ref)
+    grad_close(bigg.grad[1:3, 4:20], fo.grad)
+    assert float(bigg.grad[0].abs().sum()) == 0.0 and float(bigg.grad[:, :4].abs().sum()) == 0.0
+
+
+def test_kat3_ema_class_centres(api, golden):
+    _, utils_mod = api
+    feas, labels = cases.kat1()
+    cc = cases.shipped_centres().to(dev())
+    new = utils_mod.update_class_center_iter(feas.to(dev()), labels.to(dev()), cc, m=.9)
+    close(new, golden["kat3_centres"])
+    lab = labels.clone()
+    lab[lab == 2] = 1
+    new = utils_mod.update_class_center_iter(feas.to(dev()), lab.to(dev()), cc, m=.9)
+    close(new, golden["kat3_empty_centres"])
+    rf, rl, rc, _ = cases.ragged_case()
+    new = utils_mod.update_class_center_iter(rf.to(dev()), rl.to(dev()), rc.to(dev()), m=.8, num_class=5)
+    close(new, golden["ragged_ema"])
+
+
+def test_class_counts_bit_exact():
+    """Weight-sum column of the class sums = exact integer class counts."""
+    gen = cases.g(55)
+    feas = torch.randn(3, 32, 20, 20, generator=gen)
+    labels = torch.randint(-1, 5, (3, 20, 20), generator=gen)       # includes out-of-range -1 and 4
+    sums = torch.ops.slcl.class_sums(feas.to(dev()), labels.view(-1).to(dev()), None, False, 0.0, None, 1, 4)
+    counts = sums[:, -1].cpu()
+    expect = torch.stack([(labels == k).sum() for k in range(4)]).double()
+    assert torch.equal(counts, expect)
+    ref_sums = torch.stack([(feas * (labels == k).unsqueeze(1)).sum(dim=(0, 2, 3)) for k in range(4)])
+    close(sums[:, :-1], ref_sums, rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------
+# centroid path
+# ---------------------------------------------------------------------------
+def test_kat5_hard_centroids(api, golden):
+    _, utils_mod = api
+    feas, labels = cases.kat1()
+    ft = cases.kat2()
+    c1, ratio, std = utils_mod.cal_centroid(feas.to(dev()), labels.to(dev()), momentum=.9)
+    assert ratio is None and std == []
+    close(c1, golden["kat5_c1"])
+    f = ft.to(dev()).requires_grad_(True)
+    c2, _, _ = utils_mod.cal_centroid(f, labels.to(dev()), previous_centroid=c1.detach(), momentum=.9)
+    (c2 * c2).sum().backward()
+    close(c2, golden["kat5_c2"])
+    grad_close(f.grad, golden["kat5_dft"])
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("wtd", dict(weighted_ave=True)),
+    ("wtd_thd", dict(weighted_ave=True, threshold=0.6)),
+    ("hardpl_thd", dict(weighted_ave=False, threshold=0.6)),
+    ("wtd_ema", dict(weighted_ave=True, momentum=.9)),
+])
+def test_soft_centroids_and_contrastive_vs_repaired_reference(api, golden, name, kw):
+    loss_mod, utils_mod = api
+    sft, probs = cases.soft_case()
+    if name == "wtd_ema":
+        kw = dict(kw, previous_centroid=cases.shipped_centres().to(dev()))
+    f = sft.to(dev()).requires_grad_(True)
+    p = probs.to(dev()).requires_grad_(True)
+    cen, _, _ = utils_mod.cal_centroid(f, p, pseudo_label=True, **kw)
+    src_c, _ = cases.kat4()
+    out = loss_mod.ContrastiveLoss()(src_c.to(dev()), cen) + (cen * cen).sum()
+    out.backward()
+    close(cen, golden[f"soft_{name}_cen"])
+    close(out, golden[f"soft_{name}_loss"])
+    grad_close(f.grad, golden[f"soft_{name}_dft"])
+    if golden[f"soft_{name}_dp"].size:
+        grad_close(p.grad, golden[f"soft_{name}_dp"])
+    else:
+        assert p.grad is None or float(p.grad.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("k,parts,thr", [(4, 2, None), (5, 2, 0.5), (4, 3, None), (8, 2, None)])
+def test_rmc_partitions_vs_oracle(api, k, parts, thr):
+    """Partitions are our spec (parity unpinned by the reference): part_id comes from PyTorch's RNG
+    stream on the host, so both sides consume identical indices; per-partition weight sums match."""
+    _, utils_mod = api
+    ft, probs = cases.soft_case(seed=40 + k, b=2, c=24, h=10, w=12, k=k)
+    pid = O.rmc_partition_ids(2 * 10 * 12, parts, cases.g(9))
+    fo = ft.clone().requires_grad_(True)
+    po = probs.clone().requires_grad_(True)
+    ref, _, _ = O.cal_centroid(fo, po, pseudo_label=True, weighted_ave=True, n_class=k, partition=parts,
+                               threshold=thr, part_id=pid)
+    sum((r * (i + 1.5)).pow(2).sum() for i, r in enumerate(ref)).backward()
+    f = ft.to(dev()).requires_grad_(True)
+    p = probs.to(dev()).requires_grad_(True)
+    got, _, _ = utils_mod.cal_centroid(f, p, pseudo_label=True, weighted_ave=True, n_class=k, partition=parts,
+                                       threshold=thr, part_id=pid.to(dev()))
+    assert isinstance(got, list) and len(got) == parts
+    sum((r * (i + 1.5)).pow(2).sum() for i, r in enumerate(got)).backward()
+    for a, b in zip(got, ref):
+        close(a, b, atol=1e-6)
+    grad_close(f.grad, fo.grad)
+    grad_close(p.grad, po.grad)
+    # same generator state -> same partition ids as the product's own sampler
+    mine = utils_mod.rmc_partition_ids(240, parts, cases.g(9))
+    assert torch.equal(mine, pid)
+
+
+def test_kat4_contrastive_loss_and_cnr(api, golden):
+    loss_mod, _ = api
+    cs, ct = cases.kat4()
+    for name, kw in (("plain", {}), ("split", {"split": True}), ("bg", {"bg": True})):
+        a = cs.to(dev()).requires_grad_(True)
+        b = ct.to(dev()).requires_grad_(True)
+        out = loss_mod.ContrastiveLoss(tau=5)(a, b, **kw)
+        (out * 2.0).backward()
+        close(out, golden[f"kat4_{name}_loss"])
+        grad_close(a.grad / 2.0, golden[f"kat4_{name}_ds"])
+        grad_close(b.grad / 2.0, golden[f"kat4_{name}_dt"])
+    # tau is ignored by the reference (bug-compatible)
+    assert loss_mod.ContrastiveLoss(tau=.1)(cs.to(dev()), ct.to(dev())).item() == \
+        loss_mod.ContrastiveLoss(tau=5)(cs.to(dev()), ct.to(dev())).item()
+    # CNR vs oracle
+    so = cs.clone().requires_grad_(True)
+    to = [ct.clone().requires_grad_(True), (ct * 1.7).clone().requires_grad_(True)]
+    ref = O.cnr_loss(so, to)
+    ref.backward()
+    sg = cs.to(dev()).requires_grad_(True)
+    tg = [ct.to(dev()).requires_grad_(True), (ct * 1.7).to(dev()).requires_grad_(True)]
+    out = loss_mod.cnr_loss(sg, tg)
+    out.backward()
+    close(out, ref)
+    grad_close(sg.grad, so.grad)
+    grad_close(tg[1].grad, to[1].grad)
+
+
+# ---------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(1, 4), (255, 4), (4096, 5), (4097, 5), (100003, 8)])
+def test_compaction_bit_exact_with_nonzero(n, k):
+    gen = cases.g(n + k)
+    labels = torch.randint(-1, k + 1, (n,), generator=gen)       # out-of-range labels are dropped
+    counts, offsets, index = torch.ops.slcl.compact_by_class(labels.to(dev()), k)
+    counts, offsets, index = counts.cpu(), offsets.cpu(), index.cpu()
+    for c in range(k):
+        want = torch.nonzero(labels == c).squeeze(1)
+        assert counts[c].item() == want.numel()
+        assert torch.equal(index[offsets[c]:offsets[c + 1]], want)
+    assert offsets[0].item() == 0 and offsets[k].item() == int(((labels >= 0) & (labels < k)).sum())
+
+
+def test_gather_unit_rows_vs_oracle():
+    gen = cases.g(77)
+    feat = torch.randn(2, 40, 9, 7, generator=gen)
+    idx = torch.randperm(2 * 9 * 7, generator=gen)[:50]
+    want = O.gather_unit_rows(feat, idx)
+    bf, f32, inv = torch.ops.slcl.gather_unit_rows(feat.to(dev()), idx.to(dev()), True, True, True)
+    close(f32, want, rtol=1e-5, atol=1e-7)
+    assert torch.equal(bf.cpu(), f32.cpu().to(torch.bfloat16))       # bf16 rows are the rounded fp32 rows
+    rows = feat.permute(0, 2, 3, 1).reshape(-1, 40)[idx]
+    close(inv, 1.0 / rows.norm(dim=1), rtol=1e-5)
+    # backward through gather + normalise
+    fo = feat.clone().requires_grad_(True)
+    g_rows = torch.randn(50, 40, generator=gen)
+    (O.gather_unit_rows(fo, idx) * g_rows).sum().backward()
+    dfeat = torch.zeros_like(feat, device=dev())
+    torch.ops.slcl.scatter_rows_bwd(feat.to(dev()), idx.to(dev()), True, g_rows.to(dev()), inv, dfeat)
+    grad_close(dfeat, fo.grad)
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at full size (cfg2 / cfg4 shapes)
+# ---------------------------------------------------------------------------
+def test_full_size_properties_cfg4_shape(api):
+    """cfg4 per-GPU shape B16 C32 224x224 K4: (i) counts are exact and sum to N, (ii) EMA with m=1 is the
+    identity, (iii) the loss of a batch equals the pixel-weighted mean of the losses of its halves,
+    (iv) gradient of the mean loss sums linearly, (v) pseudo-label of a centre-aligned map is exact."""
+    loss_mod, utils_mod = api
+    torch.manual_seed(0)
+    b, c, h, w, k = 16, 32, 224, 224, 4
+    feas = torch.randn(b, c, h, w, device=dev())
+    labels = torch.randint(0, k, (b, h, w), device=dev())
+    cc = torch.randn(k, c, device=dev())
+    sums = torch.ops.slcl.class_sums(feas, labels.view(-1), None, False, 0.0, None, 1, k)
+    assert int(sums[:, -1].sum().item()) == b * h * w
+    assert torch.equal(sums[:, -1].long(), torch.bincount(labels.view(-1), minlength=k))
+    assert torch.equal(utils_mod.update_class_center_iter(feas, labels, cc, m=1.0), cc)
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.4)
+    whole = loss_mod.mpcl_loss_calc(feas, labels, cc, mp)
+    h1 = loss_mod.mpcl_loss_calc(feas[:8], labels[:8], cc, mp)
+    h2 = loss_mod.mpcl_loss_calc(feas[8:], labels[8:], cc, mp)
+    close(whole, 0.5 * (h1 + h2), rtol=1e-5)
+    f = feas.clone().requires_grad_(True)
+    loss_mod.mpcl_loss_calc(f, labels, cc, mp).backward()
+    fh = feas[:8].clone().requires_grad_(True)
+    loss_mod.mpcl_loss_calc(fh, labels[:8], cc, mp).backward()
+    grad_close(f.grad[:8] * 2.0, fh.grad, rtol=1e-5)
+    # rows of a normalised gradient are orthogonal to the pixel (d/dx of a function of x/|x|)
+    radial = (f.grad * feas).sum(1).abs().max().item()
+    assert radial < 1e-9
+    # a map whose pixels are the centres themselves: label = class, gap = 1 - max off-diagonal cosine
+    aligned = cc[labels].permute(0, 3, 1, 2).contiguous()
+    hard, sel = utils_mod.generate_pseudo_label(aligned, cc, 0.0)
+    assert torch.equal(hard, labels.view(-1)) and bool((sel == 1).all())
