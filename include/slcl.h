@@ -94,6 +94,11 @@ int slcl_proto_fwd(const float* feat, const slcl_map_t* map,
                    float* stash, float* cstate, float* scal,
                    void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
+/* Data-parallel use: each rank runs slcl_proto_fwd on its shard, the
+ * caller all-reduces scal[2..3] (weight sum, weighted row-loss sum) across ranks, then this
+ * call recomputes scal[0] (global loss) and scal[1] (global coefficient) in place. */
+int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream);
+
 /* Backward w.r.t. the feature map.  grad_out: device scalar dL/dloss.
  * dfeat uses the strides of `map`. */
 int slcl_proto_bwd(const float* feat, const slcl_map_t* map,

@@ -288,6 +288,16 @@ __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2*
   }
 }
 
+// After a cross-rank all-reduce of scal[2..3] (weight sum, weighted row-loss sum):
+// recompute the global loss and coefficient in place.
+__global__ void proto_rescale_kernel(float* scal, int has_sel) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float coef = has_sel ? 1.0f / (scal[2] + 1e-4f) : 1.0f / scal[2];
+    scal[0] = scal[3] * coef;
+    scal[1] = coef;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // backward: dF = gamma * ( sum_k a_k chat_k - b x )
 // ---------------------------------------------------------------------------
@@ -541,6 +551,12 @@ extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const in
   })
   proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, sel != nullptr, scal);
   return check_launch("slcl_proto_fwd");
+}
+
+extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream_) {
+  if (!scal) return SLCL_ERR_INVALID_ARGUMENT;
+  proto_rescale_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(scal, has_sel);
+  return check_launch("slcl_proto_rescale");
 }
 
 extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,

@@ -20,10 +20,16 @@ class _ProtoLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature, margin,
-                easy_margin, normalize):
+                easy_margin, normalize, group):
         scal, stash, cstate = _ops.proto_fwd(feat.detach(), labels, None if soft_mask is None else soft_mask.detach(),
                                              None if sel is None else sel.detach(), centres.detach(), rows_layout,
                                              n_class, temperature, base_temperature, margin, easy_margin, normalize)
+        if group is not None:
+            # data-parallel: global mean = all-reduced numerator / denominator
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
+                dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
+                _ops.proto_rescale(scal, sel is not None)
         ctx.save_for_backward(feat, stash, cstate, scal)
         ctx.cfg = (rows_layout, n_class, normalize)
         ctx.soft = soft_mask is not None and soft_mask.requires_grad
@@ -43,14 +49,14 @@ class _ProtoLoss(torch.autograd.Function):
             dfeat = _ops.proto_bwd(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
         if ctx.needs_input_grad[4]:
             dcen = _ops.proto_bwd_centres(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
-        return dfeat, None, None, None, dcen, None, None, None, None, None, None, None
+        return dfeat, None, None, None, dcen, None, None, None, None, None, None, None, None
 
 
 def proto_loss(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor], centres: Tensor,
                *, rows_layout: bool, n_class: int, temperature: float, base_temperature: float, margin: float,
-               easy_margin: bool, normalize: bool) -> Tensor:
+               easy_margin: bool, normalize: bool, group=None) -> Tensor:
     return _ProtoLoss.apply(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature,
-                            margin, easy_margin, normalize)
+                            margin, easy_margin, normalize, group)
 
 
 class _Centroids(torch.autograd.Function):

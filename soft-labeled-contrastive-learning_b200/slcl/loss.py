@@ -64,12 +64,14 @@ class MPCL(nn.Module):
         return SF.proto_loss(rows, labels, mask, sel, centres, rows_layout=True, **self._kw(normalize=False))
 
 
-def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=None, tag='source'):
+def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=None, tag='source', group=None):
     """feas [B,C,h,w]; labels [B,H,W] (source) or [N] (target); class_center_feas
     [K,C]; loss_func an ``MPCL``.  Reference: utils/loss.py:576-605.  With an slcl
     ``MPCL`` the normalisation, the NCHW->NHWC copy and the loss are one fused
     kernel over the NCHW map; any other callable gets the reference call
-    sequence."""
+    sequence.  ``group`` (addition): torch.distributed group (or True for the
+    default group) over which the batch is sharded -- the loss becomes the mean
+    over the GLOBAL batch (one 8-byte all-reduce), gradients follow."""
     n, c, fea_h, fea_w = feas.size()
     if tag == 'source' and (labels.size()[1] != fea_h or labels.size()[2] != fea_w):     # :585-590
         labels = labels.float()
@@ -82,7 +84,7 @@ def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=Non
         if labels.shape[0] != n * fea_h * fea_w:
             raise ValueError('Num of labels does not match num of features')
         sel = None if pixel_sel_loc is None else pixel_sel_loc.view(-1)
-        return SF.proto_loss(feas, labels, None, sel, class_center_feas, rows_layout=False,
+        return SF.proto_loss(feas, labels, None, sel, class_center_feas, rows_layout=False, group=group,
                              **loss_func._kw(normalize=True))
     unit = F.normalize(feas, p=2, dim=1).permute(0, 2, 3, 1).reshape(n * fea_h * fea_w, c).unsqueeze(1)
     centres = F.normalize(class_center_feas, p=2, dim=1).transpose(0, 1)

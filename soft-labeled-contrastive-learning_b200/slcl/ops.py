@@ -100,6 +100,15 @@ def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, 
     return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class))
 
 
+@torch.library.custom_op("slcl::proto_rescale", mutates_args=("scal",), device_types="cuda")
+def proto_rescale(scal: Tensor, has_sel: bool) -> None:
+    """Recompute scal[0:2] from the (all-reduced) sums scal[2:4], in place."""
+    dev = require_cuda(scal)
+    with torch.cuda.device(dev):
+        st = _lib.load().slcl_proto_rescale(ptr(scal), int(has_sel), stream_ptr(dev))
+    check(st, "slcl_proto_rescale")
+
+
 @torch.library.custom_op("slcl::proto_bwd", mutates_args=(), device_types="cuda")
 def proto_bwd(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_out: Tensor, rows_layout: bool,
               n_class: int, normalize: bool) -> Tensor:
