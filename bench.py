@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- SLCL loss fwd+bwd pixels/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # product arm (CUDA kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+Workload at every N (weak scaling, one process per GPU): BASELINE.json configs[1] --
+"SLCL prototype path at 256x256 full-res 128-d embeddings, batch 32, 5 classes" (cfg2 of
+SURVEY.md 8): per GPU a [32,128,256,256] fp32 NCHW feature map (1.07 GB), int64 labels,
+fp32 pixel-selection mask, [5,128] class centres, T=0.1, base_T=1, m=0.2.
+
+A step = one forward + backward of the prototype loss (reference mpcl_loss_calc + MPCL.forward,
+utils/loss.py:576-605,484-573 and its autograd backward): 3 forward launches (centre prep, fused
+loss, finalise) + 1 backward launch; with N>1 the loss is the mean over the GLOBAL batch, so one
+8-byte NCCL all-reduce + a rescale launch sit between forward and backward.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  No L2 flush is needed: every step streams
+1.07 GB (> 126 MB L2) of input.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "soft-labeled-contrastive-learning_b200")
+for _p in (ROOT, PKG_DIR):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "SLCL loss fwd+bwd pixels/sec"
+UNIT = "pixels/s"
+CFG = dict(B=32, C=128, H=256, W=256, K=5, temperature=0.1, base_temperature=1.0, margin=0.2, seed=1234)
+WORKLOAD = ("cfg2: SLCL prototype path (mpcl_loss_calc+MPCL fwd+bwd, target variant with pixel_sel_loc), "
+            "B32 C128 256x256 K5 fp32 NCHW per GPU")
+FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="slcl", choices=["slcl", "reference"])
+    ap.add_argument("--cpu-sample-images", type=int, default=4, help="images of the cfg2 shape per CPU step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table of the other path kernels")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu --set full summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as fh:
+            return json.load(fh)["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs: CPU generator -> identical bits for oracle and GPU
+# ----------------------------------------------------------------------------
+def make_inputs(n_images: int, seed: int, pin: bool):
+    gen = torch.Generator().manual_seed(seed)
+    c, h, w, k = CFG["C"], CFG["H"], CFG["W"], CFG["K"]
+    feats = torch.empty((n_images, c, h, w), dtype=torch.float32, pin_memory=pin)
+    feats.normal_(generator=gen)
+    labels = torch.empty((n_images * h * w,), dtype=torch.int64, pin_memory=pin)
+    labels.random_(0, k, generator=gen)
+    sel = torch.empty((n_images * h * w,), dtype=torch.float32, pin_memory=pin)
+    sel.copy_((torch.rand(n_images * h * w, generator=gen) > 0.5).float())
+    centres = torch.randn(k, c, generator=gen)
+    return feats, labels, sel, centres
+
+
+# ----------------------------------------------------------------------------
+# clocks sampler (NVML, same fields as the nvidia-smi line of B200_PROFILING.md)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period_s: float = 0.005):
+        self.samples = []
+        self.period = period_s
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                                   # pragma: no cover
+            self.err = repr(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((time.perf_counter(), mhz, reasons, util))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.ok:
+            self.thread.join(timeout=2)
+
+    def summary(self, t0: float, t1: float):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        where = "timed region"
+        if len(inside) < 3:          # timed region shorter than the sampling period: use every sample under load
+            inside = [s for s in self.samples if s[3] > 0] or self.samples
+            where = "whole run under load (timed region too short to sample)"
+        names = {
+            getattr(nv, "nvmlClocksEventReasonGpuIdle", 0x1): "gpu_idle",
+            getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSyncBoost", 0x10): "sync_boost",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        mask = 0
+        for s in inside:
+            mask |= int(s[2])
+        reasons = sorted(n for bit, n in names.items() if mask & bit and n != "gpu_idle")
+        return {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside), "sampled_over": where}
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's own call sequence
+# ----------------------------------------------------------------------------
+def cpu_step_fn(n_images: int):
+    from oracle import slcl_oracle as O
+    feats, labels, sel, centres = make_inputs(n_images, CFG["seed"], pin=False)
+    spec = O.MarginSpec(num_class=CFG["K"], temperature=CFG["temperature"], m=CFG["margin"],
+                        base_temperature=CFG["base_temperature"])
+    feats.requires_grad_(True)
+
+    def step():
+        feats.grad = None
+        loss = O.mpcl_loss_calc(feats, labels, centres, spec, pixel_sel_loc=sel, tag="target")
+        loss.backward()
+        return float(loss.detach())
+    return step, n_images * CFG["H"] * CFG["W"]
+
+
+def time_cpu(n_images: int, warmup: int, steps: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, pixels = cpu_step_fn(n_images)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return pixels, times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = args.cpu_sample_images
+    pixels, times, cores = time_cpu(n_img, max(args.warmup, 1), args.steps)
+    total = sum(times)
+    value = pixels * len(times) / total
+    sample = (f"{n_img} of the 32 images of the cfg2 batch per step ({pixels} px, same shapes/hyper-parameters); "
+              f"oracle port of mpcl_loss_calc+MPCL.forward fwd+bwd (torch CPU ops, fp32)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample of the workload per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------
+def run_slcl(args):
+    import torch.distributed as dist
+    from slcl import ops  # noqa: F401
+    from slcl.loss import MPCL, mpcl_loss_calc
+    from slcl.plan import ProtoPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    B, C, H, W, K = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["K"]
+    n_px = B * H * W
+    feats_h, labels_h, sel_h, centres_h = make_inputs(B, CFG["seed"] + rank, pin=True)
+    feats = feats_h.to(dev, non_blocking=True)
+    labels = labels_h.to(dev, non_blocking=True)
+    sel = sel_h.to(dev, non_blocking=True)
+    centres = centres_h.to(dev)
+    # Timed loop: raw C-ABI launches on pre-allocated buffers (slcl.plan.ProtoPlan) so the host
+    # never gates the GPU; the torch custom-op / autograd route is what `e2e` measures.
+    plan = ProtoPlan(feats, labels, sel, centres, K, CFG["temperature"], CFG["base_temperature"], CFG["margin"])
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def step(record: bool):
+        e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
+        if record:
+            e0.record()
+        scal = plan.forward()
+        if record:
+            e1.record()
+        if world > 1:
+            dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
+            plan.rescale()
+        if record:
+            e2.record()
+        dfeat = plan.backward()
+        if record:
+            e3.record()
+            marks.append((e0, e1, e2, e3))
+        return scal, dfeat
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    start, end = ev(), ev()
+    t_wall0 = time.perf_counter()
+    start.record()
+    for _ in range(args.steps):
+        scal, dfeat = step(True)
+    end.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    elapsed_ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n_px * args.steps / (elapsed_ms * 1e-3)
+    fwd_ms = statistics.mean(m[0].elapsed_time(m[1]) for m in marks)
+    xch_ms = statistics.mean(m[1].elapsed_time(m[2]) for m in marks)
+    bwd_ms = statistics.mean(m[2].elapsed_time(m[3]) for m in marks)
+    loss_value = float(scal[0])
+    launches_per_step = 4 + (1 if world > 1 else 0)
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        mp = MPCL(dev, num_class=K, temperature=CFG["temperature"], m=CFG["margin"],
+                  base_temperature=CFG["base_temperature"])
+        grad_h = torch.empty_like(feats_h, pin_memory=True)
+        loss_h = torch.empty((), dtype=torch.float32, pin_memory=True)
+        group = True if world > 1 else None
+        del dfeat, plan
+
+        def e2e_step():
+            f = feats_h.to(dev, non_blocking=True).requires_grad_(True)
+            lab = labels_h.to(dev, non_blocking=True)
+            s = sel_h.to(dev, non_blocking=True)
+            loss = mpcl_loss_calc(f, lab, centres, mp, pixel_sel_loc=s, tag="target", group=group)
+            loss.backward()
+            loss_h.copy_(loss.detach(), non_blocking=True)
+            grad_h.copy_(f.grad, non_blocking=True)
+
+        n_e2e = max(1, min(args.steps, 20))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s2, e2 = ev(), ev()
+        s2.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e2.record()
+        barrier()
+        ms = s2.elapsed_time(e2)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        h2d = feats_h.numel() * 4 + labels_h.numel() * 8 + sel_h.numel() * 4
+        d2h = grad_h.numel() * 4 + 4
+        e2e = {"value": world * n_px * n_e2e / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms / n_e2e,
+               "api": "slcl.loss.mpcl_loss_calc(...).backward() on pinned host buffers; loss and dF copied back",
+               "loss": float(loss_h)}
+        del grad_h
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    bwd_bytes = 8 * C * n_px                     # read F + write dF; the 4(K+1) B/px stash is overhead
+    fwd_bytes = (4 * C + 12) * n_px              # read F + labels + sel
+    step_bytes = (12 * C + 24) * n_px
+    bwd_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "proto_bwd_kernel<5,4>", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
+        "frac": bwd_gbs / peak, "traffic": ncu_traffic("proto_bwd_kernel"), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms,
+        "forward": {"kernel": "proto_fwd_kernel<5,4> (+prep, finalise)", "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9,
+                    "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": fwd_bytes,
+                    "avg_ms": fwd_ms, "traffic": ncu_traffic("proto_fwd_kernel")},
+        "step": {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                 "algorithmic_bytes": step_bytes, "exchange_ms": xch_ms},
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": n_px,
+                   "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
+                   "parallelism": f"dp{world} (batch sharded; 8-byte loss all-reduce)" if world > 1 else "single GPU",
+                   "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
+    }
+    if not args.no_extras and world == 1:
+        out["kernels"] = extra_kernels(dev, feats, labels, centres, peak)
+    if not args.no_cpu and world == 1:
+        n_img = args.cpu_sample_images
+        pixels, times, cores = time_cpu(n_img, 1, 3)
+        out["cpu_baseline"] = {
+            "value": pixels / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_img} of the 32 cfg2 images per step ({pixels} px), oracle port of the reference call sequence, "
+                      f"fwd+bwd, min of 3 after 1 warm-up, torch CPU fp32 with {cores} threads"}
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_kernels(dev, feats, labels, centres, peak):
+    """Device-time and roofline fraction of the other kernels of the path on the same map
+    (not part of `value`): pseudo labels, EMA class centres, soft centroid fwd/bwd."""
+    op = torch.ops.slcl
+    B, C, H, W = feats.shape
+    K = centres.shape[0]
+    n_px = B * H * W
+    gen = torch.Generator(device=dev).manual_seed(7)
+    probs = torch.softmax(3 * torch.randn(B, K, H, W, device=dev, generator=gen), 1)
+    part = (torch.randperm(n_px, device=dev, generator=gen) % 2).to(torch.int32)
+    gcen = torch.randn(2 * K, C, device=dev, generator=gen)
+
+    def timed(fn, iters=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize(dev)
+        return s.elapsed_time(e) / iters
+
+    res = {}
+
+    def add(name, ms, bytes_):
+        gbs = bytes_ / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                     "pixels_per_s": n_px / (ms * 1e-3)}
+
+    add("pseudo_label (generate_pseudo_label)", timed(lambda: op.pseudo_label(feats, centres, 0.25)), (4 * C + 12) * n_px)
+    add("class_sums hard + ema_finalize (update_class_center_iter)",
+        timed(lambda: op.ema_finalize(op.class_sums(feats, labels, None, False, 0.0, None, 1, K), centres, 0.9)),
+        (4 * C + 8) * n_px)
+    sums = op.class_sums(feats, None, probs, True, 0.0, part, 2, K)
+    add("class_sums soft P=2 (cal_centroid fwd)", timed(lambda: op.class_sums(feats, None, probs, True, 0.0, part, 2, K)),
+        (4 * C + 4 * K + 4) * n_px)
+    add("centroid_bwd soft P=2 (cal_centroid bwd: dF + dP)",
+        timed(lambda: op.centroid_bwd(feats, None, probs, True, 0.0, part, 2, K, gcen, sums, 1.0, True)),
+        (8 * C + 8 * K + 4) * n_px)
+    return res
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_slcl(args)
+
+
+if __name__ == "__main__":
+    main()

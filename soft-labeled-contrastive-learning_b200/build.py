@@ -20,13 +20,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "slcl")
-OBJ_DIR = os.path.join(HERE, "build")
-LIB = os.path.join(OUT_DIR, "libslcl.so")
+OBJ_DIR = os.path.join(HERE, "build", os.environ.get("SLCL_LIB_NAME", "libslcl.so")[:-3])
+LIB = os.path.join(OUT_DIR, os.environ.get("SLCL_LIB_NAME", "libslcl.so"))      # tuning variants: other names
+EXTRA = os.environ.get("SLCL_EXTRA_NVCC_FLAGS", "").split()
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC, *EXTRA,
 ]
 
 
@@ -45,6 +46,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for path in _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + \
             [os.path.join(ROOT, "include", "slcl.h"), os.path.abspath(__file__)]:
+        h.update(" ".join(EXTRA).encode())
         with open(path, "rb") as fh:
             h.update(path.encode())
             h.update(fh.read())

@@ -21,11 +21,27 @@
 namespace slcl {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll = 8;      // channel planes in flight per thread (8 x 16 B)
+#ifndef SLCL_PROTO_THREADS
+#define SLCL_PROTO_THREADS 256
+#endif
+constexpr int kThreads = SLCL_PROTO_THREADS;
+#ifndef SLCL_FWD_UNROLL
+#define SLCL_FWD_UNROLL 8
+#endif
+#ifndef SLCL_BWD_UNROLL
+#define SLCL_BWD_UNROLL 8
+#endif
+#ifndef SLCL_FWD_MINBLK
+#define SLCL_FWD_MINBLK 3
+#endif
+#ifndef SLCL_BWD_MINBLK
+#define SLCL_BWD_MINBLK 3
+#endif
+constexpr int kUnroll = SLCL_FWD_UNROLL;      // channel planes in flight per thread (8 x 16 B)
+constexpr int kUnrollBwd = SLCL_BWD_UNROLL;
 
 struct MarginConst {
-  float temperature, scale /* T / T_b */, cos_m, sin_m, th, mm;
+  float inv_t /* 1 / T */, scale /* T / T_b */, cos_m, sin_m, th, mm;
   int easy, normalize;
 };
 
@@ -153,20 +169,24 @@ __device__ __forceinline__ void channel_pass(const float* base, int64_t sc, int 
 template <int K>
 __device__ __forceinline__ float margin_row(const float (&cosv)[K], const float (&M)[K], float selw, float inv_n,
                                             const MarginConst& mc, float (&coef)[K + 1]) {
+  // Divisions by T are multiplications by a host-computed 1/T (<= 1 ulp from the reference's
+  // torch.div, far inside the 1e-4 budget); cs/sine uses rsqrt of the clamped 1-cos^2.
   float plain[K], marg[K], dphi[K];
   float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    float cs = cosv[k];
-    plain[k] = cs / mc.temperature;                                  // :530
-    float u = 1.0f - cs * cs;                                        // :534
-    float sine = sqrtf(fminf(fmaxf(u, 1e-4f), 1.0f));
-    float phi = cs * mc.cos_m - sine * mc.sin_m;                     // :536
-    bool on = mc.easy ? (cs > 0.f) : (cs > mc.th);                   // :538-541
-    float ph = on ? phi : (mc.easy ? cs : cs - mc.mm);
-    marg[k] = ph / mc.temperature;                                   // :543
-    bool unclamped = (u >= 1e-4f) && (u <= 1.0f);
-    dphi[k] = on ? (unclamped ? mc.cos_m + mc.sin_m * cs / sine : mc.cos_m) : 1.0f;
+    const float cs = cosv[k];
+    plain[k] = cs * mc.inv_t;                                        // :530
+    const float u = 1.0f - cs * cs;                                  // :534
+    const float uc = fminf(fmaxf(u, 1e-4f), 1.0f);
+    const float rs = rsqrtf(uc);
+    const float sine = uc * rs;
+    const float phi = cs * mc.cos_m - sine * mc.sin_m;               // :536
+    const bool on = mc.easy ? (cs > 0.f) : (cs > mc.th);             // :538-541
+    const float ph = on ? phi : (mc.easy ? cs : cs - mc.mm);
+    marg[k] = ph * mc.inv_t;                                         // :543
+    const bool unclamped = (u >= 1e-4f) && (u <= 1.0f);
+    dphi[k] = on ? (unclamped ? fmaf(mc.sin_m * cs, rs, mc.cos_m) : mc.cos_m) : 1.0f;
     m1 = fmaxf(m1, plain[k]);                                        // :531 (detached)
     m2 = fmaxf(m2, marg[k]);                                         // :545 (detached)
   }
@@ -179,20 +199,22 @@ __device__ __forceinline__ float margin_row(const float (&cosv)[K], const float 
     s += ez[k];
     sum_m += M[k];
   }
-  float den = s + 1e-4f;                                             // :556
-  float lse = logf(den);
+  const float den = s + 1e-4f;                                       // :556
+  const float lse = logf(den);
+  const float inv_den = 1.0f / den;
   float row = 0.f;
 #pragma unroll
   for (int k = 0; k < K; ++k) row += M[k] * (z[k] - lse);            // :562 / :568
   float bsum = 0.f;
+  const float w_row = selw * inv_n * mc.inv_t;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    float dz = -mc.scale * (M[k] - sum_m * ez[k] / den);
-    float e = dz * ((1.0f - M[k]) + M[k] * dphi[k]) / mc.temperature;
-    coef[k] = selw * e * inv_n;
+    const float dz = -mc.scale * (M[k] - sum_m * ez[k] * inv_den);
+    const float e = dz * ((1.0f - M[k]) + M[k] * dphi[k]);           // times 1/T, folded into w_row
+    coef[k] = w_row * e;
     bsum = fmaf(e, cosv[k], bsum);
   }
-  coef[K] = mc.normalize ? selw * bsum * inv_n * inv_n : 0.f;
+  coef[K] = mc.normalize ? w_row * bsum * inv_n : 0.f;
   return -mc.scale * row;
 }
 
@@ -200,7 +222,7 @@ __device__ __forceinline__ float margin_row(const float (&cosv)[K], const float 
 // forward: loss rows + stash
 // ---------------------------------------------------------------------------
 template <int K, int VEC>
-__global__ void __launch_bounds__(kThreads) proto_fwd_kernel(const ProtoArgs a) {
+__global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINBLK : 1) proto_fwd_kernel(const ProtoArgs a) {
   extern __shared__ __align__(16) float sC[];
   __shared__ double red[2][kThreads / 32];
   const int C = (int)a.channels;
@@ -233,12 +255,12 @@ __global__ void __launch_bounds__(kThreads) proto_fwd_kernel(const ProtoArgs a) 
     float out[K + 1][VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      float n = a.mc.normalize ? fmaxf(sqrtf(nrm[v]), 1e-12f) : 1.0f;   // F.normalize eps (:595)
-      float inv_n = 1.0f / n;
+      const float n = a.mc.normalize ? fmaxf(sqrtf(nrm[v]), 1e-12f) : 1.0f;   // F.normalize eps (:595)
+      const float inv_n = 1.0f / n;
       float cosv[K], M[K], coef[K + 1];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        cosv[k] = a.mc.normalize ? dot[k][v] / n : dot[k][v];
+        cosv[k] = dot[k][v] * inv_n;
         if (a.labels != nullptr) M[k] = (lab[v] == (long long)k) ? 1.0f : 0.0f;      // :513
         else M[k] = a.soft_mask[(pix + v) * K + k];                                    // :517
       }
@@ -302,7 +324,7 @@ __global__ void proto_rescale_kernel(float* scal, int has_sel) {
 // backward: dF = gamma * ( sum_k a_k chat_k - b x )
 // ---------------------------------------------------------------------------
 template <int K, int VEC>
-__global__ void __launch_bounds__(kThreads) proto_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
+__global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_BWD_MINBLK : 1) proto_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
                                                              float* dfeat) {
   extern __shared__ __align__(16) float sC[];
   const int C = (int)a.channels;
@@ -321,12 +343,12 @@ __global__ void __launch_bounds__(kThreads) proto_bwd_kernel(const ProtoArgs a, 
   const float* src = a.feat + off;
   float* dst = dfeat + off;
   int c = 0;
-  for (; c + kUnroll <= C; c += kUnroll) {
-    float x[kUnroll][VEC];
+  for (; c + kUnrollBwd <= C; c += kUnrollBwd) {
+    float x[kUnrollBwd][VEC];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) Vec<VEC>::load(src + (int64_t)(c + u) * a.sc, x[u]);
+    for (int u = 0; u < kUnrollBwd; ++u) Vec<VEC>::load(src + (int64_t)(c + u) * a.sc, x[u]);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kUnrollBwd; ++u) {
       float ck[K];
       centre_row<K>(sC, c + u, ck);
       float o[VEC];
@@ -480,7 +502,7 @@ ProtoArgs base_args(const float* feat, const slcl_map_t* m, const float* cstate)
 
 MarginConst make_const(const slcl_proto_params_t* p) {
   MarginConst mc;
-  mc.temperature = p->temperature;
+  mc.inv_t = (float)(1.0 / (double)p->temperature);
   mc.scale = p->temperature / p->base_temperature;
   mc.cos_m = (float)cos((double)p->margin);
   mc.sin_m = (float)sin((double)p->margin);

@@ -2,7 +2,7 @@
 import glob, os, re, subprocess, sys
 here = os.path.dirname(os.path.abspath(__file__))
 rows = []
-for log in sorted(glob.glob(os.path.join(here, "build", "*.ptxas.log"))):
+for log in sorted(glob.glob(os.path.join(here, "build", "libslcl", "*.ptxas.log"))):
     txt = open(log).read()
     for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?Function properties for \S+\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers(?:, used \d+ barriers)?(?:, (\d+) bytes smem)?", txt, re.S):
         rows.append((os.path.basename(log)[:-10], m.group(1), int(m.group(5)), int(m.group(2)), int(m.group(3)), int(m.group(6) or 0)))

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslcl.so")
+LIB_PATH = os.environ.get("SLCL_LIB_PATH", os.path.join(_HERE, "libslcl.so"))   # override: kernel-tuning variants
 
 SLCL_OK = 0
 MAX_CLASSES = 8

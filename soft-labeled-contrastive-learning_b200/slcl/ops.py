@@ -18,6 +18,24 @@ from ._lib import MapT, ProtoParamsT, check, ptr, require_cuda, stream_ptr
 _F32 = torch.float32
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def _guard(dev):
+    """Device guard only when the tensor's device is not the current one."""
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NOGUARD
+    return torch.cuda.device(dev)
+
+
 def _ws(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -85,7 +103,7 @@ def proto_fwd(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor
     nbytes = lib.slcl_proto_workspace_bytes(n)
     ws = _ws(nbytes, dev)
     p = _params(n_class, temperature, base_temperature, margin, easy_margin, normalize)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_proto_fwd(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(centres), C.byref(p),
                                 ptr(stash), ptr(cstate), ptr(scal), ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_proto_fwd")
@@ -104,7 +122,7 @@ def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, 
 def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     """Recompute scal[0:2] from the (all-reduced) sums scal[2:4], in place."""
     dev = require_cuda(scal)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = _lib.load().slcl_proto_rescale(ptr(scal), int(has_sel), stream_ptr(dev))
     check(st, "slcl_proto_rescale")
 
@@ -118,7 +136,7 @@ def proto_bwd(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_ou
     dfeat = torch.empty_strided(feat_c.shape, feat_c.stride(), dtype=_F32, device=dev)
     grad_out = grad_out.to(_F32).contiguous()
     p = _params(n_class, 1.0, 1.0, 0.0, False, normalize)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_proto_bwd(ptr(feat_c), C.byref(m), ptr(stash), ptr(cstate), ptr(scal), ptr(grad_out), C.byref(p),
                                 ptr(dfeat), stream_ptr(dev))
     check(st, "slcl_proto_bwd")
@@ -140,7 +158,7 @@ def proto_bwd_centres(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor,
     grad_out = grad_out.to(_F32).contiguous()
     ws = _ws(lib.slcl_proto_bwd_centres_workspace_bytes(m.batch * m.pixels, m.channels, n_class), dev)
     p = _params(n_class, 1.0, 1.0, 0.0, False, normalize)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_proto_bwd_centres(ptr(feat_c), C.byref(m), ptr(stash), ptr(cstate), ptr(scal), ptr(grad_out),
                                         C.byref(p), ptr(dcen), ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_proto_bwd_centres")
@@ -163,7 +181,7 @@ def pseudo_label(feat: Tensor, centres: Tensor, threshold: float) -> Tuple[Tenso
     label = torch.empty(n, dtype=torch.int64, device=dev)
     sel = torch.empty(n, dtype=_F32, device=dev)
     ws = _ws((k * m.channels + k) * 4, dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_pseudo_label(ptr(feat_c), C.byref(m), ptr(centres), k, float(threshold), ptr(label), ptr(sel),
                                    ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_pseudo_label")
@@ -208,7 +226,7 @@ def class_sums(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], 
     cols = n_partitions * n_class
     sums = torch.empty((cols, c + 1), dtype=torch.float64, device=dev)
     ws = _ws(lib.slcl_class_sums_workspace_bytes(b, c, h * w, cols), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_class_sums(ptr(feat), b, c, h * w, ptr(labels), ptr(probs), int(weighted), float(threshold),
                                  ptr(part_id), n_partitions, n_class, ptr(sums), ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_class_sums")
@@ -229,7 +247,7 @@ def ema_finalize(sums: Tensor, old_centres: Tensor, m: float) -> Tensor:
     if sums.dtype != torch.float64 or sums.shape != (k, c + 1):
         raise ValueError("sums must be float64 [K, C+1]")
     out = torch.empty_like(old)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_ema_finalize(ptr(sums.contiguous()), ptr(old), float(m), k, c, ptr(out), stream_ptr(dev))
     check(st, "slcl_ema_finalize")
     return out
@@ -256,7 +274,7 @@ def centroid_finalize(sums: Tensor, previous: Optional[Tensor], momentum: float,
             raise ValueError("previous centroid must be [K, C]")
     cen = torch.empty((rows, c), dtype=_F32, device=dev)
     inv_w = torch.empty(rows, dtype=_F32, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_centroid_finalize(ptr(sums), ptr(previous), float(momentum), n_sets, n_class, c, ptr(cen),
                                         ptr(inv_w), stream_ptr(dev))
     check(st, "slcl_centroid_finalize")
@@ -290,7 +308,7 @@ def centroid_bwd(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor]
     dfeat = torch.empty_like(feat)
     dprobs = torch.empty_like(probs) if (need_dprobs and probs is not None) else torch.empty(0, dtype=_F32, device=dev)
     ws = _ws(lib.slcl_centroid_bwd_workspace_bytes(c, cols), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_centroid_bwd(ptr(feat), b, c, h * w, ptr(labels), ptr(probs), int(weighted), float(threshold),
                                    ptr(part_id), n_partitions, n_class, ptr(g), ptr(sums.contiguous()), float(ema_scale),
                                    ptr(dfeat), ptr(dprobs) if dprobs.numel() else None, ptr(ws), ws.numel(),
@@ -320,7 +338,7 @@ def centroid_loss(centroid_s: Tensor, centroid_t: Tensor, mode: int, first_row: 
     loss = torch.empty(1, dtype=_F32, device=dev)
     ds = torch.empty_like(s)
     dt = torch.empty_like(t)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_centroid_loss(ptr(s), ptr(t), k, c, mode, first_row, n_rows, int(norm), ptr(loss), ptr(ds), ptr(dt),
                                     stream_ptr(dev))
     check(st, "slcl_centroid_loss")
@@ -348,7 +366,7 @@ def compact_by_class(labels: Tensor, n_class: int) -> Tuple[Tensor, Tensor, Tens
     offsets = torch.empty(n_class + 1, dtype=torch.int64, device=dev)
     index = torch.empty(n, dtype=torch.int64, device=dev)
     ws = _ws(lib.slcl_compact_workspace_bytes(n, n_class), dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_compact_by_class(ptr(lab), n, n_class, ptr(counts), ptr(offsets), ptr(index), ptr(ws), ws.numel(),
                                        stream_ptr(dev))
     check(st, "slcl_compact_by_class")
@@ -376,7 +394,7 @@ def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16
     rows_bf16 = torch.empty((r, c) if want_bf16 else (0, c), dtype=torch.bfloat16, device=dev)
     rows_f32 = torch.empty((r, c) if want_f32 else (0, c), dtype=_F32, device=dev)
     inv_norm = torch.empty(r, dtype=_F32, device=dev)
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_gather_unit_rows(ptr(feat), b, c, h * w, ptr(idx), r, int(normalize),
                                        ptr(rows_bf16) if want_bf16 else None, ptr(rows_f32) if want_f32 else None,
                                        ptr(inv_norm), stream_ptr(dev))
@@ -401,7 +419,7 @@ def scatter_rows_bwd(feat: Tensor, pixel_idx: Tensor, normalize: bool, d_rows: T
     b, c, h, w = feat.shape
     idx = pixel_idx.reshape(-1).contiguous()
     d_rows = d_rows.to(_F32).contiguous()
-    with torch.cuda.device(dev):
+    with _guard(dev):
         st = lib.slcl_scatter_rows_bwd(ptr(feat), b, c, h * w, ptr(idx), idx.numel(), int(normalize), ptr(d_rows),
                                        ptr(inv_norm), ptr(dfeat), stream_ptr(dev))
     check(st, "slcl_scatter_rows_bwd")

@@ -1,0 +1,86 @@
+"""Low-overhead launch plans over the C ABI.
+
+A plan owns every output / stash / workspace buffer of one fixed-shape call and
+pre-builds the ctypes argument list, so a step is a couple of raw C calls (a few
+microseconds of host time) instead of the torch custom-op dispatch path.  The
+launches are stream-ordered and allocation-free, so ``capture_graph()`` can
+record forward + backward into one CUDA graph for launch-bound shapes (cfg1:
+8 712 pixels).  The trainers' drop-in API (slcl.loss / slcl.utils_) does not need
+this; it exists for callers that drive the kernels every step on static shapes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MapT, ProtoParamsT, check, ptr
+from .ops import _map_nchw
+
+
+class ProtoPlan:
+    """Prototype-loss forward/backward (reference mpcl_loss_calc + MPCL.forward,
+    utils/loss.py:576-605,484-573) on fixed device buffers."""
+
+    def __init__(self, feat: torch.Tensor, labels: torch.Tensor, sel: Optional[torch.Tensor], centres: torch.Tensor,
+                 n_class: int, temperature: float, base_temperature: float, margin: float, easy_margin: bool = False,
+                 normalize: bool = True):
+        self.lib = _lib.load()
+        self.dev = _lib.require_cuda(feat, labels, sel, centres)
+        self.feat, self.map = _map_nchw(feat)
+        if self.feat.data_ptr() != feat.data_ptr():
+            raise ValueError("ProtoPlan needs a feature map whose H,W collapse to one stride (e.g. contiguous NCHW)")
+        n = self.map.batch * self.map.pixels
+        self.n_pixels = n
+        self.labels = labels.reshape(-1).contiguous()
+        self.sel = None if sel is None else sel.reshape(-1).float().contiguous()
+        self.centres = centres.float().contiguous()
+        if self.labels.dtype != torch.int64 or self.labels.numel() != n:
+            raise ValueError("labels must be int64 with B*H*W elements")
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.params = ProtoParamsT(int(n_class), float(temperature), float(base_temperature), float(margin),
+                                   int(easy_margin), int(normalize))
+        self.scal = torch.empty(4, **f32)
+        self.stash = torch.empty((n_class + 1, n), **f32)
+        self.cstate = torch.empty(n_class * self.map.channels + n_class, **f32)
+        self.ws = torch.empty(max(self.lib.slcl_proto_workspace_bytes(n), 256), dtype=torch.uint8, device=self.dev)
+        self.dfeat = torch.empty_strided(self.feat.shape, self.feat.stride(), **f32)
+        self.grad_out = torch.ones(1, **f32)
+        self._fwd_args = (ptr(self.feat), C.byref(self.map), ptr(self.labels), None, ptr(self.sel), ptr(self.centres),
+                          C.byref(self.params), ptr(self.stash), ptr(self.cstate), ptr(self.scal), ptr(self.ws),
+                          self.ws.numel())
+        self._bwd_args = (ptr(self.feat), C.byref(self.map), ptr(self.stash), ptr(self.cstate), ptr(self.scal),
+                          ptr(self.grad_out), C.byref(self.params), ptr(self.dfeat))
+        self.graph = None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def forward(self) -> torch.Tensor:
+        """Launch the forward; returns scal (scal[0] is the loss).  Asynchronous."""
+        check(self.lib.slcl_proto_fwd(*self._fwd_args, self._stream()), "slcl_proto_fwd")
+        return self.scal
+
+    def rescale(self) -> None:
+        check(self.lib.slcl_proto_rescale(ptr(self.scal), int(self.sel is not None), self._stream()), "slcl_proto_rescale")
+
+    def backward(self) -> torch.Tensor:
+        """Launch the backward for dL/dloss = grad_out (device scalar, default 1); returns dfeat."""
+        check(self.lib.slcl_proto_bwd(*self._bwd_args, self._stream()), "slcl_proto_bwd")
+        return self.dfeat
+
+    def capture_graph(self) -> "torch.cuda.CUDAGraph":
+        """Record forward + backward into one CUDA graph (replay with ``plan.graph.replay()``)."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.forward(); self.backward()          # warm-up outside capture
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+            self.backward()
+        self.graph = g
+        return g
