@@ -129,10 +129,11 @@ class ClockSampler:
     def start(self):
         if self.ok:
             self.thread.start()
+            self.started = True
 
     def stop(self):
         self.stop_flag.set()
-        if self.ok:
+        if self.ok and getattr(self, "started", False):
             self.thread.join(timeout=2)
 
     def summary(self, t0: float, t1: float):
@@ -437,10 +438,33 @@ def extra_kernels(dev, feats, labels, centres, peak):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_slcl(args)
+    # Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout) write to
+    # stderr while the benchmark runs; the real stdout is restored just for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+    orig_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            orig_print(*a, **k)
+    builtins.print = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_slcl(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":
