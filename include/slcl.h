@@ -185,8 +185,10 @@ int slcl_centroid_loss(const float* centroid_s, const float* centroid_t, int n_c
  * slcl_compact_by_class: stable compaction of pixel indices by label, order
  * bit-identical to torch.nonzero(labels == k) for every k.  counts [K] int64,
  * offsets [K+1] int64 (exclusive scan), index [N] int64 (class-major).
- * slcl_gather_unit_rows: rows pixel_idx of an NCHW map -> [R, C] L2-normalised
- * (eps 1e-12) bf16 and/or fp32 row-major, inverse norms [R] fp32.
+ * slcl_gather_unit_rows: rows pixel_idx of an NCHW map -> [R, C] fp32 and/or
+ * [R, bf16_row_stride] bf16 row-major (columns >= C zero-filled: the tensor-core
+ * kernel wants a multiple of 64), L2-normalised (eps 1e-12) when `normalize`;
+ * inv_norm [R] = 1/max(||x||, 1e-12) is written in both cases.
  * ------------------------------------------------------------------------- */
 size_t slcl_compact_workspace_bytes(int64_t n_pixels, int n_class);
 int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, int n_class,
@@ -194,12 +196,42 @@ int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, int n_class,
                           void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
                           const int64_t* pixel_idx, int64_t n_rows, int normalize,
-                          void* rows_bf16, float* rows_f32, float* inv_norm, slcl_stream_t stream);
+                          void* rows_bf16, int64_t bf16_row_stride, float* rows_f32, float* inv_norm,
+                          slcl_stream_t stream);
 /* scatter-add of row gradients back into an NCHW gradient map, through the
  * normalisation backward: dx = (g - xhat (xhat.g)) * inv_norm. */
 int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
                           const int64_t* pixel_idx, int64_t n_rows, int normalize,
                           const float* d_rows, const float* inv_norm, float* dfeat, slcl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Pixel <-> pixel supervised contrastive loss (SupConLoss.forward,
+ * utils/loss.py:327-387 = utils/losses.py:106-161, and its autograd backward;
+ * rectangular anchors x contrast-rows generalisation of SURVEY.md 8(c)-3).
+ * a [A, dp] anchors and b [M, dp] contrast rows: bf16 row-major, dp = dim_padded,
+ * a multiple of 64 <= 256 (pad columns zero).  Similarities S = a b^T / T run on
+ * tcgen05 tensor cores with fp32 TMEM accumulation; S is never written to memory.
+ *   a_meta / b_meta: int32 pairs {label, id} per row.  Pairs with equal id are the
+ *     self pairs (excluded, :365-371); pairs with equal label and different id are the
+ *     positives (:352-354,:368).  Unlabelled mode (:359-361): pass the pixel index
+ *     within the view as "label".
+ *   shift  [A] fp32: any upper bound of S_ij over j (e.g. ||a_i|| max_j||b_j|| / T);
+ *     exponentials are evaluated as exp(S - shift), the result is shift-invariant.
+ *   weight [A] fp32: w_i of the final reduction (fg_i / sum fg, :382-384, or 1/A).
+ * forward : stats [A,3] = {sum_j exp(S_ij - shift_i), sum_pos S_ij * T, #pos},
+ *           loss [1] = sum_i w_i (shift_i + log stats_i0 - stats_i1/(T stats_i2)).
+ * backward: d_a [A, dim] and/or d_b [M, dim] fp32 = dL/da, dL/db for dL/dloss = *grad_out
+ *           (either pointer may be null).
+ * ------------------------------------------------------------------------- */
+size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast, int64_t dim_padded);
+int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
+                 const int32_t* a_meta, const int32_t* b_meta, const float* shift, const float* weight,
+                 float temperature, float* stats, float* loss,
+                 void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
+                 int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const float* shift, const float* weight,
+                 float temperature, const float* stats, const float* grad_out, float* d_a, float* d_b,
+                 void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kThreads) compact_write_kernel(const int64_t* 
 // One warp per sampled row: gather C strided values, L2-normalise, write row-major.
 __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* feat, int64_t C, int64_t HW,
                                                                const int64_t* pixel_idx, int64_t n_rows, int normalize,
-                                                               __nv_bfloat16* out_bf16, float* out_f32, float* inv_norm) {
+                                                               __nv_bfloat16* out_bf16, int64_t bf16_stride, float* out_f32,
+                                                               float* inv_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -128,12 +129,16 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* feat
   float ss = 0.f;
   for (int64_t c = lane; c < C; c += 32) { float x = base[c * HW]; ss = fmaf(x, x, ss); }
   ss = warp_sum(ss);
-  const float inv = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
-  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+  const float inv_n = 1.0f / fmaxf(sqrtf(ss), 1e-12f);      // always reported: callers derive the exp shift from it
+  const float inv = normalize ? inv_n : 1.0f;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv_n;
   for (int64_t c = lane; c < C; c += 32) {
     float x = base[c * HW] * inv;       // second touch hits L1/L2 (the row's sectors were just loaded)
     if (out_f32) out_f32[row * C + c] = x;
-    if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(x);
+    if (out_bf16) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(x);
+  }
+  if (out_bf16) {
+    for (int64_t c = C + lane; c < bf16_stride; c += 32) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -192,13 +197,14 @@ extern "C" int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, in
 
 extern "C" int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
                                      const int64_t* pixel_idx, int64_t n_rows, int normalize, void* rows_bf16,
-                                     float* rows_f32, float* inv_norm, slcl_stream_t stream_) {
+                                     int64_t bf16_row_stride, float* rows_f32, float* inv_norm, slcl_stream_t stream_) {
   if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !pixel_idx || n_rows <= 0) return SLCL_ERR_INVALID_ARGUMENT;
   if (!rows_bf16 && !rows_f32) return SLCL_ERR_INVALID_ARGUMENT;
+  if (rows_bf16 && bf16_row_stride < channels) return SLCL_ERR_INVALID_ARGUMENT;
   const int blocks = (int)ceil_div<int64_t>(n_rows, kWarps);
   gather_rows_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream_>>>(feat, channels, pixels, pixel_idx, n_rows, normalize,
-                                                                    reinterpret_cast<__nv_bfloat16*>(rows_bf16), rows_f32,
-                                                                    inv_norm);
+                                                                    reinterpret_cast<__nv_bfloat16*>(rows_bf16),
+                                                                    bf16_row_stride, rows_f32, inv_norm);
   return check_launch("slcl_gather_unit_rows");
 }
 

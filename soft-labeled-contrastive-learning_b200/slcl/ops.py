@@ -383,6 +383,7 @@ def _(labels, n_class):
 @torch.library.custom_op("slcl::gather_unit_rows", mutates_args=(), device_types="cuda")
 def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16: bool,
                      want_f32: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (rows_bf16 [R, pad64(C)] (pad columns zero), rows_f32 [R, C], inv_norm [R])."""
     dev = require_cuda(feat, pixel_idx)
     lib = _lib.load()
     feat = _nchw_contig(feat)
@@ -391,12 +392,13 @@ def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16
     if idx.dtype != torch.int64:
         raise ValueError("pixel_idx must be int64")
     r = idx.numel()
-    rows_bf16 = torch.empty((r, c) if want_bf16 else (0, c), dtype=torch.bfloat16, device=dev)
+    cp = (c + 63) // 64 * 64
+    rows_bf16 = torch.empty((r, cp) if want_bf16 else (0, cp), dtype=torch.bfloat16, device=dev)
     rows_f32 = torch.empty((r, c) if want_f32 else (0, c), dtype=_F32, device=dev)
     inv_norm = torch.empty(r, dtype=_F32, device=dev)
     with _guard(dev):
         st = lib.slcl_gather_unit_rows(ptr(feat), b, c, h * w, ptr(idx), r, int(normalize),
-                                       ptr(rows_bf16) if want_bf16 else None, ptr(rows_f32) if want_f32 else None,
+                                       ptr(rows_bf16) if want_bf16 else None, cp, ptr(rows_f32) if want_f32 else None,
                                        ptr(inv_norm), stream_ptr(dev))
     check(st, "slcl_gather_unit_rows")
     return rows_bf16, rows_f32, inv_norm
@@ -405,7 +407,8 @@ def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16
 @gather_unit_rows.register_fake
 def _(feat, pixel_idx, normalize, want_bf16, want_f32):
     r, c = pixel_idx.numel(), feat.shape[1]
-    return (torch.empty((r if want_bf16 else 0, c), dtype=torch.bfloat16, device=feat.device),
+    cp = (c + 63) // 64 * 64
+    return (torch.empty((r if want_bf16 else 0, cp), dtype=torch.bfloat16, device=feat.device),
             torch.empty((r if want_f32 else 0, c), dtype=_F32, device=feat.device), feat.new_empty(r))
 
 
@@ -423,3 +426,71 @@ def scatter_rows_bwd(feat: Tensor, pixel_idx: Tensor, normalize: bool, d_rows: T
         st = lib.slcl_scatter_rows_bwd(ptr(feat), b, c, h * w, ptr(idx), idx.numel(), int(normalize), ptr(d_rows),
                                        ptr(inv_norm), ptr(dfeat), stream_ptr(dev))
     check(st, "slcl_scatter_rows_bwd")
+
+
+# ----------------------------------------------------------------------------
+# pixel <-> pixel (tensor cores)
+# ----------------------------------------------------------------------------
+def _p2p_check(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor):
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("anchors / contrast rows must be bf16 [rows, dim_padded] with equal dim_padded")
+    if a.shape[1] % 64 or a.shape[1] > 256:
+        raise ValueError("dim_padded must be a multiple of 64, at most 256")
+    if not (a.is_contiguous() and b.is_contiguous()):
+        raise ValueError("rows must be contiguous")
+    for m, t in ((a_meta, a), (b_meta, b)):
+        if m.dtype != torch.int32 or m.shape != (t.shape[0], 2) or not m.is_contiguous():
+            raise ValueError("meta must be contiguous int32 [rows, 2] = {label, id}")
+    if shift.shape != (a.shape[0],) or weight.shape != (a.shape[0],) or shift.dtype != _F32 or weight.dtype != _F32:
+        raise ValueError("shift / weight must be float32 [A]")
+
+
+@torch.library.custom_op("slcl::p2p_fwd", mutates_args=(), device_types="cuda")
+def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
+            temperature: float) -> Tuple[Tensor, Tensor]:
+    """-> (loss[1], stats[A,3])"""
+    dev = require_cuda(a, b, a_meta, b_meta, shift, weight)
+    lib = _lib.load()
+    _p2p_check(a, b, a_meta, b_meta, shift, weight)
+    na, dp = a.shape
+    m = b.shape[0]
+    stats = torch.empty((na, 3), dtype=_F32, device=dev)
+    loss = torch.empty(1, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
+    with _guard(dev):
+        st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(shift.contiguous()),
+                              ptr(weight.contiguous()), float(temperature), ptr(stats), ptr(loss), ptr(ws), ws.numel(),
+                              stream_ptr(dev))
+    check(st, "slcl_p2p_fwd")
+    return loss, stats
+
+
+@p2p_fwd.register_fake
+def _(a, b, a_meta, b_meta, shift, weight, temperature):
+    return shift.new_empty(1), shift.new_empty((a.shape[0], 3))
+
+
+@torch.library.custom_op("slcl::p2p_bwd", mutates_args=(), device_types="cuda")
+def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
+            temperature: float, stats: Tensor, grad_out: Tensor, need_a: bool, need_b: bool) -> Tuple[Tensor, Tensor]:
+    """-> (d_a [A, dim], d_b [M, dim]) fp32 (empty when not needed)."""
+    dev = require_cuda(a, b, a_meta, b_meta, shift, weight, stats, grad_out)
+    lib = _lib.load()
+    _p2p_check(a, b, a_meta, b_meta, shift, weight)
+    na, dp = a.shape
+    m = b.shape[0]
+    d_a = torch.empty((na, dim) if need_a else (0, dim), dtype=_F32, device=dev)
+    d_b = torch.empty((m, dim) if need_b else (0, dim), dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
+    g = grad_out.to(_F32).reshape(1).contiguous()
+    with _guard(dev):
+        st = lib.slcl_p2p_bwd(ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(shift.contiguous()),
+                              ptr(weight.contiguous()), float(temperature), ptr(stats.contiguous()), ptr(g),
+                              ptr(d_a) if need_a else None, ptr(d_b) if need_b else None, ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_p2p_bwd")
+    return d_a, d_b
+
+
+@p2p_bwd.register_fake
+def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b):
+    return (shift.new_empty((a.shape[0] if need_a else 0, dim)), shift.new_empty((b.shape[0] if need_b else 0, dim)))

@@ -1,13 +1,104 @@
-"""Pixel <-> pixel supervised contrastive losses (reference utils/loss.py:315-466,
-duplicated at utils/losses.py:95-239).  Placeholder module body is filled by the
-tensor-core path; see p2p kernels."""
+"""Pixel <-> pixel supervised contrastive losses on the tensor-core path.
+
+Drop-ins for the reference's ``SupConLoss`` / ``LocalConLoss`` / ``BlockConLoss``
+(utils/loss.py:315-466, duplicated at utils/losses.py:95-239) plus the sampled
+rectangular variant of SURVEY.md 8(c)-3 (``sampled_supcon_loss``).  Rows are
+gathered from the NCHW map into bf16 K-major rows, similarities run as
+tcgen05 GEMMs with fp32 accumulation and a fused soft-max epilogue; the M x M
+matrix of the reference (:342-349) is never materialised.
+"""
 from __future__ import annotations
+
+from typing import Optional
 
 import torch
 import torch.nn as nn
 
+from . import ops  # noqa: F401
+
+_ops = torch.ops.slcl
+
+
+class _P2PLoss(torch.autograd.Function):
+    """loss(feat) for anchor rows idx_a and contrast rows idx_b of an NCHW map (appendix A.6)."""
+
+    @staticmethod
+    def forward(ctx, feat, idx_a, idx_b, meta_a, meta_b, weight, temperature, normalize, same_rows):
+        fm = feat.detach().contiguous()
+        c = fm.shape[1]
+        b_bf16, _, inv_b = _ops.gather_unit_rows(fm, idx_b, normalize, True, False)
+        if same_rows:
+            a_bf16, inv_a = b_bf16, inv_b
+        else:
+            a_bf16, _, inv_a = _ops.gather_unit_rows(fm, idx_a, normalize, True, False)
+        if normalize:
+            shift = torch.full_like(inv_a, 1.0 / temperature)
+        else:   # upper bound of S_ij: |a_i| max_j |b_j| / T
+            shift = (1.0 / inv_a) * ((1.0 / inv_b).amax() / temperature)
+        loss, stats = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature)
+        ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats)
+        ctx.cfg = (temperature, normalize, same_rows, c)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats = ctx.saved_tensors
+        temperature, normalize, same_rows, c = ctx.cfg
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 9
+        d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
+                                grad_out.reshape(1), True, True)
+        dfeat = torch.zeros_like(fm)
+        _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
+        _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
+        return dfeat, None, None, None, None, None, None, None, None
+
+
+def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False):
+    meta_a = torch.stack([lab_a.to(torch.int32), id_a.to(torch.int32)], dim=1).contiguous()
+    meta_b = meta_a if same_rows else torch.stack([lab_b.to(torch.int32), id_b.to(torch.int32)], dim=1).contiguous()
+    return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
+                          float(temperature), bool(normalize), bool(same_rows))
+
+
+def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch.Tensor, device) -> torch.Tensor:
+    """Pixel indices (into the [b*v, c, h, w] memory-order map) of the reference's row order
+    ``cat(unbind(features, dim=1), dim=0)`` (utils/loss.py:337-343) restricted to rows ys, cols xs."""
+    grid = (ys.view(-1, 1) * w + xs.view(1, -1)).reshape(-1)                      # [hs*ws]
+    img = (torch.arange(b, device=device).view(1, -1) * v + torch.arange(v, device=device).view(-1, 1)).reshape(-1)
+    return (img.view(-1, 1) * (h * w) + grid.view(1, -1)).reshape(-1)             # (v, b, y, x) order
+
+
+def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False):
+    if features.ndim <= 3:                                                          # :334-336
+        raise ValueError('`features` needs to be [bsz, n_views, ...],'
+                         'at least 4 dimensions are required')
+    if features.ndim != 5:
+        raise ValueError("slcl SupConLoss expects [bsz, n_views, c, h, w] features")
+    b, v, c, h, w = features.shape
+    dev = features.device
+    fmap = features.reshape(b * v, c, h, w)
+    idx = _view_major_rows(b, v, h, w, ys, xs, dev)
+    m = idx.numel()
+    ids = torch.arange(m, device=dev, dtype=torch.int32)
+    if labels is not None:
+        lab_map = labels.reshape(-1)
+        lab = lab_map[idx].to(torch.int32)                                          # :352-353
+        fg = (lab != 0).float()                                                     # :356-358
+        denom = fg.sum()
+        if zero_if_no_foreground:      # LocalConLoss / BlockConLoss early-out (:405-407, :439-440), without a host sync
+            denom = denom.clamp_min(1.0)
+        weight = fg / denom                                                         # :382-384
+    else:
+        lab = (ids % (m // v)).to(torch.int32)                                      # :360-361 same pixel, other views
+        weight = torch.full((m,), 1.0 / m, device=dev)                              # :386
+    return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True)
+
 
 class SupConLoss(nn.Module):
+    """Reference utils/loss.py:315-387.  ``contrast_mode`` / ``base_temperature`` are stored and
+    unused there too."""
+
     def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07):
         super().__init__()
         self.temperature = temperature
@@ -15,24 +106,95 @@ class SupConLoss(nn.Module):
         self.base_temperature = base_temperature
 
     def forward(self, features, labels=None):
-        raise NotImplementedError("pixel<->pixel tensor-core path not built yet")
+        if features.ndim <= 3:
+            raise ValueError('`features` needs to be [bsz, n_views, ...],'
+                             'at least 4 dimensions are required')
+        h, w = features.shape[-2:]
+        dev = features.device
+        return _supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev))
 
 
 class LocalConLoss(nn.Module):
+    """Reference utils/loss.py:390-413: stride-subsampled SupCon."""
+
     def __init__(self, temperature=0.7, stride=4):
         super().__init__()
-        self.supconloss = SupConLoss(temperature=temperature)
+        self.temp = temperature
+        self.supconloss = SupConLoss(temperature=self.temp)
         self.stride = stride
 
     def forward(self, features, labels=None):
-        raise NotImplementedError("pixel<->pixel tensor-core path not built yet")
+        h, w = features.shape[-2:]
+        dev = features.device
+        ys = torch.arange(0, h, self.stride, device=dev)
+        xs = torch.arange(0, w, self.stride, device=dev)
+        return _supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True)
 
 
 class BlockConLoss(nn.Module):
+    """Reference utils/loss.py:416-466: mean of SupCon over block_size x block_size tiles; tiles whose
+    labels are all background are skipped (decided on the device, no per-tile host sync)."""
+
     def __init__(self, temperature=0.7, block_size=32):
         super().__init__()
         self.block_size = block_size
         self.supconloss = SupConLoss(temperature=temperature)
 
     def forward(self, features, labels=None):
-        raise NotImplementedError("pixel<->pixel tensor-core path not built yet")
+        dev = features.device
+        bs = self.block_size
+        div = features.shape[-1] // bs                                               # :426-428
+        t = self.supconloss.temperature
+        losses, flags = [], []
+        for i in range(div):
+            for j in range(div):
+                ys = torch.arange(i * bs, (i + 1) * bs, device=dev)
+                xs = torch.arange(j * bs, (j + 1) * bs, device=dev)
+                losses.append(_supcon(features, labels, t, ys, xs, zero_if_no_foreground=True))
+                if labels is not None:
+                    flags.append((labels[:, :, i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] != 0).any())
+        if not losses:
+            return torch.zeros((), device=dev)
+        stacked = torch.stack(losses)
+        if labels is None:
+            return stacked.mean()                                                    # :465
+        keep = torch.stack(flags).float()
+        return (stacked * keep).sum() / keep.sum().clamp_min(1.0)                    # :445-448 (0 when every tile is skipped)
+
+
+def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
+                          generator: Optional[torch.Generator] = None):
+    """Class-balanced sampler.  Per class k the candidate list is the stable
+    compaction ``nonzero(labels == k)`` (CUDA kernel, bit-exact order); the picks are the first
+    ceil(n/K) entries of ``torch.randperm(count_k, generator)`` -- PyTorch's own RNG stream.
+    Anchors are a prefix of the contrast picks of their class.  Returns (anchor_idx, contrast_idx)."""
+    lab = labels.reshape(-1).long()
+    counts, offsets, index = _ops.compact_by_class(lab, n_class)
+    counts_h = counts.cpu().tolist()           # one host sync: randperm needs the sizes
+    offs_h = [0]
+    for cnt in counts_h:
+        offs_h.append(offs_h[-1] + cnt)
+    per_a = -(-n_anchor // n_class)
+    per_c = -(-n_contrast // n_class)
+    gen_dev = generator.device if generator is not None else torch.device("cpu")
+    a_parts, c_parts = [], []
+    for k in range(n_class):
+        perm = torch.randperm(counts_h[k], generator=generator, device=gen_dev).to(lab.device)
+        picks = index[offs_h[k] + perm[:per_c]]
+        c_parts.append(picks)
+        a_parts.append(picks[:per_a])
+    return torch.cat(a_parts), torch.cat(c_parts)
+
+
+def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
+                        temperature: float = 0.7, generator: Optional[torch.Generator] = None,
+                        anchor_idx: Optional[torch.Tensor] = None, contrast_idx: Optional[torch.Tensor] = None):
+    """Sampled rectangular pixel <-> pixel loss (BASELINE.json configs[2]): anchors x contrast rows
+    drawn class-balanced from an NCHW map, L2-normalised, bf16 tensor-core similarities."""
+    if anchor_idx is None or contrast_idx is None:
+        anchor_idx, contrast_idx = sample_class_balanced(labels, n_anchor, n_contrast, n_class, generator)
+    lab = labels.reshape(-1)
+    la, lb = lab[anchor_idx], lab[contrast_idx]
+    fg = (la != 0).float()
+    weight = fg / fg.sum()
+    return p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True)
