@@ -211,7 +211,9 @@ int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, in
  * a [A, dp] anchors and b [M, dp] contrast rows: bf16 row-major, dp = dim_padded,
  * a multiple of 64 <= 256 (pad columns zero).  Similarities S = a b^T / T run on
  * tcgen05 tensor cores with fp32 TMEM accumulation; S is never written to memory.
- *   a_meta / b_meta: int32 pairs {label, id} per row.  Pairs with equal id are the
+ *   a_meta / b_meta: int32 pairs {label, id} per row, each array PADDED to a multiple of 64
+ *     entries with {INT_MIN, INT_MIN} (the kernel fetches whole 64-entry tiles with bulk
+ *     copies), 16-byte aligned.  Pairs with equal id are the
  *     self pairs (excluded, :365-371); pairs with equal label and different id are the
  *     positives (:352-354,:368).  Unlabelled mode (:359-361): pass the pixel index
  *     within the view as "label".

@@ -22,6 +22,8 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <limits.h>
+#include <stdlib.h>
 #include <math.h>
 
 namespace slcl {
@@ -45,6 +47,7 @@ struct P2PArgs {
   int n_rows, n_cols, d;              // d padded to a multiple of 64
   int col_begin, cols_per_split;      // this kernel instance sweeps columns [col_begin + split*cols_per_split, ...)
   int mode;
+  int debug;                          // bring-up knobs (SLCL_P2P_DEBUG): 1 skip epilogue math, 2 skip tmem load, 4 skip MMA1
   float scale_log2;                   // log2(e) / T
   const int2* row_meta;               // {label, id}
   const int2* col_meta;
@@ -52,6 +55,7 @@ struct P2PArgs {
   const float4* col_stat;             // kBwdCols: {shift*log2e, alpha, beta, -}
   float* stat_partial;                // kFwd: [n_slots][n_rows][3]  (Zs, P_raw, n)
   float* grad_partial;                // bwd:  [n_splits][n_rows][d] fp32
+  unsigned long long* prof;           // bring-up: per-role wait-cycle counters of CTA (0,0), or null
 };
 
 // --------------------------- PTX wrappers ----------------------------------
@@ -78,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -89,6 +98,32 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// same, multicast: the box lands at the same CTA-relative offset (and signals the same CTA-relative
+// mbarrier) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -117,6 +152,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// same, arriving on the barrier at this CTA-relative offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -129,6 +171,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (SM100 UMMA), 128-byte swizzle.
@@ -151,12 +199,23 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn_major) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+// Column metadata of one 64-column tile.  The TMA producer brings it in with 1-D bulk copies into a
+// kMetaSlots-deep ring of its own (the epilogue reads it after the tile's smem stage has already been
+// handed back), so the epilogue warps never issue a global load.  The caller pads the metadata arrays
+// to a multiple of 64 entries; pad entries carry id INT_MIN (masked).
+constexpr int kMetaSlots = 4;
+struct __align__(128) ColMeta {
+  float4 stat[BN];      // kBwdCols: {shift*log2e, alpha, beta, -}
+  int2 meta[BN];        // {label, id}
+};
+
 struct __align__(8) Barriers {
   uint64_t r_full;
   uint64_t c_full[kStages], c_empty[kStages];
   uint64_t s_full[2], s_empty[2];
   uint64_t g_full[2], g_empty[2];
   uint64_t acc_full;
+  uint64_t m_full[kMetaSlots], m_empty[kMetaSlots];
   uint32_t tmem_base;
 };
 
@@ -166,9 +225,14 @@ struct __align__(8) Barriers {
 //   G   : [2][128 rows][128 B]
 __host__ __device__ inline size_t smem_bytes_for(int d) {
   const size_t kc = d / KCH;
-  return 1024 /*align slack*/ + kc * BM * 128 + (size_t)kStages * kc * BN * 128 + 2 * BM * 128 + sizeof(Barriers) + 64;
+  return 1024 /*align slack*/ + kc * BM * 128 + (size_t)kStages * kc * BN * 128 + 2 * BM * 128 + kMetaSlots * sizeof(ColMeta) +
+         sizeof(Barriers) + 64;
 }
 
+// CS = thread-block-cluster size along the row-tile axis.  The CS CTAs of a cluster sweep the same
+// column tiles in lock step: each one fetches 1/CS of every column tile and TMA-multicasts it to all,
+// so the L2 -> SM traffic of the streamed operand drops CS-fold.
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -177,7 +241,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   uint8_t* sR = base;
   uint8_t* sC = sR + (size_t)kc * BM * 128;
   uint8_t* sG = sC + (size_t)kStages * kc * BN * 128;
-  Barriers* bars = reinterpret_cast<Barriers*>(sG + 2 * BM * 128);
+  ColMeta* sMeta = reinterpret_cast<ColMeta*>(sG + 2 * BM * 128);
+  Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * BM;
@@ -186,12 +251,18 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   const int col_end = min(a.n_cols, col0 + a.cols_per_split);
   const int n_tiles = (col_end - col0 + BN - 1) / BN;
   const bool bwd = a.mode != kFwd;
+  // Every CTA sweeps the same column tiles; start each one at a different tile so the CTAs do not
+  // all hit the same L2 lines at the same moment (the sums do not depend on the sweep order).
+  const int rot = (int)(((blockIdx.x / CS) * 37u + blockIdx.y * 11u) % (unsigned)n_tiles);
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
+  auto tile_col = [&](int t) { int tt = t + rot; if (tt >= n_tiles) tt -= n_tiles; return col0 + tt * BN; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_rows);
     tma_prefetch_desc(&map_cols);
     mbar_init(&bars->r_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->c_full[s], 1); mbar_init(&bars->c_empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->c_full[s], 1); mbar_init(&bars->c_empty[s], CS); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
       mbar_init(&bars->s_empty[s], kEpiWarps);
@@ -199,25 +270,50 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       mbar_init(&bars->g_empty[s], 1);
     }
     mbar_init(&bars->acc_full, 1);
+    for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&bars->m_full[s], 1); mbar_init(&bars->m_empty[s], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();          // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      unsigned long long w0 = 0, w1 = 0;
+      const long long tstart = clock64();
       mbar_expect_tx(&bars->r_full, (uint32_t)kc * BM * 128);
       for (int c = 0; c < kc; ++c) tma_load_2d(sR + (size_t)c * BM * 128, &map_rows, &bars->r_full, c * KCH, row0);
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % kStages;
-        mbar_wait(&bars->c_empty[s], ((t / kStages) & 1) ^ 1);
+        mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ 1, w0);
+        if (a.debug & 8) { mbar_arrive(&bars->c_full[s]); goto meta_part; }
         mbar_expect_tx(&bars->c_full[s], (uint32_t)kc * BN * 128);
+        {
         uint8_t* dst = sC + (size_t)s * kc * BN * 128;
-        for (int c = 0; c < kc; ++c) tma_load_2d(dst + (size_t)c * BN * 128, &map_cols, &bars->c_full[s], c * KCH, col0 + t * BN);
+        if (CS == 1) {
+          for (int c = 0; c < kc; ++c) tma_load_2d(dst + (size_t)c * BN * 128, &map_cols, &bars->c_full[s], c * KCH, tile_col(t));
+        } else {
+          constexpr int kSlice = BN / CS;        // rows of the tile this CTA fetches for the whole cluster
+          for (int c = 0; c < kc; ++c)
+            tma_load_2d_mc(dst + (size_t)c * BN * 128 + (size_t)crank * kSlice * 128, &map_cols, &bars->c_full[s], c * KCH,
+                           tile_col(t) + (int)crank * kSlice, kAllCtas);
+        }
+        }
+      meta_part:
+        if (a.debug & 16) continue;
+        const int ms = t % kMetaSlots;
+        mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
+        const bool with_stat = a.mode == kBwdCols;
+        mbar_expect_tx(&bars->m_full[ms], (uint32_t)(BN * sizeof(int2) + (with_stat ? BN * sizeof(float4) : 0)));
+        bulk_load_1d(sMeta[ms].meta, a.col_meta + tile_col(t), BN * sizeof(int2), &bars->m_full[ms]);
+        if (with_stat) bulk_load_1d(sMeta[ms].stat, a.col_stat + tile_col(t), BN * sizeof(float4), &bars->m_full[ms]);
+      }
+      if (a.prof && blockIdx.x == 0 && blockIdx.y == 0) {
+        a.prof[0] = (unsigned long long)(clock64() - tstart); a.prof[1] = w0; a.prof[2] = w1;
       }
     }
   } else if (warp == 1) {
@@ -226,41 +322,53 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       const uint32_t idesc1 = make_idesc(BN, 0);
       const uint32_t idesc2 = make_idesc(a.d, 1);
       const uint32_t r_addr = smem_u32(sR), c_addr = smem_u32(sC), g_addr = smem_u32(sG);
+      unsigned long long w0 = 0, w1 = 0, w2 = 0;
+      const long long tstart = clock64();
       mbar_wait(&bars->r_full, 0);
+      // Descriptors are built once; inside the loops only the 14-bit start-address field moves
+      // (all operand addresses are < 256 KB, so adding (bytes >> 4) to the low word never carries out).
+      const uint64_t descR = make_desc(r_addr, 16, 1024);
+      const uint64_t descC = make_desc(c_addr, 16, 1024);              // K-major view of a column tile (MMA1)
+      const uint64_t descCmn = make_desc(c_addr, BN * 128, 1024);      // MN-major view of the same bytes (MMA2)
+      const uint64_t descG = make_desc(g_addr, 16, 1024);
+      const uint32_t stage_units = (uint32_t)(kc * BN * 128) >> 4;
       for (int t = 0; t <= n_tiles; ++t) {
         if (t < n_tiles) {
           const int s = t % kStages, buf = t & 1;
-          mbar_wait(&bars->c_full[s], (t / kStages) & 1);
-          mbar_wait(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1);
+          mbar_wait_t(&bars->c_full[s], (t / kStages) & 1, w0);
+          mbar_wait_t(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1, w1);
           tc_fence_after();
+          if (a.debug & 32) { mbar_arrive(&bars->s_full[buf]); mbar_arrive(&bars->c_empty[s]); continue; }   // CS==1, fwd only
           // S[buf] = R_tile . Cm_tile^T : both operands K-major, 128-byte swizzle, 16 bf16 (32 B) per K step
+          const uint32_t d_tmem = tmem + kColS + buf * BN;
+          uint64_t da = descR, db = descC + (uint64_t)(s * stage_units);
           for (int c = 0; c < kc; ++c) {
-            const uint32_t ra = r_addr + (uint32_t)c * BM * 128;
-            const uint32_t ca = c_addr + (uint32_t)(s * kc + c) * BN * 128;
 #pragma unroll
             for (int k = 0; k < KCH / 16; ++k)
-              umma_bf16(tmem + kColS + buf * BN, make_desc(ra + k * 32, 16, 1024), make_desc(ca + k * 32, 16, 1024), idesc1,
-                        (c | k) != 0);
+              if (!(a.debug & 4)) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc1, (c | k) != 0);
+            da += (BM * 128) >> 4;
+            db += (BN * 128) >> 4;
           }
           umma_commit(&bars->s_full[buf]);
-          if (!bwd) umma_commit(&bars->c_empty[s]);
+          if (!bwd) { if (CS == 1) umma_commit(&bars->c_empty[s]); else umma_commit_mc(&bars->c_empty[s], kAllCtas); }
         }
         if (bwd && t > 0) {
           // dR += G(t-1)[128 x 64] . Cm_tile(t-1)[64 x d] : A = G K-major; B = Cm tile as MN-major operand
           const int tp = t - 1, sp = tp % kStages, bp = tp & 1;
-          mbar_wait(&bars->g_full[bp], (tp >> 1) & 1);
+          mbar_wait_t(&bars->g_full[bp], (tp >> 1) & 1, w2);
           tc_fence_after();
-          const uint32_t ga = g_addr + (uint32_t)bp * BM * 128;
-          const uint32_t ca = c_addr + (uint32_t)(sp * kc) * BN * 128;
+          const uint64_t dg = descG + (uint64_t)(bp * ((BM * 128) >> 4));
+          const uint64_t dc = descCmn + (uint64_t)(sp * stage_units);
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k)
-            umma_bf16(tmem + kColAcc, make_desc(ga + k * 32, 16, 1024), make_desc(ca + k * 2048, BN * 128, 1024), idesc2,
-                      (tp | k) != 0);
+          for (int k = 0; k < BN / 16; ++k) umma_bf16(tmem + kColAcc, dg + 2 * k, dc + k * (2048 >> 4), idesc2, (tp | k) != 0);
           umma_commit(&bars->g_empty[bp]);
-          umma_commit(&bars->c_empty[sp]);
+          if (CS == 1) umma_commit(&bars->c_empty[sp]); else umma_commit_mc(&bars->c_empty[sp], kAllCtas);
         }
       }
       if (bwd) umma_commit(&bars->acc_full);
+      if (a.prof && blockIdx.x == 0 && blockIdx.y == 0) {
+        a.prof[4] = (unsigned long long)(clock64() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: one thread per row, 32 of the 64 tile columns per warp =====================
@@ -269,37 +377,44 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     const int r_local = q * 32 + lane;
     const int row = row0 + r_local;
     const bool row_ok = row < a.n_rows;
-    const int2 rm = row_ok ? a.row_meta[row] : make_int2(-1, -1);
+    const int2 rm = row_ok ? a.row_meta[row] : make_int2(INT_MIN + 1, INT_MIN + 1);
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.mode != kBwdCols && row_ok) rs = a.row_stat[row];
     float zs = 0.f, praw = 0.f, npos = 0.f;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;
+    const long long tstart = clock64();
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
-
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int jbase = col0 + t * BN + half * 32;
-      mbar_wait(&bars->s_full[buf], (t >> 1) & 1);
+      const int ms = t % kMetaSlots;
+      const ColMeta& cmeta = sMeta[ms];
+      if (!(a.debug & 16)) mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
+      mbar_wait_t(&bars->s_full[buf], (t >> 1) & 1, w1);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem + lane_addr + kColS + buf * BN + half * 32, v);
-      tmem_ld_wait();
+      if (!(a.debug & 2)) {
+        tmem_ld32(tmem + lane_addr + kColS + buf * BN + half * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0x3f000000u + i;
+      }
       // S buffer is free as soon as it sits in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[buf]);
 
-      if (!bwd) {
+      if ((a.debug & 1) && !bwd) {
+        zs += __uint_as_float(v[0]) + __uint_as_float(v[31]);
+      } else if (!bwd) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const int j = jbase + jj;
-          const int2 cm = (j < col_end) ? __ldg(&a.col_meta[j]) : make_int2(-2, rm.y);      // out of range == self
+          const int2 cm = cmeta.meta[half * 32 + jj];
           const float s = __uint_as_float(v[jj]);
-          const bool valid = cm.y != rm.y;
-          const bool pos = valid && (cm.x == rm.x);
-          const float e = exp2f(fmaf(s, a.scale_log2, -rs.x));
-          zs += valid ? e : 0.f;
-          praw += pos ? s : 0.f;
-          npos += pos ? 1.f : 0.f;
+          const float e = ex2_approx(fmaf(s, a.scale_log2, -rs.x));
+          const bool valid = (cm.y != rm.y) && (cm.y != INT_MIN);
+          if (valid) zs += e;
+          if (valid && cm.x == rm.x) { praw += s; npos += 1.f; }
         }
       } else {
         uint32_t packed[16];
@@ -308,23 +423,19 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           float g2[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int j = jbase + jj + u;
-            const bool in = j < col_end;
-            const int2 cm = in ? __ldg(&a.col_meta[j]) : make_int2(-2, rm.y);
+            const int2 cm = cmeta.meta[half * 32 + jj + u];
             float4 st = rs;
-            if (a.mode == kBwdCols) st = in ? __ldg(&a.col_stat[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.mode == kBwdCols) st = cmeta.stat[half * 32 + jj + u];
             const float s = __uint_as_float(v[jj + u]);
-            const bool valid = (cm.y != rm.y) && row_ok;
-            const bool pos = cm.x == rm.x;
-            float g = st.y * exp2f(fmaf(s, a.scale_log2, -st.x));
-            g -= pos ? st.z : 0.f;
-            g2[u] = valid ? g : 0.f;
+            const float e = ex2_approx(fmaf(s, a.scale_log2, -st.x));
+            const float g = fmaf(st.y, e, (cm.x == rm.x) ? -st.z : 0.f);
+            g2[u] = ((cm.y != rm.y) && (cm.y != INT_MIN)) ? g : 0.f;
           }
           __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
           packed[jj >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         // G tile -> smem as a K-major, 128-byte-swizzled A operand: row r_local, 16-byte chunk (half*4 + i) ^ (r_local & 7)
-        mbar_wait(&bars->g_empty[buf], ((t >> 1) & 1) ^ 1);
+        mbar_wait_t(&bars->g_empty[buf], ((t >> 1) & 1) ^ 1, w2);
         uint8_t* grow = sG + (size_t)buf * BM * 128 + (size_t)r_local * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -336,8 +447,14 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->g_full[buf]);
       }
+      __syncwarp();
+      if (lane == 0 && !(a.debug & 16)) mbar_arrive(&bars->m_empty[ms]);
     }
 
+    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
+      unsigned long long* pp = a.prof + (warp == 4 ? 8 : 12);
+      pp[0] = (unsigned long long)(clock64() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = w2;
+    }
     if (!bwd) {
       if (row_ok) {
         float* out = a.stat_partial + ((size_t)(split * 2 + half) * a.n_rows + row) * 3;
@@ -363,6 +480,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     }
   }
   __syncthreads();
+  if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);
@@ -372,26 +490,38 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
 // ---------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------
-// stats[i] = sum over slots of partial (deterministic order)
-__global__ void p2p_reduce_stats_kernel(const float* partial, int n_slots, int n_rows, float* stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows * 3) return;
-  float t = 0.f;
-  for (int s = 0; s < n_slots; ++s) t += partial[(size_t)s * n_rows * 3 + i];
-  stats[i] = t;
+// stats[i] = sum over slots of partial (deterministic order); also the per-block partial of
+// sum_i w_i * (shift_i + log(Zs_i) - P_i / n_i),  P_i = P_raw_i / T     (utils/loss.py:371-386)
+__global__ void __launch_bounds__(256) p2p_reduce_stats_kernel(const float* partial, int n_slots, int n_rows, const float* shift,
+                                                               const float* weight, float inv_t, float* stats,
+                                                               double* loss_partial) {
+  __shared__ double red[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double acc = 0.0;
+  if (i < n_rows) {
+    float t[3] = {0.f, 0.f, 0.f};
+    for (int s = 0; s < n_slots; ++s) {
+      const float* p = partial + ((size_t)s * n_rows + i) * 3;
+      t[0] += p[0]; t[1] += p[1]; t[2] += p[2];
+    }
+    stats[3 * i] = t[0]; stats[3 * i + 1] = t[1]; stats[3 * i + 2] = t[2];
+    const float li = shift[i] + logf(t[0]) - (t[1] * inv_t) / t[2];     // n == 0 -> NaN, as 0/0 in the reference (:376-380)
+    acc = (double)(weight[i] * li);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    loss_partial[blockIdx.x] = t;
+  }
 }
 
-// loss = sum_i w_i * (shift_i + log(Zs_i) - P_i / n_i),  P_i = P_raw_i / T     (utils/loss.py:371-386)
-__global__ void __launch_bounds__(256) p2p_loss_kernel(const float* stats, const float* shift, const float* weight, int n,
-                                                        float inv_t, float* loss) {
+__global__ void __launch_bounds__(256) p2p_loss_kernel(const double* loss_partial, int n_blocks, float* loss) {
   __shared__ double red[8];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float w = weight[i];
-    const float zs = stats[3 * i], p = stats[3 * i + 1] * inv_t, np = stats[3 * i + 2];
-    const float li = shift[i] + logf(zs) - p / np;          // np == 0 -> NaN, as 0/0 in the reference (:376-380)
-    acc += (double)(w * li);
-  }
+  for (int i = threadIdx.x; i < n_blocks; i += 256) acc += loss_partial[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -404,9 +534,10 @@ __global__ void __launch_bounds__(256) p2p_loss_kernel(const float* stats, const
 
 // per-anchor backward constants {shift*log2e, alpha, beta, 0}: alpha = g w /(T Zs), beta = g w /(T n)
 __global__ void p2p_anchor_stat_kernel(const float* stats, const float* shift, const float* weight, const float* grad_out,
-                                       int n, float inv_t, int with_grad, float4* out) {
+                                       int n, int n_padded, float inv_t, int with_grad, float4* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n_padded) return;
+  if (i >= n) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); return; }      // pad entries (bulk-copied as column stats)
   float4 o = make_float4(shift[i] * kLog2e, 0.f, 0.f, 0.f);
   if (with_grad) {
     const float gw = grad_out[0] * weight[i] * inv_t;
@@ -463,7 +594,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_r
   return SLCL_OK;
 }
 
-struct Sweep { int row_tiles, splits, cols_per_split; };
+struct Sweep { int row_tiles, splits, cols_per_split, cluster; };
 
 Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   Sweep s;
@@ -474,6 +605,8 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
   s.cols_per_split = tiles_per_split * BN;
+  s.cluster = s.row_tiles >= 4 ? 4 : (s.row_tiles >= 2 ? 2 : 1);
+  { const char* e = getenv("SLCL_P2P_CLUSTER"); if (e) s.cluster = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1); }   // tuning knob
   return s;
 }
 
@@ -483,23 +616,45 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   CUtensorMap mr, mc;
   int st = make_map(&mr, rows, n_rows, d, BM);
   if (st != SLCL_OK) return st;
-  st = make_map(&mc, cols, n_cols, d, BN);
+  st = make_map(&mc, cols, n_cols, d, BN / sw.cluster);
   if (st != SLCL_OK) return st;
   P2PArgs a{};
   a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
   a.col_begin = 0; a.cols_per_split = sw.cols_per_split;
   a.mode = mode;
+  { const char* e = getenv("SLCL_P2P_DEBUG"); a.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   a.scale_log2 = inv_t * kLog2e;
   a.row_meta = row_meta; a.col_meta = col_meta; a.row_stat = row_stat; a.col_stat = col_stat;
   a.stat_partial = stat_partial; a.grad_partial = grad_partial;
   const size_t smem = smem_bytes_for(d);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(kMaxD));
+    const int mx = (int)smem_bytes_for(kMaxD);
+    cudaError_t e = cudaFuncSetAttribute(p2p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
-  p2p_kernel<<<dim3(sw.row_tiles, sw.splits), kThreads, smem, stream>>>(mr, mc, a);
+  const int cs = sw.cluster;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ceil_div(sw.row_tiles, cs) * cs), (unsigned)sw.splits, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
+  if (cs == 4) le = cudaLaunchKernelEx(&cfg, p2p_kernel<4>, mr, mc, a);
+  else if (cs == 2) le = cudaLaunchKernelEx(&cfg, p2p_kernel<2>, mr, mc, a);
+  else le = cudaLaunchKernelEx(&cfg, p2p_kernel<1>, mr, mc, a);
+  if (le != cudaSuccess) { set_cuda_error(le, "cudaLaunchKernelEx(p2p_kernel)"); return SLCL_ERR_CUDA; }
   return check_launch("p2p_kernel");
 }
 
@@ -517,7 +672,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   size_t o1 = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
-  size_t o2 = take((size_t)na * sizeof(float4));
+  size_t o2 = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
   size_t o3 = take((size_t)sa.splits * na * d * sizeof(float));
   size_t o4 = take((size_t)sb.splits * m * d * sizeof(float));
   P2PWs w;
@@ -559,13 +714,17 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   P2PWs w = carve(workspace, n_anchor, n_contrast, d);
   const float inv_t = 1.0f / temperature;
   const int na = (int)n_anchor;
-  p2p_anchor_stat_kernel<<<ceil_div(na, 256), 256, 0, stream>>>(nullptr, shift, weight, nullptr, na, inv_t, 0, w.anchor_stat);
+  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(nullptr, shift, weight, nullptr, na, (int)align_up((size_t)na, BN), inv_t, 0,
+                                                                     w.anchor_stat);
   Sweep sw = plan_sweep(n_anchor, n_contrast);
   int st = launch_sweep(a_bf16, n_anchor, b_bf16, n_contrast, d, kFwd, inv_t, reinterpret_cast<const int2*>(a_meta),
                         reinterpret_cast<const int2*>(b_meta), w.anchor_stat, nullptr, w.stat_partial, nullptr, sw, stream);
   if (st != SLCL_OK) return st;
-  p2p_reduce_stats_kernel<<<ceil_div(na * 3, 256), 256, 0, stream>>>(w.stat_partial, 2 * sw.splits, na, stats);
-  p2p_loss_kernel<<<1, 256, 0, stream>>>(stats, shift, weight, na, inv_t, loss);
+  // the forward no longer needs grad_partial_a: its head doubles as the per-block loss partials
+  double* loss_partial = reinterpret_cast<double*>(w.grad_partial_a);
+  const int nb = ceil_div(na, 256);
+  p2p_reduce_stats_kernel<<<nb, 256, 0, stream>>>(w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats, loss_partial);
+  p2p_loss_kernel<<<1, 256, 0, stream>>>(loss_partial, nb, loss);
   return check_launch("slcl_p2p_fwd");
 }
 
@@ -583,7 +742,8 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   P2PWs w = carve(workspace, n_anchor, n_contrast, d);
   const float inv_t = 1.0f / temperature;
   const int na = (int)n_anchor;
-  p2p_anchor_stat_kernel<<<ceil_div(na, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, inv_t, 1, w.anchor_stat);
+  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, (int)align_up((size_t)na, BN), inv_t, 1,
+                                                                     w.anchor_stat);
   const int2* am = reinterpret_cast<const int2*>(a_meta);
   const int2* bm = reinterpret_cast<const int2*>(b_meta);
   if (d_a) {

@@ -431,6 +431,15 @@ def scatter_rows_bwd(feat: Tensor, pixel_idx: Tensor, normalize: bool, d_rows: T
 # ----------------------------------------------------------------------------
 # pixel <-> pixel (tensor cores)
 # ----------------------------------------------------------------------------
+def pad_meta(label: Tensor, ident: Tensor) -> Tensor:
+    """{label, id} int32 pairs padded to a multiple of 64 rows with INT_MIN (the kernel's masked sentinel)."""
+    n = label.numel()
+    out = torch.full(((n + 63) // 64 * 64, 2), -2 ** 31, dtype=torch.int32, device=label.device)
+    out[:n, 0] = label.to(torch.int32)
+    out[:n, 1] = ident.to(torch.int32)
+    return out
+
+
 def _p2p_check(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor):
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
         raise ValueError("anchors / contrast rows must be bf16 [rows, dim_padded] with equal dim_padded")
@@ -439,8 +448,8 @@ def _p2p_check(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tens
     if not (a.is_contiguous() and b.is_contiguous()):
         raise ValueError("rows must be contiguous")
     for m, t in ((a_meta, a), (b_meta, b)):
-        if m.dtype != torch.int32 or m.shape != (t.shape[0], 2) or not m.is_contiguous():
-            raise ValueError("meta must be contiguous int32 [rows, 2] = {label, id}")
+        if m.dtype != torch.int32 or m.shape != ((t.shape[0] + 63) // 64 * 64, 2) or not m.is_contiguous():
+            raise ValueError("meta must be contiguous int32 [pad64(rows), 2] = {label, id} (see pad_meta)")
     if shift.shape != (a.shape[0],) or weight.shape != (a.shape[0],) or shift.dtype != _F32 or weight.dtype != _F32:
         raise ValueError("shift / weight must be float32 [A]")
 

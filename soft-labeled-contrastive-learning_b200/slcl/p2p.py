@@ -55,8 +55,8 @@ class _P2PLoss(torch.autograd.Function):
 
 
 def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False):
-    meta_a = torch.stack([lab_a.to(torch.int32), id_a.to(torch.int32)], dim=1).contiguous()
-    meta_b = meta_a if same_rows else torch.stack([lab_b.to(torch.int32), id_b.to(torch.int32)], dim=1).contiguous()
+    meta_a = ops.pad_meta(lab_a, id_a)
+    meta_b = meta_a if same_rows else ops.pad_meta(lab_b, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
                           float(temperature), bool(normalize), bool(same_rows))
 

@@ -35,7 +35,7 @@ def run(A, M, d, T, seed=0, same=False):
     A = ab.shape[0]
     fg = (la != 0).float(); w = fg / fg.sum()
     shift = torch.full((A,), 1.0 / T, device=dev)
-    ma = torch.stack([la, ia], 1).contiguous(); mb = torch.stack([lb, ib], 1).contiguous()
+    ma = ops.pad_meta(la, ia); mb = ops.pad_meta(lb, ib)
     loss, stats = op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
     torch.cuda.synchronize()
     l_ref, da_ref, db_ref = ref(ab[:, :d], bb[:, :d], la, lb, ia, ib, w, T)
@@ -53,3 +53,36 @@ if __name__ == "__main__":
     run(256, 1000, 128, 0.1)
     run(0, 500, 256, 0.07, same=True)
     run(4096, 16384, 256, 0.7)
+
+
+def bench(A=4096, M=16384, d=256, T=0.7, iters=20):
+    g = torch.Generator(device=dev).manual_seed(1)
+    bb = torch.nn.functional.normalize(torch.randn(M, d, device=dev, generator=g), dim=1).to(torch.bfloat16)
+    lb = torch.randint(0, 5, (M,), device=dev, generator=g, dtype=torch.int32)
+    ib = torch.arange(M, device=dev, dtype=torch.int32)
+    pick = torch.randperm(M, device=dev, generator=g)[:A]
+    ab, la, ia = bb[pick].contiguous(), lb[pick].contiguous(), ib[pick].contiguous()
+    fg = (la != 0).float(); w = fg / fg.sum()
+    shift = torch.full((A,), 1.0 / T, device=dev)
+    ma = ops.pad_meta(la, ia); mb = ops.pad_meta(lb, ib)
+    one = torch.ones(1, device=dev)
+    def fwd(): return op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
+    loss, stats = fwd()
+    def bwd(): return op.p2p_bwd(ab, bb, d, ma, mb, shift, w, T, stats, one, True, True)
+    def timed(fn):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters): fn()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters * 1e3
+    tf, tb = timed(fwd), timed(bwd)
+    fl = 2.0 * A * M * d
+    print(f"p2p A={A} M={M} d={d}: fwd {tf:.1f} us ({fl/tf/1e6:.0f} TFLOP/s)  bwd {tb:.1f} us ({3*fl/tb/1e6:.0f} TFLOP/s of 6AMd)  "
+          f"total {tf+tb:.1f} us -> {4*fl/(tf+tb)/1e6:.0f} TFLOP/s algorithmic (8AMd), {4*fl/(tf+tb)/1e6/1643.3*100:.1f}% of 1643 TF peak")
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bench":
+    bench()
+    bench(16384, 16384, 256)
+    bench(8192, 65536, 128)
