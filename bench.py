@@ -420,8 +420,7 @@ def extra_kernels(dev, feats, labels, centres, peak):
 
     def add(name, ms, bytes_):
         gbs = bytes_ / (ms * 1e-3) / 1e9
-        res[name] = {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak,
-                     "pixels_per_s": n_px / (ms * 1e-3)}
+        res[name] = {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
 
     add("pseudo_label (generate_pseudo_label)", timed(lambda: op.pseudo_label(feats, centres, 0.25)), (4 * C + 12) * n_px)
     add("class_sums hard + ema_finalize (update_class_center_iter)",
@@ -433,6 +432,22 @@ def extra_kernels(dev, feats, labels, centres, peak):
     add("centroid_bwd soft P=2 (cal_centroid bwd: dF + dP)",
         timed(lambda: op.centroid_bwd(feats, None, probs, True, 0.0, part, 2, K, gcen, sums, 1.0, True)),
         (8 * C + 8 * K + 4) * n_px)
+    # cfg5 geometry (DRUNet decoder map, C=32, K=4, P=2; 64 images of 224x224 per GPU)
+    del probs, part, gcen, sums
+    b5, c5, h5, k5 = 64, 32, 224, 4
+    n_px = b5 * h5 * h5
+    f5 = torch.randn(b5, c5, h5, h5, device=dev, generator=gen)
+    p5 = torch.softmax(3 * torch.randn(b5, k5, h5, h5, device=dev, generator=gen), 1)
+    part5 = (torch.randperm(n_px, device=dev, generator=gen) % 2).to(torch.int32)
+    lab5 = torch.randint(0, k5, (n_px,), device=dev, generator=gen)
+    g5 = torch.randn(2 * k5, c5, device=dev, generator=gen)
+    s5 = op.class_sums(f5, None, p5, True, 0.0, part5, 2, k5)
+    add("cfg5 shape: class_sums hard (EMA centres) C32 K4", timed(lambda: op.class_sums(f5, lab5, None, False, 0.0, None, 1, k5)),
+        (4 * c5 + 8) * n_px)
+    add("cfg5 shape: class_sums soft P=2 C32 K4 (cal_centroid fwd)",
+        timed(lambda: op.class_sums(f5, None, p5, True, 0.0, part5, 2, k5)), (4 * c5 + 4 * k5 + 4) * n_px)
+    add("cfg5 shape: centroid_bwd soft P=2 C32 K4 (dF + dP)",
+        timed(lambda: op.centroid_bwd(f5, None, p5, True, 0.0, part5, 2, k5, g5, s5, 1.0, True)), (8 * c5 + 8 * k5 + 4) * n_px)
     return res
 
 

@@ -127,15 +127,25 @@ __device__ __forceinline__ void build_weights(const SumArgs& a, int64_t b, int64
   }
 }
 
+// Block tile = kChunks x (32*VEC) pixels.  Phase A: each thread builds the weight rows of VEC pixels
+// ONCE and parks them in shared memory as sW[column][pixel]; phase B: a warp owns CPW channels of the
+// tile's chunks, streams them with 128-bit loads and reads the weights back with conflict-free
+// 128-bit shared loads.  The weights therefore cost registers only transiently, whatever P*K is.
+constexpr int kChunks = 8;
+
 template <int KWT, int CPW, int VEC>
 __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a) {
+  constexpr bool kPipe = KWT <= 8;       // wide weight rows: keep one x buffer, the accumulators need the registers
+  extern __shared__ __align__(16) float sW[];            // [KWT][TP]
   __shared__ float s_acc[kWarps][CPW * KWT];
   __shared__ float s_w[kWarps][KWT];
+  constexpr int TP = kChunks * 32 * VEC;                 // pixels per block tile (1024 or 256)
+  constexpr int CPS = (8 / CPW) < 1 ? 1 : (8 / CPW);     // chunks loaded together (8 vector loads in flight per lane)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = warp % a.cg_per_block, pt = warp / a.cg_per_block;
   const int C = (int)a.channels;
   const int c0 = (blockIdx.y * a.cg_per_block + cg) * CPW;
-  const bool count_weights = (blockIdx.y == 0) && (cg == 0);
+  const bool count_weights = blockIdx.y == 0;
 
   float acc[CPW][KWT];
   float wacc[KWT];
@@ -146,38 +156,92 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
 #pragma unroll
   for (int q = 0; q < KWT; ++q) wacc[q] = 0.f;
 
-  const int64_t n_super = ceil_div<int64_t>(a.n_tiles, a.pt_per_block);
-  for (int64_t s = blockIdx.x; s < n_super; s += gridDim.x) {
-    const int64_t tile = s * a.pt_per_block + pt;
-    if (tile >= a.n_tiles) continue;
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t b = tile / a.tiles_per_image;
-    const int64_t p = (tile - b * a.tiles_per_image) * (32 * VEC) + (int64_t)lane * VEC;
-    if (p >= a.pixels) continue;
-    const int64_t pix = b * a.pixels + p;
-    float w[VEC][KWT];
-    build_weights<KWT, VEC>(a, b, p, pix, w);
-    const float* base = a.feat + b * a.sb + p * a.sp;
-    float x[CPW][VEC];
+    const int64_t p_tile = (tile - b * a.tiles_per_image) * TP;
+    {   // ---- phase A: weights of this tile -> shared memory
+      // one pixel at a time keeps the register footprint of this phase at KWT (+ K probabilities);
+      // consecutive threads take consecutive pixels, so loads and the smem stores are conflict-free
+#pragma unroll 1
+      for (int v = 0; v < VEC; ++v) {
+        const int pl = v * kThreads + threadIdx.x;
+        const int64_t p = p_tile + pl;
+        float w1[1][KWT];
+        if (p < a.pixels) build_weights<KWT, 1>(a, b, p, b * a.pixels + p, w1);
+        else {
 #pragma unroll
-    for (int j = 0; j < CPW; ++j) {
-      if (c0 + j < C) ld_vec<VEC>(base + (int64_t)(c0 + j) * a.sc, x[j]);
-      else {
+          for (int q = 0; q < KWT; ++q) w1[0][q] = 0.f;
+        }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) x[j][v] = 0.f;
+        for (int q = 0; q < KWT; ++q) {
+          sW[q * TP + pl] = w1[0][q];
+          if (count_weights) wacc[q] += w1[0][q];
+        }
       }
     }
+    __syncthreads();
+    // ---- phase B: stream the channels of this warp's chunks, software-pipelined: the loads of step
+    // i+1 are in flight while step i is being accumulated (two register buffers)
+    const float* img = a.feat + b * a.sb;
+    const int step_stride = a.pt_per_block * CPS;
+    auto load_step = [&](int ch0, float (&x)[CPS][CPW][VEC]) {
 #pragma unroll
-    for (int j = 0; j < CPW; ++j)
+      for (int u = 0; u < CPS; ++u) {
+        const int ch = ch0 + u * a.pt_per_block;
+        const int64_t p = p_tile + (int64_t)ch * (32 * VEC) + lane * VEC;
+        const bool ok = ch < kChunks && p < a.pixels;
 #pragma unroll
-      for (int q = 0; q < KWT; ++q)
+        for (int j = 0; j < CPW; ++j) {
+          if (ok && c0 + j < C) ld_vec<VEC>(img + (int64_t)(c0 + j) * a.sc + p * a.sp, x[u][j]);
+          else {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[j][q] = fmaf(w[v][q], x[j][v], acc[j][q]);
-    if (count_weights) {
+            for (int v = 0; v < VEC; ++v) x[u][j][v] = 0.f;
+          }
+        }
+      }
+    };
+    auto accumulate = [&](int ch0, const float (&x)[CPS][CPW][VEC]) {
 #pragma unroll
-      for (int q = 0; q < KWT; ++q)
+      for (int u = 0; u < CPS; ++u) {
+        const int ch = ch0 + u * a.pt_per_block;
+        if (ch < kChunks) {
+          const int pl = ch * (32 * VEC) + lane * VEC;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) wacc[q] += w[v][q];
+          for (int q = 0; q < KWT; ++q) {
+            float wq[VEC];
+            if constexpr (VEC == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(sW + q * TP + pl);
+              wq[0] = t.x; wq[1] = t.y; wq[2] = t.z; wq[3] = t.w;
+            } else {
+              wq[0] = sW[q * TP + pl];
+            }
+#pragma unroll
+            for (int j = 0; j < CPW; ++j)
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[j][q] = fmaf(wq[v], x[u][j][v], acc[j][q]);
+          }
+        }
+      }
+    };
+    if constexpr (!kPipe) {
+      float xa[CPS][CPW][VEC];
+      for (int ch0 = pt; ch0 < kChunks; ch0 += step_stride) { load_step(ch0, xa); accumulate(ch0, xa); }
+    } else {
+      float xa[CPS][CPW][VEC], xb[CPS][CPW][VEC];
+      int ch0 = pt;
+      if (ch0 < kChunks) load_step(ch0, xa);
+      while (ch0 < kChunks) {
+        const int ch1 = ch0 + step_stride;
+        if (ch1 < kChunks) load_step(ch1, xb);
+        accumulate(ch0, xa);
+        if (ch1 >= kChunks) break;
+        const int ch2 = ch1 + step_stride;
+        if (ch2 < kChunks) load_step(ch2, xa);
+        accumulate(ch1, xb);
+        ch0 = ch2;
+      }
     }
+    __syncthreads();
   }
   // one cross-lane reduction per block
 #pragma unroll
@@ -207,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
   }
   if (blockIdx.y == 0 && threadIdx.x < KWT) {
     float t = 0.f;
-    for (int pp = 0; pp < a.pt_per_block; ++pp) t += s_w[pp * a.cg_per_block][threadIdx.x];
+    for (int w = 0; w < kWarps; ++w) t += s_w[w][threadIdx.x];
     out[(int64_t)threadIdx.x * (C + 1) + C] = t;
   }
 }
@@ -400,21 +464,20 @@ struct SumPlan { int kwt, cpw, vec, cg_per_block, pt_per_block; dim3 grid; int64
 SumPlan plan_sums(int64_t B, int64_t C, int64_t HW, int n_cols, bool vec4) {
   SumPlan p;
   p.kwt = pick_kwt(n_cols);
-  p.cpw = p.kwt <= 5 ? 8 : (p.kwt <= 8 ? 4 : 2);
+  p.cpw = p.kwt <= 3 ? 8 : 4;
   p.vec = vec4 ? 4 : 1;
   int n_groups = (int)ceil_div<int64_t>(C, p.cpw);
   int cg = 1;
   while (cg < n_groups && cg < kWarps) cg *= 2;
   p.cg_per_block = cg;
   p.pt_per_block = kWarps / cg;
-  p.tiles_per_image = ceil_div<int64_t>(HW, 32 * p.vec);
+  p.tiles_per_image = ceil_div<int64_t>(HW, kChunks * 32 * p.vec);
   p.n_tiles = B * p.tiles_per_image;
   int gy = (int)ceil_div<int64_t>(n_groups, cg);
-  int64_t n_super = ceil_div<int64_t>(p.n_tiles, p.pt_per_block);
   int64_t gx = (int64_t)sm_count() * 2 / gy;
   if (gx < 1) gx = 1;
-  // keep at least 4 super tiles per block so the end-of-block reduction is amortised
-  if (gx > ceil_div<int64_t>(n_super, 4)) gx = ceil_div<int64_t>(n_super, 4);
+  // keep at least 2 block tiles per block so the end-of-block reduction is amortised
+  if (gx > ceil_div<int64_t>(p.n_tiles, 2)) gx = ceil_div<int64_t>(p.n_tiles, 2);
   if (gx < 1) gx = 1;
   p.grid = dim3((unsigned)gx, (unsigned)gy, 1);
   return p;
@@ -426,8 +489,13 @@ size_t partial_bytes(const SumPlan& p, int64_t C) {
 
 template <int KWT, int CPW>
 void launch_sums(const SumArgs& a, const SumPlan& p, cudaStream_t stream) {
-  if (p.vec == 4) class_sums_kernel<KWT, CPW, 4><<<p.grid, kThreads, 0, stream>>>(a);
-  else class_sums_kernel<KWT, CPW, 1><<<p.grid, kThreads, 0, stream>>>(a);
+  const size_t smem = (size_t)KWT * kChunks * 32 * p.vec * sizeof(float);
+  if (p.vec == 4) {
+    if (smem > 32 * 1024) cudaFuncSetAttribute(class_sums_kernel<KWT, CPW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    class_sums_kernel<KWT, CPW, 4><<<p.grid, kThreads, smem, stream>>>(a);
+  } else {
+    class_sums_kernel<KWT, CPW, 1><<<p.grid, kThreads, smem, stream>>>(a);
+  }
 }
 
 int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -441,13 +509,13 @@ int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t w
   switch (p.kwt) {
     case 2: launch_sums<2, 8>(a, p, stream); break;
     case 3: launch_sums<3, 8>(a, p, stream); break;
-    case 4: launch_sums<4, 8>(a, p, stream); break;
-    case 5: launch_sums<5, 8>(a, p, stream); break;
+    case 4: launch_sums<4, 4>(a, p, stream); break;
+    case 5: launch_sums<5, 4>(a, p, stream); break;
     case 6: launch_sums<6, 4>(a, p, stream); break;
     case 8: launch_sums<8, 4>(a, p, stream); break;
-    case 10: launch_sums<10, 2>(a, p, stream); break;
-    case 12: launch_sums<12, 2>(a, p, stream); break;
-    case 16: launch_sums<16, 2>(a, p, stream); break;
+    case 10: launch_sums<10, 4>(a, p, stream); break;
+    case 12: launch_sums<12, 4>(a, p, stream); break;
+    case 16: launch_sums<16, 4>(a, p, stream); break;
     default: return SLCL_ERR_INVALID_ARGUMENT;
   }
   const int total = a.n_cols * ((int)a.channels + 1);
