@@ -497,3 +497,50 @@ def test_p2p_full_size_properties_cfg3():
     row = lz - (s * pos).sum(1) / pos.sum(1)
     close(l1, (row * w).sum(), rtol=1e-4)
     assert torch.equal(st1[:, 2].long(), pos.sum(1))                       # positive counts are exact
+
+
+def test_c_abi_called_directly_with_ctypes():
+    """The INTEGRATION.md stub: raw ctypes against include/slcl.h, no torch custom-op layer in between."""
+    import ctypes as C
+    from slcl._lib import LIB_PATH
+    lib = C.CDLL(LIB_PATH)
+
+    class MapT(C.Structure):
+        _fields_ = [(n, C.c_int64) for n in ("batch", "channels", "pixels", "stride_b", "stride_c", "stride_p")]
+
+    class ParamsT(C.Structure):
+        _fields_ = [("n_class", C.c_int), ("temperature", C.c_float), ("base_temperature", C.c_float),
+                    ("margin", C.c_float), ("easy_margin", C.c_int), ("normalize", C.c_int)]
+    P = C.c_void_p
+    lib.slcl_proto_workspace_bytes.restype = C.c_size_t
+    lib.slcl_proto_workspace_bytes.argtypes = [C.c_int64]
+    lib.slcl_proto_fwd.argtypes = [P, C.POINTER(MapT), P, P, P, P, C.POINTER(ParamsT), P, P, P, P, C.c_size_t, P]
+    lib.slcl_proto_bwd.argtypes = [P, C.POINTER(MapT), P, P, P, P, C.POINTER(ParamsT), P, P]
+    gen = cases.g(321)
+    b, c, h, w, k = 2, 64, 16, 16, 5
+    feat_h = torch.randn(b, c, h, w, generator=gen)
+    lab_h = torch.randint(0, k, (b * h * w,), generator=gen)
+    cen_h = torch.randn(k, c, generator=gen)
+    feat, labels, centres = feat_h.to(dev()), lab_h.to(dev()), cen_h.to(dev())
+    n = b * h * w
+    m = MapT(b, c, h * w, c * h * w, h * w, 1)
+    p = ParamsT(k, 0.1, 1.0, 0.4, 0, 1)
+    stash = torch.empty(k + 1, n, device=dev())
+    cstate = torch.empty(k * c + k, device=dev())
+    scal = torch.empty(4, device=dev())
+    ws = torch.empty(lib.slcl_proto_workspace_bytes(n), dtype=torch.uint8, device=dev())
+    dfeat = torch.empty_like(feat)
+    g = torch.ones(1, device=dev())
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.slcl_proto_fwd(feat.data_ptr(), C.byref(m), labels.data_ptr(), None, None, centres.data_ptr(), C.byref(p),
+                              stash.data_ptr(), cstate.data_ptr(), scal.data_ptr(), ws.data_ptr(), ws.numel(), s) == 0
+    assert lib.slcl_proto_bwd(feat.data_ptr(), C.byref(m), stash.data_ptr(), cstate.data_ptr(), scal.data_ptr(),
+                              g.data_ptr(), C.byref(p), dfeat.data_ptr(), s) == 0
+    # error path: too small a workspace is refused before any launch
+    assert lib.slcl_proto_fwd(feat.data_ptr(), C.byref(m), labels.data_ptr(), None, None, centres.data_ptr(), C.byref(p),
+                              stash.data_ptr(), cstate.data_ptr(), scal.data_ptr(), ws.data_ptr(), 8, s) == -3
+    fo = feat_h.clone().requires_grad_(True)
+    ref = O.mpcl_loss_calc(fo, lab_h.view(b, h, w), cen_h, O.MarginSpec(k, .1, .4, 1.0))
+    ref.backward()
+    close(scal[0], ref)
+    grad_close(dfeat, fo.grad)
