@@ -311,14 +311,13 @@ def run_slcl(args):
         group = True if world > 1 else None
         del dfeat, plan
 
+        from slcl.host import mpcl_loss_and_grad_host
+
         def e2e_step():
-            f = feats_h.to(dev, non_blocking=True).requires_grad_(True)
-            lab = labels_h.to(dev, non_blocking=True)
-            s = sel_h.to(dev, non_blocking=True)
-            loss = mpcl_loss_calc(f, lab, centres, mp, pixel_sel_loc=s, tag="target", group=group)
-            loss.backward()
-            loss_h.copy_(loss.detach(), non_blocking=True)
-            grad_h.copy_(f.grad, non_blocking=True)
+            # public host-buffer API: chunked H2D -> fwd -> bwd -> D2H pipeline over 3 streams
+            loss, _ = mpcl_loss_and_grad_host(feats_h, labels_h, centres, mp, pixel_sel_loc_h=sel_h, grad_out_h=grad_h,
+                                              device=dev, chunk_images=4, group=group)
+            loss_h.copy_(loss, non_blocking=True)
 
         n_e2e = max(1, min(args.steps, 20))
         for _ in range(2):
@@ -339,7 +338,8 @@ def run_slcl(args):
         d2h = grad_h.numel() * 4 + 4
         e2e = {"value": world * n_px * n_e2e / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms / n_e2e,
-               "api": "slcl.loss.mpcl_loss_calc(...).backward() on pinned host buffers; loss and dF copied back",
+               "api": "slcl.host.mpcl_loss_and_grad_host(pinned feats/labels/sel -> loss, pinned dF): 4-image chunks, "
+                      "H2D / kernels / D2H overlapped on 3 streams",
                "loss": float(loss_h)}
         del grad_h
     sampler.stop()

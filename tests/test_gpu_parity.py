@@ -544,3 +544,25 @@ def test_c_abi_called_directly_with_ctypes():
     ref.backward()
     close(scal[0], ref)
     grad_close(dfeat, fo.grad)
+
+
+def test_host_buffer_pipeline_matches_device_path(api):
+    """slcl.host: chunked H2D -> fwd -> bwd -> D2H pipeline == mpcl_loss_calc(...).backward() on the device."""
+    loss_mod, _ = api
+    from slcl.host import mpcl_loss_and_grad_host
+    gen = cases.g(404)
+    b, c, h, w, k = 8, 32, 16, 16, 4
+    feat_h = torch.randn(b, c, h, w, generator=gen).pin_memory()
+    lab_h = torch.randint(0, k, (b, h, w), generator=gen).pin_memory()
+    sel_h = (torch.rand(b * h * w, generator=gen) > 0.4).float().pin_memory()
+    cc = torch.randn(k, c, generator=gen).to(dev())
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.2)
+    for sel in (sel_h, None):
+        loss, grad_h = mpcl_loss_and_grad_host(feat_h, lab_h, cc, mp, pixel_sel_loc_h=sel, device=dev(), chunk_images=2)
+        torch.cuda.synchronize()
+        f = feat_h.to(dev()).requires_grad_(True)
+        ref = loss_mod.mpcl_loss_calc(f, lab_h.view(-1).to(dev()), cc, mp, pixel_sel_loc=None if sel is None else sel.to(dev()),
+                                      tag='target')
+        ref.backward()
+        close(loss, ref, rtol=1e-5)
+        grad_close(grad_h, f.grad.cpu(), rtol=1e-5)
