@@ -448,7 +448,52 @@ def extra_kernels(dev, feats, labels, centres, peak):
         timed(lambda: op.class_sums(f5, None, p5, True, 0.0, part5, 2, k5)), (4 * c5 + 4 * k5 + 4) * n_px)
     add("cfg5 shape: centroid_bwd soft P=2 C32 K4 (dF + dP)",
         timed(lambda: op.centroid_bwd(f5, None, p5, True, 0.0, part5, 2, k5, g5, s5, 1.0, True)), (8 * c5 + 8 * k5 + 4) * n_px)
+    # cfg3: sampled pixel<->pixel loss, 4096 anchors x 16384 contrast rows, d = 256, bf16 tensor cores
+    del f5, p5, part5, lab5, g5, s5
+    res.update(p2p_kernels(dev, gen))
     return res
+
+
+def p2p_kernels(dev, gen):
+    from slcl import ops as slcl_ops
+    from slcl.plan import P2PPlan
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            tf_peak = float(json.load(fh)["bf16_tflops"])
+    except Exception:
+        tf_peak = 1590.0
+    A, M, d, T = 4096, 16384, 256, 0.7
+    b = torch.nn.functional.normalize(torch.randn(M, d, device=dev, generator=gen), dim=1).to(torch.bfloat16)
+    lb = torch.randint(0, 5, (M,), device=dev, generator=gen, dtype=torch.int32)
+    ib = torch.arange(M, device=dev, dtype=torch.int32)
+    pick = torch.randperm(M, device=dev, generator=gen)[:A]
+    a, la, ia = b[pick].contiguous(), lb[pick].contiguous(), ib[pick].contiguous()
+    fg = (la != 0).float()
+    plan = P2PPlan(a, b, d, slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib), torch.full((A,), 1.0 / T, device=dev),
+                   fg / fg.sum(), T)
+    graph = plan.capture_graph()
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize(dev)
+        return s.elapsed_time(e) / iters
+
+    out = {}
+    for name, fn, flops in (("cfg3 p2p forward (A4096 x M16384 x d256, bf16 tcgen05)", plan.forward, 2.0 * A * M * d),
+                            ("cfg3 p2p backward (dA + dB, S recomputed)", plan.backward, 6.0 * A * M * d),
+                            ("cfg3 p2p fwd+bwd, one CUDA graph", graph.replay, 8.0 * A * M * d)):
+        ms = timed(fn)
+        tf = flops / (ms * 1e-3) / 1e12
+        out[name] = {"ms": ms, "algorithmic_flop": flops, "achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / tf_peak,
+                     "rows_per_s": (A + M) / (ms * 1e-3)}
+    return out
 
 
 def main():

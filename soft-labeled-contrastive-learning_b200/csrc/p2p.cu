@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <limits.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <math.h>
 
@@ -32,13 +33,14 @@ namespace {
 constexpr int BM = 128;            // rows per CTA (UMMA M)
 constexpr int BN = 64;             // streamed rows (S tile columns) per step
 constexpr int KCH = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int kStages = 3;
+constexpr int kStages = 5;
 constexpr int kMaxD = 256;
 constexpr int kEpiWarps = 8;       // warps 4..11; (warp % 4) selects the TMEM lane quarter
 constexpr int kThreads = 32 * (4 + kEpiWarps);
 constexpr int kTmemCols = 512;
 constexpr int kColS = 0;           // S double buffer: columns [0,64) and [64,128)
 constexpr int kColAcc = 128;       // dR accumulators: columns [128, 128 + d)
+constexpr int kColR = 384;         // resident row operand R (bf16 pairs): columns [384, 384 + d/2)
 constexpr float kLog2e = 1.4426950408889634f;
 
 enum Mode { kFwd = 0, kBwdRows = 1 /* dA: stats per row */, kBwdCols = 2 /* dB: stats per column */ };
@@ -49,6 +51,7 @@ struct P2PArgs {
   int mode;
   int debug;                          // bring-up knobs (SLCL_P2P_DEBUG): 1 skip epilogue math, 2 skip tmem load, 4 skip MMA1
   float scale_log2;                   // log2(e) / T
+  const uint32_t* rows_u32;           // resident operand, bf16 row-major [n_rows, d] viewed as 32-bit words
   const int2* row_meta;               // {label, id}
   const int2* col_meta;
   const float4* row_stat;             // kFwd: {shift*log2e,-,-,-}; kBwdRows: {shift*log2e, alpha, beta, -}
@@ -86,6 +89,19 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += (unsigned long long)(clock64() - t0);
+}
+// one lane of a converged warp (elect.sync): the idiom the compiler recognises for single-thread
+// issue of uniform-datapath instructions
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -148,6 +164,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from tensor memory (rows = lanes, bf16 pairs packed along K in 32-bit columns):
+// no per-instruction shared-memory fetch of the 128 A rows, so a narrow-N MMA runs at its N/2-cycle floor
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -171,6 +199,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -220,12 +260,12 @@ struct __align__(8) Barriers {
 };
 
 // dynamic smem carve-up (1024-byte aligned tiles)
-//   R   : [d/64][128 rows][128 B]
+//   (the resident row operand R lives in tensor memory, not here)
 //   Cm  : [kStages][d/64][64 rows][128 B]
 //   G   : [2][128 rows][128 B]
 __host__ __device__ inline size_t smem_bytes_for(int d) {
   const size_t kc = d / KCH;
-  return 1024 /*align slack*/ + kc * BM * 128 + (size_t)kStages * kc * BN * 128 + 2 * BM * 128 + kMetaSlots * sizeof(ColMeta) +
+  return 1024 /*align slack*/ + (size_t)kStages * kc * BN * 128 + 2 * BM * 128 + kMetaSlots * sizeof(ColMeta) +
          sizeof(Barriers) + 64;
 }
 
@@ -238,8 +278,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const int kc = a.d / KCH;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sR = base;
-  uint8_t* sC = sR + (size_t)kc * BM * 128;
+  uint8_t* sC = base;
   uint8_t* sG = sC + (size_t)kStages * kc * BN * 128;
   ColMeta* sMeta = reinterpret_cast<ColMeta*>(sG + 2 * BM * 128);
   Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
@@ -259,9 +298,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   auto tile_col = [&](int t) { int tt = t + rot; if (tt >= n_tiles) tt -= n_tiles; return col0 + tt * BN; };
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_rows);
     tma_prefetch_desc(&map_cols);
-    mbar_init(&bars->r_full, 1);
+    mbar_init(&bars->r_full, 4);                 // the four warps that fill R's lane quarters
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->c_full[s], 1); mbar_init(&bars->c_empty[s], CS); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
@@ -280,19 +318,21 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  // Producer and MMA roles run with the WHOLE warp in the loop (converged, warp-uniform control flow) and
+  // elect one lane only around the asynchronous instructions.  Running them under `if (lane == 0)` makes
+  // the compiler wrap every UTCHMMA / UTMALDG in an ELECT + R2UR waterfall loop (~100 cycles per MMA).
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      unsigned long long w0 = 0, w1 = 0;
-      const long long tstart = clock64();
-      mbar_expect_tx(&bars->r_full, (uint32_t)kc * BM * 128);
-      for (int c = 0; c < kc; ++c) tma_load_2d(sR + (size_t)c * BM * 128, &map_rows, &bars->r_full, c * KCH, row0);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kStages;
-        mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ 1, w0);
-        if (a.debug & 8) { mbar_arrive(&bars->c_full[s]); goto meta_part; }
+    unsigned long long w0 = 0, w1 = 0;
+    const long long tstart = clock64();
+    const bool with_stat = a.mode == kBwdCols;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kStages;
+      const int ms = t % kMetaSlots;
+      mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ 1, w0);
+      mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->c_full[s], (uint32_t)kc * BN * 128);
-        {
         uint8_t* dst = sC + (size_t)s * kc * BN * 128;
         if (CS == 1) {
           for (int c = 0; c < kc; ++c) tma_load_2d(dst + (size_t)c * BN * 128, &map_cols, &bars->c_full[s], c * KCH, tile_col(t));
@@ -302,61 +342,59 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
             tma_load_2d_mc(dst + (size_t)c * BN * 128 + (size_t)crank * kSlice * 128, &map_cols, &bars->c_full[s], c * KCH,
                            tile_col(t) + (int)crank * kSlice, kAllCtas);
         }
-        }
-      meta_part:
-        if (a.debug & 16) continue;
-        const int ms = t % kMetaSlots;
-        mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
-        const bool with_stat = a.mode == kBwdCols;
         mbar_expect_tx(&bars->m_full[ms], (uint32_t)(BN * sizeof(int2) + (with_stat ? BN * sizeof(float4) : 0)));
         bulk_load_1d(sMeta[ms].meta, a.col_meta + tile_col(t), BN * sizeof(int2), &bars->m_full[ms]);
         if (with_stat) bulk_load_1d(sMeta[ms].stat, a.col_stat + tile_col(t), BN * sizeof(float4), &bars->m_full[ms]);
       }
-      if (a.prof && blockIdx.x == 0 && blockIdx.y == 0) {
-        a.prof[0] = (unsigned long long)(clock64() - tstart); a.prof[1] = w0; a.prof[2] = w1;
-      }
+      __syncwarp();
+    }
+    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      a.prof[0] = (unsigned long long)(clock64() - tstart); a.prof[1] = w0; a.prof[2] = w1;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(BN, 0);
-      const uint32_t idesc2 = make_idesc(a.d, 1);
-      const uint32_t r_addr = smem_u32(sR), c_addr = smem_u32(sC), g_addr = smem_u32(sG);
-      unsigned long long w0 = 0, w1 = 0, w2 = 0;
-      const long long tstart = clock64();
-      mbar_wait(&bars->r_full, 0);
-      // Descriptors are built once; inside the loops only the 14-bit start-address field moves
-      // (all operand addresses are < 256 KB, so adding (bytes >> 4) to the low word never carries out).
-      const uint64_t descR = make_desc(r_addr, 16, 1024);
-      const uint64_t descC = make_desc(c_addr, 16, 1024);              // K-major view of a column tile (MMA1)
-      const uint64_t descCmn = make_desc(c_addr, BN * 128, 1024);      // MN-major view of the same bytes (MMA2)
-      const uint64_t descG = make_desc(g_addr, 16, 1024);
-      const uint32_t stage_units = (uint32_t)(kc * BN * 128) >> 4;
-      for (int t = 0; t <= n_tiles; ++t) {
-        if (t < n_tiles) {
-          const int s = t % kStages, buf = t & 1;
-          mbar_wait_t(&bars->c_full[s], (t / kStages) & 1, w0);
-          mbar_wait_t(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1, w1);
-          tc_fence_after();
-          if (a.debug & 32) { mbar_arrive(&bars->s_full[buf]); mbar_arrive(&bars->c_empty[s]); continue; }   // CS==1, fwd only
-          // S[buf] = R_tile . Cm_tile^T : both operands K-major, 128-byte swizzle, 16 bf16 (32 B) per K step
+    // ===================== MMA issuer =====================
+    const uint32_t idesc1 = make_idesc(BN, 0);
+    const uint32_t idesc2 = make_idesc(a.d, 1);
+    const uint32_t c_addr = smem_u32(sC), g_addr = smem_u32(sG);
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;
+    const long long tstart = clock64();
+    mbar_wait(&bars->r_full, 0);
+    tc_fence_after();
+    // Descriptors are built once; inside the loops only the 14-bit start-address field moves
+    // (all operand addresses are < 256 KB, so adding (bytes >> 4) to the low word never carries out).
+    const uint64_t descC = make_desc(c_addr, 16, 1024);              // K-major view of a column tile (MMA1)
+    const uint64_t descCmn = make_desc(c_addr, BN * 128, 1024);      // MN-major view of the same bytes (MMA2)
+    const uint64_t descG = make_desc(g_addr, 16, 1024);
+    const uint32_t stage_units = (uint32_t)(kc * BN * 128) >> 4;
+    for (int t = 0; t <= n_tiles; ++t) {
+      if (t < n_tiles) {
+        const int s = t % kStages, buf = t & 1;
+        mbar_wait_t(&bars->c_full[s], (t / kStages) & 1, w0);
+        mbar_wait_t(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1, w1);
+        tc_fence_after();
+        if (elect_one()) {
+          // S[buf] = R . Cm_tile^T : A = R from tensor memory, B = column tile K-major, 16 bf16 of K per MMA
           const uint32_t d_tmem = tmem + kColS + buf * BN;
-          uint64_t da = descR, db = descC + (uint64_t)(s * stage_units);
+          uint32_t ta = tmem + kColR;                          // 16 bf16 of K = 8 tensor-memory columns per step
+          uint64_t db = descC + (uint64_t)(s * stage_units);
           for (int c = 0; c < kc; ++c) {
 #pragma unroll
             for (int k = 0; k < KCH / 16; ++k)
-              if (!(a.debug & 4)) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc1, (c | k) != 0);
-            da += (BM * 128) >> 4;
+              umma_bf16_ts(d_tmem, ta + 8 * k, db + 2 * k, idesc1, (c | k) != 0);
+            ta += KCH / 2;
             db += (BN * 128) >> 4;
           }
           umma_commit(&bars->s_full[buf]);
           if (!bwd) { if (CS == 1) umma_commit(&bars->c_empty[s]); else umma_commit_mc(&bars->c_empty[s], kAllCtas); }
         }
-        if (bwd && t > 0) {
-          // dR += G(t-1)[128 x 64] . Cm_tile(t-1)[64 x d] : A = G K-major; B = Cm tile as MN-major operand
-          const int tp = t - 1, sp = tp % kStages, bp = tp & 1;
-          mbar_wait_t(&bars->g_full[bp], (tp >> 1) & 1, w2);
-          tc_fence_after();
+        __syncwarp();
+      }
+      if (bwd && t > 0) {
+        // dR += G(t-1)[128 x 64] . Cm_tile(t-1)[64 x d] : A = G K-major (smem); B = Cm tile as MN-major operand
+        const int tp = t - 1, sp = tp % kStages, bp = tp & 1;
+        mbar_wait_t(&bars->g_full[bp], (tp >> 1) & 1, w2);
+        tc_fence_after();
+        if (elect_one()) {
           const uint64_t dg = descG + (uint64_t)(bp * ((BM * 128) >> 4));
           const uint64_t dc = descCmn + (uint64_t)(sp * stage_units);
 #pragma unroll
@@ -364,11 +402,13 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           umma_commit(&bars->g_empty[bp]);
           if (CS == 1) umma_commit(&bars->c_empty[sp]); else umma_commit_mc(&bars->c_empty[sp], kAllCtas);
         }
+        __syncwarp();
       }
-      if (bwd) umma_commit(&bars->acc_full);
-      if (a.prof && blockIdx.x == 0 && blockIdx.y == 0) {
-        a.prof[4] = (unsigned long long)(clock64() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
-      }
+    }
+    if (bwd && elect_one()) umma_commit(&bars->acc_full);
+    __syncwarp();
+    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      a.prof[4] = (unsigned long long)(clock64() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
     }
   } else if (warp >= 4) {
     // ===================== epilogue: one thread per row, 32 of the 64 tile columns per warp =====================
@@ -382,58 +422,103 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     if (a.mode != kBwdCols && row_ok) rs = a.row_stat[row];
     float zs = 0.f, praw = 0.f, npos = 0.f;
     unsigned long long w0 = 0, w1 = 0, w2 = 0;
+    const uint32_t lane_addr0 = ((uint32_t)(q * 32) << 16);
+    if (half == 0) {
+      // resident operand: this thread's row (bf16 pairs, 32-bit words) -> tensor memory lane r_local
+      const uint4* src = reinterpret_cast<const uint4*>(a.rows_u32 + (size_t)row * (a.d / 2));
+      for (int c = 0; c < a.d / 2; c += 32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 t = row_ok ? __ldg(src + (c >> 2) + i) : make_uint4(0u, 0u, 0u, 0u);
+          v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+        tmem_st32(tmem + lane_addr0 + kColR + c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->r_full);
+    }
     const long long tstart = clock64();
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const int ms = t % kMetaSlots;
       const ColMeta& cmeta = sMeta[ms];
-      if (!(a.debug & 16)) mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
+      mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
       mbar_wait_t(&bars->s_full[buf], (t >> 1) & 1, w1);
       tc_fence_after();
       uint32_t v[32];
-      if (!(a.debug & 2)) {
-        tmem_ld32(tmem + lane_addr + kColS + buf * BN + half * 32, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0x3f000000u + i;
-      }
+      tmem_ld32(tmem + lane_addr + kColS + buf * BN + half * 32, v);
+      tmem_ld_wait();
       // S buffer is free as soon as it sits in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[buf]);
 
-      if ((a.debug & 1) && !bwd) {
-        zs += __uint_as_float(v[0]) + __uint_as_float(v[31]);
-      } else if (!bwd) {
+      if (!bwd) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int2 cm = cmeta.meta[half * 32 + jj];
           const float s = __uint_as_float(v[jj]);
           const float e = ex2_approx(fmaf(s, a.scale_log2, -rs.x));
-          const bool valid = (cm.y != rm.y) && (cm.y != INT_MIN);
-          if (valid) zs += e;
-          if (valid && cm.x == rm.x) { praw += s; npos += 1.f; }
+          // predicated adds spelled out in PTX: 2 compares + 3 predicated FADDs, no selects, no branches
+          asm("{\n\t"
+              ".reg .pred pv, pp;\n\t"
+              "setp.ne.s32 pv, %5, %6;\n\t"
+              "setp.eq.and.s32 pp, %7, %8, pv;\n\t"
+              "@pv add.f32 %0, %0, %3;\n\t"
+              "@pp add.f32 %1, %1, %4;\n\t"
+              "@pp add.f32 %2, %2, 0f3F800000;\n\t"
+              "}\n"
+              : "+f"(zs), "+f"(praw), "+f"(npos)
+              : "f"(e), "f"(s), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
+        }
+        // Padding columns (beyond col_end; only the last tile of a sweep has them) were read as zero rows
+        // by TMA, carry the sentinel id/label and therefore entered zs as exp(0 - shift): take them out
+        // analytically instead of testing every element.
+        {
+          const int jb = tile_col(t) + half * 32;
+          const int n_pad = max(0, min(32, jb + 32 - col_end));
+          if (n_pad > 0) zs -= (float)n_pad * ex2_approx(-rs.x);
         }
       } else {
         uint32_t packed[16];
+        // the statistics {shift, alpha, beta} belong to the row (dA sweep) or to the column (dB sweep):
+        // decide once per tile, not per element
+        auto make_g = [&](auto col_stat) {
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 2) {
-          float g2[2];
+          for (int jj = 0; jj < 32; jj += 2) {
+            float g2[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int2 cm = cmeta.meta[half * 32 + jj + u];
-            float4 st = rs;
-            if (a.mode == kBwdCols) st = cmeta.stat[half * 32 + jj + u];
-            const float s = __uint_as_float(v[jj + u]);
-            const float e = ex2_approx(fmaf(s, a.scale_log2, -st.x));
-            const float g = fmaf(st.y, e, (cm.x == rm.x) ? -st.z : 0.f);
-            g2[u] = ((cm.y != rm.y) && (cm.y != INT_MIN)) ? g : 0.f;
+            for (int u = 0; u < 2; ++u) {
+              const int2 cm = cmeta.meta[half * 32 + jj + u];
+              float sh = rs.x, al = rs.y, be = rs.z;
+              if constexpr (decltype(col_stat)::value) {
+                const float4 st = cmeta.stat[half * 32 + jj + u];
+                sh = st.x; al = st.y; be = st.z;
+              }
+              const float s = __uint_as_float(v[jj + u]);
+              const float e = ex2_approx(fmaf(s, a.scale_log2, -sh));
+              float g;      // alpha*e - [same label] beta, zero for the self pair
+              asm("{\n\t"
+                  ".reg .pred pv, pp;\n\t"
+                  "setp.ne.s32 pv, %4, %5;\n\t"
+                  "setp.eq.s32 pp, %6, %7;\n\t"
+                  "mul.f32 %0, %1, %2;\n\t"
+                  "@pp sub.f32 %0, %0, %3;\n\t"
+                  "@!pv mov.f32 %0, 0f00000000;\n\t"
+                  "}\n"
+                  : "=&f"(g)
+                  : "f"(al), "f"(e), "f"(be), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
+              g2[u] = g;
+            }
+            __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
+            packed[jj >> 1] = *reinterpret_cast<uint32_t*>(&h);
           }
-          __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
-          packed[jj >> 1] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        };
+        if (a.mode == kBwdCols) make_g(std::true_type{}); else make_g(std::false_type{});
         // G tile -> smem as a K-major, 128-byte-swizzled A operand: row r_local, 16-byte chunk (half*4 + i) ^ (r_local & 7)
         mbar_wait_t(&bars->g_empty[buf], ((t >> 1) & 1) ^ 1, w2);
         uint8_t* grow = sG + (size_t)buf * BM * 128 + (size_t)r_local * 128;
@@ -448,7 +533,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
         if (lane == 0) mbar_arrive(&bars->g_full[buf]);
       }
       __syncwarp();
-      if (lane == 0 && !(a.debug & 16)) mbar_arrive(&bars->m_empty[ms]);
+      if (lane == 0) mbar_arrive(&bars->m_empty[ms]);
     }
 
     if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
@@ -605,7 +690,7 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
   s.cols_per_split = tiles_per_split * BN;
-  s.cluster = s.row_tiles >= 4 ? 4 : (s.row_tiles >= 2 ? 2 : 1);
+  s.cluster = 1;      // measured on B200: multicast clusters (2, 4) bring no gain here -- the sweep is MMA/epilogue-bound, not L2-bound
   { const char* e = getenv("SLCL_P2P_CLUSTER"); if (e) s.cluster = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1); }   // tuning knob
   return s;
 }
@@ -625,6 +710,7 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   { const char* e = getenv("SLCL_P2P_DEBUG"); a.debug = e ? atoi(e) : 0; }
   { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   a.scale_log2 = inv_t * kLog2e;
+  a.rows_u32 = reinterpret_cast<const uint32_t*>(rows);
   a.row_meta = row_meta; a.col_meta = col_meta; a.row_stat = row_stat; a.col_stat = col_stat;
   a.stat_partial = stat_partial; a.grad_partial = grad_partial;
   const size_t smem = smem_bytes_for(d);

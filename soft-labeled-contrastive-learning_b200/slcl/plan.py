@@ -84,3 +84,55 @@ class ProtoPlan:
             self.backward()
         self.graph = g
         return g
+
+
+class P2PPlan:
+    """Pixel<->pixel loss forward + backward (slcl_p2p_fwd / slcl_p2p_bwd) on fixed device buffers:
+    anchors a [A, dp] and contrast rows b [M, dp] (bf16, dp % 64 == 0), padded int32 metadata
+    (slcl.ops.pad_meta), shift / weight [A].  Outputs: loss[1], stats[A,3], d_a [A, dim], d_b [M, dim]."""
+
+    def __init__(self, a: torch.Tensor, b: torch.Tensor, dim: int, a_meta: torch.Tensor, b_meta: torch.Tensor,
+                 shift: torch.Tensor, weight: torch.Tensor, temperature: float):
+        self.lib = _lib.load()
+        self.dev = _lib.require_cuda(a, b, a_meta, b_meta, shift, weight)
+        na, dp = a.shape
+        m = b.shape[0]
+        self.keep = (a, b, a_meta, b_meta, shift, weight)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.stats = torch.empty((na, 3), **f32)
+        self.loss = torch.empty(1, **f32)
+        self.d_a = torch.empty((na, dim), **f32)
+        self.d_b = torch.empty((m, dim), **f32)
+        self.grad_out = torch.ones(1, **f32)
+        self.ws = torch.empty(max(self.lib.slcl_p2p_workspace_bytes(na, m, dp), 256), dtype=torch.uint8, device=self.dev)
+        t = C.c_float(float(temperature))
+        self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(shift), ptr(weight), t, ptr(self.stats),
+                          ptr(self.loss), ptr(self.ws), self.ws.numel())
+        self._bwd_args = (ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(shift), ptr(weight), t,
+                          ptr(self.stats), ptr(self.grad_out), ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
+        self.flops = 8.0 * na * m * dp
+        self.graph = None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def forward(self) -> torch.Tensor:
+        check(self.lib.slcl_p2p_fwd(*self._fwd_args, self._stream()), "slcl_p2p_fwd")
+        return self.loss
+
+    def backward(self):
+        check(self.lib.slcl_p2p_bwd(*self._bwd_args, self._stream()), "slcl_p2p_bwd")
+        return self.d_a, self.d_b
+
+    def capture_graph(self) -> "torch.cuda.CUDAGraph":
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.forward(); self.backward()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+            self.backward()
+        self.graph = g
+        return g
