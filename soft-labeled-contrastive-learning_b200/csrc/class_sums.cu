@@ -184,7 +184,23 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
     // i+1 are in flight while step i is being accumulated (two register buffers)
     const float* img = a.feat + b * a.sb;
     const int step_stride = a.pt_per_block * CPS;
+    // interior tiles (all pixels and all CPW channels exist) take a predicate-free load path
+    const bool full = (p_tile + TP <= a.pixels) && (c0 + CPW <= C) && (kChunks % step_stride == 0 || true);
+    const float* lane_base = img + (int64_t)c0 * a.sc + (p_tile + (int64_t)lane * VEC) * a.sp;
+    const int64_t chunk_stride = (int64_t)(32 * VEC) * a.sp;
     auto load_step = [&](int ch0, float (&x)[CPS][CPW][VEC]) {
+      if (full) {
+#pragma unroll
+        for (int u = 0; u < CPS; ++u) {
+          const int ch = ch0 + u * a.pt_per_block;
+          if (ch < kChunks) {
+            const float* pch = lane_base + ch * chunk_stride;
+#pragma unroll
+            for (int j = 0; j < CPW; ++j) ld_vec<VEC>(pch + (int64_t)j * a.sc, x[u][j]);
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int u = 0; u < CPS; ++u) {
         const int ch = ch0 + u * a.pt_per_block;
@@ -276,16 +292,19 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
   }
 }
 
-// sums[col][c] = sum over blocks (fp64, block order)
+// sums[col][c] = sum over blocks in fp64.  One warp per output element: lane l adds blocks l, l+32, ...
+// then a fixed-shape shuffle tree, so the result is deterministic and the serial chain is n_blocks/32 long.
 __global__ void __launch_bounds__(kThreads) class_sums_reduce_kernel(const float* partial, int n_blocks, int kwt,
                                                                      int n_cols, int C, double* sums) {
-  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int row = C + 1;
   if (idx >= n_cols * row) return;
   const int col = idx / row, c = idx % row;
   double t = 0.0;
-  for (int b = 0; b < n_blocks; ++b) t += (double)partial[((int64_t)b * kwt + col) * row + c];
-  sums[idx] = t;
+  for (int b = lane; b < n_blocks; b += 32) t += (double)partial[((int64_t)b * kwt + col) * row + c];
+  t = warp_sum(t);
+  if (lane == 0) sums[idx] = t;
 }
 
 // utils_.py:585-592
@@ -519,7 +538,7 @@ int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t w
     default: return SLCL_ERR_INVALID_ARGUMENT;
   }
   const int total = a.n_cols * ((int)a.channels + 1);
-  class_sums_reduce_kernel<<<ceil_div(total, kThreads), kThreads, 0, stream>>>(a.partial, (int)p.grid.x, p.kwt, a.n_cols,
+  class_sums_reduce_kernel<<<ceil_div(total, kWarps), kThreads, 0, stream>>>(a.partial, (int)p.grid.x, p.kwt, a.n_cols,
                                                                               (int)a.channels, sums);
   return check_launch("slcl_class_sums");
 }
