@@ -94,6 +94,15 @@ int slcl_proto_fwd(const float* feat, const slcl_map_t* map,
                    float* stash, float* cstate, float* scal,
                    void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
+/* Fused target step: generate_pseudo_label (utils/utils_.py:597-624) and the target-side
+ * mpcl_loss_calc forward (trainer/Trainer_MPSCL.py:135,144) in ONE read of the target feature map.  Writes
+ * label [N] int64 and sel [N] fp32 exactly as slcl_pseudo_label would, and stash / cstate / scal exactly as
+ * slcl_proto_fwd(labels = label, sel = sel) would.  params->normalize must be 1. */
+int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float* centres,
+                          const slcl_proto_params_t* params, float sel_threshold,
+                          int64_t* label, float* sel, float* stash, float* cstate, float* scal,
+                          void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
 /* Data-parallel use: each rank runs slcl_proto_fwd on its shard, the
  * caller all-reduces scal[2..3] (weight sum, weighted row-loss sum) across ranks, then this
  * call recomputes scal[0] (global loss) and scal[1] (global coefficient) in place. */

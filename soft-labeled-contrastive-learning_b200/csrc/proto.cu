@@ -58,6 +58,7 @@ struct ProtoArgs {
   int64_t* out_label;         // pseudo-label mode
   float* out_sel;
   float sel_threshold;
+  int fused_target;           // forward derives label/sel itself (generate_pseudo_label fused in) and writes them out
   MarginConst mc;
 };
 
@@ -252,6 +253,32 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
         lab[0] = a.labels[pix];
       }
     }
+    if (a.fused_target) {
+      // generate_pseudo_label (utils/utils_.py:597-624) on the cosines already in registers: same
+      // arithmetic as pseudo_label_kernel (dot / n, strict >, first index wins ties)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float n = fmaxf(sqrtf(nrm[v]), 1e-12f);
+        float t1 = -INFINITY, t2 = -INFINITY;
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float cs = dot[k][v] / n;
+          if (cs > t1) { t2 = t1; t1 = cs; best = k; }
+          else if (cs > t2) { t2 = cs; }
+        }
+        lab[v] = best;
+        selv[v] = (t1 - t2 > a.sel_threshold) ? 1.0f : 0.0f;
+      }
+      if constexpr (VEC == 4) {
+        longlong2* lp = reinterpret_cast<longlong2*>(a.out_label + pix);
+        lp[0] = make_longlong2(lab[0], lab[1]);
+        lp[1] = make_longlong2(lab[2], lab[3]);
+      } else {
+        a.out_label[pix] = lab[0];
+      }
+      Vec<VEC>::store_keep(a.out_sel + pix, selv);
+    }
     float out[K + 1][VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         cosv[k] = dot[k][v] * inv_n;
-        if (a.labels != nullptr) M[k] = (lab[v] == (long long)k) ? 1.0f : 0.0f;      // :513
+        if (a.labels != nullptr || a.fused_target) M[k] = (lab[v] == (long long)k) ? 1.0f : 0.0f;      // :513
         else M[k] = a.soft_mask[(pix + v) * K + k];                                    // :517
       }
       float row = margin_row<K>(cosv, M, selv[v], inv_n, a.mc, coef);
@@ -573,6 +600,34 @@ extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const in
   })
   proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, sel != nullptr, scal);
   return check_launch("slcl_proto_fwd");
+}
+
+extern "C" int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float* centres,
+                                     const slcl_proto_params_t* params, float sel_threshold, int64_t* label, float* sel,
+                                     float* stash, float* cstate, float* scal, void* workspace, size_t workspace_bytes,
+                                     slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !centres || !params || !label || !sel || !stash || !cstate || !scal || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f) || !params->normalize)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan plan = make_plan(map, K, {feat, label, sel, stash});
+  if (workspace_bytes < slcl_proto_workspace_bytes(plan.n_total)) return SLCL_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return SLCL_ERR_INVALID_ARGUMENT;
+  ProtoArgs a = base_args(feat, map, cstate);
+  a.stash = stash;
+  a.partial = reinterpret_cast<double2*>(workspace);
+  a.mc = make_const(params);
+  a.fused_target = 1; a.sel_threshold = sel_threshold; a.out_label = label; a.out_sel = sel;
+  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, 1, cstate);
+  SLCL_DISPATCH_K(K, plan.vec, {
+    int st = ensure_smem(proto_fwd_kernel<KK, VV>, plan.smem);
+    if (st != SLCL_OK) return st;
+    proto_fwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a);
+  })
+  proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, 1, scal);
+  return check_launch("slcl_proto_fwd_target");
 }
 
 extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream_) {

@@ -52,6 +52,39 @@ class _ProtoLoss(torch.autograd.Function):
         return dfeat, None, None, None, dcen, None, None, None, None, None, None, None, None
 
 
+class _ProtoTargetStep(torch.autograd.Function):
+    """generate_pseudo_label + target mpcl_loss_calc fused (trainer/Trainer_MPSCL.py:135,144): one read of the
+    target map in the forward; backward identical to _ProtoLoss."""
+
+    @staticmethod
+    def forward(ctx, feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin, group):
+        scal, stash, cstate, label, sel = _ops.proto_fwd_target(feat.detach(), centres.detach(), sel_threshold, n_class,
+                                                                temperature, base_temperature, margin, easy_margin)
+        if group is not None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
+                dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
+                _ops.proto_rescale(scal, True)
+        ctx.save_for_backward(feat, stash, cstate, scal)
+        ctx.n_class = n_class
+        ctx.mark_non_differentiable(label, sel)
+        return scal[0], label, sel
+
+    @staticmethod
+    def backward(ctx, grad_out, _gl, _gs):
+        feat, stash, cstate, scal = ctx.saved_tensors
+        dfeat = None
+        if ctx.needs_input_grad[0]:
+            dfeat = _ops.proto_bwd(feat.detach(), stash, cstate, scal, grad_out.reshape(1), False, ctx.n_class, True)
+        return dfeat, None, None, None, None, None, None, None, None
+
+
+def proto_target_step(feat: Tensor, centres: Tensor, sel_threshold: float, *, n_class: int, temperature: float,
+                      base_temperature: float, margin: float, easy_margin: bool, group=None):
+    return _ProtoTargetStep.apply(feat, centres, float(sel_threshold), n_class, temperature, base_temperature, margin,
+                                  easy_margin, group)
+
+
 def proto_loss(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor], centres: Tensor,
                *, rows_layout: bool, n_class: int, temperature: float, base_temperature: float, margin: float,
                easy_margin: bool, normalize: bool, group=None) -> Tensor:

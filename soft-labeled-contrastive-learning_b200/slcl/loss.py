@@ -91,6 +91,21 @@ def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=Non
     return loss_func(unit, labels, centres, pixel_sel_loc=pixel_sel_loc)
 
 
+def mpcl_target_step(feas_t, class_center_feas, loss_func, pixel_sel_th=.25, group=None):
+    """Fused target step of trainer/Trainer_MPSCL.py:135,144 (an addition):
+
+        hard, mask = generate_pseudo_label(feas_t, class_center_feas, pixel_sel_th)
+        loss = mpcl_loss_calc(feas_t, hard, class_center_feas, loss_func, pixel_sel_loc=mask, tag='target')
+
+    in ONE read of ``feas_t`` (the reference reads and normalises it twice).  Returns ``(loss, hard, mask)``;
+    gradients flow to ``feas_t`` only (the reference callers pass detached centres, :145)."""
+    if not isinstance(loss_func, MPCL):
+        raise TypeError("loss_func must be an slcl.loss.MPCL")
+    kw = loss_func._kw(normalize=True)
+    kw.pop("normalize")
+    return SF.proto_target_step(feas_t, class_center_feas, pixel_sel_th, group=group, **kw)
+
+
 class ContrastiveLoss(nn.Module):
     """Centroid <-> centroid InfoNCE.  Reference: utils/loss.py:233-275.
     Bug-compatible: ``tau`` is stored and never used (:236 vs :264-265); the row

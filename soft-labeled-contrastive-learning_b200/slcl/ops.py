@@ -118,6 +118,38 @@ def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, 
     return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class))
 
 
+@torch.library.custom_op("slcl::proto_fwd_target", mutates_args=(), device_types="cuda")
+def proto_fwd_target(feat: Tensor, centres: Tensor, sel_threshold: float, n_class: int, temperature: float,
+                     base_temperature: float, margin: float,
+                     easy_margin: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (scal[4], stash, cstate, label[N] int64, sel[N]) : pseudo labels + target loss forward, one read of feat."""
+    dev = require_cuda(feat, centres)
+    lib = _lib.load()
+    feat_c, m = _map_nchw(feat)
+    n = m.batch * m.pixels
+    centres = centres.to(_F32).contiguous()
+    scal = torch.empty(4, dtype=_F32, device=dev)
+    stash = torch.empty((n_class + 1, n), dtype=_F32, device=dev)
+    cstate = torch.empty(n_class * m.channels + n_class, dtype=_F32, device=dev)
+    label = torch.empty(n, dtype=torch.int64, device=dev)
+    sel = torch.empty(n, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_proto_workspace_bytes(n), dev)
+    p = _params(n_class, temperature, base_temperature, margin, easy_margin, True)
+    with _guard(dev):
+        st = lib.slcl_proto_fwd_target(ptr(feat_c), C.byref(m), ptr(centres), C.byref(p), float(sel_threshold), ptr(label),
+                                       ptr(sel), ptr(stash), ptr(cstate), ptr(scal), ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_proto_fwd_target")
+    return scal, stash, cstate, label, sel
+
+
+@proto_fwd_target.register_fake
+def _(feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin):
+    n = feat.shape[0] * feat.shape[2] * feat.shape[3]
+    c = feat.shape[1]
+    return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class),
+            torch.empty(n, dtype=torch.int64, device=feat.device), feat.new_empty(n))
+
+
 @torch.library.custom_op("slcl::proto_rescale", mutates_args=("scal",), device_types="cuda")
 def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     """Recompute scal[0:2] from the (all-reduced) sums scal[2:4], in place."""

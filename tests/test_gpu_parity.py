@@ -566,3 +566,32 @@ def test_host_buffer_pipeline_matches_device_path(api):
         ref.backward()
         close(loss, ref, rtol=1e-5)
         grad_close(grad_h, f.grad.cpu(), rtol=1e-5)
+
+
+def test_fused_target_step_equals_two_call_sequence(api, golden):
+    """f-1: generate_pseudo_label + target mpcl_loss_calc in one read of the map == the reference call sequence."""
+    loss_mod, utils_mod = api
+    ft = cases.kat2().to(dev())
+    cc = cases.shipped_centres().to(dev())
+    mp = loss_mod.MPCL(dev(), num_class=4, temperature=.1, base_temperature=1, m=.2)
+    f = ft.clone().requires_grad_(True)
+    out, hard, sel = loss_mod.mpcl_target_step(f, cc, mp, .25)
+    out.backward()
+    assert np.array_equal(hard.cpu().numpy(), golden["kat2_label"]) and np.array_equal(sel.cpu().numpy(), golden["kat2_sel"])
+    close(out, golden["kat2_loss"], atol=1e-8)
+    grad_close(f.grad, golden["kat2_dfeas"])
+    # bit-identical to the unfused product path on a bigger, ragged map (scalar path) and a vector-path map
+    for shape, k in (((3, 20, 7, 9), 5), ((2, 128, 16, 16), 5)):
+        gen = cases.g(sum(shape))
+        x = torch.randn(*shape, generator=gen).to(dev())
+        cen = torch.randn(k, shape[1], generator=gen).to(dev())
+        mpk = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.2)
+        h2, s2 = utils_mod.generate_pseudo_label(x, cen, .05)
+        x1 = x.clone().requires_grad_(True)
+        l2 = loss_mod.mpcl_loss_calc(x1, h2, cen, mpk, pixel_sel_loc=s2, tag='target')
+        l2.backward()
+        x2 = x.clone().requires_grad_(True)
+        l1, h1, s1 = loss_mod.mpcl_target_step(x2, cen, mpk, .05)
+        l1.backward()
+        assert torch.equal(h1, h2) and torch.equal(s1, s2)
+        assert torch.equal(l1, l2) and torch.equal(x1.grad, x2.grad)
