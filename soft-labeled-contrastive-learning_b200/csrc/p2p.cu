@@ -43,13 +43,18 @@ constexpr int kColAcc = 128;       // dR accumulators: columns [128, 128 + d)
 constexpr int kColR = 384;         // resident row operand R (bf16 pairs): columns [384, 384 + d/2)
 constexpr float kLog2e = 1.4426950408889634f;
 
+#ifdef SLCL_P2P_PROFILE
+constexpr bool kProfile = true;
+#else
+constexpr bool kProfile = false;
+#endif
+
 enum Mode { kFwd = 0, kBwdRows = 1 /* dA: stats per row */, kBwdCols = 2 /* dB: stats per column */ };
 
 struct P2PArgs {
   int n_rows, n_cols, d;              // d padded to a multiple of 64
   int col_begin, cols_per_split;      // this kernel instance sweeps columns [col_begin + split*cols_per_split, ...)
   int mode;
-  int debug;                          // bring-up knobs (SLCL_P2P_DEBUG): 1 skip epilogue math, 2 skip tmem load, 4 skip MMA1
   float scale_log2;                   // log2(e) / T
   const uint32_t* rows_u32;           // resident operand, bf16 row-major [n_rows, d] viewed as 32-bit words
   const int2* row_meta;               // {label, id}
@@ -85,11 +90,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// Bring-up instrumentation (per-role barrier-wait cycle counters, read by tools/p2p_prof.py) is compiled
+// in only with -DSLCL_P2P_PROFILE; the shipped library waits without touching the clock.
+#ifdef SLCL_P2P_PROFILE
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += (unsigned long long)(clock64() - t0);
 }
+#define SLCL_PROF_NOW() clock64()
+#else
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long&) { mbar_wait(bar, parity); }
+#define SLCL_PROF_NOW() 0ll
+#endif
 // one lane of a converged warp (elect.sync): the idiom the compiler recognises for single-thread
 // issue of uniform-datapath instructions
 __device__ __forceinline__ bool elect_one() {
@@ -216,7 +229,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (SM100 UMMA), 128-byte swizzle.
@@ -324,7 +336,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     unsigned long long w0 = 0, w1 = 0;
-    const long long tstart = clock64();
+    const long long tstart = SLCL_PROF_NOW();
     const bool with_stat = a.mode == kBwdCols;
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kStages;
@@ -348,8 +360,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       }
       __syncwarp();
     }
-    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
-      a.prof[0] = (unsigned long long)(clock64() - tstart); a.prof[1] = w0; a.prof[2] = w1;
+    if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      a.prof[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); a.prof[1] = w0; a.prof[2] = w1;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -357,7 +369,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     const uint32_t idesc2 = make_idesc(a.d, 1);
     const uint32_t c_addr = smem_u32(sC), g_addr = smem_u32(sG);
     unsigned long long w0 = 0, w1 = 0, w2 = 0;
-    const long long tstart = clock64();
+    const long long tstart = SLCL_PROF_NOW();
     mbar_wait(&bars->r_full, 0);
     tc_fence_after();
     // Descriptors are built once; inside the loops only the 14-bit start-address field moves
@@ -407,8 +419,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     }
     if (bwd && elect_one()) umma_commit(&bars->acc_full);
     __syncwarp();
-    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
-      a.prof[4] = (unsigned long long)(clock64() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
+    if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      a.prof[4] = (unsigned long long)(SLCL_PROF_NOW() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
     }
   } else if (warp >= 4) {
     // ===================== epilogue: one thread per row, 32 of the 64 tile columns per warp =====================
@@ -440,7 +452,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->r_full);
     }
-    const long long tstart = clock64();
+    const long long tstart = SLCL_PROF_NOW();
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
@@ -536,9 +548,9 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       if (lane == 0) mbar_arrive(&bars->m_empty[ms]);
     }
 
-    if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
+    if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
       unsigned long long* pp = a.prof + (warp == 4 ? 8 : 12);
-      pp[0] = (unsigned long long)(clock64() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = w2;
+      pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = w2;
     }
     if (!bwd) {
       if (row_ok) {
@@ -690,8 +702,11 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
   s.cols_per_split = tiles_per_split * BN;
-  s.cluster = 1;      // measured on B200: multicast clusters (2, 4) bring no gain here -- the sweep is MMA/epilogue-bound, not L2-bound
-  { const char* e = getenv("SLCL_P2P_CLUSTER"); if (e) s.cluster = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1); }   // tuning knob
+  // Cluster size of the multicast variant.  Measured on B200 (cfg3 and 16384^2): clusters of 2 and 4 bring no
+  // gain -- the sweep is MMA-issue/epilogue-bound, not L2-bound -- so the default is 1; SLCL_P2P_CLUSTER selects
+  // 2 or 4 for experiments on other shapes.
+  s.cluster = 1;
+  { const char* e = getenv("SLCL_P2P_CLUSTER"); if (e) s.cluster = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1); }
   return s;
 }
 
@@ -707,8 +722,9 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
   a.col_begin = 0; a.cols_per_split = sw.cols_per_split;
   a.mode = mode;
-  { const char* e = getenv("SLCL_P2P_DEBUG"); a.debug = e ? atoi(e) : 0; }
+#ifdef SLCL_P2P_PROFILE
   { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
   a.scale_log2 = inv_t * kLog2e;
   a.rows_u32 = reinterpret_cast<const uint32_t*>(rows);
   a.row_meta = row_meta; a.col_meta = col_meta; a.row_stat = row_stat; a.col_stat = col_stat;

@@ -132,3 +132,20 @@ def test_shard_range_covers_batch():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_centre_state_in_checkpoint_dict(tmp_path):
+    """f-3: the [K,C] state rides in the reference-style checkpoint dict and falls back to the .npy."""
+    from slcl import state
+    src = os.path.join(ROOT, "tests", "golden", "class_center_ct_f0.npy")
+    cc = state.load_class_centers(src, device="cpu")
+    ckpt = {"epoch": 3, "model_state_dict": {}, "optimizer_state_dict": {}}
+    state.add_to_checkpoint(ckpt, cc * 2)
+    path = tmp_path / "last.pt"
+    torch.save(ckpt, path)
+    back = torch.load(path)
+    assert torch.equal(state.from_checkpoint(back, device="cpu"), cc * 2)
+    old_style = {"epoch": 3, "model_state_dict": {}, "optimizer_state_dict": {}}
+    assert torch.equal(state.from_checkpoint(old_style, device="cpu", fallback_npy=src), cc)
+    with pytest.raises(KeyError):
+        state.from_checkpoint(old_style, device="cpu")

@@ -1,4 +1,4 @@
-"""bring-up: per-role wait-cycle profile of one p2p sweep (CTA 0)."""
+"""bring-up (needs a library built with SLCL_EXTRA_NVCC_FLAGS=-DSLCL_P2P_PROFILE): per-role wait-cycle profile of one p2p sweep (CTA 0)."""
 import os, sys, torch
 sys.path.insert(0, 'soft-labeled-contrastive-learning_b200')
 dev = torch.device('cuda:0')

@@ -1,4 +1,4 @@
-"""bring-up: forward-sweep wait-cycle profile under a debug knob."""
+"""bring-up (needs a library built with SLCL_EXTRA_NVCC_FLAGS=-DSLCL_P2P_PROFILE): forward-sweep wait-cycle profile under a debug knob."""
 import os, sys, torch
 sys.path.insert(0, 'soft-labeled-contrastive-learning_b200')
 dev = torch.device('cuda:0')
