@@ -214,6 +214,24 @@ int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, in
                           const float* d_rows, const float* inv_norm, float* dfeat, slcl_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Segmentation losses on the logits: loss_calc (utils/loss.py:46-66: CrossEntropyLoss
+ * [+ jaccard_loss :11-43]) and dice_loss (:69-103) in ONE pass over logits [B,K,HW] fp32 + labels [B,HW]
+ * int64, and their fused backward.  K >= 2 (the reference's num_classes == 1 sigmoid branch is not built).
+ *   stats  [B,K,4] fp32 = per (image, class) {sum p*g, sum p*p, sum g, sum p}
+ *   losses [3]     fp32 = {cross entropy (mean over pixels), dice, jaccard}
+ *   backward: grad_losses [3] device fp32 = d/d{ce, dice, jaccard}; dlogits [B,K,HW].
+ * slcl_entropy_map: prob_2_entropy (utils/utils_.py:627-631), out = -p log2(p+1e-7)/log2(K) and/or its
+ * backward dprob = grad_out * d out / d p (either output pointer may be null).
+ * ------------------------------------------------------------------------- */
+size_t slcl_seg_workspace_bytes(int64_t batch, int64_t pixels, int n_class);
+int slcl_seg_fwd(const float* logits, const int64_t* labels, int64_t batch, int n_class, int64_t pixels,
+                 float* stats, float* losses, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+int slcl_seg_bwd(const float* logits, const int64_t* labels, int64_t batch, int n_class, int64_t pixels,
+                 const float* stats, const float* grad_losses, float* dlogits, slcl_stream_t stream);
+int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out, const float* grad_out,
+                     float* dprob, slcl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Pixel <-> pixel supervised contrastive loss (SupConLoss.forward,
  * utils/loss.py:327-387 = utils/losses.py:106-161, and its autograd backward;
  * rectangular anchors x contrast-rows generalisation of SURVEY.md 8(c)-3).

@@ -83,3 +83,12 @@ def ragged_case(seed: int = 31, b: int = 3, c: int = 20, h: int = 7, w: int = 9,
     cc = torch.randn(k, c, generator=gen)
     sel = (torch.rand(b * h * w, generator=gen) > 0.4).float()
     return ft, lab, cc, sel
+
+
+def seg_case(seed: int = 51, b: int = 3, k: int = 4, h: int = 12, w: int = 10):
+    """Segmentation logits + labels; class k-1 is absent from image 0."""
+    gen = g(seed)
+    logits = 2.0 * torch.randn(b, k, h, w, generator=gen)
+    labels = torch.randint(0, k, (b, h, w), generator=gen)
+    labels[0][labels[0] == k - 1] = 0
+    return logits, labels

@@ -142,6 +142,31 @@ def main() -> None:
         loss.backward()
         out.update(ragged_easy_loss=_np(loss), ragged_easy_dfeas=_np(f.grad))
 
+    seg = {}
+    with ref_loader.host_tensors():
+        logits, labels = cases.seg_case()
+        for name, fn in (("ce", lambda z: ref.loss_calc(z, labels, 0, False)),
+                         ("ce_jac", lambda z: ref.loss_calc(z, labels, 0, True)),
+                         ("jac", lambda z: ref.jaccard_loss(labels, z)),
+                         ("dice", lambda z: ref.dice_loss(z, labels)),
+                         ("mpscl_seg", lambda z: ref.loss_calc(z, labels, 0, False) + ref.dice_loss(z, labels))):
+            z = logits.clone().requires_grad_(True)
+            val = fn(z)
+            val.backward()
+            seg[f"seg_{name}_loss"] = _np(val)
+            seg[f"seg_{name}_dlogits"] = _np(z.grad)
+        z = logits.clone().requires_grad_(True)
+        ent = ref.prob_2_entropy(torch.softmax(z, dim=1))
+        (ent * torch.linspace(0.5, 1.5, ent.numel()).view_as(ent)).sum().backward()
+        seg["seg_entropy_map"] = _np(ent)
+        seg["seg_entropy_dlogits"] = _np(z.grad)
+    seg_path = os.path.join(cases.GOLDEN_DIR, "reference_seg_outputs.npz")
+    np.savez_compressed(seg_path, **seg)
+    print(f"wrote {seg_path}: {len(seg)} arrays")
+    for k in sorted(seg):
+        if seg[k].size == 1:
+            print(f"  {k} = {float(seg[k]):.10g}")
+
     path = os.path.join(cases.GOLDEN_DIR, "reference_outputs.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")

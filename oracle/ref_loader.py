@@ -78,6 +78,8 @@ def load():
         LocalConLoss=ref_loss.LocalConLoss, BlockConLoss=ref_loss.BlockConLoss,
         SupConLoss_dup=ref_losses.SupConLoss,
         cal_centroid=ref_utils.cal_centroid, cal_centroid_repaired=scope["cal_centroid_repaired"],
+        loss_calc=ref_loss.loss_calc, dice_loss=ref_loss.dice_loss, jaccard_loss=ref_loss.jaccard_loss,
+        prob_2_entropy=ref_utils.prob_2_entropy,
         update_class_center_iter=ref_utils.update_class_center_iter,
         generate_pseudo_label=ref_utils.generate_pseudo_label,
         class_center_file=os.path.join(REFERENCE_ROOT, "class_center_ct_f0.npy"),

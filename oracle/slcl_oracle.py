@@ -394,3 +394,40 @@ def gather_unit_rows(feat_nchw: torch.Tensor, pixel_idx: torch.Tensor, dtype=tor
     b, c, h, w = feat_nchw.shape
     rows = feat_nchw.permute(0, 2, 3, 1).reshape(-1, c)[pixel_idx]
     return F.normalize(rows, p=2, dim=1).to(dtype)
+
+
+# --------------------------------------------------------------------------
+# f-2  segmentation losses                     utils/loss.py:11-103, utils/utils_.py:627-631
+# --------------------------------------------------------------------------
+def jaccard_loss(true: torch.Tensor, logits: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """utils/loss.py:11-43 (num_classes > 1 branch)."""
+    k = logits.shape[1]
+    onehot = F.one_hot(true.reshape(true.shape[0], *logits.shape[2:]).long(), k).movedim(-1, 1).to(logits.dtype)   # :34-35
+    probas = F.softmax(logits, dim=1)                              # :36
+    dims = (0, 2, 3)
+    inter = (probas * onehot).sum(dims)                            # :39
+    card = (probas + onehot).sum(dims)                             # :40
+    return 1 - (inter / (card - inter + eps)).mean()               # :41-43
+
+
+def loss_calc(pred: torch.Tensor, label: torch.Tensor, jaccard: bool = False) -> torch.Tensor:
+    """utils/loss.py:46-66."""
+    loss = F.cross_entropy(pred, label.long())
+    return loss + jaccard_loss(label, pred) if jaccard else loss
+
+
+def dice_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """utils/loss.py:69-103."""
+    n, c, h, w = pred.shape
+    onehot = torch.zeros(n, c, h, w, dtype=pred.dtype).scatter_(1, target.unsqueeze(1).long(), 1)    # :77-79
+    probs = F.softmax(pred, dim=1)                                 # :88
+    num = (probs * onehot).sum(3).sum(2)                           # :89-91
+    den1 = (probs * probs).sum(3).sum(2)                           # :93-95
+    den2 = (onehot * onehot).sum(3).sum(2)                         # :97-99
+    dice = 2.0 * (num / (den1 + den2 + 1e-5))                      # :101
+    return 1 - dice.sum() / dice.size(0) / c                       # :103-104
+
+
+def prob_2_entropy(prob: torch.Tensor) -> torch.Tensor:
+    """utils/utils_.py:627-631."""
+    return -prob * torch.log2(prob + 1e-7) / math.log2(prob.shape[1])

@@ -535,3 +535,89 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
 @p2p_bwd.register_fake
 def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b):
     return (shift.new_empty((a.shape[0] if need_a else 0, dim)), shift.new_empty((b.shape[0] if need_b else 0, dim)))
+
+
+# ----------------------------------------------------------------------------
+# segmentation losses / entropy map
+# ----------------------------------------------------------------------------
+@torch.library.custom_op("slcl::seg_fwd", mutates_args=(), device_types="cuda")
+def seg_fwd(logits: Tensor, labels: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> (losses[3] = {ce, dice, jaccard}, stats[B,K,4])"""
+    dev = require_cuda(logits, labels)
+    lib = _lib.load()
+    if logits.dim() != 4 or logits.dtype != _F32:
+        raise ValueError("logits must be float32 [B, K, H, W]")
+    logits = logits.contiguous()
+    b, k, h, w = logits.shape
+    labels = labels.reshape(b, -1).long().contiguous()
+    if labels.shape[1] != h * w:
+        raise ValueError("labels must be [B, H, W] at the resolution of the logits")
+    stats = torch.empty((b, k, 4), dtype=_F32, device=dev)
+    losses = torch.empty(3, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_seg_workspace_bytes(b, h * w, k), dev)
+    with _guard(dev):
+        st = lib.slcl_seg_fwd(ptr(logits), ptr(labels), b, k, h * w, ptr(stats), ptr(losses), ptr(ws), ws.numel(),
+                              stream_ptr(dev))
+    check(st, "slcl_seg_fwd")
+    return losses, stats
+
+
+@seg_fwd.register_fake
+def _(logits, labels):
+    return logits.new_empty(3), logits.new_empty((logits.shape[0], logits.shape[1], 4))
+
+
+@torch.library.custom_op("slcl::seg_bwd", mutates_args=(), device_types="cuda")
+def seg_bwd(logits: Tensor, labels: Tensor, stats: Tensor, grad_losses: Tensor) -> Tensor:
+    dev = require_cuda(logits, labels, stats, grad_losses)
+    lib = _lib.load()
+    logits = logits.contiguous()
+    b, k, h, w = logits.shape
+    labels = labels.reshape(b, -1).long().contiguous()
+    g = grad_losses.to(_F32).reshape(3).contiguous()
+    dlogits = torch.empty_like(logits)
+    with _guard(dev):
+        st = lib.slcl_seg_bwd(ptr(logits), ptr(labels), b, k, h * w, ptr(stats.contiguous()), ptr(g), ptr(dlogits),
+                              stream_ptr(dev))
+    check(st, "slcl_seg_bwd")
+    return dlogits
+
+
+@seg_bwd.register_fake
+def _(logits, labels, stats, grad_losses):
+    return torch.empty_like(logits)
+
+
+@torch.library.custom_op("slcl::entropy_map", mutates_args=(), device_types="cuda")
+def entropy_map(prob: Tensor) -> Tensor:
+    dev = require_cuda(prob)
+    lib = _lib.load()
+    p = prob.to(_F32).contiguous()
+    out = torch.empty_like(p)
+    with _guard(dev):
+        st = lib.slcl_entropy_map(ptr(p), p.numel(), p.shape[1], ptr(out), None, None, stream_ptr(dev))
+    check(st, "slcl_entropy_map")
+    return out
+
+
+@entropy_map.register_fake
+def _(prob):
+    return torch.empty_like(prob)
+
+
+@torch.library.custom_op("slcl::entropy_map_bwd", mutates_args=(), device_types="cuda")
+def entropy_map_bwd(prob: Tensor, grad_out: Tensor) -> Tensor:
+    dev = require_cuda(prob, grad_out)
+    lib = _lib.load()
+    p = prob.to(_F32).contiguous()
+    g = grad_out.to(_F32).contiguous()
+    dp = torch.empty_like(p)
+    with _guard(dev):
+        st = lib.slcl_entropy_map(ptr(p), p.numel(), p.shape[1], None, ptr(g), ptr(dp), stream_ptr(dev))
+    check(st, "slcl_entropy_map")
+    return dp
+
+
+@entropy_map_bwd.register_fake
+def _(prob, grad_out):
+    return torch.empty_like(prob)

@@ -595,3 +595,49 @@ def test_fused_target_step_equals_two_call_sequence(api, golden):
         l1.backward()
         assert torch.equal(h1, h2) and torch.equal(s1, s2)
         assert torch.equal(l1, l2) and torch.equal(x1.grad, x2.grad)
+
+
+# ---------------------------------------------------------------------------
+# f-2: segmentation losses + entropy map
+# ---------------------------------------------------------------------------
+def test_seg_losses_vs_reference_golden_gpu():
+    import os
+    from slcl import seg
+    gold = dict(np.load(os.path.join(cases.GOLDEN_DIR, "reference_seg_outputs.npz")))
+    logits, labels = cases.seg_case()
+    lab = labels.to(dev())
+    for name, fn in (("ce", lambda z: seg.loss_calc(z, lab, 0, False)),
+                     ("ce_jac", lambda z: seg.loss_calc(z, lab, 0, True)),
+                     ("jac", lambda z: seg.jaccard_loss(lab, z)),
+                     ("dice", lambda z: seg.dice_loss(z, lab)),
+                     ("mpscl_seg", lambda z: seg.loss_calc(z, lab, 0, False) + seg.dice_loss(z, lab))):
+        z = logits.to(dev()).requires_grad_(True)
+        val = fn(z)
+        (val * 1.5).backward()
+        close(val, gold[f"seg_{name}_loss"])
+        grad_close(z.grad / 1.5, gold[f"seg_{name}_dlogits"])
+    z = logits.to(dev()).requires_grad_(True)
+    ent = seg.prob_2_entropy(torch.softmax(z, dim=1))
+    (ent * torch.linspace(0.5, 1.5, ent.numel(), device=dev()).view_as(ent)).sum().backward()
+    close(ent, gold["seg_entropy_map"], atol=1e-7)
+    grad_close(z.grad, gold["seg_entropy_dlogits"])
+    # all three losses from ONE pass
+    z = logits.to(dev())
+    all3 = seg.seg_losses(z, lab)
+    close(all3, [float(gold["seg_ce_loss"]), float(gold["seg_dice_loss"]), float(gold["seg_jac_loss"])])
+
+
+@pytest.mark.parametrize("b,k,h,w", [(2, 4, 224, 224), (3, 5, 33, 33), (1, 2, 7, 5)])
+def test_seg_losses_vs_oracle_shapes(b, k, h, w):
+    from slcl import seg
+    gen = cases.g(b * 1000 + k * 100 + h)
+    logits = 1.5 * torch.randn(b, k, h, w, generator=gen)
+    labels = torch.randint(0, k, (b, h, w), generator=gen)
+    zo = logits.clone().requires_grad_(True)
+    ref = O.loss_calc(zo, labels, True) + 0.5 * O.dice_loss(zo, labels)
+    ref.backward()
+    z = logits.to(dev()).requires_grad_(True)
+    out = seg.loss_calc(z, labels.to(dev()), 0, True) + 0.5 * seg.dice_loss(z, labels.to(dev()))
+    out.backward()
+    close(out, ref)
+    grad_close(z.grad, zo.grad)

@@ -225,3 +225,29 @@ def test_rmc_partitions_balanced_and_reproducible():
     w = [(probs * (pid.view(2, 1, 12, 10) == p)).sum(dim=(0, 2, 3)) for p in range(2)]
     recombined = (parts[0] * w[0][:, None] + parts[1] * w[1][:, None]) / (w[0] + w[1])[:, None]
     close(recombined, whole, rtol=1e-4, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def seg_golden():
+    import os
+    return dict(np.load(os.path.join(cases.GOLDEN_DIR, "reference_seg_outputs.npz")))
+
+
+def test_seg_losses_vs_reference_golden(seg_golden):
+    """f-2: loss_calc / jaccard_loss / dice_loss / prob_2_entropy restatements vs the reference's outputs."""
+    logits, labels = cases.seg_case()
+    for name, fn in (("ce", lambda z: O.loss_calc(z, labels, False)),
+                     ("ce_jac", lambda z: O.loss_calc(z, labels, True)),
+                     ("jac", lambda z: O.jaccard_loss(labels, z)),
+                     ("dice", lambda z: O.dice_loss(z, labels)),
+                     ("mpscl_seg", lambda z: O.loss_calc(z, labels, False) + O.dice_loss(z, labels))):
+        z = logits.clone().requires_grad_(True)
+        val = fn(z)
+        val.backward()
+        close(val, seg_golden[f"seg_{name}_loss"])
+        close(z.grad, seg_golden[f"seg_{name}_dlogits"], atol=1e-8)
+    z = logits.clone().requires_grad_(True)
+    ent = O.prob_2_entropy(torch.softmax(z, dim=1))
+    (ent * torch.linspace(0.5, 1.5, ent.numel()).view_as(ent)).sum().backward()
+    close(ent, seg_golden["seg_entropy_map"], atol=1e-8)
+    close(z.grad, seg_golden["seg_entropy_dlogits"], atol=1e-7)
