@@ -92,3 +92,14 @@ def seg_case(seed: int = 51, b: int = 3, k: int = 4, h: int = 12, w: int = 10):
     labels = torch.randint(0, k, (b, h, w), generator=gen)
     labels[0][labels[0] == k - 1] = 0
     return logits, labels
+
+
+def iscl_case(seed: int = 71, n: int = 96, d: int = 48, k: int = 4):
+    """Mix-up batch for ISCL: features, two label sets, dominant labels, lambdas."""
+    gen = g(seed)
+    feats = torch.randn(n, d, generator=gen)
+    l1 = torch.randint(0, k, (n,), generator=gen)
+    l2 = l1[torch.randperm(n, generator=gen)]
+    lam = torch.rand(n, generator=gen)
+    dom = torch.where(lam >= 0.5, l1, l2)
+    return feats, l1, l2, dom, lam

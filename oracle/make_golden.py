@@ -160,6 +160,12 @@ def main() -> None:
         (ent * torch.linspace(0.5, 1.5, ent.numel()).view_as(ent)).sum().backward()
         seg["seg_entropy_map"] = _np(ent)
         seg["seg_entropy_dlogits"] = _np(z.grad)
+    feats, l1, l2, dom, lam = cases.iscl_case()
+    f = feats.clone().requires_grad_(True)
+    val = ref.ISCL(0.5)(f, l1, l2, dom, lam)
+    val.backward()
+    seg["iscl_loss"] = _np(val)
+    seg["iscl_dfeat"] = _np(f.grad)
     seg_path = os.path.join(cases.GOLDEN_DIR, "reference_seg_outputs.npz")
     np.savez_compressed(seg_path, **seg)
     print(f"wrote {seg_path}: {len(seg)} arrays")

@@ -76,7 +76,7 @@ def load():
         MPCL=ref_loss.MPCL, mpcl_loss_calc=ref_loss.mpcl_loss_calc,
         ContrastiveLoss=ref_loss.ContrastiveLoss, SupConLoss=ref_loss.SupConLoss,
         LocalConLoss=ref_loss.LocalConLoss, BlockConLoss=ref_loss.BlockConLoss,
-        SupConLoss_dup=ref_losses.SupConLoss,
+        SupConLoss_dup=ref_losses.SupConLoss, ISCL=ref_losses.InterpolatedSupervisedContrastiveLoss,
         cal_centroid=ref_utils.cal_centroid, cal_centroid_repaired=scope["cal_centroid_repaired"],
         loss_calc=ref_loss.loss_calc, dice_loss=ref_loss.dice_loss, jaccard_loss=ref_loss.jaccard_loss,
         prob_2_entropy=ref_utils.prob_2_entropy,

@@ -431,3 +431,22 @@ def dice_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 def prob_2_entropy(prob: torch.Tensor) -> torch.Tensor:
     """utils/utils_.py:627-631."""
     return -prob * torch.log2(prob + 1e-7) / math.log2(prob.shape[1])
+
+
+# --------------------------------------------------------------------------
+# f-4  InterpolatedSupervisedContrastiveLoss           utils/losses.py:6-81
+# --------------------------------------------------------------------------
+def iscl_loss(features, labels_1, labels_2, dominant_labels, lambdas, temperature, normalize=True):
+    if normalize:                                                  # :44-45
+        features = F.normalize(features, dim=-1, p=2)
+    s = features @ features.t() / temperature                      # :47-48
+    s = s - s.max(dim=1, keepdim=True).values.detach()             # :50-51
+    n = s.shape[0]
+    off = ~torch.eye(n, dtype=torch.bool, device=s.device)         # :67-68
+
+    def per_sample(query):                                         # :61-81
+        pos = (query.unsqueeze(1) == dominant_labels.unsqueeze(0)) & off
+        cnt = pos.sum(-1).to(s.dtype)
+        return -(1 / cnt) * (pos * (s - torch.log((off * torch.exp(s)).sum(-1, keepdim=True)))).sum(-1)
+
+    return (lambdas * per_sample(labels_1) + (1 - lambdas) * per_sample(labels_2)).mean()      # :53-59

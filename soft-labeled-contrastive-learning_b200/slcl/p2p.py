@@ -55,8 +55,10 @@ class _P2PLoss(torch.autograd.Function):
 
 
 def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False):
+    """``same_rows``: anchors and contrast rows are the same gathered rows (one gather); their labels may
+    still differ (ISCL compares query labels with the anchors' dominant labels)."""
     meta_a = ops.pad_meta(lab_a, id_a)
-    meta_b = meta_a if same_rows else ops.pad_meta(lab_b, id_b)
+    meta_b = meta_a if (same_rows and lab_b is lab_a) else ops.pad_meta(lab_b, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
                           float(temperature), bool(normalize), bool(same_rows))
 
@@ -198,3 +200,26 @@ def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int,
     fg = (la != 0).float()
     weight = fg / fg.sum()
     return p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True)
+
+
+class InterpolatedSupervisedContrastiveLoss(nn.Module):
+    """ISCL on [N, d] feature vectors (reference utils/losses.py:6-81): mix-up supervised
+    contrastive loss -- two label sets over the SAME Gram matrix, mixed with lambda.  Each term is one sweep of
+    the tensor-core kernel with different row (query) labels and the dominant labels on the columns."""
+
+    def __init__(self, temperature):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, features, labels_1, labels_2, dominant_labels, lambdas, normalize=True):
+        n, d = features.shape
+        dev = features.device
+        fmap = features.reshape(n, d, 1, 1)                 # rows [N,d] are an NCHW map with HW = 1
+        idx = torch.arange(n, device=dev)
+        ids = idx.to(torch.int32)
+        lam = lambdas.to(torch.float32).reshape(-1)
+        dom = dominant_labels.reshape(-1)
+        t1 = p2p_loss(fmap, idx, idx, labels_1.reshape(-1), dom, ids, ids, lam / n, self.temperature, normalize, same_rows=True)
+        t2 = p2p_loss(fmap, idx, idx, labels_2.reshape(-1), dom, ids, ids, (1.0 - lam) / n, self.temperature, normalize,
+                      same_rows=True)
+        return t1 + t2                                       # :55-59 (losses.mean())

@@ -641,3 +641,16 @@ def test_seg_losses_vs_oracle_shapes(b, k, h, w):
     out.backward()
     close(out, ref)
     grad_close(z.grad, zo.grad)
+
+
+def test_iscl_vs_reference_golden_gpu():
+    """f-4: ISCL = two sweeps of the tensor-core kernel (bf16 inputs: rtol 2e-2)."""
+    import os
+    from slcl import losses
+    gold = dict(np.load(os.path.join(cases.GOLDEN_DIR, "reference_seg_outputs.npz")))
+    feats, l1, l2, dom, lam = cases.iscl_case()
+    f = feats.to(dev()).requires_grad_(True)
+    val = losses.InterpolatedSupervisedContrastiveLoss(0.5)(f, l1.to(dev()), l2.to(dev()), dom.to(dev()), lam.to(dev()))
+    val.backward()
+    close(val, gold["iscl_loss"], rtol=P2P_RTOL)
+    grad_close(f.grad, gold["iscl_dfeat"], rtol=P2P_RTOL, floor=0.5)

@@ -251,3 +251,12 @@ def test_seg_losses_vs_reference_golden(seg_golden):
     (ent * torch.linspace(0.5, 1.5, ent.numel()).view_as(ent)).sum().backward()
     close(ent, seg_golden["seg_entropy_map"], atol=1e-8)
     close(z.grad, seg_golden["seg_entropy_dlogits"], atol=1e-7)
+
+
+def test_iscl_vs_reference_golden(seg_golden):
+    feats, l1, l2, dom, lam = cases.iscl_case()
+    f = feats.clone().requires_grad_(True)
+    val = O.iscl_loss(f, l1, l2, dom, lam, 0.5)
+    val.backward()
+    close(val, seg_golden["iscl_loss"])
+    close(f.grad, seg_golden["iscl_dfeat"], atol=1e-8)
