@@ -469,9 +469,15 @@ def p2p_kernels(dev, gen):
     pick = torch.randperm(M, device=dev, generator=gen)[:A]
     a, la, ia = b[pick].contiguous(), lb[pick].contiguous(), ib[pick].contiguous()
     fg = (la != 0).float()
-    plan = P2PPlan(a, b, d, slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib), torch.full((A,), 1.0 / T, device=dev),
-                   fg / fg.sum(), T)
+    shift, weight = torch.full((A,), 1.0 / T, device=dev), fg / fg.sum()
+    meta_a, meta_b = slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib)
+    selfcol, selfrow = slcl_ops.self_maps(ia, ib)
+    # headline: the analytic sweeps (class-index labels; forward keeps U, backward = one dB sweep)
+    plan = P2PPlan(a, b, d, meta_a, meta_b, shift, weight, T, n_class=5, a_selfcol=selfcol, b_selfrow=selfrow)
     graph = plan.capture_graph()
+    # general-label sweeps (per-element {label, id} tests; what unlabelled SupCon / ISCL use)
+    gplan = P2PPlan(a, b, d, meta_a, meta_b, shift, weight, T)
+    ggraph = gplan.capture_graph()
 
     def timed(fn, iters=20):
         for _ in range(3):
@@ -486,9 +492,11 @@ def p2p_kernels(dev, gen):
         return s.elapsed_time(e) / iters
 
     out = {}
-    for name, fn, flops in (("cfg3 p2p forward (A4096 x M16384 x d256, bf16 tcgen05)", plan.forward, 2.0 * A * M * d),
-                            ("cfg3 p2p backward (dA + dB, S recomputed)", plan.backward, 6.0 * A * M * d),
-                            ("cfg3 p2p fwd+bwd, one CUDA graph", graph.replay, 8.0 * A * M * d)):
+    for name, fn, flops in (("cfg3 p2p forward only (A4096 x M16384 x d256, bf16 tcgen05)", plan.forward_only, 2.0 * A * M * d),
+                            ("cfg3 p2p forward keeping U for the backward (S + E.B)", plan.forward, 4.0 * A * M * d),
+                            ("cfg3 p2p backward (dB sweep: S recomputed + G^T.A; dA from U)", plan.backward, 4.0 * A * M * d),
+                            ("cfg3 p2p fwd+bwd, one CUDA graph", graph.replay, 8.0 * A * M * d),
+                            ("cfg3 p2p fwd+bwd, general labels, one CUDA graph", ggraph.replay, 8.0 * A * M * d)):
         ms = timed(fn)
         tf = flops / (ms * 1e-3) / 1e12
         out[name] = {"ms": ms, "algorithmic_flop": flops, "achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / tf_peak,

@@ -247,6 +247,17 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *   shift  [A] fp32: any upper bound of S_ij over j (e.g. ||a_i|| max_j||b_j|| / T);
  *     exponentials are evaluated as exp(S - shift), the result is shift-invariant.
  *   weight [A] fp32: w_i of the final reduction (fg_i / sum fg, :382-384, or 1/A).
+ *   n_class: 0 = general labels (any int32; self pairs and positives are tested per element from
+ *     the {label, id} pairs; a_selfcol / b_selfrow / u / label_sums must be null).
+ *     1..8 = "analytic" mode for class-index labels in [0, n_class) and UNIQUE ids, weights >= 0: the
+ *     positive-pair terms are rank-n_class and are evaluated outside the tensor-core sweeps from per-class row
+ *     sums, the self pair is removed afterwards with one dot product per anchor.  The ids inside the meta arrays
+ *     are then unused; instead
+ *       a_selfcol [A] int32: the contrast row holding anchor i's own pixel, or -1 (null: no anchor is a contrast row)
+ *       b_selfrow [M] int32: its inverse (anchor whose pixel contrast row j is, or -1); both or none.
+ *       u [A, dp] fp32, label_sums [n_class, dp + 1] fp32 (both or none): extra forward OUTPUTS
+ *         U_i = sum_{j != self} exp(S_ij - shift_i) b_j  and  {sum_{lab_j = k} b_j, #{lab_j = k}}; handing them back
+ *         to slcl_p2p_bwd saves the backward one of its two sweeps (it regenerates them when null).
  * forward : stats [A,3] = {sum_j exp(S_ij - shift_i), sum_pos S_ij * T, #pos},
  *           loss [1] = sum_i w_i (shift_i + log stats_i0 - stats_i1/(T stats_i2)).
  * backward: d_a [A, dim] and/or d_b [M, dim] fp32 = dL/da, dL/db for dL/dloss = *grad_out
@@ -254,13 +265,14 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  * ------------------------------------------------------------------------- */
 size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast, int64_t dim_padded);
 int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                 const int32_t* a_meta, const int32_t* b_meta, const float* shift, const float* weight,
-                 float temperature, float* stats, float* loss,
-                 void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+                 const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
+                 const float* shift, const float* weight, float temperature, float* stats, float* loss,
+                 float* u, float* label_sums, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                 int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const float* shift, const float* weight,
-                 float temperature, const float* stats, const float* grad_out, float* d_a, float* d_b,
-                 void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+                 int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
+                 const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
+                 const float* stats, const float* u, const float* label_sums, const float* grad_out,
+                 float* d_a, float* d_b, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
 #ifdef __cplusplus
 }

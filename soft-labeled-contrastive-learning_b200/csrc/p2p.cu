@@ -7,17 +7,27 @@
 //   (SURVEY.md 8(c)-3).
 //
 // Roofline: tensor core.  Flash-attention style: the similarity matrix never exists in memory.
-//   One CTA owns a 128-row tile of the "row operand" R (resident in shared memory) and streams
-//   64-row tiles of the "column operand" Cm through a 3-stage TMA ring.
+//   One CTA owns a 128-row tile of the "row operand" R (resident in TENSOR MEMORY as the A operand of
+//   MMA1) and streams 64-row tiles of the "column operand" Cm through a TMA ring in shared memory.
 //     MMA1 (tcgen05.mma, bf16 -> fp32 TMEM):  S[128 x 64] = R_tile . Cm_tile^T        (K = d)
-//     epilogue warps (tcgen05.ld, one thread per row): temperature, self/positive masks from
-//       labels + pixel ids, exp -> row statistics (forward) or the gradient tile G (backward),
-//       G is written as a bf16 K-major swizzled smem operand
-//     MMA2 (backward only):  dR[128 x d] += G[128 x 64] . Cm_tile[64 x d]   (Cm tile re-used from
-//       shared memory as an MN-major B operand; accumulators stay in TMEM for the whole sweep)
+//     epilogue warps (tcgen05.ld, one thread per row): exp2 of the scaled, shifted similarities ->
+//       row sums (forward) and/or the bf16 tile G, written back INTO TENSOR MEMORY over the S columns it
+//       was computed from (tcgen05.st)
+//     MMA2:  D[128 x d] += G[128 x 64] . Cm_tile[64 x d]   (A = G from tensor memory, B = the Cm tile
+//       re-read from shared memory as an MN-major operand; accumulators stay in TMEM for the whole sweep)
 //   S is double-buffered in TMEM so MMA1 of tile t+1 overlaps the epilogue of tile t.
-//   The same kernel runs forward (rows = anchors), dA (rows = anchors) and dB (rows = contrast
-//   rows, columns = anchors: per-column statistics).
+//
+// Two families of sweeps share the kernel (template parameter MODE):
+//   * "analytic" (labels are class indices 0..K-1, K <= 8; ids unique): the positive-pair terms of loss and
+//     gradient are rank-K and are taken OUT of the sweep --
+//         sum_{j in pos(i)} S_ij = a_i . Bsum[lab_i] - [self]            Bsum[k] = sum_{lab_j = k} b_j
+//         dA_i = alpha_i U_i - beta_i (Bsum[lab_i] - [self] b_self)      U_i = sum_j e_ij b_j
+//         dB_j = sum_i alpha_i e_ij a_i - ABsum[lab_j] + [self] ...      ABsum[k] = sum_{lab_i = k} beta_i a_i
+//     so the epilogue is FFMA + EX2 (+ FADD) per element with no integer work, the forward sweep also
+//     produces U (its MMA2), and the whole backward is ONE more sweep (dB).  Tensor work = 8 A M d flop,
+//     exactly the algorithmic count (S is formed twice, not three times).
+//   * "general" (arbitrary integer labels, e.g. the unlabelled SupCon mode where the label is the pixel
+//     position): self pairs and positives are decided per element from {label, id} pairs.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -33,15 +43,17 @@ namespace {
 constexpr int BM = 128;            // rows per CTA (UMMA M)
 constexpr int BN = 64;             // streamed rows (S tile columns) per step
 constexpr int KCH = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int kStages = 5;
+constexpr int kStages = 6;
 constexpr int kMaxD = 256;
 constexpr int kEpiWarps = 8;       // warps 4..11; (warp % 4) selects the TMEM lane quarter
 constexpr int kThreads = 32 * (4 + kEpiWarps);
 constexpr int kTmemCols = 512;
-constexpr int kColS = 0;           // S double buffer: columns [0,64) and [64,128)
-constexpr int kColAcc = 128;       // dR accumulators: columns [128, 128 + d)
+constexpr int kColS = 0;           // S double buffer: columns [0,64) and [64,128); G(t) overwrites S(t) in place
+constexpr int kColAcc = 128;       // MMA2 accumulators: columns [128, 128 + d)
 constexpr int kColR = 384;         // resident row operand R (bf16 pairs): columns [384, 384 + d/2)
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kMaxLabelClasses = 8;     // analytic sweeps: labels in [0, K), K <= 8
+constexpr float kShiftOff = 1.0e30f;    // column shift that switches a column off (exp2(-1e30) = 0)
 
 #ifdef SLCL_P2P_PROFILE
 constexpr bool kProfile = true;
@@ -49,20 +61,34 @@ constexpr bool kProfile = true;
 constexpr bool kProfile = false;
 #endif
 
-enum Mode { kFwd = 0, kBwdRows = 1 /* dA: stats per row */, kBwdCols = 2 /* dB: stats per column */ };
+enum Mode {
+  kGenFwd = 0,    // general: row statistics {Zs, P_raw, n} with per-element {label, id} tests
+  kGenRows = 1,   // general: dA sweep, statistics per row
+  kGenCols = 2,   // general: dB sweep, statistics per column
+  kAnaFwd = 3,    // analytic: row sums of exp only
+  kAnaFwdU = 4,   // analytic: row sums of exp + U = E . B (MMA2)
+  kAnaCols = 5    // analytic: dB sweep, G = exp2(s * scale - colshift)  (alpha folded into the shift)
+};
+template <int MODE> struct ModeTraits {
+  static constexpr bool kMma2 = MODE == kGenRows || MODE == kGenCols || MODE == kAnaFwdU || MODE == kAnaCols;
+  static constexpr bool kRowSums = MODE == kGenFwd || MODE == kAnaFwd || MODE == kAnaFwdU;
+  static constexpr bool kColRing = MODE == kGenFwd || MODE == kGenRows || MODE == kGenCols || MODE == kAnaCols;
+  static constexpr int kStatN = MODE == kGenFwd ? 3 : 1;      // floats per row and slot in stat_partial
+};
 
 struct P2PArgs {
   int n_rows, n_cols, d;              // d padded to a multiple of 64
-  int col_begin, cols_per_split;      // this kernel instance sweeps columns [col_begin + split*cols_per_split, ...)
-  int mode;
+  int cols_per_split;                 // CTA (x, y) sweeps columns [y * cols_per_split, ...)
   float scale_log2;                   // log2(e) / T
   const uint32_t* rows_u32;           // resident operand, bf16 row-major [n_rows, d] viewed as 32-bit words
-  const int2* row_meta;               // {label, id}
+  const int2* row_meta;               // general modes: {label, id}
   const int2* col_meta;
-  const float4* row_stat;             // kFwd: {shift*log2e,-,-,-}; kBwdRows: {shift*log2e, alpha, beta, -}
-  const float4* col_stat;             // kBwdCols: {shift*log2e, alpha, beta, -}
-  float* stat_partial;                // kFwd: [n_slots][n_rows][3]  (Zs, P_raw, n)
-  float* grad_partial;                // bwd:  [n_splits][n_rows][d] fp32
+  const float* row_shift;             // kGenFwd / kAnaFwd / kAnaFwdU: shift [n_rows] in natural-log units
+  const float4* row_stat;             // kGenRows: {shift*log2e, alpha, beta, -}
+  const float4* col_stat;             // kGenCols: {shift*log2e, alpha, beta, -}, padded to 64 entries
+  const float* col_shift;             // kAnaCols: shift*log2e - log2(alpha) per column, padded to 64 entries
+  float* stat_partial;                // row sums: [n_slots][n_rows][kStatN]
+  float* grad_partial;                // MMA2 modes: [n_splits][n_rows][d] fp32
   unsigned long long* prof;           // bring-up: per-role wait-cycle counters of CTA (0,0), or null
 };
 
@@ -251,57 +277,66 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn_major) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // Column metadata of one 64-column tile.  The TMA producer brings it in with 1-D bulk copies into a
 // kMetaSlots-deep ring of its own (the epilogue reads it after the tile's smem stage has already been
 // handed back), so the epilogue warps never issue a global load.  The caller pads the metadata arrays
-// to a multiple of 64 entries; pad entries carry id INT_MIN (masked).
+// to a multiple of 64 entries; pad entries carry id INT_MIN (masked) / shift kShiftOff.
 constexpr int kMetaSlots = 4;
 struct __align__(128) ColMeta {
-  float4 stat[BN];      // kBwdCols: {shift*log2e, alpha, beta, -}
-  int2 meta[BN];        // {label, id}
+  float4 stat[BN];      // kGenCols: {shift*log2e, alpha, beta, -};  kAnaCols: the first 64 floats = column shifts
+  int2 meta[BN];        // general modes: {label, id}
 };
 
 struct __align__(8) Barriers {
   uint64_t r_full;
   uint64_t c_full[kStages], c_empty[kStages];
   uint64_t s_full[2], s_empty[2];
-  uint64_t g_full[2], g_empty[2];
+  uint64_t g_full[2];
   uint64_t acc_full;
   uint64_t m_full[kMetaSlots], m_empty[kMetaSlots];
   uint32_t tmem_base;
 };
 
-// dynamic smem carve-up (1024-byte aligned tiles)
-//   (the resident row operand R lives in tensor memory, not here)
+// dynamic smem carve-up (1024-byte aligned tiles); R and G live in tensor memory
 //   Cm  : [kStages][d/64][64 rows][128 B]
-//   G   : [2][128 rows][128 B]
 __host__ __device__ inline size_t smem_bytes_for(int d) {
   const size_t kc = d / KCH;
-  return 1024 /*align slack*/ + (size_t)kStages * kc * BN * 128 + 2 * BM * 128 + kMetaSlots * sizeof(ColMeta) +
-         sizeof(Barriers) + 64;
+  return 1024 /*align slack*/ + (size_t)kStages * kc * BN * 128 + kMetaSlots * sizeof(ColMeta) + sizeof(Barriers) + 64;
 }
 
 // CS = thread-block-cluster size along the row-tile axis.  The CS CTAs of a cluster sweep the same
 // column tiles in lock step: each one fetches 1/CS of every column tile and TMA-multicasts it to all,
 // so the L2 -> SM traffic of the streamed operand drops CS-fold.
-template <int CS>
+template <int CS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
+p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
+  using MT = ModeTraits<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const int kc = a.d / KCH;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sC = base;
-  uint8_t* sG = sC + (size_t)kStages * kc * BN * 128;
-  ColMeta* sMeta = reinterpret_cast<ColMeta*>(sG + 2 * BM * 128);
+  ColMeta* sMeta = reinterpret_cast<ColMeta*>(sC + (size_t)kStages * kc * BN * 128);
   Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * BM;
   const int split = blockIdx.y;
-  const int col0 = a.col_begin + split * a.cols_per_split;
+  const int col0 = split * a.cols_per_split;
   const int col_end = min(a.n_cols, col0 + a.cols_per_split);
   const int n_tiles = (col_end - col0 + BN - 1) / BN;
-  const bool bwd = a.mode != kFwd;
   // Every CTA sweeps the same column tiles; start each one at a different tile so the CTAs do not
   // all hit the same L2 lines at the same moment (the sums do not depend on the sweep order).
   const int rot = (int)(((blockIdx.x / CS) * 37u + blockIdx.y * 11u) % (unsigned)n_tiles);
@@ -317,7 +352,6 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       mbar_init(&bars->s_full[s], 1);
       mbar_init(&bars->s_empty[s], kEpiWarps);
       mbar_init(&bars->g_full[s], kEpiWarps);
-      mbar_init(&bars->g_empty[s], 1);
     }
     mbar_init(&bars->acc_full, 1);
     for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&bars->m_full[s], 1); mbar_init(&bars->m_empty[s], kEpiWarps); }
@@ -337,12 +371,11 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     // ===================== TMA producer =====================
     unsigned long long w0 = 0, w1 = 0;
     const long long tstart = SLCL_PROF_NOW();
-    const bool with_stat = a.mode == kBwdCols;
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kStages;
       const int ms = t % kMetaSlots;
       mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ 1, w0);
-      mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
+      if (MT::kColRing) mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
       if (elect_one()) {
         mbar_expect_tx(&bars->c_full[s], (uint32_t)kc * BN * 128);
         uint8_t* dst = sC + (size_t)s * kc * BN * 128;
@@ -354,9 +387,15 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
             tma_load_2d_mc(dst + (size_t)c * BN * 128 + (size_t)crank * kSlice * 128, &map_cols, &bars->c_full[s], c * KCH,
                            tile_col(t) + (int)crank * kSlice, kAllCtas);
         }
-        mbar_expect_tx(&bars->m_full[ms], (uint32_t)(BN * sizeof(int2) + (with_stat ? BN * sizeof(float4) : 0)));
-        bulk_load_1d(sMeta[ms].meta, a.col_meta + tile_col(t), BN * sizeof(int2), &bars->m_full[ms]);
-        if (with_stat) bulk_load_1d(sMeta[ms].stat, a.col_stat + tile_col(t), BN * sizeof(float4), &bars->m_full[ms]);
+        if (MODE == kAnaCols) {
+          mbar_expect_tx(&bars->m_full[ms], (uint32_t)(BN * sizeof(float)));
+          bulk_load_1d(sMeta[ms].stat, a.col_shift + tile_col(t), BN * sizeof(float), &bars->m_full[ms]);
+        } else if (MT::kColRing) {
+          constexpr bool with_stat = MODE == kGenCols;
+          mbar_expect_tx(&bars->m_full[ms], (uint32_t)(BN * sizeof(int2) + (with_stat ? BN * sizeof(float4) : 0)));
+          bulk_load_1d(sMeta[ms].meta, a.col_meta + tile_col(t), BN * sizeof(int2), &bars->m_full[ms]);
+          if (with_stat) bulk_load_1d(sMeta[ms].stat, a.col_stat + tile_col(t), BN * sizeof(float4), &bars->m_full[ms]);
+        }
       }
       __syncwarp();
     }
@@ -367,7 +406,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     // ===================== MMA issuer =====================
     const uint32_t idesc1 = make_idesc(BN, 0);
     const uint32_t idesc2 = make_idesc(a.d, 1);
-    const uint32_t c_addr = smem_u32(sC), g_addr = smem_u32(sG);
+    const uint32_t c_addr = smem_u32(sC);
     unsigned long long w0 = 0, w1 = 0, w2 = 0;
     const long long tstart = SLCL_PROF_NOW();
     mbar_wait(&bars->r_full, 0);
@@ -376,13 +415,14 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     // (all operand addresses are < 256 KB, so adding (bytes >> 4) to the low word never carries out).
     const uint64_t descC = make_desc(c_addr, 16, 1024);              // K-major view of a column tile (MMA1)
     const uint64_t descCmn = make_desc(c_addr, BN * 128, 1024);      // MN-major view of the same bytes (MMA2)
-    const uint64_t descG = make_desc(g_addr, 16, 1024);
     const uint32_t stage_units = (uint32_t)(kc * BN * 128) >> 4;
     for (int t = 0; t <= n_tiles; ++t) {
       if (t < n_tiles) {
         const int s = t % kStages, buf = t & 1;
         mbar_wait_t(&bars->c_full[s], (t / kStages) & 1, w0);
-        mbar_wait_t(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1, w1);
+        // S[buf] is free once the epilogue of tile t-2 has it in registers.  In the MMA2 modes that is implied:
+        // MMA2(t-2), issued in the previous iteration, waited for G(t-2), which the epilogue writes after the read.
+        if (!MT::kMma2) mbar_wait_t(&bars->s_empty[buf], ((t >> 1) & 1) ^ 1, w1);
         tc_fence_after();
         if (elect_one()) {
           // S[buf] = R . Cm_tile^T : A = R from tensor memory, B = column tile K-major, 16 bf16 of K per MMA
@@ -397,27 +437,28 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
             db += (BN * 128) >> 4;
           }
           umma_commit(&bars->s_full[buf]);
-          if (!bwd) { if (CS == 1) umma_commit(&bars->c_empty[s]); else umma_commit_mc(&bars->c_empty[s], kAllCtas); }
+          if (!MT::kMma2) { if (CS == 1) umma_commit(&bars->c_empty[s]); else umma_commit_mc(&bars->c_empty[s], kAllCtas); }
         }
         __syncwarp();
       }
-      if (bwd && t > 0) {
-        // dR += G(t-1)[128 x 64] . Cm_tile(t-1)[64 x d] : A = G K-major (smem); B = Cm tile as MN-major operand
+      if (MT::kMma2 && t > 0) {
+        // D += G(t-1)[128 x 64] . Cm_tile(t-1)[64 x d] : A = G from tensor memory (the epilogue warp of column half h
+        // left its 32 bf16 columns packed in S columns [32h, 32h+16)); B = Cm tile as MN-major operand
         const int tp = t - 1, sp = tp % kStages, bp = tp & 1;
         mbar_wait_t(&bars->g_full[bp], (tp >> 1) & 1, w2);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t dg = descG + (uint64_t)(bp * ((BM * 128) >> 4));
+          const uint32_t ga = tmem + kColS + bp * BN;
           const uint64_t dc = descCmn + (uint64_t)(sp * stage_units);
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k) umma_bf16(tmem + kColAcc, dg + 2 * k, dc + k * (2048 >> 4), idesc2, (tp | k) != 0);
-          umma_commit(&bars->g_empty[bp]);
+          for (int k = 0; k < BN / 16; ++k)
+            umma_bf16_ts(tmem + kColAcc, ga + (k >> 1) * 32 + (k & 1) * 8, dc + k * (2048 >> 4), idesc2, (tp | k) != 0);
           if (CS == 1) umma_commit(&bars->c_empty[sp]); else umma_commit_mc(&bars->c_empty[sp], kAllCtas);
         }
         __syncwarp();
       }
     }
-    if (bwd && elect_one()) umma_commit(&bars->acc_full);
+    if (MT::kMma2 && elect_one()) umma_commit(&bars->acc_full);
     __syncwarp();
     if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
       a.prof[4] = (unsigned long long)(SLCL_PROF_NOW() - tstart); a.prof[5] = w0; a.prof[6] = w1; a.prof[7] = w2;
@@ -429,12 +470,16 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     const int r_local = q * 32 + lane;
     const int row = row0 + r_local;
     const bool row_ok = row < a.n_rows;
-    const int2 rm = row_ok ? a.row_meta[row] : make_int2(INT_MIN + 1, INT_MIN + 1);
+    int2 rm = make_int2(INT_MIN + 1, INT_MIN + 1);
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.mode != kBwdCols && row_ok) rs = a.row_stat[row];
-    float zs = 0.f, praw = 0.f, npos = 0.f;
-    unsigned long long w0 = 0, w1 = 0, w2 = 0;
-    const uint32_t lane_addr0 = ((uint32_t)(q * 32) << 16);
+    if (MODE == kGenFwd || MODE == kGenRows) { if (row_ok) rm = a.row_meta[row]; }
+    if (MODE == kGenCols) { if (row_ok) rm = a.row_meta[row]; }
+    if (MODE == kGenRows) { if (row_ok) rs = a.row_stat[row]; }
+    if (MODE == kGenFwd || MODE == kAnaFwd || MODE == kAnaFwdU) { if (row_ok) rs.x = a.row_shift[row] * kLog2e; }
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
+    float praw = 0.f, npos = 0.f;
+    unsigned long long w0 = 0, w1 = 0;
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     if (half == 0) {
       // resident operand: this thread's row (bf16 pairs, 32-bit words) -> tensor memory lane r_local
       const uint4* src = reinterpret_cast<const uint4*>(a.rows_u32 + (size_t)row * (a.d / 2));
@@ -445,7 +490,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           const uint4 t = row_ok ? __ldg(src + (c >> 2) + i) : make_uint4(0u, 0u, 0u, 0u);
           v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
-        tmem_st32(tmem + lane_addr0 + kColR + c, v);
+        tmem_st32(tmem + lane_addr + kColR + c, v);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -453,23 +498,48 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       if (lane == 0) mbar_arrive(&bars->r_full);
     }
     const long long tstart = SLCL_PROF_NOW();
-    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const int ms = t % kMetaSlots;
       const ColMeta& cmeta = sMeta[ms];
-      mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
+      if (MT::kColRing) mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
       mbar_wait_t(&bars->s_full[buf], (t >> 1) & 1, w1);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem + lane_addr + kColS + buf * BN + half * 32, v);
+      const uint32_t s_addr = tmem + lane_addr + kColS + buf * BN + half * 32;
+      tmem_ld32(s_addr, v);
       tmem_ld_wait();
-      // S buffer is free as soon as it sits in registers
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[buf]);
+      if (!MT::kMma2) {
+        // S buffer is free as soon as it sits in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_empty[buf]);
+      }
+      uint32_t packed[16];
 
-      if (!bwd) {
+      if (MODE == kAnaFwd || MODE == kAnaFwdU) {
+        // e = exp2(s * scale - shift): four independent accumulation chains
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[jj]), a.scale_log2, -rs.x));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[jj + 1]), a.scale_log2, -rs.x));
+          zs[jj & 2] += e0;
+          zs[(jj & 2) + 1] += e1;
+          if (MODE == kAnaFwdU) packed[jj >> 1] = pack_bf16x2(e0, e1);
+        }
+      } else if (MODE == kAnaCols) {
+        const float4* cs4 = reinterpret_cast<const float4*>(cmeta.stat) + half * 8;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          const float4 sh = cs4[jj >> 2];
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[jj]), a.scale_log2, -sh.x));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[jj + 1]), a.scale_log2, -sh.y));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(v[jj + 2]), a.scale_log2, -sh.z));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(v[jj + 3]), a.scale_log2, -sh.w));
+          packed[jj >> 1] = pack_bf16x2(e0, e1);
+          packed[(jj >> 1) + 1] = pack_bf16x2(e2, e3);
+        }
+      } else if (MODE == kGenFwd) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int2 cm = cmeta.meta[half * 32 + jj];
@@ -484,80 +554,75 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
               "@pp add.f32 %1, %1, %4;\n\t"
               "@pp add.f32 %2, %2, 0f3F800000;\n\t"
               "}\n"
-              : "+f"(zs), "+f"(praw), "+f"(npos)
+              : "+f"(zs[0]), "+f"(praw), "+f"(npos)
               : "f"(e), "f"(s), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
         }
-        // Padding columns (beyond col_end; only the last tile of a sweep has them) were read as zero rows
-        // by TMA, carry the sentinel id/label and therefore entered zs as exp(0 - shift): take them out
-        // analytically instead of testing every element.
-        {
-          const int jb = tile_col(t) + half * 32;
-          const int n_pad = max(0, min(32, jb + 32 - col_end));
-          if (n_pad > 0) zs -= (float)n_pad * ex2_approx(-rs.x);
-        }
       } else {
-        uint32_t packed[16];
-        // the statistics {shift, alpha, beta} belong to the row (dA sweep) or to the column (dB sweep):
-        // decide once per tile, not per element
-        auto make_g = [&](auto col_stat) {
+        // general backward: G = alpha e - [same label] beta, zero for the self pair.  The statistics
+        // {shift, alpha, beta} belong to the row (dA sweep) or to the column (dB sweep).
 #pragma unroll
-          for (int jj = 0; jj < 32; jj += 2) {
-            float g2[2];
+        for (int jj = 0; jj < 32; jj += 2) {
+          float g2[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int2 cm = cmeta.meta[half * 32 + jj + u];
-              float sh = rs.x, al = rs.y, be = rs.z;
-              if constexpr (decltype(col_stat)::value) {
-                const float4 st = cmeta.stat[half * 32 + jj + u];
-                sh = st.x; al = st.y; be = st.z;
-              }
-              const float s = __uint_as_float(v[jj + u]);
-              const float e = ex2_approx(fmaf(s, a.scale_log2, -sh));
-              float g;      // alpha*e - [same label] beta, zero for the self pair
-              asm("{\n\t"
-                  ".reg .pred pv, pp;\n\t"
-                  "setp.ne.s32 pv, %4, %5;\n\t"
-                  "setp.eq.s32 pp, %6, %7;\n\t"
-                  "mul.f32 %0, %1, %2;\n\t"
-                  "@pp sub.f32 %0, %0, %3;\n\t"
-                  "@!pv mov.f32 %0, 0f00000000;\n\t"
-                  "}\n"
-                  : "=&f"(g)
-                  : "f"(al), "f"(e), "f"(be), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
-              g2[u] = g;
+          for (int u = 0; u < 2; ++u) {
+            const int2 cm = cmeta.meta[half * 32 + jj + u];
+            float sh = rs.x, al = rs.y, be = rs.z;
+            if (MODE == kGenCols) {
+              const float4 st = cmeta.stat[half * 32 + jj + u];
+              sh = st.x; al = st.y; be = st.z;
             }
-            __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
-            packed[jj >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            const float s = __uint_as_float(v[jj + u]);
+            const float e = ex2_approx(fmaf(s, a.scale_log2, -sh));
+            float g;
+            asm("{\n\t"
+                ".reg .pred pv, pp;\n\t"
+                "setp.ne.s32 pv, %4, %5;\n\t"
+                "setp.eq.s32 pp, %6, %7;\n\t"
+                "mul.f32 %0, %1, %2;\n\t"
+                "@pp sub.f32 %0, %0, %3;\n\t"
+                "@!pv mov.f32 %0, 0f00000000;\n\t"
+                "}\n"
+                : "=&f"(g)
+                : "f"(al), "f"(e), "f"(be), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
+            g2[u] = g;
           }
-        };
-        if (a.mode == kBwdCols) make_g(std::true_type{}); else make_g(std::false_type{});
-        // G tile -> smem as a K-major, 128-byte-swizzled A operand: row r_local, 16-byte chunk (half*4 + i) ^ (r_local & 7)
-        mbar_wait_t(&bars->g_empty[buf], ((t >> 1) & 1) ^ 1, w2);
-        uint8_t* grow = sG + (size_t)buf * BM * 128 + (size_t)r_local * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = (half * 4 + i) ^ (r_local & 7);
-          *reinterpret_cast<uint4*>(grow + chunk * 16) =
-              make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          packed[jj >> 1] = pack_bf16x2(g2[0], g2[1]);
         }
-        fence_proxy_async();
+      }
+      if (MT::kRowSums) {
+        // Padding columns (beyond col_end; only the last tile of a sweep has them) were read as zero rows
+        // by TMA (sentinel id/label in the general mode) and therefore entered zs as exp(0 - shift): take
+        // them out analytically instead of testing every element.  Their G entries multiply zero rows.
+        const int jb = tile_col(t) + half * 32;
+        const int n_pad = max(0, min(32, jb + 32 - col_end));
+        if (n_pad > 0) zs[0] -= (float)n_pad * ex2_approx(-rs.x);
+      }
+      if (MT::kMma2) {
+        // G tile -> tensor memory, over the S columns this warp has just read: row = lane, 16 words of bf16 pairs
+        tmem_st16(s_addr, packed);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->g_full[buf]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->m_empty[ms]);
+      if (MT::kColRing) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->m_empty[ms]);
+      }
     }
 
     if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
       unsigned long long* pp = a.prof + (warp == 4 ? 8 : 12);
-      pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = w2;
+      pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = 0;
     }
-    if (!bwd) {
+    if (MT::kRowSums) {
       if (row_ok) {
-        float* out = a.stat_partial + ((size_t)(split * 2 + half) * a.n_rows + row) * 3;
-        out[0] = zs; out[1] = praw; out[2] = npos;
+        float* out = a.stat_partial + ((size_t)(split * 2 + half) * a.n_rows + row) * MT::kStatN;
+        out[0] = (zs[0] + zs[1]) + (zs[2] + zs[3]);
+        if (MODE == kGenFwd) { out[1] = praw; out[2] = npos; }
       }
-    } else {
+    }
+    if (MT::kMma2) {
       // accumulators -> global partial, 32 columns at a time; warps of the two halves split the d columns
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
@@ -587,6 +652,20 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
 // ---------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------
+// dot product of two bf16 rows (length d, multiple of 64) by one warp, fp32 accumulate
+__device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* x, const __nv_bfloat16* y, int d, int lane) {
+  float acc = 0.f;
+  for (int c = lane * 2; c < d; c += 64) {
+    const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + c));
+    const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y + c));
+    acc = fmaf(a2.x, b2.x, acc);
+    acc = fmaf(a2.y, b2.y, acc);
+  }
+  return warp_sum(acc);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---- general path -----------------------------------------------------------
 // stats[i] = sum over slots of partial (deterministic order); also the per-block partial of
 // sum_i w_i * (shift_i + log(Zs_i) - P_i / n_i),  P_i = P_raw_i / T     (utils/loss.py:371-386)
 __global__ void __launch_bounds__(256) p2p_reduce_stats_kernel(const float* partial, int n_slots, int n_rows, const float* shift,
@@ -631,29 +710,312 @@ __global__ void __launch_bounds__(256) p2p_loss_kernel(const double* loss_partia
 
 // per-anchor backward constants {shift*log2e, alpha, beta, 0}: alpha = g w /(T Zs), beta = g w /(T n)
 __global__ void p2p_anchor_stat_kernel(const float* stats, const float* shift, const float* weight, const float* grad_out,
-                                       int n, int n_padded, float inv_t, int with_grad, float4* out) {
+                                       int n, int n_padded, float inv_t, float4* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded) return;
   if (i >= n) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); return; }      // pad entries (bulk-copied as column stats)
-  float4 o = make_float4(shift[i] * kLog2e, 0.f, 0.f, 0.f);
-  if (with_grad) {
-    const float gw = grad_out[0] * weight[i] * inv_t;
-    o.y = gw / stats[3 * i];
-    o.z = gw / stats[3 * i + 2];
-  }
-  out[i] = o;
+  const float gw = grad_out[0] * weight[i] * inv_t;
+  out[i] = make_float4(shift[i] * kLog2e, gw / stats[3 * i], gw / stats[3 * i + 2], 0.f);
 }
 
 __global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64_t n_elems, int d_pad, int d, float* out) {
   // partial: [splits][rows][d_pad] -> out [rows][d]
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t rows_d = n_elems;        // rows * d
-  if (idx >= rows_d) return;
+  if (idx >= n_elems) return;
   const int64_t r = idx / d, c = idx % d;
   float t = 0.f;
-  const int64_t stride = (rows_d / d) * d_pad;
+  const int64_t stride = (n_elems / d) * d_pad;
   for (int s = 0; s < n_splits; ++s) t += partial[(size_t)s * stride + r * d_pad + c];
   out[idx] = t;
+}
+
+// ---- analytic path ----------------------------------------------------------
+// Per-class row sums  out[k] = sum_{rows r with label k} coef_r * x_r  (and sum coef_r as the class "count").
+//   plain mode (stats == null): coef = 1                              -> Bsum / class counts of the contrast rows
+//   anchor mode: coef_i = beta~_i = w_i / (T n_i)  (0 when n_i == 0)  -> ABsum; the kernel also writes the per-anchor
+//     constants alpha~_i = w_i / (T Zs_i), beta~_i and the column shift of the dB sweep
+//     shift_i log2e - log2(alpha~_i)  (kShiftOff when alpha~_i == 0; pad entries up to a multiple of 64 too).
+// Stage 1: a block owns kLabelRowsPerBlock rows; a warp walks every 8th row of them with 16-byte loads (lane = 8
+// bf16 columns), four rows in flight; accumulators acc[K][8] in registers; fixed-order combine over the 8 warps
+// -> partial[block][K][d], cnt[block][K].  Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
+constexpr int kLabelRowsPerBlock = 128;
+__global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16* rows, int n_rows, int d, const int2* meta,
+                                                             int n_class, const float* stats, const float* weight,
+                                                             const float* shift, float inv_t, float* alpha_out,
+                                                             float* beta_out, float* colshift_out, int n_rows_padded,
+                                                             float* partial, float* cnt) {
+  extern __shared__ float sm_lp[];                 // [8 warps][K][d] + [8][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * kLabelRowsPerBlock;
+  const int r1 = min(n_rows, r0 + kLabelRowsPerBlock);
+  const bool col_ok = lane * 8 < d;
+  float acc[kMaxLabelClasses][8];
+  float c_acc[kMaxLabelClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxLabelClasses; ++k) {
+    c_acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+  }
+  for (int rb = r0 + warp; rb < r1; rb += 32) {
+    uint4 x[4];
+    int lab[4];
+    float coef[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + 8 * u;
+      lab[u] = -1; coef[u] = 1.f; x[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < r1) {
+        lab[u] = meta[r].x;
+        if (col_ok) x[u] = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)r * d) + lane);
+        if (stats != nullptr) {
+          const float wt = weight[r] * inv_t;
+          const float n = stats[3 * r + 2];
+          coef[u] = n > 0.f ? wt / n : 0.f;
+          if (lane == 0) {
+            const float al = wt / stats[3 * r];
+            alpha_out[r] = al;
+            beta_out[r] = coef[u];
+            colshift_out[r] = al > 0.f ? shift[r] * kLog2e - log2f(al) : kShiftOff;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t wv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(wv[i] << 16);
+        f[2 * i + 1] = __uint_as_float(wv[i] & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxLabelClasses; ++k) {
+        if (lab[u] == k) {
+          c_acc[k] += coef[u];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(coef[u], f[i], acc[k][i]);
+        }
+      }
+    }
+  }
+  if (colshift_out != nullptr && blockIdx.x == 0)          // pad entries of the column-shift array
+    for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 256) colshift_out[r] = kShiftOff;
+  float* s_sum = sm_lp;
+  float* s_cnt = sm_lp + (size_t)8 * n_class * d;
+#pragma unroll
+  for (int k = 0; k < kMaxLabelClasses; ++k) {
+    if (k < n_class) {
+      if (col_ok) {
+        float4* dst = reinterpret_cast<float4*>(s_sum + ((size_t)warp * n_class + k) * d + lane * 8);
+        dst[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        dst[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+      }
+      if (lane == 0) s_cnt[warp * n_class + k] = c_acc[k];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_class * d; idx += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_sum[(size_t)w * n_class * d + idx];
+    partial[(size_t)blockIdx.x * n_class * d + idx] = t;
+  }
+  if (threadIdx.x < n_class) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_cnt[w * n_class + threadIdx.x];
+    cnt[blockIdx.x * n_class + threadIdx.x] = t;
+  }
+}
+
+// Stage 2: out[k][c] (row stride d + 1; column d = count) = sum over blocks, fixed order.  A block owns 32 outputs;
+// 8 partial-lanes per output, combined through shared memory.
+__global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* partial, const float* cnt, int n_blocks,
+                                                               int n_class, int d, float* out) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int n_out = n_class * (d + 1);
+  const int idx = blockIdx.x * 32 + o;
+  float t = 0.f;
+  if (idx < n_out) {
+    const int k = idx / (d + 1), c = idx % (d + 1);
+    const float* src = c < d ? partial + (size_t)k * d + c : cnt + k;
+    const size_t stride = c < d ? (size_t)n_class * d : (size_t)n_class;
+    float t4[4] = {0.f, 0.f, 0.f, 0.f};
+    int b = pl;
+    for (; b + 24 < n_blocks; b += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t4[u] += src[(size_t)(b + 8 * u) * stride];
+    }
+    for (; b < n_blocks; b += 8) t4[0] += src[(size_t)b * stride];
+    t = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+  }
+  red[pl][o] = t;
+  __syncthreads();
+  if (pl == 0 && idx < n_out) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][o];
+    out[idx] = s;
+  }
+}
+
+// per-class sums [K][d + 1] (global) -> shared s_sum[K][d], s_cnt[K]   (all threads; ends with __syncthreads)
+__device__ __forceinline__ void label_sums_to_smem(const float* sums, int n_class, int d, float* s_sum, float* s_cnt) {
+  for (int idx = threadIdx.x; idx < n_class * (d + 1); idx += blockDim.x) {
+    const int k = idx / (d + 1), c = idx % (d + 1);
+    const float v = sums[idx];
+    if (c < d) s_sum[k * d + c] = v; else s_cnt[k] = v;
+  }
+  __syncthreads();
+}
+
+// Forward finish, one warp per anchor i (fixed summation orders throughout):
+//   Zs_i   = sum_slots zs - e_self                      e_self = exp(S_i,self / T - shift_i) if anchor i is a contrast row
+//   P_raw  = a_i . Bsum[lab_i] - [labels agree] S_i,self        n_i = count[lab_i] - [labels agree]
+//   U_i    = sum_splits U_partial - bf16(e_self) b_self         (the sweep multiplied bf16-rounded exponentials)
+//   block partial of  sum_i w_i (shift_i + log Zs_i - P_raw_i / (T n_i))                  (utils/loss.py:371-386)
+__global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_partial, int n_slots, int n_rows, const float* shift,
+                                                             const float* weight, float inv_t, const __nv_bfloat16* a,
+                                                             const __nv_bfloat16* b, int d, const int2* a_meta,
+                                                             const int2* b_meta, const int32_t* a_selfcol,
+                                                             const float* label_sums, int n_class, const float* u_partial,
+                                                             int n_splits, float* u_out, float* stats, double* loss_partial) {
+  extern __shared__ float sm_ff[];                 // [K][d] + [K]
+  __shared__ double red[8];
+  float* s_sum = sm_ff;
+  float* s_cnt = sm_ff + n_class * d;
+  label_sums_to_smem(label_sums, n_class, d, s_sum, s_cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int i = blockIdx.x * 8 + warp; i < n_rows; i += gridDim.x * 8) {
+    float zs = 0.f;
+    for (int s = 0; s < n_slots; ++s) zs += zs_partial[(size_t)s * n_rows + i];
+    const __nv_bfloat16* ai = a + (size_t)i * d;
+    const int lab = a_meta[i].x;
+    const bool lab_ok = lab >= 0 && lab < n_class;
+    float praw = 0.f, n = 0.f;
+    if (lab_ok) {
+      float t = 0.f;
+      for (int c = lane * 2; c < d; c += 64) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
+        t = fmaf(x.x, s_sum[lab * d + c], t);
+        t = fmaf(x.y, s_sum[lab * d + c + 1], t);
+      }
+      praw = warp_sum(t);
+      n = s_cnt[lab];
+    }
+    const int sc = a_selfcol ? a_selfcol[i] : -1;
+    float e_self_r = 0.f;
+    if (sc >= 0) {
+      const float s_self = warp_dot_bf16(ai, b + (size_t)sc * d, d, lane);
+      const float e_self = ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
+      zs -= e_self;
+      e_self_r = bf16_round(e_self);
+      if (lab == b_meta[sc].x) { praw -= s_self; n -= 1.f; }
+    }
+    if (u_out != nullptr) {
+      const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
+      for (int c = lane * 2; c < d; c += 64) {
+        float2 t = make_float2(0.f, 0.f);
+        for (int s = 0; s < n_splits; ++s) {
+          const float2 p = *reinterpret_cast<const float2*>(u_partial + ((size_t)s * n_rows + i) * d + c);
+          t.x += p.x; t.y += p.y;
+        }
+        if (sc >= 0) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
+          t.x = fmaf(-e_self_r, x.x, t.x); t.y = fmaf(-e_self_r, x.y, t.y);
+        }
+        *reinterpret_cast<float2*>(u_out + (size_t)i * d + c) = t;
+      }
+    }
+    if (lane == 0) {
+      stats[3 * i] = zs; stats[3 * i + 1] = praw; stats[3 * i + 2] = n;
+      const float li = shift[i] + logf(zs) - (praw * inv_t) / n;      // n == 0 -> NaN, as 0/0 in the reference (:376-380)
+      acc += (double)(weight[i] * li);
+    }
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    loss_partial[blockIdx.x] = t;
+  }
+}
+
+// Backward finish, one warp per output row (anchors first, then contrast rows), g = dL/dloss:
+//   d_a[i] = g ( alpha~_i U_i - beta~_i (Bsum[lab_i] - [labels agree] b_self) )
+//   d_b[j] = g ( sum_splits Acc_j - bf16(alpha~_i e_i,self) a_i - ABsum[lab_j] + [labels agree] beta~_i a_i ),  i = b_selfrow[j]
+__global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n_contrast, int d, int dim,
+                                                             const __nv_bfloat16* a, const __nv_bfloat16* b, const int2* a_meta,
+                                                             const int2* b_meta, const int32_t* a_selfcol,
+                                                             const int32_t* b_selfrow, const float* label_sums,
+                                                             const float* ab_sums, int n_class, const float* alpha,
+                                                             const float* beta,
+                                                             const float* colshift, float scale_log2, const float* u,
+                                                             const float* acc_partial, int n_splits, const float* grad_out,
+                                                             float* d_a, float* d_b) {
+  extern __shared__ float sm_fb[];                 // Bsum [K][d] + ABsum [K][d] + [K]
+  float* s_b = sm_fb;
+  float* s_ab = sm_fb + n_class * d;
+  float* s_cnt = s_ab + n_class * d;
+  for (int idx = threadIdx.x; idx < n_class * d; idx += 256) s_b[idx] = label_sums[(idx / d) * (d + 1) + idx % d];
+  label_sums_to_smem(ab_sums, n_class, d, s_ab, s_cnt);
+  const float g = grad_out[0];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_begin = d_a ? 0 : n_anchor, r_end = d_b ? n_anchor + n_contrast : n_anchor;
+  for (int r = r_begin + blockIdx.x * 8 + warp; r < r_end; r += gridDim.x * 8) {
+    if (r < n_anchor) {
+      const int i = r;
+      const int lab = a_meta[i].x;
+      const bool lab_ok = lab >= 0 && lab < n_class;
+      const int sc = a_selfcol ? a_selfcol[i] : -1;
+      const bool match = sc >= 0 && lab == b_meta[sc].x;
+      const float al = alpha[i], be = lab_ok ? beta[i] : 0.f;
+      const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
+      for (int c = lane * 2; c < dim; c += 64) {
+        const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)i * d + c);
+        float2 p = make_float2(0.f, 0.f);
+        if (lab_ok) { p.x = s_b[lab * d + c]; p.y = s_b[lab * d + c + 1]; }
+        if (match) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
+          p.x -= x.x; p.y -= x.y;
+        }
+        const float ox = g * (al * uu.x - be * p.x), oy = g * (al * uu.y - be * p.y);
+        d_a[(size_t)i * dim + c] = ox;
+        if (c + 1 < dim) d_a[(size_t)i * dim + c + 1] = oy;
+      }
+    } else {
+      const int j = r - n_anchor;
+      const int lab = b_meta[j].x;
+      const bool lab_ok = lab >= 0 && lab < n_class;
+      const int i = b_selfrow ? b_selfrow[j] : -1;
+      float g_self = 0.f, be_self = 0.f;
+      const __nv_bfloat16* as = a + (size_t)max(i, 0) * d;
+      if (i >= 0) {
+        const float s_self = warp_dot_bf16(as, b + (size_t)j * d, d, lane);
+        g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
+        if (a_meta[i].x == lab) be_self = beta[i];
+      }
+      for (int c = lane * 2; c < dim; c += 64) {
+        float2 t = make_float2(0.f, 0.f);
+        for (int s = 0; s < n_splits; ++s) {
+          const float2 p = *reinterpret_cast<const float2*>(acc_partial + ((size_t)s * n_contrast + j) * d + c);
+          t.x += p.x; t.y += p.y;
+        }
+        if (lab_ok) { t.x -= s_ab[lab * d + c]; t.y -= s_ab[lab * d + c + 1]; }
+        if (i >= 0) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(as + c));
+          t.x += (be_self - g_self) * x.x; t.y += (be_self - g_self) * x.y;
+        }
+        d_b[(size_t)j * dim + c] = g * t.x;
+        if (c + 1 < dim) d_b[(size_t)j * dim + c + 1] = g * t.y;
+      }
+    }
+  }
 }
 
 // ------------------------------ host side ----------------------------------
@@ -702,70 +1064,76 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
   s.cols_per_split = tiles_per_split * BN;
-  // Cluster size of the multicast variant.  Measured on B200 (cfg3 and 16384^2): clusters of 2 and 4 bring no
-  // gain -- the sweep is MMA-issue/epilogue-bound, not L2-bound -- so the default is 1; SLCL_P2P_CLUSTER selects
-  // 2 or 4 for experiments on other shapes.
+  // Cluster size of the multicast variant (1, 2 or 4 CTAs along the row tiles share every column tile).
   s.cluster = 1;
   { const char* e = getenv("SLCL_P2P_CLUSTER"); if (e) s.cluster = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1); }
   return s;
 }
 
-int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_cols, int d, int mode, float inv_t,
-                 const int2* row_meta, const int2* col_meta, const float4* row_stat, const float4* col_stat,
-                 float* stat_partial, float* grad_partial, const Sweep& sw, cudaStream_t stream) {
-  CUtensorMap mr, mc;
-  int st = make_map(&mr, rows, n_rows, d, BM);
-  if (st != SLCL_OK) return st;
-  st = make_map(&mc, cols, n_cols, d, BN / sw.cluster);
-  if (st != SLCL_OK) return st;
-  P2PArgs a{};
-  a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
-  a.col_begin = 0; a.cols_per_split = sw.cols_per_split;
-  a.mode = mode;
-#ifdef SLCL_P2P_PROFILE
-  { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
-#endif
-  a.scale_log2 = inv_t * kLog2e;
-  a.rows_u32 = reinterpret_cast<const uint32_t*>(rows);
-  a.row_meta = row_meta; a.col_meta = col_meta; a.row_stat = row_stat; a.col_stat = col_stat;
-  a.stat_partial = stat_partial; a.grad_partial = grad_partial;
-  const size_t smem = smem_bytes_for(d);
-  static bool attr_set = false;
+template <int CS, int MODE>
+int launch_one(const CUtensorMap& mc, const P2PArgs& a, const Sweep& sw, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;          // per instantiation
   if (!attr_set) {
-    const int mx = (int)smem_bytes_for(kMaxD);
-    cudaError_t e = cudaFuncSetAttribute(p2p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaError_t e = cudaFuncSetAttribute(p2p_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(kMaxD));
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
-  const int cs = sw.cluster;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ceil_div(sw.row_tiles, cs) * cs), (unsigned)sw.splits, 1);
+  cfg.gridDim = dim3((unsigned)(ceil_div(sw.row_tiles, CS) * CS), (unsigned)sw.splits, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.x = (unsigned)CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le;
-  if (cs == 4) le = cudaLaunchKernelEx(&cfg, p2p_kernel<4>, mr, mc, a);
-  else if (cs == 2) le = cudaLaunchKernelEx(&cfg, p2p_kernel<2>, mr, mc, a);
-  else le = cudaLaunchKernelEx(&cfg, p2p_kernel<1>, mr, mc, a);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, p2p_kernel<CS, MODE>, mc, a);
   if (le != cudaSuccess) { set_cuda_error(le, "cudaLaunchKernelEx(p2p_kernel)"); return SLCL_ERR_CUDA; }
   return check_launch("p2p_kernel");
 }
 
-// workspace layout helpers
+template <int MODE>
+int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_cols, int d, float inv_t, P2PArgs a,
+                 const Sweep& sw, cudaStream_t stream) {
+  CUtensorMap mc;
+  int st = make_map(&mc, cols, n_cols, d, BN / sw.cluster);
+  if (st != SLCL_OK) return st;
+  a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
+  a.cols_per_split = sw.cols_per_split;
+  a.scale_log2 = inv_t * kLog2e;
+  a.rows_u32 = reinterpret_cast<const uint32_t*>(rows);
+#ifdef SLCL_P2P_PROFILE
+  { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
+  const size_t smem = smem_bytes_for(d);
+  if (sw.cluster == 4) return launch_one<4, MODE>(mc, a, sw, smem, stream);
+  if (sw.cluster == 2) return launch_one<2, MODE>(mc, a, sw, smem, stream);
+  return launch_one<1, MODE>(mc, a, sw, smem, stream);
+}
+
+// workspace layout (one carve-up serves the general and the analytic path)
+constexpr int kMaxFinishBlocks = 1024;
 struct P2PWs {
   float* stat_partial;     // [2*splits_a][Na][3]
-  float4* anchor_stat;     // [Na]
-  float* grad_partial_a;   // [splits_a][Na][d]
+  float4* anchor_stat;     // general: [pad64(Na)]
+  float* grad_partial_a;   // [splits_a][Na][d]   (general dA sweep / analytic U)
   float* grad_partial_b;   // [splits_b][M][d]
+  float* lab_partial_b;    // analytic: [blocks_b][K][d], then cnt [blocks_b][K]
+  float* lab_cnt_b;
+  float* lab_partial_a;
+  float* lab_cnt_a;
+  float* alpha;            // [Na]
+  float* beta;             // [Na]
+  float* colshift;         // [pad64(Na)]
+  float* label_sums;       // [K][d+1]   (when the caller does not keep the forward's)
+  float* ab_sums;          // [K][d+1]
+  float* u;                // [Na][d]    (same)
+  float* stats_scratch;    // [Na][3]    (same)
+  double* loss_partial;    // [kMaxFinishBlocks]
+  int blocks_a, blocks_b;
   size_t total;
 };
 
@@ -773,23 +1141,93 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   Sweep sa = plan_sweep(na, m), sb = plan_sweep(m, na);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  size_t o1 = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
-  size_t o2 = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
-  size_t o3 = take((size_t)sa.splits * na * d * sizeof(float));
-  size_t o4 = take((size_t)sb.splits * m * d * sizeof(float));
   P2PWs w;
+  w.blocks_a = (int)ceil_div<int64_t>(na, kLabelRowsPerBlock);
+  w.blocks_b = (int)ceil_div<int64_t>(m, kLabelRowsPerBlock);
+  const size_t K = kMaxLabelClasses;
+  size_t o[16];
+  o[0] = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
+  o[1] = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
+  o[2] = take((size_t)sa.splits * na * d * sizeof(float));
+  o[3] = take((size_t)sb.splits * m * d * sizeof(float));
+  o[4] = take((size_t)w.blocks_b * K * d * sizeof(float));
+  o[5] = take((size_t)w.blocks_b * K * sizeof(float));
+  o[6] = take((size_t)w.blocks_a * K * d * sizeof(float));
+  o[7] = take((size_t)w.blocks_a * K * sizeof(float));
+  o[8] = take((size_t)na * sizeof(float));
+  o[9] = take((size_t)na * sizeof(float));
+  o[10] = take((size_t)align_up((size_t)na, BN) * sizeof(float));
+  o[11] = take(K * (d + 1) * sizeof(float));
+  o[12] = take((size_t)na * d * sizeof(float));
+  o[13] = take((size_t)na * 3 * sizeof(float));
+  o[14] = take((size_t)kMaxFinishBlocks * sizeof(double));
+  o[15] = take(K * (d + 1) * sizeof(float));
   char* b = reinterpret_cast<char*>(ws);
-  w.stat_partial = reinterpret_cast<float*>(b + o1);
-  w.anchor_stat = reinterpret_cast<float4*>(b + o2);
-  w.grad_partial_a = reinterpret_cast<float*>(b + o3);
-  w.grad_partial_b = reinterpret_cast<float*>(b + o4);
+  w.stat_partial = reinterpret_cast<float*>(b + o[0]);
+  w.anchor_stat = reinterpret_cast<float4*>(b + o[1]);
+  w.grad_partial_a = reinterpret_cast<float*>(b + o[2]);
+  w.grad_partial_b = reinterpret_cast<float*>(b + o[3]);
+  w.lab_partial_b = reinterpret_cast<float*>(b + o[4]);
+  w.lab_cnt_b = reinterpret_cast<float*>(b + o[5]);
+  w.lab_partial_a = reinterpret_cast<float*>(b + o[6]);
+  w.lab_cnt_a = reinterpret_cast<float*>(b + o[7]);
+  w.alpha = reinterpret_cast<float*>(b + o[8]);
+  w.beta = reinterpret_cast<float*>(b + o[9]);
+  w.colshift = reinterpret_cast<float*>(b + o[10]);
+  w.label_sums = reinterpret_cast<float*>(b + o[11]);
+  w.u = reinterpret_cast<float*>(b + o[12]);
+  w.stats_scratch = reinterpret_cast<float*>(b + o[13]);
+  w.loss_partial = reinterpret_cast<double*>(b + o[14]);
+  w.ab_sums = reinterpret_cast<float*>(b + o[15]);
   w.total = off;
   return w;
 }
 
-bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t d_pad) {
-  return a && b && na > 0 && m > 0 && d_pad >= KCH && d_pad <= kMaxD && d_pad % KCH == 0 && aligned16(a) && aligned16(b) &&
-         na < (1ll << 31) && m < (1ll << 31);
+bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t dp) {
+  return a && b && na > 0 && m > 0 && dp >= KCH && dp <= kMaxD && dp % KCH == 0 && na < (int64_t)INT_MAX - BM &&
+         m < (int64_t)INT_MAX - BM && aligned16(a) && aligned16(b);
+}
+
+int finish_blocks(int64_t rows) {
+  const int64_t want = ceil_div<int64_t>(rows, 8), cap = kMaxFinishBlocks < 2 * sm_count() ? kMaxFinishBlocks : 2 * sm_count();
+  return (int)(want < cap ? want : cap);
+}
+
+int label_part_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared memory (> the 48 KB default)
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(8 * kMaxLabelClasses * (kMaxD + 1) * sizeof(float)));
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p_label_part_kernel)"); return SLCL_ERR_CUDA; }
+    done = true;
+  }
+  return SLCL_OK;
+}
+
+// analytic forward pieces shared by slcl_p2p_fwd and the backward's fallback
+int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, const int2* am, const int2* bm,
+                const int32_t* a_selfcol, int n_class, const float* shift, const float* weight, float inv_t, bool want_u,
+                float* stats, float* u_out, float* label_sums_out, const P2PWs& w, cudaStream_t stream) {
+  const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a);
+  const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
+  float* lsum = label_sums_out ? label_sums_out : w.label_sums;
+  if (int st0 = label_part_smem_ok()) return st0;
+  p2p_label_part_kernel<<<w.blocks_b, 256, (size_t)8 * n_class * (d + 1) * sizeof(float), stream>>>(
+      bb, (int)m, d, bm, n_class, nullptr, nullptr, nullptr, inv_t, nullptr, nullptr, nullptr, 0, w.lab_partial_b, w.lab_cnt_b);
+  p2p_label_reduce_kernel<<<ceil_div(n_class * (d + 1), 32), 256, 0, stream>>>(w.lab_partial_b, w.lab_cnt_b, w.blocks_b, n_class, d, lsum);
+  Sweep sw = plan_sweep(na, m);
+  P2PArgs args{};
+  args.row_shift = shift;
+  args.stat_partial = w.stat_partial;
+  args.grad_partial = w.grad_partial_a;
+  int st = want_u ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream)
+                  : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
+  if (st != SLCL_OK) return st;
+  const int nb = finish_blocks(na);
+  p2p_finish_fwd_kernel<<<nb, 256, (size_t)n_class * (d + 1) * sizeof(float), stream>>>(
+      w.stat_partial, 2 * sw.splits, (int)na, shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, lsum, n_class,
+      w.grad_partial_a, sw.splits, want_u ? u_out : nullptr, stats, w.loss_partial);
+  return nb;
 }
 
 }  // namespace
@@ -798,68 +1236,118 @@ bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t d_
 using namespace slcl;
 
 extern "C" size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast, int64_t dim_padded) {
-  if (n_anchor <= 0 || n_contrast <= 0 || dim_padded < KCH || dim_padded > kMaxD || dim_padded % KCH) return 0;
+  if (n_anchor <= 0 || n_contrast <= 0 || dim_padded <= 0 || dim_padded > kMaxD) return 0;
   return carve(nullptr, n_anchor, n_contrast, (int)dim_padded).total;
 }
 
 extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                            const int32_t* a_meta, const int32_t* b_meta, const float* shift, const float* weight,
-                            float temperature, float* stats, float* loss, void* workspace, size_t workspace_bytes,
-                            slcl_stream_t stream_) {
+                            const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
+                            const float* shift, const float* weight, float temperature, float* stats, float* loss, float* u,
+                            float* label_sums, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
-      !loss || !workspace || !(temperature > 0.f))
+      !loss || !workspace || !(temperature > 0.f) || n_class < 0 || n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && (a_selfcol || u || label_sums)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class > 0 && (u != nullptr) != (label_sums != nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
+  if (n_anchor >= (int64_t)kMaxFinishBlocks * 256) return SLCL_ERR_UNSUPPORTED;
   cudaStream_t stream = (cudaStream_t)stream_;
   P2PWs w = carve(workspace, n_anchor, n_contrast, d);
   const float inv_t = 1.0f / temperature;
   const int na = (int)n_anchor;
-  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(nullptr, shift, weight, nullptr, na, (int)align_up((size_t)na, BN), inv_t, 0,
-                                                                     w.anchor_stat);
-  Sweep sw = plan_sweep(n_anchor, n_contrast);
-  int st = launch_sweep(a_bf16, n_anchor, b_bf16, n_contrast, d, kFwd, inv_t, reinterpret_cast<const int2*>(a_meta),
-                        reinterpret_cast<const int2*>(b_meta), w.anchor_stat, nullptr, w.stat_partial, nullptr, sw, stream);
-  if (st != SLCL_OK) return st;
-  // the forward no longer needs grad_partial_a: its head doubles as the per-block loss partials
-  double* loss_partial = reinterpret_cast<double*>(w.grad_partial_a);
-  const int nb = ceil_div(na, 256);
-  p2p_reduce_stats_kernel<<<nb, 256, 0, stream>>>(w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats, loss_partial);
-  p2p_loss_kernel<<<1, 256, 0, stream>>>(loss_partial, nb, loss);
+  const int2* am = reinterpret_cast<const int2*>(a_meta);
+  const int2* bm = reinterpret_cast<const int2*>(b_meta);
+  int nb;
+  if (n_class > 0) {
+    nb = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, u != nullptr,
+                     stats, u, label_sums, w, stream);
+    if (nb < 0) return nb;
+  } else {
+    Sweep sw = plan_sweep(n_anchor, n_contrast);
+    P2PArgs args{};
+    args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
+    int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
+    if (st != SLCL_OK) return st;
+    nb = ceil_div(na, 256);
+    p2p_reduce_stats_kernel<<<nb, 256, 0, stream>>>(w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats, w.loss_partial);
+  }
+  p2p_loss_kernel<<<1, 256, 0, stream>>>(w.loss_partial, nb, loss);
   return check_launch("slcl_p2p_fwd");
 }
 
 extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                            int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const float* shift,
-                            const float* weight, float temperature, const float* stats, const float* grad_out, float* d_a,
+                            int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
+                            const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
+                            const float* stats, const float* u, const float* label_sums, const float* grad_out, float* d_a,
                             float* d_b, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
-      !grad_out || !workspace || !(temperature > 0.f) || dim <= 0 || dim > dim_padded || (!d_a && !d_b))
+      !grad_out || !workspace || !(temperature > 0.f) || dim <= 0 || dim > dim_padded || (!d_a && !d_b) || n_class < 0 ||
+      n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
+  if ((a_selfcol == nullptr) != (b_selfrow == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && (a_selfcol || u || label_sums)) return SLCL_ERR_INVALID_ARGUMENT;
+  if ((u != nullptr) != (label_sums != nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
+  if (n_anchor >= (int64_t)kMaxFinishBlocks * 256) return SLCL_ERR_UNSUPPORTED;
   cudaStream_t stream = (cudaStream_t)stream_;
   P2PWs w = carve(workspace, n_anchor, n_contrast, d);
   const float inv_t = 1.0f / temperature;
   const int na = (int)n_anchor;
-  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, (int)align_up((size_t)na, BN), inv_t, 1,
-                                                                     w.anchor_stat);
   const int2* am = reinterpret_cast<const int2*>(a_meta);
   const int2* bm = reinterpret_cast<const int2*>(b_meta);
+  if (n_class > 0) {
+    const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a_bf16);
+    const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b_bf16);
+    if (u == nullptr) {
+      // the caller did not keep the forward's U / label sums: one more forward sweep regenerates them
+      int nb = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, true,
+                           w.stats_scratch, w.u, w.label_sums, w, stream);
+      if (nb < 0) return nb;
+      u = w.u; label_sums = w.label_sums;
+    }
+    // per-anchor constants, dB column shifts and stage 1 of ABsum in one launch
+    const int na_pad = (int)align_up((size_t)na, BN);
+    if (int st0 = label_part_smem_ok()) return st0;
+    p2p_label_part_kernel<<<w.blocks_a, 256, (size_t)8 * n_class * (d + 1) * sizeof(float), stream>>>(
+        ab, na, d, am, n_class, stats, weight, shift, inv_t, w.alpha, w.beta, w.colshift, na_pad, w.lab_partial_a, w.lab_cnt_a);
+    p2p_label_reduce_kernel<<<ceil_div(n_class * (d + 1), 32), 256, 0, stream>>>(w.lab_partial_a, w.lab_cnt_a, w.blocks_a, n_class, d,
+                                                                                 w.ab_sums);
+    int n_splits_b = 0;
+    if (d_b) {
+      Sweep sw = plan_sweep(n_contrast, n_anchor);
+      P2PArgs args{};
+      args.col_shift = w.colshift;
+      args.grad_partial = w.grad_partial_b;
+      int st = launch_sweep<kAnaCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
+      if (st != SLCL_OK) return st;
+      n_splits_b = sw.splits;
+    }
+    const int64_t rows = (d_a ? n_anchor : 0) + (d_b ? n_contrast : 0);
+    p2p_finish_bwd_kernel<<<finish_blocks(rows), 256, (size_t)(2 * n_class * d + n_class) * sizeof(float), stream>>>(
+        na, (int)n_contrast, d, (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, label_sums, w.ab_sums, n_class, w.alpha, w.beta,
+        w.colshift, inv_t * kLog2e, u, w.grad_partial_b, n_splits_b, grad_out, d_a, d_b);
+    return check_launch("slcl_p2p_bwd");
+  }
+  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, (int)align_up((size_t)na, BN),
+                                                                     inv_t, w.anchor_stat);
   if (d_a) {
     Sweep sw = plan_sweep(n_anchor, n_contrast);
-    int st = launch_sweep(a_bf16, n_anchor, b_bf16, n_contrast, d, kBwdRows, inv_t, am, bm, w.anchor_stat, nullptr, nullptr,
-                          w.grad_partial_a, sw, stream);
+    P2PArgs args{};
+    args.row_meta = am; args.col_meta = bm; args.row_stat = w.anchor_stat; args.grad_partial = w.grad_partial_a;
+    int st = launch_sweep<kGenRows>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
     if (st != SLCL_OK) return st;
     const int64_t n = n_anchor * dim;
     p2p_reduce_grad_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(w.grad_partial_a, sw.splits, n, d, (int)dim, d_a);
   }
   if (d_b) {
     Sweep sw = plan_sweep(n_contrast, n_anchor);
-    int st = launch_sweep(b_bf16, n_contrast, a_bf16, n_anchor, d, kBwdCols, inv_t, bm, am, nullptr, w.anchor_stat, nullptr,
-                          w.grad_partial_b, sw, stream);
+    P2PArgs args{};
+    args.row_meta = bm; args.col_meta = am; args.col_stat = w.anchor_stat; args.grad_partial = w.grad_partial_b;
+    int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
     if (st != SLCL_OK) return st;
     const int64_t n = n_contrast * dim;
     p2p_reduce_grad_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(w.grad_partial_b, sw.splits, n, d, (int)dim, d_b);

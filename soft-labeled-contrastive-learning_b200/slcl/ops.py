@@ -486,54 +486,99 @@ def _p2p_check(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tens
         raise ValueError("shift / weight must be float32 [A]")
 
 
+def self_maps(id_a: Tensor, id_b: Tensor) -> Tuple[Tensor, Tensor]:
+    """(a_selfcol [A], b_selfrow [M]) int32 for the analytic p2p mode: the contrast row carrying anchor i's id
+    (-1: none) and its inverse.  Ids must be unique within each side."""
+    sorted_b, perm = torch.sort(id_b.reshape(-1).long())
+    ia = id_a.reshape(-1).long()
+    pos = torch.searchsorted(sorted_b, ia).clamp_(max=sorted_b.numel() - 1)
+    found = sorted_b[pos] == ia
+    selfcol = torch.where(found, perm[pos], torch.full_like(pos, -1))
+    selfrow = torch.full((id_b.numel(),), -1, dtype=torch.long, device=id_b.device)
+    anchors = torch.arange(ia.numel(), device=ia.device)
+    selfrow[selfcol[found]] = anchors[found]
+    return selfcol.to(torch.int32), selfrow.to(torch.int32)
+
+
+def _selfcol_check(t: Optional[Tensor], n: int, what: str):
+    if t is not None and (t.dtype != torch.int32 or t.shape != (n,) or not t.is_contiguous()):
+        raise ValueError(f"{what} must be contiguous int32 [{n}]")
+
+
 @torch.library.custom_op("slcl::p2p_fwd", mutates_args=(), device_types="cuda")
 def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
-            temperature: float) -> Tuple[Tensor, Tensor]:
-    """-> (loss[1], stats[A,3])"""
+            temperature: float, n_class: int = 0, a_selfcol: Optional[Tensor] = None,
+            want_u: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (loss[1], stats[A,3], u[A,dp], label_sums[n_class,dp+1]); u / label_sums are empty unless
+    n_class > 0 (analytic mode, include/slcl.h) and want_u."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight)
     lib = _lib.load()
     _p2p_check(a, b, a_meta, b_meta, shift, weight)
     na, dp = a.shape
     m = b.shape[0]
+    _selfcol_check(a_selfcol, na, "a_selfcol")
+    if n_class == 0 and (a_selfcol is not None or want_u):
+        raise ValueError("a_selfcol / want_u need n_class > 0 (analytic mode)")
     stats = torch.empty((na, 3), dtype=_F32, device=dev)
     loss = torch.empty(1, dtype=_F32, device=dev)
+    keep = n_class > 0 and want_u
+    u = torch.empty((na, dp) if keep else (0, dp), dtype=_F32, device=dev)
+    label_sums = torch.empty((n_class, dp + 1) if keep else (0, dp + 1), dtype=_F32, device=dev)
     ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
     with _guard(dev):
-        st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(shift.contiguous()),
-                              ptr(weight.contiguous()), float(temperature), ptr(stats), ptr(loss), ptr(ws), ws.numel(),
+        st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class),
+                              ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature), ptr(stats), ptr(loss),
+                              ptr(u) if keep else None, ptr(label_sums) if keep else None, ptr(ws), ws.numel(),
                               stream_ptr(dev))
     check(st, "slcl_p2p_fwd")
-    return loss, stats
+    return loss, stats, u, label_sums
 
 
 @p2p_fwd.register_fake
-def _(a, b, a_meta, b_meta, shift, weight, temperature):
-    return shift.new_empty(1), shift.new_empty((a.shape[0], 3))
+def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, want_u=False):
+    keep = n_class > 0 and want_u
+    return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), shift.new_empty((a.shape[0] if keep else 0, a.shape[1])),
+            shift.new_empty((n_class if keep else 0, a.shape[1] + 1)))
 
 
 @torch.library.custom_op("slcl::p2p_bwd", mutates_args=(), device_types="cuda")
 def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
-            temperature: float, stats: Tensor, grad_out: Tensor, need_a: bool, need_b: bool) -> Tuple[Tensor, Tensor]:
+            temperature: float, stats: Tensor, grad_out: Tensor, need_a: bool, need_b: bool, n_class: int = 0,
+            a_selfcol: Optional[Tensor] = None, b_selfrow: Optional[Tensor] = None, u: Optional[Tensor] = None,
+            label_sums: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """-> (d_a [A, dim], d_b [M, dim]) fp32 (empty when not needed)."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight, stats, grad_out)
     lib = _lib.load()
     _p2p_check(a, b, a_meta, b_meta, shift, weight)
     na, dp = a.shape
     m = b.shape[0]
+    _selfcol_check(a_selfcol, na, "a_selfcol")
+    _selfcol_check(b_selfrow, m, "b_selfrow")
+    if u is not None and u.numel() == 0:
+        u = None
+    if label_sums is not None and label_sums.numel() == 0:
+        label_sums = None
+    if u is not None and (u.shape != (na, dp) or u.dtype != _F32 or not u.is_contiguous()):
+        raise ValueError("u must be contiguous float32 [A, dim_padded]")
+    if label_sums is not None and (label_sums.shape != (n_class, dp + 1) or label_sums.dtype != _F32
+                                   or not label_sums.is_contiguous()):
+        raise ValueError("label_sums must be contiguous float32 [n_class, dim_padded + 1]")
     d_a = torch.empty((na, dim) if need_a else (0, dim), dtype=_F32, device=dev)
     d_b = torch.empty((m, dim) if need_b else (0, dim), dtype=_F32, device=dev)
     ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
     g = grad_out.to(_F32).reshape(1).contiguous()
     with _guard(dev):
-        st = lib.slcl_p2p_bwd(ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(shift.contiguous()),
-                              ptr(weight.contiguous()), float(temperature), ptr(stats.contiguous()), ptr(g),
+        st = lib.slcl_p2p_bwd(ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
+                              int(n_class), ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature),
+                              ptr(stats.contiguous()), ptr(u), ptr(label_sums), ptr(g),
                               ptr(d_a) if need_a else None, ptr(d_b) if need_b else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_p2p_bwd")
     return d_a, d_b
 
 
 @p2p_bwd.register_fake
-def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b):
+def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b, n_class=0, a_selfcol=None,
+      b_selfrow=None, u=None, label_sums=None):
     return (shift.new_empty((a.shape[0] if need_a else 0, dim)), shift.new_empty((b.shape[0] if need_b else 0, dim)))
 
 

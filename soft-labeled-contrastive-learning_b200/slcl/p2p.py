@@ -20,10 +20,14 @@ _ops = torch.ops.slcl
 
 
 class _P2PLoss(torch.autograd.Function):
-    """loss(feat) for anchor rows idx_a and contrast rows idx_b of an NCHW map (appendix A.6)."""
+    """loss(feat) for anchor rows idx_a and contrast rows idx_b of an NCHW map (appendix A.6).
+
+    ``n_class`` > 0 selects the analytic sweeps (include/slcl.h): labels are class indices in [0, n_class), ids
+    unique; the forward then also produces U and the per-class row sums, and the backward is one sweep."""
 
     @staticmethod
-    def forward(ctx, feat, idx_a, idx_b, meta_a, meta_b, weight, temperature, normalize, same_rows):
+    def forward(ctx, feat, idx_a, idx_b, meta_a, meta_b, weight, temperature, normalize, same_rows, n_class, selfcol,
+                selfrow):
         fm = feat.detach().contiguous()
         c = fm.shape[1]
         b_bf16, _, inv_b = _ops.gather_unit_rows(fm, idx_b, normalize, True, False)
@@ -35,32 +39,45 @@ class _P2PLoss(torch.autograd.Function):
             shift = torch.full_like(inv_a, 1.0 / temperature)
         else:   # upper bound of S_ij: |a_i| max_j |b_j| / T
             shift = (1.0 / inv_a) * ((1.0 / inv_b).amax() / temperature)
-        loss, stats = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature)
-        ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats)
-        ctx.cfg = (temperature, normalize, same_rows, c)
+        want_u = n_class > 0 and ctx.needs_input_grad[0]
+        loss, stats, u, lsum = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol,
+                                            want_u)
+        ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, u, lsum,
+                              selfcol, selfrow)
+        ctx.cfg = (temperature, normalize, same_rows, c, n_class)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
-        fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats = ctx.saved_tensors
-        temperature, normalize, same_rows, c = ctx.cfg
+        (fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, u, lsum, selfcol,
+         selfrow) = ctx.saved_tensors
+        temperature, normalize, same_rows, c, n_class = ctx.cfg
         if not ctx.needs_input_grad[0]:
-            return (None,) * 9
+            return (None,) * 12
         d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
-                                grad_out.reshape(1), True, True)
+                                grad_out.reshape(1), True, True, n_class, selfcol, selfrow, u, lsum)
         dfeat = torch.zeros_like(fm)
         _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
         _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
-        return dfeat, None, None, None, None, None, None, None, None
+        return (dfeat,) + (None,) * 11
 
 
-def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False):
+def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False, n_class=0,
+             selfcol=None, selfrow=None):
     """``same_rows``: anchors and contrast rows are the same gathered rows (one gather); their labels may
-    still differ (ISCL compares query labels with the anchors' dominant labels)."""
+    still differ (ISCL compares query labels with the anchors' dominant labels).
+    ``n_class`` in 1..8: labels are class indices in [0, n_class) and ids are unique -> analytic sweeps; the
+    self-pair maps are derived from the ids unless given."""
     meta_a = ops.pad_meta(lab_a, id_a)
     meta_b = meta_a if (same_rows and lab_b is lab_a) else ops.pad_meta(lab_b, id_b)
+    if n_class > 0 and selfcol is None:
+        if same_rows:
+            selfcol = torch.arange(idx_a.numel(), device=feat.device, dtype=torch.int32)
+            selfrow = selfcol
+        else:
+            selfcol, selfrow = ops.self_maps(id_a, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
-                          float(temperature), bool(normalize), bool(same_rows))
+                          float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow)
 
 
 def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch.Tensor, device) -> torch.Tensor:
@@ -71,7 +88,7 @@ def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch
     return (img.view(-1, 1) * (h * w) + grid.view(1, -1)).reshape(-1)             # (v, b, y, x) order
 
 
-def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False):
+def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False, n_class=0):
     if features.ndim <= 3:                                                          # :334-336
         raise ValueError('`features` needs to be [bsz, n_views, ...],'
                          'at least 4 dimensions are required')
@@ -94,18 +111,20 @@ def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False):
     else:
         lab = (ids % (m // v)).to(torch.int32)                                      # :360-361 same pixel, other views
         weight = torch.full((m,), 1.0 / m, device=dev)                              # :386
-    return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True)
+    return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True,
+                    n_class=n_class if labels is not None else 0)
 
 
 class SupConLoss(nn.Module):
     """Reference utils/loss.py:315-387.  ``contrast_mode`` / ``base_temperature`` are stored and
     unused there too."""
 
-    def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07):
+    def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07, n_class=0):
         super().__init__()
         self.temperature = temperature
         self.contrast_mode = contrast_mode
         self.base_temperature = base_temperature
+        self.n_class = n_class          # extension: 1..8 = labels are class indices -> analytic tensor-core sweeps
 
     def forward(self, features, labels=None):
         if features.ndim <= 3:
@@ -113,16 +132,17 @@ class SupConLoss(nn.Module):
                              'at least 4 dimensions are required')
         h, w = features.shape[-2:]
         dev = features.device
-        return _supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev))
+        return _supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev),
+                       n_class=self.n_class)
 
 
 class LocalConLoss(nn.Module):
     """Reference utils/loss.py:390-413: stride-subsampled SupCon."""
 
-    def __init__(self, temperature=0.7, stride=4):
+    def __init__(self, temperature=0.7, stride=4, n_class=0):
         super().__init__()
         self.temp = temperature
-        self.supconloss = SupConLoss(temperature=self.temp)
+        self.supconloss = SupConLoss(temperature=self.temp, n_class=n_class)
         self.stride = stride
 
     def forward(self, features, labels=None):
@@ -130,17 +150,17 @@ class LocalConLoss(nn.Module):
         dev = features.device
         ys = torch.arange(0, h, self.stride, device=dev)
         xs = torch.arange(0, w, self.stride, device=dev)
-        return _supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True)
+        return _supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True, n_class=self.supconloss.n_class)
 
 
 class BlockConLoss(nn.Module):
     """Reference utils/loss.py:416-466: mean of SupCon over block_size x block_size tiles; tiles whose
     labels are all background are skipped (decided on the device, no per-tile host sync)."""
 
-    def __init__(self, temperature=0.7, block_size=32):
+    def __init__(self, temperature=0.7, block_size=32, n_class=0):
         super().__init__()
         self.block_size = block_size
-        self.supconloss = SupConLoss(temperature=temperature)
+        self.supconloss = SupConLoss(temperature=temperature, n_class=n_class)
 
     def forward(self, features, labels=None):
         dev = features.device
@@ -152,7 +172,8 @@ class BlockConLoss(nn.Module):
             for j in range(div):
                 ys = torch.arange(i * bs, (i + 1) * bs, device=dev)
                 xs = torch.arange(j * bs, (j + 1) * bs, device=dev)
-                losses.append(_supcon(features, labels, t, ys, xs, zero_if_no_foreground=True))
+                losses.append(_supcon(features, labels, t, ys, xs, zero_if_no_foreground=True,
+                                      n_class=self.supconloss.n_class))
                 if labels is not None:
                     flags.append((labels[:, :, i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] != 0).any())
         if not losses:
@@ -190,7 +211,8 @@ def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, 
 
 def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
                         temperature: float = 0.7, generator: Optional[torch.Generator] = None,
-                        anchor_idx: Optional[torch.Tensor] = None, contrast_idx: Optional[torch.Tensor] = None):
+                        anchor_idx: Optional[torch.Tensor] = None, contrast_idx: Optional[torch.Tensor] = None,
+                        analytic: bool = True):
     """Sampled rectangular pixel <-> pixel loss (BASELINE.json configs[2]): anchors x contrast rows
     drawn class-balanced from an NCHW map, L2-normalised, bf16 tensor-core similarities."""
     if anchor_idx is None or contrast_idx is None:
@@ -199,7 +221,9 @@ def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int,
     la, lb = lab[anchor_idx], lab[contrast_idx]
     fg = (la != 0).float()
     weight = fg / fg.sum()
-    return p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True)
+    # analytic sweeps need class-index labels (true here) and unique picks (randperm prefixes are)
+    return p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True,
+                    n_class=n_class if (analytic and n_class <= 8) else 0)
 
 
 class InterpolatedSupervisedContrastiveLoss(nn.Module):

@@ -89,27 +89,34 @@ class ProtoPlan:
 class P2PPlan:
     """Pixel<->pixel loss forward + backward (slcl_p2p_fwd / slcl_p2p_bwd) on fixed device buffers:
     anchors a [A, dp] and contrast rows b [M, dp] (bf16, dp % 64 == 0), padded int32 metadata
-    (slcl.ops.pad_meta), shift / weight [A].  Outputs: loss[1], stats[A,3], d_a [A, dim], d_b [M, dim]."""
+    (slcl.ops.pad_meta), shift / weight [A].  ``n_class`` > 0 selects the analytic sweeps (class-index labels,
+    self-pair maps a_selfcol / b_selfrow).  Outputs: loss[1], stats[A,3], d_a [A, dim], d_b [M, dim]."""
 
     def __init__(self, a: torch.Tensor, b: torch.Tensor, dim: int, a_meta: torch.Tensor, b_meta: torch.Tensor,
-                 shift: torch.Tensor, weight: torch.Tensor, temperature: float):
+                 shift: torch.Tensor, weight: torch.Tensor, temperature: float, n_class: int = 0,
+                 a_selfcol: torch.Tensor = None, b_selfrow: torch.Tensor = None):
         self.lib = _lib.load()
         self.dev = _lib.require_cuda(a, b, a_meta, b_meta, shift, weight)
         na, dp = a.shape
         m = b.shape[0]
-        self.keep = (a, b, a_meta, b_meta, shift, weight)
+        self.keep = (a, b, a_meta, b_meta, shift, weight, a_selfcol, b_selfrow)
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.stats = torch.empty((na, 3), **f32)
         self.loss = torch.empty(1, **f32)
         self.d_a = torch.empty((na, dim), **f32)
         self.d_b = torch.empty((m, dim), **f32)
         self.grad_out = torch.ones(1, **f32)
+        self.u = torch.empty((na, dp), **f32) if n_class > 0 else None
+        self.label_sums = torch.empty((n_class, dp + 1), **f32) if n_class > 0 else None
         self.ws = torch.empty(max(self.lib.slcl_p2p_workspace_bytes(na, m, dp), 256), dtype=torch.uint8, device=self.dev)
         t = C.c_float(float(temperature))
-        self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(shift), ptr(weight), t, ptr(self.stats),
-                          ptr(self.loss), ptr(self.ws), self.ws.numel())
-        self._bwd_args = (ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(shift), ptr(weight), t,
-                          ptr(self.stats), ptr(self.grad_out), ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
+        self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class), ptr(shift),
+                          ptr(weight), t, ptr(self.stats), ptr(self.loss), ptr(self.u), ptr(self.label_sums), ptr(self.ws),
+                          self.ws.numel())
+        self._fwd_only_args = self._fwd_args[:14] + (None, None) + self._fwd_args[16:]
+        self._bwd_args = (ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
+                          int(n_class), ptr(shift), ptr(weight), t, ptr(self.stats), ptr(self.u), ptr(self.label_sums),
+                          ptr(self.grad_out), ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
         self.flops = 8.0 * na * m * dp
         self.graph = None
 
@@ -117,7 +124,13 @@ class P2PPlan:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def forward(self) -> torch.Tensor:
+        """forward that also keeps what the backward needs (analytic mode: U and the per-class row sums)"""
         check(self.lib.slcl_p2p_fwd(*self._fwd_args, self._stream()), "slcl_p2p_fwd")
+        return self.loss
+
+    def forward_only(self) -> torch.Tensor:
+        """loss and statistics only (no-grad evaluation)"""
+        check(self.lib.slcl_p2p_fwd(*self._fwd_only_args, self._stream()), "slcl_p2p_fwd")
         return self.loss
 
     def backward(self):

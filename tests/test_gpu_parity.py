@@ -404,6 +404,13 @@ def test_kat6_supcon_vs_reference_golden(api, golden):
     grad_close(f.grad, golden["kat6_unlab_dfeat"], rtol=P2P_RTOL, floor=0.5)
     from slcl import losses
     close(losses.SupConLoss(.7)(f5.to(dev()), lab.to(dev())), golden["kat6_dup_loss"], rtol=P2P_RTOL)
+    # analytic sweeps (labels declared as class indices 0..3): same numbers
+    f = f5.to(dev()).requires_grad_(True)
+    out = loss_mod.SupConLoss(.7, n_class=4)(f, lab.to(dev()))
+    out.backward()
+    close(out, golden["kat6_loss"], rtol=P2P_RTOL)
+    assert abs(out.item() - 4.883881568908691) < 4.883881568908691 * 2e-3
+    grad_close(f.grad, golden["kat6_dfeat"], rtol=P2P_RTOL, floor=0.5)
 
 
 def test_kat7_local_and_block_con_loss(api, golden):
@@ -413,6 +420,8 @@ def test_kat7_local_and_block_con_loss(api, golden):
     close(loss_mod.LocalConLoss(.7, 4)(f, lab7.to(dev())), golden["kat7_local"], rtol=P2P_RTOL)
     close(loss_mod.BlockConLoss(.7, 32)(f, lab7.to(dev())), golden["kat7_block"], rtol=P2P_RTOL)
     close(loss_mod.LocalConLoss(.7, 4)(f), golden["kat7_local_unlab"], rtol=P2P_RTOL)
+    close(loss_mod.LocalConLoss(.7, 4, n_class=4)(f, lab7.to(dev())), golden["kat7_local"], rtol=P2P_RTOL)
+    close(loss_mod.BlockConLoss(.7, 32, n_class=4)(f, lab7.to(dev())), golden["kat7_block"], rtol=P2P_RTOL)
     # all-background labels: the reference returns 0 (early-out, utils/loss.py:405-407 / :445-447)
     zero = torch.zeros_like(lab7).to(dev())
     assert loss_mod.LocalConLoss(.7, 4)(f, zero).item() == 0.0
@@ -435,12 +444,14 @@ def test_supcon_unnormalised_features_vs_oracle(api):
     grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
 
 
+@pytest.mark.parametrize("analytic", [True, False])
 @pytest.mark.parametrize("b,c,h,w,k,na,nc,t", [
     (2, 40, 24, 24, 4, 200, 600, 0.7),        # ragged: A, M not multiples of the tiles; C padded 40 -> 64
     (2, 256, 16, 16, 5, 128, 512, 0.07),      # cfg3 dimensionality and temperature stress
     (1, 96, 12, 12, 3, 60, 144, 0.2),         # anchors == a third of all pixels
+    (4, 128, 32, 32, 5, 1000, 3000, 0.7),     # several row tiles and column splits
 ])
-def test_sampled_rectangular_loss_vs_oracle(b, c, h, w, k, na, nc, t):
+def test_sampled_rectangular_loss_vs_oracle(b, c, h, w, k, na, nc, t, analytic):
     """Sampler + rectangular loss are our spec (parity unpinned by the reference); the indices come from
     PyTorch's RNG stream on both sides, so they must be bit-identical."""
     from slcl import p2p
@@ -464,7 +475,8 @@ def test_sampled_rectangular_loss_vs_oracle(b, c, h, w, k, na, nc, t):
                         lab_flat[c_idx_o], a_idx_o, c_idx_o, t)
     ref.backward()
     f = feat.to(dev()).requires_grad_(True)
-    out = p2p.sampled_supcon_loss(f, labels.to(dev()), na, nc, k, temperature=t, anchor_idx=a_idx, contrast_idx=c_idx)
+    out = p2p.sampled_supcon_loss(f, labels.to(dev()), na, nc, k, temperature=t, anchor_idx=a_idx, contrast_idx=c_idx,
+                                  analytic=analytic)
     out.backward()
     close(out, ref, rtol=P2P_RTOL)
     grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
@@ -487,8 +499,8 @@ def test_p2p_full_size_properties_cfg3():
     from slcl import ops as slcl_ops
     ma, mb = slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib)
     s1 = torch.full((na,), 1.0 / t, device=dev())
-    l1, st1 = op.p2p_fwd(a, b, ma, mb, s1, w, t)
-    l2, _ = op.p2p_fwd(a, b, ma, mb, s1 * 1.5 + 0.3, w, t)
+    l1, st1, _, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t)
+    l2, _, _, _ = op.p2p_fwd(a, b, ma, mb, s1 * 1.5 + 0.3, w, t)
     close(l1, l2, rtol=1e-5)
     s = a.float() @ b.float().t() / t
     notself = ia.view(-1, 1) != ib.view(1, -1)
@@ -497,6 +509,29 @@ def test_p2p_full_size_properties_cfg3():
     row = lz - (s * pos).sum(1) / pos.sum(1)
     close(l1, (row * w).sum(), rtol=1e-4)
     assert torch.equal(st1[:, 2].long(), pos.sum(1))                       # positive counts are exact
+    # analytic sweeps (class-index labels): same statistics, loss and gradients as the per-element path and as
+    # fp32 torch autograd on the same bf16 rows
+    selfcol, selfrow = slcl_ops.self_maps(ia, ib)
+    assert torch.equal(selfcol.long(), pick) and torch.equal(selfrow[pick].long(), torch.arange(na, device=dev()))
+    l3, st3, u, lsum = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, True)
+    l4, st4, _, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, False)
+    close(l3, l1, rtol=1e-5)
+    close(l4, l1, rtol=1e-5)
+    assert torch.equal(st3[:, 2].long(), pos.sum(1))
+    assert torch.allclose(st3[:, 0], st1[:, 0], rtol=1e-4) and torch.allclose(st3[:, 1], st1[:, 1], rtol=1e-3, atol=1e-2)
+    assert torch.equal(lsum[:, -1].long(), torch.bincount(lb.long(), minlength=5))
+    g_out = torch.full((1,), 0.7, device=dev())
+    da_g, db_g = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st1, g_out, True, True)
+    da_a, db_a = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow, u, lsum)
+    da_r, db_r = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow)   # U regenerated
+    af, bf = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    sf = af @ bf.t() / t
+    lzf = torch.logsumexp(sf.masked_fill(~notself, float("-inf")), dim=1)
+    ((lzf - (sf * pos).sum(1) / pos.sum(1)) * w).sum().mul(0.7).backward()
+    for got_a, got_b in ((da_g, db_g), (da_a, db_a), (da_r, db_r)):
+        grad_close(got_a, af.grad, rtol=P2P_RTOL, floor=0.5)
+        grad_close(got_b, bf.grad, rtol=P2P_RTOL, floor=0.5)
+    assert torch.equal(da_a, da_r) and torch.equal(db_a, db_r)             # deterministic, with or without the kept U
 
 
 def test_c_abi_called_directly_with_ctypes():

@@ -17,7 +17,7 @@ names = ["prod total", "prod wait c_empty", "prod wait m_empty", "-", "mma total
          "epi4 total", "epi4 wait m_full", "epi4 wait s_full", "epi4 wait g_empty", "epi11 total", "epi11 wait m_full", "epi11 wait s_full", "epi11 wait g_empty"]
 for mode in ("fwd", "bwd"):
     for _ in range(2):
-        loss, stats = op.p2p_fwd(bb, bb, mb, mb, shift, w, T)
+        loss, stats, _, _ = op.p2p_fwd(bb, bb, mb, mb, shift, w, T)
         torch.cuda.synchronize()
         if mode == "fwd":
             vals = prof.cpu().tolist()
