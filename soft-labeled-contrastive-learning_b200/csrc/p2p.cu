@@ -736,9 +736,9 @@ __global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64
 //     constants alpha~_i = w_i / (T Zs_i), beta~_i and the column shift of the dB sweep
 //     shift_i log2e - log2(alpha~_i)  (kShiftOff when alpha~_i == 0; pad entries up to a multiple of 64 too).
 // Stage 1: a block owns kLabelRowsPerBlock rows; a warp walks every 8th row of them with 16-byte loads (lane = 8
-// bf16 columns), four rows in flight; accumulators acc[K][8] in registers; fixed-order combine over the 8 warps
-// -> partial[block][K][d], cnt[block][K].  Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
-constexpr int kLabelRowsPerBlock = 128;
+// bf16 columns), eight rows in flight; label-indexed accumulators private to the warp in shared memory; fixed-order
+// combine over the 8 warps -> partial[block][K][d], cnt[block][K].  Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
+constexpr int kLabelRowsPerBlock = 64;
 __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16* rows, int n_rows, int d, const int2* meta,
                                                              int n_class, const float* stats, const float* weight,
                                                              const float* shift, float inv_t, float* alpha_out,
@@ -749,20 +749,21 @@ __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16
   const int r0 = blockIdx.x * kLabelRowsPerBlock;
   const int r1 = min(n_rows, r0 + kLabelRowsPerBlock);
   const bool col_ok = lane * 8 < d;
-  float acc[kMaxLabelClasses][8];
-  float c_acc[kMaxLabelClasses];
+  // the warp's private accumulators live in shared memory (label-indexed; lane = 8 columns, no conflicts)
+  float* s_sum = sm_lp;
+  float* s_cnt = sm_lp + (size_t)8 * n_class * d;
+  float* my_sum = s_sum + (size_t)warp * n_class * d;
+  float* my_cnt = s_cnt + warp * n_class;
+  for (int idx = lane; idx < n_class * d; idx += 32) my_sum[idx] = 0.f;
+  if (lane < n_class) my_cnt[lane] = 0.f;
+  __syncwarp();
+  constexpr int kInFlight = 8;
+  for (int rb = r0 + warp; rb < r1; rb += 8 * kInFlight) {
+    uint4 x[kInFlight];
+    int lab[kInFlight];
+    float coef[kInFlight];
 #pragma unroll
-  for (int k = 0; k < kMaxLabelClasses; ++k) {
-    c_acc[k] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-  }
-  for (int rb = r0 + warp; rb < r1; rb += 32) {
-    uint4 x[4];
-    int lab[4];
-    float coef[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kInFlight; ++u) {
       const int r = rb + 8 * u;
       lab[u] = -1; coef[u] = 1.f; x[u] = make_uint4(0u, 0u, 0u, 0u);
       if (r < r1) {
@@ -782,39 +783,24 @@ __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t wv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(wv[i] << 16);
-        f[2 * i + 1] = __uint_as_float(wv[i] & 0xFFFF0000u);
-      }
-#pragma unroll
-      for (int k = 0; k < kMaxLabelClasses; ++k) {
-        if (lab[u] == k) {
-          c_acc[k] += coef[u];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(coef[u], f[i], acc[k][i]);
+    for (int u = 0; u < kInFlight; ++u) {
+      if (lab[u] >= 0 && lab[u] < n_class) {            // warp-uniform
+        if (col_ok) {
+          float4* acc = reinterpret_cast<float4*>(my_sum + (size_t)lab[u] * d + lane * 8);
+          float4 a0 = acc[0], a1 = acc[1];
+          const float c = coef[u];
+          a0.x = fmaf(c, __uint_as_float(x[u].x << 16), a0.x); a0.y = fmaf(c, __uint_as_float(x[u].x & 0xFFFF0000u), a0.y);
+          a0.z = fmaf(c, __uint_as_float(x[u].y << 16), a0.z); a0.w = fmaf(c, __uint_as_float(x[u].y & 0xFFFF0000u), a0.w);
+          a1.x = fmaf(c, __uint_as_float(x[u].z << 16), a1.x); a1.y = fmaf(c, __uint_as_float(x[u].z & 0xFFFF0000u), a1.y);
+          a1.z = fmaf(c, __uint_as_float(x[u].w << 16), a1.z); a1.w = fmaf(c, __uint_as_float(x[u].w & 0xFFFF0000u), a1.w);
+          acc[0] = a0; acc[1] = a1;
         }
+        if (lane == 0) my_cnt[lab[u]] += coef[u];
       }
     }
   }
   if (colshift_out != nullptr && blockIdx.x == 0)          // pad entries of the column-shift array
     for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 256) colshift_out[r] = kShiftOff;
-  float* s_sum = sm_lp;
-  float* s_cnt = sm_lp + (size_t)8 * n_class * d;
-#pragma unroll
-  for (int k = 0; k < kMaxLabelClasses; ++k) {
-    if (k < n_class) {
-      if (col_ok) {
-        float4* dst = reinterpret_cast<float4*>(s_sum + ((size_t)warp * n_class + k) * d + lane * 8);
-        dst[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-        dst[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
-      }
-      if (lane == 0) s_cnt[warp * n_class + k] = c_acc[k];
-    }
-  }
   __syncthreads();
   for (int idx = threadIdx.x; idx < n_class * d; idx += 256) {
     float t = 0.f;
@@ -862,17 +848,8 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
   }
 }
 
-// per-class sums [K][d + 1] (global) -> shared s_sum[K][d], s_cnt[K]   (all threads; ends with __syncthreads)
-__device__ __forceinline__ void label_sums_to_smem(const float* sums, int n_class, int d, float* s_sum, float* s_cnt) {
-  for (int idx = threadIdx.x; idx < n_class * (d + 1); idx += blockDim.x) {
-    const int k = idx / (d + 1), c = idx % (d + 1);
-    const float v = sums[idx];
-    if (c < d) s_sum[k * d + c] = v; else s_cnt[k] = v;
-  }
-  __syncthreads();
-}
-
-// Forward finish, one warp per anchor i (fixed summation orders throughout):
+// Forward finish, one warp per anchor i (fixed summation orders throughout).  The per-class sums
+// label_sums[K][d + 1] (last column = class count) are read through L1 (a 5 KB table every warp shares).
 //   Zs_i   = sum_slots zs - e_self                      e_self = exp(S_i,self / T - shift_i) if anchor i is a contrast row
 //   P_raw  = a_i . Bsum[lab_i] - [labels agree] S_i,self        n_i = count[lab_i] - [labels agree]
 //   U_i    = sum_splits U_partial - bf16(e_self) b_self         (the sweep multiplied bf16-rounded exponentials)
@@ -883,31 +860,29 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
                                                              const int2* b_meta, const int32_t* a_selfcol,
                                                              const float* label_sums, int n_class, const float* u_partial,
                                                              int n_splits, float* u_out, float* stats, double* loss_partial) {
-  extern __shared__ float sm_ff[];                 // [K][d] + [K]
   __shared__ double red[8];
-  float* s_sum = sm_ff;
-  float* s_cnt = sm_ff + n_class * d;
-  label_sums_to_smem(label_sums, n_class, d, s_sum, s_cnt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
   for (int i = blockIdx.x * 8 + warp; i < n_rows; i += gridDim.x * 8) {
-    float zs = 0.f;
-    for (int s = 0; s < n_slots; ++s) zs += zs_partial[(size_t)s * n_rows + i];
     const __nv_bfloat16* ai = a + (size_t)i * d;
     const int lab = a_meta[i].x;
+    const int sc = a_selfcol ? a_selfcol[i] : -1;
     const bool lab_ok = lab >= 0 && lab < n_class;
+    float zp = 0.f;
+    for (int s = lane; s < n_slots; s += 32) zp += zs_partial[(size_t)s * n_rows + i];
+    float zs = warp_sum(zp);
     float praw = 0.f, n = 0.f;
     if (lab_ok) {
+      const float* bs = label_sums + (size_t)lab * (d + 1);
       float t = 0.f;
       for (int c = lane * 2; c < d; c += 64) {
         const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
-        t = fmaf(x.x, s_sum[lab * d + c], t);
-        t = fmaf(x.y, s_sum[lab * d + c + 1], t);
+        t = fmaf(x.x, __ldg(bs + c), t);
+        t = fmaf(x.y, __ldg(bs + c + 1), t);
       }
       praw = warp_sum(t);
-      n = s_cnt[lab];
+      n = __ldg(bs + d);
     }
-    const int sc = a_selfcol ? a_selfcol[i] : -1;
     float e_self_r = 0.f;
     if (sc >= 0) {
       const float s_self = warp_dot_bf16(ai, b + (size_t)sc * d, d, lane);
@@ -918,10 +893,21 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
     }
     if (u_out != nullptr) {
       const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
+      const size_t split_stride = (size_t)n_rows * d;
       for (int c = lane * 2; c < d; c += 64) {
+        const float* src = u_partial + (size_t)i * d + c;
         float2 t = make_float2(0.f, 0.f);
-        for (int s = 0; s < n_splits; ++s) {
-          const float2 p = *reinterpret_cast<const float2*>(u_partial + ((size_t)s * n_rows + i) * d + c);
+        int s = 0;
+        for (; s + 4 <= n_splits; s += 4) {                 // four loads in flight, summed in split order
+          const float2 p0 = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
+          const float2 p1 = *reinterpret_cast<const float2*>(src + (size_t)(s + 1) * split_stride);
+          const float2 p2 = *reinterpret_cast<const float2*>(src + (size_t)(s + 2) * split_stride);
+          const float2 p3 = *reinterpret_cast<const float2*>(src + (size_t)(s + 3) * split_stride);
+          t.x = (((t.x + p0.x) + p1.x) + p2.x) + p3.x;
+          t.y = (((t.y + p0.y) + p1.y) + p2.y) + p3.y;
+        }
+        for (; s < n_splits; ++s) {
+          const float2 p = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
           t.x += p.x; t.y += p.y;
         }
         if (sc >= 0) {
@@ -954,16 +940,9 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
                                                              const int2* b_meta, const int32_t* a_selfcol,
                                                              const int32_t* b_selfrow, const float* label_sums,
                                                              const float* ab_sums, int n_class, const float* alpha,
-                                                             const float* beta,
-                                                             const float* colshift, float scale_log2, const float* u,
-                                                             const float* acc_partial, int n_splits, const float* grad_out,
-                                                             float* d_a, float* d_b) {
-  extern __shared__ float sm_fb[];                 // Bsum [K][d] + ABsum [K][d] + [K]
-  float* s_b = sm_fb;
-  float* s_ab = sm_fb + n_class * d;
-  float* s_cnt = s_ab + n_class * d;
-  for (int idx = threadIdx.x; idx < n_class * d; idx += 256) s_b[idx] = label_sums[(idx / d) * (d + 1) + idx % d];
-  label_sums_to_smem(ab_sums, n_class, d, s_ab, s_cnt);
+                                                             const float* beta, const float* colshift, float scale_log2,
+                                                             const float* u, const float* acc_partial, int n_splits,
+                                                             const float* grad_out, float* d_a, float* d_b) {
   const float g = grad_out[0];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r_begin = d_a ? 0 : n_anchor, r_end = d_b ? n_anchor + n_contrast : n_anchor;
@@ -976,10 +955,11 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
       const bool match = sc >= 0 && lab == b_meta[sc].x;
       const float al = alpha[i], be = lab_ok ? beta[i] : 0.f;
       const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
+      const float* bsum = label_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
       for (int c = lane * 2; c < dim; c += 64) {
         const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)i * d + c);
         float2 p = make_float2(0.f, 0.f);
-        if (lab_ok) { p.x = s_b[lab * d + c]; p.y = s_b[lab * d + c + 1]; }
+        if (lab_ok) { p.x = __ldg(bsum + c); p.y = __ldg(bsum + c + 1); }
         if (match) {
           const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
           p.x -= x.x; p.y -= x.y;
@@ -1000,13 +980,14 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
         g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
         if (a_meta[i].x == lab) be_self = beta[i];
       }
+      const float* absum = ab_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
       for (int c = lane * 2; c < dim; c += 64) {
         float2 t = make_float2(0.f, 0.f);
         for (int s = 0; s < n_splits; ++s) {
           const float2 p = *reinterpret_cast<const float2*>(acc_partial + ((size_t)s * n_contrast + j) * d + c);
           t.x += p.x; t.y += p.y;
         }
-        if (lab_ok) { t.x -= s_ab[lab * d + c]; t.y -= s_ab[lab * d + c + 1]; }
+        if (lab_ok) { t.x -= __ldg(absum + c); t.y -= __ldg(absum + c + 1); }
         if (i >= 0) {
           const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(as + c));
           t.x += (be_self - g_self) * x.x; t.y += (be_self - g_self) * x.y;
@@ -1188,9 +1169,9 @@ bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t dp
          m < (int64_t)INT_MAX - BM && aligned16(a) && aligned16(b);
 }
 
-int finish_blocks(int64_t rows) {
-  const int64_t want = ceil_div<int64_t>(rows, 8), cap = kMaxFinishBlocks < 2 * sm_count() ? kMaxFinishBlocks : 2 * sm_count();
-  return (int)(want < cap ? want : cap);
+int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks loss partials
+  const int64_t want = ceil_div<int64_t>(rows, 8);
+  return (int)(want < kMaxFinishBlocks ? want : kMaxFinishBlocks);
 }
 
 int label_part_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared memory (> the 48 KB default)
@@ -1224,7 +1205,7 @@ int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, cons
                   : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
   if (st != SLCL_OK) return st;
   const int nb = finish_blocks(na);
-  p2p_finish_fwd_kernel<<<nb, 256, (size_t)n_class * (d + 1) * sizeof(float), stream>>>(
+  p2p_finish_fwd_kernel<<<nb, 256, 0, stream>>>(
       w.stat_partial, 2 * sw.splits, (int)na, shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, lsum, n_class,
       w.grad_partial_a, sw.splits, want_u ? u_out : nullptr, stats, w.loss_partial);
   return nb;
@@ -1327,7 +1308,7 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
       n_splits_b = sw.splits;
     }
     const int64_t rows = (d_a ? n_anchor : 0) + (d_b ? n_contrast : 0);
-    p2p_finish_bwd_kernel<<<finish_blocks(rows), 256, (size_t)(2 * n_class * d + n_class) * sizeof(float), stream>>>(
+    p2p_finish_bwd_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, stream>>>(
         na, (int)n_contrast, d, (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, label_sums, w.ab_sums, n_class, w.alpha, w.beta,
         w.colshift, inv_t * kLog2e, u, w.grad_partial_b, n_splits_b, grad_out, d_a, d_b);
     return check_launch("slcl_p2p_bwd");
