@@ -89,6 +89,11 @@ struct P2PArgs {
   const float* col_shift;             // kAnaCols: shift*log2e - log2(alpha) per column, padded to 64 entries
   float* stat_partial;                // row sums: [n_slots][n_rows][kStatN]
   float* grad_partial;                // MMA2 modes: [n_splits][n_rows][d] fp32
+  float* fused_out;                   // kAnaCols, one split: d_b [n_rows][ld_out] written by the drain itself (else null):
+  int ld_out;                         //   out = g (Acc - ABsum[label of the row]);  ab_sums [K][d+1], row labels = row_meta
+  int n_class;
+  const float* ab_sums;
+  const float* grad_out;
   unsigned long long* prof;           // bring-up: per-role wait-cycle counters of CTA (0,0), or null
 };
 
@@ -331,6 +336,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
   ColMeta* sMeta = reinterpret_cast<ColMeta*>(sC + (size_t)kStages * kc * BN * 128);
   Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
 
+  const long long t_entry = SLCL_PROF_NOW();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * BM;
   const int split = blockIdx.y;
@@ -613,8 +619,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
 
     if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
       unsigned long long* pp = a.prof + (warp == 4 ? 8 : 12);
-      pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1; pp[3] = 0;
+      pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1;
+      if (warp == 4) a.prof[3] = (unsigned long long)(tstart - t_entry);          // set-up + R load
     }
+    const long long t_drain = SLCL_PROF_NOW();
     if (MT::kRowSums) {
       if (row_ok) {
         float* out = a.stat_partial + ((size_t)(split * 2 + half) * a.n_rows + row) * MT::kStatN;
@@ -623,22 +631,60 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
       }
     }
     if (MT::kMma2) {
-      // accumulators -> global partial, 32 columns at a time; warps of the two halves split the d columns
+      // Accumulators -> global, 32 columns at a time; the warps of the two column halves interleave over d.
+      // Each 32 x 32 block is transposed through a padded staging tile in shared memory (the operand ring is idle
+      // now), so every store instruction writes one full 128-byte line of one row.
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
-      float* out = a.grad_partial + ((size_t)split * a.n_rows + row) * a.d;
+      float* stg = reinterpret_cast<float*>(sC) + (size_t)(warp - 4) * (32 * 33);
+      const bool fused = MODE == kAnaCols && a.fused_out != nullptr;
+      float* out = fused ? a.fused_out : a.grad_partial + (size_t)split * a.n_rows * a.d;
+      const int ld = fused ? a.ld_out : a.d;
+      float gscale = 1.f;
+      int lab = -1;
+      const float* tab = reinterpret_cast<const float*>(sC) + 8 * (32 * 33);      // fused: ABsum [K][d] in shared memory
+      if (fused) {
+        gscale = a.grad_out[0];
+        if (row_ok) lab = a.row_meta[row].x;
+        if (lab >= a.n_class) lab = -1;
+        float* tabw = reinterpret_cast<float*>(sC) + 8 * (32 * 33);
+        for (int idx = threadIdx.x - 128; idx < a.n_class * a.d; idx += 32 * kEpiWarps)
+          tabw[idx] = a.ab_sums[(size_t)(idx / a.d) * (a.d + 1) + idx % a.d];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");         // the eight epilogue warps only
+      }
       for (int c = half * 32; c < a.d; c += 64) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + kColAcc + c, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (fused) {
+          // thread = row: subtract the row's class sum (rows of one label broadcast the same 16 bytes) and scale
+          const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)max(lab, 0) * a.d + c);
+          const float m = lab >= 0 ? 1.f : 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(out + c + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                                  __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = t4[i];
+            v[4 * i] = __float_as_uint(gscale * fmaf(-m, t.x, __uint_as_float(v[4 * i])));
+            v[4 * i + 1] = __float_as_uint(gscale * fmaf(-m, t.y, __uint_as_float(v[4 * i + 1])));
+            v[4 * i + 2] = __float_as_uint(gscale * fmaf(-m, t.z, __uint_as_float(v[4 * i + 2])));
+            v[4 * i + 3] = __float_as_uint(gscale * fmaf(-m, t.w, __uint_as_float(v[4 * i + 3])));
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(v[i]);
+        __syncwarp();
+        const bool col_ok = c + lane < ld;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int grow = row0 + q * 32 + rr;
+          if (grow < a.n_rows && col_ok) out[(size_t)grow * ld + c + lane] = stg[rr * 33 + lane];
+        }
+        __syncwarp();
       }
       tc_fence_before();
+    }
+    if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp == 4) {
+      a.prof[11] = (unsigned long long)(SLCL_PROF_NOW() - t_drain);               // accumulator drain
+      a.prof[15] = (unsigned long long)(SLCL_PROF_NOW() - t_entry);               // whole CTA
     }
   }
   __syncthreads();
@@ -942,10 +988,12 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
                                                              const float* ab_sums, int n_class, const float* alpha,
                                                              const float* beta, const float* colshift, float scale_log2,
                                                              const float* u, const float* acc_partial, int n_splits,
-                                                             const float* grad_out, float* d_a, float* d_b) {
+                                                             int fused_db, const float* grad_out, float* d_a, float* d_b) {
+  // fused_db: the dB sweep already wrote d_b = g (Acc - ABsum[lab_j]); only the self-pair term is left, and it is
+  // added here by the warp of the anchor it belongs to (ids are unique, so no two warps touch the same row)
   const float g = grad_out[0];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_begin = d_a ? 0 : n_anchor, r_end = d_b ? n_anchor + n_contrast : n_anchor;
+  const int r_begin = (d_a || fused_db) ? 0 : n_anchor, r_end = (d_b && !fused_db) ? n_anchor + n_contrast : n_anchor;
   for (int r = r_begin + blockIdx.x * 8 + warp; r < r_end; r += gridDim.x * 8) {
     if (r < n_anchor) {
       const int i = r;
@@ -956,6 +1004,18 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
       const float al = alpha[i], be = lab_ok ? beta[i] : 0.f;
       const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
       const float* bsum = label_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
+      if (fused_db && sc >= 0) {
+        const __nv_bfloat16* ai = a + (size_t)i * d;
+        const float s_self = warp_dot_bf16(ai, bs, d, lane);
+        const float g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
+        const float coef = g * ((match ? beta[i] : 0.f) - g_self);
+        for (int c = lane * 2; c < dim; c += 64) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
+          d_b[(size_t)sc * dim + c] += coef * x.x;
+          if (c + 1 < dim) d_b[(size_t)sc * dim + c + 1] += coef * x.y;
+        }
+      }
+      if (d_a == nullptr) continue;
       for (int c = lane * 2; c < dim; c += 64) {
         const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)i * d + c);
         float2 p = make_float2(0.f, 0.f);
@@ -1297,20 +1357,25 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
         ab, na, d, am, n_class, stats, weight, shift, inv_t, w.alpha, w.beta, w.colshift, na_pad, w.lab_partial_a, w.lab_cnt_a);
     p2p_label_reduce_kernel<<<ceil_div(n_class * (d + 1), 32), 256, 0, stream>>>(w.lab_partial_a, w.lab_cnt_a, w.blocks_a, n_class, d,
                                                                                  w.ab_sums);
-    int n_splits_b = 0;
+    int n_splits_b = 0, fused_db = 0;
     if (d_b) {
       Sweep sw = plan_sweep(n_contrast, n_anchor);
       P2PArgs args{};
       args.col_shift = w.colshift;
       args.grad_partial = w.grad_partial_b;
+      if (sw.splits == 1) {        // one CTA sees all anchors of its rows: the drain writes d_b itself
+        fused_db = 1;
+        args.fused_out = d_b; args.ld_out = (int)dim; args.n_class = n_class; args.ab_sums = w.ab_sums; args.grad_out = grad_out;
+        args.row_meta = bm;
+      }
       int st = launch_sweep<kAnaCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
       if (st != SLCL_OK) return st;
       n_splits_b = sw.splits;
     }
-    const int64_t rows = (d_a ? n_anchor : 0) + (d_b ? n_contrast : 0);
+    const int64_t rows = ((d_a || fused_db) ? n_anchor : 0) + ((d_b && !fused_db) ? n_contrast : 0);
     p2p_finish_bwd_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, stream>>>(
         na, (int)n_contrast, d, (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, label_sums, w.ab_sums, n_class, w.alpha, w.beta,
-        w.colshift, inv_t * kLog2e, u, w.grad_partial_b, n_splits_b, grad_out, d_a, d_b);
+        w.colshift, inv_t * kLog2e, u, w.grad_partial_b, n_splits_b, fused_db, grad_out, d_a, d_b);
     return check_launch("slcl_p2p_bwd");
   }
   p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, (int)align_up((size_t)na, BN),
