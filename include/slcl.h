@@ -255,24 +255,28 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *     are then unused; instead
  *       a_selfcol [A] int32: the contrast row holding anchor i's own pixel, or -1 (null: no anchor is a contrast row)
  *       b_selfrow [M] int32: its inverse (anchor whose pixel contrast row j is, or -1); both or none.
- *       u [A, dp] fp32, label_sums [n_class, dp + 1] fp32 (both or none): extra forward OUTPUTS
- *         U_i = sum_{j != self} exp(S_ij - shift_i) b_j  and  {sum_{lab_j = k} b_j, #{lab_j = k}}; handing them back
- *         to slcl_p2p_bwd saves the backward one of its two sweeps (it regenerates them when null).
+ *       bwd_state: optional caller-owned buffer of slcl_p2p_state_bytes() bytes (16-byte aligned) that the forward
+ *         fills with what the backward can reuse -- U_i = sum_{j != self} exp(S_ij - shift_i) b_j, the per-class row
+ *         sums of both sides and the per-anchor constants.  Handing it back to slcl_p2p_bwd leaves the backward with
+ *         ONE tensor-core sweep (dB) and one finishing kernel; with null the backward regenerates it (one more sweep).
+ *     The per-class sums of the contrast rows do not depend on the sweep: they run on a side stream owned by the
+ *     library (one per host thread and device, created on first use; fork/join by events, graph-capturable).
  * forward : stats [A,3] = {sum_j exp(S_ij - shift_i), sum_pos S_ij * T, #pos},
  *           loss [1] = sum_i w_i (shift_i + log stats_i0 - stats_i1/(T stats_i2)).
  * backward: d_a [A, dim] and/or d_b [M, dim] fp32 = dL/da, dL/db for dL/dloss = *grad_out
  *           (either pointer may be null).
  * ------------------------------------------------------------------------- */
 size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast, int64_t dim_padded);
+size_t slcl_p2p_state_bytes(int64_t n_anchor, int64_t dim_padded);
 int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                  const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
                  const float* shift, const float* weight, float temperature, float* stats, float* loss,
-                 float* u, float* label_sums, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+                 void* bwd_state, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                  int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
                  const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
-                 const float* stats, const float* u, const float* label_sums, const float* grad_out,
-                 float* d_a, float* d_b, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+                 const float* stats, const void* bwd_state, const float* grad_out, float* d_a, float* d_b,
+                 void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
 #ifdef __cplusplus
 }

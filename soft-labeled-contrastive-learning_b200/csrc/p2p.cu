@@ -147,6 +147,11 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Programmatic dependent launch: every p2p kernel is launched with programmatic stream serialization, signals its
+// dependents right away and waits for its predecessors before it touches global memory, so launch latency and
+// set-up (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of the kernel in front.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -369,6 +374,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
   if (CS > 1) cluster_sync_all();          // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  pdl_trigger();
+  pdl_wait();                              // nothing above reads or writes global memory
 
   // Producer and MMA roles run with the WHOLE warp in the loop (converged, warp-uniform control flow) and
   // elect one lane only around the asynchronous instructions.  Running them under `if (lane == 0)` makes
@@ -717,6 +724,8 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __global__ void __launch_bounds__(256) p2p_reduce_stats_kernel(const float* partial, int n_slots, int n_rows, const float* shift,
                                                                const float* weight, float inv_t, float* stats,
                                                                double* loss_partial) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[8];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double acc = 0.0;
@@ -741,6 +750,8 @@ __global__ void __launch_bounds__(256) p2p_reduce_stats_kernel(const float* part
 }
 
 __global__ void __launch_bounds__(256) p2p_loss_kernel(const double* loss_partial, int n_blocks, float* loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[8];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n_blocks; i += 256) acc += loss_partial[i];
@@ -757,6 +768,8 @@ __global__ void __launch_bounds__(256) p2p_loss_kernel(const double* loss_partia
 // per-anchor backward constants {shift*log2e, alpha, beta, 0}: alpha = g w /(T Zs), beta = g w /(T n)
 __global__ void p2p_anchor_stat_kernel(const float* stats, const float* shift, const float* weight, const float* grad_out,
                                        int n, int n_padded, float inv_t, float4* out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded) return;
   if (i >= n) { out[i] = make_float4(0.f, 0.f, 0.f, 0.f); return; }      // pad entries (bulk-copied as column stats)
@@ -765,6 +778,8 @@ __global__ void p2p_anchor_stat_kernel(const float* stats, const float* shift, c
 }
 
 __global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64_t n_elems, int d_pad, int d, float* out) {
+  pdl_trigger();
+  pdl_wait();
   // partial: [splits][rows][d_pad] -> out [rows][d]
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_elems) return;
@@ -776,26 +791,49 @@ __global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64
 }
 
 // ---- analytic path ----------------------------------------------------------
-// Per-class row sums  out[k] = sum_{rows r with label k} coef_r * x_r  (and sum coef_r as the class "count").
-//   plain mode (stats == null): coef = 1                              -> Bsum / class counts of the contrast rows
-//   anchor mode: coef_i = beta~_i = w_i / (T n_i)  (0 when n_i == 0)  -> ABsum; the kernel also writes the per-anchor
-//     constants alpha~_i = w_i / (T Zs_i), beta~_i and the column shift of the dB sweep
-//     shift_i log2e - log2(alpha~_i)  (kShiftOff when alpha~_i == 0; pad entries up to a multiple of 64 too).
-// Stage 1: a block owns kLabelRowsPerBlock rows; a warp walks every 8th row of them with 16-byte loads (lane = 8
-// bf16 columns), eight rows in flight; label-indexed accumulators private to the warp in shared memory; fixed-order
-// combine over the 8 warps -> partial[block][K][d], cnt[block][K].  Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
+// Label-indexed accumulation of one bf16 row into a warp-private table in shared memory: tab[lab][c] += coef * x[c]
+// (lane = 8 consecutive columns, so the 32 lanes never collide), cnt[lab] += coef.
+__device__ __forceinline__ void label_table_add(float* tab, float* cnt, int d, int lab, float coef, uint4 x, int lane) {
+  if (lane * 8 < d) {
+    float4* acc = reinterpret_cast<float4*>(tab + (size_t)lab * d + lane * 8);
+    float4 a0 = acc[0], a1 = acc[1];
+    a0.x = fmaf(coef, __uint_as_float(x.x << 16), a0.x); a0.y = fmaf(coef, __uint_as_float(x.x & 0xFFFF0000u), a0.y);
+    a0.z = fmaf(coef, __uint_as_float(x.y << 16), a0.z); a0.w = fmaf(coef, __uint_as_float(x.y & 0xFFFF0000u), a0.w);
+    a1.x = fmaf(coef, __uint_as_float(x.z << 16), a1.x); a1.y = fmaf(coef, __uint_as_float(x.z & 0xFFFF0000u), a1.y);
+    a1.z = fmaf(coef, __uint_as_float(x.w << 16), a1.z); a1.w = fmaf(coef, __uint_as_float(x.w & 0xFFFF0000u), a1.w);
+    acc[0] = a0; acc[1] = a1;
+  }
+  if (lane == 0) cnt[lab] += coef;
+}
+// fixed-order combine of the eight warp tables of a block -> partial[block][K][d], cnt[block][K]  (after __syncthreads)
+__device__ __forceinline__ void label_tables_flush(const float* s_sum, const float* s_cnt, int n_class, int d, float* partial,
+                                                   float* cnt) {
+  for (int idx = threadIdx.x; idx < n_class * d; idx += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_sum[(size_t)w * n_class * d + idx];
+    partial[(size_t)blockIdx.x * n_class * d + idx] = t;
+  }
+  if ((int)threadIdx.x < n_class) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_cnt[w * n_class + threadIdx.x];
+    cnt[blockIdx.x * n_class + threadIdx.x] = t;
+  }
+}
+
+// Per-class row sums of the contrast rows, stage 1:  Bsum[k] = sum_{rows r with label k} x_r, count[k].
+// A block owns kLabelRowsPerBlock rows; a warp walks every 8th row of them with 16-byte loads, eight rows in flight.
+// Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
 constexpr int kLabelRowsPerBlock = 64;
 __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16* rows, int n_rows, int d, const int2* meta,
-                                                             int n_class, const float* stats, const float* weight,
-                                                             const float* shift, float inv_t, float* alpha_out,
-                                                             float* beta_out, float* colshift_out, int n_rows_padded,
-                                                             float* partial, float* cnt) {
+                                                             int n_class, float* partial, float* cnt) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm_lp[];                 // [8 warps][K][d] + [8][K]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = blockIdx.x * kLabelRowsPerBlock;
   const int r1 = min(n_rows, r0 + kLabelRowsPerBlock);
-  const bool col_ok = lane * 8 < d;
-  // the warp's private accumulators live in shared memory (label-indexed; lane = 8 columns, no conflicts)
   float* s_sum = sm_lp;
   float* s_cnt = sm_lp + (size_t)8 * n_class * d;
   float* my_sum = s_sum + (size_t)warp * n_class * d;
@@ -807,65 +845,29 @@ __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16
   for (int rb = r0 + warp; rb < r1; rb += 8 * kInFlight) {
     uint4 x[kInFlight];
     int lab[kInFlight];
-    float coef[kInFlight];
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
       const int r = rb + 8 * u;
-      lab[u] = -1; coef[u] = 1.f; x[u] = make_uint4(0u, 0u, 0u, 0u);
+      lab[u] = -1; x[u] = make_uint4(0u, 0u, 0u, 0u);
       if (r < r1) {
         lab[u] = meta[r].x;
-        if (col_ok) x[u] = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)r * d) + lane);
-        if (stats != nullptr) {
-          const float wt = weight[r] * inv_t;
-          const float n = stats[3 * r + 2];
-          coef[u] = n > 0.f ? wt / n : 0.f;
-          if (lane == 0) {
-            const float al = wt / stats[3 * r];
-            alpha_out[r] = al;
-            beta_out[r] = coef[u];
-            colshift_out[r] = al > 0.f ? shift[r] * kLog2e - log2f(al) : kShiftOff;
-          }
-        }
+        if (lane * 8 < d) x[u] = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)r * d) + lane);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kInFlight; ++u) {
-      if (lab[u] >= 0 && lab[u] < n_class) {            // warp-uniform
-        if (col_ok) {
-          float4* acc = reinterpret_cast<float4*>(my_sum + (size_t)lab[u] * d + lane * 8);
-          float4 a0 = acc[0], a1 = acc[1];
-          const float c = coef[u];
-          a0.x = fmaf(c, __uint_as_float(x[u].x << 16), a0.x); a0.y = fmaf(c, __uint_as_float(x[u].x & 0xFFFF0000u), a0.y);
-          a0.z = fmaf(c, __uint_as_float(x[u].y << 16), a0.z); a0.w = fmaf(c, __uint_as_float(x[u].y & 0xFFFF0000u), a0.w);
-          a1.x = fmaf(c, __uint_as_float(x[u].z << 16), a1.x); a1.y = fmaf(c, __uint_as_float(x[u].z & 0xFFFF0000u), a1.y);
-          a1.z = fmaf(c, __uint_as_float(x[u].w << 16), a1.z); a1.w = fmaf(c, __uint_as_float(x[u].w & 0xFFFF0000u), a1.w);
-          acc[0] = a0; acc[1] = a1;
-        }
-        if (lane == 0) my_cnt[lab[u]] += coef[u];
-      }
-    }
+    for (int u = 0; u < kInFlight; ++u)
+      if (lab[u] >= 0 && lab[u] < n_class) label_table_add(my_sum, my_cnt, d, lab[u], 1.f, x[u], lane);      // warp-uniform
   }
-  if (colshift_out != nullptr && blockIdx.x == 0)          // pad entries of the column-shift array
-    for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 256) colshift_out[r] = kShiftOff;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < n_class * d; idx += 256) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_sum[(size_t)w * n_class * d + idx];
-    partial[(size_t)blockIdx.x * n_class * d + idx] = t;
-  }
-  if (threadIdx.x < n_class) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_cnt[w * n_class + threadIdx.x];
-    cnt[blockIdx.x * n_class + threadIdx.x] = t;
-  }
+  label_tables_flush(s_sum, s_cnt, n_class, d, partial, cnt);
 }
 
 // Stage 2: out[k][c] (row stride d + 1; column d = count) = sum over blocks, fixed order.  A block owns 32 outputs;
 // 8 partial-lanes per output, combined through shared memory.
 __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* partial, const float* cnt, int n_blocks,
                                                                int n_class, int d, float* out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int o = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int n_out = n_class * (d + 1);
@@ -894,6 +896,55 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
   }
 }
 
+// Last kernel of the analytic forward: blocks [0, n_red) are stage 2 of ABsum (same scheme as p2p_label_reduce_kernel,
+// skipped when n_red == 0); the last block adds the per-block loss partials in index order.
+__global__ void __launch_bounds__(256) p2p_final_reduce_kernel(const float* ab_partial, const float* ab_cnt, int n_part_blocks,
+                                                               int n_class, int d, float* ab_out, int n_red,
+                                                               const double* loss_partial, int n_loss, float* loss) {
+  pdl_trigger();
+  pdl_wait();
+  if ((int)blockIdx.x < n_red) {
+    __shared__ float red[8][33];
+    const int o = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int n_out = n_class * (d + 1);
+    const int idx = blockIdx.x * 32 + o;
+    float t = 0.f;
+    if (idx < n_out) {
+      const int k = idx / (d + 1), c = idx % (d + 1);
+      const float* src = c < d ? ab_partial + (size_t)k * d + c : ab_cnt + k;
+      const size_t stride = c < d ? (size_t)n_class * d : (size_t)n_class;
+      float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int bb = pl;
+      for (; bb + 56 < n_part_blocks; bb += 64) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] += src[(size_t)(bb + 8 * u) * stride];
+      }
+      for (; bb < n_part_blocks; bb += 8) t8[0] += src[(size_t)bb * stride];
+      t = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+    }
+    red[pl][o] = t;
+    __syncthreads();
+    if (pl == 0 && idx < n_out) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[w][o];
+      ab_out[idx] = sum;
+    }
+    return;
+  }
+  __shared__ double redd[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_loss; i += 256) acc += loss_partial[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) redd[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += redd[w];
+    loss[0] = (float)t;
+  }
+}
+
 // Forward finish, one warp per anchor i (fixed summation orders throughout).  The per-class sums
 // label_sums[K][d + 1] (last column = class count) are read through L1 (a 5 KB table every warp shares).
 //   Zs_i   = sum_slots zs - e_self                      e_self = exp(S_i,self / T - shift_i) if anchor i is a contrast row
@@ -905,7 +956,24 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
                                                              const __nv_bfloat16* b, int d, const int2* a_meta,
                                                              const int2* b_meta, const int32_t* a_selfcol,
                                                              const float* label_sums, int n_class, const float* u_partial,
-                                                             int n_splits, float* u_out, float* stats, double* loss_partial) {
+                                                             int n_splits, float* u_out, float* alpha_out, float* beta_out,
+                                                             float* colshift_out, int n_rows_padded, float* ab_partial,
+                                                             float* ab_cnt, float* stats, double* loss_partial) {
+  pdl_trigger();
+  pdl_wait();
+  // With u_out (the forward keeps state for the backward) the kernel also writes the per-anchor constants
+  //   alpha~_i = w_i / (T Zs_i),  beta~_i = w_i / (T n_i) (0 when n_i == 0),  colshift_i = shift_i log2e - log2 alpha~_i
+  // and stage 1 of ABsum[k] = sum_{lab_i = k} beta~_i a_i  (block partials; p2p_final_reduce_kernel is stage 2).
+  extern __shared__ float sm_ff[];                 // keep-state mode: [8 warps][K][d] + [8][K]
+  float* s_sum = sm_ff;
+  float* s_cnt = sm_ff + (size_t)8 * n_class * d;
+  const bool keep = u_out != nullptr;
+  if (keep) {
+    for (int idx = threadIdx.x; idx < 8 * n_class * d; idx += 256) s_sum[idx] = 0.f;
+    if (threadIdx.x < 8 * n_class) s_cnt[threadIdx.x] = 0.f;
+    if (blockIdx.x == 0) for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 256) colshift_out[r] = kShiftOff;
+    __syncthreads();
+  }
   __shared__ double red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
@@ -963,11 +1031,28 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
         *reinterpret_cast<float2*>(u_out + (size_t)i * d + c) = t;
       }
     }
+    if (keep) {
+      const float wt = weight[i] * inv_t;
+      const float al = wt / zs, be = n > 0.f ? wt / n : 0.f;
+      if (lane == 0) {
+        alpha_out[i] = al; beta_out[i] = be;
+        colshift_out[i] = al > 0.f ? shift[i] * kLog2e - log2f(al) : kShiftOff;
+      }
+      if (lab_ok) {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (lane * 8 < d) x = __ldg(reinterpret_cast<const uint4*>(ai) + lane);
+        label_table_add(s_sum + (size_t)warp * n_class * d, s_cnt + warp * n_class, d, lab, be, x, lane);
+      }
+    }
     if (lane == 0) {
       stats[3 * i] = zs; stats[3 * i + 1] = praw; stats[3 * i + 2] = n;
       const float li = shift[i] + logf(zs) - (praw * inv_t) / n;      // n == 0 -> NaN, as 0/0 in the reference (:376-380)
       acc += (double)(weight[i] * li);
     }
+  }
+  if (keep) {
+    __syncthreads();
+    label_tables_flush(s_sum, s_cnt, n_class, d, ab_partial, ab_cnt);
   }
   if (lane == 0) red[warp] = acc;
   __syncthreads();
@@ -989,6 +1074,8 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
                                                              const float* beta, const float* colshift, float scale_log2,
                                                              const float* u, const float* acc_partial, int n_splits,
                                                              int fused_db, const float* grad_out, float* d_a, float* d_b) {
+  pdl_trigger();
+  pdl_wait();
   // fused_db: the dB sweep already wrote d_b = g (Acc - ABsum[lab_j]); only the self-pair term is left, and it is
   // added here by the warp of the anchor it belongs to (ids are unique, so no two warps touch the same row)
   const float g = grad_out[0];
@@ -1094,6 +1181,18 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_r
   return SLCL_OK;
 }
 
+// launch with programmatic stream serialization (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);        // errors surface through check_launch()
+}
+
 struct Sweep { int row_tiles, splits, cols_per_split, cluster; };
 
 Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
@@ -1124,13 +1223,15 @@ int launch_one(const CUtensorMap& mc, const P2PArgs& a, const Sweep& sw, size_t 
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t le = cudaLaunchKernelEx(&cfg, p2p_kernel<CS, MODE>, mc, a);
   if (le != cudaSuccess) { set_cuda_error(le, "cudaLaunchKernelEx(p2p_kernel)"); return SLCL_ERR_CUDA; }
   return check_launch("p2p_kernel");
@@ -1155,6 +1256,30 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   return launch_one<1, MODE>(mc, a, sw, smem, stream);
 }
 
+// State the analytic forward leaves for the backward (slcl_p2p_state_bytes): one caller-owned buffer.
+struct P2PState {
+  float* u;          // [Na][d]        U_i = sum_{j != self} exp(S_ij - shift_i) b_j
+  float* bsum;       // [K][d+1]       per-class sums / counts of the contrast rows
+  float* absum;      // [K][d+1]       sum_{lab_i = k} beta~_i a_i
+  float* colshift;   // [pad64(Na)]    column shifts of the dB sweep
+  float* alpha;      // [Na]
+  float* beta;       // [Na]
+  size_t total;
+};
+P2PState carve_state(void* p, int64_t na, int d) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t K = kMaxLabelClasses;
+  size_t o0 = take((size_t)na * d * sizeof(float)), o1 = take(K * (d + 1) * sizeof(float)), o2 = take(K * (d + 1) * sizeof(float));
+  size_t o3 = take(align_up((size_t)na, BN) * sizeof(float)), o4 = take((size_t)na * sizeof(float)), o5 = take((size_t)na * sizeof(float));
+  char* b = reinterpret_cast<char*>(p);
+  P2PState st;
+  st.u = reinterpret_cast<float*>(b + o0); st.bsum = reinterpret_cast<float*>(b + o1); st.absum = reinterpret_cast<float*>(b + o2);
+  st.colshift = reinterpret_cast<float*>(b + o3); st.alpha = reinterpret_cast<float*>(b + o4); st.beta = reinterpret_cast<float*>(b + o5);
+  st.total = off;
+  return st;
+}
+
 // workspace layout (one carve-up serves the general and the analytic path)
 constexpr int kMaxFinishBlocks = 1024;
 struct P2PWs {
@@ -1162,19 +1287,15 @@ struct P2PWs {
   float4* anchor_stat;     // general: [pad64(Na)]
   float* grad_partial_a;   // [splits_a][Na][d]   (general dA sweep / analytic U)
   float* grad_partial_b;   // [splits_b][M][d]
-  float* lab_partial_b;    // analytic: [blocks_b][K][d], then cnt [blocks_b][K]
+  float* lab_partial_b;    // analytic: [blocks_b][K][d], cnt [blocks_b][K]
   float* lab_cnt_b;
-  float* lab_partial_a;
-  float* lab_cnt_a;
-  float* alpha;            // [Na]
-  float* beta;             // [Na]
-  float* colshift;         // [pad64(Na)]
-  float* label_sums;       // [K][d+1]   (when the caller does not keep the forward's)
-  float* ab_sums;          // [K][d+1]
-  float* u;                // [Na][d]    (same)
-  float* stats_scratch;    // [Na][3]    (same)
+  float* ab_partial;       // [kMaxFinishBlocks][K][d], cnt [kMaxFinishBlocks][K]
+  float* ab_cnt;
+  float* bsum;             // [K][d+1]   (forward without state)
+  float* stats_scratch;    // [Na][3]    (backward without state)
   double* loss_partial;    // [kMaxFinishBlocks]
-  int blocks_a, blocks_b;
+  void* state;             // backward without state: regenerated here
+  int blocks_b;
   size_t total;
 };
 
@@ -1183,26 +1304,21 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   P2PWs w;
-  w.blocks_a = (int)ceil_div<int64_t>(na, kLabelRowsPerBlock);
   w.blocks_b = (int)ceil_div<int64_t>(m, kLabelRowsPerBlock);
   const size_t K = kMaxLabelClasses;
-  size_t o[16];
+  size_t o[12];
   o[0] = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
   o[1] = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
   o[2] = take((size_t)sa.splits * na * d * sizeof(float));
   o[3] = take((size_t)sb.splits * m * d * sizeof(float));
   o[4] = take((size_t)w.blocks_b * K * d * sizeof(float));
   o[5] = take((size_t)w.blocks_b * K * sizeof(float));
-  o[6] = take((size_t)w.blocks_a * K * d * sizeof(float));
-  o[7] = take((size_t)w.blocks_a * K * sizeof(float));
-  o[8] = take((size_t)na * sizeof(float));
-  o[9] = take((size_t)na * sizeof(float));
-  o[10] = take((size_t)align_up((size_t)na, BN) * sizeof(float));
-  o[11] = take(K * (d + 1) * sizeof(float));
-  o[12] = take((size_t)na * d * sizeof(float));
-  o[13] = take((size_t)na * 3 * sizeof(float));
-  o[14] = take((size_t)kMaxFinishBlocks * sizeof(double));
-  o[15] = take(K * (d + 1) * sizeof(float));
+  o[6] = take((size_t)kMaxFinishBlocks * K * d * sizeof(float));
+  o[7] = take((size_t)kMaxFinishBlocks * K * sizeof(float));
+  o[8] = take(K * (d + 1) * sizeof(float));
+  o[9] = take((size_t)na * 3 * sizeof(float));
+  o[10] = take((size_t)kMaxFinishBlocks * sizeof(double));
+  o[11] = take(carve_state(nullptr, na, d).total);
   char* b = reinterpret_cast<char*>(ws);
   w.stat_partial = reinterpret_cast<float*>(b + o[0]);
   w.anchor_stat = reinterpret_cast<float4*>(b + o[1]);
@@ -1210,16 +1326,12 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   w.grad_partial_b = reinterpret_cast<float*>(b + o[3]);
   w.lab_partial_b = reinterpret_cast<float*>(b + o[4]);
   w.lab_cnt_b = reinterpret_cast<float*>(b + o[5]);
-  w.lab_partial_a = reinterpret_cast<float*>(b + o[6]);
-  w.lab_cnt_a = reinterpret_cast<float*>(b + o[7]);
-  w.alpha = reinterpret_cast<float*>(b + o[8]);
-  w.beta = reinterpret_cast<float*>(b + o[9]);
-  w.colshift = reinterpret_cast<float*>(b + o[10]);
-  w.label_sums = reinterpret_cast<float*>(b + o[11]);
-  w.u = reinterpret_cast<float*>(b + o[12]);
-  w.stats_scratch = reinterpret_cast<float*>(b + o[13]);
-  w.loss_partial = reinterpret_cast<double*>(b + o[14]);
-  w.ab_sums = reinterpret_cast<float*>(b + o[15]);
+  w.ab_partial = reinterpret_cast<float*>(b + o[6]);
+  w.ab_cnt = reinterpret_cast<float*>(b + o[7]);
+  w.bsum = reinterpret_cast<float*>(b + o[8]);
+  w.stats_scratch = reinterpret_cast<float*>(b + o[9]);
+  w.loss_partial = reinterpret_cast<double*>(b + o[10]);
+  w.state = b + o[11];
   w.total = off;
   return w;
 }
@@ -1229,46 +1341,81 @@ bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t dp
          m < (int64_t)INT_MAX - BM && aligned16(a) && aligned16(b);
 }
 
-int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks loss partials
+int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks partials
   const int64_t want = ceil_div<int64_t>(rows, 8);
   return (int)(want < kMaxFinishBlocks ? want : kMaxFinishBlocks);
 }
 
-int label_part_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared memory (> the 48 KB default)
+int big_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared memory (> the 48 KB default)
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(8 * kMaxLabelClasses * (kMaxD + 1) * sizeof(float)));
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p_label_part_kernel)"); return SLCL_ERR_CUDA; }
+    const int bytes = (int)(8 * kMaxLabelClasses * (kMaxD + 1) * sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_finish_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p label tables)"); return SLCL_ERR_CUDA; }
     done = true;
   }
   return SLCL_OK;
 }
 
-// analytic forward pieces shared by slcl_p2p_fwd and the backward's fallback
+// Side stream for work that does not depend on the sweep (the per-class sums of the contrast rows): it runs on the
+// SMs the sweep leaves idle.  One stream + two events per host thread and device, created on first use; the fork
+// and the join are ordinary event dependencies, so they are captured into CUDA graphs like any other edge.
+struct Aux { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+Aux* aux_stream() {
+  static thread_local Aux cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Aux& x = cache[dev];
+  if (x.s == nullptr) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) {
+      x.s = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &x;
+}
+
+// analytic forward: [side stream: label sums of b]  ||  sweep  ->  finish (+ constants, ABsum partials)  ->  final reduce
 int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, const int2* am, const int2* bm,
-                const int32_t* a_selfcol, int n_class, const float* shift, const float* weight, float inv_t, bool want_u,
-                float* stats, float* u_out, float* label_sums_out, const P2PWs& w, cudaStream_t stream) {
+                const int32_t* a_selfcol, int n_class, const float* shift, const float* weight, float inv_t,
+                float* stats, float* loss, const P2PState* state, const P2PWs& w, cudaStream_t stream) {
   const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a);
   const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
-  float* lsum = label_sums_out ? label_sums_out : w.label_sums;
-  if (int st0 = label_part_smem_ok()) return st0;
-  p2p_label_part_kernel<<<w.blocks_b, 256, (size_t)8 * n_class * (d + 1) * sizeof(float), stream>>>(
-      bb, (int)m, d, bm, n_class, nullptr, nullptr, nullptr, inv_t, nullptr, nullptr, nullptr, 0, w.lab_partial_b, w.lab_cnt_b);
-  p2p_label_reduce_kernel<<<ceil_div(n_class * (d + 1), 32), 256, 0, stream>>>(w.lab_partial_b, w.lab_cnt_b, w.blocks_b, n_class, d, lsum);
+  if (int st0 = big_smem_ok()) return st0;
+  const bool keep = state != nullptr;
+  float* bsum = keep ? state->bsum : w.bsum;
+  const size_t table_smem = (size_t)8 * n_class * (d + 1) * sizeof(float);
+  Aux* aux = aux_stream();
+  cudaStream_t side = stream;
+  if (aux != nullptr && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
+    side = aux->s;
+  launch_pdl(p2p_label_part_kernel, dim3(w.blocks_b), dim3(256), table_smem, side, bb, (int)m, d, bm, n_class, w.lab_partial_b,
+             w.lab_cnt_b);
+  launch_pdl(p2p_label_reduce_kernel, dim3(ceil_div(n_class * (d + 1), 32)), dim3(256), 0, side, w.lab_partial_b, w.lab_cnt_b,
+             w.blocks_b, n_class, d, bsum);
+  if (side != stream) cudaEventRecord(aux->join, side);
   Sweep sw = plan_sweep(na, m);
   P2PArgs args{};
   args.row_shift = shift;
   args.stat_partial = w.stat_partial;
   args.grad_partial = w.grad_partial_a;
-  int st = want_u ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream)
-                  : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
+  int st = keep ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream)
+                : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
+  if (side != stream) cudaStreamWaitEvent(stream, aux->join, 0);          // join even when the sweep failed to launch
   if (st != SLCL_OK) return st;
   const int nb = finish_blocks(na);
-  p2p_finish_fwd_kernel<<<nb, 256, 0, stream>>>(
-      w.stat_partial, 2 * sw.splits, (int)na, shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, lsum, n_class,
-      w.grad_partial_a, sw.splits, want_u ? u_out : nullptr, stats, w.loss_partial);
-  return nb;
+  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(256), keep ? table_smem : 0, stream, w.stat_partial, 2 * sw.splits, (int)na,
+             shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, bsum, n_class, w.grad_partial_a, sw.splits,
+             keep ? state->u : nullptr, keep ? state->alpha : nullptr, keep ? state->beta : nullptr,
+             keep ? state->colshift : nullptr, (int)align_up((size_t)na, BN), w.ab_partial, w.ab_cnt, stats, w.loss_partial);
+  const int n_red = keep ? ceil_div(n_class * (d + 1), 32) : 0;
+  launch_pdl(p2p_final_reduce_kernel, dim3(n_red + 1), dim3(256), 0, stream, w.ab_partial, w.ab_cnt, nb, n_class, d,
+             keep ? state->absum : nullptr, n_red, w.loss_partial, nb, loss);
+  return SLCL_OK;
 }
 
 }  // namespace
@@ -1281,15 +1428,20 @@ extern "C" size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast,
   return carve(nullptr, n_anchor, n_contrast, (int)dim_padded).total;
 }
 
+extern "C" size_t slcl_p2p_state_bytes(int64_t n_anchor, int64_t dim_padded) {
+  if (n_anchor <= 0 || dim_padded <= 0 || dim_padded > kMaxD) return 0;
+  return carve_state(nullptr, n_anchor, (int)dim_padded).total;
+}
+
 extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                             const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
-                            const float* shift, const float* weight, float temperature, float* stats, float* loss, float* u,
-                            float* label_sums, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+                            const float* shift, const float* weight, float temperature, float* stats, float* loss,
+                            void* bwd_state, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
       !loss || !workspace || !(temperature > 0.f) || n_class < 0 || n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
-  if (n_class == 0 && (a_selfcol || u || label_sums)) return SLCL_ERR_INVALID_ARGUMENT;
-  if (n_class > 0 && (u != nullptr) != (label_sums != nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
@@ -1300,36 +1452,37 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   const int na = (int)n_anchor;
   const int2* am = reinterpret_cast<const int2*>(a_meta);
   const int2* bm = reinterpret_cast<const int2*>(b_meta);
-  int nb;
   if (n_class > 0) {
-    nb = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, u != nullptr,
-                     stats, u, label_sums, w, stream);
-    if (nb < 0) return nb;
-  } else {
-    Sweep sw = plan_sweep(n_anchor, n_contrast);
-    P2PArgs args{};
-    args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
-    int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
+    P2PState st_ = carve_state(bwd_state, n_anchor, d);
+    int st = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, stats, loss,
+                         bwd_state ? &st_ : nullptr, w, stream);
     if (st != SLCL_OK) return st;
-    nb = ceil_div(na, 256);
-    p2p_reduce_stats_kernel<<<nb, 256, 0, stream>>>(w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats, w.loss_partial);
+    return check_launch("slcl_p2p_fwd");
   }
-  p2p_loss_kernel<<<1, 256, 0, stream>>>(w.loss_partial, nb, loss);
+  Sweep sw = plan_sweep(n_anchor, n_contrast);
+  P2PArgs args{};
+  args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
+  int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
+  if (st != SLCL_OK) return st;
+  const int nb = ceil_div(na, 256);
+  launch_pdl(p2p_reduce_stats_kernel, dim3(nb), dim3(256), 0, stream, w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats,
+             w.loss_partial);
+  launch_pdl(p2p_loss_kernel, dim3(1), dim3(256), 0, stream, w.loss_partial, nb, loss);
   return check_launch("slcl_p2p_fwd");
 }
 
 extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                             int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
                             const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
-                            const float* stats, const float* u, const float* label_sums, const float* grad_out, float* d_a,
-                            float* d_b, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+                            const float* stats, const void* bwd_state, const float* grad_out, float* d_a, float* d_b,
+                            void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
       !grad_out || !workspace || !(temperature > 0.f) || dim <= 0 || dim > dim_padded || (!d_a && !d_b) || n_class < 0 ||
       n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
   if ((a_selfcol == nullptr) != (b_selfrow == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
-  if (n_class == 0 && (a_selfcol || u || label_sums)) return SLCL_ERR_INVALID_ARGUMENT;
-  if ((u != nullptr) != (label_sums != nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
@@ -1343,29 +1496,22 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   if (n_class > 0) {
     const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a_bf16);
     const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b_bf16);
-    if (u == nullptr) {
-      // the caller did not keep the forward's U / label sums: one more forward sweep regenerates them
-      int nb = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, true,
-                           w.stats_scratch, w.u, w.label_sums, w, stream);
-      if (nb < 0) return nb;
-      u = w.u; label_sums = w.label_sums;
+    P2PState st_ = carve_state(const_cast<void*>(bwd_state ? bwd_state : w.state), n_anchor, d);
+    if (bwd_state == nullptr) {
+      // the caller did not keep the forward's state: one more forward sweep regenerates it in the workspace
+      int st = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t,
+                           w.stats_scratch, reinterpret_cast<float*>(w.loss_partial) /* scratch */, &st_, w, stream);
+      if (st != SLCL_OK) return st;
     }
-    // per-anchor constants, dB column shifts and stage 1 of ABsum in one launch
-    const int na_pad = (int)align_up((size_t)na, BN);
-    if (int st0 = label_part_smem_ok()) return st0;
-    p2p_label_part_kernel<<<w.blocks_a, 256, (size_t)8 * n_class * (d + 1) * sizeof(float), stream>>>(
-        ab, na, d, am, n_class, stats, weight, shift, inv_t, w.alpha, w.beta, w.colshift, na_pad, w.lab_partial_a, w.lab_cnt_a);
-    p2p_label_reduce_kernel<<<ceil_div(n_class * (d + 1), 32), 256, 0, stream>>>(w.lab_partial_a, w.lab_cnt_a, w.blocks_a, n_class, d,
-                                                                                 w.ab_sums);
     int n_splits_b = 0, fused_db = 0;
     if (d_b) {
       Sweep sw = plan_sweep(n_contrast, n_anchor);
       P2PArgs args{};
-      args.col_shift = w.colshift;
+      args.col_shift = st_.colshift;
       args.grad_partial = w.grad_partial_b;
       if (sw.splits == 1) {        // one CTA sees all anchors of its rows: the drain writes d_b itself
         fused_db = 1;
-        args.fused_out = d_b; args.ld_out = (int)dim; args.n_class = n_class; args.ab_sums = w.ab_sums; args.grad_out = grad_out;
+        args.fused_out = d_b; args.ld_out = (int)dim; args.n_class = n_class; args.ab_sums = st_.absum; args.grad_out = grad_out;
         args.row_meta = bm;
       }
       int st = launch_sweep<kAnaCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
@@ -1373,13 +1519,14 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
       n_splits_b = sw.splits;
     }
     const int64_t rows = ((d_a || fused_db) ? n_anchor : 0) + ((d_b && !fused_db) ? n_contrast : 0);
-    p2p_finish_bwd_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, stream>>>(
-        na, (int)n_contrast, d, (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, label_sums, w.ab_sums, n_class, w.alpha, w.beta,
-        w.colshift, inv_t * kLog2e, u, w.grad_partial_b, n_splits_b, fused_db, grad_out, d_a, d_b);
+    launch_pdl(p2p_finish_bwd_kernel, dim3((unsigned)ceil_div<int64_t>(rows, 8)), dim3(256), 0, stream, na, (int)n_contrast, d,
+               (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, (const float*)st_.bsum, (const float*)st_.absum, n_class,
+               (const float*)st_.alpha, (const float*)st_.beta, (const float*)st_.colshift, inv_t * kLog2e, (const float*)st_.u,
+               (const float*)w.grad_partial_b, n_splits_b, fused_db, grad_out, d_a, d_b);
     return check_launch("slcl_p2p_bwd");
   }
-  p2p_anchor_stat_kernel<<<ceil_div(na + BN, 256), 256, 0, stream>>>(stats, shift, weight, grad_out, na, (int)align_up((size_t)na, BN),
-                                                                     inv_t, w.anchor_stat);
+  launch_pdl(p2p_anchor_stat_kernel, dim3(ceil_div(na + BN, 256)), dim3(256), 0, stream, stats, shift, weight, grad_out, na,
+             (int)align_up((size_t)na, BN), inv_t, w.anchor_stat);
   if (d_a) {
     Sweep sw = plan_sweep(n_anchor, n_contrast);
     P2PArgs args{};
@@ -1387,7 +1534,8 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     int st = launch_sweep<kGenRows>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
     if (st != SLCL_OK) return st;
     const int64_t n = n_anchor * dim;
-    p2p_reduce_grad_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(w.grad_partial_a, sw.splits, n, d, (int)dim, d_a);
+    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_a, sw.splits,
+               n, d, (int)dim, d_a);
   }
   if (d_b) {
     Sweep sw = plan_sweep(n_contrast, n_anchor);
@@ -1396,7 +1544,8 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
     if (st != SLCL_OK) return st;
     const int64_t n = n_contrast * dim;
-    p2p_reduce_grad_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(w.grad_partial_b, sw.splits, n, d, (int)dim, d_b);
+    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_b, sw.splits,
+               n, d, (int)dim, d_b);
   }
   return check_launch("slcl_p2p_bwd");
 }

@@ -508,44 +508,40 @@ def _selfcol_check(t: Optional[Tensor], n: int, what: str):
 @torch.library.custom_op("slcl::p2p_fwd", mutates_args=(), device_types="cuda")
 def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
             temperature: float, n_class: int = 0, a_selfcol: Optional[Tensor] = None,
-            want_u: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """-> (loss[1], stats[A,3], u[A,dp], label_sums[n_class,dp+1]); u / label_sums are empty unless
-    n_class > 0 (analytic mode, include/slcl.h) and want_u."""
+            keep_state: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (loss[1], stats[A,3], state): ``state`` is the opaque uint8 buffer for p2p_bwd (empty unless
+    n_class > 0 -- analytic mode, include/slcl.h -- and keep_state)."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight)
     lib = _lib.load()
     _p2p_check(a, b, a_meta, b_meta, shift, weight)
     na, dp = a.shape
     m = b.shape[0]
     _selfcol_check(a_selfcol, na, "a_selfcol")
-    if n_class == 0 and (a_selfcol is not None or want_u):
-        raise ValueError("a_selfcol / want_u need n_class > 0 (analytic mode)")
+    if n_class == 0 and (a_selfcol is not None or keep_state):
+        raise ValueError("a_selfcol / keep_state need n_class > 0 (analytic mode)")
     stats = torch.empty((na, 3), dtype=_F32, device=dev)
     loss = torch.empty(1, dtype=_F32, device=dev)
-    keep = n_class > 0 and want_u
-    u = torch.empty((na, dp) if keep else (0, dp), dtype=_F32, device=dev)
-    label_sums = torch.empty((n_class, dp + 1) if keep else (0, dp + 1), dtype=_F32, device=dev)
+    keep = n_class > 0 and keep_state
+    state = torch.empty(lib.slcl_p2p_state_bytes(na, dp) if keep else 0, dtype=torch.uint8, device=dev)
     ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
     with _guard(dev):
         st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class),
                               ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature), ptr(stats), ptr(loss),
-                              ptr(u) if keep else None, ptr(label_sums) if keep else None, ptr(ws), ws.numel(),
-                              stream_ptr(dev))
+                              ptr(state) if keep else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_p2p_fwd")
-    return loss, stats, u, label_sums
+    return loss, stats, state
 
 
 @p2p_fwd.register_fake
-def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, want_u=False):
-    keep = n_class > 0 and want_u
-    return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), shift.new_empty((a.shape[0] if keep else 0, a.shape[1])),
-            shift.new_empty((n_class if keep else 0, a.shape[1] + 1)))
+def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, keep_state=False):
+    return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), torch.empty(0, dtype=torch.uint8, device=a.device))
 
 
 @torch.library.custom_op("slcl::p2p_bwd", mutates_args=(), device_types="cuda")
 def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
             temperature: float, stats: Tensor, grad_out: Tensor, need_a: bool, need_b: bool, n_class: int = 0,
-            a_selfcol: Optional[Tensor] = None, b_selfrow: Optional[Tensor] = None, u: Optional[Tensor] = None,
-            label_sums: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+            a_selfcol: Optional[Tensor] = None, b_selfrow: Optional[Tensor] = None,
+            state: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """-> (d_a [A, dim], d_b [M, dim]) fp32 (empty when not needed)."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight, stats, grad_out)
     lib = _lib.load()
@@ -554,15 +550,11 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
     m = b.shape[0]
     _selfcol_check(a_selfcol, na, "a_selfcol")
     _selfcol_check(b_selfrow, m, "b_selfrow")
-    if u is not None and u.numel() == 0:
-        u = None
-    if label_sums is not None and label_sums.numel() == 0:
-        label_sums = None
-    if u is not None and (u.shape != (na, dp) or u.dtype != _F32 or not u.is_contiguous()):
-        raise ValueError("u must be contiguous float32 [A, dim_padded]")
-    if label_sums is not None and (label_sums.shape != (n_class, dp + 1) or label_sums.dtype != _F32
-                                   or not label_sums.is_contiguous()):
-        raise ValueError("label_sums must be contiguous float32 [n_class, dim_padded + 1]")
+    if state is not None and state.numel() == 0:
+        state = None
+    if state is not None and (state.dtype != torch.uint8 or state.numel() < lib.slcl_p2p_state_bytes(na, dp)
+                              or not state.is_contiguous()):
+        raise ValueError("state must be the uint8 buffer returned by p2p_fwd(..., keep_state=True)")
     d_a = torch.empty((na, dim) if need_a else (0, dim), dtype=_F32, device=dev)
     d_b = torch.empty((m, dim) if need_b else (0, dim), dtype=_F32, device=dev)
     ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
@@ -570,7 +562,7 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
     with _guard(dev):
         st = lib.slcl_p2p_bwd(ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
                               int(n_class), ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature),
-                              ptr(stats.contiguous()), ptr(u), ptr(label_sums), ptr(g),
+                              ptr(stats.contiguous()), ptr(state), ptr(g),
                               ptr(d_a) if need_a else None, ptr(d_b) if need_b else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_p2p_bwd")
     return d_a, d_b
@@ -578,7 +570,7 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
 
 @p2p_bwd.register_fake
 def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b, n_class=0, a_selfcol=None,
-      b_selfrow=None, u=None, label_sums=None):
+      b_selfrow=None, state=None):
     return (shift.new_empty((a.shape[0] if need_a else 0, dim)), shift.new_empty((b.shape[0] if need_b else 0, dim)))
 
 

@@ -39,23 +39,22 @@ class _P2PLoss(torch.autograd.Function):
             shift = torch.full_like(inv_a, 1.0 / temperature)
         else:   # upper bound of S_ij: |a_i| max_j |b_j| / T
             shift = (1.0 / inv_a) * ((1.0 / inv_b).amax() / temperature)
-        want_u = n_class > 0 and ctx.needs_input_grad[0]
-        loss, stats, u, lsum = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol,
-                                            want_u)
-        ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, u, lsum,
+        keep = n_class > 0 and ctx.needs_input_grad[0]
+        loss, stats, state = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol, keep)
+        ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state,
                               selfcol, selfrow)
         ctx.cfg = (temperature, normalize, same_rows, c, n_class)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
-        (fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, u, lsum, selfcol,
+        (fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state, selfcol,
          selfrow) = ctx.saved_tensors
         temperature, normalize, same_rows, c, n_class = ctx.cfg
         if not ctx.needs_input_grad[0]:
             return (None,) * 12
         d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
-                                grad_out.reshape(1), True, True, n_class, selfcol, selfrow, u, lsum)
+                                grad_out.reshape(1), True, True, n_class, selfcol, selfrow, state)
         dfeat = torch.zeros_like(fm)
         _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
         _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)

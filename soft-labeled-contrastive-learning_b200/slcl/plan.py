@@ -106,17 +106,16 @@ class P2PPlan:
         self.d_a = torch.empty((na, dim), **f32)
         self.d_b = torch.empty((m, dim), **f32)
         self.grad_out = torch.ones(1, **f32)
-        self.u = torch.empty((na, dp), **f32) if n_class > 0 else None
-        self.label_sums = torch.empty((n_class, dp + 1), **f32) if n_class > 0 else None
+        self.state = (torch.empty(self.lib.slcl_p2p_state_bytes(na, dp), dtype=torch.uint8, device=self.dev)
+                      if n_class > 0 else None)
         self.ws = torch.empty(max(self.lib.slcl_p2p_workspace_bytes(na, m, dp), 256), dtype=torch.uint8, device=self.dev)
         t = C.c_float(float(temperature))
         self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class), ptr(shift),
-                          ptr(weight), t, ptr(self.stats), ptr(self.loss), ptr(self.u), ptr(self.label_sums), ptr(self.ws),
-                          self.ws.numel())
-        self._fwd_only_args = self._fwd_args[:14] + (None, None) + self._fwd_args[16:]
+                          ptr(weight), t, ptr(self.stats), ptr(self.loss), ptr(self.state), ptr(self.ws), self.ws.numel())
+        self._fwd_only_args = self._fwd_args[:14] + (None,) + self._fwd_args[15:]
         self._bwd_args = (ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
-                          int(n_class), ptr(shift), ptr(weight), t, ptr(self.stats), ptr(self.u), ptr(self.label_sums),
-                          ptr(self.grad_out), ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
+                          int(n_class), ptr(shift), ptr(weight), t, ptr(self.stats), ptr(self.state), ptr(self.grad_out),
+                          ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
         self.flops = 8.0 * na * m * dp
         self.graph = None
 
@@ -124,7 +123,7 @@ class P2PPlan:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def forward(self) -> torch.Tensor:
-        """forward that also keeps what the backward needs (analytic mode: U and the per-class row sums)"""
+        """forward that also keeps what the backward needs (analytic mode: the state buffer)"""
         check(self.lib.slcl_p2p_fwd(*self._fwd_args, self._stream()), "slcl_p2p_fwd")
         return self.loss
 

@@ -499,8 +499,8 @@ def test_p2p_full_size_properties_cfg3():
     from slcl import ops as slcl_ops
     ma, mb = slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib)
     s1 = torch.full((na,), 1.0 / t, device=dev())
-    l1, st1, _, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t)
-    l2, _, _, _ = op.p2p_fwd(a, b, ma, mb, s1 * 1.5 + 0.3, w, t)
+    l1, st1, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t)
+    l2, _, _ = op.p2p_fwd(a, b, ma, mb, s1 * 1.5 + 0.3, w, t)
     close(l1, l2, rtol=1e-5)
     s = a.float() @ b.float().t() / t
     notself = ia.view(-1, 1) != ib.view(1, -1)
@@ -513,17 +513,17 @@ def test_p2p_full_size_properties_cfg3():
     # fp32 torch autograd on the same bf16 rows
     selfcol, selfrow = slcl_ops.self_maps(ia, ib)
     assert torch.equal(selfcol.long(), pick) and torch.equal(selfrow[pick].long(), torch.arange(na, device=dev()))
-    l3, st3, u, lsum = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, True)
-    l4, st4, _, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, False)
+    l3, st3, state = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, True)
+    l4, st4, _ = op.p2p_fwd(a, b, ma, mb, s1, w, t, 5, selfcol, False)
     close(l3, l1, rtol=1e-5)
     close(l4, l1, rtol=1e-5)
     assert torch.equal(st3[:, 2].long(), pos.sum(1))
     assert torch.allclose(st3[:, 0], st1[:, 0], rtol=1e-4) and torch.allclose(st3[:, 1], st1[:, 1], rtol=1e-3, atol=1e-2)
-    assert torch.equal(lsum[:, -1].long(), torch.bincount(lb.long(), minlength=5))
+    assert torch.equal(st3, st4)
     g_out = torch.full((1,), 0.7, device=dev())
     da_g, db_g = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st1, g_out, True, True)
-    da_a, db_a = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow, u, lsum)
-    da_r, db_r = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow)   # U regenerated
+    da_a, db_a = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow, state)
+    da_r, db_r = op.p2p_bwd(a, b, d, ma, mb, s1, w, t, st3, g_out, True, True, 5, selfcol, selfrow)   # state regenerated
     af, bf = a.float().requires_grad_(True), b.float().requires_grad_(True)
     sf = af @ bf.t() / t
     lzf = torch.logsumexp(sf.masked_fill(~notself, float("-inf")), dim=1)
@@ -531,7 +531,7 @@ def test_p2p_full_size_properties_cfg3():
     for got_a, got_b in ((da_g, db_g), (da_a, db_a), (da_r, db_r)):
         grad_close(got_a, af.grad, rtol=P2P_RTOL, floor=0.5)
         grad_close(got_b, bf.grad, rtol=P2P_RTOL, floor=0.5)
-    assert torch.equal(da_a, da_r) and torch.equal(db_a, db_r)             # deterministic, with or without the kept U
+    assert torch.equal(da_a, da_r) and torch.equal(db_a, db_r)             # deterministic, with or without the kept state
 
 
 def test_c_abi_called_directly_with_ctypes():

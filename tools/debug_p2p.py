@@ -36,7 +36,7 @@ def run(A, M, d, T, seed=0, same=False):
     fg = (la != 0).float(); w = fg / fg.sum()
     shift = torch.full((A,), 1.0 / T, device=dev)
     ma = ops.pad_meta(la, ia); mb = ops.pad_meta(lb, ib)
-    loss, stats, _, _ = op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
+    loss, stats, _ = op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
     torch.cuda.synchronize()
     l_ref, da_ref, db_ref = ref(ab[:, :d], bb[:, :d], la, lb, ia, ib, w, T)
     print(f"A={A} M={M} d={d} T={T} same={same}: loss {loss.item():.6f} ref {l_ref.item():.6f} rel {abs(loss.item()-l_ref.item())/abs(l_ref.item()):.2e}", flush=True)

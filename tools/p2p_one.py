@@ -16,7 +16,7 @@ fg = (la != 0).float(); w = fg / fg.sum()
 shift = torch.full((A,), 1.0 / T, device=dev)
 one = torch.ones(1, device=dev)
 for _ in range(3):
-    loss, stats, _, _ = op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
+    loss, stats, _ = op.p2p_fwd(ab, bb, ma, mb, shift, w, T)
     if len(sys.argv) > 4:
         op.p2p_bwd(ab, bb, d, ma, mb, shift, w, T, stats, one, True, True)
 torch.cuda.synchronize()

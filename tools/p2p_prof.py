@@ -25,11 +25,11 @@ tiles = {"fwd only": 64, "fwd+U": 64, "dB": 64}
 for mode in ("fwd only", "fwd+U", "dB"):
     for _ in range(2):
         prof.zero_()
-        loss, stats, u, ls = op.p2p_fwd(ab, bb, ma, mb, shift, w, T, 5, sc, mode != "fwd only")
+        loss, stats, state = op.p2p_fwd(ab, bb, ma, mb, shift, w, T, 5, sc, mode != "fwd only")
         torch.cuda.synchronize()
         if mode == "dB":
             prof.zero_()
-            op.p2p_bwd(ab, bb, d, ma, mb, shift, w, T, stats, one, True, True, 5, sc, sr, u, ls)
+            op.p2p_bwd(ab, bb, d, ma, mb, shift, w, T, stats, one, True, True, 5, sc, sr, state)
             torch.cuda.synchronize()
         vals = prof.cpu().tolist()
     print(mode, f"cycles per tile ({tiles[mode]} tiles per CTA):")
