@@ -190,6 +190,16 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// TMA store of a 3-D box shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -311,7 +321,7 @@ struct __align__(128) ColMeta {
 };
 
 struct __align__(8) Barriers {
-  uint64_t r_full;
+  uint64_t r_in, r_full;
   uint64_t c_full[kStages], c_empty[kStages];
   uint64_t s_full[2], s_empty[2];
   uint64_t g_full[2];
@@ -322,9 +332,14 @@ struct __align__(8) Barriers {
 
 // dynamic smem carve-up (1024-byte aligned tiles); R and G live in tensor memory
 //   Cm  : [kStages][d/64][64 rows][128 B]
+//   after the sweep the ring doubles as the drain's staging area: 8 warps x 2 x 4 KB + the fused class-sum table
+constexpr size_t kDrainBytes = 8 * 2 * 4096 + (size_t)kMaxLabelClasses * kMaxD * sizeof(float);
+__host__ __device__ inline size_t ring_bytes_for(int d) {
+  const size_t ring = (size_t)kStages * (d / KCH) * BN * 128;
+  return ring > kDrainBytes ? ring : kDrainBytes;
+}
 __host__ __device__ inline size_t smem_bytes_for(int d) {
-  const size_t kc = d / KCH;
-  return 1024 /*align slack*/ + (size_t)kStages * kc * BN * 128 + kMetaSlots * sizeof(ColMeta) + sizeof(Barriers) + 64;
+  return 1024 /*align slack*/ + ring_bytes_for(d) + kMetaSlots * sizeof(ColMeta) + sizeof(Barriers) + 64;
 }
 
 // CS = thread-block-cluster size along the row-tile axis.  The CS CTAs of a cluster sweep the same
@@ -332,13 +347,14 @@ __host__ __device__ inline size_t smem_bytes_for(int d) {
 // so the L2 -> SM traffic of the streamed operand drops CS-fold.
 template <int CS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
+p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_cols,
+           const __grid_constant__ CUtensorMap map_out, const P2PArgs a) {
   using MT = ModeTraits<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const int kc = a.d / KCH;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sC = base;
-  ColMeta* sMeta = reinterpret_cast<ColMeta*>(sC + (size_t)kStages * kc * BN * 128);
+  ColMeta* sMeta = reinterpret_cast<ColMeta*>(sC + ring_bytes_for(a.d));
   Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
 
   const long long t_entry = SLCL_PROF_NOW();
@@ -356,8 +372,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
   auto tile_col = [&](int t) { int tt = t + rot; if (tt >= n_tiles) tt -= n_tiles; return col0 + tt * BN; };
 
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_rows);
     tma_prefetch_desc(&map_cols);
-    mbar_init(&bars->r_full, 4);                 // the four warps that fill R's lane quarters
+    mbar_init(&bars->r_in, 1);                   // R tile landed in its staging stages (TMA)
+    mbar_init(&bars->r_full, 4);                 // the four warps that move R's lane quarters into tensor memory
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->c_full[s], 1); mbar_init(&bars->c_empty[s], CS); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
@@ -374,8 +392,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
   if (CS > 1) cluster_sync_all();          // every CTA's barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  const long long t_setup = SLCL_PROF_NOW();
   pdl_trigger();
   pdl_wait();                              // nothing above reads or writes global memory
+  const long long t_pdl = SLCL_PROF_NOW();
 
   // Producer and MMA roles run with the WHOLE warp in the loop (converged, warp-uniform control flow) and
   // elect one lane only around the asynchronous instructions.  Running them under `if (lane == 0)` makes
@@ -384,10 +404,20 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
     // ===================== TMA producer =====================
     unsigned long long w0 = 0, w1 = 0;
     const long long tstart = SLCL_PROF_NOW();
+    // The resident operand R comes in first, staged in the last two ring stages (128 rows = two 64-row stages);
+    // the ring starts with the other stages and takes these two over once R sits in tensor memory.
+    if (elect_one()) {
+      mbar_expect_tx(&bars->r_in, (uint32_t)kc * BM * 128);
+      uint8_t* rdst = sC + (size_t)(kStages - 2) * kc * BN * 128;
+      for (int c = 0; c < kc; ++c) tma_load_2d(rdst + (size_t)c * BM * 128, &map_rows, &bars->r_in, c * KCH, row0);
+    }
+    __syncwarp();
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kStages;
       const int ms = t % kMetaSlots;
-      mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ 1, w0);
+      // the two staging stages start "full" (of R): their first hand-over is a real phase, signalled by the MMA
+      // warp of every CTA of the cluster once R sits in tensor memory, so their parity runs one phase behind
+      mbar_wait_t(&bars->c_empty[s], ((t / kStages) & 1) ^ (s >= kStages - 2 ? 0 : 1), w0);
       if (MT::kColRing) mbar_wait_t(&bars->m_empty[ms], ((t / kMetaSlots) & 1) ^ 1, w1);
       if (elect_one()) {
         mbar_expect_tx(&bars->c_full[s], (uint32_t)kc * BN * 128);
@@ -424,6 +454,12 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
     const long long tstart = SLCL_PROF_NOW();
     mbar_wait(&bars->r_full, 0);
     tc_fence_after();
+    if (elect_one()) {                       // R has left its staging stages: release them to the ring (in every CTA)
+      for (int s = kStages - 2; s < kStages; ++s) {
+        if (CS == 1) umma_commit(&bars->c_empty[s]); else umma_commit_mc(&bars->c_empty[s], kAllCtas);
+      }
+    }
+    __syncwarp();
     // Descriptors are built once; inside the loops only the 14-bit start-address field moves
     // (all operand addresses are < 256 KB, so adding (bytes >> 4) to the low word never carries out).
     const uint64_t descC = make_desc(c_addr, 16, 1024);              // K-major view of a column tile (MMA1)
@@ -494,16 +530,18 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
     unsigned long long w0 = 0, w1 = 0;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     if (half == 0) {
-      // resident operand: this thread's row (bf16 pairs, 32-bit words) -> tensor memory lane r_local
-      const uint4* src = reinterpret_cast<const uint4*>(a.rows_u32 + (size_t)row * (a.d / 2));
-      for (int c = 0; c < a.d / 2; c += 32) {
+      // resident operand: this thread's row of the staged tile (128-byte-swizzled rows of 64 bf16) -> tensor memory
+      // lane r_local as packed bf16 pairs.  Rows past n_rows were zero-filled by TMA.
+      mbar_wait(&bars->r_in, 0);
+      const uint8_t* rsrc = sC + (size_t)(kStages - 2) * kc * BN * 128 + (size_t)r_local * 128;
+      for (int c = 0; c < kc; ++c) {
         uint32_t v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint4 t = row_ok ? __ldg(src + (c >> 2) + i) : make_uint4(0u, 0u, 0u, 0u);
+          const uint4 t = *reinterpret_cast<const uint4*>(rsrc + (size_t)c * BM * 128 + ((i ^ (r_local & 7)) << 4));
           v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
-        tmem_st32(tmem + lane_addr + kColR + c, v);
+        tmem_st32(tmem + lane_addr + kColR + c * 32, v);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -627,7 +665,11 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
     if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 11)) {
       unsigned long long* pp = a.prof + (warp == 4 ? 8 : 12);
       pp[0] = (unsigned long long)(SLCL_PROF_NOW() - tstart); pp[1] = w0; pp[2] = w1;
-      if (warp == 4) a.prof[3] = (unsigned long long)(tstart - t_entry);          // set-up + R load
+      if (warp == 4) {
+        a.prof[3] = (unsigned long long)(tstart - t_entry);          // set-up + R load
+        a.prof[9] = (unsigned long long)(t_setup - t_entry);         // barrier init, TMEM allocation
+        a.prof[10] = (unsigned long long)(t_pdl - t_setup);          // waiting for the kernel in front
+      }
     }
     const long long t_drain = SLCL_PROF_NOW();
     if (MT::kRowSums) {
@@ -643,23 +685,27 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
       // now), so every store instruction writes one full 128-byte line of one row.
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
-      float* stg = reinterpret_cast<float*>(sC) + (size_t)(warp - 4) * (32 * 33);
+      if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp == 4)
+        a.prof[13] = (unsigned long long)(SLCL_PROF_NOW() - t_drain);             // waiting for the last MMA2
+      // Each warp stages a 32-row x 32-column fp32 block (thread = row, 128 bytes, 16-byte chunks XOR-swizzled so
+      // the 128-bit stores are conflict-free) in the idle operand ring and hands it to a TMA store; two staging
+      // buffers per warp keep one store in flight while the next block is read out of tensor memory.
+      uint8_t* stg = sC + (size_t)(warp - 4) * (2 * 4096);
       const bool fused = MODE == kAnaCols && a.fused_out != nullptr;
-      float* out = fused ? a.fused_out : a.grad_partial + (size_t)split * a.n_rows * a.d;
-      const int ld = fused ? a.ld_out : a.d;
       float gscale = 1.f;
       int lab = -1;
-      const float* tab = reinterpret_cast<const float*>(sC) + 8 * (32 * 33);      // fused: ABsum [K][d] in shared memory
+      const float* tab = reinterpret_cast<const float*>(sC + 8 * (2 * 4096));      // fused: ABsum [K][d] in shared memory
       if (fused) {
         gscale = a.grad_out[0];
         if (row_ok) lab = a.row_meta[row].x;
         if (lab >= a.n_class) lab = -1;
-        float* tabw = reinterpret_cast<float*>(sC) + 8 * (32 * 33);
+        float* tabw = reinterpret_cast<float*>(sC + 8 * (2 * 4096));
         for (int idx = threadIdx.x - 128; idx < a.n_class * a.d; idx += 32 * kEpiWarps)
           tabw[idx] = a.ab_sums[(size_t)(idx / a.d) * (a.d + 1) + idx % a.d];
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");         // the eight epilogue warps only
       }
-      for (int c = half * 32; c < a.d; c += 64) {
+      int nbuf = 0;
+      for (int c = half * 32; c < a.d; c += 64, nbuf ^= 1) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + kColAcc + c, v);
         tmem_ld_wait();
@@ -676,17 +722,21 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_cols, const P2PArgs a) {
             v[4 * i + 3] = __float_as_uint(gscale * fmaf(-m, t.w, __uint_as_float(v[4 * i + 3])));
           }
         }
+        if (lane == 0) bulk_wait_read<1>();            // the store that last read this staging buffer is done with it
+        __syncwarp();
+        uint8_t* dst = stg + nbuf * 4096 + lane * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(dst + ((i ^ (lane & 7)) << 4)) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async();
         __syncwarp();
-        const bool col_ok = c + lane < ld;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          const int grow = row0 + q * 32 + rr;
-          if (grow < a.n_rows && col_ok) out[(size_t)grow * ld + c + lane] = stg[rr * 33 + lane];
+        if (lane == 0) {
+          tma_store_3d(&map_out, stg + nbuf * 4096, c, row0 + q * 32, fused ? 0 : split);
+          bulk_commit();
         }
-        __syncwarp();
       }
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
       tc_fence_before();
     }
     if (kProfile && a.prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp == 4) {
@@ -1210,8 +1260,28 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
   return s;
 }
 
+// fp32 output of the MMA2 drain as a 3-D tensor [splits][rows][ld]: box = 32 columns (128 B) x 32 rows, 128-byte swizzle;
+// rows past n_rows and columns past n_cols are clipped by the TMA unit
+int make_out_map(CUtensorMap* m, const float* ptr, int64_t n_cols, int64_t ld, int64_t rows, int64_t splits) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return SLCL_ERR_CUDA;
+  cuuint64_t dims[3] = {(cuuint64_t)n_cols, (cuuint64_t)rows, (cuuint64_t)splits};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rows * ld * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(out)");
+    return SLCL_ERR_CUDA;
+  }
+  return SLCL_OK;
+}
+
 template <int CS, int MODE>
-int launch_one(const CUtensorMap& mc, const P2PArgs& a, const Sweep& sw, size_t smem, cudaStream_t stream) {
+int launch_one(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const P2PArgs& a, const Sweep& sw, size_t smem,
+               cudaStream_t stream) {
   static bool attr_set = false;          // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(p2p_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(kMaxD));
@@ -1232,7 +1302,7 @@ int launch_one(const CUtensorMap& mc, const P2PArgs& a, const Sweep& sw, size_t 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, p2p_kernel<CS, MODE>, mc, a);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, p2p_kernel<CS, MODE>, mr, mc, mo, a);
   if (le != cudaSuccess) { set_cuda_error(le, "cudaLaunchKernelEx(p2p_kernel)"); return SLCL_ERR_CUDA; }
   return check_launch("p2p_kernel");
 }
@@ -1240,9 +1310,18 @@ int launch_one(const CUtensorMap& mc, const P2PArgs& a, const Sweep& sw, size_t 
 template <int MODE>
 int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_cols, int d, float inv_t, P2PArgs a,
                  const Sweep& sw, cudaStream_t stream) {
-  CUtensorMap mc;
-  int st = make_map(&mc, cols, n_cols, d, BN / sw.cluster);
+  CUtensorMap mr, mc, mo;
+  int st = make_map(&mr, rows, n_rows, d, BM);
   if (st != SLCL_OK) return st;
+  st = make_map(&mc, cols, n_cols, d, BN / sw.cluster);
+  if (st != SLCL_OK) return st;
+  if (ModeTraits<MODE>::kMma2) {
+    st = a.fused_out ? make_out_map(&mo, a.fused_out, a.ld_out, a.ld_out, n_rows, 1)
+                     : make_out_map(&mo, a.grad_partial, d, d, n_rows, sw.splits);
+    if (st != SLCL_OK) return st;
+  } else {
+    mo = mc;          // unused
+  }
   a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
   a.cols_per_split = sw.cols_per_split;
   a.scale_log2 = inv_t * kLog2e;
@@ -1251,9 +1330,9 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
   const size_t smem = smem_bytes_for(d);
-  if (sw.cluster == 4) return launch_one<4, MODE>(mc, a, sw, smem, stream);
-  if (sw.cluster == 2) return launch_one<2, MODE>(mc, a, sw, smem, stream);
-  return launch_one<1, MODE>(mc, a, sw, smem, stream);
+  if (sw.cluster == 4) return launch_one<4, MODE>(mr, mc, mo, a, sw, smem, stream);
+  if (sw.cluster == 2) return launch_one<2, MODE>(mr, mc, mo, a, sw, smem, stream);
+  return launch_one<1, MODE>(mr, mc, mo, a, sw, smem, stream);
 }
 
 // State the analytic forward leaves for the backward (slcl_p2p_state_bytes): one caller-owned buffer.
@@ -1509,7 +1588,8 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
       P2PArgs args{};
       args.col_shift = st_.colshift;
       args.grad_partial = w.grad_partial_b;
-      if (sw.splits == 1) {        // one CTA sees all anchors of its rows: the drain writes d_b itself
+      if (sw.splits == 1 && dim % 4 == 0) {        // one CTA sees all anchors of its rows: the drain writes d_b itself
+                                                  // (TMA store: the row pitch must be a multiple of 16 bytes)
         fused_db = 1;
         args.fused_out = d_b; args.ld_out = (int)dim; args.n_class = n_class; args.ab_sums = st_.absum; args.grad_out = grad_out;
         args.row_meta = bm;

@@ -20,7 +20,7 @@ ma, mb = ops.pad_meta(la, ia), ops.pad_meta(lb, ib)
 sc, sr = ops.self_maps(ia, ib)
 w = torch.full((A,), 1.0 / A, device=dev); shift = torch.full((A,), 1.0 / T, device=dev); one = torch.ones(1, device=dev)
 names = ["prod total", "prod wait c_empty", "prod wait m_empty", "SETUP+R (abs)", "mma total", "mma wait c_full", "mma wait s_empty", "mma wait g_full",
-         "epi4 total", "epi4 wait m_full", "epi4 wait s_full", "DRAIN (abs)", "epi11 total", "epi11 wait m_full", "epi11 wait s_full", "CTA TOTAL (abs)"]
+         "epi4 total", "  of SETUP: init+alloc (abs)", "  of SETUP: pdl wait (abs)", "DRAIN (abs)", "epi11 total", "  of DRAIN: acc_full wait (abs)", "epi11 wait s_full", "CTA TOTAL (abs)"]
 tiles = {"fwd only": 64, "fwd+U": 64, "dB": 64}
 for mode in ("fwd only", "fwd+U", "dB"):
     for _ in range(2):
