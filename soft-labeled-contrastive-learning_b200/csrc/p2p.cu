@@ -332,14 +332,15 @@ struct __align__(8) Barriers {
 
 // dynamic smem carve-up (1024-byte aligned tiles); R and G live in tensor memory
 //   Cm  : [kStages][d/64][64 rows][128 B]
-//   after the sweep the ring doubles as the drain's staging area: 8 warps x 2 x 4 KB + the fused class-sum table
-constexpr size_t kDrainBytes = 8 * 2 * 4096 + (size_t)kMaxLabelClasses * kMaxD * sizeof(float);
+//   after the sweep the ring doubles as the drain's staging area: 8 warps x 2 x 4 KB
+constexpr size_t kDrainBytes = 8 * 2 * 4096;
+constexpr size_t kTableBytes = (size_t)kMaxLabelClasses * kMaxD * sizeof(float);      // fused dB drain: ABsum [K][d]
 __host__ __device__ inline size_t ring_bytes_for(int d) {
   const size_t ring = (size_t)kStages * (d / KCH) * BN * 128;
   return ring > kDrainBytes ? ring : kDrainBytes;
 }
 __host__ __device__ inline size_t smem_bytes_for(int d) {
-  return 1024 /*align slack*/ + ring_bytes_for(d) + kMetaSlots * sizeof(ColMeta) + sizeof(Barriers) + 64;
+  return 1024 /*align slack*/ + ring_bytes_for(d) + kMetaSlots * sizeof(ColMeta) + kTableBytes + sizeof(Barriers) + 64;
 }
 
 // CS = thread-block-cluster size along the row-tile axis.  The CS CTAs of a cluster sweep the same
@@ -355,7 +356,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sC = base;
   ColMeta* sMeta = reinterpret_cast<ColMeta*>(sC + ring_bytes_for(a.d));
-  Barriers* bars = reinterpret_cast<Barriers*>(sMeta + kMetaSlots);
+  float* sTab = reinterpret_cast<float*>(sMeta + kMetaSlots);
+  Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(sTab) + kTableBytes);
 
   const long long t_entry = SLCL_PROF_NOW();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -529,6 +531,18 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     float praw = 0.f, npos = 0.f;
     unsigned long long w0 = 0, w1 = 0;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+    // fused dB drain (kAnaCols, one split): fetch what the drain needs now, long before it is used
+    const bool fused = MODE == kAnaCols && a.fused_out != nullptr;
+    float gscale = 1.f;
+    int lab = -1;
+    if (fused) {
+      gscale = a.grad_out[0];
+      if (row_ok) lab = a.row_meta[row].x;
+      if (lab >= a.n_class) lab = -1;
+      for (int idx = threadIdx.x - 128; idx < a.n_class * a.d; idx += 32 * kEpiWarps)
+        sTab[idx] = a.ab_sums[(size_t)(idx / a.d) * (a.d + 1) + idx % a.d];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");         // the eight epilogue warps only
+    }
     if (half == 0) {
       // resident operand: this thread's row of the staged tile (128-byte-swizzled rows of 64 bf16) -> tensor memory
       // lane r_local as packed bf16 pairs.  Rows past n_rows were zero-filled by TMA.
@@ -691,19 +705,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       // the 128-bit stores are conflict-free) in the idle operand ring and hands it to a TMA store; two staging
       // buffers per warp keep one store in flight while the next block is read out of tensor memory.
       uint8_t* stg = sC + (size_t)(warp - 4) * (2 * 4096);
-      const bool fused = MODE == kAnaCols && a.fused_out != nullptr;
-      float gscale = 1.f;
-      int lab = -1;
-      const float* tab = reinterpret_cast<const float*>(sC + 8 * (2 * 4096));      // fused: ABsum [K][d] in shared memory
-      if (fused) {
-        gscale = a.grad_out[0];
-        if (row_ok) lab = a.row_meta[row].x;
-        if (lab >= a.n_class) lab = -1;
-        float* tabw = reinterpret_cast<float*>(sC + 8 * (2 * 4096));
-        for (int idx = threadIdx.x - 128; idx < a.n_class * a.d; idx += 32 * kEpiWarps)
-          tabw[idx] = a.ab_sums[(size_t)(idx / a.d) * (a.d + 1) + idx % a.d];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");         // the eight epilogue warps only
-      }
+      const float* tab = sTab;
       int nbuf = 0;
       for (int c = half * 32; c < a.d; c += 64, nbuf ^= 1) {
         uint32_t v[32];
