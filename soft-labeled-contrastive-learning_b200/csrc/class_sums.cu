@@ -18,7 +18,10 @@
 // order (deterministic; exact integer counts beyond 2^24).
 #include "common.cuh"
 
+#include <cuda.h>
+#include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace slcl {
 namespace {
@@ -292,6 +295,249 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
   }
 }
 
+// ---------------------------------------------------------------------------
+// v3: TMA-fed, warp-specialised class sums (the default for contiguous-pixel maps with HW % 4 == 0).
+//
+// The v2 kernel above issues its loads from the warps that also do the arithmetic, 16 warps per SM at
+// 128 registers: with wide weight rows (soft labels x partitions) it is latency-bound at ~45 % of the HBM
+// roofline.  Here the three jobs are separate roles of one persistent CTA per SM:
+//   warp 0       TMA producer: one cp.async.bulk.tensor.3d box [128 pixels x CB channels] per stage into a
+//                5-stage ring (up to 160 KB in flight per SM, completion on mbarriers)
+//   warps 1-8    weight builders: labels / soft probabilities / partition ids of the stage's 128 pixels ->
+//                sW[stage][column][pixel]; two warps per stage, four teams round-robin over the stages, and each
+//                warp fetches the raw inputs of its NEXT stage before it waits for that stage's slot, so its
+//                global-load latency is covered by four stage periods; they also own the weight-sum column
+//   warps 9-24   consumers: warp w owns CPW channels; lane l owns pixels 4l..4l+3 of the stage; x and the weights
+//                come back from shared memory with conflict-free 128-bit loads; acc[CPW][KWT] in registers for
+//                the whole sweep; every channel has exactly one owner, so the block result needs no combine
+// Partials and the fp64 second stage are those of v2.
+// ---------------------------------------------------------------------------
+constexpr int kV3ConsumerWarps = 16;
+constexpr int kV3WeightWarps = 8;       // two per stage (64 pixels each), four stage teams round-robin
+constexpr int kV3Threads = 32 * (1 + kV3WeightWarps + kV3ConsumerWarps);
+constexpr int kV3Px = 128;
+constexpr int kV3Stages = 5;
+
+__device__ __forceinline__ uint32_t v3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void v3_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(v3_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void v3_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v3_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void v3_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(v3_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void v3_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "V3_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra V3_WAIT_DONE;\n\t"
+      "bra V3_WAIT_LOOP;\n\t"
+      "V3_WAIT_DONE:\n\t"
+      "}\n" ::"r"(v3_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void v3_tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          v3_smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(v3_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct __align__(8) V3Bars { uint64_t x_full[kV3Stages], w_full[kV3Stages], empty[kV3Stages]; };
+
+template <int KWT, int CPW>
+__global__ void __launch_bounds__(kV3Threads, 1)
+class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs a) {
+  constexpr int CB = kV3ConsumerWarps * CPW;                   // channels per block
+  constexpr int kStageBytes = CB * kV3Px * 4;
+  extern __shared__ __align__(128) uint8_t v3_smem[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v3_smem) + 127) & ~(uintptr_t)127);
+  float* sX = reinterpret_cast<float*>(base);                                   // [stages][CB][128]
+  float* sWt = reinterpret_cast<float*>(base + (size_t)kV3Stages * kStageBytes); // [stages][KWT][128]
+  V3Bars* bars = reinterpret_cast<V3Bars*>(sWt + (size_t)kV3Stages * KWT * kV3Px);
+  __shared__ float s_w[kV3WeightWarps][KWT];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = (int)a.channels;
+  const int c_base = blockIdx.y * CB;
+  const int64_t tiles_per_image = (a.pixels + kV3Px - 1) / kV3Px;
+  const int64_t n_tiles = a.batch * tiles_per_image;
+  const int64_t n_iter = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_feat)) : "memory");
+    for (int s = 0; s < kV3Stages; ++s) {
+      v3_mbar_init(&bars->x_full[s], 1);
+      v3_mbar_init(&bars->w_full[s], 2);
+      v3_mbar_init(&bars->empty[s], kV3ConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int s = (int)(it % kV3Stages);
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t b = tile / tiles_per_image;
+      const int p0 = (int)((tile - b * tiles_per_image) * kV3Px);
+      v3_mbar_wait(&bars->empty[s], (uint32_t)(((it / kV3Stages) & 1) ^ 1));
+      if (lane == 0) {
+        v3_mbar_expect_tx(&bars->x_full[s], kStageBytes);
+        v3_tma_load_3d(sX + (size_t)s * CB * kV3Px, &map_feat, &bars->x_full[s], p0, c_base, (int)b);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= kV3WeightWarps) {
+    // ===================== weight builders =====================
+    const int wv = warp - 1;
+    const int team = wv >> 1, hf = wv & 1;             // team -> stages team, team+4, ...; half of the 128 pixels
+    const bool count_weights = blockIdx.y == 0;
+    constexpr int kTeams = kV3WeightWarps / 2;
+    constexpr int kPl = 2;                              // pixels per lane: 64 pixels per warp
+    float wacc[KWT];
+#pragma unroll
+    for (int q = 0; q < KWT; ++q) wacc[q] = 0.f;
+    // raw inputs of kPl pixels (whatever the mode needs), fetched one stage ahead
+    float r_f[kPl][KWT > SLCL_MAX_CLASSES ? KWT : SLCL_MAX_CLASSES];
+    int r_part[kPl];
+    long long r_lab[kPl];
+    auto fetch = [&](int64_t it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t b = tile / tiles_per_image;
+      const int64_t p0 = (tile - b * tiles_per_image) * kV3Px + hf * 64;
+#pragma unroll
+      for (int i = 0; i < kPl; ++i) {
+        const int64_t p = p0 + lane + 32 * i;
+        const bool ok = p < a.pixels;
+        const int64_t pix = b * a.pixels + p;
+        r_part[i] = (ok && a.part_id) ? a.part_id[pix] : 0;
+        r_lab[i] = -1;
+        if (a.mode == kPlanar) {
+          const int64_t n = a.batch * a.pixels;
+#pragma unroll
+          for (int j = 0; j < KWT; ++j) r_f[i][j] = (ok && j < a.n_cols) ? a.planar[(int64_t)j * n + pix] : 0.f;
+        } else if (a.mode == kHard) {
+          if (ok) r_lab[i] = a.labels[pix];
+        } else {
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+            r_f[i][k] = (ok && k < a.n_class) ? a.probs[(b * a.n_class + k) * a.pixels + p] : 0.f;
+          if (!ok) r_part[i] = -1;                      // pixels past the image: all-zero weight row
+        }
+      }
+    };
+    if (team < n_iter) fetch(team);
+    for (int64_t it = team; it < n_iter; it += kTeams) {
+      const int s = (int)(it % kV3Stages);
+      v3_mbar_wait(&bars->empty[s], (uint32_t)(((it / kV3Stages) & 1) ^ 1));
+      float* dst = sWt + (size_t)s * KWT * kV3Px + hf * 64;
+#pragma unroll
+      for (int i = 0; i < kPl; ++i) {
+        float w[KWT];
+#pragma unroll
+        for (int q = 0; q < KWT; ++q) w[q] = 0.f;
+        if (a.mode == kPlanar) {
+#pragma unroll
+          for (int q = 0; q < KWT; ++q) w[q] = r_f[i][q];
+        } else if (a.mode == kHard) {
+          // utils_.py:581 / :535
+          const bool ok = r_lab[i] >= 0 && r_lab[i] < a.n_class && r_part[i] >= 0 && r_part[i] < a.n_part;
+          const int col = ok ? r_part[i] * a.n_class + (int)r_lab[i] : -1;
+#pragma unroll
+          for (int q = 0; q < KWT; ++q) w[q] = (q == col) ? 1.0f : 0.0f;
+        } else {
+          // soft probabilities: :517-519 (weighted) or :524-525 (arg-max one-hot); certainty :511-514
+          float best = -INFINITY;
+          int arg = 0;
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+            if (k < a.n_class && r_f[i][k] > best) { best = r_f[i][k]; arg = k; }
+          const float cert = (a.threshold > 0.f && a.threshold < 1.f) ? ((best >= a.threshold) ? 1.f : 0.f) : 1.f;
+          const bool ok = r_part[i] >= 0 && r_part[i] < a.n_part;
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+            if (k < a.n_class) {
+              const float wk = a.weighted ? r_f[i][k] * cert : ((k == arg) ? cert : 0.f);
+              const int col = r_part[i] * a.n_class + k;
+#pragma unroll
+              for (int q = 0; q < KWT; ++q) if (ok && q == col) w[q] = wk;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < KWT; ++q) {
+          dst[q * kV3Px + lane + 32 * i] = w[q];
+          if (count_weights) wacc[q] += w[q];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
+      if (it + kTeams < n_iter) fetch(it + kTeams);     // in flight while this warp waits for its next slot
+    }
+#pragma unroll
+    for (int q = 0; q < KWT; ++q) {
+      const float r = warp_sum(wacc[q]);
+      if (lane == 0) s_w[wv][q] = r;
+    }
+  } else {
+    // ===================== consumers =====================
+    const int cw = warp - 1 - kV3WeightWarps;
+    float acc[CPW][KWT];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j)
+#pragma unroll
+      for (int q = 0; q < KWT; ++q) acc[j][q] = 0.f;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int s = (int)(it % kV3Stages);
+      const uint32_t par = (uint32_t)((it / kV3Stages) & 1);
+      v3_mbar_wait(&bars->x_full[s], par);
+      v3_mbar_wait(&bars->w_full[s], par);
+      const float4* xs = reinterpret_cast<const float4*>(sX + ((size_t)s * CB + cw * CPW) * kV3Px) + lane;
+      const float4* ws = reinterpret_cast<const float4*>(sWt + (size_t)s * KWT * kV3Px) + lane;
+      float4 x[CPW];
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) x[j] = xs[j * (kV3Px / 4)];
+#pragma unroll
+      for (int q = 0; q < KWT; ++q) {
+        const float4 w = ws[q * (kV3Px / 4)];
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          acc[j][q] = fmaf(w.x, x[j].x, acc[j][q]);
+          acc[j][q] = fmaf(w.y, x[j].y, acc[j][q]);
+          acc[j][q] = fmaf(w.z, x[j].z, acc[j][q]);
+          acc[j][q] = fmaf(w.w, x[j].w, acc[j][q]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) v3_mbar_arrive(&bars->empty[s]);
+    }
+    float* out = a.partial + (int64_t)blockIdx.x * KWT * (C + 1);
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) {
+      const int c = c_base + cw * CPW + j;
+#pragma unroll
+      for (int q = 0; q < KWT; ++q) {
+        const float r = warp_sum(acc[j][q]);
+        if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
+      }
+    }
+  }
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x < KWT) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kV3WeightWarps; ++w) t += s_w[w][threadIdx.x];
+    a.partial[(int64_t)blockIdx.x * KWT * (C + 1) + (int64_t)threadIdx.x * (C + 1) + C] = t;
+  }
+}
+
 // sums[col][c] = sum over blocks in fp64.  One warp per output element: lane l adds blocks l, l+32, ...
 // then a fixed-shape shuffle tree, so the result is deterministic and the serial chain is n_blocks/32 long.
 __global__ void __launch_bounds__(kThreads) class_sums_reduce_kernel(const float* partial, int n_blocks, int kwt,
@@ -517,11 +763,112 @@ void launch_sums(const SumArgs& a, const SumPlan& p, cudaStream_t stream) {
   }
 }
 
+// ---- v3 host side ----
+typedef CUresult (*V3EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+V3EncodeFn v3_encode_fn() {
+  static V3EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<V3EncodeFn>(p);
+  }
+  return fn;
+}
+
+struct V3Plan { bool ok; int kwt, cpw; dim3 grid; };
+
+V3Plan plan_v3(const SumArgs& a, bool vec4) {
+  V3Plan p{};
+  p.ok = false;
+  { const char* e = getenv("SLCL_CLASS_SUMS_V2"); if (e && atoi(e) != 0) return p; }
+  if (!vec4 || a.sp != 1 || a.sc % 4 != 0 || a.sb % 4 != 0 || a.pixels > INT_MAX || a.batch > INT_MAX) return p;
+  p.kwt = pick_kwt(a.n_cols);
+  if (p.kwt < 0) return p;
+  const int C = (int)a.channels;
+  p.cpw = C <= 16 ? 1 : (C <= 32 ? 2 : 4);
+  if (p.kwt > 10 && p.cpw > 2) p.cpw = 2;           // 96 registers per thread: keep acc[CPW][KWT] <= 40
+  const int cb = kV3ConsumerWarps * p.cpw;
+  const int gy = ceil_div(C, cb);
+  const int64_t n_tiles = a.batch * ceil_div<int64_t>(a.pixels, kV3Px);
+  int64_t gx = sm_count() / gy;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  if (gx > (int64_t)sm_count() * 2) gx = (int64_t)sm_count() * 2;      // partial buffer is sized for 2 blocks per SM
+  p.grid = dim3((unsigned)gx, (unsigned)gy, 1);
+  p.ok = true;
+  return p;
+}
+
+size_t v3_smem_bytes(int kwt, int cpw) {
+  return 128 + (size_t)kV3Stages * (kV3ConsumerWarps * cpw * kV3Px * 4 + kwt * kV3Px * 4) + sizeof(V3Bars) + 64;
+}
+
+template <int KWT, int CPW>
+int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
+  V3EncodeFn fn = v3_encode_fn();
+  if (!fn) return SLCL_ERR_CUDA;
+  CUtensorMap map;
+  cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.channels, (cuuint64_t)a.batch};
+  cuuint64_t strides[2] = {(cuuint64_t)a.sc * 4, (cuuint64_t)a.sb * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)(kV3ConsumerWarps * CPW), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.feat), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(class sums)"); return SLCL_ERR_CUDA; }
+  const size_t smem = v3_smem_bytes(KWT, CPW);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(class_sums_v3_kernel)"); return SLCL_ERR_CUDA; }
+    attr_set = true;
+  }
+  class_sums_v3_kernel<KWT, CPW><<<p.grid, kV3Threads, smem, stream>>>(map, a);
+  return SLCL_OK;
+}
+
+template <int KWT>
+int launch_v3_cpw(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
+  switch (p.cpw) {
+    case 1: return launch_v3<KWT, 1>(a, p, stream);
+    case 2: return launch_v3<KWT, 2>(a, p, stream);
+    default:
+      if constexpr (KWT <= 10) return launch_v3<KWT, 4>(a, p, stream);
+      else return launch_v3<KWT, 2>(a, p, stream);
+  }
+}
+
 int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (a.n_cols < 1 || a.n_cols > SLCL_MAX_WEIGHT_COLS) return SLCL_ERR_INVALID_ARGUMENT;
   SumPlan p = plan_sums(a.batch, a.channels, a.pixels, a.n_cols, vec4);
   if (p.kwt < 0) return SLCL_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < partial_bytes(p, a.channels) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  const V3Plan v3 = plan_v3(a, vec4);
+  if (v3.ok && (size_t)v3.grid.x * v3.kwt * (a.channels + 1) * sizeof(float) <= workspace_bytes) {
+    a.partial = reinterpret_cast<float*>(workspace);
+    int st;
+    switch (v3.kwt) {
+      case 2: st = launch_v3_cpw<2>(a, v3, stream); break;
+      case 3: st = launch_v3_cpw<3>(a, v3, stream); break;
+      case 4: st = launch_v3_cpw<4>(a, v3, stream); break;
+      case 5: st = launch_v3_cpw<5>(a, v3, stream); break;
+      case 6: st = launch_v3_cpw<6>(a, v3, stream); break;
+      case 8: st = launch_v3_cpw<8>(a, v3, stream); break;
+      case 10: st = launch_v3_cpw<10>(a, v3, stream); break;
+      case 12: st = launch_v3_cpw<12>(a, v3, stream); break;
+      case 16: st = launch_v3_cpw<16>(a, v3, stream); break;
+      default: return SLCL_ERR_INVALID_ARGUMENT;
+    }
+    if (st != SLCL_OK) return st;
+    const int total = a.n_cols * ((int)a.channels + 1);
+    class_sums_reduce_kernel<<<ceil_div(total, kWarps), kThreads, 0, stream>>>(a.partial, (int)v3.grid.x, v3.kwt, a.n_cols,
+                                                                                (int)a.channels, sums);
+    return check_launch("slcl_class_sums");
+  }
   a.tiles_per_image = p.tiles_per_image; a.n_tiles = p.n_tiles;
   a.cg_per_block = p.cg_per_block; a.pt_per_block = p.pt_per_block;
   a.partial = reinterpret_cast<float*>(workspace);
