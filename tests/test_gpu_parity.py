@@ -211,6 +211,51 @@ def test_class_counts_bit_exact():
     close(sums[:, :-1], ref_sums, rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("b,c,h,w,k,parts,mode", [
+    (3, 128, 24, 20, 5, 1, "hard"),        # two channel blocks (C = 128 > 64), pixel tail (480 = 3*128 + 96)
+    (2, 32, 16, 16, 4, 2, "soft"),         # cfg5-like: CPW = 2, partitions
+    (5, 12, 8, 12, 3, 1, "hard"),          # C < 16: CPW = 1, channel tail inside the TMA box
+    (2, 72, 12, 12, 8, 2, "soft"),         # 16 weight columns (KWT = 16 -> CPW = 2), C tail in the last channel block
+    (4, 64, 10, 10, 5, 3, "argmax"),       # arg-max one-hot with certainty threshold, 15 columns
+    (1, 40, 33, 33, 5, 1, "hard"),         # HW % 4 != 0: the v2 kernel
+])
+def test_class_sums_kernels_vs_torch(b, c, h, w, k, parts, mode, monkeypatch):
+    """slcl::class_sums against a plain fp64 torch evaluation, through the TMA-fed v3 kernel (default where the
+    shape allows) and through the v2 kernel (SLCL_CLASS_SUMS_V2=1); weight sums of hard labels are exact integers."""
+    gen = cases.g(700 + c + h)
+    feat = torch.randn(b, c, h, w, generator=gen)
+    n = b * h * w
+    part = (torch.randperm(n, generator=gen) % parts).to(torch.int32) if parts > 1 else None
+    pid = part.long() if part is not None else torch.zeros(n, dtype=torch.long)
+    if mode == "hard":
+        labels = torch.randint(-1, k + 1, (n,), generator=gen)           # includes out-of-range labels
+        wts = torch.zeros(n, parts * k, dtype=torch.float64)
+        ok = (labels >= 0) & (labels < k)
+        wts[torch.arange(n)[ok], (pid * k + labels)[ok]] = 1.0
+        args = (labels.to(dev()), None, False, 0.0)
+    else:
+        probs = torch.softmax(3 * torch.randn(b, k, h, w, generator=gen), dim=1)
+        pf = probs.permute(0, 2, 3, 1).reshape(n, k).double()
+        thr = 0.6 if mode == "argmax" else 0.0
+        cert = (pf.max(1).values >= thr).double() if thr > 0 else torch.ones(n, dtype=torch.float64)
+        rows = pf * cert[:, None] if mode == "soft" else torch.nn.functional.one_hot(pf.argmax(1), k).double() * cert[:, None]
+        wts = torch.zeros(n, parts * k, dtype=torch.float64)
+        for pp in range(parts):
+            wts[pid == pp, pp * k:(pp + 1) * k] = rows[pid == pp]
+        args = (None, probs.to(dev()), mode == "soft", thr)
+    x = feat.permute(0, 2, 3, 1).reshape(n, c).double()
+    ref = torch.cat([wts.t() @ x, wts.sum(0)[:, None]], dim=1)
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("SLCL_CLASS_SUMS_V2", v2)
+        got = torch.ops.slcl.class_sums(feat.to(dev()), args[0], args[1], args[2], args[3],
+                                        part.to(dev()) if part is not None else None, parts, k).cpu()
+        close(got[:, :-1], ref[:, :-1], rtol=1e-5, atol=1e-4)
+        if mode == "hard":
+            assert torch.equal(got[:, -1], ref[:, -1])
+        else:
+            close(got[:, -1], ref[:, -1], rtol=1e-5)
+
+
 # ---------------------------------------------------------------------------
 # centroid path
 # ---------------------------------------------------------------------------
