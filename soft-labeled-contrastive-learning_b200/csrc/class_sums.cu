@@ -615,6 +615,7 @@ __global__ void __launch_bounds__(kThreads) centroid_bwd_prep_kernel(const float
 }
 
 template <int KWT> constexpr int kwpad() { return (KWT + 3) / 4 * 4; }
+constexpr int kCenRing = 12;        // channels in flight per thread in the centroid backward (cp.async ring)
 
 template <int KWT, int VEC, bool HAS_DP>
 __global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs a) {
@@ -643,9 +644,24 @@ __global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs
     for (int v = 0; v < VEC; ++v) dot[j][v] = 0.f;
 
   constexpr int U = 4;
+  // With soft labels the kernel also reads x (for d probs).  Those loads go through a per-thread cp.async ring in
+  // shared memory, kCenRing channels deep (each thread copies and later reads only its own 16 bytes, so no barrier is
+  // involved): ~48 KB per block in flight without spending registers on it.
+  constexpr bool kRing = HAS_DP && VEC == 4;
+  float4* ring = reinterpret_cast<float4*>(sG + (size_t)((C * KP + 3) / 4 * 4));
+  auto ring_fetch = [&](int c) {
+    if (c < C) {
+      const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(c % kCenRing) * kThreads + threadIdx.x);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src + (int64_t)c * a.s.sc) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");          // one group per channel, empty past the end
+  };
+  if constexpr (kRing) {
+    for (int c = 0; c < kCenRing; ++c) ring_fetch(c);
+  }
   for (int c = 0; c < C; c += U) {
     float x[U][VEC];
-    if constexpr (HAS_DP) {
+    if constexpr (HAS_DP && !kRing) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c + u < C) ld_vec<VEC>(src + (int64_t)(c + u) * a.s.sc, x[u]);
@@ -654,6 +670,12 @@ __global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (c + u < C) {
+        if constexpr (kRing) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(kCenRing - 1) : "memory");
+          const float4 t = ring[(size_t)((c + u) % kCenRing) * kThreads + threadIdx.x];
+          x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][3] = t.w;
+          ring_fetch(c + u + kCenRing);
+        }
         float gj[KP];
         const float4* row = reinterpret_cast<const float4*>(sG + (size_t)(c + u) * KP);
 #pragma unroll
@@ -1006,7 +1028,8 @@ extern "C" int slcl_centroid_bwd(const float* feat, int64_t batch, int64_t chann
   const int kwt = pick_kwt(a.s.n_cols);
   const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id, dfeat, dprobs});
   const int vec = vec4 ? 4 : 1;
-  const size_t smem = (size_t)channels * ((kwt + 3) / 4 * 4) * sizeof(float);
+  size_t smem = (size_t)channels * ((kwt + 3) / 4 * 4) * sizeof(float);
+  if (dprobs && vec4) smem = align_up(smem, 16) + (size_t)kCenRing * kThreads * 16;      // + the cp.async ring
   if (smem > 200 * 1024) return SLCL_ERR_UNSUPPORTED;
   const int blocks = (int)ceil_div<int64_t>(batch * pixels / vec, kThreads);
   cudaStream_t stream = (cudaStream_t)stream_;
