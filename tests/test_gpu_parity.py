@@ -579,6 +579,48 @@ def test_p2p_full_size_properties_cfg3():
     assert torch.equal(da_a, da_r) and torch.equal(db_a, db_r)             # deterministic, with or without the kept state
 
 
+@pytest.mark.parametrize("na,m,d,k,t", [
+    (9000, 9000, 192, 8, 0.5),      # > 8192 anchors: several anchors per finish warp; d = 192 (three 64-column chunks); K = 8
+    (300, 5000, 64, 3, 0.2),        # one row tile, many column splits; d = 64 (ring smaller than the drain staging)
+    (4100, 130, 128, 5, 1.0),       # row tail (4100 = 32*128 + 4), three column tiles (fewer than ring stages)
+])
+def test_p2p_analytic_equals_general_op_level(na, m, d, k, t):
+    """Analytic sweeps (class sums outside the tensor-core sweep, forward keeps state) against the per-element general
+    sweeps on the same bf16 rows: statistics, loss, dA, dB; anchors are contrast rows (self pairs) where na <= m."""
+    from slcl import ops as slcl_ops
+    op = torch.ops.slcl
+    g = torch.Generator(device=dev()).manual_seed(100 + d)
+    b = (F.normalize(torch.randn(m, d, device=dev(), generator=g), dim=1) * 1.3).to(torch.bfloat16)
+    lb = torch.randint(0, k, (m,), device=dev(), generator=g, dtype=torch.int32)
+    ib = torch.arange(m, device=dev(), dtype=torch.int32)
+    if na <= m:
+        pick = torch.randperm(m, device=dev(), generator=g)[:na]
+        a, la, ia = b[pick].contiguous(), lb[pick].contiguous(), ib[pick].contiguous()
+    else:                                                   # more anchors than contrast rows: the extra ones have no self pair
+        extra = na - m
+        a2 = (F.normalize(torch.randn(extra, d, device=dev(), generator=g), dim=1) * 0.9).to(torch.bfloat16)
+        a = torch.cat([b, a2]).contiguous()
+        la = torch.cat([lb, torch.randint(0, k, (extra,), device=dev(), generator=g, dtype=torch.int32)])
+        ia = torch.cat([ib, torch.arange(m, m + extra, device=dev(), dtype=torch.int32)])
+    w = torch.rand(na, device=dev(), generator=g)
+    w = w / w.sum()
+    ma, mb = slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib)
+    shift = (a.float().norm(dim=1) * b.float().norm(dim=1).max() / t).contiguous()
+    selfcol, selfrow = slcl_ops.self_maps(ia, ib)
+    l_g, st_g, _ = op.p2p_fwd(a, b, ma, mb, shift, w, t)
+    l_a, st_a, state = op.p2p_fwd(a, b, ma, mb, shift, w, t, k, selfcol, True)
+    close(l_a, l_g, rtol=1e-5)
+    assert torch.equal(st_a[:, 2], st_g[:, 2])
+    assert torch.allclose(st_a[:, 0], st_g[:, 0], rtol=2e-4) and torch.allclose(st_a[:, 1], st_g[:, 1], rtol=1e-3, atol=2e-2)
+    g_out = torch.full((1,), -1.5, device=dev())            # negative upstream gradient
+    da_g, db_g = op.p2p_bwd(a, b, d - 3, ma, mb, shift, w, t, st_g, g_out, True, True)
+    da_a, db_a = op.p2p_bwd(a, b, d - 3, ma, mb, shift, w, t, st_a, g_out, True, True, k, selfcol, selfrow, state)
+    grad_close(da_a, da_g, rtol=P2P_RTOL, floor=0.5)
+    grad_close(db_a, db_g, rtol=P2P_RTOL, floor=0.5)
+    only_b = op.p2p_bwd(a, b, d - 3, ma, mb, shift, w, t, st_a, g_out, False, True, k, selfcol, selfrow, state)[1]
+    assert torch.equal(only_b, db_a)
+
+
 def test_c_abi_called_directly_with_ctypes():
     """The INTEGRATION.md stub: raw ctypes against include/slcl.h, no torch custom-op layer in between."""
     import ctypes as C
