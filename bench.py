@@ -344,6 +344,12 @@ def run_slcl(args):
         del grad_h
     sampler.stop()
 
+    # configs[3]/[4]: the MCCL loss section of one adaptation step at the cfg5 geometry, through the Python API inside
+    # autograd, with the centroid all-reduce over NCCL when N > 1 (every rank runs it; rank 0 reports the max)
+    mccl = None
+    if not args.no_extras:
+        mccl = mccl_loss_section(dev, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,6 +382,9 @@ def run_slcl(args):
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
+    if mccl is not None:
+        mccl["frac_of_hbm_peak"] = mccl["achieved_GBps_per_gpu"] / peak
+        out["mccl_loss_section"] = mccl
     if not args.no_extras and world == 1:
         out["kernels"] = extra_kernels(dev, feats, labels, centres, peak)
     if not args.no_cpu and world == 1:
@@ -390,6 +399,89 @@ def run_slcl(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def mccl_loss_section(dev, world):
+    import torch.distributed as dist
+    """Trainer_MCCL.py:275-332 between "the decoder produced feature maps" and "the loss has gradients": source centroids
+    (hard labels), target and augmented-target centroids (soft labels x certainty, 2 reversed-Monte-Carlo partitions),
+    ContrastiveLoss per partition + centroid-norm regulariser, backward to the three feature maps and both soft-label
+    maps.  cfg5 geometry per GPU: 64 images of 224x224, C = 32, K = 4 (weak scaling); the per-class sums are all-reduced
+    with NCCL when N > 1.  Bytes: source 8C+8, each target 12C+12K+8 per pixel (SURVEY.md 8(d))."""
+    from slcl.loss import ContrastiveLoss, cnr_loss
+    from slcl.utils_ import cal_centroid
+    b, c, h, k, parts = 64, 32, 224, 4, 2
+    n_px = b * h * h
+    gen = torch.Generator(device=dev).manual_seed(4321 + int(os.environ.get("RANK", "0")))
+    ft = [torch.randn(b, c, h, h, device=dev, generator=gen).requires_grad_(True) for _ in range(3)]
+    lab_s = torch.randint(0, k, (b, h, h), device=dev, generator=gen)
+    pr = [torch.softmax(3 * torch.randn(b, k, h, h, device=dev, generator=gen), 1).requires_grad_(True) for _ in range(2)]
+    part = [(torch.randperm(n_px, device=dev, generator=gen) % parts).to(torch.int32) for _ in range(2)]
+    crit = ContrastiveLoss()
+    group = True if world > 1 else None
+
+    def make_step(ft, pr):
+        def step():
+            cs, _, _ = cal_centroid(ft[0], lab_s, n_class=k, group=group)
+            loss = 0
+            for i in range(2):
+                ct, _, _ = cal_centroid(ft[1 + i], pr[i], pseudo_label=True, weighted_ave=True, partition=parts, n_class=k,
+                                        part_id=part[i], group=group)
+                for c_p in ct:
+                    loss = loss + crit(cs, c_p)
+                loss = loss + 4e-5 * cnr_loss(cs, ct)
+            loss.backward()
+            for t in ft + pr:
+                t.grad = None
+            return loss.detach()
+        return step
+
+    step = make_step(ft, pr)
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            out = fn()
+        e.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), out
+
+    ms_eager, loss = timed(step)          # what a plain eager trainer sees: ~30 custom-op calls, host-launch-bound
+    ms, how = ms_eager, "eager"
+    if world == 1:
+        # the same step captured once in a CUDA graph (forward + autograd backward): the device time of the section
+        try:
+            # fresh leaves: their AccumulateGrad nodes must be born on the capture side stream, not the default one
+            gstep = make_step([t.detach().requires_grad_(True) for t in ft], [t.detach().requires_grad_(True) for t in pr])
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                gstep()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = gstep()
+            ms, _ = timed(graph.replay)
+            loss, how = static_loss, "one CUDA graph (forward + autograd backward captured)"
+        except Exception as exc:          # capture is an optimisation of the measurement, not of the product
+            print(f"[bench] MCCL section: graph capture unavailable ({exc!r}); reporting the eager time", file=sys.stderr)
+    bytes_ = ((8 * c + 8) + 2 * (12 * c + 12 * k + 8)) * n_px
+    return {"workload": "cfg5 geometry: MCCL loss section (3 x cal_centroid + 4 x ContrastiveLoss + CNR, fwd+bwd) through the "
+                        "Python API inside autograd, per GPU 64 x 32 x 224 x 224, K=4, P=2",
+            "ms_per_step": ms, "timed_as": how, "ms_per_step_eager": ms_eager,
+            "pixels_per_s": world * 3 * n_px / (ms * 1e-3), "algorithmic_bytes_per_gpu": bytes_,
+            "achieved_GBps_per_gpu": bytes_ / (ms * 1e-3) / 1e9, "n_gpus": world, "loss": float(loss),
+            "exchange": "all-reduce of [sets*K, C+1] fp64 class sums per cal_centroid (NCCL)" if world > 1 else "none"}
 
 
 def extra_kernels(dev, feats, labels, centres, peak):
