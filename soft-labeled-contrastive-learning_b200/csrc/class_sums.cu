@@ -45,6 +45,8 @@ struct SumArgs {
   int n_cols;                // logical columns (n_part * n_class, or planar cols)
   int64_t tiles_per_image, n_tiles;
   int cg_per_block, pt_per_block;   // warps = cg_per_block * pt_per_block
+  int n_cw;                         // v3: consumer warps in use (channels per block = n_cw * CPW)
+  int n_stages;                     // v3: ring depth
   float* partial;            // [gridDim.x][KWT][C+1]
 };
 
@@ -302,12 +304,13 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
 // 128 registers: with wide weight rows (soft labels x partitions) it is latency-bound at ~45 % of the HBM
 // roofline.  Here the three jobs are separate roles of one persistent CTA per SM:
 //   warp 0       TMA producer: one cp.async.bulk.tensor.3d box [128 pixels x CB channels] per stage into a
-//                5-stage ring (up to 160 KB in flight per SM, completion on mbarriers)
+//                ring of up to 12 stages (~200 KB in flight per SM whatever the channel count, completion on mbarriers)
 //   warps 1-8    weight builders: labels / soft probabilities / partition ids of the stage's 128 pixels ->
 //                sW[stage][column][pixel]; two warps per stage, four teams round-robin over the stages, and each
-//                warp fetches the raw inputs of its NEXT stage before it waits for that stage's slot, so its
-//                global-load latency is covered by four stage periods; they also own the weight-sum column
-//   warps 9-24   consumers: warp w owns CPW channels; lane l owns pixels 4l..4l+3 of the stage; x and the weights
+//                warp fetches the raw inputs of its next two stages before it waits for their slots, so its
+//                global-load latency is covered by eight stage periods
+//   last warp    counter (channel block 0 only): sums the weights themselves -> the class-count column
+//   warps 9-24   consumers (as many as the channel count needs): warp w owns CPW channels; lane l owns pixels 4l..4l+3 of the stage; x and the weights
 //                come back from shared memory with conflict-free 128-bit loads; acc[CPW][KWT] in registers for
 //                the whole sweep; every channel has exactly one owner, so the block result needs no combine
 // Partials and the fp64 second stage are those of v2.
@@ -316,7 +319,7 @@ constexpr int kV3ConsumerWarps = 16;
 constexpr int kV3WeightWarps = 8;       // two per stage (64 pixels each), four stage teams round-robin
 constexpr int kV3Threads = 32 * (1 + kV3WeightWarps + kV3ConsumerWarps);
 constexpr int kV3Px = 128;
-constexpr int kV3Stages = 5;
+constexpr int kV3MaxStages = 12;      // ring depth is chosen per shape: as many stages as fit in ~200 KB, at most this
 
 __device__ __forceinline__ uint32_t v3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void v3_mbar_init(uint64_t* bar, uint32_t count) {
@@ -348,19 +351,30 @@ __device__ __forceinline__ void v3_tma_load_3d(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
-struct __align__(8) V3Bars { uint64_t x_full[kV3Stages], w_full[kV3Stages], empty[kV3Stages]; };
+// ring position of iteration `it`: slot = it % n, phase = (it / n) & 1, advanced without divisions
+struct V3Pos {
+  int slot, phase, n;
+  __device__ __forceinline__ V3Pos(int start, int n_) : slot(start), phase(0), n(n_) { norm(); }
+  __device__ __forceinline__ void norm() { while (slot >= n) { slot -= n; phase ^= 1; } }
+  __device__ __forceinline__ void advance(int step) { slot += step; norm(); }
+};
 
-template <int KWT, int CPW>
-__global__ void __launch_bounds__(kV3Threads, 1)
+struct __align__(8) V3Bars { uint64_t x_full[kV3MaxStages], w_full[kV3MaxStages], empty[kV3MaxStages]; };
+
+// NCW = upper bound of the consumer warps (8 or 16): it sets the register budget (120 vs 72 per thread) and, with it,
+// how far ahead the weight builders prefetch (small channel counts mean short stages: two visits ahead).
+template <int KWT, int CPW, int NCW>
+__global__ void __launch_bounds__(32 * (2 + kV3WeightWarps + NCW), 1)
 class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs a) {
-  constexpr int CB = kV3ConsumerWarps * CPW;                   // channels per block
-  constexpr int kStageBytes = CB * kV3Px * 4;
+  constexpr bool kDeep = NCW <= 8;
+  const int kV3Stages = a.n_stages;
+  const int CB = a.n_cw * CPW;                                 // channels per block
+  const int kStageBytes = CB * kV3Px * 4;
   extern __shared__ __align__(128) uint8_t v3_smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v3_smem) + 127) & ~(uintptr_t)127);
   float* sX = reinterpret_cast<float*>(base);                                   // [stages][CB][128]
   float* sWt = reinterpret_cast<float*>(base + (size_t)kV3Stages * kStageBytes); // [stages][KWT][128]
   V3Bars* bars = reinterpret_cast<V3Bars*>(sWt + (size_t)kV3Stages * KWT * kV3Px);
-  __shared__ float s_w[kV3WeightWarps][KWT];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = (int)a.channels;
@@ -374,7 +388,7 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
     for (int s = 0; s < kV3Stages; ++s) {
       v3_mbar_init(&bars->x_full[s], 1);
       v3_mbar_init(&bars->w_full[s], 2);
-      v3_mbar_init(&bars->empty[s], kV3ConsumerWarps);
+      v3_mbar_init(&bars->empty[s], a.n_cw + (blockIdx.y == 0 ? 1 : 0));      // + the counter warp of channel block 0
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -382,12 +396,13 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    for (int64_t it = 0; it < n_iter; ++it) {
-      const int s = (int)(it % kV3Stages);
+    V3Pos pos(0, kV3Stages);
+    for (int64_t it = 0; it < n_iter; ++it, pos.advance(1)) {
+      const int s = pos.slot;
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t b = tile / tiles_per_image;
       const int p0 = (int)((tile - b * tiles_per_image) * kV3Px);
-      v3_mbar_wait(&bars->empty[s], (uint32_t)(((it / kV3Stages) & 1) ^ 1));
+      v3_mbar_wait(&bars->empty[s], (uint32_t)(pos.phase ^ 1));
       if (lane == 0) {
         v3_mbar_expect_tx(&bars->x_full[s], kStageBytes);
         v3_tma_load_3d(sX + (size_t)s * CB * kV3Px, &map_feat, &bars->x_full[s], p0, c_base, (int)b);
@@ -398,17 +413,17 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
     // ===================== weight builders =====================
     const int wv = warp - 1;
     const int team = wv >> 1, hf = wv & 1;             // team -> stages team, team+4, ...; half of the 128 pixels
-    const bool count_weights = blockIdx.y == 0;
     constexpr int kTeams = kV3WeightWarps / 2;
     constexpr int kPl = 2;                              // pixels per lane: 64 pixels per warp
-    float wacc[KWT];
-#pragma unroll
-    for (int q = 0; q < KWT; ++q) wacc[q] = 0.f;
-    // raw inputs of kPl pixels (whatever the mode needs), fetched one stage ahead
-    float r_f[kPl][KWT > SLCL_MAX_CLASSES ? KWT : SLCL_MAX_CLASSES];
-    int r_part[kPl];
-    long long r_lab[kPl];
-    auto fetch = [&](int64_t it) {
+    // raw inputs of kPl pixels (whatever the mode needs), fetched one visit (= 4 stages) ahead, or two with kDeep: under
+    // a saturated HBM the load latency exceeds four periods of a 16 KB stage
+    struct Raw {
+      float f[kPl][KWT > SLCL_MAX_CLASSES ? KWT : SLCL_MAX_CLASSES];
+      int part[kPl];
+      long long lab[kPl];
+    };
+    auto fetch = [&](Raw& r, int64_t it) {
+      if (it >= n_iter) return;
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t b = tile / tiles_per_image;
       const int64_t p0 = (tile - b * tiles_per_image) * kV3Px + hf * 64;
@@ -417,86 +432,98 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
         const int64_t p = p0 + lane + 32 * i;
         const bool ok = p < a.pixels;
         const int64_t pix = b * a.pixels + p;
-        r_part[i] = (ok && a.part_id) ? a.part_id[pix] : 0;
-        r_lab[i] = -1;
+        r.part[i] = (ok && a.part_id) ? a.part_id[pix] : 0;
+        r.lab[i] = -1;
         if (a.mode == kPlanar) {
           const int64_t n = a.batch * a.pixels;
 #pragma unroll
-          for (int j = 0; j < KWT; ++j) r_f[i][j] = (ok && j < a.n_cols) ? a.planar[(int64_t)j * n + pix] : 0.f;
+          for (int j = 0; j < KWT; ++j) r.f[i][j] = (ok && j < a.n_cols) ? a.planar[(int64_t)j * n + pix] : 0.f;
         } else if (a.mode == kHard) {
-          if (ok) r_lab[i] = a.labels[pix];
+          if (ok) r.lab[i] = a.labels[pix];
         } else {
 #pragma unroll
           for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
-            r_f[i][k] = (ok && k < a.n_class) ? a.probs[(b * a.n_class + k) * a.pixels + p] : 0.f;
-          if (!ok) r_part[i] = -1;                      // pixels past the image: all-zero weight row
+            r.f[i][k] = (ok && k < a.n_class) ? a.probs[(b * a.n_class + k) * a.pixels + p] : 0.f;
+          if (!ok) r.part[i] = -1;                      // pixels past the image: all-zero weight row
         }
       }
     };
-    if (team < n_iter) fetch(team);
-    for (int64_t it = team; it < n_iter; it += kTeams) {
-      const int s = (int)(it % kV3Stages);
-      v3_mbar_wait(&bars->empty[s], (uint32_t)(((it / kV3Stages) & 1) ^ 1));
-      float* dst = sWt + (size_t)s * KWT * kV3Px + hf * 64;
+    V3Pos bpos(team, kV3Stages);
+    auto build = [&](const Raw& r) {               // builds the stage at bpos, then moves bpos to this team's next stage
+      const int s = bpos.slot;
+      v3_mbar_wait(&bars->empty[s], (uint32_t)(bpos.phase ^ 1));
+      float* dst = sWt + (size_t)s * KWT * kV3Px + hf * 64 + lane;
+      const bool use_thr = a.threshold > 0.f && a.threshold < 1.f;
 #pragma unroll
       for (int i = 0; i < kPl; ++i) {
-        float w[KWT];
-#pragma unroll
-        for (int q = 0; q < KWT; ++q) w[q] = 0.f;
+        float* d = dst + 32 * i;
         if (a.mode == kPlanar) {
 #pragma unroll
-          for (int q = 0; q < KWT; ++q) w[q] = r_f[i][q];
-        } else if (a.mode == kHard) {
-          // utils_.py:581 / :535
-          const bool ok = r_lab[i] >= 0 && r_lab[i] < a.n_class && r_part[i] >= 0 && r_part[i] < a.n_part;
-          const int col = ok ? r_part[i] * a.n_class + (int)r_lab[i] : -1;
+          for (int q = 0; q < KWT; ++q) d[q * kV3Px] = r.f[i][q];
+          continue;
+        }
+        // every column zero, then the (at most K) columns of the pixel's partition: no select chains, the column index
+        // only ever appears in a shared-memory address
 #pragma unroll
-          for (int q = 0; q < KWT; ++q) w[q] = (q == col) ? 1.0f : 0.0f;
-        } else {
+        for (int q = 0; q < KWT; ++q) d[q * kV3Px] = 0.f;
+        const bool part_ok = r.part[i] >= 0 && r.part[i] < a.n_part;
+        if (a.mode == kHard) {
+          // utils_.py:581 / :535
+          if (part_ok && r.lab[i] >= 0 && r.lab[i] < a.n_class) d[(r.part[i] * a.n_class + (int)r.lab[i]) * kV3Px] = 1.0f;
+        } else if (part_ok) {
           // soft probabilities: :517-519 (weighted) or :524-525 (arg-max one-hot); certainty :511-514
-          float best = -INFINITY;
+          float cert = 1.f;
           int arg = 0;
+          if (use_thr || !a.weighted) {
+            float best = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+              if (k < a.n_class && r.f[i][k] > best) { best = r.f[i][k]; arg = k; }
+            if (use_thr) cert = best >= a.threshold ? 1.f : 0.f;
+          }
+          float* dp = d + (size_t)r.part[i] * a.n_class * kV3Px;
 #pragma unroll
           for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
-            if (k < a.n_class && r_f[i][k] > best) { best = r_f[i][k]; arg = k; }
-          const float cert = (a.threshold > 0.f && a.threshold < 1.f) ? ((best >= a.threshold) ? 1.f : 0.f) : 1.f;
-          const bool ok = r_part[i] >= 0 && r_part[i] < a.n_part;
-#pragma unroll
-          for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
-            if (k < a.n_class) {
-              const float wk = a.weighted ? r_f[i][k] * cert : ((k == arg) ? cert : 0.f);
-              const int col = r_part[i] * a.n_class + k;
-#pragma unroll
-              for (int q = 0; q < KWT; ++q) if (ok && q == col) w[q] = wk;
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < KWT; ++q) {
-          dst[q * kV3Px + lane + 32 * i] = w[q];
-          if (count_weights) wacc[q] += w[q];
+            if (k < a.n_class) dp[k * kV3Px] = a.weighted ? r.f[i][k] * cert : ((k == arg) ? cert : 0.f);
         }
       }
       __syncwarp();
       if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
-      if (it + kTeams < n_iter) fetch(it + kTeams);     // in flight while this warp waits for its next slot
-    }
-#pragma unroll
-    for (int q = 0; q < KWT; ++q) {
-      const float r = warp_sum(wacc[q]);
-      if (lane == 0) s_w[wv][q] = r;
+      bpos.advance(kTeams);
+    };
+    if constexpr (kDeep) {
+      Raw ra, rb;
+      fetch(ra, team);
+      fetch(rb, team + kTeams);
+      for (int64_t it = team; it < n_iter; it += 2 * kTeams) {
+        build(ra);
+        fetch(ra, it + 2 * kTeams);                       // in flight while this warp waits for its next slots
+        if (it + kTeams < n_iter) {
+          build(rb);
+          fetch(rb, it + 3 * kTeams);
+        }
+      }
+    } else {
+      Raw ra;
+      fetch(ra, team);
+      for (int64_t it = team; it < n_iter; it += kTeams) {
+        build(ra);
+        fetch(ra, it + kTeams);
+      }
     }
   } else {
     // ===================== consumers =====================
     const int cw = warp - 1 - kV3WeightWarps;
+    if (cw < a.n_cw) {
     float acc[CPW][KWT];
 #pragma unroll
-    for (int j = 0; j < CPW; ++j)
+    for (int q = 0; q < KWT; ++q)
 #pragma unroll
-      for (int q = 0; q < KWT; ++q) acc[j][q] = 0.f;
-    for (int64_t it = 0; it < n_iter; ++it) {
-      const int s = (int)(it % kV3Stages);
-      const uint32_t par = (uint32_t)((it / kV3Stages) & 1);
+      for (int j = 0; j < CPW; ++j) acc[j][q] = 0.f;
+    V3Pos cpos(0, kV3Stages);
+    for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
+      const int s = cpos.slot;
+      const uint32_t par = (uint32_t)cpos.phase;
       v3_mbar_wait(&bars->x_full[s], par);
       v3_mbar_wait(&bars->w_full[s], par);
       const float4* xs = reinterpret_cast<const float4*>(sX + ((size_t)s * CB + cw * CPW) * kV3Px) + lane;
@@ -528,13 +555,32 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
         if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
       }
     }
-  }
-  __syncthreads();
-  if (blockIdx.y == 0 && threadIdx.x < KWT) {
-    float t = 0.f;
+    } else if (cw == a.n_cw && blockIdx.y == 0) {
+      // ===================== counter: the weight-sum ("class count") column =====================
+      // sums of the weights themselves, read back like a consumer does (exact integers for hard labels)
+      float cacc[KWT];
 #pragma unroll
-    for (int w = 0; w < kV3WeightWarps; ++w) t += s_w[w][threadIdx.x];
-    a.partial[(int64_t)blockIdx.x * KWT * (C + 1) + (int64_t)threadIdx.x * (C + 1) + C] = t;
+      for (int q = 0; q < KWT; ++q) cacc[q] = 0.f;
+      V3Pos cpos(0, kV3Stages);
+      for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
+        const int s = cpos.slot;
+        v3_mbar_wait(&bars->w_full[s], (uint32_t)cpos.phase);
+        const float4* ws = reinterpret_cast<const float4*>(sWt + (size_t)s * KWT * kV3Px) + lane;
+#pragma unroll
+        for (int q = 0; q < KWT; ++q) {
+          const float4 w = ws[q * (kV3Px / 4)];
+          cacc[q] += (w.x + w.y) + (w.z + w.w);
+        }
+        __syncwarp();
+        if (lane == 0) v3_mbar_arrive(&bars->empty[s]);
+      }
+      float* out = a.partial + (int64_t)blockIdx.x * KWT * (C + 1);
+#pragma unroll
+      for (int q = 0; q < KWT; ++q) {
+        const float r = warp_sum(cacc[q]);
+        if (lane == 0) out[(int64_t)q * (C + 1) + C] = r;
+      }
+    }
   }
 }
 
@@ -801,7 +847,7 @@ V3EncodeFn v3_encode_fn() {
   return fn;
 }
 
-struct V3Plan { bool ok; int kwt, cpw; dim3 grid; };
+struct V3Plan { bool ok; int kwt, cpw, n_cw; dim3 grid; };
 
 V3Plan plan_v3(const SumArgs& a, bool vec4) {
   V3Plan p{};
@@ -811,9 +857,12 @@ V3Plan plan_v3(const SumArgs& a, bool vec4) {
   p.kwt = pick_kwt(a.n_cols);
   if (p.kwt < 0) return p;
   const int C = (int)a.channels;
-  p.cpw = C <= 16 ? 1 : (C <= 32 ? 2 : 4);
-  if (p.kwt > 10 && p.cpw > 2) p.cpw = 2;           // 96 registers per thread: keep acc[CPW][KWT] <= 40
-  const int cb = kV3ConsumerWarps * p.cpw;
+  // Few, fat consumer warps: every consumer re-reads the stage's weights from shared memory, so the weight traffic per
+  // stage is n_cw x KWT x 512 B -- with 4 channels per warp it stays below the feature traffic's share of the LSU.
+  p.cpw = p.kwt > 10 ? 2 : 4;                       // 72-96 registers per thread: keep acc[CPW][KWT] <= 40
+  p.n_cw = ceil_div(C, p.cpw);
+  if (p.n_cw > kV3ConsumerWarps) p.n_cw = kV3ConsumerWarps;
+  const int cb = p.n_cw * p.cpw;
   const int gy = ceil_div(C, cb);
   const int64_t n_tiles = a.batch * ceil_div<int64_t>(a.pixels, kV3Px);
   int64_t gx = sm_count() / gy;
@@ -825,43 +874,47 @@ V3Plan plan_v3(const SumArgs& a, bool vec4) {
   return p;
 }
 
-size_t v3_smem_bytes(int kwt, int cpw) {
-  return 128 + (size_t)kV3Stages * (kV3ConsumerWarps * cpw * kV3Px * 4 + kwt * kV3Px * 4) + sizeof(V3Bars) + 64;
+size_t v3_stage_bytes(int kwt, int cpw, int n_cw) { return (size_t)(n_cw * cpw + kwt) * kV3Px * 4; }
+int v3_stages(int kwt, int cpw, int n_cw) {          // as deep as ~200 KB allow: small-C stages are short, the ring must be long
+  int n = (int)((200 * 1024) / v3_stage_bytes(kwt, cpw, n_cw));
+  return n < 2 ? 2 : (n > kV3MaxStages ? kV3MaxStages : n);
+}
+size_t v3_smem_bytes(int kwt, int cpw, int n_cw) {
+  return 128 + (size_t)v3_stages(kwt, cpw, n_cw) * v3_stage_bytes(kwt, cpw, n_cw) + sizeof(V3Bars) + 64;
 }
 
-template <int KWT, int CPW>
+template <int KWT, int CPW, int NCW>
 int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
   V3EncodeFn fn = v3_encode_fn();
   if (!fn) return SLCL_ERR_CUDA;
   CUtensorMap map;
   cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.channels, (cuuint64_t)a.batch};
   cuuint64_t strides[2] = {(cuuint64_t)a.sc * 4, (cuuint64_t)a.sb * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)(kV3ConsumerWarps * CPW), 1};
+  cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)(p.n_cw * CPW), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.feat), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(class sums)"); return SLCL_ERR_CUDA; }
-  const size_t smem = v3_smem_bytes(KWT, CPW);
+  const size_t smem = v3_smem_bytes(KWT, CPW, p.n_cw);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         220 * 1024);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(class_sums_v3_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
-  class_sums_v3_kernel<KWT, CPW><<<p.grid, kV3Threads, smem, stream>>>(map, a);
+  SumArgs av = a;
+  av.n_cw = p.n_cw;
+  av.n_stages = v3_stages(KWT, CPW, p.n_cw);
+  class_sums_v3_kernel<KWT, CPW, NCW><<<p.grid, 32 * (2 + kV3WeightWarps + p.n_cw), smem, stream>>>(map, av);
   return SLCL_OK;
 }
 
 template <int KWT>
 int launch_v3_cpw(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
-  switch (p.cpw) {
-    case 1: return launch_v3<KWT, 1>(a, p, stream);
-    case 2: return launch_v3<KWT, 2>(a, p, stream);
-    default:
-      if constexpr (KWT <= 10) return launch_v3<KWT, 4>(a, p, stream);
-      else return launch_v3<KWT, 2>(a, p, stream);
-  }
+  if constexpr (KWT <= 10) return p.n_cw <= 8 ? launch_v3<KWT, 4, 8>(a, p, stream) : launch_v3<KWT, 4, 16>(a, p, stream);
+  else return p.n_cw <= 8 ? launch_v3<KWT, 2, 8>(a, p, stream) : launch_v3<KWT, 2, 16>(a, p, stream);
 }
 
 int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
