@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
 // Partials and the fp64 second stage are those of v2.
 // ---------------------------------------------------------------------------
 constexpr int kV3ConsumerWarps = 16;
-constexpr int kV3WeightWarps = 8;       // two per stage (64 pixels each), four stage teams round-robin
-constexpr int kV3Threads = 32 * (1 + kV3WeightWarps + kV3ConsumerWarps);
+constexpr int v3_builder_warps(int ncw) { return ncw > 8 ? 4 : 8; }      // two per stage; fewer when the stages are long
+constexpr int kV3MaxBuilderWarps = 8;
 constexpr int kV3Px = 128;
 constexpr int kV3MaxStages = 12;      // ring depth is chosen per shape: as many stages as fit in ~200 KB, at most this
 
@@ -364,9 +364,10 @@ struct __align__(8) V3Bars { uint64_t x_full[kV3MaxStages], w_full[kV3MaxStages]
 // NCW = upper bound of the consumer warps (8 or 16): it sets the register budget (120 vs 72 per thread) and, with it,
 // how far ahead the weight builders prefetch (small channel counts mean short stages: two visits ahead).
 template <int KWT, int CPW, int NCW>
-__global__ void __launch_bounds__(32 * (2 + kV3WeightWarps + NCW), 1)
+__global__ void __launch_bounds__(32 * (2 + v3_builder_warps(NCW) + NCW), 1)
 class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs a) {
   constexpr bool kDeep = NCW <= 8;
+  constexpr int kV3WeightWarps = v3_builder_warps(NCW);
   const int kV3Stages = a.n_stages;
   const int CB = a.n_cw * CPW;                                 // channels per block
   const int kStageBytes = CB * kV3Px * 4;
@@ -907,7 +908,7 @@ int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
   SumArgs av = a;
   av.n_cw = p.n_cw;
   av.n_stages = v3_stages(KWT, CPW, p.n_cw);
-  class_sums_v3_kernel<KWT, CPW, NCW><<<p.grid, 32 * (2 + kV3WeightWarps + p.n_cw), smem, stream>>>(map, av);
+  class_sums_v3_kernel<KWT, CPW, NCW><<<p.grid, 32 * (2 + v3_builder_warps(NCW) + p.n_cw), smem, stream>>>(map, av);
   return SLCL_OK;
 }
 
