@@ -11,7 +11,7 @@ from torch import Tensor
 
 from . import ops  # noqa: F401  (registers torch.ops.slcl.*)
 
-_ops = torch.ops.slcl
+_ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
 class _ProtoLoss(torch.autograd.Function):

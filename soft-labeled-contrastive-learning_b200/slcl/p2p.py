@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import ops  # noqa: F401
 
-_ops = torch.ops.slcl
+_ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
 class _P2PLoss(torch.autograd.Function):

@@ -8,7 +8,7 @@ import torch
 
 from . import ops  # noqa: F401
 
-_ops = torch.ops.slcl
+_ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
 class _SegLosses(torch.autograd.Function):

@@ -8,8 +8,9 @@ import torch
 import torch.nn.functional as F
 
 from . import functional as SF
+from . import ops
 
-_ops = torch.ops.slcl
+_ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
 def update_class_center_iter(cla_src_feas, batch_src_labels, class_center_feas, m=.2, num_class=4, group=None):
