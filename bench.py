@@ -584,6 +584,29 @@ def p2p_kernels(dev, gen):
         return s.elapsed_time(e) / iters
 
     out = {}
+    # BlockConLoss at the reference's documented shape (1, 2, 32, 224, 224), 32 x 32 tiles: 49 tiles of 2048 rows as ONE
+    # block-diagonal problem (the reference and the per-tile loop launch 49 separate SupCon problems)
+    from slcl.loss import BlockConLoss
+    fb = torch.nn.functional.normalize(torch.randn(1, 2, 32, 224, 224, device=dev, generator=gen), dim=2).requires_grad_(True)
+    lbk = torch.randint(0, 4, (1, 2, 224, 224), device=dev, generator=gen)
+    crit = BlockConLoss(0.7, 32)
+
+    def block_step():
+        loss_b = crit(fb, lbk)
+        loss_b.backward()
+        fb.grad = None
+    ms = timed(block_step, iters=10)
+    m_t, n_t = 2048, 49
+    fl = 8.0 * n_t * m_t * m_t * 64          # 32 channels padded to 64 bf16 columns
+    out["BlockConLoss (1,2,32,224,224) fwd+bwd through the Python API, 49 tiles batched"] = {
+        "ms": ms, "algorithmic_flop": fl, "achieved_TFLOPs": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tf_peak,
+        "rows_per_s": n_t * m_t / (ms * 1e-3)}
+    crit.batched = False
+    ms_loop = timed(block_step, iters=3)
+    out["BlockConLoss (1,2,32,224,224) fwd+bwd, per-tile loop (49 SupCon calls, the reference's structure)"] = {
+        "ms": ms_loop, "algorithmic_flop": fl, "achieved_TFLOPs": fl / (ms_loop * 1e-3) / 1e12,
+        "frac_of_bf16_peak": fl / (ms_loop * 1e-3) / 1e12 / tf_peak, "rows_per_s": n_t * m_t / (ms_loop * 1e-3)}
+    del fb, lbk
     for name, fn, flops in (("cfg3 p2p forward only (A4096 x M16384 x d256, bf16 tcgen05)", plan.forward_only, 2.0 * A * M * d),
                             ("cfg3 p2p forward keeping U for the backward (S + E.B)", plan.forward, 4.0 * A * M * d),
                             ("cfg3 p2p backward (dB sweep: S recomputed + G^T.A; dA from U)", plan.backward, 4.0 * A * M * d),

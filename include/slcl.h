@@ -261,6 +261,9 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *         ONE tensor-core sweep (dB) and one finishing kernel; with null the backward regenerates it (one more sweep).
  *     The per-class sums of the contrast rows do not depend on the sweep: they run on a side stream owned by the
  *     library (one per host thread and device, created on first use; fork/join by events, graph-capturable).
+ *   n_batch: 1, or the number of equal BLOCK-DIAGONAL batches (general mode only): anchors [z A/n, (z+1) A/n) are
+ *     contrasted with contrast rows [z M/n, (z+1) M/n) only -- BlockConLoss (utils/loss.py:416-466) as ONE launch per
+ *     sweep instead of div_num^2 separate problems.  A/n and M/n must be multiples of 128.
  * forward : stats [A,3] = {sum_j exp(S_ij - shift_i), sum_pos S_ij * T, #pos},
  *           loss [1] = sum_i w_i (shift_i + log stats_i0 - stats_i1/(T stats_i2)).
  * backward: d_a [A, dim] and/or d_b [M, dim] fp32 = dL/da, dL/db for dL/dloss = *grad_out
@@ -269,13 +272,13 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
 size_t slcl_p2p_workspace_bytes(int64_t n_anchor, int64_t n_contrast, int64_t dim_padded);
 size_t slcl_p2p_state_bytes(int64_t n_anchor, int64_t dim_padded);
 int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                 const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
+                 const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class, int n_batch,
                  const float* shift, const float* weight, float temperature, float* stats, float* loss,
                  void* bwd_state, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                  int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
-                 const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
-                 const float* stats, const void* bwd_state, const float* grad_out, float* d_a, float* d_b,
+                 const int32_t* b_selfrow, int n_class, int n_batch, const float* shift, const float* weight,
+                 float temperature, const float* stats, const void* bwd_state, const float* grad_out, float* d_a, float* d_b,
                  void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
 #ifdef __cplusplus

@@ -79,6 +79,8 @@ template <int MODE> struct ModeTraits {
 struct P2PArgs {
   int n_rows, n_cols, d;              // d padded to a multiple of 64
   int cols_per_split;                 // CTA (x, y) sweeps columns [y * cols_per_split, ...)
+  int rows_per_batch, cols_per_batch; // block-diagonal batches (grid.z): batch z contrasts rows [z rpb, (z+1) rpb) with columns
+                                      // [z cpb, (z+1) cpb) only; rpb % 128 == 0 and cpb % 64 == 0.  One batch: the whole problem.
   float scale_log2;                   // log2(e) / T
   const uint32_t* rows_u32;           // resident operand, bf16 row-major [n_rows, d] viewed as 32-bit words
   const int2* row_meta;               // general modes: {label, id}
@@ -361,14 +363,16 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
 
   const long long t_entry = SLCL_PROF_NOW();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * BM;
+  const int batch = blockIdx.z;
+  const int row0 = batch * a.rows_per_batch + blockIdx.x * BM;
+  const int row_end = min(a.n_rows, (batch + 1) * a.rows_per_batch);
   const int split = blockIdx.y;
-  const int col0 = split * a.cols_per_split;
-  const int col_end = min(a.n_cols, col0 + a.cols_per_split);
+  const int col0 = batch * a.cols_per_batch + split * a.cols_per_split;
+  const int col_end = min(min(a.n_cols, (batch + 1) * a.cols_per_batch), col0 + a.cols_per_split);
   const int n_tiles = (col_end - col0 + BN - 1) / BN;
   // Every CTA sweeps the same column tiles; start each one at a different tile so the CTAs do not
   // all hit the same L2 lines at the same moment (the sums do not depend on the sweep order).
-  const int rot = (int)(((blockIdx.x / CS) * 37u + blockIdx.y * 11u) % (unsigned)n_tiles);
+  const int rot = (int)(((blockIdx.x / CS) * 37u + blockIdx.y * 11u + blockIdx.z * 5u) % (unsigned)n_tiles);
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
   auto tile_col = [&](int t) { int tt = t + rot; if (tt >= n_tiles) tt -= n_tiles; return col0 + tt * BN; };
@@ -520,7 +524,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     const int half = (warp - 4) >> 2;             // column half of the S tile
     const int r_local = q * 32 + lane;
     const int row = row0 + r_local;
-    const bool row_ok = row < a.n_rows;
+    const bool row_ok = row < row_end;
     int2 rm = make_int2(INT_MIN + 1, INT_MIN + 1);
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MODE == kGenFwd || MODE == kGenRows) { if (row_ok) rm = a.row_meta[row]; }
@@ -1247,11 +1251,11 @@ void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
 
 struct Sweep { int row_tiles, splits, cols_per_split, cluster; };
 
-Sweep plan_sweep(int64_t n_rows, int64_t n_cols) {
+Sweep plan_sweep(int64_t n_rows, int64_t n_cols, int n_batch = 1) {          // sizes are per batch
   Sweep s;
   s.row_tiles = (int)ceil_div<int64_t>(n_rows, BM);
   int col_tiles = (int)ceil_div<int64_t>(n_cols, BN);
-  int want = max(1, sm_count() / s.row_tiles);      // fill the SMs: row tiles x column splits ~ #SMs
+  int want = max(1, sm_count() / (s.row_tiles * n_batch));      // fill the SMs: batches x row tiles x column splits ~ #SMs
   s.splits = min(want, col_tiles);
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
@@ -1283,7 +1287,7 @@ int make_out_map(CUtensorMap* m, const float* ptr, int64_t n_cols, int64_t ld, i
 
 template <int CS, int MODE>
 int launch_one(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const P2PArgs& a, const Sweep& sw, size_t smem,
-               cudaStream_t stream) {
+               int n_batch, cudaStream_t stream) {
   static bool attr_set = false;          // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(p2p_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(kMaxD));
@@ -1291,7 +1295,7 @@ int launch_one(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& 
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ceil_div(sw.row_tiles, CS) * CS), (unsigned)sw.splits, 1);
+  cfg.gridDim = dim3((unsigned)(ceil_div(sw.row_tiles, CS) * CS), (unsigned)sw.splits, (unsigned)n_batch);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -1311,7 +1315,7 @@ int launch_one(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& 
 
 template <int MODE>
 int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_cols, int d, float inv_t, P2PArgs a,
-                 const Sweep& sw, cudaStream_t stream) {
+                 const Sweep& sw, cudaStream_t stream, int n_batch = 1) {
   CUtensorMap mr, mc, mo;
   int st = make_map(&mr, rows, n_rows, d, BM);
   if (st != SLCL_OK) return st;
@@ -1325,6 +1329,7 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
     mo = mc;          // unused
   }
   a.n_rows = (int)n_rows; a.n_cols = (int)n_cols; a.d = d;
+  a.rows_per_batch = (int)(n_rows / n_batch); a.cols_per_batch = (int)(n_cols / n_batch);
   a.cols_per_split = sw.cols_per_split;
   a.scale_log2 = inv_t * kLog2e;
   a.rows_u32 = reinterpret_cast<const uint32_t*>(rows);
@@ -1332,9 +1337,9 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
   { const char* e = getenv("SLCL_P2P_PROF"); a.prof = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
   const size_t smem = smem_bytes_for(d);
-  if (sw.cluster == 4) return launch_one<4, MODE>(mr, mc, mo, a, sw, smem, stream);
-  if (sw.cluster == 2) return launch_one<2, MODE>(mr, mc, mo, a, sw, smem, stream);
-  return launch_one<1, MODE>(mr, mc, mo, a, sw, smem, stream);
+  if (sw.cluster == 4) return launch_one<4, MODE>(mr, mc, mo, a, sw, smem, n_batch, stream);
+  if (sw.cluster == 2) return launch_one<2, MODE>(mr, mc, mo, a, sw, smem, n_batch, stream);
+  return launch_one<1, MODE>(mr, mc, mo, a, sw, smem, n_batch, stream);
 }
 
 // State the analytic forward leaves for the backward (slcl_p2p_state_bytes): one caller-owned buffer.
@@ -1420,6 +1425,13 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
 bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t dp) {
   return a && b && na > 0 && m > 0 && dp >= KCH && dp <= kMaxD && dp % KCH == 0 && na < (int64_t)INT_MAX - BM &&
          m < (int64_t)INT_MAX - BM && aligned16(a) && aligned16(b);
+}
+
+// block-diagonal batching (general sweeps only): equal batches whose row / column ranges are whole tiles
+bool batches_ok(int64_t na, int64_t m, int n_class, int n_batch) {
+  if (n_batch == 1) return true;
+  return n_batch > 1 && n_batch <= 65535 && n_class == 0 && na % n_batch == 0 && m % n_batch == 0 && (na / n_batch) % BM == 0 &&
+         (m / n_batch) % BM == 0;
 }
 
 int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks partials
@@ -1515,7 +1527,7 @@ extern "C" size_t slcl_p2p_state_bytes(int64_t n_anchor, int64_t dim_padded) {
 }
 
 extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
-                            const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class,
+                            const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol, int n_class, int n_batch,
                             const float* shift, const float* weight, float temperature, float* stats, float* loss,
                             void* bwd_state, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
@@ -1523,6 +1535,7 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     return SLCL_ERR_INVALID_ARGUMENT;
   if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (!batches_ok(n_anchor, n_contrast, n_class, n_batch)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
@@ -1540,10 +1553,10 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     if (st != SLCL_OK) return st;
     return check_launch("slcl_p2p_fwd");
   }
-  Sweep sw = plan_sweep(n_anchor, n_contrast);
+  Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
   P2PArgs args{};
   args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
-  int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
+  int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream, n_batch);
   if (st != SLCL_OK) return st;
   const int nb = ceil_div(na, 256);
   launch_pdl(p2p_reduce_stats_kernel, dim3(nb), dim3(256), 0, stream, w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats,
@@ -1554,15 +1567,16 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
 
 extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_anchor, int64_t n_contrast, int64_t dim_padded,
                             int64_t dim, const int32_t* a_meta, const int32_t* b_meta, const int32_t* a_selfcol,
-                            const int32_t* b_selfrow, int n_class, const float* shift, const float* weight, float temperature,
-                            const float* stats, const void* bwd_state, const float* grad_out, float* d_a, float* d_b,
-                            void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+                            const int32_t* b_selfrow, int n_class, int n_batch, const float* shift, const float* weight,
+                            float temperature, const float* stats, const void* bwd_state, const float* grad_out, float* d_a,
+                            float* d_b, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
       !grad_out || !workspace || !(temperature > 0.f) || dim <= 0 || dim > dim_padded || (!d_a && !d_b) || n_class < 0 ||
       n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
   if ((a_selfcol == nullptr) != (b_selfrow == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
   if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (!batches_ok(n_anchor, n_contrast, n_class, n_batch)) return SLCL_ERR_INVALID_ARGUMENT;
   if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
   if (workspace_bytes < slcl_p2p_workspace_bytes(n_anchor, n_contrast, dim_padded) || !aligned16(workspace))
@@ -1610,20 +1624,20 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   launch_pdl(p2p_anchor_stat_kernel, dim3(ceil_div(na + BN, 256)), dim3(256), 0, stream, stats, shift, weight, grad_out, na,
              (int)align_up((size_t)na, BN), inv_t, w.anchor_stat);
   if (d_a) {
-    Sweep sw = plan_sweep(n_anchor, n_contrast);
+    Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
     P2PArgs args{};
     args.row_meta = am; args.col_meta = bm; args.row_stat = w.anchor_stat; args.grad_partial = w.grad_partial_a;
-    int st = launch_sweep<kGenRows>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream);
+    int st = launch_sweep<kGenRows>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream, n_batch);
     if (st != SLCL_OK) return st;
     const int64_t n = n_anchor * dim;
     launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_a, sw.splits,
                n, d, (int)dim, d_a);
   }
   if (d_b) {
-    Sweep sw = plan_sweep(n_contrast, n_anchor);
+    Sweep sw = plan_sweep(n_contrast / n_batch, n_anchor / n_batch, n_batch);
     P2PArgs args{};
     args.row_meta = bm; args.col_meta = am; args.col_stat = w.anchor_stat; args.grad_partial = w.grad_partial_b;
-    int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
+    int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream, n_batch);
     if (st != SLCL_OK) return st;
     const int64_t n = n_contrast * dim;
     launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_b, sw.splits,

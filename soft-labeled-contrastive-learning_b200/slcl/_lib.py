@@ -72,9 +72,10 @@ SIGNATURES = {
     "slcl_entropy_map": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P]),
     "slcl_p2p_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "slcl_p2p_state_bytes": (_SZ, [_I64, _I64]),
-    "slcl_p2p_fwd": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _SZ, _P]),
-    "slcl_p2p_bwd": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P,
-                               _P, _P, _SZ, _P]),
+    "slcl_p2p_fwd": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _SZ,
+                               _P]),
+    "slcl_p2p_bwd": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P,
+                               _P, _P, _P, _SZ, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

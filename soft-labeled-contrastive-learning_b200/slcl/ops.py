@@ -508,7 +508,7 @@ def _selfcol_check(t: Optional[Tensor], n: int, what: str):
 @torch.library.custom_op("slcl::p2p_fwd", mutates_args=(), device_types="cuda")
 def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
             temperature: float, n_class: int = 0, a_selfcol: Optional[Tensor] = None,
-            keep_state: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+            keep_state: bool = False, n_batch: int = 1) -> Tuple[Tensor, Tensor, Tensor]:
     """-> (loss[1], stats[A,3], state): ``state`` is the opaque uint8 buffer for p2p_bwd (empty unless
     n_class > 0 -- analytic mode, include/slcl.h -- and keep_state)."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight)
@@ -525,7 +525,7 @@ def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor,
     state = torch.empty(lib.slcl_p2p_state_bytes(na, dp) if keep else 0, dtype=torch.uint8, device=dev)
     ws = _ws(lib.slcl_p2p_workspace_bytes(na, m, dp), dev)
     with _guard(dev):
-        st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class),
+        st = lib.slcl_p2p_fwd(ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class), int(n_batch),
                               ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature), ptr(stats), ptr(loss),
                               ptr(state) if keep else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_p2p_fwd")
@@ -533,7 +533,7 @@ def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor,
 
 
 @p2p_fwd.register_fake
-def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, keep_state=False):
+def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, keep_state=False, n_batch=1):
     return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), torch.empty(0, dtype=torch.uint8, device=a.device))
 
 
@@ -541,7 +541,7 @@ def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=Non
 def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shift: Tensor, weight: Tensor,
             temperature: float, stats: Tensor, grad_out: Tensor, need_a: bool, need_b: bool, n_class: int = 0,
             a_selfcol: Optional[Tensor] = None, b_selfrow: Optional[Tensor] = None,
-            state: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+            state: Optional[Tensor] = None, n_batch: int = 1) -> Tuple[Tensor, Tensor]:
     """-> (d_a [A, dim], d_b [M, dim]) fp32 (empty when not needed)."""
     dev = require_cuda(a, b, a_meta, b_meta, shift, weight, stats, grad_out)
     lib = _lib.load()
@@ -561,7 +561,7 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
     g = grad_out.to(_F32).reshape(1).contiguous()
     with _guard(dev):
         st = lib.slcl_p2p_bwd(ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
-                              int(n_class), ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature),
+                              int(n_class), int(n_batch), ptr(shift.contiguous()), ptr(weight.contiguous()), float(temperature),
                               ptr(stats.contiguous()), ptr(state), ptr(g),
                               ptr(d_a) if need_a else None, ptr(d_b) if need_b else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_p2p_bwd")
@@ -570,7 +570,7 @@ def p2p_bwd(a: Tensor, b: Tensor, dim: int, a_meta: Tensor, b_meta: Tensor, shif
 
 @p2p_bwd.register_fake
 def _(a, b, dim, a_meta, b_meta, shift, weight, temperature, stats, grad_out, need_a, need_b, n_class=0, a_selfcol=None,
-      b_selfrow=None, state=None):
+      b_selfrow=None, state=None, n_batch=1):
     return (shift.new_empty((a.shape[0] if need_a else 0, dim)), shift.new_empty((b.shape[0] if need_b else 0, dim)))
 
 

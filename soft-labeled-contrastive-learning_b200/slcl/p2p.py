@@ -27,7 +27,7 @@ class _P2PLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, idx_a, idx_b, meta_a, meta_b, weight, temperature, normalize, same_rows, n_class, selfcol,
-                selfrow):
+                selfrow, n_batch):
         fm = feat.detach().contiguous()
         c = fm.shape[1]
         b_bf16, _, inv_b = _ops.gather_unit_rows(fm, idx_b, normalize, True, False)
@@ -40,31 +40,34 @@ class _P2PLoss(torch.autograd.Function):
         else:   # upper bound of S_ij: |a_i| max_j |b_j| / T
             shift = (1.0 / inv_a) * ((1.0 / inv_b).amax() / temperature)
         keep = n_class > 0 and ctx.needs_input_grad[0]
-        loss, stats, state = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol, keep)
+        loss, stats, state = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol, keep,
+                                          n_batch)
         ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state,
                               selfcol, selfrow)
-        ctx.cfg = (temperature, normalize, same_rows, c, n_class)
+        ctx.cfg = (temperature, normalize, same_rows, c, n_class, n_batch)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
         (fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state, selfcol,
          selfrow) = ctx.saved_tensors
-        temperature, normalize, same_rows, c, n_class = ctx.cfg
+        temperature, normalize, same_rows, c, n_class, n_batch = ctx.cfg
         if not ctx.needs_input_grad[0]:
-            return (None,) * 12
+            return (None,) * 13
         d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
-                                grad_out.reshape(1), True, True, n_class, selfcol, selfrow, state)
+                                grad_out.reshape(1), True, True, n_class, selfcol, selfrow, state, n_batch)
         dfeat = torch.zeros_like(fm)
         _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
         _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
-        return (dfeat,) + (None,) * 11
+        return (dfeat,) + (None,) * 12
 
 
 def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False, n_class=0,
-             selfcol=None, selfrow=None):
+             selfcol=None, selfrow=None, n_batch=1):
     """``same_rows``: anchors and contrast rows are the same gathered rows (one gather); their labels may
     still differ (ISCL compares query labels with the anchors' dominant labels).
+    ``n_batch`` > 1: block-diagonal batches -- rows [z R/n, (z+1) R/n) of both sides only see each other (general mode,
+    R/n a multiple of 128).
     ``n_class`` in 1..8: labels are class indices in [0, n_class) and ids are unique -> analytic sweeps; the
     self-pair maps are derived from the ids unless given."""
     meta_a = ops.pad_meta(lab_a, id_a)
@@ -76,7 +79,7 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
         else:
             selfcol, selfrow = ops.self_maps(id_a, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
-                          float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow)
+                          float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow, int(n_batch))
 
 
 def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch.Tensor, device) -> torch.Tensor:
@@ -160,12 +163,19 @@ class BlockConLoss(nn.Module):
         super().__init__()
         self.block_size = block_size
         self.supconloss = SupConLoss(temperature=temperature, n_class=n_class)
+        self.batched = True             # all tiles as one block-diagonal problem where the shape allows (False: per-tile loop)
 
     def forward(self, features, labels=None):
         dev = features.device
         bs = self.block_size
         div = features.shape[-1] // bs                                               # :426-428
         t = self.supconloss.temperature
+        if div == 0:
+            return torch.zeros((), device=dev)
+        if self.batched and features.ndim == 5 and self.supconloss.n_class == 0:
+            b, v = features.shape[:2]
+            if (b * v * bs * bs) % 128 == 0:
+                return self._forward_batched(features, labels, div, t)
         losses, flags = [], []
         for i in range(div):
             for j in range(div):
@@ -175,13 +185,38 @@ class BlockConLoss(nn.Module):
                                       n_class=self.supconloss.n_class))
                 if labels is not None:
                     flags.append((labels[:, :, i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] != 0).any())
-        if not losses:
-            return torch.zeros((), device=dev)
         stacked = torch.stack(losses)
         if labels is None:
             return stacked.mean()                                                    # :465
         keep = torch.stack(flags).float()
         return (stacked * keep).sum() / keep.sum().clamp_min(1.0)                    # :445-448 (0 when every tile is skipped)
+
+    def _forward_batched(self, features, labels, div, t):
+        """All div x div tiles as ONE block-diagonal problem (one launch per tensor-core sweep instead of div^2
+        separate SupCon calls): rows are ordered (tile, view, image, y, x); the per-tile weighting of :445-448 /
+        :465 -- fg_i / sum_tile fg, averaged over the tiles that have foreground -- is folded into the row weights."""
+        b, v, c, h, w = features.shape
+        dev = features.device
+        bs = self.block_size
+        fmap = features.reshape(b * v, c, h, w)
+        ar = torch.arange(bs, device=dev)
+        ti = torch.arange(div, device=dev)
+        ys = (ti.view(-1, 1) * bs + ar.view(1, -1))                                  # [div, bs]
+        grid = (ys.view(div, 1, bs, 1) * w + ys.view(1, div, 1, bs)).reshape(div * div, bs * bs)      # [tiles, bs*bs]
+        img = (torch.arange(b, device=dev).view(1, -1) * v + torch.arange(v, device=dev).view(-1, 1)).reshape(-1)   # (v, b)
+        idx = (img.view(1, -1, 1) * (h * w) + grid.view(div * div, 1, bs * bs)).reshape(-1)           # (tile, v, b, y, x)
+        n_tiles, m_tile = div * div, b * v * bs * bs
+        ids = torch.arange(idx.numel(), device=dev, dtype=torch.int32)
+        if labels is not None:
+            lab = labels.reshape(-1)[idx].to(torch.int32)
+            fg = (lab != 0).float().view(n_tiles, m_tile)
+            tile_fg = fg.sum(1, keepdim=True)
+            keep = (tile_fg > 0).float()
+            weight = (fg / tile_fg.clamp_min(1.0) * keep / keep.sum().clamp_min(1.0)).reshape(-1)
+        else:
+            lab = (ids % (m_tile // v)).to(torch.int32)                               # same pixel of the tile, other views
+            weight = torch.full((idx.numel(),), 1.0 / (m_tile * n_tiles), device=dev)
+        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True, n_batch=n_tiles)
 
 
 def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,

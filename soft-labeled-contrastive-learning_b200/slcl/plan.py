@@ -110,11 +110,11 @@ class P2PPlan:
                       if n_class > 0 else None)
         self.ws = torch.empty(max(self.lib.slcl_p2p_workspace_bytes(na, m, dp), 256), dtype=torch.uint8, device=self.dev)
         t = C.c_float(float(temperature))
-        self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class), ptr(shift),
+        self._fwd_args = (ptr(a), ptr(b), na, m, dp, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), int(n_class), 1, ptr(shift),
                           ptr(weight), t, ptr(self.stats), ptr(self.loss), ptr(self.state), ptr(self.ws), self.ws.numel())
-        self._fwd_only_args = self._fwd_args[:14] + (None,) + self._fwd_args[15:]
+        self._fwd_only_args = self._fwd_args[:15] + (None,) + self._fwd_args[16:]
         self._bwd_args = (ptr(a), ptr(b), na, m, dp, dim, ptr(a_meta), ptr(b_meta), ptr(a_selfcol), ptr(b_selfrow),
-                          int(n_class), ptr(shift), ptr(weight), t, ptr(self.stats), ptr(self.state), ptr(self.grad_out),
+                          int(n_class), 1, ptr(shift), ptr(weight), t, ptr(self.stats), ptr(self.state), ptr(self.grad_out),
                           ptr(self.d_a), ptr(self.d_b), ptr(self.ws), self.ws.numel())
         self.flops = 8.0 * na * m * dp
         self.graph = None

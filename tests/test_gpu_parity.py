@@ -473,6 +473,31 @@ def test_kat7_local_and_block_con_loss(api, golden):
     assert loss_mod.BlockConLoss(.7, 32)(f, zero).item() == 0.0
 
 
+@pytest.mark.parametrize("b,v,c,hw,bs,labelled", [
+    (1, 2, 32, 64, 32, True),        # 4 tiles of 2048 rows: the block-diagonal batched sweeps
+    (2, 2, 24, 48, 16, True),        # 9 tiles of 1024 rows, some all-background tiles
+    (1, 2, 16, 64, 32, False),       # unlabelled: other views are the positives
+    (1, 2, 16, 36, 12, True),        # 288 rows per tile (not a multiple of 128): the per-tile loop
+])
+def test_block_con_loss_vs_oracle(api, b, v, c, hw, bs, labelled):
+    """BlockConLoss (utils/loss.py:416-466): all tiles as one block-diagonal problem (or the per-tile loop when a tile
+    is not a whole number of 128-row tiles) against the oracle's per-tile evaluation, loss and gradient."""
+    loss_mod, _ = api
+    gen = cases.g(800 + hw + bs)
+    f5 = F.normalize(torch.randn(b, v, c, hw, hw, generator=gen), dim=2)
+    lab = torch.randint(0, 4, (b, v, hw, hw), generator=gen) if labelled else None
+    if labelled:
+        lab[..., :bs, :bs] = 0                                          # one all-background tile: skipped (:439-440)
+    fo = f5.clone().requires_grad_(True)
+    ref = O.block_con_loss(fo, lab, 0.7, bs)
+    ref.backward()
+    f = f5.to(dev()).requires_grad_(True)
+    out = loss_mod.BlockConLoss(0.7, bs)(f, lab.to(dev()) if labelled else None)
+    out.backward()
+    close(out, ref, rtol=P2P_RTOL)
+    grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+
+
 def test_supcon_unnormalised_features_vs_oracle(api):
     """SupConLoss does not normalise (utils/loss.py:342-349): rows of norm ~2, T = 0.5 -> the exp shift matters."""
     loss_mod, _ = api
