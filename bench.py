@@ -540,6 +540,20 @@ def extra_kernels(dev, feats, labels, centres, peak):
         timed(lambda: op.class_sums(f5, None, p5, True, 0.0, part5, 2, k5)), (4 * c5 + 4 * k5 + 4) * n_px)
     add("cfg5 shape: centroid_bwd soft P=2 C32 K4 (dF + dP)",
         timed(lambda: op.centroid_bwd(f5, None, p5, True, 0.0, part5, 2, k5, g5, s5, 1.0, True)), (8 * c5 + 8 * k5 + 4) * n_px)
+    # cfg4 geometry per GPU (MS-CMRSeg: 16 of the 128 images per GPU, C = 32, K = 4, 224 x 224): prototype loss fwd+bwd
+    from slcl.plan import ProtoPlan
+    f4 = f5[:16].contiguous()
+    lab4 = torch.randint(0, k5, (16 * h5 * h5,), device=dev, generator=gen)
+    sel4 = (torch.rand(16 * h5 * h5, device=dev, generator=gen) > 0.3).float()
+    cen4 = torch.randn(k5, c5, device=dev, generator=gen)
+    plan4 = ProtoPlan(f4, lab4, sel4, cen4, k5, CFG["temperature"], CFG["base_temperature"], CFG["margin"])
+
+    def proto4():
+        plan4.forward()
+        plan4.backward()
+    add("cfg4 shape per GPU: prototype loss fwd+bwd, 16 x 32 x 224 x 224, K4", timed(proto4, iters=20),
+        (12 * c5 + 24) * 16 * h5 * h5)
+    del f4, lab4, sel4, cen4, plan4
     # cfg3: sampled pixel<->pixel loss, 4096 anchors x 16384 contrast rows, d = 256, bf16 tensor cores
     del f5, p5, part5, lab5, g5, s5
     res.update(p2p_kernels(dev, gen))
