@@ -214,19 +214,9 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same with the A operand read from tensor memory (rows = lanes, bf16 pairs packed along K in 32-bit columns):
-// no per-instruction shared-memory fetch of the 128 A rows, so a narrow-N MMA runs at its N/2-cycle floor
+// D[tmem] (+)= A[tmem] * B[smem desc]; issued by ONE thread.  The A operand is read from tensor memory (rows = lanes,
+// bf16 pairs packed along K in 32-bit columns): no per-instruction shared-memory fetch of the 128 A rows, so a narrow-N
+// MMA runs at its N/2-cycle floor
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
