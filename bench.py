@@ -38,6 +38,7 @@ import torch  # noqa: E402
 
 METRIC = "SLCL loss fwd+bwd pixels/sec"
 UNIT = "pixels/s"
+E2E_CHUNK = int(os.environ.get("SLCL_E2E_CHUNK", "2"))      # images per pipeline chunk of the host-buffer path
 CFG = dict(B=32, C=128, H=256, W=256, K=5, temperature=0.1, base_temperature=1.0, margin=0.2, seed=1234)
 WORKLOAD = ("cfg2: SLCL prototype path (mpcl_loss_calc+MPCL fwd+bwd, target variant with pixel_sel_loc), "
             "B32 C128 256x256 K5 fp32 NCHW per GPU")
@@ -316,7 +317,7 @@ def run_slcl(args):
         def e2e_step():
             # public host-buffer API: chunked H2D -> fwd -> bwd -> D2H pipeline over 3 streams
             loss, _ = mpcl_loss_and_grad_host(feats_h, labels_h, centres, mp, pixel_sel_loc_h=sel_h, grad_out_h=grad_h,
-                                              device=dev, chunk_images=4, group=group)
+                                              device=dev, chunk_images=E2E_CHUNK, group=group)
             loss_h.copy_(loss, non_blocking=True)
 
         n_e2e = max(1, min(args.steps, 20))
@@ -338,7 +339,7 @@ def run_slcl(args):
         d2h = grad_h.numel() * 4 + 4
         e2e = {"value": world * n_px * n_e2e / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms / n_e2e,
-               "api": "slcl.host.mpcl_loss_and_grad_host(pinned feats/labels/sel -> loss, pinned dF): 4-image chunks, "
+               "api": f"slcl.host.mpcl_loss_and_grad_host(pinned feats/labels/sel -> loss, pinned dF): {E2E_CHUNK}-image chunks, "
                       "H2D / kernels / D2H overlapped on 3 streams",
                "loss": float(loss_h)}
         del grad_h
