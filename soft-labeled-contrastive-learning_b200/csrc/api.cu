@@ -18,6 +18,12 @@ int check_launch(const char* where) {
   return SLCL_ERR_CUDA;
 }
 
+int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
 int sm_count() {
   // cached per device (the only global state of the library)
   static int cached[64] = {0};

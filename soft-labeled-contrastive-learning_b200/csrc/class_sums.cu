@@ -898,7 +898,8 @@ int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(class sums)"); return SLCL_ERR_CUDA; }
   const size_t smem = v3_smem_bytes(KWT, CPW, p.n_cw);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};          // function attributes are per device
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          220 * 1024);

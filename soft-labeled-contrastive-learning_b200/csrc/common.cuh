@@ -20,6 +20,7 @@ constexpr int kNumSMsDefault = 148;
 void set_cuda_error(cudaError_t e, const char* where);
 int  check_launch(const char* where);     // returns SLCL_OK or SLCL_ERR_CUDA
 int  sm_count();                          // cached cudaDevAttrMultiProcessorCount of the current device
+int  current_device_slot();               // current CUDA device index clamped to [0, 64): index of per-device caches
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

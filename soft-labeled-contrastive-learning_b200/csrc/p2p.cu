@@ -1278,7 +1278,8 @@ int make_out_map(CUtensorMap* m, const float* ptr, int64_t n_cols, int64_t ld, i
 template <int CS, int MODE>
 int launch_one(const CUtensorMap& mr, const CUtensorMap& mc, const CUtensorMap& mo, const P2PArgs& a, const Sweep& sw, size_t smem,
                int n_batch, cudaStream_t stream) {
-  static bool attr_set = false;          // per instantiation
+  static bool attr_set_dev[64] = {};     // per instantiation and per device (function attributes are per device)
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(p2p_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(kMaxD));
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p_kernel)"); return SLCL_ERR_CUDA; }
@@ -1430,7 +1431,8 @@ int finish_blocks(int64_t rows) {          // forward finish: one warp per ancho
 }
 
 int big_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared memory (> the 48 KB default)
-  static bool done = false;
+  static bool done_dev[64] = {};
+  bool& done = done_dev[current_device_slot()];
   if (!done) {
     const int bytes = (int)(8 * kMaxLabelClasses * (kMaxD + 1) * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
