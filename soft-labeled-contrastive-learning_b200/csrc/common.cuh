@@ -40,6 +40,23 @@ __device__ __forceinline__ float  ld_stream1(const float* p) { return __ldcs(p);
 __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st_stream1(float* p, float v) { __stcs(p, v); }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while the kernel in front of it in the
+// stream is still running; it signals its own dependents right away (pdl_trigger) and waits for the kernel in front to
+// complete (pdl_wait) BEFORE it touches global memory.  Launch latency and block scheduling overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);        // errors surface through check_launch()
+}
+
 template <typename T>
 __host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -149,11 +149,7 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// Programmatic dependent launch: every p2p kernel is launched with programmatic stream serialization, signals its
-// dependents right away and waits for its predecessors before it touches global memory, so launch latency and
-// set-up (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of the kernel in front.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (pdl_trigger / pdl_wait / launch_pdl: common.cuh -- every p2p kernel uses programmatic dependent launch)
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -1225,18 +1221,6 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_r
     return SLCL_ERR_CUDA;
   }
   return SLCL_OK;
-}
-
-// launch with programmatic stream serialization (see pdl_wait above)
-template <typename... KArgs, typename... Args>
-void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);        // errors surface through check_launch()
 }
 
 struct Sweep { int row_tiles, splits, cols_per_split, cluster; };

@@ -224,6 +224,8 @@ __device__ __forceinline__ float margin_row(const float (&cosv)[K], const float 
 // ---------------------------------------------------------------------------
 template <int K, int VEC>
 __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINBLK : 1) proto_fwd_kernel(const ProtoArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sC[];
   __shared__ double red[2][kThreads / 32];
   const int C = (int)a.channels;
@@ -318,6 +320,8 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
 // scal = {loss, coefficient, weight sum, weighted row-loss sum}.
 __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2* partial, int n_blocks, int64_t n_total,
                                                                    int has_sel, float* scal) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[2][kThreads / 32];
   double l = 0.0, s = 0.0;
   for (int i = threadIdx.x; i < n_blocks; i += kThreads) { double2 p = partial[i]; l += p.x; s += p.y; }
@@ -340,6 +344,8 @@ __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2*
 // After a cross-rank all-reduce of scal[2..3] (weight sum, weighted row-loss sum):
 // recompute the global loss and coefficient in place.
 __global__ void proto_rescale_kernel(float* scal, int has_sel) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float coef = has_sel ? 1.0f / (scal[2] + 1e-4f) : 1.0f / scal[2];
     scal[0] = scal[3] * coef;
@@ -353,6 +359,8 @@ __global__ void proto_rescale_kernel(float* scal, int has_sel) {
 template <int K, int VEC>
 __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_BWD_MINBLK : 1) proto_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
                                                              float* dfeat) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sC[];
   const int C = (int)a.channels;
   load_centres_smem<K>(sC, a.cstate, C);
@@ -446,6 +454,8 @@ __global__ void __launch_bounds__(kThreads) pseudo_label_kernel(const ProtoArgs 
 // Unit centres + norms: cstate[k*C+c] = c_k[c] / max(||c_k||, 1e-12), cstate[K*C+k] = max(||c_k||, 1e-12).
 __global__ void __launch_bounds__(kThreads) prep_centres_kernel(const float* centres, int C, int K, int normalize,
                                                                 float* cstate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[kThreads / 32];
   __shared__ float s_norm;
   const int k = blockIdx.x;
@@ -592,13 +602,13 @@ extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const in
   a.partial = reinterpret_cast<double2*>(workspace);
   a.mc = make_const(params);
 
-  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, params->normalize, cstate);
+  launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, (int)map->channels, K, params->normalize, cstate);
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(proto_fwd_kernel<KK, VV>, plan.smem);
     if (st != SLCL_OK) return st;
-    proto_fwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a);
+    launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, sel != nullptr, scal);
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, (int)(sel != nullptr), scal);
   return check_launch("slcl_proto_fwd");
 }
 
@@ -620,19 +630,19 @@ extern "C" int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, c
   a.partial = reinterpret_cast<double2*>(workspace);
   a.mc = make_const(params);
   a.fused_target = 1; a.sel_threshold = sel_threshold; a.out_label = label; a.out_sel = sel;
-  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, 1, cstate);
+  launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, (int)map->channels, K, 1, cstate);
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(proto_fwd_kernel<KK, VV>, plan.smem);
     if (st != SLCL_OK) return st;
-    proto_fwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a);
+    launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  proto_finalize_kernel<<<1, kThreads, 0, stream>>>(a.partial, plan.n_blocks, plan.n_total, 1, scal);
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, 1, scal);
   return check_launch("slcl_proto_fwd_target");
 }
 
 extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream_) {
   if (!scal) return SLCL_ERR_INVALID_ARGUMENT;
-  proto_rescale_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(scal, has_sel);
+  launch_pdl(proto_rescale_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream_, scal, has_sel);
   return check_launch("slcl_proto_rescale");
 }
 
@@ -651,7 +661,7 @@ extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const fl
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(proto_bwd_kernel<KK, VV>, plan.smem);
     if (st != SLCL_OK) return st;
-    proto_bwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a, scal, grad_out, dfeat);
+    launch_pdl(proto_bwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a, scal, grad_out, dfeat);
   })
   return check_launch("slcl_proto_bwd");
 }
@@ -669,7 +679,7 @@ extern "C" int slcl_pseudo_label(const float* feat, const slcl_map_t* map, const
   Plan plan = make_plan(map, K, {feat, label, sel});
   ProtoArgs a = base_args(feat, map, cstate);
   a.out_label = label; a.out_sel = sel; a.sel_threshold = threshold;
-  prep_centres_kernel<<<K, kThreads, 0, stream>>>(centres, (int)map->channels, K, 1, cstate);
+  launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, (int)map->channels, K, 1, cstate);
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(pseudo_label_kernel<KK, VV>, plan.smem);
     if (st != SLCL_OK) return st;
