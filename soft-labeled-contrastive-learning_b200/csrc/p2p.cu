@@ -993,7 +993,8 @@ __global__ void __launch_bounds__(256) p2p_final_reduce_kernel(const float* ab_p
 //   P_raw  = a_i . Bsum[lab_i] - [labels agree] S_i,self        n_i = count[lab_i] - [labels agree]
 //   U_i    = sum_splits U_partial - bf16(e_self) b_self         (the sweep multiplied bf16-rounded exponentials)
 //   block partial of  sum_i w_i (shift_i + log Zs_i - P_raw_i / (T n_i))                  (utils/loss.py:371-386)
-__global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_partial, int n_slots, int n_rows, const float* shift,
+constexpr int kFinWarps = 32;          // warps (= anchors in flight) per block of the forward finish
+__global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const float* zs_partial, int n_slots, int n_rows, const float* shift,
                                                              const float* weight, float inv_t, const __nv_bfloat16* a,
                                                              const __nv_bfloat16* b, int d, const int2* a_meta,
                                                              const int2* b_meta, const int32_t* a_selfcol,
@@ -1006,20 +1007,27 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
   // With u_out (the forward keeps state for the backward) the kernel also writes the per-anchor constants
   //   alpha~_i = w_i / (T Zs_i),  beta~_i = w_i / (T n_i) (0 when n_i == 0),  colshift_i = shift_i log2e - log2 alpha~_i
   // and stage 1 of ABsum[k] = sum_{lab_i = k} beta~_i a_i  (block partials; p2p_final_reduce_kernel is stage 2).
-  extern __shared__ float sm_ff[];                 // keep-state mode: [8 warps][K][d] + [8][K]
-  float* s_sum = sm_ff;
-  float* s_cnt = sm_ff + (size_t)8 * n_class * d;
+  // ABsum: every warp parks beta~_i a_i of its anchor in shared memory, then the block adds the parked rows into its
+  // per-class table in warp order (fixed order, no atomics); one table per block -> few partials for stage 2.
+  extern __shared__ float sm_ff[];                 // keep-state mode: rows [kFinWarps][d], table [K][d]
+  float* s_rows = sm_ff;
+  float* s_tab = sm_ff + (size_t)kFinWarps * d;
+  __shared__ int s_lab[kFinWarps];
+  __shared__ float s_be[kFinWarps];
+  __shared__ float s_cnt[kMaxLabelClasses];
   const bool keep = u_out != nullptr;
   if (keep) {
-    for (int idx = threadIdx.x; idx < 8 * n_class * d; idx += 256) s_sum[idx] = 0.f;
-    if (threadIdx.x < 8 * n_class) s_cnt[threadIdx.x] = 0.f;
-    if (blockIdx.x == 0) for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 256) colshift_out[r] = kShiftOff;
-    __syncthreads();
+    for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) s_tab[idx] = 0.f;
+    if ((int)threadIdx.x < n_class) s_cnt[threadIdx.x] = 0.f;
+    if (blockIdx.x == 0) for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 32 * kFinWarps) colshift_out[r] = kShiftOff;
   }
-  __shared__ double red[8];
+  __shared__ double red[kFinWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
-  for (int i = blockIdx.x * 8 + warp; i < n_rows; i += gridDim.x * 8) {
+  for (int base = blockIdx.x * kFinWarps; base < n_rows; base += gridDim.x * kFinWarps) {
+    const int i = base + warp;
+    if (keep) s_lab[warp] = -1;                    // (warp-private slot; rewritten below when the anchor takes part)
+    if (i < n_rows) {
     const __nv_bfloat16* ai = a + (size_t)i * d;
     const int lab = a_meta[i].x;
     const int sc = a_selfcol ? a_selfcol[i] : -1;
@@ -1081,9 +1089,11 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
         colshift_out[i] = al > 0.f ? shift[i] * kLog2e - log2f(al) : kShiftOff;
       }
       if (lab_ok) {
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (lane * 8 < d) x = __ldg(reinterpret_cast<const uint4*>(ai) + lane);
-        label_table_add(s_sum + (size_t)warp * n_class * d, s_cnt + warp * n_class, d, lab, be, x, lane);
+        for (int c = lane * 2; c < d; c += 64) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
+          *reinterpret_cast<float2*>(s_rows + (size_t)warp * d + c) = make_float2(be * x.x, be * x.y);
+        }
+        if (lane == 0) { s_lab[warp] = lab; s_be[warp] = be; }
       }
     }
     if (lane == 0) {
@@ -1091,16 +1101,35 @@ __global__ void __launch_bounds__(256) p2p_finish_fwd_kernel(const float* zs_par
       const float li = shift[i] + logf(zs) - (praw * inv_t) / n;      // n == 0 -> NaN, as 0/0 in the reference (:376-380)
       acc += (double)(weight[i] * li);
     }
+    }
+    if (keep) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) {
+        const int k = idx / d, c = idx - k * d;
+        float t = s_tab[idx];
+#pragma unroll 8
+        for (int w = 0; w < kFinWarps; ++w)
+          if (s_lab[w] == k) t += s_rows[(size_t)w * d + c];
+        s_tab[idx] = t;
+      }
+      if ((int)threadIdx.x < n_class) {
+        float t = s_cnt[threadIdx.x];
+        for (int w = 0; w < kFinWarps; ++w)
+          if (s_lab[w] == (int)threadIdx.x) t += s_be[w];
+        s_cnt[threadIdx.x] = t;
+      }
+      __syncthreads();
+    }
   }
   if (keep) {
-    __syncthreads();
-    label_tables_flush(s_sum, s_cnt, n_class, d, ab_partial, ab_cnt);
+    for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) ab_partial[(size_t)blockIdx.x * n_class * d + idx] = s_tab[idx];
+    if ((int)threadIdx.x < n_class) ab_cnt[blockIdx.x * n_class + threadIdx.x] = s_cnt[threadIdx.x];
   }
   if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w];
+    for (int w = 0; w < kFinWarps; ++w) t += red[w];
     loss_partial[blockIdx.x] = t;
   }
 }
@@ -1410,7 +1439,7 @@ bool batches_ok(int64_t na, int64_t m, int n_class, int n_batch) {
 }
 
 int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks partials
-  const int64_t want = ceil_div<int64_t>(rows, 8);
+  const int64_t want = ceil_div<int64_t>(rows, kFinWarps);
   return (int)(want < kMaxFinishBlocks ? want : kMaxFinishBlocks);
 }
 
@@ -1477,7 +1506,7 @@ int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, cons
   if (side != stream) cudaStreamWaitEvent(stream, aux->join, 0);          // join even when the sweep failed to launch
   if (st != SLCL_OK) return st;
   const int nb = finish_blocks(na);
-  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(256), keep ? table_smem : 0, stream, w.stat_partial, 2 * sw.splits, (int)na,
+  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(32 * kFinWarps), keep ? (size_t)(kFinWarps + n_class) * d * sizeof(float) : 0, stream, w.stat_partial, 2 * sw.splits, (int)na,
              shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, bsum, n_class, w.grad_partial_a, sw.splits,
              keep ? state->u : nullptr, keep ? state->alpha : nullptr, keep ? state->beta : nullptr,
              keep ? state->colshift : nullptr, (int)align_up((size_t)na, BN), w.ab_partial, w.ab_cnt, stats, w.loss_partial);
