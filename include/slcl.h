@@ -247,8 +247,10 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *   shift  [A] fp32: any upper bound of S_ij over j (e.g. ||a_i|| max_j||b_j|| / T);
  *     exponentials are evaluated as exp(S - shift), the result is shift-invariant.
  *   weight [A] fp32: w_i of the final reduction (fg_i / sum fg, :382-384, or 1/A).
- *   n_class: 0 = general labels (any int32; self pairs and positives are tested per element from
- *     the {label, id} pairs; a_selfcol / b_selfrow / u / label_sums must be null).
+ *   n_class: 0 = general labels (any int32; positives are tested per element from the labels; self pairs are found by
+ *     comparing ids per element, or -- when a_selfcol / b_selfrow are given (unique ids) -- treated as ordinary pairs in
+ *     the sweeps and removed afterwards; warps whose 32 columns carry one label then skip all per-element integer work,
+ *     so sorting the contrast rows by label pays).  bwd_state must be null.
  *     1..8 = "analytic" mode for class-index labels in [0, n_class) and UNIQUE ids, weights >= 0: the
  *     positive-pair terms are rank-n_class and are evaluated outside the tensor-core sweeps from per-class row
  *     sums, the self pair is removed afterwards with one dot product per anchor.  The ids inside the meta arrays

@@ -82,6 +82,8 @@ struct P2PArgs {
   int rows_per_batch, cols_per_batch; // block-diagonal batches (grid.z): batch z contrasts rows [z rpb, (z+1) rpb) with columns
                                       // [z cpb, (z+1) cpb) only; rpb % 128 == 0 and cpb % 64 == 0.  One batch: the whole problem.
   float scale_log2;                   // log2(e) / T
+  int self_by_id;                     // general modes: 1 = self pairs found by comparing ids per element; 0 = the caller gave
+                                      // self maps (unique ids): the sweep treats them as ordinary pairs, they are removed afterwards
   const uint32_t* rows_u32;           // resident operand, bf16 row-major [n_rows, d] viewed as 32-bit words
   const int2* row_meta;               // general modes: {label, id}
   const int2* col_meta;
@@ -571,6 +573,14 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
         if (lane == 0) mbar_arrive(&bars->s_empty[buf]);
       }
       uint32_t packed[16];
+      // general modes with self maps: is this warp's half tile label-uniform?  (one shared load, a shuffle and a vote)
+      bool gen_fast = false, gen_same = false;
+      if ((MODE == kGenFwd || MODE == kGenRows || MODE == kGenCols) && !a.self_by_id) {
+        const int my_col_label = cmeta.meta[half * 32 + lane].x;
+        const int tile_label = __shfl_sync(0xffffffffu, my_col_label, 0);
+        gen_fast = __all_sync(0xffffffffu, my_col_label == tile_label);
+        gen_same = rm.x == tile_label;
+      }
 
       if (MODE == kAnaFwd || MODE == kAnaFwdU) {
         // e = exp2(s * scale - shift): four independent accumulation chains
@@ -595,26 +605,57 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           packed[(jj >> 1) + 1] = pack_bf16x2(e2, e3);
         }
       } else if (MODE == kGenFwd) {
+        if (gen_fast) {
+          // label-uniform half tile (the caller sorted the contrast rows by label) and no id tests: FFMA + EX2 + 2 FADD
+          float tsum = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int2 cm = cmeta.meta[half * 32 + jj];
-          const float s = __uint_as_float(v[jj]);
-          const float e = ex2_approx(fmaf(s, a.scale_log2, -rs.x));
-          // predicated adds spelled out in PTX: 2 compares + 3 predicated FADDs, no selects, no branches
-          asm("{\n\t"
-              ".reg .pred pv, pp;\n\t"
-              "setp.ne.s32 pv, %5, %6;\n\t"
-              "setp.eq.and.s32 pp, %7, %8, pv;\n\t"
-              "@pv add.f32 %0, %0, %3;\n\t"
-              "@pp add.f32 %1, %1, %4;\n\t"
-              "@pp add.f32 %2, %2, 0f3F800000;\n\t"
-              "}\n"
-              : "+f"(zs[0]), "+f"(praw), "+f"(npos)
-              : "f"(e), "f"(s), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
+          for (int jj = 0; jj < 32; ++jj) {
+            const float sv = __uint_as_float(v[jj]);
+            zs[jj & 3] += ex2_approx(fmaf(sv, a.scale_log2, -rs.x));
+            tsum += sv;
+          }
+          if (gen_same) { praw += tsum; npos += 32.f; }
+        } else {
+          const int rid = a.self_by_id ? rm.y : INT_MIN + 2;      // self maps given: never equal to a column id
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int2 cm = cmeta.meta[half * 32 + jj];
+            const float s = __uint_as_float(v[jj]);
+            const float e = ex2_approx(fmaf(s, a.scale_log2, -rs.x));
+            // predicated adds spelled out in PTX: 2 compares + 3 predicated FADDs, no selects, no branches
+            asm("{\n\t"
+                ".reg .pred pv, pp;\n\t"
+                "setp.ne.s32 pv, %5, %6;\n\t"
+                "setp.eq.and.s32 pp, %7, %8, pv;\n\t"
+                "@pv add.f32 %0, %0, %3;\n\t"
+                "@pp add.f32 %1, %1, %4;\n\t"
+                "@pp add.f32 %2, %2, 0f3F800000;\n\t"
+                "}\n"
+                : "+f"(zs[0]), "+f"(praw), "+f"(npos)
+                : "f"(e), "f"(s), "r"(cm.y), "r"(rid), "r"(cm.x), "r"(rm.x));
+          }
+        }
+      } else if (gen_fast) {
+        // general backward on a label-uniform half tile: G = alpha e - [row label == tile label] beta, no integer work
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+          float g2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float sh = rs.x, al = rs.y, be = rs.z;
+            if (MODE == kGenCols) {
+              const float4 st = cmeta.stat[half * 32 + jj + u];
+              sh = st.x; al = st.y; be = st.z;
+            }
+            const float e = ex2_approx(fmaf(__uint_as_float(v[jj + u]), a.scale_log2, -sh));
+            g2[u] = fmaf(al, e, gen_same ? -be : 0.f);
+          }
+          packed[jj >> 1] = pack_bf16x2(g2[0], g2[1]);
         }
       } else {
         // general backward: G = alpha e - [same label] beta, zero for the self pair.  The statistics
         // {shift, alpha, beta} belong to the row (dA sweep) or to the column (dB sweep).
+        const int rid = a.self_by_id ? rm.y : INT_MIN + 2;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 2) {
           float g2[2];
@@ -638,7 +679,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
                 "@!pv mov.f32 %0, 0f00000000;\n\t"
                 "}\n"
                 : "=&f"(g)
-                : "f"(al), "f"(e), "f"(be), "r"(cm.y), "r"(rm.y), "r"(cm.x), "r"(rm.x));
+                : "f"(al), "f"(e), "f"(be), "r"(cm.y), "r"(rid), "r"(cm.x), "r"(rm.x));
             g2[u] = g;
           }
           packed[jj >> 1] = pack_bf16x2(g2[0], g2[1]);
@@ -819,17 +860,89 @@ __global__ void p2p_anchor_stat_kernel(const float* stats, const float* shift, c
   out[i] = make_float4(shift[i] * kLog2e, gw / stats[3 * i], gw / stats[3 * i + 2], 0.f);
 }
 
-__global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64_t n_elems, int d_pad, int d, float* out) {
+// out[r][c] = sum over splits of partial[s][r][c]  (-  g_self * other[c] when the caller gave self maps: the sweep treated
+// the self pair as an ordinary pair)
+//   dA sweep: rows are anchors:       other row = b[a_selfcol[r]],  g_self = gself[r]
+//   dB sweep: rows are contrast rows: anchor m = b_selfrow[r], other row = a[m], g_self = gself[m]
+__global__ void p2p_reduce_grad_kernel(const float* partial, int n_splits, int64_t n_elems, int d_pad, int d, float* out,
+                                       const float* gself, const int32_t* self_map, const __nv_bfloat16* other,
+                                       int rows_are_anchors) {
   pdl_trigger();
   pdl_wait();
-  // partial: [splits][rows][d_pad] -> out [rows][d]
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_elems) return;
   const int64_t r = idx / d, c = idx % d;
   float t = 0.f;
   const int64_t stride = (n_elems / d) * d_pad;
   for (int s = 0; s < n_splits; ++s) t += partial[(size_t)s * stride + r * d_pad + c];
+  if (self_map != nullptr) {
+    const int m = self_map[r];
+    if (m >= 0) t -= (rows_are_anchors ? gself[r] : gself[m]) * __bfloat162float(other[(size_t)m * d_pad + c]);
+  }
   out[idx] = t;
+}
+
+// General sweeps with self maps, forward finish: one warp per anchor.  stats[i] = sum over slots (fixed order) minus the
+// self pair  S_ii = a_i . b_selfcol(i):  Zs -= exp(S_ii / T - shift);  labels agree -> P_raw -= S_ii, n -= 1.
+// Also the per-block partial of  sum_i w_i (shift_i + log Zs_i - P_raw_i / (T n_i))        (utils/loss.py:371-386)
+__global__ void __launch_bounds__(256) p2p_reduce_stats_self_kernel(const float* partial, int n_slots, int n_rows,
+                                                                    const float* shift, const float* weight, float inv_t,
+                                                                    const __nv_bfloat16* a, const __nv_bfloat16* b, int d,
+                                                                    const int2* a_meta, const int2* b_meta,
+                                                                    const int32_t* a_selfcol, float* stats,
+                                                                    double* loss_partial) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 8 + warp;
+  double acc = 0.0;
+  if (i < n_rows) {
+    float t[3] = {0.f, 0.f, 0.f};
+    for (int s = lane; s < n_slots; s += 32) {
+      const float* p = partial + ((size_t)s * n_rows + i) * 3;
+      t[0] += p[0]; t[1] += p[1]; t[2] += p[2];
+    }
+    t[0] = warp_sum(t[0]); t[1] = warp_sum(t[1]); t[2] = warp_sum(t[2]);
+    const int sc = a_selfcol[i];
+    if (sc >= 0) {
+      const float s_self = warp_dot_bf16(a + (size_t)i * d, b + (size_t)sc * d, d, lane);
+      t[0] -= ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
+      if (a_meta[i].x == b_meta[sc].x) { t[1] -= s_self; t[2] -= 1.f; }
+    }
+    if (lane == 0) {
+      stats[3 * i] = t[0]; stats[3 * i + 1] = t[1]; stats[3 * i + 2] = t[2];
+      const float li = shift[i] + logf(t[0]) - (t[1] * inv_t) / t[2];     // n == 0 -> NaN, as 0/0 in the reference (:376-380)
+      acc = (double)(weight[i] * li);
+    }
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt = 0.0;
+    for (int w = 0; w < 8; ++w) tt += red[w];
+    loss_partial[blockIdx.x] = tt;
+  }
+}
+
+// Self-pair entry of the gradient tile, exactly as the sweeps formed it (bf16-rounded):
+// g_self[i] = bf16(alpha_i exp(S_ii / T - shift_i) - [labels agree] beta_i), 0 when anchor i has no self column.
+__global__ void __launch_bounds__(256) p2p_gself_kernel(const float4* anchor_stat, float scale_log2, const __nv_bfloat16* a,
+                                                        const __nv_bfloat16* b, int d, const int2* a_meta, const int2* b_meta,
+                                                        const int32_t* a_selfcol, int n_rows, float* gself) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int sc = a_selfcol[i];
+  float g = 0.f;
+  if (sc >= 0) {
+    const float s_self = warp_dot_bf16(a + (size_t)i * d, b + (size_t)sc * d, d, lane);
+    const float4 st = anchor_stat[i];
+    g = bf16_round(fmaf(st.y, ex2_approx(fmaf(s_self, scale_log2, -st.x)), (a_meta[i].x == b_meta[sc].x) ? -st.z : 0.f));
+  }
+  if (lane == 0) gself[i] = g;
 }
 
 // ---- analytic path ----------------------------------------------------------
@@ -1383,7 +1496,8 @@ struct P2PWs {
   float* ab_cnt;
   float* bsum;             // [K][d+1]   (forward without state)
   float* stats_scratch;    // [Na][3]    (backward without state)
-  double* loss_partial;    // [kMaxFinishBlocks]
+  float* gself;            // [Na]       (general sweeps with self maps)
+  double* loss_partial;    // [max(kMaxFinishBlocks, ceil(Na / 8))]
   void* state;             // backward without state: regenerated here
   int blocks_b;
   size_t total;
@@ -1396,7 +1510,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   P2PWs w;
   w.blocks_b = (int)ceil_div<int64_t>(m, kLabelRowsPerBlock);
   const size_t K = kMaxLabelClasses;
-  size_t o[12];
+  size_t o[13];
   o[0] = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
   o[1] = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
   o[2] = take((size_t)sa.splits * na * d * sizeof(float));
@@ -1407,8 +1521,10 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   o[7] = take((size_t)kMaxFinishBlocks * K * sizeof(float));
   o[8] = take(K * (d + 1) * sizeof(float));
   o[9] = take((size_t)na * 3 * sizeof(float));
-  o[10] = take((size_t)kMaxFinishBlocks * sizeof(double));
+  const int64_t n_loss_partial = ceil_div<int64_t>(na, 8) > kMaxFinishBlocks ? ceil_div<int64_t>(na, 8) : kMaxFinishBlocks;
+  o[10] = take((size_t)n_loss_partial * sizeof(double));
   o[11] = take(carve_state(nullptr, na, d).total);
+  o[12] = take((size_t)na * sizeof(float));
   char* b = reinterpret_cast<char*>(ws);
   w.stat_partial = reinterpret_cast<float*>(b + o[0]);
   w.anchor_stat = reinterpret_cast<float4*>(b + o[1]);
@@ -1422,6 +1538,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   w.stats_scratch = reinterpret_cast<float*>(b + o[9]);
   w.loss_partial = reinterpret_cast<double*>(b + o[10]);
   w.state = b + o[11];
+  w.gself = reinterpret_cast<float*>(b + o[12]);
   w.total = off;
   return w;
 }
@@ -1538,7 +1655,7 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   if (!p2p_args_ok(a_bf16, b_bf16, n_anchor, n_contrast, dim_padded) || !a_meta || !b_meta || !shift || !weight || !stats ||
       !loss || !workspace || !(temperature > 0.f) || n_class < 0 || n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
-  if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && bwd_state) return SLCL_ERR_INVALID_ARGUMENT;
   if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   if (!batches_ok(n_anchor, n_contrast, n_class, n_batch)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
@@ -1561,11 +1678,20 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
   P2PArgs args{};
   args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
+  args.self_by_id = a_selfcol == nullptr;
   int st = launch_sweep<kGenFwd>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream, n_batch);
   if (st != SLCL_OK) return st;
-  const int nb = ceil_div(na, 256);
-  launch_pdl(p2p_reduce_stats_kernel, dim3(nb), dim3(256), 0, stream, w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t, stats,
-             w.loss_partial);
+  int nb;
+  if (a_selfcol == nullptr) {
+    nb = ceil_div(na, 256);
+    launch_pdl(p2p_reduce_stats_kernel, dim3(nb), dim3(256), 0, stream, w.stat_partial, 2 * sw.splits, na, shift, weight, inv_t,
+               stats, w.loss_partial);
+  } else {
+    nb = ceil_div(na, 8);
+    launch_pdl(p2p_reduce_stats_self_kernel, dim3(nb), dim3(256), 0, stream, (const float*)w.stat_partial, 2 * sw.splits, na, shift,
+               weight, inv_t, reinterpret_cast<const __nv_bfloat16*>(a_bf16), reinterpret_cast<const __nv_bfloat16*>(b_bf16), d, am,
+               bm, a_selfcol, stats, w.loss_partial);
+  }
   launch_pdl(p2p_loss_kernel, dim3(1), dim3(256), 0, stream, w.loss_partial, nb, loss);
   return check_launch("slcl_p2p_fwd");
 }
@@ -1580,7 +1706,7 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
       n_class > kMaxLabelClasses)
     return SLCL_ERR_INVALID_ARGUMENT;
   if ((a_selfcol == nullptr) != (b_selfrow == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
-  if (n_class == 0 && (a_selfcol || bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class == 0 && bwd_state) return SLCL_ERR_INVALID_ARGUMENT;
   if (!batches_ok(n_anchor, n_contrast, n_class, n_batch)) return SLCL_ERR_INVALID_ARGUMENT;
   if (bwd_state && !aligned16(bwd_state)) return SLCL_ERR_INVALID_ARGUMENT;
   const int d = (int)dim_padded;
@@ -1628,25 +1754,36 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   }
   launch_pdl(p2p_anchor_stat_kernel, dim3(ceil_div(na + BN, 256)), dim3(256), 0, stream, stats, shift, weight, grad_out, na,
              (int)align_up((size_t)na, BN), inv_t, w.anchor_stat);
+  const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a_bf16);
+  const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b_bf16);
+  const int by_id = a_selfcol == nullptr;
+  const float* gself = nullptr;
+  if (!by_id) {          // self maps: the sweeps treat the self pair as an ordinary pair, its entry is taken out afterwards
+    launch_pdl(p2p_gself_kernel, dim3(ceil_div(na, 8)), dim3(256), 0, stream, (const float4*)w.anchor_stat, inv_t * kLog2e, ab, bb, d,
+               am, bm, a_selfcol, na, w.gself);
+    gself = w.gself;
+  }
   if (d_a) {
     Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
     P2PArgs args{};
     args.row_meta = am; args.col_meta = bm; args.row_stat = w.anchor_stat; args.grad_partial = w.grad_partial_a;
+    args.self_by_id = by_id;
     int st = launch_sweep<kGenRows>(a_bf16, n_anchor, b_bf16, n_contrast, d, inv_t, args, sw, stream, n_batch);
     if (st != SLCL_OK) return st;
     const int64_t n = n_anchor * dim;
-    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_a, sw.splits,
-               n, d, (int)dim, d_a);
+    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, (const float*)w.grad_partial_a,
+               sw.splits, n, d, (int)dim, d_a, gself, a_selfcol, bb, 1);
   }
   if (d_b) {
     Sweep sw = plan_sweep(n_contrast / n_batch, n_anchor / n_batch, n_batch);
     P2PArgs args{};
     args.row_meta = bm; args.col_meta = am; args.col_stat = w.anchor_stat; args.grad_partial = w.grad_partial_b;
+    args.self_by_id = by_id;
     int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream, n_batch);
     if (st != SLCL_OK) return st;
     const int64_t n = n_contrast * dim;
-    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, w.grad_partial_b, sw.splits,
-               n, d, (int)dim, d_b);
+    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, (const float*)w.grad_partial_b,
+               sw.splits, n, d, (int)dim, d_b, gself, b_selfrow, ab, 0);
   }
   return check_launch("slcl_p2p_bwd");
 }

@@ -517,8 +517,8 @@ def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor,
     na, dp = a.shape
     m = b.shape[0]
     _selfcol_check(a_selfcol, na, "a_selfcol")
-    if n_class == 0 and (a_selfcol is not None or keep_state):
-        raise ValueError("a_selfcol / keep_state need n_class > 0 (analytic mode)")
+    if n_class == 0 and keep_state:
+        raise ValueError("keep_state needs n_class > 0 (analytic mode)")
     stats = torch.empty((na, 3), dtype=_F32, device=dev)
     loss = torch.empty(1, dtype=_F32, device=dev)
     keep = n_class > 0 and keep_state

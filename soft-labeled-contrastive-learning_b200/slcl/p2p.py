@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import ops  # noqa: F401
 
 _ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
+_SORT_MIN_ROWS = 8192        # one-row-set problems at least this large are gathered sorted by label (see p2p_loss)
 
 
 class _P2PLoss(torch.autograd.Function):
@@ -70,6 +71,20 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
     R/n a multiple of 128).
     ``n_class`` in 1..8: labels are class indices in [0, n_class) and ids are unique -> analytic sweeps; the
     self-pair maps are derived from the ids unless given."""
+    if same_rows and n_class == 0 and n_batch == 1 and idx_a.numel() >= _SORT_MIN_ROWS:
+        # General labels over ONE large row set (SupCon family, ISCL): the sums are order-invariant, so gather the rows
+        # sorted by contrast label -- label-uniform column tiles take the sweeps' fast path -- and hand the kernels the
+        # self maps (row i is its own contrast row), which takes the id tests out of the sweeps.  (Small or batched
+        # problems are launch-bound: the sort would cost more than it saves.)
+        n = idx_a.numel()
+        order = torch.argsort(lab_b.long(), stable=True)
+        same_labels = lab_b is lab_a
+        idx_a = idx_b = idx_a[order]
+        lab_b = lab_b[order]
+        lab_a = lab_b if same_labels else lab_a[order]
+        weight = weight[order]
+        id_a = id_b = torch.arange(n, device=feat.device, dtype=torch.int32)
+        selfcol = selfrow = id_a
     meta_a = ops.pad_meta(lab_a, id_a)
     meta_b = meta_a if (same_rows and lab_b is lab_a) else ops.pad_meta(lab_b, id_b)
     if n_class > 0 and selfcol is None:

@@ -644,6 +644,27 @@ def test_p2p_analytic_equals_general_op_level(na, m, d, k, t):
     grad_close(db_a, db_g, rtol=P2P_RTOL, floor=0.5)
     only_b = op.p2p_bwd(a, b, d - 3, ma, mb, shift, w, t, st_a, g_out, False, True, k, selfcol, selfrow, state)[1]
     assert torch.equal(only_b, db_a)
+    # general sweeps with self maps (no id tests, label-uniform tiles on the fast path): same again
+    l_s, st_s, _ = op.p2p_fwd(a, b, ma, mb, shift, w, t, 0, selfcol)
+    close(l_s, l_g, rtol=1e-5)
+    assert torch.equal(st_s[:, 2], st_g[:, 2])
+    assert torch.allclose(st_s[:, 0], st_g[:, 0], rtol=2e-4) and torch.allclose(st_s[:, 1], st_g[:, 1], rtol=1e-3, atol=2e-2)
+    da_s, db_s = op.p2p_bwd(a, b, d - 3, ma, mb, shift, w, t, st_s, g_out, True, True, 0, selfcol, selfrow)
+    grad_close(da_s, da_g, rtol=P2P_RTOL, floor=0.5)
+    grad_close(db_s, db_g, rtol=P2P_RTOL, floor=0.5)
+    # ... and with the contrast rows sorted by label (what slcl.p2p does for one-row-set problems): uniform tiles
+    order = torch.argsort(lb.long(), stable=True)
+    b2, lb2 = b[order].contiguous(), lb[order].contiguous()
+    inv = torch.empty_like(order); inv[order] = torch.arange(m, device=dev())
+    sc2 = torch.where(selfcol >= 0, inv[selfcol.clamp_min(0).long()].to(torch.int32), selfcol)
+    sr2 = selfrow[order].contiguous()
+    mb2 = slcl_ops.pad_meta(lb2, ib)
+    l_o, st_o, _ = op.p2p_fwd(a, b2, ma, mb2, shift, w, t, 0, sc2.contiguous())
+    close(l_o, l_g, rtol=1e-5)
+    assert torch.equal(st_o[:, 2], st_g[:, 2])
+    da_o, db_o = op.p2p_bwd(a, b2, d - 3, ma, mb2, shift, w, t, st_o, g_out, True, True, 0, sc2.contiguous(), sr2)
+    grad_close(da_o, da_g, rtol=P2P_RTOL, floor=0.5)
+    grad_close(db_o[inv], db_g, rtol=P2P_RTOL, floor=0.5)
 
 
 def test_c_abi_called_directly_with_ctypes():
@@ -801,3 +822,36 @@ def test_iscl_vs_reference_golden_gpu():
     val.backward()
     close(val, gold["iscl_loss"], rtol=P2P_RTOL)
     grad_close(f.grad, gold["iscl_dfeat"], rtol=P2P_RTOL, floor=0.5)
+
+
+def test_large_one_row_set_problems_take_the_sorted_path(api):
+    """>= 8192 rows over one row set: slcl.p2p gathers the rows sorted by label and hands the general sweeps self maps
+    (label-uniform tiles on the fast path, no id tests).  SupConLoss (labelled) and ISCL against the oracle."""
+    loss_mod, _ = api
+    from slcl import losses, p2p
+    assert 2 * 64 * 64 >= p2p._SORT_MIN_ROWS
+    gen = cases.g(4242)
+    f5 = F.normalize(torch.randn(1, 2, 16, 64, 64, generator=gen), dim=2)
+    lab = torch.randint(0, 5, (1, 2, 64, 64), generator=gen)
+    fo = f5.clone().requires_grad_(True)
+    ref = O.supcon_loss(fo, lab, 0.7)
+    ref.backward()
+    f = f5.to(dev()).requires_grad_(True)
+    out = loss_mod.SupConLoss(0.7)(f, lab.to(dev()))
+    out.backward()
+    close(out, ref, rtol=P2P_RTOL)
+    grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+    n, d = 8192, 48
+    feats = torch.randn(n, d, generator=gen)
+    l1 = torch.randint(0, 6, (n,), generator=gen)
+    l2 = torch.randint(0, 6, (n,), generator=gen)
+    lam = torch.rand(n, generator=gen)
+    dom = torch.where(lam > 0.5, l1, l2)
+    fo = feats.clone().requires_grad_(True)
+    ref = O.iscl_loss(fo, l1, l2, dom, lam, 0.5)
+    ref.backward()
+    f = feats.to(dev()).requires_grad_(True)
+    val = losses.InterpolatedSupervisedContrastiveLoss(0.5)(f, l1.to(dev()), l2.to(dev()), dom.to(dev()), lam.to(dev()))
+    val.backward()
+    close(val, ref, rtol=P2P_RTOL)
+    grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
