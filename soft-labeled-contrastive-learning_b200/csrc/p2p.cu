@@ -93,7 +93,8 @@ struct P2PArgs {
   const float* col_shift;             // kAnaCols: shift*log2e - log2(alpha) per column, padded to 64 entries
   float* stat_partial;                // row sums: [n_slots][n_rows][kStatN]
   float* grad_partial;                // MMA2 modes: [n_splits][n_rows][d] fp32
-  float* fused_out;                   // kAnaCols, one split: d_b [n_rows][ld_out] written by the drain itself (else null):
+  float* fused_out;                   // dB sweeps with one split: d_b [n_rows][ld_out] written by the drain itself (else null);
+                                      // kAnaCols also folds in:
   int ld_out;                         //   out = g (Acc - ABsum[label of the row]);  ab_sums [K][d+1], row labels = row_meta
   int n_class;
   const float* ab_sums;
@@ -524,10 +525,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     unsigned long long w0 = 0, w1 = 0;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     // fused dB drain (kAnaCols, one split): fetch what the drain needs now, long before it is used
-    const bool fused = MODE == kAnaCols && a.fused_out != nullptr;
+    const bool fused = (MODE == kAnaCols || MODE == kGenCols) && a.fused_out != nullptr;      // the drain writes d_b itself
     float gscale = 1.f;
     int lab = -1;
-    if (fused) {
+    if (MODE == kAnaCols && fused) {
       gscale = a.grad_out[0];
       if (row_ok) lab = a.row_meta[row].x;
       if (lab >= a.n_class) lab = -1;
@@ -742,7 +743,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + kColAcc + c, v);
         tmem_ld_wait();
-        if (fused) {
+        if (MODE == kAnaCols && fused) {
           // thread = row: subtract the row's class sum (rows of one label broadcast the same 16 bytes) and scale
           const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)max(lab, 0) * a.d + c);
           const float m = lab >= 0 ? 1.f : 0.f;
@@ -943,6 +944,21 @@ __global__ void __launch_bounds__(256) p2p_gself_kernel(const float4* anchor_sta
     g = bf16_round(fmaf(st.y, ex2_approx(fmaf(s_self, scale_log2, -st.x)), (a_meta[i].x == b_meta[sc].x) ? -st.z : 0.f));
   }
   if (lane == 0) gself[i] = g;
+}
+
+// General dB sweep whose drain wrote d_b directly (one column split), self maps given: take the self-pair entry out,
+//   d_b[selfcol(i)] -= g_self[i] * a_i      (one warp per anchor; ids are unique, so no two warps touch the same row)
+__global__ void __launch_bounds__(256) p2p_self_fix_kernel(const float* gself, const int32_t* a_selfcol, const __nv_bfloat16* a,
+                                                           int d_pad, int dim, int n_anchor, float* d_b) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n_anchor) return;
+  const int sc = a_selfcol[i];
+  if (sc < 0) return;
+  const float g = gself[i];
+  for (int c = lane; c < dim; c += 32) d_b[(size_t)sc * dim + c] -= g * __bfloat162float(a[(size_t)i * d_pad + c]);
 }
 
 // ---- analytic path ----------------------------------------------------------
@@ -1779,11 +1795,17 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     P2PArgs args{};
     args.row_meta = bm; args.col_meta = am; args.col_stat = w.anchor_stat; args.grad_partial = w.grad_partial_b;
     args.self_by_id = by_id;
+    const bool fused = sw.splits == 1 && dim % 4 == 0;        // one CTA sees all anchors of its rows: the drain writes d_b
+    if (fused) { args.fused_out = d_b; args.ld_out = (int)dim; }
     int st = launch_sweep<kGenCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream, n_batch);
     if (st != SLCL_OK) return st;
-    const int64_t n = n_contrast * dim;
-    launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream, (const float*)w.grad_partial_b,
-               sw.splits, n, d, (int)dim, d_b, gself, b_selfrow, ab, 0);
+    if (!fused) {
+      const int64_t n = n_contrast * dim;
+      launch_pdl(p2p_reduce_grad_kernel, dim3((unsigned)ceil_div<int64_t>(n, 256)), dim3(256), 0, stream,
+                 (const float*)w.grad_partial_b, sw.splits, n, d, (int)dim, d_b, gself, b_selfrow, ab, 0);
+    } else if (!by_id) {
+      launch_pdl(p2p_self_fix_kernel, dim3(ceil_div(na, 8)), dim3(256), 0, stream, gself, a_selfcol, ab, d, (int)dim, na, d_b);
+    }
   }
   return check_launch("slcl_p2p_bwd");
 }
