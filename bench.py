@@ -516,6 +516,10 @@ def extra_kernels(dev, feats, labels, centres, peak):
         res[name] = {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
 
     add("pseudo_label (generate_pseudo_label)", timed(lambda: op.pseudo_label(feats, centres, 0.25)), (4 * C + 12) * n_px)
+    # f-1: generate_pseudo_label + target MPCL forward fused into one read of the map (vs the two separate passes)
+    add("fused target step: pseudo labels + target prototype-loss forward, one read of F_t",
+        timed(lambda: op.proto_fwd_target(feats, centres, 0.25, K, CFG["temperature"], CFG["base_temperature"], CFG["margin"],
+                                          False)), (4 * C + 12) * n_px)
     add("class_sums hard + ema_finalize (update_class_center_iter)",
         timed(lambda: op.ema_finalize(op.class_sums(feats, labels, None, False, 0.0, None, 1, K), centres, 0.9)),
         (4 * C + 8) * n_px)
