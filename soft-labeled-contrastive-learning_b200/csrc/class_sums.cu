@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(kThreads) centroid_bwd_prep_kernel(const float
 }
 
 template <int KWT> constexpr int kwpad() { return (KWT + 3) / 4 * 4; }
-constexpr int kCenRing = 12;        // channels in flight per thread in the centroid backward (cp.async ring)
+constexpr int kCenRing = 8;         // channels in flight per thread in the centroid backward (cp.async ring; a power of two)
 
 template <int KWT, int VEC, bool HAS_DP>
 __global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs a) {
