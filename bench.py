@@ -529,6 +529,28 @@ def extra_kernels(dev, feats, labels, centres, peak):
     add("centroid_bwd soft P=2 (cal_centroid bwd: dF + dP)",
         timed(lambda: op.centroid_bwd(feats, None, probs, True, 0.0, part, 2, K, gcen, sums, 1.0, True)),
         (8 * C + 8 * K + 4) * n_px)
+    # north_star (1): the sampler -- stable per-class compaction of the label map (bit-exact with torch.nonzero) and the
+    # gather of the sampled rows (L2-normalised, bf16, padded to 64 columns) for the cfg3 problem.  These are short
+    # kernels: timed as CUDA-graph replays so that the host-side launch cost of the Python op is not what is measured.
+    def timed_graph(fn, iters=20):
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()                                   # noqa: F841  (outputs stay alive with the graph)
+        return timed(g.replay, iters=iters)
+
+    add("sampler: compact_by_class over the cfg2 label map (int64 in, int64 indices out)",
+        timed_graph(lambda: op.compact_by_class(labels, K)), (8 + 8) * n_px)
+    fmap3 = torch.randn(16, 256, 64, 64, device=dev, generator=gen)
+    rows3 = torch.randperm(16 * 64 * 64, device=dev, generator=gen)[:16384 + 4096]
+    add("sampler: gather_unit_rows, 20480 rows x 256 channels from a [16,256,64,64] map -> unit bf16 rows",
+        timed_graph(lambda: op.gather_unit_rows(fmap3, rows3, True, True, False)), 20480 * 256 * 32)   # 32 B sector per element
+    del fmap3, rows3
     # cfg5 geometry (DRUNet decoder map, C=32, K=4, P=2; 64 images of 224x224 per GPU)
     del probs, part, gcen, sums
     b5, c5, h5, k5 = 64, 32, 224, 4
