@@ -127,15 +127,40 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* feat
   const int64_t b = pix / HW, p = pix - b * HW;
   const float* base = feat + b * C * HW + p;
   float ss = 0.f;
-  for (int64_t c = lane; c < C; c += 32) { float x = base[c * HW]; ss = fmaf(x, x, ss); }
+  constexpr int kRegs = 8;                                   // C <= 256: the row stays in registers (one touch, 8 loads in flight)
+  float v[kRegs];
+  const bool in_regs = C <= 32 * kRegs;
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+      const int64_t c = lane + 32 * j;
+      v[j] = c < C ? __ldg(base + c * HW) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) ss = fmaf(v[j], v[j], ss);
+  } else {
+    for (int64_t c = lane; c < C; c += 32) { float x = base[c * HW]; ss = fmaf(x, x, ss); }
+  }
   ss = warp_sum(ss);
   const float inv_n = 1.0f / fmaxf(sqrtf(ss), 1e-12f);      // always reported: callers derive the exp shift from it
   const float inv = normalize ? inv_n : 1.0f;
   if (lane == 0 && inv_norm) inv_norm[row] = inv_n;
-  for (int64_t c = lane; c < C; c += 32) {
-    float x = base[c * HW] * inv;       // second touch hits L1/L2 (the row's sectors were just loaded)
-    if (out_f32) out_f32[row * C + c] = x;
-    if (out_bf16) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(x);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+      const int64_t c = lane + 32 * j;
+      if (c < C) {
+        const float x = v[j] * inv;
+        if (out_f32) out_f32[row * C + c] = x;
+        if (out_bf16) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(x);
+      }
+    }
+  } else {
+    for (int64_t c = lane; c < C; c += 32) {
+      float x = base[c * HW] * inv;       // second touch hits L1/L2 (the row's sectors were just loaded)
+      if (out_f32) out_f32[row * C + c] = x;
+      if (out_bf16) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(x);
+    }
   }
   if (out_bf16) {
     for (int64_t c = C + lane; c < bf16_stride; c += 32) out_bf16[row * bf16_stride + c] = __float2bfloat16_rn(0.f);
