@@ -23,6 +23,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _register_ops():
+    """torch.ops.slcl.* exists once slcl.ops has been imported: tests that call the ops directly must not depend on an
+    earlier test having imported the package (e.g. under ``-k``)."""
+    import slcl.ops  # noqa: F401
+
+
 def dev():
     return torch.device("cuda:0")
 
