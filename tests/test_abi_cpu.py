@@ -43,6 +43,13 @@ def test_argument_validation_without_gpu():
     assert lib.slcl_class_sums(None, 1, 1, 1, None, None, 0, 0.0, None, 1, 4, None, None, 0, None) == -1
     assert lib.slcl_centroid_loss(None, None, 4, 32, 0, 1, 4, 1, None, None, None, None) == -1
     assert lib.slcl_compact_by_class(None, 10, 4, None, None, None, None, 0, None) == -1
+    # pixel<->pixel entry points: null operands are rejected before anything touches the device; the size queries work
+    assert lib.slcl_p2p_fwd(None, None, 128, 128, 64, None, None, None, 0, 1, None, None, 0.7, None, None, None, None, 0, None) == -1
+    assert lib.slcl_p2p_bwd(None, None, 128, 128, 64, 64, None, None, None, None, 0, 1, None, None, 0.7, None, None, None, None,
+                            None, None, 0, None) == -1
+    assert lib.slcl_p2p_state_bytes(4096, 256) >= 4096 * 256 * 4
+    assert lib.slcl_p2p_state_bytes(0, 256) == 0 and lib.slcl_p2p_workspace_bytes(4096, 16384, 512) == 0
+    assert lib.slcl_p2p_workspace_bytes(4096, 16384, 256) > 0
 
 
 def test_reference_signatures_are_kept():
