@@ -18,6 +18,14 @@ int check_launch(const char* where) {
   return SLCL_ERR_CUDA;
 }
 
+void ensure_context_on_this_thread() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);          // the canonical no-op that initialises / binds the primary context of the current device
+    bound = true;
+  }
+}
+
 int current_device_slot() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;

@@ -886,6 +886,7 @@ size_t v3_smem_bytes(int kwt, int cpw, int n_cw) {
 
 template <int KWT, int CPW, int NCW>
 int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
+  ensure_context_on_this_thread();
   V3EncodeFn fn = v3_encode_fn();
   if (!fn) return SLCL_ERR_CUDA;
   CUtensorMap map;

@@ -21,6 +21,10 @@ void set_cuda_error(cudaError_t e, const char* where);
 int  check_launch(const char* where);     // returns SLCL_OK or SLCL_ERR_CUDA
 int  sm_count();                          // cached cudaDevAttrMultiProcessorCount of the current device
 int  current_device_slot();               // current CUDA device index clamped to [0, 64): index of per-device caches
+// Driver-API entry points (cuTensorMapEncodeTiled) need a context that is CURRENT ON THE CALLING THREAD; a thread whose
+// first CUDA activity is one of our calls (PyTorch's autograd worker running a backward) has none until a runtime call
+// binds the primary context.  Call this before any driver-API call.
+void ensure_context_on_this_thread();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

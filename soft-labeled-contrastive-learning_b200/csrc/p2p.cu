@@ -1365,6 +1365,7 @@ EncodeTiledFn encode_fn() {
 
 // [rows, d] bf16 row-major, box = 64 elements (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero
 int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_rows) {
+  ensure_context_on_this_thread();
   EncodeTiledFn fn = encode_fn();
   if (!fn) return SLCL_ERR_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
@@ -1375,7 +1376,10 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_r
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    char what[160];
+    snprintf(what, sizeof(what), "cuTensorMapEncodeTiled(rows=%lld, d=%lld, box_rows=%d, ptr%%16=%d, CUresult=%d)", (long long)rows,
+             (long long)d, box_rows, (int)(reinterpret_cast<uintptr_t>(ptr) & 15), (int)r);
+    set_cuda_error(cudaErrorInvalidValue, what);
     return SLCL_ERR_CUDA;
   }
   return SLCL_OK;
@@ -1401,6 +1405,7 @@ Sweep plan_sweep(int64_t n_rows, int64_t n_cols, int n_batch = 1) {          // 
 // fp32 output of the MMA2 drain as a 3-D tensor [splits][rows][ld]: box = 32 columns (128 B) x 32 rows, 128-byte swizzle;
 // rows past n_rows and columns past n_cols are clipped by the TMA unit
 int make_out_map(CUtensorMap* m, const float* ptr, int64_t n_cols, int64_t ld, int64_t rows, int64_t splits) {
+  ensure_context_on_this_thread();
   EncodeTiledFn fn = encode_fn();
   if (!fn) return SLCL_ERR_CUDA;
   cuuint64_t dims[3] = {(cuuint64_t)n_cols, (cuuint64_t)rows, (cuuint64_t)splits};
@@ -1411,7 +1416,10 @@ int make_out_map(CUtensorMap* m, const float* ptr, int64_t n_cols, int64_t ld, i
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(out)");
+    char what[200];
+    snprintf(what, sizeof(what), "cuTensorMapEncodeTiled(out: cols=%lld, ld=%lld, rows=%lld, splits=%lld, ptr%%16=%d, CUresult=%d)",
+             (long long)n_cols, (long long)ld, (long long)rows, (long long)splits, (int)(reinterpret_cast<uintptr_t>(ptr) & 15), (int)r);
+    set_cuda_error(cudaErrorInvalidValue, what);
     return SLCL_ERR_CUDA;
   }
   return SLCL_OK;

@@ -862,3 +862,46 @@ def test_large_one_row_set_problems_take_the_sorted_path(api):
     val.backward()
     close(val, ref, rtol=P2P_RTOL)
     grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+
+
+def test_first_cuda_activity_of_the_autograd_thread_can_be_ours():
+    """Regression: the tensor-core backward builds TMA descriptors with a driver-API call; in a fresh process the
+    autograd worker thread has no current context until a runtime call binds one (CUDA_ERROR_INVALID_CONTEXT otherwise).
+    Run the sampled pixel<->pixel loss fwd+bwd and a centre-gradient backward as the first things a new process does."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from slcl import p2p, loss
+dev = torch.device('cuda:0')
+g = torch.Generator().manual_seed(1)
+feat = torch.randn(2, 40, 24, 24, generator=g).to(dev).requires_grad_(True)
+labels = torch.randint(0, 4, (2, 24, 24), generator=g).to(dev)
+a_idx, c_idx = p2p.sample_class_balanced(labels, 200, 600, 4, torch.Generator().manual_seed(5))
+out = p2p.sampled_supcon_loss(feat, labels, 200, 600, 4, temperature=0.7, anchor_idx=a_idx, contrast_idx=c_idx)
+out.backward()
+assert torch.isfinite(feat.grad).all()
+print('p2p ok', float(out))
+""" % os.path.join(root, "soft-labeled-contrastive-learning_b200")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "p2p ok" in res.stdout, res.stderr[-2000:]
+    code2 = """
+import sys, torch
+sys.path.insert(0, %r)
+from slcl import loss
+dev = torch.device('cuda:0')
+g = torch.Generator().manual_seed(2)
+feat = torch.randn(2, 64, 16, 16, generator=g).to(dev).requires_grad_(True)
+labels = torch.randint(0, 5, (2, 16, 16), generator=g).to(dev)
+cen = torch.randn(5, 64, generator=g).to(dev).requires_grad_(True)
+mp = loss.MPCL(dev, num_class=5, temperature=.1, base_temperature=1, m=.4)
+out = loss.mpcl_loss_calc(feat, labels, cen, mp)
+out.backward()
+assert torch.isfinite(cen.grad).all() and torch.isfinite(feat.grad).all()
+print('proto ok', float(out))
+""" % os.path.join(root, "soft-labeled-contrastive-learning_b200")
+    res = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "proto ok" in res.stdout, res.stderr[-2000:]
