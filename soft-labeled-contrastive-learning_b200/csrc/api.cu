@@ -21,7 +21,8 @@ int check_launch(const char* where) {
 void ensure_context_on_this_thread() {
   static thread_local bool bound = false;
   if (!bound) {
-    cudaFree(nullptr);          // the canonical no-op that initialises / binds the primary context of the current device
+    int dev = 0;                // cudaSetDevice (CUDA >= 12) initialises the primary context and makes it current on this
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);      // thread; unlike cudaFree(0) it is legal during stream capture
     bound = true;
   }
 }
