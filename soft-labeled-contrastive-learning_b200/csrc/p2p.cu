@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <limits.h>
+#include <algorithm>
 #include <type_traits>
 #include <stdlib.h>
 #include <math.h>
@@ -993,18 +994,25 @@ __device__ __forceinline__ void label_tables_flush(const float* s_sum, const flo
   }
 }
 
-// Per-class row sums of the contrast rows, stage 1:  Bsum[k] = sum_{rows r with label k} x_r, count[k].
-// A block owns kLabelRowsPerBlock rows; a warp walks every 8th row of them with 16-byte loads, eight rows in flight.
-// Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
+// Per-class row sums, stage 1:  sum[k] = sum_{rows r with label k} coef_r x_r,  cnt[k] = sum coef_r.
+//   kBeta = false: coef = 1 (Bsum / class counts of the contrast rows);
+//   kBeta = true : coef = beta~_r = w_r / (T n_r),  n_r = count[lab_r] - [row r is itself a contrast row with the same label]
+//                  (0 when n_r == 0) -> ABsum of the anchors; the coefficients are also written to beta_out.  They depend on
+//                  labels and weights only, so this runs on the side stream next to the forward sweep.
+// A block owns kLabelRowsPerBlock rows at a time (grid-stride over the row blocks); a warp walks every 8th row of them with
+// 16-byte loads, eight rows in flight.  Stage 2 (p2p_label_reduce_kernel) sums the blocks in fixed order.
 constexpr int kLabelRowsPerBlock = 64;
+template <bool kBeta>
 __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16* rows, int n_rows, int d, const int2* meta,
-                                                             int n_class, float* partial, float* cnt) {
+                                                             int n_class, float* partial, float* cnt, const float* weight,
+                                                             float inv_t, const int32_t* selfcol, const int2* other_meta,
+                                                             const float* other_sums, float* beta_out,
+                                                             unsigned int* zero_ticket) {
   pdl_trigger();
   pdl_wait();
+  if (zero_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ticket = 0u;      // (see p2p_finish_fwd_kernel)
   extern __shared__ float sm_lp[];                 // [8 warps][K][d] + [8][K]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r0 = blockIdx.x * kLabelRowsPerBlock;
-  const int r1 = min(n_rows, r0 + kLabelRowsPerBlock);
   float* s_sum = sm_lp;
   float* s_cnt = sm_lp + (size_t)8 * n_class * d;
   float* my_sum = s_sum + (size_t)warp * n_class * d;
@@ -1013,21 +1021,43 @@ __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16
   if (lane < n_class) my_cnt[lane] = 0.f;
   __syncwarp();
   constexpr int kInFlight = 8;
-  for (int rb = r0 + warp; rb < r1; rb += 8 * kInFlight) {
-    uint4 x[kInFlight];
-    int lab[kInFlight];
+  for (int r0 = blockIdx.x * kLabelRowsPerBlock; r0 < n_rows; r0 += gridDim.x * kLabelRowsPerBlock) {
+    const int r1 = min(n_rows, r0 + kLabelRowsPerBlock);
+    for (int rb = r0 + warp; rb < r1; rb += 8 * kInFlight) {
+      uint4 x[kInFlight];
+      int lab[kInFlight];
+      float coef[kInFlight];
 #pragma unroll
-    for (int u = 0; u < kInFlight; ++u) {
-      const int r = rb + 8 * u;
-      lab[u] = -1; x[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (r < r1) {
-        lab[u] = meta[r].x;
-        if (lane * 8 < d) x[u] = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)r * d) + lane);
+      for (int u = 0; u < kInFlight; ++u) {
+        const int r = rb + 8 * u;
+        lab[u] = -1; x[u] = make_uint4(0u, 0u, 0u, 0u); coef[u] = 1.f;
+        if (r < r1) {
+          lab[u] = meta[r].x;
+          if (lane * 8 < d) x[u] = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)r * d) + lane);
+        }
       }
-    }
+      if (kBeta) {
 #pragma unroll
-    for (int u = 0; u < kInFlight; ++u)
-      if (lab[u] >= 0 && lab[u] < n_class) label_table_add(my_sum, my_cnt, d, lab[u], 1.f, x[u], lane);      // warp-uniform
+        for (int u = 0; u < kInFlight; ++u) {
+          const int r = rb + 8 * u;
+          if (r < r1) {
+            const bool ok = lab[u] >= 0 && lab[u] < n_class;
+            float n = 0.f;
+            if (ok) {
+              n = __ldg(other_sums + (size_t)lab[u] * (d + 1) + d);
+              const int sc = selfcol ? selfcol[r] : -1;
+              if (sc >= 0 && other_meta[sc].x == lab[u]) n -= 1.f;
+            }
+            const float wt = weight[r] * inv_t;
+            coef[u] = n > 0.f ? wt / n : 0.f;
+            if (lane == 0) beta_out[r] = coef[u];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u)
+        if (lab[u] >= 0 && lab[u] < n_class) label_table_add(my_sum, my_cnt, d, lab[u], coef[u], x[u], lane);      // warp-uniform
+    }
   }
   __syncthreads();
   label_tables_flush(s_sum, s_cnt, n_class, d, partial, cnt);
@@ -1067,96 +1097,37 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
   }
 }
 
-// Last kernel of the analytic forward: blocks [0, n_red) are stage 2 of ABsum (same scheme as p2p_label_reduce_kernel,
-// skipped when n_red == 0); the last block adds the per-block loss partials in index order.
-__global__ void __launch_bounds__(256) p2p_final_reduce_kernel(const float* ab_partial, const float* ab_cnt, int n_part_blocks,
-                                                               int n_class, int d, float* ab_out, int n_red,
-                                                               const double* loss_partial, int n_loss, float* loss) {
-  pdl_trigger();
-  pdl_wait();
-  if ((int)blockIdx.x < n_red) {
-    __shared__ float red[8][33];
-    const int o = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    const int n_out = n_class * (d + 1);
-    const int idx = blockIdx.x * 32 + o;
-    float t = 0.f;
-    if (idx < n_out) {
-      const int k = idx / (d + 1), c = idx % (d + 1);
-      const float* src = c < d ? ab_partial + (size_t)k * d + c : ab_cnt + k;
-      const size_t stride = c < d ? (size_t)n_class * d : (size_t)n_class;
-      float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int bb = pl;
-      for (; bb + 56 < n_part_blocks; bb += 64) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t8[u] += src[(size_t)(bb + 8 * u) * stride];
-      }
-      for (; bb < n_part_blocks; bb += 8) t8[0] += src[(size_t)bb * stride];
-      t = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
-    }
-    red[pl][o] = t;
-    __syncthreads();
-    if (pl == 0 && idx < n_out) {
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) sum += red[w][o];
-      ab_out[idx] = sum;
-    }
-    return;
-  }
-  __shared__ double redd[8];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n_loss; i += 256) acc += loss_partial[i];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) redd[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += redd[w];
-    loss[0] = (float)t;
-  }
-}
-
 // Forward finish, one warp per anchor i (fixed summation orders throughout).  The per-class sums
 // label_sums[K][d + 1] (last column = class count) are read through L1 (a 5 KB table every warp shares).
 //   Zs_i   = sum_slots zs - e_self                      e_self = exp(S_i,self / T - shift_i) if anchor i is a contrast row
 //   P_raw  = a_i . Bsum[lab_i] - [labels agree] S_i,self        n_i = count[lab_i] - [labels agree]
-//   U_i    = sum_splits U_partial - bf16(e_self) b_self         (the sweep multiplied bf16-rounded exponentials)
 //   block partial of  sum_i w_i (shift_i + log Zs_i - P_raw_i / (T n_i))                  (utils/loss.py:371-386)
+// With alpha_out (the forward keeps state for the backward) it also writes the per-anchor constants
+//   alpha~_i = w_i / (T Zs_i),   colshift_i = shift_i log2e - log2 alpha~_i
+// (beta~ and ABsum do not depend on the sweep: p2p_label_part_kernel<true> on the side stream; the split partials of U
+// stay where the sweep wrote them and are summed by the backward finish).
+// The block that finishes last adds the per-block loss partials in index order (ticket counter `done`, zeroed by the
+// first side-stream kernel of the call and wrapped back to zero by atomicInc), so the forward ends with this launch.
 constexpr int kFinWarps = 32;          // warps (= anchors in flight) per block of the forward finish
 __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const float* zs_partial, int n_slots, int n_rows, const float* shift,
                                                              const float* weight, float inv_t, const __nv_bfloat16* a,
                                                              const __nv_bfloat16* b, int d, const int2* a_meta,
                                                              const int2* b_meta, const int32_t* a_selfcol,
-                                                             const float* label_sums, int n_class, const float* u_partial,
-                                                             int n_splits, float* u_out, float* alpha_out, float* beta_out,
-                                                             float* colshift_out, int n_rows_padded, float* ab_partial,
-                                                             float* ab_cnt, float* stats, double* loss_partial) {
+                                                             const float* label_sums, int n_class, float* alpha_out,
+                                                             float* colshift_out, int n_rows_padded, float* stats,
+                                                             double* loss_partial, unsigned int* done, float* loss) {
   pdl_trigger();
   pdl_wait();
-  // With u_out (the forward keeps state for the backward) the kernel also writes the per-anchor constants
-  //   alpha~_i = w_i / (T Zs_i),  beta~_i = w_i / (T n_i) (0 when n_i == 0),  colshift_i = shift_i log2e - log2 alpha~_i
-  // and stage 1 of ABsum[k] = sum_{lab_i = k} beta~_i a_i  (block partials; p2p_final_reduce_kernel is stage 2).
-  // ABsum: every warp parks beta~_i a_i of its anchor in shared memory, then the block adds the parked rows into its
-  // per-class table in warp order (fixed order, no atomics); one table per block -> few partials for stage 2.
-  extern __shared__ float sm_ff[];                 // keep-state mode: rows [kFinWarps][d], table [K][d]
-  float* s_rows = sm_ff;
-  float* s_tab = sm_ff + (size_t)kFinWarps * d;
-  __shared__ int s_lab[kFinWarps];
-  __shared__ float s_be[kFinWarps];
-  __shared__ float s_cnt[kMaxLabelClasses];
-  const bool keep = u_out != nullptr;
-  if (keep) {
-    for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) s_tab[idx] = 0.f;
-    if ((int)threadIdx.x < n_class) s_cnt[threadIdx.x] = 0.f;
-    if (blockIdx.x == 0) for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 32 * kFinWarps) colshift_out[r] = kShiftOff;
-  }
+  const bool keep = alpha_out != nullptr;
+  if (keep && blockIdx.x == 0)
+    for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 32 * kFinWarps) colshift_out[r] = kShiftOff;
   __shared__ double red[kFinWarps];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
   for (int base = blockIdx.x * kFinWarps; base < n_rows; base += gridDim.x * kFinWarps) {
     const int i = base + warp;
-    if (keep) s_lab[warp] = -1;                    // (warp-private slot; rewritten below when the anchor takes part)
-    if (i < n_rows) {
+    if (i >= n_rows) continue;
     const __nv_bfloat16* ai = a + (size_t)i * d;
     const int lab = a_meta[i].x;
     const int sc = a_selfcol ? a_selfcol[i] : -1;
@@ -1176,83 +1147,22 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
       praw = warp_sum(t);
       n = __ldg(bs + d);
     }
-    float e_self_r = 0.f;
     if (sc >= 0) {
       const float s_self = warp_dot_bf16(ai, b + (size_t)sc * d, d, lane);
       const float e_self = ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
       zs -= e_self;
-      e_self_r = bf16_round(e_self);
       if (lab == b_meta[sc].x) { praw -= s_self; n -= 1.f; }
     }
-    if (u_out != nullptr) {
-      const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
-      const size_t split_stride = (size_t)n_rows * d;
-      for (int c = lane * 2; c < d; c += 64) {
-        const float* src = u_partial + (size_t)i * d + c;
-        float2 t = make_float2(0.f, 0.f);
-        int s = 0;
-        for (; s + 4 <= n_splits; s += 4) {                 // four loads in flight, summed in split order
-          const float2 p0 = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
-          const float2 p1 = *reinterpret_cast<const float2*>(src + (size_t)(s + 1) * split_stride);
-          const float2 p2 = *reinterpret_cast<const float2*>(src + (size_t)(s + 2) * split_stride);
-          const float2 p3 = *reinterpret_cast<const float2*>(src + (size_t)(s + 3) * split_stride);
-          t.x = (((t.x + p0.x) + p1.x) + p2.x) + p3.x;
-          t.y = (((t.y + p0.y) + p1.y) + p2.y) + p3.y;
-        }
-        for (; s < n_splits; ++s) {
-          const float2 p = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
-          t.x += p.x; t.y += p.y;
-        }
-        if (sc >= 0) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
-          t.x = fmaf(-e_self_r, x.x, t.x); t.y = fmaf(-e_self_r, x.y, t.y);
-        }
-        *reinterpret_cast<float2*>(u_out + (size_t)i * d + c) = t;
-      }
-    }
-    if (keep) {
-      const float wt = weight[i] * inv_t;
-      const float al = wt / zs, be = n > 0.f ? wt / n : 0.f;
-      if (lane == 0) {
-        alpha_out[i] = al; beta_out[i] = be;
+    if (lane == 0) {
+      if (keep) {
+        const float al = weight[i] * inv_t / zs;
+        alpha_out[i] = al;
         colshift_out[i] = al > 0.f ? shift[i] * kLog2e - log2f(al) : kShiftOff;
       }
-      if (lab_ok) {
-        for (int c = lane * 2; c < d; c += 64) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
-          *reinterpret_cast<float2*>(s_rows + (size_t)warp * d + c) = make_float2(be * x.x, be * x.y);
-        }
-        if (lane == 0) { s_lab[warp] = lab; s_be[warp] = be; }
-      }
-    }
-    if (lane == 0) {
       stats[3 * i] = zs; stats[3 * i + 1] = praw; stats[3 * i + 2] = n;
       const float li = shift[i] + logf(zs) - (praw * inv_t) / n;      // n == 0 -> NaN, as 0/0 in the reference (:376-380)
       acc += (double)(weight[i] * li);
     }
-    }
-    if (keep) {
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) {
-        const int k = idx / d, c = idx - k * d;
-        float t = s_tab[idx];
-#pragma unroll 8
-        for (int w = 0; w < kFinWarps; ++w)
-          if (s_lab[w] == k) t += s_rows[(size_t)w * d + c];
-        s_tab[idx] = t;
-      }
-      if ((int)threadIdx.x < n_class) {
-        float t = s_cnt[threadIdx.x];
-        for (int w = 0; w < kFinWarps; ++w)
-          if (s_lab[w] == (int)threadIdx.x) t += s_be[w];
-        s_cnt[threadIdx.x] = t;
-      }
-      __syncthreads();
-    }
-  }
-  if (keep) {
-    for (int idx = threadIdx.x; idx < n_class * d; idx += 32 * kFinWarps) ab_partial[(size_t)blockIdx.x * n_class * d + idx] = s_tab[idx];
-    if ((int)threadIdx.x < n_class) ab_cnt[blockIdx.x * n_class + threadIdx.x] = s_cnt[threadIdx.x];
   }
   if (lane == 0) red[warp] = acc;
   __syncthreads();
@@ -1260,6 +1170,16 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
     double t = 0.0;
     for (int w = 0; w < kFinWarps; ++w) t += red[w];
     loss_partial[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicInc(done, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (int bidx = lane; bidx < (int)gridDim.x; bidx += 32) t += __ldcg(loss_partial + bidx);
+    t = warp_sum(t);
+    if (lane == 0) loss[0] = (float)t;
   }
 }
 
@@ -1271,8 +1191,9 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
                                                              const int2* b_meta, const int32_t* a_selfcol,
                                                              const int32_t* b_selfrow, const float* label_sums,
                                                              const float* ab_sums, int n_class, const float* alpha,
-                                                             const float* beta, const float* colshift, float scale_log2,
-                                                             const float* u, const float* acc_partial, int n_splits,
+                                                             const float* beta, const float* colshift, const float* shift,
+                                                             float scale_log2, const float* u_partial, int n_splits_u,
+                                                             const float* acc_partial, int n_splits,
                                                              int fused_db, const float* grad_out, float* d_a, float* d_b) {
   pdl_trigger();
   pdl_wait();
@@ -1291,9 +1212,9 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
       const float al = alpha[i], be = lab_ok ? beta[i] : 0.f;
       const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
       const float* bsum = label_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
+      const __nv_bfloat16* ai = a + (size_t)i * d;
+      const float s_self = sc >= 0 ? warp_dot_bf16(ai, bs, d, lane) : 0.f;
       if (fused_db && sc >= 0) {
-        const __nv_bfloat16* ai = a + (size_t)i * d;
-        const float s_self = warp_dot_bf16(ai, bs, d, lane);
         const float g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
         const float coef = g * ((match ? beta[i] : 0.f) - g_self);
         for (int c = lane * 2; c < dim; c += 64) {
@@ -1303,8 +1224,29 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
         }
       }
       if (d_a == nullptr) continue;
+      // U_i = sum_splits U_partial - bf16(e_self) b_self   (the sweep multiplied bf16-rounded exponentials)
+      const float e_self_r = sc >= 0 ? bf16_round(ex2_approx(fmaf(s_self, scale_log2, -shift[i] * kLog2e))) : 0.f;
+      const size_t split_stride = (size_t)n_anchor * d;
       for (int c = lane * 2; c < dim; c += 64) {
-        const float2 uu = *reinterpret_cast<const float2*>(u + (size_t)i * d + c);
+        const float* src = u_partial + (size_t)i * d + c;
+        float2 uu = make_float2(0.f, 0.f);
+        int s = 0;
+        for (; s + 4 <= n_splits_u; s += 4) {                 // four loads in flight, summed in split order
+          const float2 p0 = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
+          const float2 p1 = *reinterpret_cast<const float2*>(src + (size_t)(s + 1) * split_stride);
+          const float2 p2 = *reinterpret_cast<const float2*>(src + (size_t)(s + 2) * split_stride);
+          const float2 p3 = *reinterpret_cast<const float2*>(src + (size_t)(s + 3) * split_stride);
+          uu.x = (((uu.x + p0.x) + p1.x) + p2.x) + p3.x;
+          uu.y = (((uu.y + p0.y) + p1.y) + p2.y) + p3.y;
+        }
+        for (; s < n_splits_u; ++s) {
+          const float2 q = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
+          uu.x += q.x; uu.y += q.y;
+        }
+        if (sc >= 0) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
+          uu.x = fmaf(-e_self_r, x.x, uu.x); uu.y = fmaf(-e_self_r, x.y, uu.y);
+        }
         float2 p = make_float2(0.f, 0.f);
         if (lab_ok) { p.x = __ldg(bsum + c); p.y = __ldg(bsum + c + 1); }
         if (match) {
@@ -1485,7 +1427,8 @@ int launch_sweep(const void* rows, int64_t n_rows, const void* cols, int64_t n_c
 
 // State the analytic forward leaves for the backward (slcl_p2p_state_bytes): one caller-owned buffer.
 struct P2PState {
-  float* u;          // [Na][d]        U_i = sum_{j != self} exp(S_ij - shift_i) b_j
+  float* u;          // [splits][Na][d]  split partials of U_i = sum_j exp(S_ij - shift_i) b_j, as the forward sweep wrote them
+                     //                  (splits <= max_splits(Na); summed, and the self pair removed, by the backward finish)
   float* bsum;       // [K][d+1]       per-class sums / counts of the contrast rows
   float* absum;      // [K][d+1]       sum_{lab_i = k} beta~_i a_i
   float* colshift;   // [pad64(Na)]    column shifts of the dB sweep
@@ -1493,11 +1436,14 @@ struct P2PState {
   float* beta;       // [Na]
   size_t total;
 };
+int max_splits(int64_t n_rows) {          // upper bound of plan_sweep(n_rows, any).splits
+  return max(1, sm_count() / (int)ceil_div<int64_t>(n_rows, BM));
+}
 P2PState carve_state(void* p, int64_t na, int d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   const size_t K = kMaxLabelClasses;
-  size_t o0 = take((size_t)na * d * sizeof(float)), o1 = take(K * (d + 1) * sizeof(float)), o2 = take(K * (d + 1) * sizeof(float));
+  size_t o0 = take((size_t)max_splits(na) * na * d * sizeof(float)), o1 = take(K * (d + 1) * sizeof(float)), o2 = take(K * (d + 1) * sizeof(float));
   size_t o3 = take(align_up((size_t)na, BN) * sizeof(float)), o4 = take((size_t)na * sizeof(float)), o5 = take((size_t)na * sizeof(float));
   char* b = reinterpret_cast<char*>(p);
   P2PState st;
@@ -1521,6 +1467,7 @@ struct P2PWs {
   float* bsum;             // [K][d+1]   (forward without state)
   float* stats_scratch;    // [Na][3]    (backward without state)
   float* gself;            // [Na]       (general sweeps with self maps)
+  unsigned int* done;      // ticket counter of the forward finish
   double* loss_partial;    // [max(kMaxFinishBlocks, ceil(Na / 8))]
   void* state;             // backward without state: regenerated here
   int blocks_b;
@@ -1534,7 +1481,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   P2PWs w;
   w.blocks_b = (int)ceil_div<int64_t>(m, kLabelRowsPerBlock);
   const size_t K = kMaxLabelClasses;
-  size_t o[13];
+  size_t o[14];
   o[0] = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
   o[1] = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
   o[2] = take((size_t)sa.splits * na * d * sizeof(float));
@@ -1549,6 +1496,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   o[10] = take((size_t)n_loss_partial * sizeof(double));
   o[11] = take(carve_state(nullptr, na, d).total);
   o[12] = take((size_t)na * sizeof(float));
+  o[13] = take(sizeof(unsigned int));
   char* b = reinterpret_cast<char*>(ws);
   w.stat_partial = reinterpret_cast<float*>(b + o[0]);
   w.anchor_stat = reinterpret_cast<float4*>(b + o[1]);
@@ -1563,6 +1511,7 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   w.loss_partial = reinterpret_cast<double*>(b + o[10]);
   w.state = b + o[11];
   w.gself = reinterpret_cast<float*>(b + o[12]);
+  w.done = reinterpret_cast<unsigned int*>(b + o[13]);
   w.total = off;
   return w;
 }
@@ -1589,8 +1538,8 @@ int big_smem_ok() {          // K = 8, d = 256 needs 64 KB of dynamic shared mem
   bool& done = done_dev[current_device_slot()];
   if (!done) {
     const int bytes = (int)(8 * kMaxLabelClasses * (kMaxD + 1) * sizeof(float));
-    cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_finish_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(p2p_label_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_label_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(p2p label tables)"); return SLCL_ERR_CUDA; }
     done = true;
   }
@@ -1618,7 +1567,7 @@ Aux* aux_stream() {
   return &x;
 }
 
-// analytic forward: [side stream: label sums of b]  ||  sweep  ->  finish (+ constants, ABsum partials)  ->  final reduce
+// analytic forward: [side stream: label sums of b -> beta~ and ABsum of the anchors]  ||  sweep  ->  finish (+ loss)
 int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, const int2* am, const int2* bm,
                 const int32_t* a_selfcol, int n_class, const float* shift, const float* weight, float inv_t,
                 float* stats, float* loss, const P2PState* state, const P2PWs& w, cudaStream_t stream) {
@@ -1628,32 +1577,39 @@ int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, cons
   const bool keep = state != nullptr;
   float* bsum = keep ? state->bsum : w.bsum;
   const size_t table_smem = (size_t)8 * n_class * (d + 1) * sizeof(float);
+  const int n_red = ceil_div(n_class * (d + 1), 32);
   Aux* aux = aux_stream();
   cudaStream_t side = stream;
   if (aux != nullptr && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
     side = aux->s;
-  launch_pdl(p2p_label_part_kernel, dim3(w.blocks_b), dim3(256), table_smem, side, bb, (int)m, d, bm, n_class, w.lab_partial_b,
-             w.lab_cnt_b);
-  launch_pdl(p2p_label_reduce_kernel, dim3(ceil_div(n_class * (d + 1), 32)), dim3(256), 0, side, w.lab_partial_b, w.lab_cnt_b,
+  launch_pdl(p2p_label_part_kernel<false>, dim3(w.blocks_b), dim3(256), table_smem, side, bb, (int)m, d, bm, n_class, w.lab_partial_b,
+             w.lab_cnt_b, (const float*)nullptr, 0.f, (const int32_t*)nullptr, (const int2*)nullptr, (const float*)nullptr,
+             (float*)nullptr, w.done);
+  launch_pdl(p2p_label_reduce_kernel, dim3(n_red), dim3(256), 0, side, (const float*)w.lab_partial_b, (const float*)w.lab_cnt_b,
              w.blocks_b, n_class, d, bsum);
+  if (keep) {
+    const int blocks_a = (int)std::min<int64_t>(ceil_div<int64_t>(na, kLabelRowsPerBlock), (int64_t)kMaxFinishBlocks);
+    launch_pdl(p2p_label_part_kernel<true>, dim3(blocks_a), dim3(256), table_smem, side, ab, (int)na, d, am, n_class, w.ab_partial,
+               w.ab_cnt, weight, inv_t, a_selfcol, bm, (const float*)bsum, state->beta,
+               (unsigned int*)nullptr);
+    launch_pdl(p2p_label_reduce_kernel, dim3(n_red), dim3(256), 0, side, (const float*)w.ab_partial, (const float*)w.ab_cnt,
+               blocks_a, n_class, d, state->absum);
+  }
   if (side != stream) cudaEventRecord(aux->join, side);
   Sweep sw = plan_sweep(na, m);
   P2PArgs args{};
   args.row_shift = shift;
   args.stat_partial = w.stat_partial;
-  args.grad_partial = w.grad_partial_a;
+  args.grad_partial = keep ? state->u : w.grad_partial_a;
   int st = keep ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream)
                 : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
   if (side != stream) cudaStreamWaitEvent(stream, aux->join, 0);          // join even when the sweep failed to launch
   if (st != SLCL_OK) return st;
   const int nb = finish_blocks(na);
-  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(32 * kFinWarps), keep ? (size_t)(kFinWarps + n_class) * d * sizeof(float) : 0, stream, w.stat_partial, 2 * sw.splits, (int)na,
-             shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, bsum, n_class, w.grad_partial_a, sw.splits,
-             keep ? state->u : nullptr, keep ? state->alpha : nullptr, keep ? state->beta : nullptr,
-             keep ? state->colshift : nullptr, (int)align_up((size_t)na, BN), w.ab_partial, w.ab_cnt, stats, w.loss_partial);
-  const int n_red = keep ? ceil_div(n_class * (d + 1), 32) : 0;
-  launch_pdl(p2p_final_reduce_kernel, dim3(n_red + 1), dim3(256), 0, stream, w.ab_partial, w.ab_cnt, nb, n_class, d,
-             keep ? state->absum : nullptr, n_red, w.loss_partial, nb, loss);
+  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(32 * kFinWarps), 0, stream, (const float*)w.stat_partial, 2 * sw.splits, (int)na,
+             shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, (const float*)bsum, n_class,
+             keep ? state->alpha : (float*)nullptr, keep ? state->colshift : (float*)nullptr, (int)align_up((size_t)na, BN), stats,
+             w.loss_partial, w.done, loss);
   return SLCL_OK;
 }
 
@@ -1772,8 +1728,9 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     const int64_t rows = ((d_a || fused_db) ? n_anchor : 0) + ((d_b && !fused_db) ? n_contrast : 0);
     launch_pdl(p2p_finish_bwd_kernel, dim3((unsigned)ceil_div<int64_t>(rows, 8)), dim3(256), 0, stream, na, (int)n_contrast, d,
                (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, (const float*)st_.bsum, (const float*)st_.absum, n_class,
-               (const float*)st_.alpha, (const float*)st_.beta, (const float*)st_.colshift, inv_t * kLog2e, (const float*)st_.u,
-               (const float*)w.grad_partial_b, n_splits_b, fused_db, grad_out, d_a, d_b);
+               (const float*)st_.alpha, (const float*)st_.beta, (const float*)st_.colshift, shift, inv_t * kLog2e,
+               (const float*)st_.u, plan_sweep(n_anchor, n_contrast).splits, (const float*)w.grad_partial_b, n_splits_b, fused_db,
+               grad_out, d_a, d_b);
     return check_launch("slcl_p2p_bwd");
   }
   launch_pdl(p2p_anchor_stat_kernel, dim3(ceil_div(na + BN, 256)), dim3(256), 0, stream, stats, shift, weight, grad_out, na,
