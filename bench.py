@@ -196,6 +196,36 @@ def time_cpu(n_images: int, warmup: int, steps: int):
     return pixels, times, cores
 
 
+def time_torch_eager_gpu(dev, feats, labels, sel, centres, iters: int = 5):
+    """SURVEY 8(d) second comparator: the reference's own op sequence (oracle port: same ATen calls, same order) run as
+    plain eager PyTorch on the SAME GPU and the SAME resident cfg2 batch.  Reported beside the CPU arm; never on the
+    product path.  Also a full-size loss check of the CUDA path against eager fp32."""
+    from oracle import slcl_oracle as O
+    spec = O.MarginSpec(num_class=CFG["K"], temperature=CFG["temperature"], m=CFG["margin"],
+                        base_temperature=CFG["base_temperature"])
+    x = feats.detach().clone().requires_grad_(True)
+
+    def step():
+        x.grad = None
+        loss = O.mpcl_loss_calc(x, labels, centres, spec, pixel_sel_loc=sel, tag="target")
+        loss.backward()
+        return loss.detach()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+    grad = x.grad
+    x.grad = None
+    return min(times), float(loss), grad
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -257,17 +287,26 @@ def run_slcl(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = []
 
+    def step_blocking():
+        # the plain exchange: all-reduce {weight sum, weighted row-loss sum} between forward and backward
+        scal = plan.forward()
+        dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
+        plan.rescale()
+        return scal, plan.backward()
+
     def step(record: bool):
         e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
+        if world > 1:
+            # data-parallel step: the normaliser is all-reduced next to the forward kernel, the loss next to the backward
+            loss, dfeat = plan.step_data_parallel(events=(e0, e1, e2, e3) if record else None)
+            if record:
+                marks.append((e0, e1, e2, e3))
+            return loss, dfeat
         if record:
             e0.record()
         scal = plan.forward()
         if record:
             e1.record()
-        if world > 1:
-            dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
-            plan.rescale()
-        if record:
             e2.record()
         dfeat = plan.backward()
         if record:
@@ -301,6 +340,17 @@ def run_slcl(args):
     bwd_ms = statistics.mean(m[2].elapsed_time(m[3]) for m in marks)
     loss_value = float(scal[0])
     launches_per_step = 4 + (1 if world > 1 else 0)
+    exchange_check = None
+    if world > 1:
+        # the overlapped exchange must give what the plain one gives: same global loss, bit-identical gradient
+        d_new = dfeat.clone()
+        scal_b, d_old = step_blocking()
+        torch.cuda.synchronize(dev)
+        rel = abs(float(scal_b[0]) - loss_value) / max(abs(float(scal_b[0])), 1e-30)
+        exchange_check = {"loss_rel_diff_vs_blocking_exchange": rel, "grad_bit_identical": bool(torch.equal(d_new, d_old))}
+        if rel > 1e-6 or not exchange_check["grad_bit_identical"]:
+            raise SystemExit(f"[bench] overlapped exchange disagrees with the blocking one: {exchange_check}")
+        del d_new, d_old
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
@@ -378,17 +428,37 @@ def run_slcl(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": n_px,
                    "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
-                   "parallelism": f"dp{world} (batch sharded; 8-byte loss all-reduce)" if world > 1 else "single GPU",
+                   "parallelism": (f"dp{world} (batch sharded; 4-byte normaliser all-reduce next to the forward kernel, 4-byte loss "
+                                   f"all-reduce next to the backward kernel)") if world > 1 else "single GPU",
                    "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
+    if exchange_check is not None:
+        out["exchange_check"] = exchange_check
     if mccl is not None:
         mccl["frac_of_hbm_peak"] = mccl["achieved_GBps_per_gpu"] / peak
         out["mccl_loss_section"] = mccl
     if not args.no_extras and world == 1:
         out["kernels"] = extra_kernels(dev, feats, labels, centres, peak)
     if not args.no_cpu and world == 1:
+        try:
+            ms_eager, loss_eager, grad_eager = time_torch_eager_gpu(dev, feats, labels, sel, centres)
+            gmax = float(grad_eager.abs().max())
+            xq = feats.detach().clone().requires_grad_(True)
+            mpq = MPCL(dev, num_class=K, temperature=CFG["temperature"], m=CFG["margin"], base_temperature=CFG["base_temperature"])
+            mpcl_loss_calc(xq, labels, centres, mpq, pixel_sel_loc=sel, tag="target").backward()
+            dfeat = xq.grad
+            out["torch_eager_gpu"] = {
+                "value": n_px / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager, "kind": "port",
+                "what": "oracle port of mpcl_loss_calc+MPCL.forward fwd+bwd as eager PyTorch fp32 on the same B200, same resident "
+                        "cfg2 batch, min of 5 after 2 warm-ups (the reference's GPU path; reported comparator, not the product)",
+                "loss": loss_eager, "loss_rel_diff_vs_cuda_path": abs(loss_eager - loss_value) / max(abs(loss_eager), 1e-30),
+                "grad_max_abs_diff_over_max_abs": float((grad_eager - dfeat).abs().max()) / max(gmax, 1e-30)}
+            del grad_eager, dfeat, xq
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 - a comparator must never take the bench line down
+            out["torch_eager_gpu"] = {"unavailable": repr(exc)[:200]}
         n_img = args.cpu_sample_images
         pixels, times, cores = time_cpu(n_img, 1, 3)
         out["cpu_baseline"] = {

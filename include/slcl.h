@@ -258,11 +258,14 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *       a_selfcol [A] int32: the contrast row holding anchor i's own pixel, or -1 (null: no anchor is a contrast row)
  *       b_selfrow [M] int32: its inverse (anchor whose pixel contrast row j is, or -1); both or none.
  *       bwd_state: optional caller-owned buffer of slcl_p2p_state_bytes() bytes (16-byte aligned) that the forward
- *         fills with what the backward can reuse -- U_i = sum_{j != self} exp(S_ij - shift_i) b_j, the per-class row
+ *         fills with what the backward can reuse -- the column-split partials of U_i = sum_j exp(S_ij - shift_i) b_j
+ *         exactly as the sweep wrote them (the backward finish sums them and removes the self pair), the per-class row
  *         sums of both sides and the per-anchor constants.  Handing it back to slcl_p2p_bwd leaves the backward with
  *         ONE tensor-core sweep (dB) and one finishing kernel; with null the backward regenerates it (one more sweep).
- *     The per-class sums of the contrast rows do not depend on the sweep: they run on a side stream owned by the
- *     library (one per host thread and device, created on first use; fork/join by events, graph-capturable).
+ *     The per-class sums of the contrast rows, and beta~_i = w_i / (T n_i) with the class sums ABsum of the anchors
+ *     (labels and weights only), do not depend on the sweep: they run on a side stream owned by the library (one per
+ *     host thread and device, created on first use; fork/join by events, graph-capturable).  The forward on the
+ *     caller's stream is the sweep plus ONE finishing launch (its last block totals the loss).
  *   n_batch: 1, or the number of equal BLOCK-DIAGONAL batches (general mode only): anchors [z A/n, (z+1) A/n) are
  *     contrasted with contrast rows [z M/n, (z+1) M/n) only -- BlockConLoss (utils/loss.py:416-466) as ONE launch per
  *     sweep instead of div_num^2 separate problems.  A/n and M/n must be multiples of 128.

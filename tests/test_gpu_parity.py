@@ -615,6 +615,8 @@ def test_p2p_full_size_properties_cfg3():
     (9000, 9000, 192, 8, 0.5),      # > 8192 anchors: several anchors per finish warp; d = 192 (three 64-column chunks); K = 8
     (300, 5000, 64, 3, 0.2),        # one row tile, many column splits; d = 64 (ring smaller than the drain staging)
     (4100, 130, 128, 5, 1.0),       # row tail (4100 = 32*128 + 4), three column tiles (fewer than ring stages)
+    (66000, 200, 64, 4, 0.7),       # > 65536 anchors: the beta~/ABsum pass walks several row blocks per CTA; most anchors
+                                    # have no self pair
 ])
 def test_p2p_analytic_equals_general_op_level(na, m, d, k, t):
     """Analytic sweeps (class sums outside the tensor-core sweep, forward keeps state) against the per-element general
@@ -672,6 +674,45 @@ def test_p2p_analytic_equals_general_op_level(na, m, d, k, t):
     da_o, db_o = op.p2p_bwd(a, b2, d - 3, ma, mb2, shift, w, t, st_o, g_out, True, True, 0, sc2.contiguous(), sr2)
     grad_close(da_o, da_g, rtol=P2P_RTOL, floor=0.5)
     grad_close(db_o[inv], db_g, rtol=P2P_RTOL, floor=0.5)
+
+
+def test_p2p_plan_graph_replay_matches_eager_launches():
+    """slcl.plan.P2PPlan (raw C-ABI launches on fixed buffers): forward + backward captured into ONE CUDA graph (side-stream
+    fork/join, programmatic dependent launches, the forward finish's ticket counter) and replayed several times gives bit
+    for bit what the same launches give outside a graph; the loss also matches an fp32 torch evaluation."""
+    from slcl import ops as slcl_ops
+    from slcl.plan import P2PPlan
+    g = torch.Generator(device=dev()).manual_seed(77)
+    na, m, d, k, t = 1000, 3000, 128, 5, 0.7
+    b = F.normalize(torch.randn(m, d, device=dev(), generator=g), dim=1).to(torch.bfloat16)
+    lb = torch.randint(0, k, (m,), device=dev(), generator=g, dtype=torch.int32)
+    ib = torch.arange(m, device=dev(), dtype=torch.int32)
+    pick = torch.randperm(m, device=dev(), generator=g)[:na]
+    a, la, ia = b[pick].contiguous(), lb[pick].contiguous(), ib[pick].contiguous()
+    w = torch.rand(na, device=dev(), generator=g)
+    w = (w / w.sum()).contiguous()
+    shift = torch.full((na,), 1.0 / t, device=dev())
+    selfcol, selfrow = slcl_ops.self_maps(ia, ib)
+    plan = P2PPlan(a, b, d, slcl_ops.pad_meta(la, ia), slcl_ops.pad_meta(lb, ib), shift, w, t, n_class=k, a_selfcol=selfcol,
+                   b_selfrow=selfrow)
+    plan.forward(); plan.backward()
+    torch.cuda.synchronize()
+    loss0, da0, db0 = plan.loss.clone(), plan.d_a.clone(), plan.d_b.clone()
+    af, bf = a.float(), b.float()
+    sf = af @ bf.t() / t
+    notself = ia.view(-1, 1) != ib.view(1, -1)
+    pos = ((la.view(-1, 1) == lb.view(1, -1)) & notself).float()
+    ref = ((torch.logsumexp(sf.masked_fill(~notself, float("-inf")), dim=1) - (sf * pos).sum(1) / pos.sum(1)) * w).sum()
+    close(loss0[0], ref, rtol=P2P_RTOL)
+    graph = plan.capture_graph()
+    for _ in range(3):
+        plan.loss.zero_(); plan.d_a.zero_(); plan.d_b.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(plan.loss, loss0) and torch.equal(plan.d_a, da0) and torch.equal(plan.d_b, db0)
+    plan.forward(); plan.backward()                       # and eager launches still work after the graph used the counter
+    torch.cuda.synchronize()
+    assert torch.equal(plan.loss, loss0) and torch.equal(plan.d_a, da0)
 
 
 def test_c_abi_called_directly_with_ctypes():
