@@ -287,26 +287,17 @@ def run_slcl(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = []
 
-    def step_blocking():
-        # the plain exchange: all-reduce {weight sum, weighted row-loss sum} between forward and backward
-        scal = plan.forward()
-        dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
-        plan.rescale()
-        return scal, plan.backward()
-
     def step(record: bool):
         e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
-        if world > 1:
-            # data-parallel step: the normaliser is all-reduced next to the forward kernel, the loss next to the backward
-            loss, dfeat = plan.step_data_parallel(events=(e0, e1, e2, e3) if record else None)
-            if record:
-                marks.append((e0, e1, e2, e3))
-            return loss, dfeat
         if record:
             e0.record()
         scal = plan.forward()
         if record:
             e1.record()
+        if world > 1:
+            dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
+            plan.rescale()
+        if record:
             e2.record()
         dfeat = plan.backward()
         if record:
@@ -340,17 +331,6 @@ def run_slcl(args):
     bwd_ms = statistics.mean(m[2].elapsed_time(m[3]) for m in marks)
     loss_value = float(scal[0])
     launches_per_step = 4 + (1 if world > 1 else 0)
-    exchange_check = None
-    if world > 1:
-        # the overlapped exchange must give what the plain one gives: same global loss, bit-identical gradient
-        d_new = dfeat.clone()
-        scal_b, d_old = step_blocking()
-        torch.cuda.synchronize(dev)
-        rel = abs(float(scal_b[0]) - loss_value) / max(abs(float(scal_b[0])), 1e-30)
-        exchange_check = {"loss_rel_diff_vs_blocking_exchange": rel, "grad_bit_identical": bool(torch.equal(d_new, d_old))}
-        if rel > 1e-6 or not exchange_check["grad_bit_identical"]:
-            raise SystemExit(f"[bench] overlapped exchange disagrees with the blocking one: {exchange_check}")
-        del d_new, d_old
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
@@ -428,14 +408,11 @@ def run_slcl(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": n_px,
                    "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
-                   "parallelism": (f"dp{world} (batch sharded; 4-byte normaliser all-reduce next to the forward kernel, 4-byte loss "
-                                   f"all-reduce next to the backward kernel)") if world > 1 else "single GPU",
+                   "parallelism": f"dp{world} (batch sharded; 8-byte loss all-reduce)" if world > 1 else "single GPU",
                    "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
-    if exchange_check is not None:
-        out["exchange_check"] = exchange_check
     if mccl is not None:
         mccl["frac_of_hbm_peak"] = mccl["achieved_GBps_per_gpu"] / peak
         out["mccl_loss_section"] = mccl

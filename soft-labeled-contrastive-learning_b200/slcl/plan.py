@@ -71,41 +71,6 @@ class ProtoPlan:
         check(self.lib.slcl_proto_bwd(*self._bwd_args, self._stream()), "slcl_proto_bwd")
         return self.dfeat
 
-    def step_data_parallel(self, group=None, events=None):
-        """One forward + backward of a batch-sharded step with both exchanges OFF the critical path.
-
-        The backward only needs the GLOBAL normaliser ``sum(pixel_sel_loc) + 1e-4`` (utils/loss.py:565), which depends on
-        the inputs alone: it is summed and all-reduced (NCCL, async) while the forward kernel runs.  The loss itself
-        (this rank's share ``sum(sel * row) / normaliser``) is all-reduced while the backward kernel runs.  Returns
-        (global loss [1], dfeat); same numbers as forward -> all_reduce(scal[2:4]) -> rescale -> backward.
-        ``events``: optional 4 CUDA events recorded at start / after forward / before backward / after backward."""
-        import torch.distributed as dist
-        if not hasattr(self, "_wsum"):
-            self._wsum = torch.empty(1, dtype=torch.float32, device=self.dev)
-            self._loss = torch.empty(1, dtype=torch.float32, device=self.dev)
-        if events:
-            events[0].record()
-        if self.sel is not None:
-            torch.sum(self.sel, dim=0, keepdim=True, out=self._wsum)
-        else:
-            self._wsum.fill_(float(self.n_pixels))
-        w = dist.all_reduce(self._wsum, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        scal = self.forward()
-        if events:
-            events[1].record()
-        w.wait()
-        scal[2:3].copy_(self._wsum)
-        self.rescale()                   # scal[1] = global coefficient, scal[0] = this rank's share of the global loss
-        self._loss.copy_(scal[0:1])
-        lw = dist.all_reduce(self._loss, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        if events:
-            events[2].record()
-        dfeat = self.backward()
-        if events:
-            events[3].record()
-        lw.wait()
-        return self._loss, dfeat
-
     def capture_graph(self) -> "torch.cuda.CUDAGraph":
         """Record forward + backward into one CUDA graph (replay with ``plan.graph.replay()``)."""
         s = torch.cuda.Stream(self.dev)
