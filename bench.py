@@ -628,10 +628,62 @@ def extra_kernels(dev, feats, labels, centres, peak):
     add("cfg4 shape per GPU: prototype loss fwd+bwd, 16 x 32 x 224 x 224, K4", timed(proto4, iters=20),
         (12 * c5 + 24) * 16 * h5 * h5)
     del f4, lab4, sel4, cen4, plan4
+    res["cfg1: prototype loss fwd+bwd, source variant, B8 C128 33x33 K5 (configs[0], the reference's CPU-runnable case)"] = \
+        cfg1_line(dev, timed)
     # cfg3: sampled pixel<->pixel loss, 4096 anchors x 16384 contrast rows, d = 256, bf16 tensor cores
     del f5, p5, part5, lab5, g5, s5
     res.update(p2p_kernels(dev, gen))
     return res
+
+
+def cfg1_line(dev, timed):
+    """BASELINE configs[0] at FULL size on both sides (no sampling): 8 x 128 x 33 x 33 features (the 2048->128 projection
+    is outside the path), labels 8 x 256 x 256 downsampled inside mpcl_loss_calc (utils/loss.py:585-590), K = 5, m = 0.4.
+    8 712 pixels: launch-latency-bound on the GPU.  HW = 1089 is odd -> the scalar (VEC = 1) kernels."""
+    from slcl.loss import MPCL, mpcl_loss_calc
+    from slcl.plan import ProtoPlan
+    from oracle import slcl_oracle as O
+    g = torch.Generator().manual_seed(CFG["seed"] + 11)
+    f_h = torch.randn(8, 128, 33, 33, generator=g)
+    lab_h = torch.randint(0, 5, (8, 256, 256), generator=g)
+    cen_h = torch.randn(5, 128, generator=g)
+    f1, lab1, cen1 = f_h.to(dev).requires_grad_(True), lab_h.to(dev), cen_h.to(dev)
+    mp = MPCL(dev, num_class=5, temperature=CFG["temperature"], m=0.4, base_temperature=CFG["base_temperature"])
+
+    def api_step():
+        f1.grad = None
+        loss = mpcl_loss_calc(f1, lab1, cen1, mp, tag="source")
+        loss.backward()
+        return loss
+    ms_api = timed(api_step, iters=20)
+    loss_gpu = float(api_step())
+    lab_ds = O.nearest_label_resize(lab_h, 33, 33).reshape(-1).long().to(dev)        # label resize outside the graph
+    plan = ProtoPlan(f1.detach(), lab_ds, None, cen1, 5, CFG["temperature"], CFG["base_temperature"], 0.4)
+    graph = plan.capture_graph()
+    ms_graph = timed(graph.replay, iters=50)
+    # CPU port on the same full config, all host threads
+    spec = O.MarginSpec(num_class=5, temperature=CFG["temperature"], m=0.4, base_temperature=CFG["base_temperature"])
+    fc = f_h.clone().requires_grad_(True)
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def cpu_step():
+        fc.grad = None
+        loss = O.mpcl_loss_calc(fc, lab_h, cen_h, spec, tag="source")
+        loss.backward()
+        return float(loss.detach())
+    for _ in range(2):
+        loss_cpu = cpu_step()
+    cpu_times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        cpu_step()
+        cpu_times.append(time.perf_counter() - t0)
+    n_px = 8 * 33 * 33
+    return {"ms_api_eager": ms_api, "ms_one_cuda_graph": ms_graph, "pixels_per_s_graph": n_px / (ms_graph * 1e-3),
+            "pixels_per_s_api_eager": n_px / (ms_api * 1e-3), "cpu_port_ms": 1e3 * min(cpu_times),
+            "cpu_port_pixels_per_s": n_px / min(cpu_times), "cpu_cores": os.cpu_count(),
+            "loss_gpu": loss_gpu, "loss_cpu_port": loss_cpu, "loss_rel_diff": abs(loss_gpu - loss_cpu) / abs(loss_cpu),
+            "bound": "launch latency (8 712 pixels, 4.5 MB): API = label resize + custom ops, graph = prep/forward/finalise/backward only"}
 
 
 def p2p_kernels(dev, gen):
