@@ -656,7 +656,7 @@ def cfg1_line(dev, timed):
         loss.backward()
         return loss
     ms_api = timed(api_step, iters=20)
-    loss_gpu = float(api_step())
+    loss_gpu = float(api_step().detach())
     lab_ds = O.nearest_label_resize(lab_h, 33, 33).reshape(-1).long().to(dev)        # label resize outside the graph
     plan = ProtoPlan(f1.detach(), lab_ds, None, cen1, 5, CFG["temperature"], CFG["base_temperature"], 0.4)
     graph = plan.capture_graph()
