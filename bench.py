@@ -378,8 +378,10 @@ def run_slcl(args):
     # configs[3]/[4]: the MCCL loss section of one adaptation step at the cfg5 geometry, through the Python API inside
     # autograd, with the centroid all-reduce over NCCL when N > 1 (every rank runs it; rank 0 reports the max)
     mccl = None
+    cfg4 = None
     if not args.no_extras:
         mccl = mccl_loss_section(dev, world)
+        cfg4 = cfg4_strong_scaling(dev, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -413,6 +415,9 @@ def run_slcl(args):
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
+    if cfg4 is not None:
+        cfg4["frac_of_hbm_peak"] = cfg4["achieved_GBps_aggregate"] / (world * peak)
+        out["cfg4_strong_scaling"] = cfg4
     if mccl is not None:
         mccl["frac_of_hbm_peak"] = mccl["achieved_GBps_per_gpu"] / peak
         out["mccl_loss_section"] = mccl
@@ -447,6 +452,70 @@ def run_slcl(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg4_strong_scaling(dev, world, rank):
+    """configs[3]: the MS-CMRSeg bSSFP->LGE shape, a FIXED global batch of 128 images (C = 32, 224 x 224,
+    K = 4) sharded over the ranks (128 / N images per GPU: STRONG scaling), prototype loss forward + backward with the
+    8-byte {weight sum, weighted row-loss sum} all-reduce + rescale between them, and the EMA class-centre update
+    (class sums all-reduced as [K, C+1] fp64) on the same shard.  Aggregate pixels/s = 6 422 528 px / max-over-ranks time."""
+    import torch.distributed as dist
+    from slcl.plan import ProtoPlan
+    from slcl.utils_ import update_class_center_iter
+    from slcl.distributed import shard_range
+    B, c, h, k = 128, 32, 224, 4
+    lo, hi = shard_range(B, rank, world)
+    b = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    f = torch.randn(b, c, h, h, device=dev, generator=gen)
+    lab = torch.randint(0, k, (b, h, h), device=dev, generator=gen)
+    sel = (torch.rand(b * h * h, device=dev, generator=gen) > 0.3).float()
+    cen = torch.randn(k, c, device=dev, generator=gen)
+    if world > 1:
+        dist.broadcast(cen, 0)
+    plan = ProtoPlan(f, lab.reshape(-1), sel, cen, k, CFG["temperature"], CFG["base_temperature"], CFG["margin"])
+    group = True if world > 1 else None
+
+    def proto_step():
+        scal = plan.forward()
+        if world > 1:
+            dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
+            plan.rescale()
+        plan.backward()
+        return scal
+
+    def ema_step():
+        return update_class_center_iter(f, lab, cen, m=0.9, num_class=k, group=group)
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            out = fn()
+        e.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), out
+
+    ms_proto, scal = timed(proto_step)
+    ms_ema, new_cen = timed(ema_step)
+    n_global = B * h * h
+    bytes_proto = (12 * c + 24) * n_global
+    return {"workload": f"cfg4: global batch 128 x 32 x 224 x 224, K=4, {b} images on this GPU ({world} GPUs, strong scaling): "
+                        "prototype loss fwd+bwd (raw C-ABI plan) and the EMA class-centre update (Python API)",
+            "scaling": "strong", "n_gpus": world, "global_pixels": n_global,
+            "proto_fwd_bwd_ms": ms_proto, "proto_pixels_per_s": n_global / (ms_proto * 1e-3),
+            "algorithmic_bytes_global": bytes_proto, "achieved_GBps_aggregate": bytes_proto / (ms_proto * 1e-3) / 1e9,
+            "ema_class_centres_ms": ms_ema, "ema_pixels_per_s": n_global / (ms_ema * 1e-3),
+            "ema_achieved_GBps_aggregate": (4 * c + 8) * n_global / (ms_ema * 1e-3) / 1e9, "loss": float(scal[0]),
+            "exchange": "8-byte all-reduce (loss pair) + [K, C+1] fp64 class sums, NCCL" if world > 1 else "none"}
 
 
 def mccl_loss_section(dev, world):
