@@ -287,6 +287,25 @@ def run_slcl(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = []
 
+    # N > 1: the 8-byte exchange between forward and backward goes through NVLink peer memory inside our own rescale kernel
+    # (slcl_proto_rescale_peer); NCCL all-reduce + rescale when symmetric memory cannot be set up on this box
+    mailbox, exchange_how = None, "none"
+    if world > 1:
+        ok = torch.zeros(1, device=dev)
+        why = ""
+        if os.environ.get("SLCL_BENCH_EXCHANGE", "peer") == "peer":
+            try:
+                from slcl.peer import PeerMailbox
+                mailbox = PeerMailbox(dev)
+                ok.fill_(1.0)
+            except Exception as exc:  # noqa: BLE001
+                why = repr(exc)[:160]
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
+        if float(ok) < 1.0:
+            mailbox = None
+        exchange_how = ("fused exchange + rescale kernel over NVLink peer memory (8-byte {epoch|fp32} stores into every "
+                        "peer's mailbox)") if mailbox is not None else f"NCCL all-reduce of 8 bytes + rescale kernel ({why})"
+
     def step(record: bool):
         e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
         if record:
@@ -294,7 +313,9 @@ def run_slcl(args):
         scal = plan.forward()
         if record:
             e1.record()
-        if world > 1:
+        if mailbox is not None:
+            plan.rescale_peer(mailbox)
+        elif world > 1:
             dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
             plan.rescale()
         if record:
@@ -331,6 +352,22 @@ def run_slcl(args):
     bwd_ms = statistics.mean(m[2].elapsed_time(m[3]) for m in marks)
     loss_value = float(scal[0])
     launches_per_step = 4 + (1 if world > 1 else 0)
+    exchange_check = None
+    if mailbox is not None:
+        # the peer exchange must give what the NCCL all-reduce gives
+        d_peer = dfeat.clone()
+        scal_n = plan.forward()
+        dist.all_reduce(scal_n[2:4], op=dist.ReduceOp.SUM)
+        plan.rescale()
+        d_nccl = plan.backward()
+        torch.cuda.synchronize(dev)
+        rel = abs(float(scal_n[0]) - loss_value) / max(abs(float(scal_n[0])), 1e-30)
+        gdiff = float((d_peer - d_nccl).abs().max()) / max(float(d_nccl.abs().max()), 1e-30)
+        exchange_check = {"loss_rel_diff_vs_nccl": rel, "grad_max_abs_diff_over_max_abs": gdiff,
+                          "timeouts": mailbox.timeouts()}
+        if not (rel < 1e-6 and gdiff < 1e-6 and exchange_check["timeouts"] == 0):
+            raise SystemExit(f"[bench] peer exchange disagrees with NCCL: {exchange_check}")
+        del d_peer, d_nccl
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
@@ -410,11 +447,13 @@ def run_slcl(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": n_px,
                    "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
-                   "parallelism": f"dp{world} (batch sharded; 8-byte loss all-reduce)" if world > 1 else "single GPU",
+                   "parallelism": f"dp{world} (batch sharded; {exchange_how})" if world > 1 else "single GPU",
                    "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
+    if exchange_check is not None:
+        out["exchange_check"] = exchange_check
     if cfg4 is not None:
         cfg4["frac_of_hbm_peak"] = cfg4["achieved_GBps_aggregate"] / (world * peak)
         out["cfg4_strong_scaling"] = cfg4

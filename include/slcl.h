@@ -108,6 +108,17 @@ int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float*
  * call recomputes scal[0] (global loss) and scal[1] (global coefficient) in place. */
 int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream);
 
+/* The same exchange + rescale fused into ONE kernel over NVLink peer memory (no collective launch between forward and
+ * backward): every rank owns a zero-initialised mailbox of slcl_peer_mailbox_bytes(world) bytes in memory that all ranks
+ * of the box have mapped (e.g. torch.distributed._symmetric_memory); peer_mailboxes_dev is a DEVICE array of `world`
+ * pointers, entry r = rank r's mailbox in this process' address space.  Each rank stores {epoch | fp32} words into every
+ * peer's mailbox, polls its own until all ranks of this call have arrived, adds scal[2..3] in rank order and rewrites
+ * scal[0..3] exactly as all-reduce + slcl_proto_rescale would.  Every rank must make the same sequence of calls.
+ * A peer that never arrives poisons scal with NaN after 5 s instead of hanging (mailbox word 1 counts time-outs). */
+size_t slcl_peer_mailbox_bytes(int world);
+int slcl_proto_rescale_peer(float* scal, int has_sel, const void* peer_mailboxes_dev, int rank, int world,
+                            slcl_stream_t stream);
+
 /* Backward w.r.t. the feature map.  grad_out: device scalar dL/dloss.
  * dfeat uses the strides of `map`. */
 int slcl_proto_bwd(const float* feat, const slcl_map_t* map,

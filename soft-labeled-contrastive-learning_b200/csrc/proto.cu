@@ -353,6 +353,66 @@ __global__ void proto_rescale_kernel(float* scal, int has_sel) {
   }
 }
 
+// The same exchange + rescale as ONE kernel over NVLink peer memory (no NCCL launch between forward and backward):
+// every rank owns a mailbox in symmetric memory (peers[r] = rank r's mailbox mapped into THIS rank's address space),
+//   word 0            : this rank's call counter ("epoch"; only its own kernel touches it)
+//   word 1            : number of time-outs seen (diagnostic)
+//   word 2 + ((q * world + r) * 2 + v) : value v (0 = weight sum, 1 = weighted row-loss sum) of sender r for epoch
+//                       parity q, packed {epoch : 32 | fp32 bits : 32} in ONE 8-byte word -- an aligned 8-byte store is
+//                       single-copy atomic, so the flag and the payload arrive together and no fence is needed (the
+//                       low-latency protocol NCCL calls LL).
+// A rank stores its two words into every peer's mailbox (NVLink P2P stores), then polls its OWN mailbox until all
+// `world` senders show this epoch, adds the values in rank order (identical on every rank) and writes scal[0..3].
+// Two parities suffice: a sender can only be two calls ahead of a reader that has not finished reading.
+constexpr int kMaxPeers = 16;
+__global__ void __launch_bounds__(64) proto_rescale_peer_kernel(float* scal, int has_sel, unsigned long long* const* peers,
+                                                                int rank, int world) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float vals[2 * kMaxPeers];
+  __shared__ unsigned int s_epoch;
+  unsigned long long* mine = peers[rank];
+  if (threadIdx.x == 0) {
+    const unsigned int e = (unsigned int)mine[0] + 1u;
+    mine[0] = e;
+    s_epoch = e;
+  }
+  __syncthreads();
+  const unsigned int e = s_epoch, q = e & 1u;
+  const int t = threadIdx.x;
+  if (t < 2 * world) {
+    const int p = t >> 1, v = t & 1;                          // destination rank, value index
+    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(scal[2 + v]);
+    volatile unsigned long long* dst = peers[p] + 2 + ((q * world + rank) * 2 + v);
+    *dst = w;
+    // the same thread now waits for sender p's value v in this rank's own mailbox
+    volatile unsigned long long* src = mine + 2 + ((q * world + p) * 2 + v);
+    unsigned long long t0, now, got;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      got = *src;
+      if ((unsigned int)(got >> 32) == e) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 5000000000ull) {                          // 5 s: a peer never arrived -- poison instead of hanging
+        got = 0x7FC00000ull;
+        atomicAdd(mine + 1, 1ull);
+        break;
+      }
+    }
+    vals[t] = __uint_as_float((unsigned int)got);
+  }
+  __syncthreads();
+  if (t == 0) {
+    float wsum = 0.f, lsum = 0.f;
+    for (int r = 0; r < world; ++r) { wsum += vals[2 * r]; lsum += vals[2 * r + 1]; }
+    const float coef = has_sel ? 1.0f / (wsum + 1e-4f) : 1.0f / wsum;
+    scal[0] = lsum * coef;
+    scal[1] = coef;
+    scal[2] = wsum;
+    scal[3] = lsum;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // backward: dF = gamma * ( sum_k a_k chat_k - b x )
 // ---------------------------------------------------------------------------
@@ -644,6 +704,20 @@ extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream
   if (!scal) return SLCL_ERR_INVALID_ARGUMENT;
   launch_pdl(proto_rescale_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream_, scal, has_sel);
   return check_launch("slcl_proto_rescale");
+}
+
+extern "C" size_t slcl_peer_mailbox_bytes(int world) {
+  if (world < 1 || world > kMaxPeers) return 0;
+  return (size_t)(2 + 4 * world) * sizeof(unsigned long long);
+}
+
+extern "C" int slcl_proto_rescale_peer(float* scal, int has_sel, const void* peer_mailboxes_dev, int rank, int world,
+                                       slcl_stream_t stream_) {
+  if (!scal || !peer_mailboxes_dev || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  launch_pdl(proto_rescale_peer_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream_, scal, has_sel,
+             reinterpret_cast<unsigned long long* const*>(peer_mailboxes_dev), rank, world);
+  return check_launch("slcl_proto_rescale_peer");
 }
 
 extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,

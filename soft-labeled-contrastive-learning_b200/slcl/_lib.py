@@ -50,6 +50,8 @@ SIGNATURES = {
     "slcl_proto_fwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, _P, _SZ, _P]),
     "slcl_proto_fwd_target": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "slcl_proto_rescale": (C.c_int, [_P, C.c_int, _P]),
+    "slcl_peer_mailbox_bytes": (_SZ, [C.c_int]),
+    "slcl_proto_rescale_peer": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "slcl_proto_bwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P]),
     "slcl_proto_bwd_centres_workspace_bytes": (_SZ, [_I64, _I64, C.c_int]),
     "slcl_proto_bwd_centres": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _SZ, _P]),

@@ -49,6 +49,11 @@ def test_argument_validation_without_gpu():
                             None, None, 0, None) == -1
     assert lib.slcl_p2p_state_bytes(4096, 256) >= 4096 * 256 * 4
     assert lib.slcl_p2p_state_bytes(0, 256) == 0 and lib.slcl_p2p_workspace_bytes(4096, 16384, 512) == 0
+    # peer-memory exchange: mailbox = 2 header words + 2 parities x world senders x 2 values, 8 bytes each; 1..16 ranks
+    assert lib.slcl_peer_mailbox_bytes(8) == (2 + 4 * 8) * 8 and lib.slcl_peer_mailbox_bytes(0) == 0
+    assert lib.slcl_peer_mailbox_bytes(17) == 0
+    assert lib.slcl_proto_rescale_peer(None, 1, None, 0, 2, None) == -1
+    assert lib.slcl_proto_rescale_peer(16, 1, 16, 2, 2, None) == -1       # rank out of range
     assert lib.slcl_p2p_workspace_bytes(4096, 16384, 256) > 0
 
 
