@@ -14,6 +14,23 @@ from . import ops  # noqa: F401  (registers torch.ops.slcl.*)
 _ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
+def _exchange_loss_pair(scal, has_sel: bool, group) -> None:
+    """Data-parallel prototype loss: global mean = summed numerator / summed denominator.
+    ``group``: None (single process), True / a ProcessGroup (NCCL all-reduce of scal[2:4] + rescale), or a
+    ``slcl.peer.PeerMailbox`` (exchange + rescale as ONE kernel over NVLink peer memory)."""
+    if group is None:
+        return
+    from .peer import PeerMailbox
+    if isinstance(group, PeerMailbox):
+        if group.world > 1:
+            _ops.proto_rescale_peer(scal, has_sel, group.ptrs_dev, group.rank, group.world)
+        return
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
+        dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
+        _ops.proto_rescale(scal, has_sel)
+
+
 class _ProtoLoss(torch.autograd.Function):
     """MPCL.forward (+ the normalise/layout work of mpcl_loss_calc): reference
     utils/loss.py:484-573, :592-601.  Backward: appendix A.1."""
@@ -24,12 +41,7 @@ class _ProtoLoss(torch.autograd.Function):
         scal, stash, cstate = _ops.proto_fwd(feat.detach(), labels, None if soft_mask is None else soft_mask.detach(),
                                              None if sel is None else sel.detach(), centres.detach(), rows_layout,
                                              n_class, temperature, base_temperature, margin, easy_margin, normalize)
-        if group is not None:
-            # data-parallel: global mean = all-reduced numerator / denominator
-            import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
-                dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
-                _ops.proto_rescale(scal, sel is not None)
+        _exchange_loss_pair(scal, sel is not None, group)
         ctx.save_for_backward(feat, stash, cstate, scal)
         ctx.cfg = (rows_layout, n_class, normalize)
         ctx.soft = soft_mask is not None and soft_mask.requires_grad
@@ -60,11 +72,7 @@ class _ProtoTargetStep(torch.autograd.Function):
     def forward(ctx, feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin, group):
         scal, stash, cstate, label, sel = _ops.proto_fwd_target(feat.detach(), centres.detach(), sel_threshold, n_class,
                                                                 temperature, base_temperature, margin, easy_margin)
-        if group is not None:
-            import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
-                dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
-                _ops.proto_rescale(scal, True)
+        _exchange_loss_pair(scal, True, group)
         ctx.save_for_backward(feat, stash, cstate, scal)
         ctx.n_class = n_class
         ctx.mark_non_differentiable(label, sel)

@@ -159,6 +159,16 @@ def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     check(st, "slcl_proto_rescale")
 
 
+@torch.library.custom_op("slcl::proto_rescale_peer", mutates_args=("scal",), device_types="cuda")
+def proto_rescale_peer(scal: Tensor, has_sel: bool, peer_mailboxes_dev: int, rank: int, world: int) -> None:
+    """Exchange scal[2:4] with the other ranks through NVLink peer mailboxes (slcl.peer.PeerMailbox) and rescale,
+    in one kernel; every rank must call it in the same order."""
+    dev = require_cuda(scal)
+    with _guard(dev):
+        st = _lib.load().slcl_proto_rescale_peer(ptr(scal), int(has_sel), peer_mailboxes_dev, rank, world, stream_ptr(dev))
+    check(st, "slcl_proto_rescale_peer")
+
+
 @torch.library.custom_op("slcl::proto_bwd", mutates_args=(), device_types="cuda")
 def proto_bwd(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_out: Tensor, rows_layout: bool,
               n_class: int, normalize: bool) -> Tensor:
