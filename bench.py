@@ -12,7 +12,8 @@ fp32 pixel-selection mask, [5,128] class centres, T=0.1, base_T=1, m=0.2.
 A step = one forward + backward of the prototype loss (reference mpcl_loss_calc + MPCL.forward,
 utils/loss.py:576-605,484-573 and its autograd backward): 3 forward launches (centre prep, fused
 loss, finalise) + 1 backward launch; with N>1 the loss is the mean over the GLOBAL batch, so one
-8-byte NCCL all-reduce + a rescale launch sit between forward and backward.
+8-byte exchange sits between forward and backward -- done by our own rescale kernel over NVLink peer memory
+(slcl_proto_rescale_peer), or by an NCCL all-reduce + rescale launch when symmetric memory is unavailable.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.  No L2 flush is needed: every step streams

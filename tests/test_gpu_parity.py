@@ -715,6 +715,31 @@ def test_p2p_plan_graph_replay_matches_eager_launches():
     assert torch.equal(plan.loss, loss0) and torch.equal(plan.d_a, da0)
 
 
+def test_peer_exchange_kernel_single_rank_matches_rescale():
+    """slcl_proto_rescale_peer with a world of one (the rank's own mailbox in ordinary device memory): the kernel stores its
+    {epoch | fp32} words, finds them again, and must rewrite scal exactly as slcl_proto_rescale does -- over several calls,
+    so both epoch parities and the slot reuse are exercised.  (The multi-rank exchange is checked against NCCL inside
+    bench.py at N > 1, before anything is timed.)"""
+    from slcl import _lib
+    from slcl._lib import check, ptr
+    lib = _lib.load()
+    n_words = lib.slcl_peer_mailbox_bytes(1) // 8
+    assert n_words == 6
+    mailbox = torch.zeros(n_words, dtype=torch.int64, device=dev())
+    peers = torch.tensor([mailbox.data_ptr()], dtype=torch.int64, device=dev())
+    stream = torch.cuda.current_stream().cuda_stream
+    g = cases.g(5)
+    for call in range(5):
+        for has_sel in (0, 1):
+            vals = torch.rand(4, generator=g) * 1000 + 1
+            a, b = vals.to(dev()), vals.to(dev())
+            check(lib.slcl_proto_rescale_peer(ptr(a), has_sel, peers.data_ptr(), 0, 1, stream), "slcl_proto_rescale_peer")
+            check(lib.slcl_proto_rescale(ptr(b), has_sel, stream), "slcl_proto_rescale")
+            torch.cuda.synchronize()
+            assert torch.equal(a, b), (call, has_sel, a, b)
+    assert int(mailbox[0]) == 10 and int(mailbox[1]) == 0          # ten calls counted, no time-outs
+
+
 def test_c_abi_called_directly_with_ctypes():
     """The INTEGRATION.md stub: raw ctypes against include/slcl.h, no torch custom-op layer in between."""
     import ctypes as C
