@@ -175,3 +175,22 @@ def test_segmentation_losses_and_entropy(ref, seed):
         same(O.dice_loss(pred, lab), ref.dice_loss(pred, lab))
     prob = torch.softmax(pred, 1)
     same(O.prob_2_entropy(prob), ref.prob_2_entropy(prob))
+
+
+@pytest.mark.parametrize("seed,t", [(101, 0.5), (102, 0.1)])
+def test_iscl_loss_and_gradient(ref, seed, t):
+    """InterpolatedSupervisedContrastiveLoss (utils/losses.py:6-81): two label sets mixed per sample over one Gram matrix."""
+    gen = g(seed)
+    n, c = 48, 20
+    feats = torch.randn(n, c, generator=gen)
+    l1 = torch.randint(0, 4, (n,), generator=gen)
+    l2 = torch.randint(0, 4, (n,), generator=gen)
+    lam = torch.rand(n, generator=gen)
+    dom = torch.where(lam >= 0.5, l1, l2)
+    fr, fo = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+    want = ref.ISCL(t)(fr, l1, l2, dom, lam)
+    got = O.iscl_loss(fo, l1, l2, dom, lam, t)
+    same(got, want, rtol=1e-5)
+    want.backward()
+    got.backward()
+    same(fo.grad, fr.grad, rtol=1e-4, atol=1e-7)
