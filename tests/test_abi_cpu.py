@@ -162,3 +162,15 @@ def test_centre_state_in_checkpoint_dict(tmp_path):
     assert torch.equal(state.from_checkpoint(old_style, device="cpu", fallback_npy=src), cc)
     with pytest.raises(KeyError):
         state.from_checkpoint(old_style, device="cpu")
+
+
+def test_peer_mailbox_needs_a_process_group_and_the_exchange_is_a_noop_without_a_group():
+    """slcl.peer / the loss-pair exchange on a host without GPUs: no silent degradation -- a mailbox cannot be built without
+    an initialised process group, and group=None leaves the scalars alone (single-process semantics)."""
+    from slcl.peer import PeerMailbox
+    from slcl.functional import _exchange_loss_pair
+    with pytest.raises(RuntimeError):
+        PeerMailbox("cpu")
+    scal = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    _exchange_loss_pair(scal, True, None)
+    assert scal.tolist() == [1.0, 2.0, 3.0, 4.0]
