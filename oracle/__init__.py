@@ -13,7 +13,10 @@ Pinning status (see DESIGN.md "Oracle"):
     ``slcl_oracle.py`` is checked against outputs of the reference's own
     functions (``tests/golden/*.npz``, produced by ``oracle/make_golden.py``
     which imports ``/root/reference`` in the build container) and against
-    the nine known-answer values of SURVEY.md section 8(c).
+    the nine known-answer values of SURVEY.md section 8(c); where the
+    reference tree is mounted, ``tests/test_oracle_live_reference.py`` also runs
+    the reference's callables and the restatement side by side on randomised
+    inputs (losses and gradients, 30 cases; seg losses and ISCL included).
   * soft-label centroid path: pinned against the reference function with the
     one-line repair described in SURVEY.md section 0 (the shipped function
     raises NameError).
