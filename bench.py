@@ -46,13 +46,23 @@ WORKLOAD = ("cfg2: SLCL prototype path (mpcl_loss_calc+MPCL fwd+bwd, target vari
 FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def base_config(world: int):
+    """`config` of the JSON line: identical for the product arm and the reference arm (same workload, same batch)."""
+    B, C, H, W, K = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["K"]
+    return {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": B * H * W,
+            "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
+            "parallelism": f"dp{world} (batch sharded, one process per GPU)" if world > 1 else "single GPU",
+            "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="slcl", choices=["slcl", "reference"])
-    ap.add_argument("--cpu-sample-images", type=int, default=4, help="images of the cfg2 shape per CPU step")
+    ap.add_argument("--cpu-sample-images", type=int, default=CFG["B"],
+                    help="images of the cfg2 shape per CPU step (default: the full batch of 32, the product arm's config)")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table of the other path kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -235,13 +245,16 @@ def run_reference(args):
     pixels, times, cores = time_cpu(n_img, max(args.warmup, 1), args.steps)
     total = sum(times)
     value = pixels * len(times) / total
-    sample = (f"{n_img} of the 32 images of the cfg2 batch per step ({pixels} px, same shapes/hyper-parameters); "
-              f"oracle port of mpcl_loss_calc+MPCL.forward fwd+bwd (torch CPU ops, fp32)")
+    sample = (("the full cfg2 batch per step" if n_img == CFG["B"] else f"{n_img} of the 32 images of the cfg2 batch per step")
+              + f" ({pixels} px, same shapes/hyper-parameters); oracle port of mpcl_loss_calc+MPCL.forward fwd+bwd "
+                f"(torch CPU ops, fp32, {cores} threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample of the workload per step"},
+        "config": base_config(args.gpus),
+        "note": "CPU arm: the reference's op sequence (oracle port; /root/reference is pure Python and not on the GPU box) on "
+                "the box's host cores, rank 0 only",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -265,6 +278,18 @@ def run_slcl(args):
         raise SystemExit("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one slice of the host cores per rank, set BEFORE the pinned buffers are first touched (NUMA placement follows the
+    # touching thread); SLCL_BENCH_AFFINITY=0 leaves the scheduler alone
+    affinity = "unchanged"
+    if world > 1 and os.environ.get("SLCL_BENCH_AFFINITY", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+            os.sched_setaffinity(0, mine)
+            affinity = f"rank pinned to {len(mine)} of {len(cpus)} host cpus ({mine[0]}..{mine[-1]})"
+        except Exception as exc:  # noqa: BLE001
+            affinity = f"unchanged ({exc!r})"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -348,6 +373,12 @@ def run_slcl(args):
             mailbox = None
             exchange_how = f"NCCL all-reduce of 8 bytes + rescale kernel (peer exchange failed its check: {exchange_check})"
 
+    sharded_check = None
+    if world > 1:
+        sharded_check = sharded_vs_global_check(dev, world, rank, mailbox)
+        if not sharded_check["ok_on_every_rank"]:
+            print(f"[bench] rank {rank}: SHARDED RESULT DIFFERS FROM THE GLOBAL ONE: {sharded_check}", file=sys.stderr)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -410,11 +441,45 @@ def run_slcl(args):
             ms = float(t.item())
         h2d = feats_h.numel() * 4 + labels_h.numel() * 8 + sel_h.numel() * 4
         d2h = grad_h.numel() * 4 + 4
+        # what the box's IO fabric gives at this N: plain pinned cudaMemcpyAsync of the same buffers, all ranks at once --
+        # H2D alone, D2H alone, both directions together (the e2e step needs both)
+        dbuf = torch.empty_like(feats_h, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def copy_ceiling(do_in, do_out):
+            barrier()
+            c0, c1 = ev(), ev()
+            c0.record()
+            s_in.wait_event(c0); s_out.wait_event(c0)
+            for _ in range(3):
+                if do_in:
+                    with torch.cuda.stream(s_in):
+                        dbuf.copy_(feats_h, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s_out):
+                        grad_h.copy_(dbuf, non_blocking=True)
+            torch.cuda.current_stream(dev).wait_stream(s_in); torch.cuda.current_stream(dev).wait_stream(s_out)
+            c1.record()
+            barrier()
+            t_ms = c0.elapsed_time(c1)
+            if world > 1:
+                tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ms = float(tt.item())
+            return 3 * feats_h.numel() * 4 / (t_ms * 1e-3) / 1e9
+        pcie = {"h2d_alone_GBps_per_gpu": copy_ceiling(True, False), "d2h_alone_GBps_per_gpu": copy_ceiling(False, True),
+                "duplex_GBps_per_gpu_each_way": copy_ceiling(True, True)}
+        del dbuf
         e2e = {"value": world * n_px * n_e2e / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms / n_e2e,
                "api": f"slcl.host.mpcl_loss_and_grad_host(pinned feats/labels/sel -> loss, pinned dF): {E2E_CHUNK}-image chunks, "
                       "H2D / kernels / D2H overlapped on 3 streams",
-               "loss": float(loss_h)}
+               "loss": float(loss_h),
+               "achieved_h2d_GBps_per_gpu": h2d * n_e2e / (ms * 1e-3) / 1e9, "achieved_d2h_GBps_per_gpu": d2h * n_e2e / (ms * 1e-3) / 1e9,
+               "memcpy_ceiling_same_n": pcie, "cpu_affinity": affinity,
+               "bound": "host<->device copies: the step moves %.2f GB in and %.2f GB out per GPU; compare achieved_*_GBps with "
+                        "memcpy_ceiling_same_n.duplex (plain pinned cudaMemcpyAsync, all ranks at once) -- when they agree the "
+                        "number is set by the box's PCIe / host-memory fabric, not by the kernels" % (h2d / 1e9, d2h / 1e9)}
         del grad_h
     sampler.stop()
 
@@ -423,7 +488,7 @@ def run_slcl(args):
     mccl = None
     cfg4 = None
     if not args.no_extras:
-        mccl = mccl_loss_section(dev, world)
+        mccl = mccl_loss_section(dev, world, mailbox)
         cfg4 = cfg4_strong_scaling(dev, world, rank, mailbox)
 
     if rank != 0:
@@ -451,15 +516,14 @@ def run_slcl(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": C, "H": H, "W": W, "K": K, "pixels_per_gpu": n_px,
-                   "temperature": CFG["temperature"], "base_temperature": CFG["base_temperature"], "margin": CFG["margin"],
-                   "parallelism": f"dp{world} (batch sharded; {exchange_how})" if world > 1 else "single GPU",
-                   "l2": "no flush: each step streams a 1.07 GB feature map (> 126 MB L2)"},
+        "config": base_config(world), "exchange": exchange_how,
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(t_wall0, t_wall1), "loss": loss_value,
     }
     if exchange_check is not None:
         out["exchange_check"] = exchange_check
+    if sharded_check is not None:
+        out["sharded_vs_global_check"] = sharded_check
     if cfg4 is not None:
         cfg4["frac_of_hbm_peak"] = cfg4["achieved_GBps_aggregate"] / (world * peak)
         out["cfg4_strong_scaling"] = cfg4
@@ -492,11 +556,103 @@ def run_slcl(args):
             "value": pixels / min(times), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_img} of the 32 cfg2 images per step ({pixels} px), oracle port of the reference call sequence, "
                       f"fwd+bwd, min of 3 after 1 warm-up, torch CPU fp32 with {cores} threads"}
+        del times
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if sharded_check is not None and not sharded_check["ok_on_every_rank"]:
+        raise SystemExit("bench.py: sharded multi-GPU result differs from the single-GPU global result (see the JSON line)")
+
+
+def sharded_vs_global_check(dev, world, rank, mailbox):
+    """SURVEY 8(e) on the hardware that has N GPUs: before anything is timed, every rank ALSO evaluates the global batch
+    (small shape, identical bits on every rank) on its own GPU and compares its sharded result -- through the Python API,
+    with the NCCL route (group=True) and the peer-mailbox route (group=PeerMailbox) -- against it: prototype loss (source,
+    target, fused target step) loss rtol 1e-6 / gradients rtol 1e-5; update_class_center_iter and cal_centroid(soft, P=2)
+    centres rtol 1e-5 with class counts torch.equal; the host-buffer pipeline's loss.  A mismatch fails the run."""
+    import torch.distributed as dist
+    from slcl.loss import MPCL, mpcl_loss_calc, mpcl_target_step
+    from slcl.utils_ import cal_centroid, update_class_center_iter
+    from slcl.host import mpcl_loss_and_grad_host
+    op = torch.ops.slcl
+    b, c, h, w, k, parts = 2 * world, 32, 48, 40, 4, 2
+    g = torch.Generator().manual_seed(2024)
+    feat = torch.randn(b, c, h, w, generator=g).to(dev)
+    lab = torch.randint(0, k, (b, h, w), generator=g)
+    lab[lab == 3] = 1                     # an empty class: the empty-class rule must act on GLOBAL counts
+    lab = lab.to(dev)
+    sel = (torch.rand(b * h * w, generator=g) > 0.4).float().to(dev)
+    probs = torch.softmax(3 * torch.randn(b, k, h, w, generator=g), 1).to(dev)
+    part = (torch.randperm(b * h * w, generator=g) % parts).to(torch.int32).to(dev)
+    cen = torch.randn(k, c, generator=g).to(dev)
+    gcen = torch.randn(parts * k, c, generator=g).to(dev)
+    mp = MPCL(dev, num_class=k, temperature=0.1, m=0.4, base_temperature=1.0)
+    lo, hi = 2 * rank, 2 * rank + 2
+    px = lambda t: t.reshape(b, -1)[lo:hi].reshape(-1)
+
+    def rel(a, ref):
+        a, ref = a.detach().double(), ref.detach().double()
+        return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+    def proto(f, labels, selv, group):
+        l1 = mpcl_loss_calc(f, labels, cen, mp, tag="source", group=group)
+        l2 = mpcl_loss_calc(f, labels.reshape(-1), cen, mp, pixel_sel_loc=selv, tag="target", group=group)
+        l3, _, _ = mpcl_target_step(f, cen, mp, 0.05, group=group)
+        return l1, l2, l3
+
+    def centres(f, labels, p, pid, group):
+        new = update_class_center_iter(f, labels, cen, m=0.9, num_class=k, group=group)
+        soft, _, _ = cal_centroid(f, p, pseudo_label=True, weighted_ave=True, partition=parts, n_class=k, part_id=pid,
+                                  group=group)
+        return new, torch.cat(soft)
+
+    # global references on this rank's GPU
+    fg, pg = feat.clone().requires_grad_(True), probs.clone().requires_grad_(True)
+    want_l = proto(fg, lab, sel, None)
+    want_new, want_soft = centres(fg, lab, pg, part, None)
+    (want_l[0] + 2 * want_l[1] + 3 * want_l[2] + (want_soft * gcen).sum()).backward()
+    counts_g = op.class_sums(feat, lab.reshape(-1), None, False, 0.0, None, 1, k)[:, -1]
+
+    out, worst = {}, 0.0
+    routes = [("nccl", True)] + ([("peer", mailbox)] if mailbox is not None else [])
+    for name, group in routes:
+        f, p = feat[lo:hi].clone().requires_grad_(True), probs[lo:hi].clone().requires_grad_(True)
+        got_l = proto(f, lab[lo:hi], px(sel), group)
+        got_new, got_soft = centres(f, lab[lo:hi], p, px(part), group)
+        (got_l[0] + 2 * got_l[1] + 3 * got_l[2] + (got_soft * gcen).sum()).backward()
+        if name == "peer":
+            _, sums = op.class_centres_update(feat[lo:hi].contiguous(), lab[lo:hi].reshape(-1), cen, 0.9, *mailbox.args())
+        else:
+            sums = op.class_sums(feat[lo:hi].contiguous(), lab[lo:hi].reshape(-1), None, False, 0.0, None, 1, k)
+            dist.all_reduce(sums)
+        r = {"loss_rel": max(rel(a, b_) for a, b_ in zip(got_l, want_l)),
+             "dfeat_rel": rel(f.grad, fg.grad[lo:hi]), "dprobs_rel": rel(p.grad, pg.grad[lo:hi]),
+             "ema_centres_rel": rel(got_new, want_new), "soft_centroids_rel": rel(got_soft, want_soft),
+             "class_counts_equal": bool(torch.equal(sums[:, -1], counts_g))}
+        r["ok"] = (r["loss_rel"] < 1e-6 and r["dfeat_rel"] < 1e-5 and r["dprobs_rel"] < 1e-5 and r["ema_centres_rel"] < 1e-5
+                   and r["soft_centroids_rel"] < 1e-5 and r["class_counts_equal"])
+        out[name] = r
+    # host-buffer pipeline (slcl.host): the returned loss must be the GLOBAL loss, the gradient the global gradient's shard
+    grad_h = torch.empty((2, c, h, w), pin_memory=True)
+    loss_h, _ = mpcl_loss_and_grad_host(feat[lo:hi].cpu().pin_memory(), lab[lo:hi].cpu(), cen, mp,
+                                        pixel_sel_loc_h=px(sel).cpu(), grad_out_h=grad_h, device=dev, chunk_images=1, group=True)
+    torch.cuda.synchronize(dev)
+    fh = feat.clone().requires_grad_(True)
+    want_h = mpcl_loss_calc(fh, lab.reshape(-1), cen, mp, pixel_sel_loc=sel, tag="target")
+    want_h.backward()
+    r = {"loss_rel": rel(loss_h, want_h), "dfeat_rel": rel(grad_h.to(dev), fh.grad[lo:hi])}
+    r["ok"] = r["loss_rel"] < 1e-6 and r["dfeat_rel"] < 1e-5
+    out["host_pipeline"] = r
+    if mailbox is not None:
+        out["peer_timeouts"] = mailbox.timeouts()
+    ok = all(v["ok"] for v in out.values() if isinstance(v, dict)) and out.get("peer_timeouts", 0) == 0
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok_on_every_rank"] = bool(float(flag) == 1.0)
+    out["shape"] = f"global batch {b} x {c} x {h} x {w}, K={k}, P={parts}; 2 images per rank; rank-0 numbers"
+    return out
 
 
 def cfg4_strong_scaling(dev, world, rank, mailbox=None):
@@ -519,7 +675,7 @@ def cfg4_strong_scaling(dev, world, rank, mailbox=None):
     if world > 1:
         dist.broadcast(cen, 0)
     plan = ProtoPlan(f, lab.reshape(-1), sel, cen, k, CFG["temperature"], CFG["base_temperature"], CFG["margin"])
-    group = True if world > 1 else None
+    group = (mailbox if mailbox is not None else True) if world > 1 else None
 
     def proto_step():
         scal = plan.forward()
@@ -553,6 +709,28 @@ def cfg4_strong_scaling(dev, world, rank, mailbox=None):
 
     ms_proto, scal = timed(proto_step)
     ms_ema, new_cen = timed(ema_step)
+    # the same two steps as CUDA-graph replays (no NCCL on either path when the peer mailboxes are in use): device time
+    # without the Python dispatch of the eager API
+    ms_proto_graph = ms_ema_graph = None
+    if world == 1 or mailbox is not None:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                proto_step(); ema_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            g_proto, g_ema = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_proto):
+                proto_step()
+            with torch.cuda.graph(g_ema):
+                keep_ema = ema_step()          # noqa: F841
+            ms_proto_graph, _ = timed(g_proto.replay)
+            ms_ema_graph, _ = timed(g_ema.replay)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] cfg4: graph capture unavailable ({exc!r})", file=sys.stderr)
     n_global = B * h * h
     bytes_proto = (12 * c + 24) * n_global
     return {"workload": f"cfg4: global batch 128 x 32 x 224 x 224, K=4, {b} images on this GPU ({world} GPUs, strong scaling): "
@@ -560,14 +738,16 @@ def cfg4_strong_scaling(dev, world, rank, mailbox=None):
             "scaling": "strong", "n_gpus": world, "global_pixels": n_global,
             "proto_fwd_bwd_ms": ms_proto, "proto_pixels_per_s": n_global / (ms_proto * 1e-3),
             "algorithmic_bytes_global": bytes_proto, "achieved_GBps_aggregate": bytes_proto / (ms_proto * 1e-3) / 1e9,
+            "proto_fwd_bwd_graph_ms": ms_proto_graph, "ema_class_centres_graph_ms": ms_ema_graph,
             "ema_class_centres_ms": ms_ema, "ema_pixels_per_s": n_global / (ms_ema * 1e-3),
             "ema_achieved_GBps_aggregate": (4 * c + 8) * n_global / (ms_ema * 1e-3) / 1e9, "loss": float(scal[0]),
             "exchange": "none" if world == 1 else
                         ("loss pair: " + ("fused peer-memory exchange + rescale kernel" if mailbox is not None else "NCCL all-reduce")
-                         + "; EMA: NCCL all-reduce of the [K, C+1] fp64 class sums")}
+                         + "; EMA: " + ("class sums exchanged inside the reduce kernel over NVLink peer mailboxes"
+                                        if mailbox is not None else "NCCL all-reduce of the [K, C+1] fp64 class sums"))}
 
 
-def mccl_loss_section(dev, world):
+def mccl_loss_section(dev, world, mailbox=None):
     import torch.distributed as dist
     """Trainer_MCCL.py:275-332 between "the decoder produced feature maps" and "the loss has gradients": source centroids
     (hard labels), target and augmented-target centroids (soft labels x certainty, 2 reversed-Monte-Carlo partitions),
@@ -584,7 +764,9 @@ def mccl_loss_section(dev, world):
     pr = [torch.softmax(3 * torch.randn(b, k, h, h, device=dev, generator=gen), 1).requires_grad_(True) for _ in range(2)]
     part = [(torch.randperm(n_px, device=dev, generator=gen) % parts).to(torch.int32) for _ in range(2)]
     crit = ContrastiveLoss()
-    group = True if world > 1 else None
+    # N > 1: the [sets*K, C+1] fp64 class sums are exchanged inside the reduce kernels over the NVLink peer mailboxes (no
+    # collective launch, so the section is graph-capturable at every N); NCCL all-reduce when there is no mailbox
+    group = (mailbox if mailbox is not None else True) if world > 1 else None
 
     def make_step(ft, pr):
         def step():
@@ -623,7 +805,7 @@ def mccl_loss_section(dev, world):
 
     ms_eager, loss = timed(step)          # what a plain eager trainer sees: ~30 custom-op calls, host-launch-bound
     ms, how = ms_eager, "eager"
-    if world == 1:
+    if world == 1 or mailbox is not None:
         # the same step captured once in a CUDA graph (forward + autograd backward): the device time of the section
         try:
             # fresh leaves: their AccumulateGrad nodes must be born on the capture side stream, not the default one
@@ -647,7 +829,10 @@ def mccl_loss_section(dev, world):
             "ms_per_step": ms, "timed_as": how, "ms_per_step_eager": ms_eager,
             "pixels_per_s": world * 3 * n_px / (ms * 1e-3), "algorithmic_bytes_per_gpu": bytes_,
             "achieved_GBps_per_gpu": bytes_ / (ms * 1e-3) / 1e9, "n_gpus": world, "loss": float(loss),
-            "exchange": "all-reduce of [sets*K, C+1] fp64 class sums per cal_centroid (NCCL)" if world > 1 else "none"}
+            "exchange": "none" if world == 1 else
+                        ("[sets*K, C+1] fp64 class sums exchanged inside the reduce kernel of each cal_centroid over NVLink peer "
+                         "mailboxes (no collective launch)" if mailbox is not None else
+                         "all-reduce of [sets*K, C+1] fp64 class sums per cal_centroid (NCCL)")}
 
 
 def extra_kernels(dev, feats, labels, centres, peak):
@@ -910,11 +1095,14 @@ def main():
         else:
             orig_print(*a, **k)
     builtins.print = capture
+    failed = None
     try:
         if args.impl == "reference":
             run_reference(args)
         else:
             run_slcl(args)
+    except SystemExit as exc:          # the JSON line (if any) is still printed before the run fails
+        failed = exc
     finally:
         builtins.print = orig_print
         sys.stdout.flush()
@@ -922,6 +1110,8 @@ def main():
         os.close(real_stdout)
     for ln in lines:
         print(ln, flush=True)
+    if failed is not None:
+        raise failed
 
 
 if __name__ == "__main__":

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 100            /* major*100 + minor */
+#define SLCL_VERSION 110            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -108,16 +108,33 @@ int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float*
  * call recomputes scal[0] (global loss) and scal[1] (global coefficient) in place. */
 int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream);
 
-/* The same exchange + rescale fused into ONE kernel over NVLink peer memory (no collective launch between forward and
- * backward): every rank owns a zero-initialised mailbox of slcl_peer_mailbox_bytes(world) bytes in memory that all ranks
- * of the box have mapped (e.g. torch.distributed._symmetric_memory); peer_mailboxes_dev is a DEVICE array of `world`
- * pointers, entry r = rank r's mailbox in this process' address space.  Each rank stores {epoch | fp32} words into every
- * peer's mailbox, polls its own until all ranks of this call have arrived, adds scal[2..3] in rank order and rewrites
- * scal[0..3] exactly as all-reduce + slcl_proto_rescale would.  Every rank must make the same sequence of calls.
- * A peer that never arrives poisons scal with NaN after 5 s instead of hanging (mailbox word 1 counts time-outs). */
-size_t slcl_peer_mailbox_bytes(int world);
-int slcl_proto_rescale_peer(float* scal, int has_sel, const void* peer_mailboxes_dev, int rank, int world,
-                            slcl_stream_t stream);
+/* ---------------------------------------------------------------------------
+ * NVLink peer-memory mailboxes: the small exchanges of the data-parallel path -- the loss pair
+ * {sum sel, sum sel*row loss} and the per-class sums [sets*K, C+1] fp64 -- are done INSIDE our own kernels with P2P
+ * stores into the peers' mailboxes instead of NCCL collectives.  Every rank owns a zero-initialised mailbox of
+ * slcl_peer_mailbox_bytes(world, capacity_words) bytes in memory that all ranks of the box have mapped (e.g.
+ * torch.distributed._symmetric_memory); mailboxes_dev is a DEVICE array of `world` pointers, entry r = rank r's
+ * mailbox in this process' address space.  capacity_words = payload words per message (2 per double; >= 2).
+ * Every rank must make the same sequence of peer calls, on one stream per mailbox set.  A peer that does not arrive
+ * within timeout_s seconds (0 = wait for ever, like NCCL) poisons the result with NaN instead of hanging; mailbox
+ * word 1 counts such time-outs.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const void* mailboxes_dev;
+  int rank, world;            /* world <= 16 */
+  int64_t capacity_words;
+  double timeout_s;
+} slcl_peer_t;
+
+size_t slcl_peer_mailbox_bytes(int world, int64_t capacity_words);
+
+/* slcl_proto_rescale with the exchange fused in: ONE kernel that sends scal[2..3] to every peer, waits for theirs,
+ * adds in rank order and rewrites scal[0..3] exactly as all-reduce + slcl_proto_rescale would. */
+int slcl_proto_rescale_peer(float* scal, int has_sel, const slcl_peer_t* peer, slcl_stream_t stream);
+
+/* In-place sum over the ranks of buf[0..n) (fp64, added in rank order: identical bits on every rank); one kernel,
+ * one warp per element.  2*n <= capacity_words. */
+int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t* peer, slcl_stream_t stream);
 
 /* Backward w.r.t. the feature map.  grad_out: device scalar dL/dloss.
  * dfeat uses the strides of `map`. */
@@ -171,6 +188,26 @@ int slcl_ema_finalize(const double* sums, const float* old_centres, float m, int
  * Outputs centroids [sets*K, C] fp32 and inv_weight [sets*K] fp32 = 1/(weight+1e-7). */
 int slcl_centroid_finalize(const double* sums, const float* previous, float momentum, int n_sets, int n_class,
                            int64_t channels, float* centroids, float* inv_weight, slcl_stream_t stream);
+
+/* Fused forms (two launches: the sweep, then ONE kernel that sums the per-block partials in fp64, optionally
+ * all-reduces them across ranks through the peer mailboxes -- `peer` may be null -- and whose last block runs the
+ * finaliser):
+ *   slcl_class_centres_update = slcl_class_sums(hard labels) [+ all-reduce] + slcl_ema_finalize
+ *                               (update_class_center_iter, utils/utils_.py:568-594, over the GLOBAL batch)
+ *   slcl_centroids_fwd        = slcl_class_sums [+ all-reduce] + slcl_centroid_finalize
+ *                               (cal_centroid, utils/utils_.py:479-565)
+ * `sums` [P*K, C+1] fp64 is still written (the backward needs it); with `peer` it holds the GLOBAL sums, so class
+ * counts match a single-GPU run bit for bit.  Workspace: slcl_class_sums_workspace_bytes(). */
+int slcl_class_centres_update(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                              const int64_t* labels, int n_class, const float* old_centres, float m,
+                              float* new_centres, double* sums, const slcl_peer_t* peer,
+                              void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+int slcl_centroids_fwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                       const int64_t* labels, const float* probs, int weighted, float threshold,
+                       const int32_t* part_id, int n_partitions, int n_class,
+                       const float* previous, float momentum, float* centroids, float* inv_weight,
+                       double* sums, const slcl_peer_t* peer,
+                       void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 
 /* Backward of the (soft / hard) centroid of cal_centroid.
  * With gc_j = grad_centroids_j * ema_scale / (W_j + 1e-7) and mu_j = S_j / (W_j + 1e-7)

@@ -17,6 +17,7 @@
 // Per-block partials are summed in fp64 by a second tiny kernel in block
 // order (deterministic; exact integer counts beyond 2^24).
 #include "common.cuh"
+#include "peer.cuh"
 
 #include <cuda.h>
 #include <limits.h>
@@ -28,6 +29,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr size_t kTicketBytes = 256;     // tail of the workspace: the reduce kernel's block counter
 
 enum WeightMode { kHard = 0, kSoft = 1, kPlanar = 2 };
 
@@ -48,6 +50,7 @@ struct SumArgs {
   int n_cw;                         // v3: consumer warps in use (channels per block = n_cw * CPW)
   int n_stages;                     // v3: ring depth
   float* partial;            // [gridDim.x][KWT][C+1]
+  unsigned int* ticket;      // block counter of the reduce kernel (zeroed by the sweep, self-resetting)
 };
 
 template <int VEC>
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
   const int C = (int)a.channels;
   const int c0 = (blockIdx.y * a.cg_per_block + cg) * CPW;
   const bool count_weights = blockIdx.y == 0;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.ticket = 0u;
 
   float acc[CPW][KWT];
   float wacc[KWT];
@@ -385,6 +389,7 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
   const int64_t n_iter = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) *a.ticket = 0u;
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_feat)) : "memory");
     for (int s = 0; s < kV3Stages; ++s) {
       v3_mbar_init(&bars->x_full[s], 1);
@@ -585,46 +590,91 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
   }
 }
 
+// Finaliser folded into the reduce kernel (its last block runs it): 0 none, 1 EMA class centres
+// (utils_.py:585-592), 2 centroids (utils_.py:520-523 / :538, EMA :552-563).
+enum FinMode { kFinNone = 0, kFinEma = 1, kFinCentroid = 2 };
+struct FinArgs {
+  int mode;
+  const float* prev;     // kFinEma: old centres [K,C]; kFinCentroid: previous centroid [K,C] or null
+  float m;               // EMA momentum
+  int K;                 // classes (rows of prev)
+  float* out;            // [rows, C]
+  float* inv_w;          // kFinCentroid: [rows]
+};
+
+__device__ __forceinline__ void finalize_rows(const double* sums, const FinArgs& fin, int rows, int C, int first, int step) {
+  for (int idx = first; idx < rows * C; idx += step) {
+    const int r = idx / C, c = idx % C;
+    const double cnt = __ldcg(sums + (int64_t)r * (C + 1) + C);
+    const double sv = __ldcg(sums + (int64_t)r * (C + 1) + c);
+    if (fin.mode == kFinEma) {
+      const float old = fin.prev[idx];
+      float batch;
+      if (cnt == 0.0) batch = old;                                              // :585-586
+      else batch = (float)sv / (float)cnt;                                      // :588
+      fin.out[idx] = fin.m * old + (1.0f - fin.m) * batch;                      // :592
+    } else {
+      const float wsum = (float)cnt + 1e-7f;
+      float mu = (float)sv / wsum;
+      if (fin.prev != nullptr) mu = fin.m * fin.prev[(r % fin.K) * C + c] + (1.0f - fin.m) * mu;
+      fin.out[idx] = mu;
+      if (c == 0) fin.inv_w[r] = 1.0f / wsum;
+    }
+  }
+}
+
 // sums[col][c] = sum over blocks in fp64.  One warp per output element: lane l adds blocks l, l+32, ...
 // then a fixed-shape shuffle tree, so the result is deterministic and the serial chain is n_blocks/32 long.
+// PEER: the element is then all-reduced over the ranks through the NVLink mailboxes (peer.cuh) by the same warp --
+// the only cross-GPU exchange of the class-centre / centroid path, with no collective launch.  The block that
+// finishes last runs the finaliser over the complete `sums`.
+template <bool PEER>
 __global__ void __launch_bounds__(kThreads) class_sums_reduce_kernel(const float* partial, int n_blocks, int kwt,
-                                                                     int n_cols, int C, double* sums) {
+                                                                     int n_cols, int C, double* sums, const PeerCtx pc,
+                                                                     const FinArgs fin, unsigned int* ticket) {
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int row = C + 1;
-  if (idx >= n_cols * row) return;
-  const int col = idx / row, c = idx % row;
-  double t = 0.0;
-  for (int b = lane; b < n_blocks; b += 32) t += (double)partial[((int64_t)b * kwt + col) * row + c];
-  t = warp_sum(t);
-  if (lane == 0) sums[idx] = t;
+  unsigned int e = 0u;
+  if constexpr (PEER) e = peer_epoch_begin(pc);
+  if (idx < n_cols * row) {
+    const int col = idx / row, c = idx % row;
+    double t = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) t += (double)partial[((int64_t)b * kwt + col) * row + c];
+    t = warp_sum(t);
+    if constexpr (PEER) t = peer_warp_allreduce(pc, e, idx, t);
+    if (lane == 0) sums[idx] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool last;
+    if constexpr (PEER) last = peer_epoch_end(pc, e, gridDim.x);
+    else {
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      if (last) *ticket = 0u;
+    }
+    s_last = last ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last || fin.mode == kFinNone) return;
+  __threadfence();
+  finalize_rows(sums, fin, n_cols, C, threadIdx.x, kThreads);
 }
 
 // utils_.py:585-592
 __global__ void __launch_bounds__(kThreads) ema_finalize_kernel(const double* sums, const float* old_c, float m, int K,
                                                                 int C, float* out) {
-  const int idx = blockIdx.x * kThreads + threadIdx.x;
-  if (idx >= K * C) return;
-  const int k = idx / C, c = idx % C;
-  const double cnt = sums[(int64_t)k * (C + 1) + C];
-  const float old = old_c[idx];
-  float batch;
-  if (cnt == 0.0) batch = old;                                              // :585-586
-  else batch = (float)sums[(int64_t)k * (C + 1) + c] / (float)cnt;          // :588
-  out[idx] = m * old + (1.0f - m) * batch;                                  // :592
+  FinArgs fin{kFinEma, old_c, m, K, out, nullptr};
+  finalize_rows(sums, fin, K, C, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
 // utils_.py:520-523 / :538 and EMA :552-563
 __global__ void __launch_bounds__(kThreads) centroid_finalize_kernel(const double* sums, const float* prev, float mom,
                                                                      int rows, int K, int C, float* cen, float* inv_w) {
-  const int idx = blockIdx.x * kThreads + threadIdx.x;
-  if (idx >= rows * C) return;
-  const int r = idx / C, c = idx % C;
-  const float wsum = (float)sums[(int64_t)r * (C + 1) + C] + 1e-7f;
-  float mu = (float)sums[(int64_t)r * (C + 1) + c] / wsum;
-  if (prev != nullptr) mu = mom * prev[(r % K) * C + c] + (1.0f - mom) * mu;
-  cen[idx] = mu;
-  if (c == 0) inv_w[r] = 1.0f / wsum;
+  FinArgs fin{kFinCentroid, prev, mom, K, cen, inv_w};
+  finalize_rows(sums, fin, rows, C, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
 // ---------------------------------------------------------------------------
@@ -920,13 +970,34 @@ int launch_v3_cpw(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
   else return p.n_cw <= 8 ? launch_v3<KWT, 2, 8>(a, p, stream) : launch_v3<KWT, 2, 16>(a, p, stream);
 }
 
-int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+void launch_reduce(const SumArgs& a, int n_blocks, int kwt, double* sums, const slcl_peer_t* peer, const FinArgs& fin,
+                   cudaStream_t stream) {
+  const int total = a.n_cols * ((int)a.channels + 1);
+  const dim3 grid(ceil_div(total, kWarps));
+  if (peer != nullptr && peer->world > 1)
+    class_sums_reduce_kernel<true><<<grid, kThreads, 0, stream>>>(a.partial, n_blocks, kwt, a.n_cols, (int)a.channels, sums,
+                                                                   peer_ctx(peer), fin, a.ticket);
+  else
+    class_sums_reduce_kernel<false><<<grid, kThreads, 0, stream>>>(a.partial, n_blocks, kwt, a.n_cols, (int)a.channels, sums,
+                                                                    PeerCtx{}, fin, a.ticket);
+}
+
+// sweep + reduce (+ cross-rank exchange through `peer`, + finaliser `fin` in the reduce kernel's last block)
+int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                   const slcl_peer_t* peer = nullptr, FinArgs fin = FinArgs{}) {
   if (a.n_cols < 1 || a.n_cols > SLCL_MAX_WEIGHT_COLS) return SLCL_ERR_INVALID_ARGUMENT;
+  if (peer != nullptr) {
+    if (!peer_valid(peer)) return SLCL_ERR_INVALID_ARGUMENT;
+    if (2 * (int64_t)a.n_cols * (a.channels + 1) > peer->capacity_words) return SLCL_ERR_INVALID_ARGUMENT;
+  }
   SumPlan p = plan_sums(a.batch, a.channels, a.pixels, a.n_cols, vec4);
   if (p.kwt < 0) return SLCL_ERR_INVALID_ARGUMENT;
-  if (workspace_bytes < partial_bytes(p, a.channels) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  if (workspace_bytes < partial_bytes(p, a.channels) + kTicketBytes || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  // the ticket lives in the last 256 bytes of the workspace the caller sized with class_sums_ws_bytes()
+  a.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + (workspace_bytes - kTicketBytes) / 16 * 16);
+  const size_t usable = workspace_bytes - kTicketBytes;
   const V3Plan v3 = plan_v3(a, vec4);
-  if (v3.ok && (size_t)v3.grid.x * v3.kwt * (a.channels + 1) * sizeof(float) <= workspace_bytes) {
+  if (v3.ok && (size_t)v3.grid.x * v3.kwt * (a.channels + 1) * sizeof(float) <= usable) {
     a.partial = reinterpret_cast<float*>(workspace);
     int st;
     switch (v3.kwt) {
@@ -942,9 +1013,7 @@ int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t w
       default: return SLCL_ERR_INVALID_ARGUMENT;
     }
     if (st != SLCL_OK) return st;
-    const int total = a.n_cols * ((int)a.channels + 1);
-    class_sums_reduce_kernel<<<ceil_div(total, kWarps), kThreads, 0, stream>>>(a.partial, (int)v3.grid.x, v3.kwt, a.n_cols,
-                                                                                (int)a.channels, sums);
+    launch_reduce(a, (int)v3.grid.x, v3.kwt, sums, peer, fin, stream);
     return check_launch("slcl_class_sums");
   }
   a.tiles_per_image = p.tiles_per_image; a.n_tiles = p.n_tiles;
@@ -962,9 +1031,7 @@ int run_class_sums(SumArgs a, bool vec4, double* sums, void* workspace, size_t w
     case 16: launch_sums<16, 4>(a, p, stream); break;
     default: return SLCL_ERR_INVALID_ARGUMENT;
   }
-  const int total = a.n_cols * ((int)a.channels + 1);
-  class_sums_reduce_kernel<<<ceil_div(total, kWarps), kThreads, 0, stream>>>(a.partial, (int)p.grid.x, p.kwt, a.n_cols,
-                                                                              (int)a.channels, sums);
+  launch_reduce(a, (int)p.grid.x, p.kwt, sums, peer, fin, stream);
   return check_launch("slcl_class_sums");
 }
 
@@ -982,7 +1049,7 @@ size_t class_sums_ws_bytes(int64_t batch, int64_t channels, int64_t pixels, int 
   // the grid never exceeds 2 blocks per SM; size for the worst case of either vector width
   int kwt = pick_kwt(n_cols);
   size_t blocks = (size_t)sm_count() * 2;
-  return align_up(blocks * kwt * (channels + 1) * sizeof(float), 256);
+  return align_up(blocks * kwt * (channels + 1) * sizeof(float), 256) + kTicketBytes;
 }
 
 // used by slcl_proto_bwd_centres: weights are the planar stash rows [cols][N]
@@ -1025,6 +1092,48 @@ extern "C" int slcl_class_sums(const float* feat, int64_t batch, int64_t channel
   a.n_cols = n_partitions * n_class;
   bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id});
   return run_class_sums(a, vec4, sums, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int slcl_class_centres_update(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                                         const int64_t* labels, int n_class, const float* old_centres, float m,
+                                         float* new_centres, double* sums, const slcl_peer_t* peer, void* workspace,
+                                         size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !labels || !old_centres || !new_centres || !sums || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class < 1 || n_class > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
+  SumArgs a{};
+  a.feat = feat;
+  a.batch = batch; a.channels = channels; a.pixels = pixels;
+  a.sb = channels * pixels; a.sc = pixels; a.sp = 1;
+  a.mode = kHard; a.labels = labels; a.n_part = 1; a.n_class = n_class; a.n_cols = n_class;
+  const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels});
+  FinArgs fin{kFinEma, old_centres, m, n_class, new_centres, nullptr};
+  return run_class_sums(a, vec4, sums, workspace, workspace_bytes, (cudaStream_t)stream_, peer, fin);
+}
+
+extern "C" int slcl_centroids_fwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
+                                  const int64_t* labels, const float* probs, int weighted, float threshold,
+                                  const int32_t* part_id, int n_partitions, int n_class, const float* previous,
+                                  float momentum, float* centroids, float* inv_weight, double* sums,
+                                  const slcl_peer_t* peer, void* workspace, size_t workspace_bytes,
+                                  slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !centroids || !inv_weight || !sums || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if ((labels == nullptr) == (probs == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_class < 1 || n_class > kMaxK || n_partitions < 1 || n_partitions * n_class > SLCL_MAX_WEIGHT_COLS)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_partitions > 1 && part_id == nullptr) return SLCL_ERR_INVALID_ARGUMENT;
+  SumArgs a{};
+  a.feat = feat;
+  a.batch = batch; a.channels = channels; a.pixels = pixels;
+  a.sb = channels * pixels; a.sc = pixels; a.sp = 1;
+  a.mode = labels ? kHard : kSoft;
+  a.labels = labels; a.probs = probs; a.weighted = weighted; a.threshold = threshold;
+  a.part_id = part_id; a.n_part = n_partitions; a.n_class = n_class;
+  a.n_cols = n_partitions * n_class;
+  const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id});
+  FinArgs fin{kFinCentroid, previous, momentum, n_class, centroids, inv_weight};
+  return run_class_sums(a, vec4, sums, workspace, workspace_bytes, (cudaStream_t)stream_, peer, fin);
 }
 
 extern "C" int slcl_ema_finalize(const double* sums, const float* old_centres, float m, int n_class, int64_t channels,

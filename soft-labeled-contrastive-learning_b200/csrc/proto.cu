@@ -15,6 +15,7 @@
 // and the stash and writes dF (8C B/px).  Nothing of size [N,C] or [N,K] is
 // materialised besides dF itself.
 #include "common.cuh"
+#include "peer.cuh"
 
 #include <math.h>
 
@@ -354,63 +355,48 @@ __global__ void proto_rescale_kernel(float* scal, int has_sel) {
 }
 
 // The same exchange + rescale as ONE kernel over NVLink peer memory (no NCCL launch between forward and backward):
-// every rank owns a mailbox in symmetric memory (peers[r] = rank r's mailbox mapped into THIS rank's address space),
-//   word 0            : this rank's call counter ("epoch"; only its own kernel touches it)
-//   word 1            : number of time-outs seen (diagnostic)
-//   word 2 + ((q * world + r) * 2 + v) : value v (0 = weight sum, 1 = weighted row-loss sum) of sender r for epoch
-//                       parity q, packed {epoch : 32 | fp32 bits : 32} in ONE 8-byte word -- an aligned 8-byte store is
-//                       single-copy atomic, so the flag and the payload arrive together and no fence is needed (the
-//                       low-latency protocol NCCL calls LL).
-// A rank stores its two words into every peer's mailbox (NVLink P2P stores), then polls its OWN mailbox until all
-// `world` senders show this epoch, adds the values in rank order (identical on every rank) and writes scal[0..3].
-// Two parities suffice: a sender can only be two calls ahead of a reader that has not finished reading.
-constexpr int kMaxPeers = 16;
-__global__ void __launch_bounds__(64) proto_rescale_peer_kernel(float* scal, int has_sel, unsigned long long* const* peers,
-                                                                int rank, int world) {
+// protocol and mailbox layout in peer.cuh.  Thread 2p+v sends value v (0 = weight sum, 1 = weighted row-loss sum) to
+// rank p's mailbox and waits for rank p's value v in its own; thread 0 then adds in rank order (identical on every
+// rank) and writes scal[0..3].
+__global__ void __launch_bounds__(64) proto_rescale_peer_kernel(float* scal, int has_sel, const PeerCtx pc) {
   pdl_trigger();
   pdl_wait();
   __shared__ float vals[2 * kMaxPeers];
-  __shared__ unsigned int s_epoch;
-  unsigned long long* mine = peers[rank];
-  if (threadIdx.x == 0) {
-    const unsigned int e = (unsigned int)mine[0] + 1u;
-    mine[0] = e;
-    s_epoch = e;
-  }
-  __syncthreads();
-  const unsigned int e = s_epoch, q = e & 1u;
+  __shared__ int s_bad;
+  const unsigned int e = peer_epoch_begin(pc);
   const int t = threadIdx.x;
-  if (t < 2 * world) {
-    const int p = t >> 1, v = t & 1;                          // destination rank, value index
-    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(scal[2 + v]);
-    volatile unsigned long long* dst = peers[p] + 2 + ((q * world + rank) * 2 + v);
-    *dst = w;
-    // the same thread now waits for sender p's value v in this rank's own mailbox
-    volatile unsigned long long* src = mine + 2 + ((q * world + p) * 2 + v);
-    unsigned long long t0, now, got;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-      got = *src;
-      if ((unsigned int)(got >> 32) == e) break;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 5000000000ull) {                          // 5 s: a peer never arrived -- poison instead of hanging
-        got = 0x7FC00000ull;
-        atomicAdd(mine + 1, 1ull);
-        break;
-      }
-    }
-    vals[t] = __uint_as_float((unsigned int)got);
+  if (t == 0) s_bad = 0;
+  __syncthreads();
+  if (t < 2 * pc.world) {
+    bool ok;
+    const unsigned int got = peer_send_recv(pc, e, t >> 1, t & 1, __float_as_uint(scal[2 + (t & 1)]), ok);
+    vals[t] = __uint_as_float(got);
+    if (!ok) s_bad = 1;
   }
   __syncthreads();
   if (t == 0) {
     float wsum = 0.f, lsum = 0.f;
-    for (int r = 0; r < world; ++r) { wsum += vals[2 * r]; lsum += vals[2 * r + 1]; }
+    for (int r = 0; r < pc.world; ++r) { wsum += vals[2 * r]; lsum += vals[2 * r + 1]; }
+    if (s_bad) { wsum = __uint_as_float(0x7FC00000u); lsum = wsum; }      // a peer never arrived: poison, do not hang
     const float coef = has_sel ? 1.0f / (wsum + 1e-4f) : 1.0f / wsum;
     scal[0] = lsum * coef;
     scal[1] = coef;
     scal[2] = wsum;
     scal[3] = lsum;
+    peer_epoch_end(pc, e, 1u);
   }
+}
+
+// In-place all-reduce (sum) of n doubles across the ranks: one warp per element.
+__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, long long n, const PeerCtx pc) {
+  const unsigned int e = peer_epoch_begin(pc);
+  const long long idx = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (idx < n) {
+    const double t = peer_warp_allreduce(pc, e, idx, buf[idx]);
+    if ((threadIdx.x & 31) == 0) buf[idx] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) peer_epoch_end(pc, e, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -706,18 +692,22 @@ extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream
   return check_launch("slcl_proto_rescale");
 }
 
-extern "C" size_t slcl_peer_mailbox_bytes(int world) {
-  if (world < 1 || world > kMaxPeers) return 0;
-  return (size_t)(2 + 4 * world) * sizeof(unsigned long long);
+extern "C" size_t slcl_peer_mailbox_bytes(int world, int64_t capacity_words) {
+  if (world < 1 || world > kMaxPeers || capacity_words < kPeerMinCapacity) return 0;
+  return (size_t)(kPeerHeaderWords + 2 * (size_t)world * (size_t)capacity_words) * sizeof(unsigned long long);
 }
 
-extern "C" int slcl_proto_rescale_peer(float* scal, int has_sel, const void* peer_mailboxes_dev, int rank, int world,
-                                       slcl_stream_t stream_) {
-  if (!scal || !peer_mailboxes_dev || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
-    return SLCL_ERR_INVALID_ARGUMENT;
-  launch_pdl(proto_rescale_peer_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream_, scal, has_sel,
-             reinterpret_cast<unsigned long long* const*>(peer_mailboxes_dev), rank, world);
+extern "C" int slcl_proto_rescale_peer(float* scal, int has_sel, const slcl_peer_t* peer, slcl_stream_t stream_) {
+  if (!scal || !peer_valid(peer)) return SLCL_ERR_INVALID_ARGUMENT;
+  launch_pdl(proto_rescale_peer_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream_, scal, has_sel, peer_ctx(peer));
   return check_launch("slcl_proto_rescale_peer");
+}
+
+extern "C" int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t* peer, slcl_stream_t stream_) {
+  if (!buf || n < 1 || !peer_valid(peer) || 2 * n > peer->capacity_words) return SLCL_ERR_INVALID_ARGUMENT;
+  peer_allreduce_f64_kernel<<<(unsigned)ceil_div<int64_t>(n, 8), 256, 0, (cudaStream_t)stream_>>>(buf, (long long)n,
+                                                                                                peer_ctx(peer));
+  return check_launch("slcl_peer_allreduce_f64");
 }
 
 extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,

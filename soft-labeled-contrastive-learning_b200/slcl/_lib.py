@@ -37,6 +37,12 @@ class ProtoParamsT(C.Structure):
                 ("margin", C.c_float), ("easy_margin", C.c_int), ("normalize", C.c_int)]
 
 
+class PeerT(C.Structure):
+    """slcl_peer_t"""
+    _fields_ = [("mailboxes_dev", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("capacity_words", C.c_int64),
+                ("timeout_s", C.c_double)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _SZ = C.c_size_t
@@ -50,8 +56,13 @@ SIGNATURES = {
     "slcl_proto_fwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, _P, _SZ, _P]),
     "slcl_proto_fwd_target": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "slcl_proto_rescale": (C.c_int, [_P, C.c_int, _P]),
-    "slcl_peer_mailbox_bytes": (_SZ, [C.c_int]),
-    "slcl_proto_rescale_peer": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "slcl_peer_mailbox_bytes": (_SZ, [C.c_int, _I64]),
+    "slcl_proto_rescale_peer": (C.c_int, [_P, C.c_int, C.POINTER(PeerT), _P]),
+    "slcl_peer_allreduce_f64": (C.c_int, [_P, _I64, C.POINTER(PeerT), _P]),
+    "slcl_class_centres_update": (C.c_int, [_P, _I64, _I64, _I64, _P, C.c_int, _P, C.c_float, _P, _P, C.POINTER(PeerT), _P, _SZ,
+                                            _P]),
+    "slcl_centroids_fwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.c_float, _P, C.c_int, C.c_int, _P, C.c_float,
+                                     _P, _P, _P, C.POINTER(PeerT), _P, _SZ, _P]),
     "slcl_proto_bwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P]),
     "slcl_proto_bwd_centres_workspace_bytes": (_SZ, [_I64, _I64, C.c_int]),
     "slcl_proto_bwd_centres": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _SZ, _P]),

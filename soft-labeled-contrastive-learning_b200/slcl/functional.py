@@ -23,7 +23,7 @@ def _exchange_loss_pair(scal, has_sel: bool, group) -> None:
     from .peer import PeerMailbox
     if isinstance(group, PeerMailbox):
         if group.world > 1:
-            _ops.proto_rescale_peer(scal, has_sel, group.ptrs_dev, group.rank, group.world)
+            _ops.proto_rescale_peer(scal, has_sel, *group.args())
         return
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
@@ -107,13 +107,19 @@ class _Centroids(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, labels, probs, previous, weighted, threshold, part_id, n_partitions, n_class, momentum, group):
-        sums = _ops.class_sums(feat.detach(), labels, None if probs is None else probs.detach(), weighted, threshold,
-                               part_id, n_partitions, n_class)
-        if group is not None:
-            from .distributed import all_reduce_sums
-            sums = all_reduce_sums(sums, group)
+        from .peer import PeerMailbox
         prev = None if previous is None else previous.detach()
-        cen, _inv_w = _ops.centroid_finalize(sums, prev, momentum, n_partitions, n_class)
+        if group is None or isinstance(group, PeerMailbox):
+            # two launches: sweep, then reduce [+ exchange over the NVLink peer mailboxes] + finalise
+            peer = group.args() if group is not None else ()
+            cen, _inv_w, sums = _ops.centroids_fwd(feat.detach(), labels, None if probs is None else probs.detach(), weighted,
+                                                   threshold, part_id, n_partitions, n_class, prev, momentum, *peer)
+        else:
+            from .distributed import all_reduce_sums
+            sums = _ops.class_sums(feat.detach(), labels, None if probs is None else probs.detach(), weighted, threshold,
+                                   part_id, n_partitions, n_class)
+            sums = all_reduce_sums(sums, group)
+            cen, _inv_w = _ops.centroid_finalize(sums, prev, momentum, n_partitions, n_class)
         ctx.save_for_backward(feat, labels, probs, part_id, sums)
         ctx.cfg = (weighted, threshold, n_partitions, n_class, momentum, previous is not None)
         return cen

@@ -23,52 +23,70 @@ from .plan import ProtoPlan
 class HostProtoPipeline:
     def __init__(self, shape, n_class: int, mpcl: MPCL, with_sel: bool, device, chunk_images: int = 4, n_slots: int = 3):
         b, c, h, w = shape
+        if min(b, c, h, w) < 1:
+            raise ValueError("feature map must be a non-empty [B, C, h, w]")
         self.shape = tuple(shape)
         self.dev = torch.device(device)
         self.chunk = max(1, min(chunk_images, b))
         self.n_slots = n_slots
         self.with_sel = with_sel
-        px = self.chunk * h * w
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.centres = torch.empty(n_class, c, **f32)
-        self.slots = []
-        for _ in range(n_slots):
-            feat = torch.empty(self.chunk, c, h, w, **f32)
-            labels = torch.empty(px, dtype=torch.int64, device=self.dev)
-            sel = torch.empty(px, **f32) if with_sel else None
-            plan = ProtoPlan(feat, labels, sel, self.centres, n_class, mpcl.temperature, mpcl.base_temperature, mpcl.m,
-                             mpcl.easy_margin, True)
-            self.slots.append(dict(feat=feat, labels=labels, sel=sel, plan=plan, stream=torch.cuda.Stream(self.dev),
-                                   done=torch.cuda.Event(), loss=torch.zeros((), **f32)))
+        self._mk = lambda n_img: self._make_slot(n_img, c, h, w, n_class, mpcl, f32)
+        self.slots = [self._mk(self.chunk) for _ in range(n_slots)]
+        tail = b % self.chunk                       # a short last chunk gets its own plan (any batch size is accepted,
+        self.tail = self._mk(tail) if tail else None                                    # like the reference path)
         self.total = torch.zeros(1, **f32)          # global weight sum (sum(sel) or N)
         self.loss = torch.zeros((), **f32)
 
+    def _make_slot(self, n_img, c, h, w, n_class, mpcl, f32):
+        px = n_img * h * w
+        feat = torch.empty(n_img, c, h, w, **f32)
+        labels = torch.empty(px, dtype=torch.int64, device=self.dev)
+        sel = torch.empty(px, **f32) if self.with_sel else None
+        plan = ProtoPlan(feat, labels, sel, self.centres, n_class, mpcl.temperature, mpcl.base_temperature, mpcl.m,
+                         mpcl.easy_margin, True)
+        return dict(feat=feat, labels=labels, sel=sel, plan=plan, stream=torch.cuda.Stream(self.dev),
+                    done=torch.cuda.Event(), loss=torch.zeros((), **f32), n_img=n_img)
+
     def run(self, feas_h: torch.Tensor, labels_h: torch.Tensor, centres: torch.Tensor, sel_h: Optional[torch.Tensor],
             grad_h: torch.Tensor, group=None) -> torch.Tensor:
+        # every check comes BEFORE the first collective: a rank that raises must not leave its peers in an all-reduce
         b, c, h, w = self.shape
         hw = h * w
-        main = torch.cuda.current_stream(self.dev)
+        if tuple(feas_h.shape) != self.shape or tuple(grad_h.shape) != self.shape:
+            raise ValueError("feas_h / grad_h do not have the shape this pipeline was built for")
         labels_h = labels_h.reshape(-1)
+        if labels_h.numel() != b * hw or labels_h.dtype != torch.int64:
+            raise ValueError("labels must be int64 at feature resolution ([B,h,w] or [B*h*w])")
+        if self.with_sel != (sel_h is not None) or (sel_h is not None and sel_h.numel() != b * hw):
+            raise ValueError("pixel_sel_loc must have B*h*w elements (and match how the pipeline was built)")
+        if tuple(centres.shape) != tuple(self.centres.shape):
+            raise ValueError("class centres must be [K, C]")
+        multi = False
+        if group is not None:
+            import torch.distributed as dist
+            pg = None if group is True else group
+            multi = dist.is_initialized() and dist.get_world_size(pg) > 1
+        main = torch.cuda.current_stream(self.dev)
         self.centres.copy_(centres, non_blocking=True)
         if self.with_sel:
             self.total.copy_(sel_h.reshape(-1).sum().reshape(1), non_blocking=True)      # host-side sum of a host tensor
         else:
             self.total.fill_(float(b * hw))
-        if group is not None:
-            import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
-                dist.all_reduce(self.total, group=None if group is True else group)
-        for sl in self.slots:
+        if multi:
+            dist.all_reduce(self.total, group=pg)             # global normaliser: sum(sel) (or N) over all ranks
+        for sl in self.slots + ([self.tail] if self.tail else []):
             sl["loss"].zero_()
         ready = torch.cuda.Event()
         ready.record(main)
-        n_chunks = (b + self.chunk - 1) // self.chunk
-        if b % self.chunk:
-            raise ValueError("batch must be a multiple of chunk_images")
-        for i in range(n_chunks):
-            sl = self.slots[i % self.n_slots]
+        n_full = b // self.chunk
+        work = [(self.slots[i % self.n_slots], i * self.chunk, (i + 1) * self.chunk) for i in range(n_full)]
+        if self.tail is not None:
+            work.append((self.tail, n_full * self.chunk, b))
+        used = []
+        for sl, lo, hi in work:
             st = sl["stream"]
-            lo, hi = i * self.chunk, (i + 1) * self.chunk
             with torch.cuda.stream(st):
                 st.wait_event(ready)
                 sl["feat"].copy_(feas_h[lo:hi], non_blocking=True)
@@ -83,9 +101,15 @@ class HostProtoPipeline:
                 grad_h[lo:hi].copy_(dfeat, non_blocking=True)
                 sl["loss"].add_(scal[0])             # per-slot accumulator: streams never share a destination
                 sl["done"].record(st)
-        for sl in self.slots:
+            if not any(sl is u for u in used):
+                used.append(sl)
+        for sl in used:
             main.wait_event(sl["done"])
-        self.loss.copy_(torch.stack([sl["loss"] for sl in self.slots]).sum())
+        self.loss.copy_(torch.stack([sl["loss"] for sl in used]).sum())
+        if multi:
+            # every chunk's share was taken with the GLOBAL normaliser, so the global loss (utils/loss.py:565 over the
+            # whole batch) is the plain sum of the ranks' shares; gradients already carry the global coefficient
+            dist.all_reduce(self.loss, group=pg)
         return self.loss
 
 

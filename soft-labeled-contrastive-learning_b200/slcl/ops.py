@@ -13,7 +13,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import MapT, ProtoParamsT, check, ptr, require_cuda, stream_ptr
+from ._lib import MapT, PeerT, ProtoParamsT, check, ptr, require_cuda, stream_ptr
 
 _F32 = torch.float32
 
@@ -159,14 +159,36 @@ def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     check(st, "slcl_proto_rescale")
 
 
+def _peer(peer_ptrs: int, rank: int, world: int, capacity_words: int, timeout_s: float) -> Optional[PeerT]:
+    """slcl_peer_t from the flat (ptrs, rank, world, capacity, timeout) form ops carry (slcl.peer.PeerMailbox.args());
+    world <= 1 or a null pointer table = no exchange."""
+    if world <= 1 or not peer_ptrs:
+        return None
+    return PeerT(peer_ptrs, rank, world, capacity_words, timeout_s)
+
+
 @torch.library.custom_op("slcl::proto_rescale_peer", mutates_args=("scal",), device_types="cuda")
-def proto_rescale_peer(scal: Tensor, has_sel: bool, peer_mailboxes_dev: int, rank: int, world: int) -> None:
+def proto_rescale_peer(scal: Tensor, has_sel: bool, peer_ptrs: int, rank: int, world: int, capacity_words: int,
+                       timeout_s: float) -> None:
     """Exchange scal[2:4] with the other ranks through NVLink peer mailboxes (slcl.peer.PeerMailbox) and rescale,
     in one kernel; every rank must call it in the same order."""
     dev = require_cuda(scal)
+    peer = PeerT(peer_ptrs, rank, world, capacity_words, timeout_s)
     with _guard(dev):
-        st = _lib.load().slcl_proto_rescale_peer(ptr(scal), int(has_sel), peer_mailboxes_dev, rank, world, stream_ptr(dev))
+        st = _lib.load().slcl_proto_rescale_peer(ptr(scal), int(has_sel), C.byref(peer), stream_ptr(dev))
     check(st, "slcl_proto_rescale_peer")
+
+
+@torch.library.custom_op("slcl::peer_allreduce_f64", mutates_args=("buf",), device_types="cuda")
+def peer_allreduce_f64(buf: Tensor, peer_ptrs: int, rank: int, world: int, capacity_words: int, timeout_s: float) -> None:
+    """In-place sum of a float64 tensor over the ranks through the peer mailboxes (one kernel, no collective)."""
+    dev = require_cuda(buf)
+    if buf.dtype != torch.float64 or not buf.is_contiguous():
+        raise ValueError("buf must be a contiguous float64 tensor")
+    peer = PeerT(peer_ptrs, rank, world, capacity_words, timeout_s)
+    with _guard(dev):
+        st = _lib.load().slcl_peer_allreduce_f64(ptr(buf), buf.numel(), C.byref(peer), stream_ptr(dev))
+    check(st, "slcl_peer_allreduce_f64")
 
 
 @torch.library.custom_op("slcl::proto_bwd", mutates_args=(), device_types="cuda")
@@ -278,6 +300,89 @@ def class_sums(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], 
 @class_sums.register_fake
 def _(feat, labels, probs, weighted, threshold, part_id, n_partitions, n_class):
     return torch.empty((n_partitions * n_class, feat.shape[1] + 1), dtype=torch.float64, device=feat.device)
+
+
+@torch.library.custom_op("slcl::class_centres_update", mutates_args=(), device_types="cuda")
+def class_centres_update(feat: Tensor, labels: Tensor, old_centres: Tensor, m: float, peer_ptrs: int = 0, rank: int = 0,
+                         world: int = 1, capacity_words: int = 0, timeout_s: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """update_class_center_iter as two launches: hard class sums, then reduce [+ peer all-reduce] + EMA finalise.
+    -> (new centres [K,C], sums [K,C+1] float64 -- the GLOBAL sums when a peer mailbox is given)."""
+    dev = require_cuda(feat, labels, old_centres)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    labels = labels.contiguous()
+    if labels.dtype != torch.int64 or labels.numel() != b * h * w:
+        raise ValueError("labels must be int64 with B*H*W elements")
+    old = old_centres.to(_F32).contiguous()
+    k = old.shape[0]
+    if old.shape != (k, c):
+        raise ValueError("class centres must be [K, C]")
+    sums = torch.empty((k, c + 1), dtype=torch.float64, device=dev)
+    new = torch.empty_like(old)
+    ws = _ws(lib.slcl_class_sums_workspace_bytes(b, c, h * w, k), dev)
+    peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
+    with _guard(dev):
+        st = lib.slcl_class_centres_update(ptr(feat), b, c, h * w, ptr(labels), k, ptr(old), float(m), ptr(new), ptr(sums),
+                                           C.byref(peer) if peer is not None else None, ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_class_centres_update")
+    return new, sums
+
+
+@class_centres_update.register_fake
+def _(feat, labels, old_centres, m, peer_ptrs=0, rank=0, world=1, capacity_words=0, timeout_s=0.0):
+    return (torch.empty_like(old_centres, dtype=_F32),
+            torch.empty((old_centres.shape[0], feat.shape[1] + 1), dtype=torch.float64, device=feat.device))
+
+
+@torch.library.custom_op("slcl::centroids_fwd", mutates_args=(), device_types="cuda")
+def centroids_fwd(feat: Tensor, labels: Optional[Tensor], probs: Optional[Tensor], weighted: bool, threshold: float,
+                  part_id: Optional[Tensor], n_partitions: int, n_class: int, previous: Optional[Tensor], momentum: float,
+                  peer_ptrs: int = 0, rank: int = 0, world: int = 1, capacity_words: int = 0,
+                  timeout_s: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """cal_centroid forward as two launches: class sums, then reduce [+ peer all-reduce] + centroid finalise.
+    -> (centroids [P*K, C], inv_weight [P*K], sums [P*K, C+1] float64)."""
+    dev = require_cuda(feat, labels, probs, part_id, previous)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    if labels is not None:
+        labels = labels.contiguous()
+        if labels.dtype != torch.int64 or labels.numel() != b * h * w:
+            raise ValueError("labels must be int64 with B*H*W elements")
+    if probs is not None:
+        probs = probs.to(_F32).contiguous()
+        if probs.shape != (b, n_class, h, w):
+            raise ValueError("probs must be [B, K, H, W] at feature resolution")
+    if part_id is not None:
+        part_id = part_id.contiguous()
+        if part_id.dtype != torch.int32 or part_id.numel() != b * h * w:
+            raise ValueError("part_id must be int32 with B*H*W elements")
+    if previous is not None:
+        previous = previous.to(_F32).contiguous()
+        if previous.shape != (n_class, c):
+            raise ValueError("previous centroid must be [K, C]")
+    cols = n_partitions * n_class
+    sums = torch.empty((cols, c + 1), dtype=torch.float64, device=dev)
+    cen = torch.empty((cols, c), dtype=_F32, device=dev)
+    inv_w = torch.empty(cols, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_class_sums_workspace_bytes(b, c, h * w, cols), dev)
+    peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
+    with _guard(dev):
+        st = lib.slcl_centroids_fwd(ptr(feat), b, c, h * w, ptr(labels), ptr(probs), int(weighted), float(threshold),
+                                    ptr(part_id), n_partitions, n_class, ptr(previous), float(momentum), ptr(cen), ptr(inv_w),
+                                    ptr(sums), C.byref(peer) if peer is not None else None, ptr(ws), ws.numel(),
+                                    stream_ptr(dev))
+    check(st, "slcl_centroids_fwd")
+    return cen, inv_w, sums
+
+
+@centroids_fwd.register_fake
+def _(feat, labels, probs, weighted, threshold, part_id, n_partitions, n_class, previous, momentum, peer_ptrs=0, rank=0,
+      world=1, capacity_words=0, timeout_s=0.0):
+    rows, c = n_partitions * n_class, feat.shape[1]
+    return (torch.empty((rows, c), dtype=_F32, device=feat.device), torch.empty(rows, dtype=_F32, device=feat.device),
+            torch.empty((rows, c + 1), dtype=torch.float64, device=feat.device))
 
 
 @torch.library.custom_op("slcl::ema_finalize", mutates_args=(), device_types="cuda")

@@ -69,8 +69,9 @@ class ProtoPlan:
     def rescale_peer(self, mailbox) -> None:
         """Exchange {weight sum, weighted row-loss sum} with the other ranks through NVLink peer memory and rescale,
         in ONE kernel (``mailbox``: slcl.peer.PeerMailbox); replaces all_reduce(scal[2:4]) + rescale()."""
-        check(self.lib.slcl_proto_rescale_peer(ptr(self.scal), int(self.sel is not None), mailbox.ptrs_dev, mailbox.rank,
-                                               mailbox.world, self._stream()), "slcl_proto_rescale_peer")
+        peer = mailbox.struct()
+        check(self.lib.slcl_proto_rescale_peer(ptr(self.scal), int(self.sel is not None), C.byref(peer), self._stream()),
+              "slcl_proto_rescale_peer")
 
     def backward(self) -> torch.Tensor:
         """Launch the backward for dL/dloss = grad_out (device scalar, default 1); returns dfeat."""

@@ -18,17 +18,22 @@ def update_class_center_iter(cla_src_feas, batch_src_labels, class_center_feas, 
     map instead of ``num_class`` masked passes; the empty-class rule (:585-588) is
     decided on the device, so there is no host sync.  ``group``: optional
     torch.distributed group -- the per-class sums/counts are all-reduced so every
-    rank holds the centres of the global batch."""
+    rank holds the centres of the global batch; a ``slcl.peer.PeerMailbox`` does that exchange inside
+    the reduce kernel over NVLink peer memory (no collective launch)."""
     feats = cla_src_feas.detach()
     labels = batch_src_labels.to(feats.device)
     if labels.shape != (feats.shape[0],) + tuple(feats.shape[2:]):
         raise ValueError("labels must be [B, h, w] at feature resolution")
-    sums = _ops.class_sums(feats, labels.reshape(-1).long(), None, False, 0.0, None, 1, num_class)
-    if group is not None:
-        from .distributed import all_reduce_sums
-        sums = all_reduce_sums(sums, group)
+    from .peer import PeerMailbox
     old = class_center_feas[:num_class]
-    new = _ops.ema_finalize(sums, old.detach(), float(m))
+    lab = labels.reshape(-1).long()
+    if group is None or isinstance(group, PeerMailbox):
+        # two launches: sweep, then reduce [+ exchange over the NVLink peer mailboxes] + EMA finalise
+        new, _sums = _ops.class_centres_update(feats, lab, old.detach(), float(m), *(group.args() if group is not None else ()))
+    else:
+        from .distributed import all_reduce_sums
+        sums = all_reduce_sums(_ops.class_sums(feats, lab, None, False, 0.0, None, 1, num_class), group)
+        new = _ops.ema_finalize(sums, old.detach(), float(m))
     if class_center_feas.requires_grad:
         # the reference keeps the graph through `m * class_center_feas` (:592) and detaches the
         # old centre only in the empty-class branch (:586)

@@ -5,6 +5,10 @@ import sys
 
 import pytest
 
+# the multi-rank tests run `world` ranks as concurrent CUDA streams of one GPU whose kernels wait for each other: every
+# stream needs its own hardware queue (default 8), or a polling kernel could sit in front of the kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG_DIR = os.path.join(ROOT, "soft-labeled-contrastive-learning_b200")
 for p in (ROOT, PKG_DIR):

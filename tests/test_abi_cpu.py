@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libslcl.so lacks {name}"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
-    assert lib.slcl_version() == 100
+    assert lib.slcl_version() == 110
     assert lib.slcl_strerror(0) == b"ok"
     assert b"invalid" in lib.slcl_strerror(-1)
     assert lib.slcl_proto_workspace_bytes(1 << 20) >= (1 << 20) // 256 * 16
@@ -49,11 +49,18 @@ def test_argument_validation_without_gpu():
                             None, None, 0, None) == -1
     assert lib.slcl_p2p_state_bytes(4096, 256) >= 4096 * 256 * 4
     assert lib.slcl_p2p_state_bytes(0, 256) == 0 and lib.slcl_p2p_workspace_bytes(4096, 16384, 512) == 0
-    # peer-memory exchange: mailbox = 2 header words + 2 parities x world senders x 2 values, 8 bytes each; 1..16 ranks
-    assert lib.slcl_peer_mailbox_bytes(8) == (2 + 4 * 8) * 8 and lib.slcl_peer_mailbox_bytes(0) == 0
-    assert lib.slcl_peer_mailbox_bytes(17) == 0
-    assert lib.slcl_proto_rescale_peer(None, 1, None, 0, 2, None) == -1
-    assert lib.slcl_proto_rescale_peer(16, 1, 16, 2, 2, None) == -1       # rank out of range
+    # peer-memory exchange: mailbox = 8 header words + 2 parities x world senders x capacity payload words; 1..16 ranks
+    assert lib.slcl_peer_mailbox_bytes(8, 2) == (8 + 2 * 8 * 2) * 8 and lib.slcl_peer_mailbox_bytes(0, 2) == 0
+    assert lib.slcl_peer_mailbox_bytes(17, 2) == 0 and lib.slcl_peer_mailbox_bytes(2, 1) == 0
+    import ctypes as C
+    assert lib.slcl_proto_rescale_peer(None, 1, None, None) == -1
+    bad_rank = _lib.PeerT(16, 2, 2, 64, 1.0)
+    assert lib.slcl_proto_rescale_peer(16, 1, C.byref(bad_rank), None) == -1       # rank out of range
+    small = _lib.PeerT(16, 0, 2, 8, 1.0)
+    assert lib.slcl_peer_allreduce_f64(16, 5, C.byref(small), None) == -1          # 2*n > capacity_words
+    assert lib.slcl_class_centres_update(None, 1, 1, 1, None, 4, None, 0.9, None, None, None, None, 0, None) == -1
+    assert lib.slcl_centroids_fwd(None, 1, 1, 1, None, None, 0, 0.0, None, 1, 4, None, 0.9, None, None, None, None, None, 0,
+                                  None) == -1
     assert lib.slcl_p2p_workspace_bytes(4096, 16384, 256) > 0
 
 

@@ -718,26 +718,198 @@ def test_p2p_plan_graph_replay_matches_eager_launches():
 def test_peer_exchange_kernel_single_rank_matches_rescale():
     """slcl_proto_rescale_peer with a world of one (the rank's own mailbox in ordinary device memory): the kernel stores its
     {epoch | fp32} words, finds them again, and must rewrite scal exactly as slcl_proto_rescale does -- over several calls,
-    so both epoch parities and the slot reuse are exercised.  (The multi-rank exchange is checked against NCCL inside
-    bench.py at N > 1, before anything is timed.)"""
+    so both epoch parities and the slot reuse are exercised."""
+    import ctypes as C
     from slcl import _lib
     from slcl._lib import check, ptr
+    from slcl.peer import LoopbackMailboxes
     lib = _lib.load()
-    n_words = lib.slcl_peer_mailbox_bytes(1) // 8
-    assert n_words == 6
-    mailbox = torch.zeros(n_words, dtype=torch.int64, device=dev())
-    peers = torch.tensor([mailbox.data_ptr()], dtype=torch.int64, device=dev())
+    assert lib.slcl_peer_mailbox_bytes(1, 2) // 8 == 8 + 4
+    box = LoopbackMailboxes(1, dev(), capacity_words=2).boxes[0]
+    peer = box.struct()
     stream = torch.cuda.current_stream().cuda_stream
     g = cases.g(5)
     for call in range(5):
         for has_sel in (0, 1):
             vals = torch.rand(4, generator=g) * 1000 + 1
             a, b = vals.to(dev()), vals.to(dev())
-            check(lib.slcl_proto_rescale_peer(ptr(a), has_sel, peers.data_ptr(), 0, 1, stream), "slcl_proto_rescale_peer")
+            check(lib.slcl_proto_rescale_peer(ptr(a), has_sel, C.byref(peer), stream), "slcl_proto_rescale_peer")
             check(lib.slcl_proto_rescale(ptr(b), has_sel, stream), "slcl_proto_rescale")
             torch.cuda.synchronize()
             assert torch.equal(a, b), (call, has_sel, a, b)
-    assert int(mailbox[0]) == 10 and int(mailbox[1]) == 0          # ten calls counted, no time-outs
+    assert box.epoch() == 10 and box.timeouts() == 0          # ten calls counted, no time-outs
+
+
+# ---------------------------------------------------------------------------
+# multi-rank protocol on ONE GPU: `world` ranks = `world` CUDA streams exchanging through loopback mailboxes
+# (slcl.peer.LoopbackMailboxes).  The kernels, the mailbox protocol and the Python `group=` route are exactly what N
+# processes over NVLink run; only the transport (same-device stores instead of P2P stores) differs.  bench.py repeats
+# the sharded-vs-global checks on real multi-GPU boxes before it times anything.
+# ---------------------------------------------------------------------------
+def _rank_streams(world):
+    return [torch.cuda.Stream(dev()) for _ in range(world)]
+
+
+def _on_streams(streams, fn):
+    """fn(rank) enqueued on streams[rank] for every rank, nothing synchronises in between; returns the results."""
+    cur = torch.cuda.current_stream()
+    out = []
+    for r, st in enumerate(streams):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            out.append(fn(r))
+    for st in streams:
+        cur.wait_stream(st)
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_allreduce_f64_ranks_on_streams_bit_exact(world):
+    from slcl.peer import LoopbackMailboxes
+    op = torch.ops.slcl
+    boxes = LoopbackMailboxes(world, dev(), capacity_words=2 * 700).boxes
+    streams = _rank_streams(world)
+    g = cases.g(77)
+    for n in (1, 9, 700, 264):                       # several calls: both parities, slots reused with other sizes
+        vals = [(torch.randn(n, generator=g, dtype=torch.float64) * 10 ** torch.randint(-3, 6, (n,), generator=g)).to(dev())
+                for _ in range(world)]
+        want = torch.zeros(n, dtype=torch.float64, device=dev())
+        for v in vals:                               # rank order, like the kernel
+            want = want + v
+        bufs = [v.clone() for v in vals]
+        torch.cuda.synchronize()
+        _on_streams(streams, lambda r: op.peer_allreduce_f64(bufs[r], *boxes[r].args()))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(bufs[r], want), (n, r)
+    assert all(b.epoch() == 4 and b.timeouts() == 0 for b in boxes)
+
+
+def test_peer_exchange_times_out_with_nan_instead_of_hanging():
+    """A peer that never arrives: the waiting rank gives up after timeout_s, returns NaN and counts the event (ADVICE r1:
+    the limit is a parameter now, default 10 minutes; PeerMailbox.check() turns the counter into an exception)."""
+    from slcl.peer import LoopbackMailboxes
+    box = LoopbackMailboxes(2, dev(), capacity_words=16, timeout_s=0.2).boxes[0]
+    buf = torch.ones(3, dtype=torch.float64, device=dev())
+    torch.ops.slcl.peer_allreduce_f64(buf, *box.args())          # rank 1 never calls
+    torch.cuda.synchronize()
+    assert torch.isnan(buf).all()
+    assert box.timeouts() >= 1
+    with pytest.raises(RuntimeError):
+        box.check()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_class_centres_and_centroids_equal_global(api, world):
+    """N sharded ranks must reproduce the 1-rank global result -- class counts bit-exactly -- for
+    update_class_center_iter / cal_centroid(hard) / cal_centroid(soft, P=2) with the exchange inside the reduce kernel."""
+    from slcl.peer import LoopbackMailboxes
+    _, U = api
+    op = torch.ops.slcl
+    b, c, h, w, k, parts = 2 * world, 32, 24, 20, 4, 2
+    g = cases.g(31)
+    feat = torch.randn(b, c, h, w, generator=g).to(dev())
+    lab = torch.randint(0, k, (b, h, w), generator=g)
+    lab[lab == 3] = 1                                   # class 3 empty everywhere: the empty-class rule must see GLOBAL counts
+    lab = lab.to(dev())
+    probs = torch.softmax(3 * torch.randn(b, k, h, w, generator=g), 1).to(dev())
+    part = (torch.randperm(b * h * w, generator=g) % parts).to(torch.int32).to(dev())
+    cen = torch.randn(k, c, generator=g).to(dev())
+    gcen = torch.randn(parts * k, c, generator=g).to(dev())
+    boxes = LoopbackMailboxes(world, dev()).boxes
+    streams = _rank_streams(world)
+    per = b // world
+    sl = lambda t, r: t[r * per:(r + 1) * per]
+    pix = lambda t, r: t.reshape(b, -1)[r * per:(r + 1) * per].reshape(-1)
+
+    # global references (one rank, no group)
+    new_g = U.update_class_center_iter(feat, lab, cen, m=.9, num_class=k)
+    sums_g = op.class_sums(feat, lab.reshape(-1), None, False, 0.0, None, 1, k)
+    fg = feat.clone().requires_grad_(True)
+    pg = probs.clone().requires_grad_(True)
+    soft_g, _, _ = U.cal_centroid(fg, pg, pseudo_label=True, weighted_ave=True, partition=parts, n_class=k, part_id=part)
+    (torch.cat(soft_g) * gcen).sum().backward()
+    hard_g, _, _ = U.cal_centroid(feat, lab, n_class=k)
+
+    def warm(r):                                        # allocator warm-up on each rank's stream (no exchange)
+        U.update_class_center_iter(sl(feat, r), sl(lab, r), cen, m=.9, num_class=k)
+        U.cal_centroid(sl(feat, r), sl(probs, r), pseudo_label=True, weighted_ave=True, partition=parts, n_class=k,
+                       part_id=pix(part, r))
+    _on_streams(streams, warm)
+    torch.cuda.synchronize()
+
+    res = {}
+
+    def rank_fn(r):
+        new = U.update_class_center_iter(sl(feat, r), sl(lab, r), cen, m=.9, num_class=k, group=boxes[r])
+        _, sums = op.class_centres_update(sl(feat, r).contiguous(), sl(lab, r).reshape(-1), cen, .9, *boxes[r].args())
+        hard, _, _ = U.cal_centroid(sl(feat, r), sl(lab, r), n_class=k, group=boxes[r])
+        f = sl(feat, r).clone().requires_grad_(True)
+        p = sl(probs, r).clone().requires_grad_(True)
+        soft, _, _ = U.cal_centroid(f, p, pseudo_label=True, weighted_ave=True, partition=parts, n_class=k,
+                                    part_id=pix(part, r), group=boxes[r])
+        (torch.cat(soft) * gcen).sum().backward()
+        res[r] = (new, sums, hard, torch.cat(soft).detach(), f.grad, p.grad)
+    _on_streams(streams, rank_fn)
+    torch.cuda.synchronize()
+    assert all(bx.timeouts() == 0 for bx in boxes)
+    for r in range(world):
+        new, sums, hard, soft, df, dp = res[r]
+        assert torch.equal(sums[:, -1], sums_g[:, -1])                        # class counts: bit-exact, GLOBAL
+        assert float(sums[3, -1]) == 0.0 and torch.equal(new[3], new_g[3])     # empty class keeps its old centre blend
+        close(sums, sums_g, rtol=1e-6, atol=1e-6)
+        close(new, new_g, rtol=1e-5)
+        close(hard, hard_g, rtol=1e-5)
+        close(soft, torch.cat(soft_g), rtol=1e-5)
+        grad_close(df, sl(fg.grad, r), rtol=1e-5)
+        grad_close(dp, sl(pg.grad, r), rtol=1e-5)
+        assert torch.equal(res[r][0], res[0][0]) and torch.equal(res[r][3], res[0][3])     # identical bits on every rank
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_prototype_loss_and_target_step_equal_global(api, world):
+    """mpcl_loss_calc(group=mailbox) / mpcl_target_step(group=mailbox): the loss is the mean over the GLOBAL batch and the
+    gradients are the global gradient's shard (utils/loss.py:558-571 over all ranks' pixels)."""
+    from slcl.peer import LoopbackMailboxes
+    L, _ = api
+    b, c, h, w, k = 2 * world, 64, 20, 28, 5
+    g = cases.g(41)
+    feat = torch.randn(b, c, h, w, generator=g).to(dev())
+    lab = torch.randint(0, k, (b, h, w), generator=g).to(dev())
+    sel = (torch.rand(b * h * w, generator=g) > 0.4).float().to(dev())
+    cen = torch.randn(k, c, generator=g).to(dev())
+    mp = L.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.4)
+    per = b // world
+    sl = lambda t, r: t[r * per:(r + 1) * per]
+    pix = lambda t, r: t.reshape(b, -1)[r * per:(r + 1) * per].reshape(-1)
+
+    def three(f, labels, selv, group):
+        l1 = L.mpcl_loss_calc(f, labels, cen, mp, tag='source', group=group)
+        l2 = L.mpcl_loss_calc(f, labels.reshape(-1), cen, mp, pixel_sel_loc=selv, tag='target', group=group)
+        l3, hard, m = L.mpcl_target_step(f, cen, mp, .05, group=group)
+        return l1, l2, l3
+
+    fg = feat.clone().requires_grad_(True)
+    want = three(fg, lab, sel, None)
+    (want[0] + 2 * want[1] + 3 * want[2]).backward()
+    boxes = LoopbackMailboxes(world, dev()).boxes
+    streams = _rank_streams(world)
+    _on_streams(streams, lambda r: sum(three(sl(feat, r).clone().requires_grad_(True), sl(lab, r), pix(sel, r), None)).backward())
+    torch.cuda.synchronize()
+    res = {}
+
+    def rank_fn(r):
+        f = sl(feat, r).clone().requires_grad_(True)
+        got = three(f, sl(lab, r), pix(sel, r), boxes[r])
+        (got[0] + 2 * got[1] + 3 * got[2]).backward()
+        res[r] = ([x.detach() for x in got], f.grad)
+    _on_streams(streams, rank_fn)
+    torch.cuda.synchronize()
+    assert all(bx.timeouts() == 0 for bx in boxes)
+    for r in range(world):
+        for a_, b_ in zip(res[r][0], want):
+            close(a_, b_, rtol=1e-6, atol=1e-9)
+        grad_close(res[r][1], sl(fg.grad, r), rtol=1e-5)
 
 
 def test_c_abi_called_directly_with_ctypes():
