@@ -917,6 +917,12 @@ def extra_kernels(dev, feats, labels, centres, peak):
         timed(lambda: op.class_sums(f5, None, p5, True, 0.0, part5, 2, k5)), (4 * c5 + 4 * k5 + 4) * n_px)
     add("cfg5 shape: centroid_bwd soft P=2 C32 K4 (dF + dP)",
         timed(lambda: op.centroid_bwd(f5, None, p5, True, 0.0, part5, 2, k5, g5, s5, 1.0, True)), (8 * c5 + 8 * k5 + 4) * n_px)
+    # the trainer-default call: cal_centroid(..., partition=2) draws the reversed-Monte-Carlo partition itself -- one
+    # torch.randperm(N) on the map's device (3.2 M elements) inside the timed call, forward only
+    from slcl.utils_ import cal_centroid as _cal_centroid
+    add("cfg5 shape: cal_centroid(soft, partition=2) through the Python API INCLUDING the rMC draw (forward)",
+        timed(lambda: _cal_centroid(f5, p5, pseudo_label=True, weighted_ave=True, partition=2, n_class=k5)),
+        (4 * c5 + 4 * k5 + 4) * n_px)
     # cfg4 geometry per GPU (MS-CMRSeg: 16 of the 128 images per GPU, C = 32, K = 4, 224 x 224): prototype loss fwd+bwd
     from slcl.plan import ProtoPlan
     f4 = f5[:16].contiguous()
@@ -1041,6 +1047,21 @@ def p2p_kernels(dev, gen):
         return s.elapsed_time(e) / iters
 
     out = {}
+    # cfg3 through the PUBLIC API: class-balanced draw (one randperm on the device) + per-class compaction + gather of the
+    # 4096 + 16384 unit rows + tensor-core sweeps + scatter of the row gradients back into the NCHW map; no host sync
+    from slcl.p2p import sampled_supcon_loss
+    fmap = torch.randn(16, 256, 64, 64, device=dev, generator=gen).requires_grad_(True)
+    lmap = torch.randint(0, 5, (16, 64, 64), device=dev, generator=gen)
+
+    def api_step():
+        loss_s = sampled_supcon_loss(fmap, lmap, A, M, 5, temperature=T)
+        loss_s.backward()
+        fmap.grad = None
+    ms = timed(api_step, iters=10)
+    out["cfg3 through the public API: sampled_supcon_loss (draw + compaction + gather + sweeps + scatter), fwd+bwd, eager"] = {
+        "ms": ms, "algorithmic_flop": 8.0 * A * M * d, "achieved_TFLOPs": 8.0 * A * M * d / (ms * 1e-3) / 1e12,
+        "frac_of_bf16_peak": 8.0 * A * M * d / (ms * 1e-3) / 1e12 / tf_peak, "rows_per_s": (A + M) / (ms * 1e-3)}
+    del fmap, lmap
     # BlockConLoss at the reference's documented shape (1, 2, 32, 224, 224), 32 x 32 tiles: 49 tiles of 2048 rows as ONE
     # block-diagonal problem (the reference and the per-tile loop launch 49 separate SupCon problems)
     from slcl.loss import BlockConLoss

@@ -359,17 +359,34 @@ def block_con_loss(features: torch.Tensor, labels: Optional[torch.Tensor] = None
 # sampled rectangular pixel <-> pixel loss (cfg3).  PARITY UNPINNED (our spec,
 # SURVEY.md section 8(c)-3); the square case A == B == all pixels is SupConLoss.
 # --------------------------------------------------------------------------
-def sample_class_balanced(labels_flat: torch.Tensor, per_class: int, n_class: int,
-                          generator: torch.Generator) -> torch.Tensor:
-    """Per class k: ascending pixel indices (``torch.nonzero`` order), then the
-    first ``per_class`` entries of a ``torch.randperm`` over them.  Returns the
-    concatenation over classes (int64)."""
-    picks = []
+def sample_class_balanced(labels_flat: torch.Tensor, n_pick: int, n_class: int, perm: torch.Tensor) -> torch.Tensor:
+    """Class-balanced pick of exactly ``n_class * ceil(n_pick / n_class)`` distinct pixels from ONE random permutation
+    ``perm`` of all pixel indices (``torch.randperm(N, generator)``, PyTorch's RNG stream):
+
+      phase 1  per class k (labels in [0, n_class)): the first ``per = ceil(n_pick / n_class)`` pixels of class k in
+               permutation order; output is class-major (class 0's picks, then class 1's, ...), each in permutation order;
+      phase 2  when classes have fewer than ``per`` members, the open slots are filled -- after all phase-1 picks --
+               with the first not-yet-picked valid pixels in permutation order, whatever their class.
+
+    The output size does not depend on the class counts, so the CUDA path needs no size on the host.  With fewer than
+    ``n_class * per`` valid pixels the tail repeats nothing: the function raises (the CUDA path returns the count and
+    poisons the loss)."""
+    lab = labels_flat.reshape(-1)[perm]
+    per = -(-n_pick // n_class)
+    total = per * n_class
+    picked = torch.zeros(perm.numel(), dtype=torch.bool)
+    out = []
     for k in range(n_class):
-        idx_k = torch.nonzero(labels_flat == k).squeeze(1)
-        perm = torch.randperm(idx_k.numel(), generator=generator, device=generator.device)[:per_class]
-        picks.append(idx_k[perm.to(idx_k.device)])
-    return torch.cat(picks)
+        pos = torch.nonzero(lab == k).squeeze(1)[:per]
+        picked[pos] = True
+        out.append(perm[pos])
+    n1 = sum(o.numel() for o in out)
+    valid = (lab >= 0) & (lab < n_class)
+    rest = torch.nonzero(valid & ~picked).squeeze(1)[:total - n1]
+    if n1 + rest.numel() < total:
+        raise ValueError("not enough labelled pixels for the requested sample")
+    out.append(perm[rest])
+    return torch.cat(out)
 
 
 def supcon_rect(anchor: torch.Tensor, contrast: torch.Tensor, anchor_lab: torch.Tensor,

@@ -114,7 +114,13 @@ __global__ void __launch_bounds__(kThreads) seg_finalize_kernel(const float* par
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < kThreads; ++i) tot += s_ce[i];
-    losses[0] = (float)(tot / ((double)B * (double)hw));                               // mean over pixels (:63-64)
+    // nn.CrossEntropyLoss (:63-64) averages over the pixels it does not ignore.  Labels outside [0, K) -- the
+    // reference's ignore_index = -100 and anything else it would raise on -- have an all-zero one-hot row here: they add
+    // nothing to any sum and are not counted (no host-visible error: that would need a synchronisation).
+    double n_valid = 0.0;
+    for (int i = 0; i < B * K; ++i) n_valid += (double)stats[(int64_t)i * kStats + 2];
+    (void)hw;
+    losses[0] = (float)(tot / n_valid);
     double dice = 0.0;
     for (int b = 0; b < B; ++b)
       for (int k = 0; k < K; ++k) {
@@ -140,7 +146,14 @@ template <int K, int VEC>
 __global__ void __launch_bounds__(kThreads) seg_bwd_kernel(const float* logits, const int64_t* labels, int64_t hw, int B,
                                                            const float* stats, const float* gout, float* dlogits) {
   __shared__ float s_dice_a[K], s_dice_b[K], s_jac_a[K], s_jac_b[K];
+  __shared__ float s_red[kWarps];
   const int b = blockIdx.y;
+  {   // pixels the cross entropy averages over = labels inside [0, K) = sum of the one-hot counts (exact in fp32 per entry)
+    double cnt = 0.0;
+    for (int i = threadIdx.x; i < B * K; i += kThreads) cnt += (double)stats[(int64_t)i * kStats + 2];
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = (float)cnt;
+  }
   if (threadIdx.x < K) {
     const int k = threadIdx.x;
     const float* s = stats + ((int64_t)b * K + k) * kStats;
@@ -164,7 +177,10 @@ __global__ void __launch_bounds__(kThreads) seg_bwd_kernel(const float* logits, 
   const float* img = logits + (int64_t)b * K * hw;
   float prob[K][VEC], logp[K][VEC];
   softmax_k<K, VEC>(img, hw, p, prob, logp);
-  const float g_ce = gout[0] / ((float)B * (float)hw);
+  float n_valid = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) n_valid += s_red[w];
+  const float g_ce = gout[0] / n_valid;
   float out[K][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -180,7 +196,8 @@ __global__ void __launch_bounds__(kThreads) seg_bwd_kernel(const float* logits, 
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const float g = (lab == k) ? 1.f : 0.f;
-      out[k][v] = g_ce * (prob[k][v] - g) + prob[k][v] * (dp[k] - dot);     // CE + softmax backward of the rest
+      const float ce = (lab >= 0 && lab < K) ? g_ce * (prob[k][v] - g) : 0.f;      // ignored pixels carry no CE gradient
+      out[k][v] = ce + prob[k][v] * (dp[k] - dot);                              // CE + softmax backward of the rest
     }
   }
 #pragma unroll

@@ -649,7 +649,10 @@ def p2p_fwd(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tensor,
 
 @p2p_fwd.register_fake
 def _(a, b, a_meta, b_meta, shift, weight, temperature, n_class=0, a_selfcol=None, keep_state=False, n_batch=1):
-    return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), torch.empty(0, dtype=torch.uint8, device=a.device))
+    # the real op returns the opaque backward state (slcl_p2p_state_bytes: a pure function of the shapes, no device
+    # needed) when it is kept, an empty tensor otherwise
+    n_state = _lib.load().slcl_p2p_state_bytes(a.shape[0], a.shape[1]) if (n_class > 0 and keep_state) else 0
+    return (shift.new_empty(1), shift.new_empty((a.shape[0], 3)), torch.empty(n_state, dtype=torch.uint8, device=a.device))
 
 
 @torch.library.custom_op("slcl::p2p_bwd", mutates_args=(), device_types="cuda")

@@ -18,6 +18,38 @@ from . import ops  # noqa: F401
 
 _ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 _SORT_MIN_ROWS = 8192        # one-row-set problems at least this large are gathered sorted by label (see p2p_loss)
+AUTO_N_CLASS = 8             # labelled SupCon family without an explicit n_class: analytic sweeps for labels in [0, 8)
+
+
+class _AutoClasses:
+    """Lets the STOCK signatures (``SupConLoss()``, ``LocalConLoss()``: no ``n_class`` argument) reach the analytic
+    tensor-core sweeps.  Those need class-index labels in [0, n_class), n_class <= 8 -- true for every label map of the
+    reference (4 or 5 classes, config.py:9) but not guaranteed by the signature.  The first labelled call of a module
+    checks the range once on the host (one synchronisation in the module's lifetime); every later call checks it on the
+    device and poisons the loss with NaN if a label ever leaves the range (no synchronisation, no silent wrong value).
+    ``n_class=0`` in the constructor forces the general sweeps (any integer labels), ``n_class=k`` trusts the caller."""
+
+    def __init__(self, n_class):
+        self.fixed = n_class            # None = auto
+        self.auto = None                # decided at the first labelled call
+
+    def resolve(self, labels):
+        """-> (n_class for the sweeps, device flag `labels in range` or None)"""
+        if self.fixed is not None:
+            return int(self.fixed), None
+        if labels is None:
+            return 0, None
+        if self.auto is None:
+            lo, hi = int(labels.min()), int(labels.max())        # once per module
+            self.auto = AUTO_N_CLASS if (lo >= 0 and hi < AUTO_N_CLASS) else 0
+        if self.auto == 0:
+            return 0, None
+        return self.auto, (labels.min() >= 0) & (labels.max() < self.auto)
+
+
+def _guard(loss, in_range):
+    return loss if in_range is None else torch.where(in_range, loss, torch.full_like(loss, float("nan")))
+
 
 
 class _P2PLoss(torch.autograd.Function):
@@ -136,12 +168,15 @@ class SupConLoss(nn.Module):
     """Reference utils/loss.py:315-387.  ``contrast_mode`` / ``base_temperature`` are stored and
     unused there too."""
 
-    def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07, n_class=0):
+    def __init__(self, temperature=0.07, contrast_mode='all', base_temperature=0.07, n_class=None):
         super().__init__()
         self.temperature = temperature
         self.contrast_mode = contrast_mode
         self.base_temperature = base_temperature
-        self.n_class = n_class          # extension: 1..8 = labels are class indices -> analytic tensor-core sweeps
+        # extension: 1..8 = labels are class indices in [0, n_class) -> analytic tensor-core sweeps; 0 = general sweeps
+        # (any integer labels); None (default) = decided from the labels themselves (_AutoClasses)
+        self.n_class = n_class
+        self._classes = _AutoClasses(n_class)
 
     def forward(self, features, labels=None):
         if features.ndim <= 3:
@@ -149,14 +184,15 @@ class SupConLoss(nn.Module):
                              'at least 4 dimensions are required')
         h, w = features.shape[-2:]
         dev = features.device
-        return _supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev),
-                       n_class=self.n_class)
+        n_class, in_range = self._classes.resolve(labels)
+        return _guard(_supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev),
+                              n_class=n_class), in_range)
 
 
 class LocalConLoss(nn.Module):
     """Reference utils/loss.py:390-413: stride-subsampled SupCon."""
 
-    def __init__(self, temperature=0.7, stride=4, n_class=0):
+    def __init__(self, temperature=0.7, stride=4, n_class=None):
         super().__init__()
         self.temp = temperature
         self.supconloss = SupConLoss(temperature=self.temp, n_class=n_class)
@@ -167,14 +203,15 @@ class LocalConLoss(nn.Module):
         dev = features.device
         ys = torch.arange(0, h, self.stride, device=dev)
         xs = torch.arange(0, w, self.stride, device=dev)
-        return _supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True, n_class=self.supconloss.n_class)
+        n_class, in_range = self.supconloss._classes.resolve(labels)
+        return _guard(_supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True, n_class=n_class), in_range)
 
 
 class BlockConLoss(nn.Module):
     """Reference utils/loss.py:416-466: mean of SupCon over block_size x block_size tiles; tiles whose
     labels are all background are skipped (decided on the device, no per-tile host sync)."""
 
-    def __init__(self, temperature=0.7, block_size=32, n_class=0):
+    def __init__(self, temperature=0.7, block_size=32, n_class=None):
         super().__init__()
         self.block_size = block_size
         self.supconloss = SupConLoss(temperature=temperature, n_class=n_class)
@@ -187,24 +224,24 @@ class BlockConLoss(nn.Module):
         t = self.supconloss.temperature
         if div == 0:
             return torch.zeros((), device=dev)
-        if self.batched and features.ndim == 5 and self.supconloss.n_class == 0:
+        if self.batched and features.ndim == 5 and not self.supconloss.n_class:
             b, v = features.shape[:2]
             if (b * v * bs * bs) % 128 == 0:
                 return self._forward_batched(features, labels, div, t)
+        n_class, in_range = self.supconloss._classes.resolve(labels)
         losses, flags = [], []
         for i in range(div):
             for j in range(div):
                 ys = torch.arange(i * bs, (i + 1) * bs, device=dev)
                 xs = torch.arange(j * bs, (j + 1) * bs, device=dev)
-                losses.append(_supcon(features, labels, t, ys, xs, zero_if_no_foreground=True,
-                                      n_class=self.supconloss.n_class))
+                losses.append(_supcon(features, labels, t, ys, xs, zero_if_no_foreground=True, n_class=n_class))
                 if labels is not None:
                     flags.append((labels[:, :, i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] != 0).any())
         stacked = torch.stack(losses)
         if labels is None:
-            return stacked.mean()                                                    # :465
+            return stacked.mean()                                                    # :465 (general sweeps: no guard)
         keep = torch.stack(flags).float()
-        return (stacked * keep).sum() / keep.sum().clamp_min(1.0)                    # :445-448 (0 when every tile is skipped)
+        return _guard((stacked * keep).sum() / keep.sum().clamp_min(1.0), in_range)   # :445-448 (0 when every tile is skipped)
 
     def _forward_batched(self, features, labels, div, t):
         """All div x div tiles as ONE block-diagonal problem (one launch per tensor-core sweep instead of div^2
@@ -234,28 +271,58 @@ class BlockConLoss(nn.Module):
         return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True, n_batch=n_tiles)
 
 
+def _balanced_prefix(perm, lp, rank, counts, valid, per: int, total: int):
+    """Pixels of ``perm`` chosen by the two-phase rule of ``sample_class_balanced`` (all on the device, no host sync):
+    returns (picks [total], n_filled 0-d)."""
+    k = counts.numel()
+    take = counts.clamp(max=per)                                   # phase-1 picks per class
+    n1 = take.sum()
+    base = torch.cumsum(take, 0) - take                            # class-major output offsets
+    p1 = rank < per                                                # rank = huge for pixels outside [0, K)
+    dest1 = base[lp.clamp(0, k - 1)] + rank
+    u = valid & ~p1
+    r2 = torch.cumsum(u, 0) - 1
+    p2 = u & (r2 < total - n1)
+    dest = torch.where(p1, dest1, torch.where(p2, n1 + r2, torch.full_like(r2, total)))      # slot `total` = dump
+    out = torch.zeros(total + 1, dtype=torch.int64, device=perm.device)
+    out.index_put_((dest,), perm)
+    return out[:total], n1 + torch.minimum(u.sum(), total - n1)
+
+
 def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
-                          generator: Optional[torch.Generator] = None):
-    """Class-balanced sampler.  Per class k the candidate list is the stable
-    compaction ``nonzero(labels == k)`` (CUDA kernel, bit-exact order); the picks are the first
-    ceil(n/K) entries of ``torch.randperm(count_k, generator)`` -- PyTorch's own RNG stream.
-    Anchors are a prefix of the contrast picks of their class.  Returns (anchor_idx, contrast_idx)."""
+                          generator: Optional[torch.Generator] = None, return_counts: bool = False):
+    """Class-balanced sampler (north_star item 1), with NO host synchronisation.
+
+    ONE permutation of all pixels is drawn from PyTorch's RNG stream -- ``torch.randperm(N, generator)``, on the label
+    map's device unless the generator lives elsewhere -- and the labels are read in that order.  The stable per-class
+    compaction of the permuted labels (CUDA kernel ``slcl_compact_by_class``, order bit-identical to ``torch.nonzero``)
+    gives every pixel its rank within its class; class k contributes its first ``ceil(n / K)`` pixels in permutation
+    order (class-major output), and slots a short class leaves open are filled with the next unpicked labelled pixels
+    (the test-side restatement of this rule is ``sample_class_balanced`` of the CPU checker).  Output sizes are ``K * ceil(n / K)`` whatever the class
+    counts, so nothing has to come back to the host.  Anchors use the same rule with their own quota (their per-class
+    picks are a prefix of the contrast picks of that class).  Returns (anchor_idx, contrast_idx[, n_filled_anchor, n_filled_contrast])."""
     lab = labels.reshape(-1).long()
-    counts, offsets, index = _ops.compact_by_class(lab, n_class)
-    counts_h = counts.cpu().tolist()           # one host sync: randperm needs the sizes
-    offs_h = [0]
-    for cnt in counts_h:
-        offs_h.append(offs_h[-1] + cnt)
+    n = lab.numel()
+    dev = lab.device
+    gen_dev = generator.device if generator is not None else dev
+    perm = torch.randperm(n, generator=generator, device=gen_dev).to(dev)
+    lp = lab[perm]
+    counts, offsets, index = _ops.compact_by_class(lp, n_class)
+    pos = torch.arange(n, device=dev)
+    n_valid = offsets[n_class]
+    cls = torch.searchsorted(offsets[1:].contiguous(), pos, right=True).clamp(max=n_class - 1)
+    rank_sorted = pos - offsets[cls]
+    rank = torch.full((n + 1,), 1 << 60, dtype=torch.int64, device=dev)
+    rank.index_put_((torch.where(pos < n_valid, index, torch.full_like(index, n)),), rank_sorted)
+    rank = rank[:n]
+    valid = (lp >= 0) & (lp < n_class)
     per_a = -(-n_anchor // n_class)
     per_c = -(-n_contrast // n_class)
-    gen_dev = generator.device if generator is not None else torch.device("cpu")
-    a_parts, c_parts = [], []
-    for k in range(n_class):
-        perm = torch.randperm(counts_h[k], generator=generator, device=gen_dev).to(lab.device)
-        picks = index[offs_h[k] + perm[:per_c]]
-        c_parts.append(picks)
-        a_parts.append(picks[:per_a])
-    return torch.cat(a_parts), torch.cat(c_parts)
+    c_idx, c_fill = _balanced_prefix(perm, lp, rank, counts, valid, per_c, per_c * n_class)
+    a_idx, a_fill = _balanced_prefix(perm, lp, rank, counts, valid, per_a, per_a * n_class)
+    if return_counts:
+        return a_idx, c_idx, a_fill, c_fill
+    return a_idx, c_idx
 
 
 def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
@@ -263,16 +330,24 @@ def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int,
                         anchor_idx: Optional[torch.Tensor] = None, contrast_idx: Optional[torch.Tensor] = None,
                         analytic: bool = True):
     """Sampled rectangular pixel <-> pixel loss (BASELINE.json configs[2]): anchors x contrast rows
-    drawn class-balanced from an NCHW map, L2-normalised, bf16 tensor-core similarities."""
+    drawn class-balanced from an NCHW map, L2-normalised, bf16 tensor-core similarities.  The whole call -- draw,
+    compaction, gather, sweeps -- runs without a host synchronisation; if the map holds fewer labelled pixels than the
+    sample needs, the loss is NaN (decided on the device)."""
+    short = None
     if anchor_idx is None or contrast_idx is None:
-        anchor_idx, contrast_idx = sample_class_balanced(labels, n_anchor, n_contrast, n_class, generator)
+        anchor_idx, contrast_idx, a_fill, c_fill = sample_class_balanced(labels, n_anchor, n_contrast, n_class, generator,
+                                                                          return_counts=True)
+        short = (a_fill < anchor_idx.numel()) | (c_fill < contrast_idx.numel())
     lab = labels.reshape(-1)
     la, lb = lab[anchor_idx], lab[contrast_idx]
     fg = (la != 0).float()
     weight = fg / fg.sum()
-    # analytic sweeps need class-index labels (true here) and unique picks (randperm prefixes are)
-    return p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True,
+    # analytic sweeps need class-index labels (true here) and unique picks (distinct pixels of one permutation are)
+    loss = p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True,
                     n_class=n_class if (analytic and n_class <= 8) else 0)
+    if short is not None:
+        loss = torch.where(short, torch.full_like(loss, float("nan")), loss)
+    return loss
 
 
 class InterpolatedSupervisedContrastiveLoss(nn.Module):

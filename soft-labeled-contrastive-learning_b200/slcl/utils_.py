@@ -52,8 +52,13 @@ def rmc_partition_ids(n_pixels: int, partition: int, generator: Optional[torch.G
     """Reversed-Monte-Carlo partition assignment (spec: SURVEY.md 8(c)-2; the
     reference fork has no sampler).  Drawn from PyTorch's RNG stream --
     ``torch.randperm(N, generator) % P`` in (b, h, w) pixel order -- so the CUDA
-    path consumes exactly the indices a PyTorch restatement sees."""
-    gen_dev = generator.device if generator is not None else torch.device("cpu")
+    path consumes exactly the indices a PyTorch restatement sees.  Without a
+    generator the draw runs on ``device`` (torch's CUDA RNG: no host round trip);
+    a generator is used on its own device."""
+    if generator is not None:
+        gen_dev = generator.device                    # the generator decides where the draw happens
+    else:
+        gen_dev = torch.device(device) if device is not None else torch.device("cpu")      # default: on the map's device
     perm = torch.randperm(n_pixels, generator=generator, device=gen_dev)
     ids = (perm % partition).to(torch.int32)
     return ids if device is None else ids.to(device)

@@ -435,6 +435,135 @@ def test_full_size_properties_cfg4_shape(api):
 
 
 # ---------------------------------------------------------------------------
+# FULL-SIZE parity against the oracle (BASELINE.json configs at their stated sizes).  The oracle is plain torch, so it
+# runs on CUDA tensors too: evaluated here on the same GPU in fp32 with TF32 off -- the reference's own op sequence at the
+# reference's own precision.  Class counts / labels bit-exact, everything else rtol 1e-4.
+# ---------------------------------------------------------------------------
+@pytest.fixture()
+def no_tf32():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _proto_full_size(loss_mod, feas, labels, cc, k, m, sel=None, tag='source'):
+    spec = O.MarginSpec(num_class=k, temperature=.1, m=m, base_temperature=1.0)
+    fo = feas.clone().requires_grad_(True)
+    ref = O.mpcl_loss_calc(fo, labels, cc, spec, pixel_sel_loc=sel, tag=tag)
+    ref.backward()
+    f = feas.clone().requires_grad_(True)
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=m)
+    out = loss_mod.mpcl_loss_calc(f, labels, cc, mp, pixel_sel_loc=sel, tag=tag)
+    out.backward()
+    close(out, ref, rtol=RTOL, atol=0)
+    grad_close(f.grad, fo.grad)
+    return out
+
+
+def test_full_size_cfg1_batch8(api, no_tf32):
+    """configs[0] at its stated size: B8, 128-d, 33x33 map, labels 256x256 (down-sampled inside), K5 -- CPU oracle."""
+    loss_mod, _ = api
+    g = cases.g(101)
+    feas = torch.randn(8, 128, 33, 33, generator=g)
+    labels = torch.randint(0, 5, (8, 256, 256), generator=g)
+    cc = torch.randn(5, 128, generator=g)
+    spec = O.MarginSpec(num_class=5, temperature=.1, m=.4, base_temperature=1.0)
+    fo = feas.clone().requires_grad_(True)
+    ref = O.mpcl_loss_calc(fo, labels, cc, spec, tag='source')
+    ref.backward()
+    f = feas.to(dev()).requires_grad_(True)
+    out = loss_mod.mpcl_loss_calc(f, labels.to(dev()), cc.to(dev()), loss_mod.MPCL(dev(), 5, .1, .4, 1.0), tag='source')
+    out.backward()
+    close(out, ref, rtol=RTOL, atol=0)
+    grad_close(f.grad, fo.grad)
+
+
+def test_full_size_cfg2_prototype_path(api, no_tf32):
+    """configs[1]: B32 C128 256x256 K5 (2 097 152 pixels), target variant with a selection mask: loss + dF vs the
+    oracle on the GPU; EMA class centres and pseudo labels on the same map."""
+    loss_mod, utils_mod = api
+    gen = torch.Generator(device=dev()).manual_seed(202)
+    b, c, h, w, k = 32, 128, 256, 256, 5
+    feas = torch.randn(b, c, h, w, device=dev(), generator=gen)
+    labels = torch.randint(0, k, (b * h * w,), device=dev(), generator=gen)
+    sel = (torch.rand(b * h * w, device=dev(), generator=gen) > 0.5).float()
+    cc = torch.randn(k, c, device=dev(), generator=gen)
+    _proto_full_size(loss_mod, feas, labels, cc, k, .2, sel=sel, tag='target')
+    new = utils_mod.update_class_center_iter(feas, labels.view(b, h, w), cc, m=.9, num_class=k)
+    close(new, O.update_class_center_iter(feas, labels.view(b, h, w), cc, m=.9, num_class=k), rtol=RTOL)
+    sums = torch.ops.slcl.class_sums(feas, labels, None, False, 0.0, None, 1, k)
+    assert torch.equal(sums[:, -1].long(), torch.bincount(labels, minlength=k))
+
+
+def _pseudo_labels_match(utils_mod, feas, cc, th):
+    hard, sel = utils_mod.generate_pseudo_label(feas, cc, th)
+    hard_o, sel_o = O.generate_pseudo_label(feas, cc, th)
+    if torch.equal(hard, hard_o) and torch.equal(sel, sel_o):
+        return
+    # two fp32 evaluation orders can only disagree at a near-tie: every mismatch must sit within 1e-6 of the decision
+    fn = F.normalize(feas, dim=1).permute(0, 2, 3, 1).reshape(-1, feas.shape[1]).double()
+    cos = fn @ F.normalize(cc, dim=1).double().t()
+    top = torch.sort(cos, dim=1).values
+    gap = top[:, -1] - top[:, -2]
+    bad_l = hard != hard_o
+    bad_s = sel != sel_o
+    assert int(bad_l.sum()) + int(bad_s.sum()) <= 4
+    assert bool((gap[bad_l] < 1e-6).all()) and bool(((gap[bad_s] - th).abs() < 1e-6).all())
+
+
+def test_full_size_cfg4_per_gpu_shape(api, no_tf32):
+    """configs[3] per GPU: 16 x 32 x 224 x 224, K4 (MS-CMRSeg): source loss with labels at another resolution is not the
+    trainer's case here -- labels at feature resolution, source + target variants, EMA centres, pseudo labels."""
+    loss_mod, utils_mod = api
+    gen = torch.Generator(device=dev()).manual_seed(404)
+    b, c, h, w, k = 16, 32, 224, 224, 4
+    feas = torch.randn(b, c, h, w, device=dev(), generator=gen)
+    labels = torch.multinomial(torch.tensor([0.9146, 0.0253, 0.0309, 0.0292], device=dev()), b * h * w, True, generator=gen)
+    cc = cases.shipped_centres().to(dev())
+    _proto_full_size(loss_mod, feas, labels.view(b, h, w), cc, k, .4, tag='source')
+    new = utils_mod.update_class_center_iter(feas, labels.view(b, h, w), cc, m=.9, num_class=k)
+    close(new, O.update_class_center_iter(feas, labels.view(b, h, w), cc, m=.9, num_class=k), rtol=RTOL)
+    _pseudo_labels_match(utils_mod, feas, new, .05)
+    hard, sel = utils_mod.generate_pseudo_label(feas, new, .05)
+    _proto_full_size(loss_mod, feas, hard, new, k, .2, sel=sel, tag='target')
+
+
+def test_full_size_cfg5_soft_centroids_two_partitions(api, no_tf32):
+    """configs[4] per GPU: 64 x 32 x 224 x 224 decoder features, K4 soft labels x certainty, P=2 reversed-Monte-Carlo
+    partitions: centroids, dF and d(soft labels) vs the oracle; hard source centroids; per-partition class counts exact."""
+    _, utils_mod = api
+    gen = torch.Generator(device=dev()).manual_seed(505)
+    b, c, h, w, k, parts = 64, 32, 224, 224, 4, 2
+    n = b * h * w
+    feas = torch.randn(b, c, h, w, device=dev(), generator=gen)
+    probs = torch.softmax(3 * torch.randn(b, k, h, w, device=dev(), generator=gen), 1)
+    part = (torch.randperm(n, device=dev(), generator=gen) % parts).to(torch.int32)
+    lab = torch.randint(0, k, (b, h, w), device=dev(), generator=gen)
+    gcen = torch.randn(parts * k, c, device=dev(), generator=gen)
+    fo, po = feas.clone().requires_grad_(True), probs.clone().requires_grad_(True)
+    ref, _, _ = O.cal_centroid(fo, po, pseudo_label=True, weighted_ave=True, partition=parts, n_class=k, threshold=.5,
+                               part_id=part)
+    (torch.cat(ref) * gcen).sum().backward()
+    f, p = feas.clone().requires_grad_(True), probs.clone().requires_grad_(True)
+    out, _, _ = utils_mod.cal_centroid(f, p, pseudo_label=True, weighted_ave=True, partition=parts, n_class=k, threshold=.5,
+                                       part_id=part)
+    (torch.cat(out) * gcen).sum().backward()
+    close(torch.cat(out), torch.cat(ref), rtol=RTOL)
+    grad_close(f.grad, fo.grad)
+    grad_close(p.grad, po.grad)
+    del fo, po, ref
+    hard, _, _ = utils_mod.cal_centroid(feas, lab, n_class=k)
+    hard_o, _, _ = O.cal_centroid(feas, lab, n_class=k)
+    close(hard, hard_o, rtol=RTOL)
+    # arg-max one-hot weights x partitions: the weight column of the class sums is an exact pixel count
+    sums = torch.ops.slcl.class_sums(feas, None, probs, False, 0.0, part, parts, k)
+    want = torch.bincount(part.long() * k + probs.argmax(1).reshape(-1), minlength=parts * k)
+    assert torch.equal(sums[:, -1].long(), want)
+
+
+# ---------------------------------------------------------------------------
 # pixel <-> pixel path (tcgen05 tensor cores, bf16 inputs / fp32 accumulate): rtol 2e-2 (north_star)
 # ---------------------------------------------------------------------------
 P2P_RTOL = 2e-2
@@ -535,15 +664,9 @@ def test_sampled_rectangular_loss_vs_oracle(b, c, h, w, k, na, nc, t, analytic):
     gen = cases.g(90 + c)
     feat = torch.randn(b, c, h, w, generator=gen)
     labels = torch.randint(0, k, (b, h, w), generator=gen)
-    per_a, per_c = -(-na // k), -(-nc // k)
-    g_o = cases.g(5)
-    picks = []
-    for cls in range(k):
-        idx_k = torch.nonzero(labels.view(-1) == cls).squeeze(1)
-        perm = torch.randperm(idx_k.numel(), generator=g_o)
-        picks.append(idx_k[perm[:per_c]])
-    c_idx_o = torch.cat(picks)
-    a_idx_o = torch.cat([p_[:per_a] for p_ in picks])
+    perm_o = torch.randperm(labels.numel(), generator=cases.g(5))          # the one draw, from PyTorch's RNG stream
+    c_idx_o = O.sample_class_balanced(labels.view(-1), nc, k, perm_o)
+    a_idx_o = O.sample_class_balanced(labels.view(-1), na, k, perm_o)
     a_idx, c_idx = p2p.sample_class_balanced(labels.to(dev()), na, nc, k, cases.g(5))
     assert torch.equal(a_idx.cpu(), a_idx_o) and torch.equal(c_idx.cpu(), c_idx_o)        # bit-exact selection
     fo = feat.clone().requires_grad_(True)
@@ -557,6 +680,47 @@ def test_sampled_rectangular_loss_vs_oracle(b, c, h, w, k, na, nc, t, analytic):
     out.backward()
     close(out, ref, rtol=P2P_RTOL)
     grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+
+
+@pytest.mark.parametrize("n,k,na,nc,rare", [(5000, 4, 64, 256, 0), (5000, 5, 100, 400, 7), (3000, 3, 30, 90, 1), (70000, 5, 4096, 16384, 0)])
+def test_sampler_without_host_sync_bit_exact(n, k, na, nc, rare):
+    """Sampler spec (oracle/slcl_oracle.py:sample_class_balanced): one randperm, rank within class from the stable
+    compaction kernel, short classes topped up in permutation order, labels outside [0, K) never picked.  Indices must be
+    bit-identical to the oracle; no .cpu()/.item() happens inside (checked with torch's sync debug mode)."""
+    from slcl import p2p
+    g = cases.g(300 + n + rare)
+    labels = torch.randint(0, k, (n,), generator=g)
+    if rare:
+        labels[labels == k - 1] = 0
+        labels[torch.randperm(n, generator=g)[:rare]] = k - 1       # class k-1 has only `rare` members: phase 2 fills its slots
+    labels[torch.randperm(n, generator=g)[:17]] = 255                # ignore label: never picked
+    dgen = lambda: torch.Generator(device=dev()).manual_seed(5)      # the draw itself runs on the device (torch's CUDA RNG)
+    perm_o = torch.randperm(n, generator=dgen(), device=dev()).cpu()
+    want_c = O.sample_class_balanced(labels, nc, k, perm_o)
+    want_a = O.sample_class_balanced(labels, na, k, perm_o)
+    lab_d = labels.to(dev())
+    p2p.sample_class_balanced(lab_d, na, nc, k, dgen())               # warm-up (allocator)
+    gen = dgen()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        a_idx, c_idx, a_fill, c_fill = p2p.sample_class_balanced(lab_d, na, nc, k, gen, return_counts=True)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.equal(c_idx.cpu(), want_c) and torch.equal(a_idx.cpu(), want_a)
+    assert int(c_fill) == want_c.numel() and int(a_fill) == want_a.numel()
+    assert c_idx.unique().numel() == c_idx.numel()                    # distinct pixels
+    assert bool((labels[c_idx.cpu()] < k).all())
+
+
+def test_sampler_reports_short_maps_and_the_loss_is_nan():
+    from slcl import p2p
+    g = cases.g(77)
+    feat = torch.randn(1, 16, 8, 8, generator=g).to(dev())
+    labels = torch.randint(0, 4, (1, 8, 8), generator=g).to(dev())
+    a_idx, c_idx, a_fill, c_fill = p2p.sample_class_balanced(labels, 32, 128, 4, cases.g(1), return_counts=True)
+    assert int(c_fill) == 64 and c_idx.numel() == 128                  # only 64 pixels exist
+    assert torch.isnan(p2p.sampled_supcon_loss(feat, labels, 32, 128, 4, generator=cases.g(1)))
 
 
 def test_p2p_full_size_properties_cfg3():
@@ -1056,6 +1220,25 @@ def test_seg_losses_vs_oracle_shapes(b, k, h, w):
     grad_close(z.grad, zo.grad)
 
 
+def test_cross_entropy_ignores_unlabelled_pixels_like_nn_cross_entropy():
+    """nn.CrossEntropyLoss (utils/loss.py:63-64) averages over the pixels it does not ignore (ignore_index = -100):
+    ignored pixels count neither in the numerator nor in the denominator and get no gradient."""
+    from slcl import seg
+    gen = cases.g(9090)
+    logits = 1.5 * torch.randn(3, 4, 20, 24, generator=gen)
+    labels = torch.randint(0, 4, (3, 20, 24), generator=gen)
+    labels[torch.rand(3, 20, 24, generator=gen) < 0.3] = -100
+    zo = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(zo, labels, ignore_index=-100)
+    ref.backward()
+    z = logits.to(dev()).requires_grad_(True)
+    out = seg.loss_calc(z, labels.to(dev()), 0, False)
+    out.backward()
+    close(out, ref)
+    grad_close(z.grad, zo.grad)
+    assert float(z.grad.permute(0, 2, 3, 1)[(labels == -100).to(dev())].abs().max()) == 0.0
+
+
 def test_iscl_vs_reference_golden_gpu():
     """f-4: ISCL = two sweeps of the tensor-core kernel (bf16 inputs: rtol 2e-2)."""
     import os
@@ -1067,6 +1250,29 @@ def test_iscl_vs_reference_golden_gpu():
     val.backward()
     close(val, gold["iscl_loss"], rtol=P2P_RTOL)
     grad_close(f.grad, gold["iscl_dfeat"], rtol=P2P_RTOL, floor=0.5)
+
+
+def test_stock_signatures_reach_the_analytic_sweeps_and_stay_safe(api):
+    """SupConLoss() / LocalConLoss() exactly as the reference constructs them (no n_class): class-index labels take the
+    analytic sweeps (same value as the general sweeps and the oracle); labels outside [0, 8) at the first call select the
+    general sweeps; labels that LEAVE the range later poison the loss with NaN instead of returning a wrong value."""
+    loss_mod, _ = api
+    gen = cases.g(808)
+    f5 = F.normalize(torch.randn(2, 2, 24, 16, 16, generator=gen), dim=2)
+    lab = torch.randint(0, 4, (2, 2, 16, 16), generator=gen)
+    ref = O.supcon_loss(f5, lab, 0.7)
+    stock = loss_mod.SupConLoss(0.7)
+    out = stock(f5.to(dev()), lab.to(dev()))
+    assert stock._classes.auto == 8
+    close(out, ref, rtol=P2P_RTOL)
+    close(out, loss_mod.SupConLoss(0.7, n_class=0)(f5.to(dev()), lab.to(dev())), rtol=1e-3)
+    close(loss_mod.LocalConLoss(0.7, 2)(f5.to(dev()), lab.to(dev())), O.local_con_loss(f5, lab, 0.7, 2), rtol=P2P_RTOL)
+    wild = lab * 37 - 5                                   # arbitrary integers: equality structure unchanged, 0 stays background?
+    wild[lab == 0] = 0
+    fresh = loss_mod.SupConLoss(0.7)
+    close(fresh(f5.to(dev()), wild.to(dev())), ref, rtol=P2P_RTOL)      # first call sees them -> general sweeps
+    assert fresh._classes.auto == 0
+    assert torch.isnan(stock(f5.to(dev()), wild.to(dev())))               # `stock` decided "analytic" earlier: guarded
 
 
 def test_large_one_row_set_problems_take_the_sorted_path(api):
@@ -1081,11 +1287,12 @@ def test_large_one_row_set_problems_take_the_sorted_path(api):
     fo = f5.clone().requires_grad_(True)
     ref = O.supcon_loss(fo, lab, 0.7)
     ref.backward()
-    f = f5.to(dev()).requires_grad_(True)
-    out = loss_mod.SupConLoss(0.7)(f, lab.to(dev()))
-    out.backward()
-    close(out, ref, rtol=P2P_RTOL)
-    grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+    for n_class in (0, None):                    # 0: general sweeps on sorted rows; None: the stock signature (auto -> analytic)
+        f = f5.to(dev()).requires_grad_(True)
+        out = loss_mod.SupConLoss(0.7, n_class=n_class)(f, lab.to(dev()))
+        out.backward()
+        close(out, ref, rtol=P2P_RTOL)
+        grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
     n, d = 8192, 48
     feats = torch.randn(n, d, generator=gen)
     l1 = torch.randint(0, 6, (n,), generator=gen)
