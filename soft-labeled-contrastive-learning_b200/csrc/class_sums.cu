@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace slcl {
 namespace {
 
@@ -306,22 +308,24 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
 //
 // The v2 kernel above issues its loads from the warps that also do the arithmetic, 16 warps per SM at
 // 128 registers: with wide weight rows (soft labels x partitions) it is latency-bound at ~45 % of the HBM
-// roofline.  Here the three jobs are separate roles of one persistent CTA per SM:
-//   warp 0       TMA producer: one cp.async.bulk.tensor.3d box [128 pixels x CB channels] per stage into a
-//                ring of up to 12 stages (~200 KB in flight per SM whatever the channel count, completion on mbarriers)
-//   warps 1-8    weight builders: labels / soft probabilities / partition ids of the stage's 128 pixels ->
-//                sW[stage][column][pixel]; two warps per stage, four teams round-robin over the stages, and each
-//                warp fetches the raw inputs of its next two stages before it waits for their slots, so its
-//                global-load latency is covered by eight stage periods
+// roofline.  Here the jobs are separate roles of one persistent CTA per SM, and EVERY global read is issued by the
+// TMA unit into a shared-memory ring (up to 12 stages, ~200 KB in flight per SM, completion on mbarriers):
+//   warp 0       producer: per stage one cp.async.bulk.tensor.3d box [128 pixels x CB channels] of the feature map
+//                (x_full), plus the stage's RAW weight inputs (r_full): the [K x 128] box of soft probabilities (or the
+//                planar weight rows) as a second tensor map, the 128 int64 labels and the 128 int32 partition ids as
+//                1-D bulk copies
+//   NBW warps    weight builders (round 2: they no longer touch global memory, so no load latency to hide and half
+//                as many warps): raw inputs of the stage -> sW[stage][column][pixel]; two warps per stage, teams
+//                round-robin over the stages
 //   last warp    counter (channel block 0 only): sums the weights themselves -> the class-count column
-//   warps 9-24   consumers (as many as the channel count needs): warp w owns CPW channels; lane l owns pixels 4l..4l+3 of the stage; x and the weights
-//                come back from shared memory with conflict-free 128-bit loads; acc[CPW][KWT] in registers for
-//                the whole sweep; every channel has exactly one owner, so the block result needs no combine
+//   consumers    (as many as the channel count needs, <= NCW): warp w owns CPW channels; lane l owns pixels 4l..4l+3
+//                of the stage; x and the weights come back from shared memory with conflict-free LDS.128;
+//                acc[CPW][KWT] in registers for the whole sweep; every channel has exactly one owner, so the block
+//                result needs no combine.  CPW = 8 for 6..10 weight columns: each consumer re-reads the stage's
+//                KWT weight rows, so fat consumers halve the shared-memory traffic (LDS.128 per FMA: 16/256 vs 12/128).
 // Partials and the fp64 second stage are those of v2.
 // ---------------------------------------------------------------------------
 constexpr int kV3ConsumerWarps = 16;
-constexpr int v3_builder_warps(int ncw) { return ncw > 8 ? 4 : 8; }      // two per stage; fewer when the stages are long
-constexpr int kV3MaxBuilderWarps = 8;
 constexpr int kV3Px = 128;
 constexpr int kV3MaxStages = 12;      // ring depth is chosen per shape: as many stages as fit in ~200 KB, at most this
 
@@ -335,6 +339,26 @@ __device__ __forceinline__ void v3_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void v3_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(v3_smem_u32(bar)) : "memory");
 }
+#ifdef SLCL_V3_DEBUG
+// bring-up aid: bounded waits that say who is stuck (build with SLCL_EXTRA_NVCC_FLAGS=-DSLCL_V3_DEBUG)
+__device__ __forceinline__ void v3_mbar_wait_dbg(uint64_t* bar, uint32_t parity, int role, int slot, long long it) {
+  for (unsigned int spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(v3_smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) {
+      if ((threadIdx.x & 31) == 0)
+        printf("v3 stuck: role %d warp %d block (%d,%d) slot %d it %lld parity %u\n", role, threadIdx.x >> 5, blockIdx.x, blockIdx.y,
+               slot, it, parity);
+      __trap();
+    }
+  }
+}
+#define V3_WAIT(bar, parity, role, slot, it) v3_mbar_wait_dbg(bar, parity, role, slot, it)
+#else
+#define V3_WAIT(bar, parity, role, slot, it) v3_mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void v3_mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -347,12 +371,59 @@ __device__ __forceinline__ void v3_mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(v3_smem_u32(bar)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void v3_tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void v3_tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          v3_smem_u32(smem_dst)),
+          smem_dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(v3_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned source, destination and size)
+__device__ __forceinline__ void v3_bulk_load(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(v3_smem_u32(bar))
+               : "memory");
+}
+
+// Explicit shared-memory accesses by 32-bit shared address.  The ring is carved out of one dynamic buffer through
+// pointer arithmetic the compiler cannot prove to stay in the shared window: plain C++ dereferences compile to GENERIC
+// LD.E / ST.E (address translation, long-scoreboard latency) instead of LDS / STS -- the first thing ncu's source view
+// showed for this kernel in round 2 (soft x 2 partitions at C = 32: 0.665 -> 0.758 of the HBM roofline from this alone).
+__device__ __forceinline__ float4 v3_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// 4 consecutive floats as two packed pairs, and the packed FMA of Blackwell's FP32 pipe: {a.lo, a.hi} * {b.lo, b.hi} +
+// {c.lo, c.hi} in ONE issue slot (same FMA rate, half the instructions: the sweep is issue-limited, not FMA-limited).
+__device__ __forceinline__ void v3_lds2x64(uint32_t addr, unsigned long long& lo, unsigned long long& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+__device__ __forceinline__ void v3_ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float v3_pair_sum(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ float v3_lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int v3_lds32i(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ long long v3_lds64i(uint32_t addr) {
+  long long v;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void v3_sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // ring position of iteration `it`: slot = it % n, phase = (it / n) & 1, advanced without divisions
@@ -363,23 +434,28 @@ struct V3Pos {
   __device__ __forceinline__ void advance(int step) { slot += step; norm(); }
 };
 
-struct __align__(8) V3Bars { uint64_t x_full[kV3MaxStages], w_full[kV3MaxStages], empty[kV3MaxStages]; };
+struct __align__(8) V3Bars { uint64_t x_full[kV3MaxStages], r_full[kV3MaxStages], w_full[kV3MaxStages], empty[kV3MaxStages]; };
 
-// NCW = upper bound of the consumer warps (8 or 16): it sets the register budget (120 vs 72 per thread) and, with it,
-// how far ahead the weight builders prefetch (small channel counts mean short stages: two visits ahead).
-template <int KWT, int CPW, int NCW>
-__global__ void __launch_bounds__(32 * (2 + v3_builder_warps(NCW) + NCW), 1)
-class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs a) {
-  constexpr bool kDeep = NCW <= 8;
-  constexpr int kV3WeightWarps = v3_builder_warps(NCW);
+// per-stage shared memory: x [CB][128] fp32 | w [KWT][128] fp32 | raw [KWT][128] fp32 (soft: K probability rows; planar:
+// the weight rows; hard: the first 1 KB holds 128 int64 labels) | part [128] int32
+__host__ __device__ constexpr int v3_raw_rows(int kwt) { return kwt < 2 ? 2 : kwt; }
+
+// NCW = upper bound of the consumer warps (8 or 16), NBW = builder warps: together they set the register budget.
+template <int KWT, int CPW, int NCW, int NBW>
+__global__ void __launch_bounds__(32 * (3 + NBW + NCW), 1)
+class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_raw,
+                     const SumArgs a) {
   const int kV3Stages = a.n_stages;
   const int CB = a.n_cw * CPW;                                 // channels per block
   const int kStageBytes = CB * kV3Px * 4;
+  constexpr int kRawRows = v3_raw_rows(KWT);
   extern __shared__ __align__(128) uint8_t v3_smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v3_smem) + 127) & ~(uintptr_t)127);
-  float* sX = reinterpret_cast<float*>(base);                                   // [stages][CB][128]
-  float* sWt = reinterpret_cast<float*>(base + (size_t)kV3Stages * kStageBytes); // [stages][KWT][128]
-  V3Bars* bars = reinterpret_cast<V3Bars*>(sWt + (size_t)kV3Stages * KWT * kV3Px);
+  const uint32_t sX_u32 = v3_smem_u32(base);                                                // [stages][CB][128]
+  const uint32_t sWt_u32 = sX_u32 + (uint32_t)(kV3Stages * kStageBytes);                    // [stages][KWT][128]
+  const uint32_t sRaw_u32 = sWt_u32 + (uint32_t)(kV3Stages * KWT * kV3Px * 4);              // [stages][kRawRows][128]
+  const uint32_t sPart_u32 = sRaw_u32 + (uint32_t)(kV3Stages * kRawRows * kV3Px * 4);       // [stages][128]
+  V3Bars* bars = reinterpret_cast<V3Bars*>(base + (size_t)kV3Stages * ((size_t)kStageBytes + (size_t)(KWT + kRawRows + 1) * kV3Px * 4));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = (int)a.channels;
@@ -387,12 +463,15 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
   const int64_t tiles_per_image = (a.pixels + kV3Px - 1) / kV3Px;
   const int64_t n_tiles = a.batch * tiles_per_image;
   const int64_t n_iter = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const bool ragged = (a.pixels % kV3Px) != 0;                 // the last tile of an image is short
 
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0 && blockIdx.y == 0) *a.ticket = 0u;
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_feat)) : "memory");
+    if (a.mode != kHard) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_raw)) : "memory");
     for (int s = 0; s < kV3Stages; ++s) {
       v3_mbar_init(&bars->x_full[s], 1);
+      v3_mbar_init(&bars->r_full[s], 1);
       v3_mbar_init(&bars->w_full[s], 2);
       v3_mbar_init(&bars->empty[s], a.n_cw + (blockIdx.y == 0 ? 1 : 0));      // + the counter warp of channel block 0
     }
@@ -400,152 +479,165 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
   }
   __syncthreads();
 
+  // tile -> (image, first pixel) without a 64-bit division per stage: the tile index advances by gridDim.x
+  struct TilePos {
+    int64_t b; int64_t t, step, per;
+    __device__ TilePos(int64_t tile0, int64_t step_, int64_t per_) : step(step_), per(per_) { b = tile0 / per_; t = tile0 - b * per_; }
+    __device__ __forceinline__ void next() { t += step; if (t >= per) { const int64_t q = t / per; b += q; t -= q * per; } }
+    __device__ __forceinline__ int p0() const { return (int)(t * kV3Px); }
+  };
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    V3Pos pos(0, kV3Stages);
-    for (int64_t it = 0; it < n_iter; ++it, pos.advance(1)) {
-      const int s = pos.slot;
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int64_t b = tile / tiles_per_image;
-      const int p0 = (int)((tile - b * tiles_per_image) * kV3Px);
-      v3_mbar_wait(&bars->empty[s], (uint32_t)(pos.phase ^ 1));
-      if (lane == 0) {
+    // ===================== TMA producer 1: the feature tile =====================
+    if (lane == 0) {
+      V3Pos pos(0, kV3Stages);
+      TilePos tp(blockIdx.x, gridDim.x, tiles_per_image);
+      for (int64_t it = 0; it < n_iter; ++it, pos.advance(1), tp.next()) {
+        const int s = pos.slot;
+        V3_WAIT(&bars->empty[s], (uint32_t)(pos.phase ^ 1), 0, s, (long long)it);
         v3_mbar_expect_tx(&bars->x_full[s], kStageBytes);
-        v3_tma_load_3d(sX + (size_t)s * CB * kV3Px, &map_feat, &bars->x_full[s], p0, c_base, (int)b);
+        v3_tma_load_3d(sX_u32 + (uint32_t)(s * kStageBytes), &map_feat, &bars->x_full[s], tp.p0(), c_base, (int)tp.b);
       }
-      __syncwarp();
     }
-  } else if (warp <= kV3WeightWarps) {
-    // ===================== weight builders =====================
-    const int wv = warp - 1;
-    const int team = wv >> 1, hf = wv & 1;             // team -> stages team, team+4, ...; half of the 128 pixels
-    constexpr int kTeams = kV3WeightWarps / 2;
-    constexpr int kPl = 2;                              // pixels per lane: 64 pixels per warp
-    // raw inputs of kPl pixels (whatever the mode needs), fetched one visit (= 4 stages) ahead, or two with kDeep: under
-    // a saturated HBM the load latency exceeds four periods of a 16 KB stage
-    struct Raw {
-      float f[kPl][KWT > SLCL_MAX_CLASSES ? KWT : SLCL_MAX_CLASSES];
-      int part[kPl];
-      long long lab[kPl];
-    };
-    auto fetch = [&](Raw& r, int64_t it) {
-      if (it >= n_iter) return;
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int64_t b = tile / tiles_per_image;
-      const int64_t p0 = (tile - b * tiles_per_image) * kV3Px + hf * 64;
-#pragma unroll
-      for (int i = 0; i < kPl; ++i) {
-        const int64_t p = p0 + lane + 32 * i;
-        const bool ok = p < a.pixels;
-        const int64_t pix = b * a.pixels + p;
-        r.part[i] = (ok && a.part_id) ? a.part_id[pix] : 0;
-        r.lab[i] = -1;
-        if (a.mode == kPlanar) {
-          const int64_t n = a.batch * a.pixels;
-#pragma unroll
-          for (int j = 0; j < KWT; ++j) r.f[i][j] = (ok && j < a.n_cols) ? a.planar[(int64_t)j * n + pix] : 0.f;
-        } else if (a.mode == kHard) {
-          if (ok) r.lab[i] = a.labels[pix];
-        } else {
-#pragma unroll
-          for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
-            r.f[i][k] = (ok && k < a.n_class) ? a.probs[(b * a.n_class + k) * a.pixels + p] : 0.f;
-          if (!ok) r.part[i] = -1;                      // pixels past the image: all-zero weight row
-        }
+  } else if (warp == 1) {
+    // ===================== TMA producer 2: the raw weight inputs of the tile =====================
+    if (lane == 0) {
+      V3Pos pos(0, kV3Stages);
+      TilePos tp(blockIdx.x, gridDim.x, tiles_per_image);
+      for (int64_t it = 0; it < n_iter; ++it, pos.advance(1), tp.next()) {
+        const int s = pos.slot;
+        const int p0 = tp.p0();
+        const int64_t b = tp.b;
+        V3_WAIT(&bars->empty[s], (uint32_t)(pos.phase ^ 1), 5, s, (long long)it);
+        const int valid = min(kV3Px, (int)(a.pixels - p0));                  // pixels of this tile inside the image
+        uint32_t raw_bytes = 0;
+        if (a.mode == kSoft) raw_bytes = (uint32_t)(a.n_class * kV3Px * 4);   // full box (out-of-image pixels zero-filled)
+        else if (a.mode == kPlanar) raw_bytes = (uint32_t)(KWT * kV3Px * 4);
+        else raw_bytes = (uint32_t)valid * 8u;
+        if (a.part_id) raw_bytes += (uint32_t)valid * 4u;
+        v3_mbar_expect_tx(&bars->r_full[s], raw_bytes);
+        const uint32_t raw_dst = sRaw_u32 + (uint32_t)(s * kRawRows * kV3Px * 4);
+        if (a.mode == kSoft) v3_tma_load_3d(raw_dst, &map_raw, &bars->r_full[s], p0, 0, (int)b);
+        else if (a.mode == kPlanar) v3_tma_load_3d(raw_dst, &map_raw, &bars->r_full[s], p0, (int)b, 0);
+        else v3_bulk_load(raw_dst, a.labels + b * a.pixels + p0, (uint32_t)valid * 8u, &bars->r_full[s]);
+        if (a.part_id)
+          v3_bulk_load(sPart_u32 + (uint32_t)(s * kV3Px * 4), a.part_id + b * a.pixels + p0, (uint32_t)valid * 4u,
+                       &bars->r_full[s]);
       }
-    };
+    }
+  } else if (warp <= 1 + NBW) {
+    // ===================== weight builders (shared memory -> shared memory) =====================
+    // Two warps per stage (64 pixels each, 2 per lane); kTeams = NBW / 2 teams take the stages round-robin, so a team
+    // has kTeams stage periods for one build.  The ring depth is a MULTIPLE of kTeams (host side): a team then meets the
+    // same slots every round and sees every phase of their barriers.  (Round 1 let the depth be odd: a team met a slot
+    // only every second round, its parity wait could not tell "previous round" from "two rounds ago", and it could run
+    // ahead of the consumers.)
+    const int wv = warp - 2;
+    const int team = wv >> 1, hf = wv & 1;
+    constexpr int kTeams = NBW / 2;
+    constexpr int kPl = 2;                              // pixels per lane
+    const bool use_thr = a.threshold > 0.f && a.threshold < 1.f;
     V3Pos bpos(team, kV3Stages);
-    auto build = [&](const Raw& r) {               // builds the stage at bpos, then moves bpos to this team's next stage
+    TilePos tp(blockIdx.x + (int64_t)team * gridDim.x, (int64_t)kTeams * gridDim.x, tiles_per_image);
+    for (int64_t it = team; it < n_iter; it += kTeams, bpos.advance(kTeams), tp.next()) {
       const int s = bpos.slot;
-      v3_mbar_wait(&bars->empty[s], (uint32_t)(bpos.phase ^ 1));
-      float* dst = sWt + (size_t)s * KWT * kV3Px + hf * 64 + lane;
-      const bool use_thr = a.threshold > 0.f && a.threshold < 1.f;
+      const int valid = ragged ? min(kV3Px, (int)(a.pixels - tp.p0())) : kV3Px;
+      V3_WAIT(&bars->r_full[s], (uint32_t)bpos.phase, 1, s, (long long)it);     // raw inputs landed (and the slot's previous round is done)
+      const uint32_t raw = sRaw_u32 + (uint32_t)(s * kRawRows * kV3Px * 4);
+      const uint32_t prt = sPart_u32 + (uint32_t)(s * kV3Px * 4);
+      const uint32_t dst = sWt_u32 + (uint32_t)((s * KWT * kV3Px + hf * 64 + lane) * 4);
 #pragma unroll
       for (int i = 0; i < kPl; ++i) {
-        float* d = dst + 32 * i;
+        const int px = hf * 64 + lane + 32 * i;
+        const uint32_t d = dst + 32 * 4 * i;
         if (a.mode == kPlanar) {
 #pragma unroll
-          for (int q = 0; q < KWT; ++q) d[q * kV3Px] = r.f[i][q];
+          for (int q = 0; q < KWT; ++q) v3_sts32(d + q * kV3Px * 4, v3_lds32(raw + (uint32_t)((q * kV3Px + px) * 4)));
           continue;
         }
         // every column zero, then the (at most K) columns of the pixel's partition: no select chains, the column index
         // only ever appears in a shared-memory address
 #pragma unroll
-        for (int q = 0; q < KWT; ++q) d[q * kV3Px] = 0.f;
-        const bool part_ok = r.part[i] >= 0 && r.part[i] < a.n_part;
+        for (int q = 0; q < KWT; ++q) v3_sts32(d + q * kV3Px * 4, 0.f);
+        const bool inside = px < valid;
+        const int part = (a.part_id && inside) ? v3_lds32i(prt + px * 4) : 0;
+        const bool part_ok = inside && part >= 0 && part < a.n_part;
         if (a.mode == kHard) {
           // utils_.py:581 / :535
-          if (part_ok && r.lab[i] >= 0 && r.lab[i] < a.n_class) d[(r.part[i] * a.n_class + (int)r.lab[i]) * kV3Px] = 1.0f;
+          const long long lab = inside ? v3_lds64i(raw + px * 8) : -1;
+          if (part_ok && lab >= 0 && lab < a.n_class) v3_sts32(d + (uint32_t)((part * a.n_class + (int)lab) * kV3Px * 4), 1.0f);
         } else if (part_ok) {
           // soft probabilities: :517-519 (weighted) or :524-525 (arg-max one-hot); certainty :511-514
+          float pr[SLCL_MAX_CLASSES];
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k) pr[k] = (k < a.n_class) ? v3_lds32(raw + (uint32_t)((k * kV3Px + px) * 4)) : 0.f;
           float cert = 1.f;
           int arg = 0;
           if (use_thr || !a.weighted) {
             float best = -INFINITY;
 #pragma unroll
             for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
-              if (k < a.n_class && r.f[i][k] > best) { best = r.f[i][k]; arg = k; }
+              if (k < a.n_class && pr[k] > best) { best = pr[k]; arg = k; }
             if (use_thr) cert = best >= a.threshold ? 1.f : 0.f;
           }
-          float* dp = d + (size_t)r.part[i] * a.n_class * kV3Px;
+          const uint32_t dp = d + (uint32_t)(part * a.n_class * kV3Px * 4);
 #pragma unroll
           for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
-            if (k < a.n_class) dp[k * kV3Px] = a.weighted ? r.f[i][k] * cert : ((k == arg) ? cert : 0.f);
+            if (k < a.n_class) v3_sts32(dp + k * kV3Px * 4, a.weighted ? pr[k] * cert : ((k == arg) ? cert : 0.f));
         }
       }
       __syncwarp();
       if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
-      bpos.advance(kTeams);
-    };
-    if constexpr (kDeep) {
-      Raw ra, rb;
-      fetch(ra, team);
-      fetch(rb, team + kTeams);
-      for (int64_t it = team; it < n_iter; it += 2 * kTeams) {
-        build(ra);
-        fetch(ra, it + 2 * kTeams);                       // in flight while this warp waits for its next slots
-        if (it + kTeams < n_iter) {
-          build(rb);
-          fetch(rb, it + 3 * kTeams);
-        }
-      }
-    } else {
-      Raw ra;
-      fetch(ra, team);
-      for (int64_t it = team; it < n_iter; it += kTeams) {
-        build(ra);
-        fetch(ra, it + kTeams);
-      }
     }
   } else {
     // ===================== consumers =====================
-    const int cw = warp - 1 - kV3WeightWarps;
+    const int cw = warp - 2 - NBW;
     if (cw < a.n_cw) {
-    float acc[CPW][KWT];
+    // kPack: acc[j][q] = {sum over the lane's pixels 0,2 ; sum over its pixels 1,3} as one packed pair, accumulated with
+    // FFMA2 (half the issue slots).  Costs 2 registers per accumulator: only where the register budget allows it.
+    constexpr bool kPack = (NCW <= 8) && (CPW * KWT <= 40);
+    using AccT = typename std::conditional<kPack, unsigned long long, float>::type;
+    AccT acc[CPW][KWT];
 #pragma unroll
     for (int q = 0; q < KWT; ++q)
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) acc[j][q] = 0.f;
+      for (int j = 0; j < CPW; ++j) acc[j][q] = AccT(0);
     V3Pos cpos(0, kV3Stages);
     for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
       const int s = cpos.slot;
       const uint32_t par = (uint32_t)cpos.phase;
-      v3_mbar_wait(&bars->x_full[s], par);
-      v3_mbar_wait(&bars->w_full[s], par);
-      const float4* xs = reinterpret_cast<const float4*>(sX + ((size_t)s * CB + cw * CPW) * kV3Px) + lane;
-      const float4* ws = reinterpret_cast<const float4*>(sWt + (size_t)s * KWT * kV3Px) + lane;
-      float4 x[CPW];
+      V3_WAIT(&bars->x_full[s], par, 2, s, (long long)it);
+      const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + ((cw * CPW) * kV3Px + lane * 4) * 4);
+      const uint32_t ws = sWt_u32 + (uint32_t)((s * KWT * kV3Px + lane * 4) * 4);
+      if constexpr (kPack) {
+        unsigned long long x01[CPW], x23[CPW];
 #pragma unroll
-      for (int j = 0; j < CPW; ++j) x[j] = xs[j * (kV3Px / 4)];
+        for (int j = 0; j < CPW; ++j) v3_lds2x64(xs + j * kV3Px * 4, x01[j], x23[j]);
+        V3_WAIT(&bars->w_full[s], par, 3, s, (long long)it);
 #pragma unroll
-      for (int q = 0; q < KWT; ++q) {
-        const float4 w = ws[q * (kV3Px / 4)];
+        for (int q = 0; q < KWT; ++q) {
+          unsigned long long w01, w23;
+          v3_lds2x64(ws + q * kV3Px * 4, w01, w23);
 #pragma unroll
-        for (int j = 0; j < CPW; ++j) {
-          acc[j][q] = fmaf(w.x, x[j].x, acc[j][q]);
-          acc[j][q] = fmaf(w.y, x[j].y, acc[j][q]);
-          acc[j][q] = fmaf(w.z, x[j].z, acc[j][q]);
-          acc[j][q] = fmaf(w.w, x[j].w, acc[j][q]);
+          for (int j = 0; j < CPW; ++j) {
+            v3_ffma2(acc[j][q], w01, x01[j]);
+            v3_ffma2(acc[j][q], w23, x23[j]);
+          }
+        }
+      } else {
+        float4 x[CPW];
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) x[j] = v3_lds128(xs + j * kV3Px * 4);
+        V3_WAIT(&bars->w_full[s], par, 3, s, (long long)it);
+#pragma unroll
+        for (int q = 0; q < KWT; ++q) {
+          const float4 w = v3_lds128(ws + q * kV3Px * 4);
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) {
+            acc[j][q] = fmaf(w.x, x[j].x, acc[j][q]);
+            acc[j][q] = fmaf(w.y, x[j].y, acc[j][q]);
+            acc[j][q] = fmaf(w.z, x[j].z, acc[j][q]);
+            acc[j][q] = fmaf(w.w, x[j].w, acc[j][q]);
+          }
         }
       }
       __syncwarp();
@@ -557,7 +649,9 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
       const int c = c_base + cw * CPW + j;
 #pragma unroll
       for (int q = 0; q < KWT; ++q) {
-        const float r = warp_sum(acc[j][q]);
+        float t;
+        if constexpr (kPack) t = v3_pair_sum(acc[j][q]); else t = acc[j][q];
+        const float r = warp_sum(t);
         if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
       }
     }
@@ -570,11 +664,11 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const SumArgs
       V3Pos cpos(0, kV3Stages);
       for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
         const int s = cpos.slot;
-        v3_mbar_wait(&bars->w_full[s], (uint32_t)cpos.phase);
-        const float4* ws = reinterpret_cast<const float4*>(sWt + (size_t)s * KWT * kV3Px) + lane;
+        V3_WAIT(&bars->w_full[s], (uint32_t)cpos.phase, 4, s, (long long)it);
+        const uint32_t ws = sWt_u32 + (uint32_t)((s * KWT * kV3Px + lane * 4) * 4);
 #pragma unroll
         for (int q = 0; q < KWT; ++q) {
-          const float4 w = ws[q * (kV3Px / 4)];
+          const float4 w = v3_lds128(ws + q * kV3Px * 4);
           cacc[q] += (w.x + w.y) + (w.z + w.w);
         }
         __syncwarp();
@@ -898,7 +992,18 @@ V3EncodeFn v3_encode_fn() {
   return fn;
 }
 
-struct V3Plan { bool ok; int kwt, cpw, n_cw; dim3 grid; };
+struct V3Plan { bool ok; int kwt, cpw, n_cw, nbw, ncw_max; dim3 grid; };
+
+// Register-tile shape per weight-column count (acc[CPW][KWT] lives in registers for the whole sweep):
+//   KWT <= 10 : CPW 4, up to 16 consumer warps (64 channels per block)
+//   KWT 12,16 : CPW 4, up to 8 consumer warps (acc[4][16] = 64 registers)
+// (CPW 8 with half as many consumer warps was measured in round 2: fewer re-reads of the weight rows but one warp per
+// scheduler cannot hide its own LDS latency -- 0.90 -> 0.80 at C = 128, KWT = 10 -- so it is not used.)
+constexpr int v3_cpw(int kwt) { return 4; }
+constexpr int v3_ncw(int kwt) { return kwt <= 10 ? 16 : 8; }
+// builder warps: 4 teams (8 warps) when the stages are short and the accumulators few; 2 teams otherwise (long stages,
+// or wide weight rows whose packed accumulators need the registers)
+constexpr int v3_nbw(int ncw, int kwt) { return (ncw > 8 || kwt >= 6) ? 4 : 8; }
 
 V3Plan plan_v3(const SumArgs& a, bool vec4) {
   V3Plan p{};
@@ -908,11 +1013,12 @@ V3Plan plan_v3(const SumArgs& a, bool vec4) {
   p.kwt = pick_kwt(a.n_cols);
   if (p.kwt < 0) return p;
   const int C = (int)a.channels;
-  // Few, fat consumer warps: every consumer re-reads the stage's weights from shared memory, so the weight traffic per
-  // stage is n_cw x KWT x 512 B -- with 4 channels per warp it stays below the feature traffic's share of the LSU.
-  p.cpw = p.kwt > 10 ? 2 : 4;                       // 72-96 registers per thread: keep acc[CPW][KWT] <= 40
+  p.cpw = v3_cpw(p.kwt);
+  p.ncw_max = v3_ncw(p.kwt);
   p.n_cw = ceil_div(C, p.cpw);
-  if (p.n_cw > kV3ConsumerWarps) p.n_cw = kV3ConsumerWarps;
+  if (p.n_cw > p.ncw_max) p.n_cw = p.ncw_max;
+  if (p.n_cw <= 8) p.ncw_max = 8;
+  p.nbw = v3_nbw(p.ncw_max, p.kwt);
   const int cb = p.n_cw * p.cpw;
   const int gy = ceil_div(C, cb);
   const int64_t n_tiles = a.batch * ceil_div<int64_t>(a.pixels, kV3Px);
@@ -925,49 +1031,80 @@ V3Plan plan_v3(const SumArgs& a, bool vec4) {
   return p;
 }
 
-size_t v3_stage_bytes(int kwt, int cpw, int n_cw) { return (size_t)(n_cw * cpw + kwt) * kV3Px * 4; }
-int v3_stages(int kwt, int cpw, int n_cw) {          // as deep as ~200 KB allow: small-C stages are short, the ring must be long
+size_t v3_stage_bytes(int kwt, int cpw, int n_cw) { return (size_t)(n_cw * cpw + kwt + v3_raw_rows(kwt) + 1) * kV3Px * 4; }
+// as deep as ~200 KB allow (small-C stages are short, the ring must be long), rounded down to a multiple of the
+// builder teams so that every team sees every phase of the slots it works on
+int v3_stages(int kwt, int cpw, int n_cw, int teams) {
   int n = (int)((200 * 1024) / v3_stage_bytes(kwt, cpw, n_cw));
-  return n < 2 ? 2 : (n > kV3MaxStages ? kV3MaxStages : n);
+  if (n > kV3MaxStages) n = kV3MaxStages;
+  n = n / teams * teams;
+  return n < teams ? teams : n;
 }
-size_t v3_smem_bytes(int kwt, int cpw, int n_cw) {
-  return 128 + (size_t)v3_stages(kwt, cpw, n_cw) * v3_stage_bytes(kwt, cpw, n_cw) + sizeof(V3Bars) + 64;
+size_t v3_smem_bytes(int kwt, int cpw, int n_cw, int teams) {
+  return 128 + (size_t)v3_stages(kwt, cpw, n_cw, teams) * v3_stage_bytes(kwt, cpw, n_cw) + sizeof(V3Bars) + 64;
 }
 
-template <int KWT, int CPW, int NCW>
-int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
-  ensure_context_on_this_thread();
+int v3_encode(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3], const cuuint64_t (&strides)[2],
+              const cuuint32_t (&box)[3]) {
   V3EncodeFn fn = v3_encode_fn();
   if (!fn) return SLCL_ERR_CUDA;
-  CUtensorMap map;
-  cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.channels, (cuuint64_t)a.batch};
-  cuuint64_t strides[2] = {(cuuint64_t)a.sc * 4, (cuuint64_t)a.sb * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)(p.n_cw * CPW), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.feat), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(class sums)"); return SLCL_ERR_CUDA; }
-  const size_t smem = v3_smem_bytes(KWT, CPW, p.n_cw);
+  return SLCL_OK;
+}
+
+template <int KWT, int CPW, int NCW, int NBW>
+int launch_v3(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
+  ensure_context_on_this_thread();
+  CUtensorMap map, map_raw;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.channels, (cuuint64_t)a.batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.sc * 4, (cuuint64_t)a.sb * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)(p.n_cw * CPW), 1};
+    int st = v3_encode(&map, a.feat, dims, strides, box);
+    if (st != SLCL_OK) return st;
+  }
+  map_raw = map;
+  if (a.mode == kSoft) {              // probs [B, K, HW]: box = all K probability rows of 128 pixels of one image
+    const cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.n_class, (cuuint64_t)a.batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.pixels * 4, (cuuint64_t)a.pixels * a.n_class * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)a.n_class, 1};
+    int st = v3_encode(&map_raw, a.probs, dims, strides, box);
+    if (st != SLCL_OK) return st;
+  } else if (a.mode == kPlanar) {     // planar weights [cols][B*HW] seen as {HW, B, cols}: rows beyond n_cols read as zero
+    const cuuint64_t dims[3] = {(cuuint64_t)a.pixels, (cuuint64_t)a.batch, (cuuint64_t)a.n_cols};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.pixels * 4, (cuuint64_t)a.pixels * a.batch * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kV3Px, 1, (cuuint32_t)KWT};
+    int st = v3_encode(&map_raw, a.planar, dims, strides, box);
+    if (st != SLCL_OK) return st;
+  }
+  const size_t smem = v3_smem_bytes(KWT, CPW, p.n_cw, NBW / 2);
   static bool attr_set_dev[64] = {};          // function attributes are per device
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(class_sums_v3_kernel<KWT, CPW, NCW, NBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          220 * 1024);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(class_sums_v3_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
   SumArgs av = a;
   av.n_cw = p.n_cw;
-  av.n_stages = v3_stages(KWT, CPW, p.n_cw);
-  class_sums_v3_kernel<KWT, CPW, NCW><<<p.grid, 32 * (2 + v3_builder_warps(NCW) + p.n_cw), smem, stream>>>(map, av);
+  av.n_stages = v3_stages(KWT, CPW, p.n_cw, NBW / 2);
+  if (smem > 220 * 1024) return SLCL_ERR_UNSUPPORTED;
+  class_sums_v3_kernel<KWT, CPW, NCW, NBW><<<p.grid, 32 * (3 + NBW + p.n_cw), smem, stream>>>(map, map_raw, av);
   return SLCL_OK;
 }
 
 template <int KWT>
 int launch_v3_cpw(const SumArgs& a, const V3Plan& p, cudaStream_t stream) {
-  if constexpr (KWT <= 10) return p.n_cw <= 8 ? launch_v3<KWT, 4, 8>(a, p, stream) : launch_v3<KWT, 4, 16>(a, p, stream);
-  else return p.n_cw <= 8 ? launch_v3<KWT, 2, 8>(a, p, stream) : launch_v3<KWT, 2, 16>(a, p, stream);
+  constexpr int CPW = v3_cpw(KWT);
+  if constexpr (v3_ncw(KWT) > 8) {
+    if (p.n_cw > 8) return launch_v3<KWT, CPW, 16, v3_nbw(16, KWT)>(a, p, stream);
+  }
+  return launch_v3<KWT, CPW, 8, v3_nbw(8, KWT)>(a, p, stream);
 }
 
 void launch_reduce(const SumArgs& a, int n_blocks, int kwt, double* sums, const slcl_peer_t* peer, const FinArgs& fin,
