@@ -1061,30 +1061,6 @@ def p2p_kernels(dev, gen):
     out["cfg3 through the public API: sampled_supcon_loss (draw + compaction + gather + sweeps + scatter), fwd+bwd, eager"] = {
         "ms": ms, "algorithmic_flop": 8.0 * A * M * d, "achieved_TFLOPs": 8.0 * A * M * d / (ms * 1e-3) / 1e12,
         "frac_of_bf16_peak": 8.0 * A * M * d / (ms * 1e-3) / 1e12 / tf_peak, "rows_per_s": (A + M) / (ms * 1e-3)}
-    try:        # the same public-API step captured once as a CUDA graph (possible because nothing in it synchronises)
-        fmap_g = fmap.detach().clone().requires_grad_(True)
-
-        def api_step_g():
-            loss_s = sampled_supcon_loss(fmap_g, lmap, A, M, 5, temperature=T)
-            loss_s.backward()
-            fmap_g.grad = None
-            return loss_s.detach()
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            api_step_g()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        g_api = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_api):
-            keep_api = api_step_g()          # noqa: F841
-        ms = timed(g_api.replay, iters=10)
-        out["cfg3 through the public API: the same sampled_supcon_loss step replayed as one CUDA graph"] = {
-            "ms": ms, "algorithmic_flop": 8.0 * A * M * d, "achieved_TFLOPs": 8.0 * A * M * d / (ms * 1e-3) / 1e12,
-            "frac_of_bf16_peak": 8.0 * A * M * d / (ms * 1e-3) / 1e12 / tf_peak, "rows_per_s": (A + M) / (ms * 1e-3)}
-        del g_api, keep_api, fmap_g
-    except Exception as exc:  # noqa: BLE001
-        print(f"[bench] sampled_supcon_loss: graph capture unavailable ({exc!r})", file=sys.stderr)
     del fmap, lmap
     # BlockConLoss at the reference's documented shape (1, 2, 32, 224, 224), 32 x 32 tiles: 49 tiles of 2048 rows as ONE
     # block-diagonal problem (the reference and the per-tile loop launch 49 separate SupCon problems)

@@ -930,6 +930,167 @@ __global__ void __launch_bounds__(kThreads) centroid_bwd_kernel(const CenBwdArgs
   }
 }
 
+// ---------------------------------------------------------------------------
+// centroid backward, round-2 form for 128-bit maps (HW % 4 == 0): same arithmetic as centroid_bwd_kernel with
+//   * the weight rows and the d-probs gather placed through a THREAD-PRIVATE shared scratch [KWT][threads] float4
+//     (a dynamic column index becomes a shared-memory address; the round-1 kernel resolved it with KWT x K predicated
+//     moves per pixel in the prologue and again in the epilogue -- 19 % + 6 % of its stall samples in ncu's source view),
+//   * packed FFMA2 arithmetic over pixel pairs: per channel 32 packed FMAs instead of 64 scalar ones; gc sits in shared
+//     memory pre-duplicated as {g, g} pairs so the broadcast load already has the packed form.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void cb_sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float cb_lds32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void cb_lds2x64(uint32_t addr, unsigned long long& lo, unsigned long long& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+__device__ __forceinline__ void cb_ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long cb_fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float2 cb_unpack(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+template <int KWT, bool HAS_DP>
+__global__ void __launch_bounds__(kThreads, 2) centroid_bwd4_kernel(const CenBwdArgs a) {
+  constexpr int KP = (KWT + 1) / 2 * 2;               // gc pairs are fetched two columns (one LDS.128) at a time
+  extern __shared__ __align__(16) float cb_smem[];    // sG2 [C][KP] {g, g} pairs | scratch [KWT][threads] float4 | x ring
+  const int C = (int)a.s.channels;
+  const uint32_t sG2 = cb_smem_u32(cb_smem);
+  const uint32_t scratch = sG2 + (uint32_t)(C * KP * 8) + threadIdx.x * 16;                   // + j * kThreads * 16
+  const uint32_t ring = sG2 + (uint32_t)(C * KP * 8) + (uint32_t)(KWT * kThreads * 16) + threadIdx.x * 16;   // + slot * kThreads * 16
+  for (int idx = threadIdx.x; idx < C * KP; idx += kThreads) {
+    const int c = idx / KP, j = idx % KP;
+    const float g = (j < a.s.n_cols) ? a.gc[(int64_t)j * C + c] : 0.f;
+    reinterpret_cast<float2*>(cb_smem)[idx] = make_float2(g, g);
+  }
+  __syncthreads();
+  const int64_t gidx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t groups = a.s.pixels / 4;
+  if (gidx >= a.s.batch * groups) return;
+  const int64_t b = gidx / groups;
+  const int64_t p = (gidx - b * groups) * 4;
+  const int64_t pix = b * a.s.pixels + p;
+  const float* src = a.s.feat + b * a.s.sb + p * a.s.sp;
+  float* dst = a.dfeat + b * a.s.sb + p * a.s.sp;
+  const int K = a.s.n_class;
+
+  // x loads (needed for d probs only) go through a per-thread cp.async ring, kCenRing channels deep
+  auto ring_fetch = [&](int c) {
+    if (c < C) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)((c % kCenRing) * kThreads * 16)),
+                            "l"(src + (int64_t)c * a.s.sc) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");          // one group per channel, empty past the end
+  };
+  if constexpr (HAS_DP) {
+    for (int c = 0; c < kCenRing; ++c) ring_fetch(c);
+  }
+
+  // ---- weight rows of the 4 pixels -> scratch[column][pixel] (zero, then the <= K columns of each pixel's partition)
+  int base[4];                                        // first column of the pixel's partition, or -1
+  float cert[4];
+  {
+    int part[4] = {0, 0, 0, 0};
+    if (a.s.part_id) { const int4 t = *reinterpret_cast<const int4*>(a.s.part_id + pix); part[0] = t.x; part[1] = t.y; part[2] = t.z; part[3] = t.w; }
+#pragma unroll
+    for (int j = 0; j < KWT; ++j) cb_sts128(scratch + (uint32_t)(j * kThreads * 16), make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { base[v] = (part[v] >= 0 && part[v] < a.s.n_part) ? part[v] * K : -1; cert[v] = base[v] >= 0 ? 1.f : 0.f; }
+    if (a.s.mode == kHard) {
+      const longlong2* lp = reinterpret_cast<const longlong2*>(a.s.labels + pix);
+      const longlong2 l0 = lp[0], l1 = lp[1];
+      const long long lab[4] = {l0.x, l0.y, l1.x, l1.y};
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (base[v] >= 0 && lab[v] >= 0 && lab[v] < K) cb_sts32(scratch + (uint32_t)((base[v] + (int)lab[v]) * kThreads * 16 + v * 4), 1.0f);
+    } else {
+      const bool use_thr = a.s.threshold > 0.f && a.s.threshold < 1.f;
+      float pr[SLCL_MAX_CLASSES][4];
+#pragma unroll
+      for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+        if (k < K) { const float4 t = *reinterpret_cast<const float4*>(a.s.probs + (b * K + k) * a.s.pixels + p); pr[k][0] = t.x; pr[k][1] = t.y; pr[k][2] = t.z; pr[k][3] = t.w; }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        int arg = 0;
+        if (use_thr || !a.s.weighted) {
+          float best = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+            if (k < K && pr[k][v] > best) { best = pr[k][v]; arg = k; }
+          if (use_thr && !(best >= a.s.threshold)) cert[v] = 0.f;
+        }
+        if (base[v] >= 0) {
+#pragma unroll
+          for (int k = 0; k < SLCL_MAX_CLASSES; ++k)
+            if (k < K) cb_sts32(scratch + (uint32_t)((base[v] + k) * kThreads * 16 + v * 4),
+                                a.s.weighted ? pr[k][v] * cert[v] : ((k == arg) ? cert[v] : 0.f));
+        }
+      }
+    }
+  }
+  unsigned long long w01[KWT], w23[KWT];
+#pragma unroll
+  for (int j = 0; j < KWT; ++j) cb_lds2x64(scratch + (uint32_t)(j * kThreads * 16), w01[j], w23[j]);
+
+  unsigned long long d01[HAS_DP ? KWT : 1], d23[HAS_DP ? KWT : 1];
+#pragma unroll
+  for (int j = 0; j < (HAS_DP ? KWT : 1); ++j) { d01[j] = 0ull; d23[j] = 0ull; }
+
+  for (int c = 0; c < C; ++c) {
+    unsigned long long x01 = 0ull, x23 = 0ull;
+    if constexpr (HAS_DP) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kCenRing - 1) : "memory");
+      cb_lds2x64(ring + (uint32_t)((c % kCenRing) * kThreads * 16), x01, x23);
+      ring_fetch(c + kCenRing);
+    }
+    unsigned long long o01 = 0ull, o23 = 0ull;
+    const uint32_t grow = sG2 + (uint32_t)(c * KP * 8);
+#pragma unroll
+    for (int j = 0; j < KWT; j += 2) {
+      unsigned long long g0, g1;                                  // {g_j, g_j}, {g_j+1, g_j+1}: warp-wide broadcast
+      cb_lds2x64(grow + j * 8, g0, g1);
+      cb_ffma2(o01, w01[j], g0);
+      cb_ffma2(o23, w23[j], g0);
+      if constexpr (HAS_DP) { cb_ffma2(d01[j], x01, g0); cb_ffma2(d23[j], x23, g0); }
+      if (j + 1 < KWT) {
+        cb_ffma2(o01, w01[j + 1], g1);
+        cb_ffma2(o23, w23[j + 1], g1);
+        if constexpr (HAS_DP) { cb_ffma2(d01[j + 1], x01, g1); cb_ffma2(d23[j + 1], x23, g1); }
+      }
+    }
+    const float2 oa = cb_unpack(o01), ob = cb_unpack(o23);
+    st_stream4(dst + (int64_t)c * a.s.sc, make_float4(oa.x, oa.y, ob.x, ob.y));
+  }
+  if constexpr (HAS_DP) {
+    // d probs[b,k,p] = cert * (x . gc_j - mu_j . gc_j), j = part*K + k: park the KWT dot rows in the scratch, gather by address
+#pragma unroll
+    for (int j = 0; j < KWT; ++j) {
+      const float m = (j < a.s.n_cols) ? a.mu_dot_gc[j] : 0.f;
+      const float2 da = cb_unpack(d01[j]), db = cb_unpack(d23[j]);
+      cb_sts128(scratch + (uint32_t)(j * kThreads * 16), make_float4(da.x - m, da.y - m, db.x - m, db.y - m));
+    }
+#pragma unroll
+    for (int k = 0; k < SLCL_MAX_CLASSES; ++k) {
+      if (k < K) {
+        float o[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          o[v] = base[v] >= 0 ? cert[v] * cb_lds32(scratch + (uint32_t)((base[v] + k) * kThreads * 16 + v * 4)) : 0.f;
+        st_stream4(a.dprobs + (b * K + k) * a.s.pixels + p, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+}
+
 // ------------------------------ host side ----------------------------------
 int pick_kwt(int n_cols) {
   static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
@@ -1331,7 +1492,10 @@ extern "C" int slcl_centroid_bwd(const float* feat, int64_t batch, int64_t chann
   const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id, dfeat, dprobs});
   const int vec = vec4 ? 4 : 1;
   size_t smem = (size_t)channels * ((kwt + 3) / 4 * 4) * sizeof(float);
-  if (dprobs && vec4) smem = align_up(smem, 16) + (size_t)kCenRing * kThreads * 16;      // + the cp.async ring
+  if (vec4) {      // centroid_bwd4_kernel: {g, g} pairs [C][KP] + per-thread scratch [KWT][threads] float4 (+ the cp.async ring)
+    smem = (size_t)channels * ((kwt + 1) / 2 * 2) * 8 + (size_t)kwt * kThreads * 16;
+    if (dprobs) smem += (size_t)kCenRing * kThreads * 16;
+  }
   if (smem > 200 * 1024) return SLCL_ERR_UNSUPPORTED;
   const int blocks = (int)ceil_div<int64_t>(batch * pixels / vec, kThreads);
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1346,8 +1510,8 @@ extern "C" int slcl_centroid_bwd(const float* feat, int64_t batch, int64_t chann
       return SLCL_OK;                                                                                         \
     };                                                                                                        \
     int st;                                                                                                   \
-    if (dprobs) st = vec4 ? launch(centroid_bwd_kernel<KW_, 4, true>) : launch(centroid_bwd_kernel<KW_, 1, true>);    \
-    else st = vec4 ? launch(centroid_bwd_kernel<KW_, 4, false>) : launch(centroid_bwd_kernel<KW_, 1, false>);         \
+    if (dprobs) st = vec4 ? launch(centroid_bwd4_kernel<KW_, true>) : launch(centroid_bwd_kernel<KW_, 1, true>);      \
+    else st = vec4 ? launch(centroid_bwd4_kernel<KW_, false>) : launch(centroid_bwd_kernel<KW_, 1, false>);           \
     if (st != SLCL_OK) return st;                                                                             \
   } break;
   switch (kwt) {

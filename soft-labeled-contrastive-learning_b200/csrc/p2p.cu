@@ -306,6 +306,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // kMetaSlots-deep ring of its own (the epilogue reads it after the tile's smem stage has already been
 // handed back), so the epilogue warps never issue a global load.  The caller pads the metadata arrays
 // to a multiple of 64 entries; pad entries carry id INT_MIN (masked) / shift kShiftOff.
+// Column metadata reads by 32-bit SHARED address: the carve-up below goes through generic pointer arithmetic, and a plain
+// C++ dereference of it compiles to a generic LD.E (address translation + long scoreboard) instead of LDS -- found in
+// round 2 with cuobjdump (64-72 LD.E per epilogue instantiation, most of them inside the per-tile loop).
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_float4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 constexpr int kMetaSlots = 4;
 struct __align__(128) ColMeta {
   float4 stat[BN];      // kGenCols: {shift*log2e, alpha, beta, -};  kAnaCols: the first 64 floats = column shifts
@@ -560,7 +573,8 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const int ms = t % kMetaSlots;
-      const ColMeta& cmeta = sMeta[ms];
+      const uint32_t cstat_u32 = (uint32_t)__cvta_generic_to_shared(sMeta + ms);               // ColMeta::stat [BN] float4
+      const uint32_t cmeta_u32 = cstat_u32 + (uint32_t)(BN * sizeof(float4));                    // ColMeta::meta [BN] int2
       if (MT::kColRing) mbar_wait_t(&bars->m_full[ms], (t / kMetaSlots) & 1, w0);
       mbar_wait_t(&bars->s_full[buf], (t >> 1) & 1, w1);
       tc_fence_after();
@@ -578,7 +592,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       // general modes with self maps: is this warp's half tile label-uniform?  (one shared load, a shuffle and a vote)
       bool gen_fast = false, gen_same = false;
       if ((MODE == kGenFwd || MODE == kGenRows || MODE == kGenCols) && !a.self_by_id) {
-        const int my_col_label = cmeta.meta[half * 32 + lane].x;
+        const int my_col_label = lds_int2(cmeta_u32 + (uint32_t)((half * 32 + lane) * 8)).x;
         const int tile_label = __shfl_sync(0xffffffffu, my_col_label, 0);
         gen_fast = __all_sync(0xffffffffu, my_col_label == tile_label);
         gen_same = rm.x == tile_label;
@@ -595,10 +609,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           if (MODE == kAnaFwdU) packed[jj >> 1] = pack_bf16x2(e0, e1);
         }
       } else if (MODE == kAnaCols) {
-        const float4* cs4 = reinterpret_cast<const float4*>(cmeta.stat) + half * 8;
+        const uint32_t cs4 = cstat_u32 + (uint32_t)(half * 8 * 16);
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
-          const float4 sh = cs4[jj >> 2];
+          const float4 sh = lds_float4(cs4 + (uint32_t)((jj >> 2) * 16));
           const float e0 = ex2_approx(fmaf(__uint_as_float(v[jj]), a.scale_log2, -sh.x));
           const float e1 = ex2_approx(fmaf(__uint_as_float(v[jj + 1]), a.scale_log2, -sh.y));
           const float e2 = ex2_approx(fmaf(__uint_as_float(v[jj + 2]), a.scale_log2, -sh.z));
@@ -621,7 +635,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           const int rid = a.self_by_id ? rm.y : INT_MIN + 2;      // self maps given: never equal to a column id
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const int2 cm = cmeta.meta[half * 32 + jj];
+            const int2 cm = lds_int2(cmeta_u32 + (uint32_t)((half * 32 + jj) * 8));
             const float s = __uint_as_float(v[jj]);
             const float e = ex2_approx(fmaf(s, a.scale_log2, -rs.x));
             // predicated adds spelled out in PTX: 2 compares + 3 predicated FADDs, no selects, no branches
@@ -646,7 +660,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           for (int u = 0; u < 2; ++u) {
             float sh = rs.x, al = rs.y, be = rs.z;
             if (MODE == kGenCols) {
-              const float4 st = cmeta.stat[half * 32 + jj + u];
+              const float4 st = lds_float4(cstat_u32 + (uint32_t)((half * 32 + jj + u) * 16));
               sh = st.x; al = st.y; be = st.z;
             }
             const float e = ex2_approx(fmaf(__uint_as_float(v[jj + u]), a.scale_log2, -sh));
@@ -663,10 +677,10 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
           float g2[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int2 cm = cmeta.meta[half * 32 + jj + u];
+            const int2 cm = lds_int2(cmeta_u32 + (uint32_t)((half * 32 + jj + u) * 8));
             float sh = rs.x, al = rs.y, be = rs.z;
             if (MODE == kGenCols) {
-              const float4 st = cmeta.stat[half * 32 + jj + u];
+              const float4 st = lds_float4(cstat_u32 + (uint32_t)((half * 32 + jj + u) * 16));
               sh = st.x; al = st.y; be = st.z;
             }
             const float s = __uint_as_float(v[jj + u]);
