@@ -44,6 +44,29 @@ __device__ __forceinline__ float  ld_stream1(const float* p) { return __ldcs(p);
 __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st_stream1(float* p, float v) { __stcs(p, v); }
 
+// L2 residency hints.  A feature map that fits in the 126 MB L2 is read twice by consecutive kernels of one step
+// (class sums -> loss forward -> loss backward): the first reader loads it with evict_last so the later readers hit L2
+// instead of HBM; maps larger than L2 keep the evict_first streaming behaviour.  One code path: the policy is a
+// run-time 64-bit operand of ld.global.L2::cache_hint.
+constexpr size_t kL2KeepBytes = 104u << 20;       // largest map we try to keep resident (cfg4 per-GPU map: 98 MiB)
+__device__ __forceinline__ uint64_t l2_policy(bool keep) {
+  uint64_t pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_policy4(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_policy1(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // Programmatic dependent launch: a kernel launched with launch_pdl() may start while the kernel in front of it in the
 // stream is still running; it signals its own dependents right away (pdl_trigger) and waits for the kernel in front to
 // complete (pdl_wait) BEFORE it touches global memory.  Launch latency and block scheduling overlap the predecessor's tail.

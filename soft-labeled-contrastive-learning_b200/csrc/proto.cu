@@ -18,6 +18,7 @@
 #include "peer.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace slcl {
 namespace {
@@ -60,6 +61,7 @@ struct ProtoArgs {
   float* out_sel;
   float sel_threshold;
   int fused_target;           // forward derives label/sel itself (generate_pseudo_label fused in) and writes them out
+  int keep_l2;                // the map fits in L2: load it with evict_last so the backward's read of F hits L2
   MarginConst mc;
 };
 
@@ -71,6 +73,9 @@ template <> struct Vec<4> {
   static __device__ __forceinline__ void load_keep(const float* p, float (&v)[4]) {
     float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  static __device__ __forceinline__ void load_pol(const float* p, float (&v)[4], uint64_t pol) {
+    float4 t = ld_policy4(p, pol); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
   }
@@ -81,6 +86,7 @@ template <> struct Vec<4> {
 template <> struct Vec<1> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = ld_stream1(p); }
   static __device__ __forceinline__ void load_keep(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void load_pol(const float* p, float (&v)[1], uint64_t pol) { v[0] = ld_policy1(p, pol); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { st_stream1(p, v[0]); }
   static __device__ __forceinline__ void store_keep(float* p, const float (&v)[1]) { *p = v[0]; }
 };
@@ -126,7 +132,7 @@ __device__ __forceinline__ bool locate(const ProtoArgs& a, int64_t& pix, int64_t
 // Accumulate squared norm and K dot products over all channels.
 template <int K, int VEC>
 __device__ __forceinline__ void channel_pass(const float* base, int64_t sc, int C, const float* sC,
-                                             float (&nrm)[VEC], float (&dot)[K][VEC]) {
+                                             float (&nrm)[VEC], float (&dot)[K][VEC], uint64_t pol) {
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     nrm[v] = 0.f;
@@ -137,7 +143,7 @@ __device__ __forceinline__ void channel_pass(const float* base, int64_t sc, int 
   for (; c + kUnroll <= C; c += kUnroll) {
     float x[kUnroll][VEC];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) Vec<VEC>::load(base + (int64_t)(c + u) * sc, x[u]);
+    for (int u = 0; u < kUnroll; ++u) Vec<VEC>::load_pol(base + (int64_t)(c + u) * sc, x[u], pol);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       float ck[K];
@@ -152,7 +158,7 @@ __device__ __forceinline__ void channel_pass(const float* base, int64_t sc, int 
   }
   for (; c < C; ++c) {
     float x[VEC];
-    Vec<VEC>::load(base + (int64_t)c * sc, x);
+    Vec<VEC>::load_pol(base + (int64_t)c * sc, x, pol);
     float ck[K];
     centre_row<K>(sC, c, ck);
 #pragma unroll
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
   double loss_acc = 0.0, sel_acc = 0.0;
   if (active) {
     float nrm[VEC], dot[K][VEC];
-    channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot);
+    channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot, l2_policy(a.keep_l2 != 0));
 
     float selv[VEC];
     if (a.sel != nullptr) Vec<VEC>::load_keep(a.sel + pix, selv);
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) pseudo_label_kernel(const ProtoArgs 
   int64_t pix, off;
   if (!locate<VEC>(a, pix, off)) return;
   float nrm[VEC], dot[K][VEC];
-  channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot);
+  channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot, l2_policy(a.keep_l2 != 0));
   long long lab[VEC];
   float selv[VEC];
 #pragma unroll
@@ -580,6 +586,8 @@ ProtoArgs base_args(const float* feat, const slcl_map_t* m, const float* cstate)
   a.sb = m->stride_b; a.sc = m->stride_c; a.sp = m->stride_p;
   a.n_total = m->batch * m->pixels;
   a.cstate = cstate;
+  { const char* e = getenv("SLCL_L2_KEEP"); const bool off = e && atoi(e) == 0;
+    a.keep_l2 = (!off && (size_t)a.n_total * (size_t)a.channels * sizeof(float) <= kL2KeepBytes) ? 1 : 0; }
   return a;
 }
 
