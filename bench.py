@@ -870,6 +870,17 @@ def extra_kernels(dev, feats, labels, centres, peak):
     add("fused target step: pseudo labels + target prototype-loss forward, one read of F_t",
         timed(lambda: op.proto_fwd_target(feats, centres, 0.25, K, CFG["temperature"], CFG["base_temperature"], CFG["margin"],
                                           False)), (4 * C + 12) * n_px)
+    # f-1 completed: the same fused target step ALSO producing the hard target centroids (class sums under the pseudo labels
+    # it has just generated) from the same single read of F_t -- vs fused target step + a second pass for the centroids
+    add("fused target step + hard target centroids, ONE read of F_t (slcl_target_step)",
+        timed(lambda: op.target_step(feats, centres, 0.25, False, K, CFG["temperature"], CFG["base_temperature"], CFG["margin"],
+                                     False, None, 0.9)), (4 * C + 12) * n_px)
+
+    def target_two_pass():
+        o = op.proto_fwd_target(feats, centres, 0.25, K, CFG["temperature"], CFG["base_temperature"], CFG["margin"], False)
+        op.centroids_fwd(feats, o[3], None, False, 0.0, None, 1, K, None, 0.9)
+    add("the same results from two passes (proto_fwd_target, then centroids_fwd over the pseudo labels): bytes = 2 reads of F_t",
+        timed(target_two_pass), (8 * C + 20) * n_px)
     add("class_sums hard + ema_finalize (update_class_center_iter)",
         timed(lambda: op.ema_finalize(op.class_sums(feats, labels, None, False, 0.0, None, 1, K), centres, 0.9)),
         (4 * C + 8) * n_px)

@@ -136,6 +136,21 @@ int slcl_proto_rescale_peer(float* scal, int has_sel, const slcl_peer_t* peer, s
  * one warp per element.  2*n <= capacity_words. */
 int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t* peer, slcl_stream_t stream);
 
+/* The same fused target step PLUS the per-class sums of the target map under the pseudo labels it has just generated
+ * (hard target centroids: cal_centroid with the map's own arg-max labels, utils/utils_.py:524-529; weights one-hot(label),
+ * or one-hot(label) * sel when weight_by_sel) -- ONE pass over F_t: every pixel's channel vector sits in a shared-memory
+ * stage, "pixel warps" derive label / sel / loss row / stash from it and the class-sum consumers read the same stage.
+ * label, sel, stash, cstate are bit-identical to slcl_proto_fwd_target's; scal likewise up to the order of the fp64 block
+ * partials.  sums [K, C+1] fp64, centroids [K, C] / inv_weight [K] as slcl_centroids_fwd (previous may be null; peer may be
+ * null, else the sums are all-reduced through the mailboxes).  Contiguous NCHW maps with HW % 4 == 0 and C <= 128
+ * (K <= 5 when C > 64); anything else returns SLCL_ERR_UNSUPPORTED and the caller uses the separate entry points. */
+size_t slcl_target_step_workspace_bytes(int64_t channels, int n_class);
+int slcl_target_step(const float* feat, int64_t batch, int64_t channels, int64_t pixels, const float* centres,
+                     const slcl_proto_params_t* params, float sel_threshold, int weight_by_sel,
+                     int64_t* label, float* sel, float* stash, float* cstate, float* scal, double* sums,
+                     const float* previous, float momentum, float* centroids, float* inv_weight,
+                     const slcl_peer_t* peer, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
 /* Backward w.r.t. the feature map.  grad_out: device scalar dL/dloss.
  * dfeat uses the strides of `map`. */
 int slcl_proto_bwd(const float* feat, const slcl_map_t* map,

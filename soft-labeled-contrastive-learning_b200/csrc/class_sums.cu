@@ -18,12 +18,14 @@
 // order (deterministic; exact integer counts beyond 2^24).
 #include "common.cuh"
 #include "peer.cuh"
+#include "proto_math.cuh"
 
 #include <cuda.h>
 #include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 
 namespace slcl {
@@ -677,6 +679,237 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_
       float* out = a.partial + (int64_t)blockIdx.x * KWT * (C + 1);
 #pragma unroll
       for (int q = 0; q < KWT; ++q) {
+        const float r = warp_sum(cacc[q]);
+        if (lane == 0) out[(int64_t)q * (C + 1) + C] = r;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused target step: generate_pseudo_label (utils/utils_.py:597-624) + the target-side
+// mpcl_loss_calc forward (trainer/Trainer_MPSCL.py:135,144) + the per-class sums of the SAME target map under the pseudo
+// labels just generated (the hard target centroids of cal_centroid, utils/utils_.py:524-529 with the map's own arg-max
+// labels) -- in ONE pass over F_t.  The class-sum ring above already has every pixel's full channel vector in shared
+// memory, so the weight builders become "pixel warps": one pixel per lane, they walk the stage's C channel rows,
+// form the cosines against the unit centres, derive label / selection mask / loss row / backward stash exactly as
+// proto_fwd_kernel's fused-target path does (same fmaf order over the channels, so labels, masks and the stash are
+// bit-identical), write the one-hot weight row, and the consumers accumulate the class sums from the same stage.
+//   warp 0: TMA producer   warps 1..4: pixel warps (every warp on every stage)   then n_cw consumers, 1 counter
+// Needs all C channels in one stage: C <= 16 * CPW (CPW = 4 or 8).
+// ---------------------------------------------------------------------------
+struct TileArgs {
+  const float* feat;
+  int64_t batch, channels, pixels, n_total;
+  const float* cstate;        // unit centres [K*C] (prep_centres_kernel)
+  MarginConst mc;
+  float sel_threshold;
+  int weight_by_sel;          // class-sum weights: one-hot(label) * sel instead of one-hot(label)
+  int64_t* out_label;
+  float* out_sel;
+  float* stash;               // [(K+1) * N]
+  double2* loss_partial;      // [gridDim.x] {sum sel*row, sum sel}
+  float* partial;             // class sums per block [gridDim.x][K][C+1]
+  unsigned int* ticket;
+  int n_cw, n_stages;
+};
+// NPW pixel warps: 4 (every warp on every stage) or 8 (two teams of four on alternating stages; the ring depth is then
+// even, so a team always meets the same slots and sees every phase of their barriers).  8 goes with <= 8 consumer warps.
+template <int K, int CPW, int NPW>
+__global__ void __launch_bounds__(32 * (2 + NPW + (NPW == 8 ? 8 : 16)), 1)
+target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs a) {
+  constexpr int kTilePixelWarps = NPW;
+  constexpr int kTeams = NPW / 4;
+  constexpr int KP = K <= 4 ? 4 : 8;
+  const int C = (int)a.channels;
+  const int kStages = a.n_stages;
+  const int kStageBytes = C * kV3Px * 4;
+  extern __shared__ __align__(128) uint8_t v3_smem[];
+  const uint32_t pad = (128u - (v3_smem_u32(v3_smem) & 127u)) & 127u;                       // align the carve-up to 128 bytes
+  uint8_t* base = v3_smem + pad;
+  const uint32_t sX_u32 = v3_smem_u32(base);                                               // [stages][C][128]
+  const uint32_t sWt_u32 = sX_u32 + (uint32_t)(kStages * kStageBytes);                     // [stages][K][128]
+  const uint32_t sC_u32 = sWt_u32 + (uint32_t)(kStages * K * kV3Px * 4);                   // [C][KP] unit centres
+  const size_t sC_off = (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kV3Px * 4);
+  V3Bars* bars = reinterpret_cast<V3Bars*>(base + (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kV3Px * 4) +
+                                           (size_t)C * KP * 4);
+  __shared__ double s_red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tiles_per_image = (a.pixels + kV3Px - 1) / kV3Px;
+  const int64_t n_tiles = a.batch * tiles_per_image;
+  const int64_t n_iter = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  pdl_trigger();
+  pdl_wait();                                   // cstate comes from prep_centres_kernel in front of us
+  for (int idx = threadIdx.x; idx < C * KP; idx += blockDim.x) {
+    const int c = idx / KP, k = idx % KP;
+    v3_sts32(sC_u32 + idx * 4, (k < K) ? a.cstate[(int64_t)k * C + c] : 0.f);
+  }
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) *a.ticket = 0u;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_feat)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      v3_mbar_init(&bars->x_full[s], 1);
+      v3_mbar_init(&bars->w_full[s], 4);
+      v3_mbar_init(&bars->empty[s], a.n_cw + 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  struct TilePos {
+    int64_t b; int64_t t, step, per;
+    __device__ TilePos(int64_t tile0, int64_t step_, int64_t per_) : step(step_), per(per_) { b = tile0 / per_; t = tile0 - b * per_; }
+    __device__ __forceinline__ void next() { t += step; if (t >= per) { const int64_t q = t / per; b += q; t -= q * per; } }
+    __device__ __forceinline__ int p0() const { return (int)(t * kV3Px); }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      V3Pos pos(0, kStages);
+      TilePos tp(blockIdx.x, gridDim.x, tiles_per_image);
+      for (int64_t it = 0; it < n_iter; ++it, pos.advance(1), tp.next()) {
+        const int s = pos.slot;
+        v3_mbar_wait(&bars->empty[s], (uint32_t)(pos.phase ^ 1));
+        v3_mbar_expect_tx(&bars->x_full[s], kStageBytes);
+        v3_tma_load_3d(sX_u32 + (uint32_t)(s * kStageBytes), &map_feat, &bars->x_full[s], tp.p0(), 0, (int)tp.b);
+      }
+    }
+  } else if (warp <= kTilePixelWarps) {
+    // ===================== pixel warps: cosines, pseudo label, loss row, stash, one-hot weights =====================
+    const int team = (warp - 1) >> 2;
+    const int px = ((warp - 1) & 3) * 32 + lane;
+    double loss_acc = 0.0, sel_acc = 0.0;
+    V3Pos bpos(team, kStages);
+    TilePos tp(blockIdx.x + (int64_t)team * gridDim.x, (int64_t)kTeams * gridDim.x, tiles_per_image);
+    for (int64_t it = team; it < n_iter; it += kTeams, bpos.advance(kTeams), tp.next()) {
+      const int s = bpos.slot;
+      const int p0 = tp.p0();
+      const bool inside = (int64_t)p0 + px < a.pixels;
+      v3_mbar_wait(&bars->x_full[s], (uint32_t)bpos.phase);
+      // plain C++ loads through pointers that stay in the shared window (offsets from the extern array itself), so the
+      // compiler emits LDS AND may software-pipeline them across the unrolled channel loop
+      const float* xs = reinterpret_cast<const float*>(v3_smem + pad + (size_t)s * kStageBytes) + px;
+      const float4* cs = reinterpret_cast<const float4*>(v3_smem + pad + sC_off);
+      float nrm = 0.f, dot[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) dot[k] = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) {
+        const float x = xs[c * kV3Px];
+        float ck[8];
+        { const float4 t = cs[c * (KP / 4)]; ck[0] = t.x; ck[1] = t.y; ck[2] = t.z; ck[3] = t.w; }
+        if constexpr (K > 4) { const float4 t = cs[c * (KP / 4) + 1]; ck[4] = t.x; ck[5] = t.y; ck[6] = t.z; ck[7] = t.w; }
+        nrm = fmaf(x, x, nrm);
+#pragma unroll
+        for (int k = 0; k < K; ++k) dot[k] = fmaf(x, ck[k], dot[k]);
+      }
+      // generate_pseudo_label on the cosines (same arithmetic as pseudo_label_kernel / proto_fwd_kernel's fused path)
+      const float n = fmaxf(sqrtf(nrm), 1e-12f);
+      float t1 = -INFINITY, t2 = -INFINITY;
+      int best = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float cs = dot[k] / n;
+        if (cs > t1) { t2 = t1; t1 = cs; best = k; }
+        else if (cs > t2) { t2 = cs; }
+      }
+      const float selv = (t1 - t2 > a.sel_threshold) ? 1.0f : 0.0f;
+      const float inv_n = 1.0f / n;
+      float cosv[K], M[K], coef[K + 1];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { cosv[k] = dot[k] * inv_n; M[k] = (best == k) ? 1.0f : 0.0f; }
+      const float row = margin_row<K>(cosv, M, selv, inv_n, a.mc, coef);
+      const uint32_t wd = sWt_u32 + (uint32_t)((s * K * kV3Px + px) * 4);
+      const float wsel = a.weight_by_sel ? selv : 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) v3_sts32(wd + (uint32_t)(k * kV3Px * 4), (inside && best == k) ? wsel : 0.f);
+      if (inside) {
+        const int64_t pix = tp.b * a.pixels + p0 + px;
+        a.out_label[pix] = best;
+        a.out_sel[pix] = selv;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) a.stash[(int64_t)k * a.n_total + pix] = coef[k];
+        loss_acc += (double)(selv * row);
+        sel_acc += (double)selv;
+      }
+      __syncwarp();
+      if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
+    }
+    loss_acc = warp_sum(loss_acc);
+    sel_acc = warp_sum(sel_acc);
+    if (lane == 0) { s_red[0][warp - 1] = loss_acc; s_red[1][warp - 1] = sel_acc; }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");         // the pixel warps only
+    if (warp == 1 && lane == 0) {
+      double l = 0.0, sv = 0.0;
+#pragma unroll
+      for (int w = 0; w < kTilePixelWarps; ++w) { l += s_red[0][w]; sv += s_red[1][w]; }
+      a.loss_partial[blockIdx.x] = make_double2(l, sv);
+    }
+  } else {
+    const int cw = warp - 1 - kTilePixelWarps;
+    if (cw < a.n_cw) {
+      // ===================== consumers (as class_sums_v3_kernel) =====================
+      float acc[CPW][K];
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) acc[j][q] = 0.f;
+      V3Pos cpos(0, kStages);
+      for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
+        const int s = cpos.slot;
+        const uint32_t par = (uint32_t)cpos.phase;
+        v3_mbar_wait(&bars->x_full[s], par);
+        v3_mbar_wait(&bars->w_full[s], par);
+        const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + ((cw * CPW) * kV3Px + lane * 4) * 4);
+        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kV3Px + lane * 4) * 4);
+        float4 w[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) w[q] = v3_lds128(ws + q * kV3Px * 4);
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+          const float4 x = v3_lds128(xs + j * kV3Px * 4);
+#pragma unroll
+          for (int q = 0; q < K; ++q) {
+            acc[j][q] = fmaf(w[q].x, x.x, acc[j][q]);
+            acc[j][q] = fmaf(w[q].y, x.y, acc[j][q]);
+            acc[j][q] = fmaf(w[q].z, x.z, acc[j][q]);
+            acc[j][q] = fmaf(w[q].w, x.w, acc[j][q]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) v3_mbar_arrive(&bars->empty[s]);
+      }
+      float* out = a.partial + (int64_t)blockIdx.x * K * (C + 1);
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) {
+        const int c = cw * CPW + j;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const float r = warp_sum(acc[j][q]);
+          if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
+        }
+      }
+    } else if (cw == a.n_cw) {
+      // ===================== counter =====================
+      float cacc[K];
+#pragma unroll
+      for (int q = 0; q < K; ++q) cacc[q] = 0.f;
+      V3Pos cpos(0, kStages);
+      for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
+        const int s = cpos.slot;
+        v3_mbar_wait(&bars->w_full[s], (uint32_t)cpos.phase);
+        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kV3Px + lane * 4) * 4);
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const float4 w = v3_lds128(ws + q * kV3Px * 4);
+          cacc[q] += (w.x + w.y) + (w.z + w.w);
+        }
+        __syncwarp();
+        if (lane == 0) v3_mbar_arrive(&bars->empty[s]);
+      }
+      float* out = a.partial + (int64_t)blockIdx.x * K * (C + 1);
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
         const float r = warp_sum(cacc[q]);
         if (lane == 0) out[(int64_t)q * (C + 1) + C] = r;
       }
@@ -1432,6 +1665,123 @@ extern "C" int slcl_centroids_fwd(const float* feat, int64_t batch, int64_t chan
   const bool vec4 = nchw_vec4(feat, channels, pixels, {feat, labels, probs, part_id});
   FinArgs fin{kFinCentroid, previous, momentum, n_class, centroids, inv_weight};
   return run_class_sums(a, vec4, sums, workspace, workspace_bytes, (cudaStream_t)stream_, peer, fin);
+}
+
+namespace slcl {
+void launch_prep_centres(const float* centres, int C, int K, int normalize, float* cstate, cudaStream_t stream);
+void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal, cudaStream_t stream);
+namespace {
+struct TilePlan { bool ok; int cpw, n_cw, npw, stages; unsigned grid; size_t smem; };
+TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
+  TilePlan p{};
+  p.ok = false;
+  if (C < 1 || C > 128 || K < 2 || K > kMaxK || pixels % 4 != 0 || pixels > INT_MAX || batch > INT_MAX) return p;
+  // register tile and pixel-warp count per shape (acc[CPW][K] <= 40 registers; 8 pixel warps need <= 8 consumer warps)
+  if (C <= 32) { p.cpw = 4; p.npw = 8; }
+  else if (C <= 64 && K <= 5) { p.cpw = 8; p.npw = 8; }
+  else if (C <= 64) { p.cpw = 4; p.npw = 4; }
+  else if (K <= 5) { p.cpw = 8; p.npw = 4; }
+  else return p;
+  p.n_cw = (int)ceil_div<int64_t>(C, p.cpw);
+  const int kp = K <= 4 ? 4 : 8;
+  const size_t stage = (size_t)(C + K) * kV3Px * 4;
+  const size_t fixed = 128 + (size_t)C * kp * 4 + sizeof(V3Bars) + 64;
+  int n = (int)((200 * 1024 - fixed) / stage);
+  if (n > kV3MaxStages) n = kV3MaxStages;
+  n = n / (p.npw / 4) * (p.npw / 4);                    // a multiple of the pixel-warp teams
+  if (n < 2) return p;
+  p.stages = n;
+  p.smem = fixed + (size_t)n * stage;
+  const int64_t n_tiles = batch * ceil_div<int64_t>(pixels, kV3Px);
+  p.grid = (unsigned)std::min<int64_t>(sm_count(), n_tiles);
+  p.ok = true;
+  return p;
+}
+template <int K, int CPW, int NPW>
+int launch_tile(const CUtensorMap& map, const TileArgs& a, const TilePlan& p, cudaStream_t stream) {
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(target_tile_kernel<K, CPW, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(target_tile_kernel)"); return SLCL_ERR_CUDA; }
+    attr_set = true;
+  }
+  launch_pdl(target_tile_kernel<K, CPW, NPW>, dim3(p.grid), dim3(32 * (2 + NPW + p.n_cw)), p.smem, stream, map, a);
+  return SLCL_OK;
+}
+template <int K>
+int launch_tile_k(const CUtensorMap& map, const TileArgs& a, const TilePlan& p, cudaStream_t stream) {
+  if (p.cpw == 4 && p.npw == 8) return launch_tile<K, 4, 8>(map, a, p, stream);
+  if (p.cpw == 4) return launch_tile<K, 4, 4>(map, a, p, stream);
+  if constexpr (K <= 5) {
+    if (p.npw == 8) return launch_tile<K, 8, 8>(map, a, p, stream);
+    return launch_tile<K, 8, 4>(map, a, p, stream);
+  }
+  return SLCL_ERR_UNSUPPORTED;
+}
+}  // namespace
+}  // namespace slcl
+
+extern "C" size_t slcl_target_step_workspace_bytes(int64_t channels, int n_class) {
+  if (channels <= 0 || n_class < 1) return 0;
+  const size_t blocks = (size_t)sm_count();
+  return align_up(blocks * sizeof(double2), 256) + align_up(blocks * n_class * (channels + 1) * sizeof(float), 256) + kTicketBytes;
+}
+
+extern "C" int slcl_target_step(const float* feat, int64_t batch, int64_t channels, int64_t pixels, const float* centres,
+                                const slcl_proto_params_t* params, float sel_threshold, int weight_by_sel,
+                                int64_t* label, float* sel, float* stash, float* cstate, float* scal, double* sums,
+                                const float* previous, float momentum, float* centroids, float* inv_weight,
+                                const slcl_peer_t* peer, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !centres || !params || !label || !sel || !stash || !cstate ||
+      !scal || !sums || !centroids || !inv_weight || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f) || !params->normalize)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (peer != nullptr && (!peer_valid(peer) || 2 * (int64_t)K * (channels + 1) > peer->capacity_words)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < slcl_target_step_workspace_bytes(channels, K) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  const TilePlan p = plan_tile(batch, channels, pixels, K);
+  if (!p.ok || !aligned16(feat) || !aligned16(label) || !aligned16(sel) || !aligned16(stash)) return SLCL_ERR_UNSUPPORTED;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ensure_context_on_this_thread();
+  CUtensorMap map;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)pixels, (cuuint64_t)channels, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)pixels * 4, (cuuint64_t)pixels * channels * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)channels, 1};
+    int st = v3_encode(&map, feat, dims, strides, box);
+    if (st != SLCL_OK) return st;
+  }
+  const size_t blocks = (size_t)sm_count();
+  char* ws = reinterpret_cast<char*>(workspace);
+  TileArgs a{};
+  a.feat = feat; a.batch = batch; a.channels = channels; a.pixels = pixels; a.n_total = batch * pixels;
+  a.cstate = cstate; a.mc = make_margin_const(params); a.sel_threshold = sel_threshold; a.weight_by_sel = weight_by_sel;
+  a.out_label = label; a.out_sel = sel; a.stash = stash;
+  a.loss_partial = reinterpret_cast<double2*>(ws);
+  a.partial = reinterpret_cast<float*>(ws + align_up(blocks * sizeof(double2), 256));
+  a.ticket = reinterpret_cast<unsigned int*>(ws + (workspace_bytes - kTicketBytes) / 16 * 16);
+  a.n_cw = p.n_cw; a.n_stages = p.stages;
+  launch_prep_centres(centres, (int)channels, K, 1, cstate, stream);
+  int st = SLCL_ERR_UNSUPPORTED;
+  switch (K) {
+    case 2: st = launch_tile_k<2>(map, a, p, stream); break;
+    case 3: st = launch_tile_k<3>(map, a, p, stream); break;
+    case 4: st = launch_tile_k<4>(map, a, p, stream); break;
+    case 5: st = launch_tile_k<5>(map, a, p, stream); break;
+    case 6: st = launch_tile_k<6>(map, a, p, stream); break;
+    case 7: st = launch_tile_k<7>(map, a, p, stream); break;
+    case 8: st = launch_tile_k<8>(map, a, p, stream); break;
+    default: return SLCL_ERR_INVALID_ARGUMENT;
+  }
+  if (st != SLCL_OK) return st;
+  launch_proto_finalize(a.loss_partial, (int)p.grid, a.n_total, 1, scal, stream);
+  SumArgs sa{};
+  sa.channels = channels; sa.n_cols = K; sa.partial = a.partial; sa.ticket = a.ticket;
+  FinArgs fin{kFinCentroid, previous, momentum, K, centroids, inv_weight};
+  launch_reduce(sa, (int)p.grid, K, sums, peer, fin, stream);
+  return check_launch("slcl_target_step");
 }
 
 extern "C" int slcl_ema_finalize(const double* sums, const float* old_centres, float m, int n_class, int64_t channels,

@@ -55,6 +55,9 @@ SIGNATURES = {
     "slcl_proto_workspace_bytes": (_SZ, [_I64]),
     "slcl_proto_fwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, _P, _SZ, _P]),
     "slcl_proto_fwd_target": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "slcl_target_step_workspace_bytes": (_SZ, [_I64, C.c_int]),
+    "slcl_target_step": (C.c_int, [_P, _I64, _I64, _I64, _P, C.POINTER(ProtoParamsT), C.c_float, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                   C.c_float, _P, _P, C.POINTER(PeerT), _P, _SZ, _P]),
     "slcl_proto_rescale": (C.c_int, [_P, C.c_int, _P]),
     "slcl_peer_mailbox_bytes": (_SZ, [C.c_int, _I64]),
     "slcl_proto_rescale_peer": (C.c_int, [_P, C.c_int, C.POINTER(PeerT), _P]),

@@ -87,6 +87,62 @@ class _ProtoTargetStep(torch.autograd.Function):
         return dfeat, None, None, None, None, None, None, None, None
 
 
+class _ProtoTargetStepCentroids(torch.autograd.Function):
+    """The fused target step that also returns the hard target centroids of the map under its own pseudo labels
+    (trainer/Trainer_MPSCL.py:135,144 + cal_centroid, utils/utils_.py:524-529): ONE pass over the target
+    map in the forward (slcl_target_step).  Backward: prototype-loss backward + centroid backward (appendix A.1 / A.4)."""
+
+    @staticmethod
+    def forward(ctx, feat, centres, previous, sel_threshold, weight_by_sel, n_class, temperature, base_temperature, margin,
+                easy_margin, momentum, group):
+        from .peer import PeerMailbox
+        prev = None if previous is None else previous.detach()
+        peer_ok = group is None or isinstance(group, PeerMailbox)
+        if peer_ok and ops.target_step_supported(feat, n_class):
+            peer = group.args() if group is not None else ()
+            scal, stash, cstate, label, sel, sums, cen, _ = _ops.target_step(
+                feat.detach(), centres.detach(), sel_threshold, weight_by_sel, n_class, temperature, base_temperature, margin,
+                easy_margin, prev, momentum, *peer)
+            wlab = torch.where(sel > 0, label, torch.full_like(label, -1)) if weight_by_sel else label
+        else:       # shapes outside the tile kernel, or an NCCL group: the separate kernels (two reads of the map)
+            scal, stash, cstate, label, sel = _ops.proto_fwd_target(feat.detach(), centres.detach(), sel_threshold, n_class,
+                                                                    temperature, base_temperature, margin, easy_margin)
+            wlab = torch.where(sel > 0, label, torch.full_like(label, -1)) if weight_by_sel else label
+            if peer_ok:
+                cen, _, sums = _ops.centroids_fwd(feat.detach(), wlab, None, False, 0.0, None, 1, n_class, prev, momentum,
+                                                  *(group.args() if group is not None else ()))
+            else:
+                from .distributed import all_reduce_sums
+                sums = all_reduce_sums(_ops.class_sums(feat.detach(), wlab, None, False, 0.0, None, 1, n_class), group)
+                cen, _ = _ops.centroid_finalize(sums, prev, momentum, 1, n_class)
+        _exchange_loss_pair(scal, True, group)
+        ctx.save_for_backward(feat, stash, cstate, scal, wlab, sums)
+        ctx.cfg = (n_class, momentum, previous is not None)
+        ctx.mark_non_differentiable(label, sel)
+        return scal[0], label, sel, cen
+
+    @staticmethod
+    def backward(ctx, g_loss, _gl, _gs, g_cen):
+        feat, stash, cstate, scal, wlab, sums = ctx.saved_tensors
+        n_class, momentum, has_prev = ctx.cfg
+        dfeat = dprev = None
+        if ctx.needs_input_grad[0]:
+            dfeat = _ops.proto_bwd(feat.detach(), stash, cstate, scal, g_loss.reshape(1), False, n_class, True)
+            dcen, _ = _ops.centroid_bwd(feat.detach(), wlab, None, False, 0.0, None, 1, n_class, g_cen.contiguous(), sums,
+                                        (1.0 - momentum) if has_prev else 1.0, False)
+            dfeat = dfeat + dcen
+        if has_prev and ctx.needs_input_grad[2]:
+            dprev = momentum * g_cen
+        return dfeat, None, dprev, None, None, None, None, None, None, None, None, None
+
+
+def proto_target_step_centroids(feat: Tensor, centres: Tensor, previous: Optional[Tensor], sel_threshold: float, *,
+                                weight_by_sel: bool, n_class: int, temperature: float, base_temperature: float, margin: float,
+                                easy_margin: bool, momentum: float, group=None):
+    return _ProtoTargetStepCentroids.apply(feat, centres, previous, float(sel_threshold), bool(weight_by_sel), n_class,
+                                           temperature, base_temperature, margin, easy_margin, float(momentum), group)
+
+
 def proto_target_step(feat: Tensor, centres: Tensor, sel_threshold: float, *, n_class: int, temperature: float,
                       base_temperature: float, margin: float, easy_margin: bool, group=None):
     return _ProtoTargetStep.apply(feat, centres, float(sel_threshold), n_class, temperature, base_temperature, margin,

@@ -91,19 +91,46 @@ def mpcl_loss_calc(feas, labels, class_center_feas, loss_func, pixel_sel_loc=Non
     return loss_func(unit, labels, centres, pixel_sel_loc=pixel_sel_loc)
 
 
-def mpcl_target_step(feas_t, class_center_feas, loss_func, pixel_sel_th=.25, group=None):
+def mpcl_target_step(feas_t, class_center_feas, loss_func, pixel_sel_th=.25, group=None, with_centroids=False,
+                     weight_by_sel=False, previous_centroid=None, momentum=0.95):
     """Fused target step of trainer/Trainer_MPSCL.py:135,144 (an addition):
 
         hard, mask = generate_pseudo_label(feas_t, class_center_feas, pixel_sel_th)
         loss = mpcl_loss_calc(feas_t, hard, class_center_feas, loss_func, pixel_sel_loc=mask, tag='target')
 
     in ONE read of ``feas_t`` (the reference reads and normalises it twice).  Returns ``(loss, hard, mask)``;
-    gradients flow to ``feas_t`` only (the reference callers pass detached centres, :145)."""
+    gradients flow to ``feas_t`` only (the reference callers pass detached centres, :145).
+
+    ``with_centroids=True`` adds, from the SAME read, the hard target centroids of the map under the pseudo labels it has
+    just produced -- ``cal_centroid(feas_t, one_hot(hard), pseudo_label=True, weighted_ave=False)`` (utils/utils_.py:524-529),
+    optionally restricted to the selected pixels (``weight_by_sel``) and EMA'd with ``previous_centroid`` -- and returns
+    ``(loss, hard, mask, centroids [K, C])``; the centroids are differentiable w.r.t. ``feas_t``."""
     if not isinstance(loss_func, MPCL):
         raise TypeError("loss_func must be an slcl.loss.MPCL")
     kw = loss_func._kw(normalize=True)
     kw.pop("normalize")
+    if with_centroids:
+        return SF.proto_target_step_centroids(feas_t, class_center_feas, previous_centroid, pixel_sel_th,
+                                              weight_by_sel=weight_by_sel, momentum=momentum, group=group, **kw)
     return SF.proto_target_step(feas_t, class_center_feas, pixel_sel_th, group=group, **kw)
+
+
+def mpcl_source_step(feas_s, labels_s, class_center_feas, loss_func, m=.2, num_class=4, group=None):
+    """Source side of trainer/Trainer_MPSCL.py:133,138 as one call:
+
+        centres = update_class_center_iter(feas_s, labels_s, class_center_feas, m)
+        loss = mpcl_loss_calc(feas_s, labels_s, centres.detach(), loss_func, tag='source')
+
+    The loss needs the centres of the WHOLE batch, so the map is walked twice by construction (class sums, then loss); what
+    this call adds is residency: a map that fits in the 126 MB L2 (the per-GPU map of configs[3] does) is kept there by
+    the first walk -- TMA loads with the default evict_normal policy, the loss forward with evict_last -- so the second
+    and third walks (loss forward, loss backward) read it from L2, not from HBM.  Returns ``(centres, loss)``."""
+    from .utils_ import update_class_center_iter
+    if labels_s.shape[-2:] != feas_s.shape[-2:]:
+        raise ValueError("labels must be at feature resolution (update_class_center_iter, utils/utils_.py:575-577)")
+    centres = update_class_center_iter(feas_s, labels_s, class_center_feas, m=m, num_class=num_class, group=group)
+    loss = mpcl_loss_calc(feas_s, labels_s, centres.detach(), loss_func, tag='source', group=group)
+    return centres, loss
 
 
 class ContrastiveLoss(nn.Module):

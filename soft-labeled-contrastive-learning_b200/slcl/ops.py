@@ -150,6 +150,61 @@ def _(feat, centres, sel_threshold, n_class, temperature, base_temperature, marg
             torch.empty(n, dtype=torch.int64, device=feat.device), feat.new_empty(n))
 
 
+@torch.library.custom_op("slcl::target_step", mutates_args=(), device_types="cuda")
+def target_step(feat: Tensor, centres: Tensor, sel_threshold: float, weight_by_sel: bool, n_class: int, temperature: float,
+                base_temperature: float, margin: float, easy_margin: bool, previous: Optional[Tensor], momentum: float,
+                peer_ptrs: int = 0, rank: int = 0, world: int = 1, capacity_words: int = 0,
+                timeout_s: float = 0.0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Fused target step in ONE pass over feat: pseudo labels + target loss forward + per-class sums under those labels.
+    -> (scal[4], stash, cstate, label[N] int64, sel[N], sums [K,C+1] f64, centroids [K,C], inv_weight [K]).
+    Raises SlclError(unsupported) for shapes the tile kernel does not cover (the caller falls back)."""
+    dev = require_cuda(feat, centres, previous)
+    lib = _lib.load()
+    feat = _nchw_contig(feat)
+    b, c, h, w = feat.shape
+    n = b * h * w
+    centres = centres.to(_F32).contiguous()
+    if previous is not None:
+        previous = previous.to(_F32).contiguous()
+    scal = torch.empty(4, dtype=_F32, device=dev)
+    stash = torch.empty((n_class + 1, n), dtype=_F32, device=dev)
+    cstate = torch.empty(n_class * c + n_class, dtype=_F32, device=dev)
+    label = torch.empty(n, dtype=torch.int64, device=dev)
+    sel = torch.empty(n, dtype=_F32, device=dev)
+    sums = torch.empty((n_class, c + 1), dtype=torch.float64, device=dev)
+    cen = torch.empty((n_class, c), dtype=_F32, device=dev)
+    inv_w = torch.empty(n_class, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_target_step_workspace_bytes(c, n_class), dev)
+    p = _params(n_class, temperature, base_temperature, margin, easy_margin, True)
+    peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
+    with _guard(dev):
+        st = lib.slcl_target_step(ptr(feat), b, c, h * w, ptr(centres), C.byref(p), float(sel_threshold), int(weight_by_sel),
+                                  ptr(label), ptr(sel), ptr(stash), ptr(cstate), ptr(scal), ptr(sums), ptr(previous),
+                                  float(momentum), ptr(cen), ptr(inv_w), C.byref(peer) if peer is not None else None, ptr(ws),
+                                  ws.numel(), stream_ptr(dev))
+    check(st, "slcl_target_step")
+    return scal, stash, cstate, label, sel, sums, cen, inv_w
+
+
+@target_step.register_fake
+def _(feat, centres, sel_threshold, weight_by_sel, n_class, temperature, base_temperature, margin, easy_margin, previous,
+      momentum, peer_ptrs=0, rank=0, world=1, capacity_words=0, timeout_s=0.0):
+    n = feat.shape[0] * feat.shape[2] * feat.shape[3]
+    c = feat.shape[1]
+    dev = feat.device
+    return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class),
+            torch.empty(n, dtype=torch.int64, device=dev), feat.new_empty(n),
+            torch.empty((n_class, c + 1), dtype=torch.float64, device=dev), feat.new_empty((n_class, c)), feat.new_empty(n_class))
+
+
+def target_step_supported(feat: Tensor, n_class: int) -> bool:
+    """Shapes the one-pass tile kernel covers (include/slcl.h, slcl_target_step)."""
+    if feat.dim() != 4 or feat.dtype != _F32:
+        return False
+    b, c, h, w = feat.shape
+    return (h * w) % 4 == 0 and c <= 128 and (c <= 64 or n_class <= 5) and 2 <= n_class <= 8
+
+
 @torch.library.custom_op("slcl::proto_rescale", mutates_args=("scal",), device_types="cuda")
 def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     """Recompute scal[0:2] from the (all-reduced) sums scal[2:4], in place."""

@@ -1177,6 +1177,62 @@ def test_fused_target_step_equals_two_call_sequence(api, golden):
 # ---------------------------------------------------------------------------
 # f-2: segmentation losses + entropy map
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("b,c,h,w,k,by_sel", [(2, 32, 16, 16, 4, False), (3, 32, 24, 20, 4, True), (4, 128, 32, 32, 5, False),
+                                                (2, 64, 12, 12, 8, True), (2, 20, 8, 6, 3, False), (2, 160, 16, 16, 4, False)])
+def test_fused_target_step_with_centroids_equals_separate_calls(api, b, c, h, w, k, by_sel):
+    """f-1: pseudo labels + target loss + hard target centroids in ONE pass over F_t (slcl_target_step) must equal
+    generate_pseudo_label -> mpcl_loss_calc(target) -> cal_centroid(one-hot of those labels): labels / mask bit-exact, loss
+    and centroids to fp32 round-off, class counts exact, gradients equal.  C = 160 exercises the fallback (two reads)."""
+    loss_mod, utils_mod = api
+    g = cases.g(b * 100 + c + k)
+    feat = torch.randn(b, c, h, w, generator=g).to(dev())
+    cen = torch.randn(k, c, generator=g).to(dev())
+    prev = torch.randn(k, c, generator=g).to(dev())
+    gcen = torch.randn(k, c, generator=g).to(dev())
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=.2)
+    # separate calls
+    fs = feat.clone().requires_grad_(True)
+    hard_s, sel_s = utils_mod.generate_pseudo_label(fs, cen, .05)
+    loss_s = loss_mod.mpcl_loss_calc(fs, hard_s, cen, mp, pixel_sel_loc=sel_s, tag='target')
+    lab_w = torch.where(sel_s > 0, hard_s, torch.full_like(hard_s, -1)) if by_sel else hard_s
+    cen_s, _, _ = utils_mod.cal_centroid(fs, lab_w.view(b, h, w), previous_centroid=prev, momentum=.9, n_class=k)
+    (loss_s + (cen_s * gcen).sum()).backward()
+    # fused
+    ff = feat.clone().requires_grad_(True)
+    loss_f, hard_f, sel_f, cen_f = loss_mod.mpcl_target_step(ff, cen, mp, .05, with_centroids=True, weight_by_sel=by_sel,
+                                                              previous_centroid=prev, momentum=.9)
+    (loss_f + (cen_f * gcen).sum()).backward()
+    assert torch.equal(hard_f, hard_s) and torch.equal(sel_f, sel_s)
+    close(loss_f, loss_s, rtol=1e-6, atol=0)
+    close(cen_f, cen_s, rtol=1e-5, atol=1e-6)
+    grad_close(ff.grad, fs.grad, rtol=1e-5)
+    if (h * w) % 4 == 0 and c <= 128:
+        from slcl import ops as slcl_ops
+        assert slcl_ops.target_step_supported(feat, k)
+        out = torch.ops.slcl.target_step(feat, cen, .05, by_sel, k, .1, 1.0, .2, False, None, .9)
+        want = torch.bincount(lab_w[lab_w >= 0], minlength=k)
+        assert torch.equal(out[5][:, -1].long(), want)                           # class counts exact
+        ref = torch.ops.slcl.proto_fwd_target(feat, cen, .05, k, .1, 1.0, .2, False)
+        assert torch.equal(out[1], ref[1]) and torch.equal(out[2], ref[2])         # stash / cstate bit-identical
+
+
+def test_source_step_equals_separate_calls(api):
+    loss_mod, utils_mod = api
+    g = cases.g(515)
+    feat = torch.randn(4, 32, 24, 24, generator=g).to(dev())
+    lab = torch.randint(0, 4, (4, 24, 24), generator=g).to(dev())
+    cen = torch.randn(4, 32, generator=g).to(dev())
+    mp = loss_mod.MPCL(dev(), num_class=4, temperature=.1, base_temperature=1, m=.4)
+    fs = feat.clone().requires_grad_(True)
+    c1 = utils_mod.update_class_center_iter(fs, lab, cen, m=.9)
+    l1 = loss_mod.mpcl_loss_calc(fs, lab, c1.detach(), mp, tag='source')
+    l1.backward()
+    ff = feat.clone().requires_grad_(True)
+    c2, l2 = loss_mod.mpcl_source_step(ff, lab, cen, mp, m=.9, num_class=4)
+    l2.backward()
+    assert torch.equal(c1, c2) and torch.equal(l1, l2) and torch.equal(fs.grad, ff.grad)
+
+
 def test_seg_losses_vs_reference_golden_gpu():
     import os
     from slcl import seg
