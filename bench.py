@@ -12,8 +12,8 @@ fp32 pixel-selection mask, [5,128] class centres, T=0.1, base_T=1, m=0.2.
 A step = one forward + backward of the prototype loss (reference mpcl_loss_calc + MPCL.forward,
 utils/loss.py:576-605,484-573 and its autograd backward): 3 forward launches (centre prep, fused
 loss, finalise) + 1 backward launch; with N>1 the loss is the mean over the GLOBAL batch, so one
-8-byte exchange sits between forward and backward -- done by our own rescale kernel over NVLink peer memory
-(slcl_proto_rescale_peer), or by an NCCL all-reduce + rescale launch when symmetric memory is unavailable.
+8-byte exchange sits between forward and backward -- done inside the forward's own finaliser kernel over NVLink peer
+memory (slcl_proto_fwd_peer), or by an NCCL all-reduce + rescale launch when symmetric memory is unavailable.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.  No L2 flush is needed: every step streams
@@ -329,19 +329,18 @@ def run_slcl(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
         if float(ok) < 1.0:
             mailbox = None
-        exchange_how = ("fused exchange + rescale kernel over NVLink peer memory (8-byte {epoch|fp32} stores into every "
-                        "peer's mailbox)") if mailbox is not None else f"NCCL all-reduce of 8 bytes + rescale kernel ({why})"
+        exchange_how = ("loss pair exchanged INSIDE the forward's finaliser kernel over NVLink peer memory (8-byte {epoch|fp32} "
+                        "stores into every peer's mailbox; no launch between forward and backward)") if mailbox is not None \
+            else f"NCCL all-reduce of 8 bytes + rescale kernel ({why})"
 
     def step(record: bool):
         e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
         if record:
             e0.record()
-        scal = plan.forward()
+        scal = plan.forward(mailbox)          # N > 1 with mailboxes: the finaliser kernel exchanges the loss pair itself
         if record:
             e1.record()
-        if mailbox is not None:
-            plan.rescale_peer(mailbox)
-        elif world > 1:
+        if mailbox is None and world > 1:
             dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
             plan.rescale()
         if record:
@@ -404,7 +403,7 @@ def run_slcl(args):
     xch_ms = statistics.mean(m[1].elapsed_time(m[2]) for m in marks)
     bwd_ms = statistics.mean(m[2].elapsed_time(m[3]) for m in marks)
     loss_value = float(scal[0])
-    launches_per_step = 4 + (1 if world > 1 else 0)
+    launches_per_step = 4 + (1 if (world > 1 and mailbox is None) else 0)
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     e2e = None
@@ -678,10 +677,8 @@ def cfg4_strong_scaling(dev, world, rank, mailbox=None):
     group = (mailbox if mailbox is not None else True) if world > 1 else None
 
     def proto_step():
-        scal = plan.forward()
-        if mailbox is not None:
-            plan.rescale_peer(mailbox)
-        elif world > 1:
+        scal = plan.forward(mailbox)
+        if mailbox is None and world > 1:
             dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
             plan.rescale()
         plan.backward()

@@ -136,6 +136,20 @@ int slcl_proto_rescale_peer(float* scal, int has_sel, const slcl_peer_t* peer, s
  * one warp per element.  2*n <= capacity_words. */
 int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t* peer, slcl_stream_t stream);
 
+/* Data-parallel forms of the two forwards: with `peer` (may be null = the plain call) the finaliser kernel exchanges
+ * {weight sum, weighted row-loss sum} with the other ranks through the mailboxes before it writes scal, so scal[0] is
+ * the loss over the GLOBAL batch and scal[1] the global coefficient -- no slcl_proto_rescale(_peer) call, no extra launch
+ * between forward and backward.  (slcl_target_step does the same with its `peer`.) */
+int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map,
+                        const int64_t* labels, const float* soft_mask, const float* sel,
+                        const float* centres, const slcl_proto_params_t* params,
+                        float* stash, float* cstate, float* scal, const slcl_peer_t* peer,
+                        void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+int slcl_proto_fwd_target_peer(const float* feat, const slcl_map_t* map, const float* centres,
+                               const slcl_proto_params_t* params, float sel_threshold,
+                               int64_t* label, float* sel, float* stash, float* cstate, float* scal,
+                               const slcl_peer_t* peer, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
 /* The same fused target step PLUS the per-class sums of the target map under the pseudo labels it has just generated
  * (hard target centroids: cal_centroid with the map's own arg-max labels, utils/utils_.py:524-529; weights one-hot(label),
  * or one-hot(label) * sel when weight_by_sel) -- ONE pass over F_t: every pixel's channel vector sits in a shared-memory

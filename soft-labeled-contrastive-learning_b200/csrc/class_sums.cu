@@ -1669,7 +1669,8 @@ extern "C" int slcl_centroids_fwd(const float* feat, int64_t batch, int64_t chan
 
 namespace slcl {
 void launch_prep_centres(const float* centres, int C, int K, int normalize, float* cstate, cudaStream_t stream);
-void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal, cudaStream_t stream);
+void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal,
+                           const slcl_peer_t* peer, cudaStream_t stream);
 namespace {
 struct TilePlan { bool ok; int cpw, n_cw, npw, stages; unsigned grid; size_t smem; };
 TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
@@ -1776,7 +1777,7 @@ extern "C" int slcl_target_step(const float* feat, int64_t batch, int64_t channe
     default: return SLCL_ERR_INVALID_ARGUMENT;
   }
   if (st != SLCL_OK) return st;
-  launch_proto_finalize(a.loss_partial, (int)p.grid, a.n_total, 1, scal, stream);
+  launch_proto_finalize(a.loss_partial, (int)p.grid, a.n_total, 1, scal, peer, stream);      // loss pair exchanged here too
   SumArgs sa{};
   sa.channels = channels; sa.n_cols = K; sa.partial = a.partial; sa.ticket = a.ticket;
   FinArgs fin{kFinCentroid, previous, momentum, K, centroids, inv_weight};

@@ -265,11 +265,17 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
 
 // Sums the block partials in index order (deterministic) and writes
 // scal = {loss, coefficient, weight sum, weighted row-loss sum}.
+// Data-parallel (pc.world > 1): the pair {weight sum, weighted row-loss sum} is exchanged with the other ranks right
+// here, through the NVLink peer mailboxes (peer.cuh) -- the same words slcl_proto_rescale_peer would send, added in the
+// same rank order -- so the forward needs no extra launch (and no collective) to return the GLOBAL loss.
 __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2* partial, int n_blocks, int64_t n_total,
-                                                                   int has_sel, float* scal) {
+                                                                   int has_sel, float* scal, const PeerCtx pc) {
   pdl_trigger();
   pdl_wait();
   __shared__ double red[2][kThreads / 32];
+  __shared__ float s_pair[2];
+  __shared__ float s_vals[2 * kMaxPeers];
+  __shared__ int s_bad;
   double l = 0.0, s = 0.0;
   for (int i = threadIdx.x; i < n_blocks; i += kThreads) { double2 p = partial[i]; l += p.x; s += p.y; }
   l = warp_sum(l); s = warp_sum(s);
@@ -279,12 +285,36 @@ __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2*
   if (threadIdx.x == 0) {
     l = 0.0; s = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) { l += red[0][w]; s += red[1][w]; }
+    s_pair[0] = has_sel ? (float)s : (float)n_total;
+    s_pair[1] = (float)l;
+    s_bad = 0;
+  }
+  __syncthreads();
+  float wsum = s_pair[0], lsum = s_pair[1];
+  if (pc.world > 1) {
+    const unsigned int e = peer_epoch_begin(pc);
+    const int t = threadIdx.x;
+    if (t < 2 * pc.world) {
+      bool ok;
+      const unsigned int got = peer_send_recv(pc, e, t >> 1, t & 1, __float_as_uint(s_pair[t & 1]), ok);
+      s_vals[t] = __uint_as_float(got);
+      if (!ok) s_bad = 1;
+    }
+    __syncthreads();
+    if (t == 0) {
+      wsum = 0.f; lsum = 0.f;
+      for (int r = 0; r < pc.world; ++r) { wsum += s_vals[2 * r]; lsum += s_vals[2 * r + 1]; }
+      if (s_bad) { wsum = __uint_as_float(0x7FC00000u); lsum = wsum; }      // a peer never arrived: poison, do not hang
+      peer_epoch_end(pc, e, 1u);
+    }
+  }
+  if (threadIdx.x == 0) {
     // with pixel_sel_loc: sum / (sum(sel) + 1e-4) (:565); else mean over N (:571)
-    float coef = has_sel ? 1.0f / ((float)s + 1e-4f) : 1.0f / (float)n_total;
-    scal[0] = (float)l * coef;
+    const float coef = has_sel ? 1.0f / (wsum + 1e-4f) : 1.0f / wsum;
+    scal[0] = lsum * coef;
     scal[1] = coef;
-    scal[2] = has_sel ? (float)s : (float)n_total;
-    scal[3] = (float)l;
+    scal[2] = wsum;
+    scal[3] = lsum;
   }
 }
 
@@ -561,9 +591,10 @@ int ensure_smem(Kern kern, size_t smem) {
 void launch_prep_centres(const float* centres, int C, int K, int normalize, float* cstate, cudaStream_t stream) {
   launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, C, K, normalize, cstate);
 }
-void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal, cudaStream_t stream) {
+void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal,
+                           const slcl_peer_t* peer, cudaStream_t stream) {
   launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, reinterpret_cast<const double2*>(partial), n_blocks,
-             n_total, has_sel, scal);
+             n_total, has_sel, scal, peer_ctx(peer));
 }
 }  // namespace slcl
 
@@ -574,12 +605,13 @@ extern "C" size_t slcl_proto_workspace_bytes(int64_t n_pixels) {
   return (size_t)ceil_div<int64_t>(n_pixels, kThreads) * sizeof(double2) + 256;
 }
 
-extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
-                              const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
-                              float* cstate, float* scal, void* workspace, size_t workspace_bytes,
-                              slcl_stream_t stream_) {
+extern "C" int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
+                                   const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
+                                   float* cstate, float* scal, const slcl_peer_t* peer, void* workspace,
+                                   size_t workspace_bytes, slcl_stream_t stream_) {
   if (!feat || !validate_map(map) || !centres || !params || !stash || !cstate || !scal || !workspace)
     return SLCL_ERR_INVALID_ARGUMENT;
+  if (peer != nullptr && !peer_valid(peer)) return SLCL_ERR_INVALID_ARGUMENT;
   if ((labels == nullptr) == (soft_mask == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;   // exactly one (:502-505)
   const int K = params->n_class;
   if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f))
@@ -600,16 +632,25 @@ extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const in
     if (st != SLCL_OK) return st;
     launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, (int)(sel != nullptr), scal);
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, (int)(sel != nullptr), scal, peer_ctx(peer));
   return check_launch("slcl_proto_fwd");
 }
 
-extern "C" int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float* centres,
-                                     const slcl_proto_params_t* params, float sel_threshold, int64_t* label, float* sel,
-                                     float* stash, float* cstate, float* scal, void* workspace, size_t workspace_bytes,
-                                     slcl_stream_t stream_) {
+extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
+                              const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
+                              float* cstate, float* scal, void* workspace, size_t workspace_bytes,
+                              slcl_stream_t stream_) {
+  return slcl_proto_fwd_peer(feat, map, labels, soft_mask, sel, centres, params, stash, cstate, scal, nullptr, workspace,
+                             workspace_bytes, stream_);
+}
+
+extern "C" int slcl_proto_fwd_target_peer(const float* feat, const slcl_map_t* map, const float* centres,
+                                          const slcl_proto_params_t* params, float sel_threshold, int64_t* label, float* sel,
+                                          float* stash, float* cstate, float* scal, const slcl_peer_t* peer, void* workspace,
+                                          size_t workspace_bytes, slcl_stream_t stream_) {
   if (!feat || !validate_map(map) || !centres || !params || !label || !sel || !stash || !cstate || !scal || !workspace)
     return SLCL_ERR_INVALID_ARGUMENT;
+  if (peer != nullptr && !peer_valid(peer)) return SLCL_ERR_INVALID_ARGUMENT;
   const int K = params->n_class;
   if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f) || !params->normalize)
     return SLCL_ERR_INVALID_ARGUMENT;
@@ -628,8 +669,16 @@ extern "C" int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, c
     if (st != SLCL_OK) return st;
     launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, 1, scal);
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, 1, scal, peer_ctx(peer));
   return check_launch("slcl_proto_fwd_target");
+}
+
+extern "C" int slcl_proto_fwd_target(const float* feat, const slcl_map_t* map, const float* centres,
+                                     const slcl_proto_params_t* params, float sel_threshold, int64_t* label, float* sel,
+                                     float* stash, float* cstate, float* scal, void* workspace, size_t workspace_bytes,
+                                     slcl_stream_t stream_) {
+  return slcl_proto_fwd_target_peer(feat, map, centres, params, sel_threshold, label, sel, stash, cstate, scal, nullptr,
+                                    workspace, workspace_bytes, stream_);
 }
 
 extern "C" int slcl_proto_rescale(float* scal, int has_sel, slcl_stream_t stream_) {

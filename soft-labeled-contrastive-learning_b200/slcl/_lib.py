@@ -54,6 +54,10 @@ SIGNATURES = {
     "slcl_last_cuda_error": (C.c_char_p, []),
     "slcl_proto_workspace_bytes": (_SZ, [_I64]),
     "slcl_proto_fwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, _P, _SZ, _P]),
+    "slcl_proto_fwd_peer": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, C.POINTER(PeerT), _P,
+                                      _SZ, _P]),
+    "slcl_proto_fwd_target_peer": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P,
+                                             C.POINTER(PeerT), _P, _SZ, _P]),
     "slcl_proto_fwd_target": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "slcl_target_step_workspace_bytes": (_SZ, [_I64, C.c_int]),
     "slcl_target_step": (C.c_int, [_P, _I64, _I64, _I64, _P, C.POINTER(ProtoParamsT), C.c_float, C.c_int, _P, _P, _P, _P, _P, _P, _P,

@@ -14,6 +14,15 @@ from . import ops  # noqa: F401  (registers torch.ops.slcl.*)
 _ops = ops.dispatch          # eager: op bodies directly; compiled: torch.ops.slcl
 
 
+def _peer_args(group):
+    """The flat mailbox arguments when `group` is a PeerMailbox over more than one rank (the forward kernels then do the
+    loss-pair exchange themselves, inside their finaliser), else ()."""
+    from .peer import PeerMailbox
+    if isinstance(group, PeerMailbox) and group.world > 1:
+        return group.args()
+    return ()
+
+
 def _exchange_loss_pair(scal, has_sel: bool, group) -> None:
     """Data-parallel prototype loss: global mean = summed numerator / summed denominator.
     ``group``: None (single process), True / a ProcessGroup (NCCL all-reduce of scal[2:4] + rescale), or a
@@ -22,9 +31,7 @@ def _exchange_loss_pair(scal, has_sel: bool, group) -> None:
         return
     from .peer import PeerMailbox
     if isinstance(group, PeerMailbox):
-        if group.world > 1:
-            _ops.proto_rescale_peer(scal, has_sel, *group.args())
-        return
+        return                       # exchanged inside the forward's finaliser kernel (_peer_args)
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1:
         dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM, group=None if group is True else group)
@@ -40,7 +47,8 @@ class _ProtoLoss(torch.autograd.Function):
                 easy_margin, normalize, group):
         scal, stash, cstate = _ops.proto_fwd(feat.detach(), labels, None if soft_mask is None else soft_mask.detach(),
                                              None if sel is None else sel.detach(), centres.detach(), rows_layout,
-                                             n_class, temperature, base_temperature, margin, easy_margin, normalize)
+                                             n_class, temperature, base_temperature, margin, easy_margin, normalize,
+                                             *_peer_args(group))
         _exchange_loss_pair(scal, sel is not None, group)
         ctx.save_for_backward(feat, stash, cstate, scal)
         ctx.cfg = (rows_layout, n_class, normalize)
@@ -71,7 +79,8 @@ class _ProtoTargetStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin, group):
         scal, stash, cstate, label, sel = _ops.proto_fwd_target(feat.detach(), centres.detach(), sel_threshold, n_class,
-                                                                temperature, base_temperature, margin, easy_margin)
+                                                                temperature, base_temperature, margin, easy_margin,
+                                                                *_peer_args(group))
         _exchange_loss_pair(scal, True, group)
         ctx.save_for_backward(feat, stash, cstate, scal)
         ctx.n_class = n_class
@@ -106,7 +115,8 @@ class _ProtoTargetStepCentroids(torch.autograd.Function):
             wlab = torch.where(sel > 0, label, torch.full_like(label, -1)) if weight_by_sel else label
         else:       # shapes outside the tile kernel, or an NCCL group: the separate kernels (two reads of the map)
             scal, stash, cstate, label, sel = _ops.proto_fwd_target(feat.detach(), centres.detach(), sel_threshold, n_class,
-                                                                    temperature, base_temperature, margin, easy_margin)
+                                                                    temperature, base_temperature, margin, easy_margin,
+                                                                    *_peer_args(group))
             wlab = torch.where(sel > 0, label, torch.full_like(label, -1)) if weight_by_sel else label
             if peer_ok:
                 cen, _, sums = _ops.centroids_fwd(feat.detach(), wlab, None, False, 0.0, None, 1, n_class, prev, momentum,

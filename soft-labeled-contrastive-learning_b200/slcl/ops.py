@@ -79,11 +79,21 @@ def _feat_map(feat: Tensor, rows_layout: bool):
 # ----------------------------------------------------------------------------
 # prototype path
 # ----------------------------------------------------------------------------
+def _peer(peer_ptrs: int, rank: int, world: int, capacity_words: int, timeout_s: float) -> Optional[PeerT]:
+    """slcl_peer_t from the flat (ptrs, rank, world, capacity, timeout) form ops carry (slcl.peer.PeerMailbox.args());
+    world <= 1 or a null pointer table = no exchange."""
+    if world <= 1 or not peer_ptrs:
+        return None
+    return PeerT(peer_ptrs, rank, world, capacity_words, timeout_s)
+
+
 @torch.library.custom_op("slcl::proto_fwd", mutates_args=(), device_types="cuda")
 def proto_fwd(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor],
               centres: Tensor, rows_layout: bool, n_class: int, temperature: float, base_temperature: float,
-              margin: float, easy_margin: bool, normalize: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (scal[4] = {loss, coef, weight sum, row-loss sum}, stash[(K+1), N], cstate[K*C+K])"""
+              margin: float, easy_margin: bool, normalize: bool, peer_ptrs: int = 0, rank: int = 0, world: int = 1,
+              capacity_words: int = 0, timeout_s: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (scal[4] = {loss, coef, weight sum, row-loss sum}, stash[(K+1), N], cstate[K*C+K]).  With a peer mailbox
+    (slcl.peer.PeerMailbox.args()) the finaliser exchanges the loss pair with the other ranks: scal is GLOBAL."""
     dev = require_cuda(feat, labels, soft_mask, sel, centres)
     lib = _lib.load()
     feat_c, m = _feat_map(feat, rows_layout)
@@ -103,16 +113,18 @@ def proto_fwd(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor
     nbytes = lib.slcl_proto_workspace_bytes(n)
     ws = _ws(nbytes, dev)
     p = _params(n_class, temperature, base_temperature, margin, easy_margin, normalize)
+    peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
     with _guard(dev):
-        st = lib.slcl_proto_fwd(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(centres), C.byref(p),
-                                ptr(stash), ptr(cstate), ptr(scal), ptr(ws), ws.numel(), stream_ptr(dev))
+        st = lib.slcl_proto_fwd_peer(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(centres), C.byref(p),
+                                     ptr(stash), ptr(cstate), ptr(scal), C.byref(peer) if peer is not None else None, ptr(ws),
+                                     ws.numel(), stream_ptr(dev))
     check(st, "slcl_proto_fwd")
     return scal, stash, cstate
 
 
 @proto_fwd.register_fake
 def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, base_temperature, margin, easy_margin,
-      normalize):
+      normalize, peer_ptrs=0, rank=0, world=1, capacity_words=0, timeout_s=0.0):
     n = feat.shape[0] if rows_layout else feat.shape[0] * feat.shape[2] * feat.shape[3]
     c = feat.shape[1]
     return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class))
@@ -120,8 +132,9 @@ def _(feat, labels, soft_mask, sel, centres, rows_layout, n_class, temperature, 
 
 @torch.library.custom_op("slcl::proto_fwd_target", mutates_args=(), device_types="cuda")
 def proto_fwd_target(feat: Tensor, centres: Tensor, sel_threshold: float, n_class: int, temperature: float,
-                     base_temperature: float, margin: float,
-                     easy_margin: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                     base_temperature: float, margin: float, easy_margin: bool, peer_ptrs: int = 0, rank: int = 0,
+                     world: int = 1, capacity_words: int = 0,
+                     timeout_s: float = 0.0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (scal[4], stash, cstate, label[N] int64, sel[N]) : pseudo labels + target loss forward, one read of feat."""
     dev = require_cuda(feat, centres)
     lib = _lib.load()
@@ -135,15 +148,18 @@ def proto_fwd_target(feat: Tensor, centres: Tensor, sel_threshold: float, n_clas
     sel = torch.empty(n, dtype=_F32, device=dev)
     ws = _ws(lib.slcl_proto_workspace_bytes(n), dev)
     p = _params(n_class, temperature, base_temperature, margin, easy_margin, True)
+    peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
     with _guard(dev):
-        st = lib.slcl_proto_fwd_target(ptr(feat_c), C.byref(m), ptr(centres), C.byref(p), float(sel_threshold), ptr(label),
-                                       ptr(sel), ptr(stash), ptr(cstate), ptr(scal), ptr(ws), ws.numel(), stream_ptr(dev))
+        st = lib.slcl_proto_fwd_target_peer(ptr(feat_c), C.byref(m), ptr(centres), C.byref(p), float(sel_threshold), ptr(label),
+                                            ptr(sel), ptr(stash), ptr(cstate), ptr(scal),
+                                            C.byref(peer) if peer is not None else None, ptr(ws), ws.numel(), stream_ptr(dev))
     check(st, "slcl_proto_fwd_target")
     return scal, stash, cstate, label, sel
 
 
 @proto_fwd_target.register_fake
-def _(feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin):
+def _(feat, centres, sel_threshold, n_class, temperature, base_temperature, margin, easy_margin, peer_ptrs=0, rank=0, world=1,
+      capacity_words=0, timeout_s=0.0):
     n = feat.shape[0] * feat.shape[2] * feat.shape[3]
     c = feat.shape[1]
     return (feat.new_empty(4), feat.new_empty((n_class + 1, n)), feat.new_empty(n_class * c + n_class),
@@ -212,14 +228,6 @@ def proto_rescale(scal: Tensor, has_sel: bool) -> None:
     with _guard(dev):
         st = _lib.load().slcl_proto_rescale(ptr(scal), int(has_sel), stream_ptr(dev))
     check(st, "slcl_proto_rescale")
-
-
-def _peer(peer_ptrs: int, rank: int, world: int, capacity_words: int, timeout_s: float) -> Optional[PeerT]:
-    """slcl_peer_t from the flat (ptrs, rank, world, capacity, timeout) form ops carry (slcl.peer.PeerMailbox.args());
-    world <= 1 or a null pointer table = no exchange."""
-    if world <= 1 or not peer_ptrs:
-        return None
-    return PeerT(peer_ptrs, rank, world, capacity_words, timeout_s)
 
 
 @torch.library.custom_op("slcl::proto_rescale_peer", mutates_args=("scal",), device_types="cuda")

@@ -58,9 +58,16 @@ class ProtoPlan:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def forward(self) -> torch.Tensor:
-        """Launch the forward; returns scal (scal[0] is the loss).  Asynchronous."""
-        check(self.lib.slcl_proto_fwd(*self._fwd_args, self._stream()), "slcl_proto_fwd")
+    def forward(self, mailbox=None) -> torch.Tensor:
+        """Launch the forward; returns scal (scal[0] is the loss).  Asynchronous.  With ``mailbox`` (slcl.peer.PeerMailbox,
+        more than one rank) the finaliser kernel exchanges the loss pair with the other ranks: scal is then GLOBAL and
+        neither ``rescale()`` nor ``rescale_peer()`` is needed before ``backward()``."""
+        if mailbox is not None and mailbox.world > 1:
+            peer = mailbox.struct()
+            args = self._fwd_args[:10] + (C.byref(peer),) + self._fwd_args[10:]
+            check(self.lib.slcl_proto_fwd_peer(*args, self._stream()), "slcl_proto_fwd_peer")
+        else:
+            check(self.lib.slcl_proto_fwd(*self._fwd_args, self._stream()), "slcl_proto_fwd")
         return self.scal
 
     def rescale(self) -> None:
