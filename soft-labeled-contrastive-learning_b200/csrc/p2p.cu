@@ -923,7 +923,12 @@ __global__ void __launch_bounds__(256) p2p_reduce_stats_self_kernel(const float*
     const int sc = a_selfcol[i];
     if (sc >= 0) {
       const float s_self = warp_dot_bf16(a + (size_t)i * d, b + (size_t)sc * d, d, lane);
-      t[0] -= ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
+      // The self term was summed by the sweep (tensor-core route) and is taken out here (fp32 route): when it dominates
+      // the row -- small T, few or distant neighbours -- the difference is pure round-off and can come out <= 0.  Floor it
+      // at the round-off level of the self term so log() and 1/Zs stay finite (the reference masks the diagonal exactly
+      // and is finite there too; below this floor no fp32 evaluation of the row is meaningful).
+      const float e_self = ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
+      t[0] = fmaxf(t[0] - e_self, e_self * 1.1920929e-7f);
       if (a_meta[i].x == b_meta[sc].x) { t[1] -= s_self; t[2] -= 1.f; }
     }
     if (lane == 0) {
@@ -1164,7 +1169,7 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
     if (sc >= 0) {
       const float s_self = warp_dot_bf16(ai, b + (size_t)sc * d, d, lane);
       const float e_self = ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
-      zs -= e_self;
+      zs = fmaxf(zs - e_self, e_self * 1.1920929e-7f);      // round-off floor, see p2p_reduce_stats_self_kernel
       if (lab == b_meta[sc].x) { praw -= s_self; n -= 1.f; }
     }
     if (lane == 0) {

@@ -129,6 +129,18 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
                           float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow, int(n_batch))
 
 
+_INDEX_CACHE = {}          # row-index tensors per geometry: pure functions of the shapes, rebuilt ~20 small torch ops a call
+
+
+def _cached(key, build):
+    hit = _INDEX_CACHE.get(key)
+    if hit is None:
+        if len(_INDEX_CACHE) > 64:
+            _INDEX_CACHE.clear()
+        hit = _INDEX_CACHE[key] = build()
+    return hit
+
+
 def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch.Tensor, device) -> torch.Tensor:
     """Pixel indices (into the [b*v, c, h, w] memory-order map) of the reference's row order
     ``cat(unbind(features, dim=1), dim=0)`` (utils/loss.py:337-343) restricted to rows ys, cols xs."""
@@ -137,7 +149,7 @@ def _view_major_rows(b: int, v: int, h: int, w: int, ys: torch.Tensor, xs: torch
     return (img.view(-1, 1) * (h * w) + grid.view(1, -1)).reshape(-1)             # (v, b, y, x) order
 
 
-def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False, n_class=0):
+def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False, n_class=0, geom=None):
     if features.ndim <= 3:                                                          # :334-336
         raise ValueError('`features` needs to be [bsz, n_views, ...],'
                          'at least 4 dimensions are required')
@@ -146,9 +158,14 @@ def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False, 
     b, v, c, h, w = features.shape
     dev = features.device
     fmap = features.reshape(b * v, c, h, w)
-    idx = _view_major_rows(b, v, h, w, ys, xs, dev)
+    if geom is not None:          # ys / xs are a pure function of `geom`: reuse the index tensors of the previous call
+        idx, ids = _cached(("rows", b, v, h, w, geom, str(dev)),
+                           lambda: (lambda i: (i, torch.arange(i.numel(), device=dev, dtype=torch.int32)))(
+                               _view_major_rows(b, v, h, w, ys(), xs(), dev)))
+    else:
+        idx = _view_major_rows(b, v, h, w, ys, xs, dev)
+        ids = torch.arange(idx.numel(), device=dev, dtype=torch.int32)
     m = idx.numel()
-    ids = torch.arange(m, device=dev, dtype=torch.int32)
     if labels is not None:
         lab_map = labels.reshape(-1)
         lab = lab_map[idx].to(torch.int32)                                          # :352-353
@@ -185,8 +202,8 @@ class SupConLoss(nn.Module):
         h, w = features.shape[-2:]
         dev = features.device
         n_class, in_range = self._classes.resolve(labels)
-        return _guard(_supcon(features, labels, self.temperature, torch.arange(h, device=dev), torch.arange(w, device=dev),
-                              n_class=n_class), in_range)
+        return _guard(_supcon(features, labels, self.temperature, lambda: torch.arange(h, device=dev),
+                              lambda: torch.arange(w, device=dev), n_class=n_class, geom=("all",)), in_range)
 
 
 class LocalConLoss(nn.Module):
@@ -201,10 +218,11 @@ class LocalConLoss(nn.Module):
     def forward(self, features, labels=None):
         h, w = features.shape[-2:]
         dev = features.device
-        ys = torch.arange(0, h, self.stride, device=dev)
-        xs = torch.arange(0, w, self.stride, device=dev)
+        st = self.stride
         n_class, in_range = self.supconloss._classes.resolve(labels)
-        return _guard(_supcon(features, labels, self.temp, ys, xs, zero_if_no_foreground=True, n_class=n_class), in_range)
+        return _guard(_supcon(features, labels, self.temp, lambda: torch.arange(0, h, st, device=dev),
+                              lambda: torch.arange(0, w, st, device=dev), zero_if_no_foreground=True, n_class=n_class,
+                              geom=("stride", st)), in_range)
 
 
 class BlockConLoss(nn.Module):
@@ -251,14 +269,17 @@ class BlockConLoss(nn.Module):
         dev = features.device
         bs = self.block_size
         fmap = features.reshape(b * v, c, h, w)
-        ar = torch.arange(bs, device=dev)
-        ti = torch.arange(div, device=dev)
-        ys = (ti.view(-1, 1) * bs + ar.view(1, -1))                                  # [div, bs]
-        grid = (ys.view(div, 1, bs, 1) * w + ys.view(1, div, 1, bs)).reshape(div * div, bs * bs)      # [tiles, bs*bs]
-        img = (torch.arange(b, device=dev).view(1, -1) * v + torch.arange(v, device=dev).view(-1, 1)).reshape(-1)   # (v, b)
-        idx = (img.view(1, -1, 1) * (h * w) + grid.view(div * div, 1, bs * bs)).reshape(-1)           # (tile, v, b, y, x)
+
+        def build():
+            ar = torch.arange(bs, device=dev)
+            ti = torch.arange(div, device=dev)
+            ys = (ti.view(-1, 1) * bs + ar.view(1, -1))                                  # [div, bs]
+            grid = (ys.view(div, 1, bs, 1) * w + ys.view(1, div, 1, bs)).reshape(div * div, bs * bs)      # [tiles, bs*bs]
+            img = (torch.arange(b, device=dev).view(1, -1) * v + torch.arange(v, device=dev).view(-1, 1)).reshape(-1)   # (v, b)
+            i = (img.view(1, -1, 1) * (h * w) + grid.view(div * div, 1, bs * bs)).reshape(-1)           # (tile, v, b, y, x)
+            return i, torch.arange(i.numel(), device=dev, dtype=torch.int32)
+        idx, ids = _cached(("blocks", b, v, h, w, bs, div, str(dev)), build)
         n_tiles, m_tile = div * div, b * v * bs * bs
-        ids = torch.arange(idx.numel(), device=dev, dtype=torch.int32)
         if labels is not None:
             lab = labels.reshape(-1)[idx].to(torch.int32)
             fg = (lab != 0).float().view(n_tiles, m_tile)

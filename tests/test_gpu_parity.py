@@ -1331,6 +1331,29 @@ def test_stock_signatures_reach_the_analytic_sweeps_and_stay_safe(api):
     assert torch.isnan(stock(f5.to(dev()), wild.to(dev())))               # `stock` decided "analytic" earlier: guarded
 
 
+@pytest.mark.parametrize("n_class", [None, 0, 4])
+def test_supcon_small_temperature_self_term_stays_finite(api, n_class):
+    """at T = 0.07 the self pair dominates a row's exp-sum; the analytic / self-map paths subtract it after the
+    sweep.  With a moderate number of rows the result must still match the oracle, and in the degenerate case (every other
+    row orthogonal or opposite: the true sum of the others underflows) it must stay finite instead of log(<= 0)."""
+    loss_mod, _ = api
+    gen = cases.g(1717)
+    f5 = F.normalize(torch.randn(1, 2, 32, 8, 8, generator=gen), dim=2)
+    lab = torch.randint(0, 4, (1, 2, 8, 8), generator=gen)
+    ref = O.supcon_loss(f5, lab, 0.07)
+    fd = f5.to(dev()).requires_grad_(True)
+    out = loss_mod.SupConLoss(0.07, n_class=n_class)(fd, lab.to(dev()))
+    out.backward()
+    close(out, ref, rtol=P2P_RTOL)
+    assert torch.isfinite(fd.grad).all()
+    # degenerate: 8 rows = +-e_1 .. +-e_4 (orthogonal or opposite), labels pair up the opposites
+    eye = torch.eye(4)
+    rows = torch.cat([eye, -eye]).reshape(1, 2, 4, 4, 1).permute(0, 1, 3, 2, 4).contiguous()      # [b=1, v=2, c=4, h=4, w=1]
+    labd = torch.tensor([1, 2, 3, 1, 1, 2, 3, 1]).reshape(1, 2, 4, 1)
+    outd = loss_mod.SupConLoss(0.07, n_class=n_class)(rows.to(dev()), labd.to(dev()))
+    assert torch.isfinite(outd)
+
+
 def test_large_one_row_set_problems_take_the_sorted_path(api):
     """>= 8192 rows over one row set: slcl.p2p gathers the rows sorted by label and hands the general sweeps self maps
     (label-uniform tiles on the fast path, no id tests).  SupConLoss (labelled) and ISCL against the oracle."""
