@@ -528,6 +528,8 @@ def run_slcl(args):
         out["cfg4_strong_scaling"] = cfg4
     if mccl is not None:
         mccl["frac_of_hbm_peak"] = mccl["achieved_GBps_per_gpu"] / peak
+        if mccl.get("fused_centroid_losses"):
+            mccl["fused_centroid_losses"]["frac_of_hbm_peak"] = mccl["fused_centroid_losses"]["achieved_GBps_per_gpu"] / peak
         out["mccl_loss_section"] = mccl
     if not args.no_extras and world == 1:
         out["kernels"] = extra_kernels(dev, feats, labels, centres, peak)
@@ -783,6 +785,24 @@ def mccl_loss_section(dev, world, mailbox=None):
 
     step = make_step(ft, pr)
 
+    def make_fused_step(ft, pr):
+        """the same section with the centroid<->centroid terms as ONE op per target map (slcl.loss.mccl_centroid_losses)"""
+        from slcl.loss import mccl_centroid_losses
+
+        def step():
+            cs, _, _ = cal_centroid(ft[0], lab_s, n_class=k, group=group)
+            loss = 0
+            for i in range(2):
+                ct, _, _ = cal_centroid(ft[1 + i], pr[i], pseudo_label=True, weighted_ave=True, partition=parts, n_class=k,
+                                        part_id=part[i], group=group)
+                total, _ = mccl_centroid_losses(cs, ct, None, inter_w=float(parts), intra_w=0.0, cnr_w=4e-5)
+                loss = loss + total
+            loss.backward()
+            for t in ft + pr:
+                t.grad = None
+            return loss.detach()
+        return step
+
     def timed(fn, iters=10):
         for _ in range(3):
             fn()
@@ -820,8 +840,29 @@ def mccl_loss_section(dev, world, mailbox=None):
             loss, how = static_loss, "one CUDA graph (forward + autograd backward captured)"
         except Exception as exc:          # capture is an optimisation of the measurement, not of the product
             print(f"[bench] MCCL section: graph capture unavailable ({exc!r}); reporting the eager time", file=sys.stderr)
+    fused = None
+    if world == 1 or mailbox is not None:
+        try:
+            fstep = make_fused_step([t.detach().requires_grad_(True) for t in ft], [t.detach().requires_grad_(True) for t in pr])
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fstep()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            fgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(fgraph):
+                f_loss = fstep()
+            ms_f, _ = timed(fgraph.replay)
+            fused = {"ms_per_step": ms_f, "loss": float(f_loss),
+                     "what": "same section, centroid<->centroid terms through slcl.loss.mccl_centroid_losses (one op per target "
+                             "map: 2 launches forward, 3 scalings backward), one CUDA graph"}
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] MCCL section (fused losses): unavailable ({exc!r})", file=sys.stderr)
     bytes_ = ((8 * c + 8) + 2 * (12 * c + 12 * k + 8)) * n_px
-    return {"workload": "cfg5 geometry: MCCL loss section (3 x cal_centroid + 4 x ContrastiveLoss + CNR, fwd+bwd) through the "
+    if fused is not None:
+        fused["achieved_GBps_per_gpu"] = bytes_ / (fused["ms_per_step"] * 1e-3) / 1e9
+    return {"fused_centroid_losses": fused, "workload": "cfg5 geometry: MCCL loss section (3 x cal_centroid + 4 x ContrastiveLoss + CNR, fwd+bwd) through the "
                         "Python API inside autograd, per GPU 64 x 32 x 224 x 224, K=4, P=2",
             "ms_per_step": ms, "timed_as": how, "ms_per_step_eager": ms_eager,
             "pixels_per_s": world * 3 * n_px / (ms * 1e-3), "algorithmic_bytes_per_gpu": bytes_,

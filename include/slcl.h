@@ -266,6 +266,18 @@ int slcl_centroid_loss(const float* centroid_s, const float* centroid_t, int n_c
                        int mode, int first_row, int n_rows, int norm,
                        float* loss, float* d_s, float* d_t, slcl_stream_t stream);
 
+/* All centroid <-> centroid terms of one MCCL adaptation step (trainer/Trainer_MCCL.py:303-326) in two launches:
+ *   inter = sum_p ContrastiveLoss(s = S, t = T_p) / P       intra = sum_p ContrastiveLoss(s = T_p, t = A) / P
+ *   cnr   = sum_p MSE(||T_p||, ||S||) / P                    total = inter_w inter + intra_w intra + cnr_w cnr
+ * S = source centroids [K,C], T = the P target-partition centroids [P*K, C] (cal_centroid's output order), A = the
+ * augmented-target centroids [K,C] or null (no intra term).  losses [4] = {total, inter, intra, cnr}; d_s, d_t_parts,
+ * d_t_aug = d total / d S, T, A for d/dtotal = 1.  Same arithmetic per pair as slcl_centroid_loss. */
+size_t slcl_mccl_losses_workspace_bytes(int n_partitions, int n_class, int64_t channels);
+int slcl_mccl_losses(const float* centroid_s, const float* centroid_t_parts, const float* centroid_t_aug,
+                     int n_partitions, int n_class, int64_t channels, int split, int bg, int norm,
+                     float inter_w, float intra_w, float cnr_w, float* losses, float* d_s, float* d_t_parts,
+                     float* d_t_aug, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Sampler: per-class compaction + gather (north_star item 1).
  * slcl_compact_by_class: stable compaction of pixel indices by label, order

@@ -24,10 +24,9 @@ __device__ __forceinline__ float row_dot(const float* a, const float* b, int C, 
   return warp_sum(t);
 }
 
-// mode 0/1: contrastive (plain / split); mode 2: CNR
-__global__ void __launch_bounds__(kThreads) centroid_loss_kernel(const float* __restrict__ s, const float* __restrict__ t,
-                                                                 int K, int C, int mode, int first, int last, int norm,
-                                                                 float* loss, float* d_s, float* d_t) {
+// mode 0/1: contrastive (plain / split); mode 2: CNR.  One thread block; d_s / d_t double as scratch.
+__device__ __forceinline__ void centroid_pair(const float* __restrict__ s, const float* __restrict__ t, int K, int C, int mode,
+                                              int first, int last, int norm, float* loss, float* d_s, float* d_t) {
   __shared__ float ns[KM], nt[KM];          // row norms
   __shared__ float U[KM][KM], V[KM][KM];    // t_hat.s_hat, t_hat.t_hat
   __shared__ float A[KM][KM], B[KM][KM];    // dL/dU, dL/dV
@@ -151,6 +150,59 @@ __global__ void __launch_bounds__(kThreads) centroid_loss_kernel(const float* __
   }
 }
 
+__global__ void __launch_bounds__(kThreads) centroid_loss_kernel(const float* __restrict__ s, const float* __restrict__ t,
+                                                                 int K, int C, int mode, int first, int last, int norm,
+                                                                 float* loss, float* d_s, float* d_t) {
+  centroid_pair(s, t, K, C, mode, first, last, norm, loss, d_s, d_t);
+}
+
+// All centroid <-> centroid terms of one MCCL step (trainer/Trainer_MCCL.py:303-326) in two launches: block i of this
+// kernel evaluates pair i -- for the P target partitions T_p: inter = CL(s = S, t = T_p), intra = CL(s = T_p, t = A),
+// cnr = CNR(S, T_p) -- into scratch {loss_i, ds_i, dt_i}; mccl_combine_kernel then forms the weighted total and the
+// gradients w.r.t. S, every T_p and A (a sum of 2P+... tiny terms per element, fixed order).
+struct McclArgs {
+  const float* S; const float* T; const float* A;     // [K,C], [P*K,C], [K,C] (A may be null: no intra term)
+  int P, K, C, split, first, norm;
+  float inter_w, intra_w, cnr_w;
+  float* scratch;                                      // [3P] x {loss (padded to 4 floats), ds [K*C], dt [K*C]}
+  float* loss; float* dS; float* dT; float* dA;
+};
+__global__ void __launch_bounds__(kThreads) mccl_pairs_kernel(const McclArgs a) {
+  const int i = blockIdx.x, kind = i / a.P, p = i % a.P;
+  const int kc = a.K * a.C;
+  float* out = a.scratch + (size_t)i * (4 + 2 * kc);
+  const float* Tp = a.T + (size_t)p * kc;
+  if (kind == 0) centroid_pair(a.S, Tp, a.K, a.C, a.split ? 1 : 0, a.first, a.K, a.norm, out, out + 4, out + 4 + kc);
+  else if (kind == 1) {
+    if (a.A != nullptr) centroid_pair(Tp, a.A, a.K, a.C, a.split ? 1 : 0, a.first, a.K, a.norm, out, out + 4, out + 4 + kc);
+  } else centroid_pair(a.S, Tp, a.K, a.C, 2, 0, a.K, 0, out, out + 4, out + 4 + kc);
+}
+__global__ void __launch_bounds__(kThreads) mccl_combine_kernel(const McclArgs a) {
+  const int kc = a.K * a.C;
+  const size_t stride = 4 + 2 * (size_t)kc;
+  const float wi = a.inter_w / a.P, wa = (a.A != nullptr) ? a.intra_w / a.P : 0.f, wc = a.cnr_w / a.P;
+  auto slot = [&](int kind, int p) { return a.scratch + (size_t)(kind * a.P + p) * stride; };
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float inter = 0.f, intra = 0.f, cnr = 0.f;
+    for (int p = 0; p < a.P; ++p) { inter += slot(0, p)[0]; if (a.A) intra += slot(1, p)[0]; cnr += slot(2, p)[0]; }
+    a.loss[0] = wi * inter + wa * intra + wc * cnr;
+    a.loss[1] = inter / a.P; a.loss[2] = intra / a.P; a.loss[3] = cnr / a.P;      // the three terms, for logging
+  }
+  for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < kc; idx += gridDim.x * kThreads) {
+    float ds = 0.f, da = 0.f;
+    for (int p = 0; p < a.P; ++p) {
+      const float* in = slot(0, p) + 4;
+      const float* cn = slot(2, p) + 4;
+      ds += wi * in[idx] + wc * cn[idx];
+      float dt = wi * in[kc + idx] + wc * cn[kc + idx];
+      if (a.A != nullptr) { const float* ia = slot(1, p) + 4; dt += wa * ia[idx]; da += wa * ia[kc + idx]; }
+      a.dT[(size_t)p * kc + idx] = dt;
+    }
+    a.dS[idx] = ds;
+    if (a.dA != nullptr) a.dA[idx] = da;
+  }
+}
+
 }  // namespace
 }  // namespace slcl
 
@@ -165,4 +217,31 @@ extern "C" int slcl_centroid_loss(const float* centroid_s, const float* centroid
   centroid_loss_kernel<<<1, kThreads, 0, (cudaStream_t)stream_>>>(centroid_s, centroid_t, n_class, (int)channels, mode,
                                                                  first_row, n_rows, norm, loss, d_s, d_t);
   return check_launch("slcl_centroid_loss");
+}
+
+extern "C" size_t slcl_mccl_losses_workspace_bytes(int n_partitions, int n_class, int64_t channels) {
+  if (n_partitions < 1 || n_class < 1 || channels <= 0) return 0;
+  return align_up((size_t)3 * n_partitions * (4 + 2 * (size_t)n_class * channels) * sizeof(float), 256);
+}
+
+extern "C" int slcl_mccl_losses(const float* centroid_s, const float* centroid_t_parts, const float* centroid_t_aug,
+                                int n_partitions, int n_class, int64_t channels, int split, int bg, int norm,
+                                float inter_w, float intra_w, float cnr_w, float* losses, float* d_s, float* d_t_parts,
+                                float* d_t_aug, void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!centroid_s || !centroid_t_parts || !losses || !d_s || !d_t_parts || !workspace) return SLCL_ERR_INVALID_ARGUMENT;
+  if ((centroid_t_aug == nullptr) != (d_t_aug == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_partitions < 1 || n_partitions > 16 || n_class < 1 || n_class > KM || channels <= 0) return SLCL_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < slcl_mccl_losses_workspace_bytes(n_partitions, n_class, channels) || !aligned16(workspace))
+    return SLCL_ERR_WORKSPACE;
+  McclArgs a{};
+  a.S = centroid_s; a.T = centroid_t_parts; a.A = centroid_t_aug;
+  a.P = n_partitions; a.K = n_class; a.C = (int)channels; a.split = split; a.first = bg ? 0 : 1; a.norm = norm;
+  a.inter_w = inter_w; a.intra_w = intra_w; a.cnr_w = cnr_w;
+  a.scratch = reinterpret_cast<float*>(workspace);
+  a.loss = losses; a.dS = d_s; a.dT = d_t_parts; a.dA = d_t_aug;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  mccl_pairs_kernel<<<3 * n_partitions, kThreads, 0, stream>>>(a);
+  const int kc = n_class * (int)channels;
+  mccl_combine_kernel<<<ceil_div(kc, kThreads) < 8 ? ceil_div(kc, kThreads) : 8, kThreads, 0, stream>>>(a);
+  return check_launch("slcl_mccl_losses");
 }

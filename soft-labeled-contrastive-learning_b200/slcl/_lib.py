@@ -82,6 +82,9 @@ SIGNATURES = {
     "slcl_centroid_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.c_float, _P, C.c_int, C.c_int, _P, _P,
                                     C.c_float, _P, _P, _P, _SZ, _P]),
     "slcl_centroid_loss": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "slcl_mccl_losses_workspace_bytes": (_SZ, [C.c_int, C.c_int, _I64]),
+    "slcl_mccl_losses": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _I64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                   _P, _P, _P, _P, _P, _SZ, _P]),
     "slcl_compact_workspace_bytes": (_SZ, [_I64, C.c_int]),
     "slcl_compact_by_class": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P, _SZ, _P]),
     "slcl_gather_unit_rows": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _I64, _P, _P, _P]),

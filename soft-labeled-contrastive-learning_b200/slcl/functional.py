@@ -237,3 +237,30 @@ class _CentroidLoss(torch.autograd.Function):
 
 def centroid_loss(cs: Tensor, ct: Tensor, *, mode: int, first_row: int, n_rows: int, norm: bool) -> Tensor:
     return _CentroidLoss.apply(cs, ct, mode, first_row, n_rows, norm)
+
+
+class _McclLosses(torch.autograd.Function):
+    """inter / intra ContrastiveLoss over the target partitions + CNR (trainer/Trainer_MCCL.py:303-326) as one op: the
+    forward also produces every gradient (appendix A.5), the backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, cs, ct_parts, ct_aug, n_partitions, split, bg, norm, inter_w, intra_w, cnr_w):
+        losses, ds, dt, da = _ops.mccl_losses(cs.detach(), ct_parts.detach(), None if ct_aug is None else ct_aug.detach(),
+                                              n_partitions, split, bg, norm, inter_w, intra_w, cnr_w)
+        ctx.save_for_backward(ds, dt, da)
+        ctx.has_aug = ct_aug is not None
+        terms = losses[1:].detach()
+        ctx.mark_non_differentiable(terms)
+        return losses[0], terms
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        ds, dt, da = ctx.saved_tensors
+        return (g * ds if ctx.needs_input_grad[0] else None, g * dt if ctx.needs_input_grad[1] else None,
+                g * da if (ctx.has_aug and ctx.needs_input_grad[2]) else None, None, None, None, None, None, None, None)
+
+
+def mccl_losses(cs: Tensor, ct_parts: Tensor, ct_aug: Optional[Tensor], *, n_partitions: int, split: bool, bg: bool, norm: bool,
+                inter_w: float, intra_w: float, cnr_w: float):
+    return _McclLosses.apply(cs, ct_parts, ct_aug, int(n_partitions), bool(split), bool(bg), bool(norm), float(inter_w),
+                             float(intra_w), float(cnr_w))

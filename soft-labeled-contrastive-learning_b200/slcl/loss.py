@@ -162,6 +162,26 @@ def cnr_loss(centroid_s, centroid_t_list):
     return total
 
 
+def mccl_centroid_losses(centroid_s, centroid_t, centroid_t_aug=None, inter_w=1.0, intra_w=1.0, cnr_w=4e-5, split=False, bg=False,
+                         norm=True):
+    """Every centroid <-> centroid term of one MCCL adaptation step (trainer/Trainer_MCCL.py:303-326) in ONE op (an
+    addition; the drop-in ``ContrastiveLoss`` / ``cnr_loss`` calls stay available and give the same numbers):
+
+        inter = sum_p ContrastiveLoss()(centroid_s, centroid_t[p], split=split) / P
+        intra = sum_p ContrastiveLoss()(centroid_t[p], centroid_t_aug, split=split) / P        (if centroid_t_aug is given)
+        cnr   = sum_p MSE(||centroid_t[p]||, ||centroid_s||) / P
+        total = inter_w * inter + intra_w * intra + cnr_w * cnr
+
+    ``centroid_t``: the list of P ``[K,C]`` tensors ``cal_centroid(..., partition=P)`` returns (or one tensor).  Returns
+    ``(total, terms)`` with ``terms = [inter, intra, cnr]`` detached for logging.  Two kernel launches forward (all pairs in
+    parallel blocks, then the weighted combination and ALL gradients), three small scalings backward -- instead of ~60."""
+    if isinstance(centroid_t, torch.Tensor):
+        centroid_t = [centroid_t]
+    parts = torch.cat(list(centroid_t), dim=0) if len(centroid_t) > 1 else centroid_t[0]
+    return SF.mccl_losses(centroid_s, parts, centroid_t_aug, n_partitions=len(centroid_t), split=split, bg=bg, norm=norm,
+                          inter_w=inter_w, intra_w=intra_w, cnr_w=cnr_w)
+
+
 SupConLoss = p2p.SupConLoss
 LocalConLoss = p2p.LocalConLoss
 BlockConLoss = p2p.BlockConLoss

@@ -560,6 +560,41 @@ def _(centroid_s, centroid_t, mode, first_row, n_rows, norm):
     return centroid_s.new_empty(1), torch.empty_like(centroid_s), torch.empty_like(centroid_t)
 
 
+@torch.library.custom_op("slcl::mccl_losses", mutates_args=(), device_types="cuda")
+def mccl_losses(centroid_s: Tensor, centroid_t_parts: Tensor, centroid_t_aug: Optional[Tensor], n_partitions: int, split: bool,
+                bg: bool, norm: bool, inter_w: float, intra_w: float, cnr_w: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """All centroid<->centroid terms of one MCCL step in two launches.
+    -> (losses[4] = {total, inter, intra, cnr}, d total/d S [K,C], d total/d T [P*K,C], d total/d A [K,C] (empty without A))."""
+    dev = require_cuda(centroid_s, centroid_t_parts, centroid_t_aug)
+    lib = _lib.load()
+    s = centroid_s.to(_F32).contiguous()
+    t = centroid_t_parts.to(_F32).contiguous()
+    k, c = s.shape
+    if t.shape != (n_partitions * k, c):
+        raise ValueError("centroid_t_parts must be [P*K, C]")
+    a = None
+    if centroid_t_aug is not None:
+        a = centroid_t_aug.to(_F32).contiguous()
+        if a.shape != (k, c):
+            raise ValueError("centroid_t_aug must be [K, C]")
+    losses = torch.empty(4, dtype=_F32, device=dev)
+    ds, dt = torch.empty_like(s), torch.empty_like(t)
+    da = torch.empty_like(s) if a is not None else torch.empty(0, dtype=_F32, device=dev)
+    ws = _ws(lib.slcl_mccl_losses_workspace_bytes(n_partitions, k, c), dev)
+    with _guard(dev):
+        st = lib.slcl_mccl_losses(ptr(s), ptr(t), ptr(a), n_partitions, k, c, int(split), int(bg), int(norm), float(inter_w),
+                                  float(intra_w), float(cnr_w), ptr(losses), ptr(ds), ptr(dt), ptr(da) if a is not None else None,
+                                  ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_mccl_losses")
+    return losses, ds, dt, da
+
+
+@mccl_losses.register_fake
+def _(centroid_s, centroid_t_parts, centroid_t_aug, n_partitions, split, bg, norm, inter_w, intra_w, cnr_w):
+    da = torch.empty_like(centroid_s) if centroid_t_aug is not None else centroid_s.new_empty(0)
+    return centroid_s.new_empty(4), torch.empty_like(centroid_s), torch.empty_like(centroid_t_parts), da
+
+
 # ----------------------------------------------------------------------------
 # sampler
 # ----------------------------------------------------------------------------

@@ -364,6 +364,38 @@ def test_kat4_contrastive_loss_and_cnr(api, golden):
 # ---------------------------------------------------------------------------
 # sampler
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("parts,split,with_aug,k,c", [(2, False, True, 4, 32), (1, True, True, 4, 32), (3, False, False, 4, 48),
+                                                      (2, True, True, 5, 128)])
+def test_fused_mccl_centroid_losses_equal_the_drop_in_calls(api, parts, split, with_aug, k, c):
+    """mccl_centroid_losses (one op, two launches) == the trainer's own loop over ContrastiveLoss / CNR
+    (trainer/Trainer_MCCL.py:303-326) built from the drop-in modules, values and gradients."""
+    loss_mod, _ = api
+    g = cases.g(parts * 10 + k)
+    cs = torch.randn(k, c, generator=g).to(dev())
+    cts = [torch.randn(k, c, generator=g).to(dev()) for _ in range(parts)]
+    ca = torch.randn(k, c, generator=g).to(dev()) if with_aug else None
+    crit = loss_mod.ContrastiveLoss()
+
+    def leaves():
+        return (cs.clone().requires_grad_(True), [t.clone().requires_grad_(True) for t in cts],
+                ca.clone().requires_grad_(True) if with_aug else None)
+    s1, t1, a1 = leaves()
+    inter = sum(crit(s1, t, split=split) for t in t1) / parts
+    intra = sum(crit(t, a1, split=split) for t in t1) / parts if with_aug else 0.0
+    ref = 0.7 * inter + 0.3 * intra + 4e-5 * loss_mod.cnr_loss(s1, t1)
+    ref.backward()
+    s2, t2, a2 = leaves()
+    out, terms = loss_mod.mccl_centroid_losses(s2, t2, a2, inter_w=0.7, intra_w=0.3, cnr_w=4e-5, split=split)
+    out.backward()
+    close(out, ref, rtol=1e-5)
+    close(terms[0], inter, rtol=1e-5)
+    grad_close(s2.grad, s1.grad, rtol=1e-5)
+    for x, y in zip(t2, t1):
+        grad_close(x.grad, y.grad, rtol=1e-5)
+    if with_aug:
+        grad_close(a2.grad, a1.grad, rtol=1e-5)
+
+
 @pytest.mark.parametrize("n,k", [(1, 4), (255, 4), (4096, 5), (4097, 5), (100003, 8)])
 def test_compaction_bit_exact_with_nonzero(n, k):
     gen = cases.g(n + k)
