@@ -329,15 +329,18 @@ def run_slcl(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
         if float(ok) < 1.0:
             mailbox = None
-        exchange_how = ("loss pair exchanged INSIDE the forward's finaliser kernel over NVLink peer memory (8-byte {epoch|fp32} "
-                        "stores into every peer's mailbox; no launch between forward and backward)") if mailbox is not None \
+        exchange_how = ("split-phase exchange over NVLink peer memory: the forward's finaliser kernel stores this rank's 8-byte "
+                        "{epoch|fp32} words into every peer's mailbox, the backward kernel receives them (block 0) -- no launch "
+                        "between forward and backward, latency hidden behind the backward's launch") if mailbox is not None \
             else f"NCCL all-reduce of 8 bytes + rescale kernel ({why})"
 
     def step(record: bool):
         e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
         if record:
             e0.record()
-        scal = plan.forward(mailbox)          # N > 1 with mailboxes: the finaliser kernel exchanges the loss pair itself
+        # N > 1 with mailboxes: split-phase exchange -- the forward's finaliser sends this rank's {weight sum, loss sum},
+        # the backward kernel receives (block 0) while its other blocks already stream: no launch, no exposed latency
+        scal = plan.forward(mailbox, split_phase=True)
         if record:
             e1.record()
         if mailbox is None and world > 1:
@@ -345,7 +348,7 @@ def run_slcl(args):
             plan.rescale()
         if record:
             e2.record()
-        dfeat = plan.backward()
+        dfeat = plan.backward(mailbox)
         if record:
             e3.record()
             marks.append((e0, e1, e2, e3))
@@ -679,11 +682,11 @@ def cfg4_strong_scaling(dev, world, rank, mailbox=None):
     group = (mailbox if mailbox is not None else True) if world > 1 else None
 
     def proto_step():
-        scal = plan.forward(mailbox)
+        scal = plan.forward(mailbox, split_phase=True)
         if mailbox is None and world > 1:
             dist.all_reduce(scal[2:4], op=dist.ReduceOp.SUM)
             plan.rescale()
-        plan.backward()
+        plan.backward(mailbox)
         return scal
 
     def ema_step():

@@ -143,8 +143,16 @@ int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t* peer, slc
 int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map,
                         const int64_t* labels, const float* soft_mask, const float* sel,
                         const float* centres, const slcl_proto_params_t* params,
-                        float* stash, float* cstate, float* scal, const slcl_peer_t* peer,
+                        float* stash, float* cstate, float* scal, const slcl_peer_t* peer, int split_phase,
                         void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+/* split_phase != 0 (fused forward + backward steps that read the loss only afterwards): the forward's finaliser only
+ * SENDS this rank's pair; the matching slcl_proto_bwd_peer call -- same mailboxes, same stream, MUST follow -- receives,
+ * adds and rewrites scal (block 0) while its other blocks already stream their first loads, so the exchange latency
+ * hides behind the backward's launch and prologue.  scal[0] (the global loss) is valid after that backward. */
+int slcl_proto_bwd_peer(const float* feat, const slcl_map_t* map,
+                        const float* stash, const float* cstate, float* scal, const float* grad_out,
+                        const slcl_proto_params_t* params, float* dfeat,
+                        const slcl_peer_t* peer, int has_sel, slcl_stream_t stream);
 int slcl_proto_fwd_target_peer(const float* feat, const slcl_map_t* map, const float* centres,
                                const slcl_proto_params_t* params, float sel_threshold,
                                int64_t* label, float* sel, float* stash, float* cstate, float* scal,

@@ -7,7 +7,9 @@
 //   word 0  epoch    : number of exchange calls this rank has completed (only its own kernels write it)
 //   word 1  timeouts : number of polls that gave up (diagnostic; a timed-out value is NaN)
 //   word 2  ticket   : block counter of a multi-block exchange kernel (self-resetting)
-//   word 3..7        : reserved
+//   word 3  ready    : split-phase exchanges: the epoch whose result this rank has published to its own blocks
+//   word 4  pending  : split-phase exchanges: the epoch a sender kernel has put on the wire and a later kernel completes
+//   word 5..7        : reserved
 //   word 8 + (q * world + r) * capacity + s : payload word s of sender r for epoch parity q
 // A payload word is {epoch : 32 | data : 32}: an aligned 8-byte store is single-copy atomic, so flag and data arrive
 // together and no fence is needed (the protocol NCCL calls LL).  A call with epoch e writes its words into every
@@ -66,6 +68,28 @@ __device__ __forceinline__ bool peer_epoch_end(const PeerCtx& c, unsigned int e,
   __threadfence();
   *reinterpret_cast<volatile unsigned long long*>(mine) = (unsigned long long)e;
   return true;
+}
+
+// Split-phase halves of peer_send_recv: a producer kernel only SENDS (and records the epoch in word 4), a later kernel
+// on the same stream RECEIVES -- the wire latency then hides behind whatever runs in between (launch, prologue, loads).
+__device__ __forceinline__ void peer_send(const PeerCtx& c, unsigned int e, int peer, long long s, unsigned int data) {
+  volatile unsigned long long* dst = peer_slot(c.boxes[peer], c, e & 1u, c.rank, s);
+  *dst = ((unsigned long long)e << 32) | (unsigned long long)data;
+}
+__device__ __forceinline__ unsigned int peer_recv(const PeerCtx& c, unsigned int e, int peer, long long s, bool& ok) {
+  volatile unsigned long long* src = peer_slot(c.boxes[c.rank], c, e & 1u, peer, s);
+  unsigned long long t0 = 0ull, now, got;
+  ok = true;
+  for (unsigned int spin = 0;; ++spin) {
+    got = *src;
+    if ((unsigned int)(got >> 32) == e) break;
+    if (c.timeout_ns != 0ull && (spin & 63u) == 63u) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > c.timeout_ns) { atomicAdd(c.boxes[c.rank] + 1, 1ull); ok = false; break; }
+    }
+  }
+  return (unsigned int)got;
 }
 
 // Send one 32-bit word to `dst_rank` (payload slot s) and return the word `src_rank` sent to us in slot s.

@@ -268,8 +268,10 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
 // Data-parallel (pc.world > 1): the pair {weight sum, weighted row-loss sum} is exchanged with the other ranks right
 // here, through the NVLink peer mailboxes (peer.cuh) -- the same words slcl_proto_rescale_peer would send, added in the
 // same rank order -- so the forward needs no extra launch (and no collective) to return the GLOBAL loss.
+// split != 0: SEND only -- scal[2..3] keep the LOCAL pair, the epoch goes to mailbox word 4, and proto_bwd_kernel
+// (launched with the same mailboxes) receives, adds and publishes: the exchange latency hides behind its launch + prologue.
 __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2* partial, int n_blocks, int64_t n_total,
-                                                                   int has_sel, float* scal, const PeerCtx pc) {
+                                                                   int has_sel, float* scal, const PeerCtx pc, int split) {
   pdl_trigger();
   pdl_wait();
   __shared__ double red[2][kThreads / 32];
@@ -291,7 +293,12 @@ __global__ void __launch_bounds__(kThreads) proto_finalize_kernel(const double2*
   }
   __syncthreads();
   float wsum = s_pair[0], lsum = s_pair[1];
-  if (pc.world > 1) {
+  if (pc.world > 1 && split) {
+    const unsigned int e = peer_epoch_begin(pc);
+    const int t = threadIdx.x;
+    if (t < 2 * pc.world) peer_send(pc, e, t >> 1, t & 1, __float_as_uint(s_pair[t & 1]));
+    if (t == 0) pc.boxes[pc.rank][4] = (unsigned long long)e;           // pending: completed by the backward kernel
+  } else if (pc.world > 1) {
     const unsigned int e = peer_epoch_begin(pc);
     const int t = threadIdx.x;
     if (t < 2 * pc.world) {
@@ -379,17 +386,49 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* buf, lo
 // backward: dF = gamma * ( sum_k a_k chat_k - b x )
 // ---------------------------------------------------------------------------
 template <int K, int VEC>
-__global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_BWD_MINBLK : 1) proto_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
-                                                             float* dfeat) {
+__global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_BWD_MINBLK : 1) proto_bwd_kernel(const ProtoArgs a, float* scal, const float* grad_out,
+                                                             float* dfeat, const PeerCtx pc, int has_sel) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float sC[];
+  __shared__ float s_coef;
+  __shared__ float s_vals[2 * kMaxPeers];
   const int C = (int)a.channels;
   load_centres_smem<K>(sC, a.cstate, C);
+  if (pc.world > 1) {
+    // second half of a split-phase exchange (proto_finalize_kernel sent this rank's pair and left the epoch in word 4):
+    // block 0 receives every rank's pair, adds in rank order, rewrites scal and publishes the epoch in word 3; the other
+    // blocks wait for that word.  By now the wire latency has been overlapped with this kernel's launch and prologue.
+    unsigned long long* mine = pc.boxes[pc.rank];
+    const unsigned int e = (unsigned int)(*reinterpret_cast<volatile unsigned long long*>(mine + 4));
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0) {
+      bool ok = true;
+      if (t < 2 * pc.world) s_vals[t] = __uint_as_float(peer_recv(pc, e, t >> 1, t & 1, ok));
+      const int bad = __syncthreads_or(!ok);
+      if (t == 0) {
+        float wsum = 0.f, lsum = 0.f;
+        for (int r = 0; r < pc.world; ++r) { wsum += s_vals[2 * r]; lsum += s_vals[2 * r + 1]; }
+        if (bad) { wsum = __uint_as_float(0x7FC00000u); lsum = wsum; }
+        const float coef = has_sel ? 1.0f / (wsum + 1e-4f) : 1.0f / wsum;
+        scal[0] = lsum * coef; scal[1] = coef; scal[2] = wsum; scal[3] = lsum;
+        s_coef = coef;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long*>(mine + 3) = (unsigned long long)e;       // ready
+        peer_epoch_end(pc, e, 1u);
+      }
+    } else if (t == 0) {
+      while ((unsigned int)(*reinterpret_cast<volatile unsigned long long*>(mine + 3)) != e) { }
+      __threadfence();
+      s_coef = *reinterpret_cast<volatile float*>(scal + 1);
+    }
+  } else if (threadIdx.x == 0) {
+    s_coef = scal[1];
+  }
   __syncthreads();
   int64_t pix, off;
   if (!locate<VEC>(a, pix, off)) return;
-  const float gamma = grad_out[0] * scal[1];
+  const float gamma = grad_out[0] * s_coef;
   float coef[K + 1][VEC];
 #pragma unroll
   for (int k = 0; k <= K; ++k) {
@@ -594,7 +633,7 @@ void launch_prep_centres(const float* centres, int C, int K, int normalize, floa
 void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal,
                            const slcl_peer_t* peer, cudaStream_t stream) {
   launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, reinterpret_cast<const double2*>(partial), n_blocks,
-             n_total, has_sel, scal, peer_ctx(peer));
+             n_total, has_sel, scal, peer_ctx(peer), 0);
 }
 }  // namespace slcl
 
@@ -607,7 +646,7 @@ extern "C" size_t slcl_proto_workspace_bytes(int64_t n_pixels) {
 
 extern "C" int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
                                    const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
-                                   float* cstate, float* scal, const slcl_peer_t* peer, void* workspace,
+                                   float* cstate, float* scal, const slcl_peer_t* peer, int split_phase, void* workspace,
                                    size_t workspace_bytes, slcl_stream_t stream_) {
   if (!feat || !validate_map(map) || !centres || !params || !stash || !cstate || !scal || !workspace)
     return SLCL_ERR_INVALID_ARGUMENT;
@@ -632,7 +671,7 @@ extern "C" int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map, con
     if (st != SLCL_OK) return st;
     launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, (int)(sel != nullptr), scal, peer_ctx(peer));
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, (int)(sel != nullptr), scal, peer_ctx(peer), split_phase);
   return check_launch("slcl_proto_fwd");
 }
 
@@ -640,7 +679,7 @@ extern "C" int slcl_proto_fwd(const float* feat, const slcl_map_t* map, const in
                               const float* sel, const float* centres, const slcl_proto_params_t* params, float* stash,
                               float* cstate, float* scal, void* workspace, size_t workspace_bytes,
                               slcl_stream_t stream_) {
-  return slcl_proto_fwd_peer(feat, map, labels, soft_mask, sel, centres, params, stash, cstate, scal, nullptr, workspace,
+  return slcl_proto_fwd_peer(feat, map, labels, soft_mask, sel, centres, params, stash, cstate, scal, nullptr, 0, workspace,
                              workspace_bytes, stream_);
 }
 
@@ -669,7 +708,7 @@ extern "C" int slcl_proto_fwd_target_peer(const float* feat, const slcl_map_t* m
     if (st != SLCL_OK) return st;
     launch_pdl(proto_fwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a);
   })
-  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, 1, scal, peer_ctx(peer));
+  launch_pdl(proto_finalize_kernel, dim3(1), dim3(kThreads), 0, stream, (const double2*)a.partial, plan.n_blocks, plan.n_total, 1, scal, peer_ctx(peer), 0);
   return check_launch("slcl_proto_fwd_target");
 }
 
@@ -705,11 +744,12 @@ extern "C" int slcl_peer_allreduce_f64(double* buf, int64_t n, const slcl_peer_t
   return check_launch("slcl_peer_allreduce_f64");
 }
 
-extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,
-                              const float* scal, const float* grad_out, const slcl_proto_params_t* params,
-                              float* dfeat, slcl_stream_t stream_) {
+extern "C" int slcl_proto_bwd_peer(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,
+                                   float* scal, const float* grad_out, const slcl_proto_params_t* params, float* dfeat,
+                                   const slcl_peer_t* peer, int has_sel, slcl_stream_t stream_) {
   if (!feat || !validate_map(map) || !stash || !cstate || !scal || !grad_out || !params || !dfeat)
     return SLCL_ERR_INVALID_ARGUMENT;
+  if (peer != nullptr && !peer_valid(peer)) return SLCL_ERR_INVALID_ARGUMENT;
   const int K = params->n_class;
   if (K < 2 || K > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -720,9 +760,16 @@ extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const fl
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(proto_bwd_kernel<KK, VV>, plan.smem);
     if (st != SLCL_OK) return st;
-    launch_pdl(proto_bwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a, scal, grad_out, dfeat);
+    launch_pdl(proto_bwd_kernel<KK, VV>, dim3(plan.n_blocks), dim3(kThreads), plan.smem, stream, a, const_cast<float*>(scal),
+               grad_out, dfeat, peer_ctx(peer), has_sel);
   })
   return check_launch("slcl_proto_bwd");
+}
+
+extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,
+                              const float* scal, const float* grad_out, const slcl_proto_params_t* params,
+                              float* dfeat, slcl_stream_t stream_) {
+  return slcl_proto_bwd_peer(feat, map, stash, cstate, const_cast<float*>(scal), grad_out, params, dfeat, nullptr, 0, stream_);
 }
 
 extern "C" int slcl_pseudo_label(const float* feat, const slcl_map_t* map, const float* centres, int n_class,

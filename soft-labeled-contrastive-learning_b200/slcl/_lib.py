@@ -54,8 +54,10 @@ SIGNATURES = {
     "slcl_last_cuda_error": (C.c_char_p, []),
     "slcl_proto_workspace_bytes": (_SZ, [_I64]),
     "slcl_proto_fwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, _P, _SZ, _P]),
-    "slcl_proto_fwd_peer": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, C.POINTER(PeerT), _P,
-                                      _SZ, _P]),
+    "slcl_proto_fwd_peer": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P, C.POINTER(PeerT),
+                                      C.c_int, _P, _SZ, _P]),
+    "slcl_proto_bwd_peer": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, C.POINTER(PeerT), C.c_int,
+                                      _P]),
     "slcl_proto_fwd_target_peer": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P,
                                              C.POINTER(PeerT), _P, _SZ, _P]),
     "slcl_proto_fwd_target": (C.c_int, [_P, C.POINTER(MapT), _P, C.POINTER(ProtoParamsT), C.c_float, _P, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -116,7 +116,7 @@ def proto_fwd(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor
     peer = _peer(peer_ptrs, rank, world, capacity_words, timeout_s)
     with _guard(dev):
         st = lib.slcl_proto_fwd_peer(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(centres), C.byref(p),
-                                     ptr(stash), ptr(cstate), ptr(scal), C.byref(peer) if peer is not None else None, ptr(ws),
+                                     ptr(stash), ptr(cstate), ptr(scal), C.byref(peer) if peer is not None else None, 0, ptr(ws),
                                      ws.numel(), stream_ptr(dev))
     check(st, "slcl_proto_fwd")
     return scal, stash, cstate

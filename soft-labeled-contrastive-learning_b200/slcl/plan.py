@@ -58,13 +58,16 @@ class ProtoPlan:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def forward(self, mailbox=None) -> torch.Tensor:
+    def forward(self, mailbox=None, split_phase: bool = False) -> torch.Tensor:
         """Launch the forward; returns scal (scal[0] is the loss).  Asynchronous.  With ``mailbox`` (slcl.peer.PeerMailbox,
         more than one rank) the finaliser kernel exchanges the loss pair with the other ranks: scal is then GLOBAL and
-        neither ``rescale()`` nor ``rescale_peer()`` is needed before ``backward()``."""
+        neither ``rescale()`` nor ``rescale_peer()`` is needed before ``backward()``.
+
+        ``split_phase=True``: the finaliser only SENDS; ``backward(mailbox)`` -- which MUST be the next use of the mailbox
+        -- receives, so the exchange latency hides behind the backward's launch; scal is global after that backward."""
         if mailbox is not None and mailbox.world > 1:
             peer = mailbox.struct()
-            args = self._fwd_args[:10] + (C.byref(peer),) + self._fwd_args[10:]
+            args = self._fwd_args[:10] + (C.byref(peer), int(split_phase)) + self._fwd_args[10:]
             check(self.lib.slcl_proto_fwd_peer(*args, self._stream()), "slcl_proto_fwd_peer")
         else:
             check(self.lib.slcl_proto_fwd(*self._fwd_args, self._stream()), "slcl_proto_fwd")
@@ -80,9 +83,15 @@ class ProtoPlan:
         check(self.lib.slcl_proto_rescale_peer(ptr(self.scal), int(self.sel is not None), C.byref(peer), self._stream()),
               "slcl_proto_rescale_peer")
 
-    def backward(self) -> torch.Tensor:
-        """Launch the backward for dL/dloss = grad_out (device scalar, default 1); returns dfeat."""
-        check(self.lib.slcl_proto_bwd(*self._bwd_args, self._stream()), "slcl_proto_bwd")
+    def backward(self, mailbox=None) -> torch.Tensor:
+        """Launch the backward for dL/dloss = grad_out (device scalar, default 1); returns dfeat.  ``mailbox``: completes a
+        ``forward(mailbox, split_phase=True)``."""
+        if mailbox is not None and mailbox.world > 1:
+            peer = mailbox.struct()
+            check(self.lib.slcl_proto_bwd_peer(*self._bwd_args, C.byref(peer), int(self.sel is not None), self._stream()),
+                  "slcl_proto_bwd_peer")
+        else:
+            check(self.lib.slcl_proto_bwd(*self._bwd_args, self._stream()), "slcl_proto_bwd")
         return self.dfeat
 
     def capture_graph(self) -> "torch.cuda.CUDAGraph":

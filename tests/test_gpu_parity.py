@@ -1108,6 +1108,40 @@ def test_sharded_prototype_loss_and_target_step_equal_global(api, world):
         grad_close(res[r][1], sl(fg.grad, r), rtol=1e-5)
 
 
+@pytest.mark.parametrize("world,with_sel", [(2, True), (4, False)])
+def test_split_phase_exchange_plan_equals_global(world, with_sel):
+    """ProtoPlan.forward(mailbox, split_phase=True) + backward(mailbox): the finaliser only sends, the backward kernel
+    receives (block 0) and publishes to its other blocks.  Ranks = streams of one GPU; result must equal the global batch,
+    over several steps (epoch parities, ready/pending words)."""
+    from slcl.peer import LoopbackMailboxes
+    from slcl.plan import ProtoPlan
+    b, c, h, w, k = 2 * world, 32, 32, 24, 4
+    g = cases.g(61 + world)
+    feat = torch.randn(b, c, h, w, generator=g).to(dev())
+    lab = torch.randint(0, k, (b * h * w,), generator=g).to(dev())
+    sel = (torch.rand(b * h * w, generator=g) > 0.4).float().to(dev()) if with_sel else None
+    cen = torch.randn(k, c, generator=g).to(dev())
+    whole = ProtoPlan(feat, lab, sel, cen, k, .1, 1.0, .4)
+    whole.forward(); whole.backward()
+    torch.cuda.synchronize()
+    per = b // world
+    hw = h * w
+    plans = [ProtoPlan(feat[r * per:(r + 1) * per].contiguous(), lab[r * per * hw:(r + 1) * per * hw].contiguous(),
+                       None if sel is None else sel[r * per * hw:(r + 1) * per * hw].contiguous(), cen, k, .1, 1.0, .4)
+             for r in range(world)]
+    boxes = LoopbackMailboxes(world, dev()).boxes
+    streams = _rank_streams(world)
+    for step in range(3):
+        _on_streams(streams, lambda r: (plans[r].forward(boxes[r], split_phase=True), plans[r].backward(boxes[r])))
+        torch.cuda.synchronize()
+        for r in range(world):
+            close(plans[r].scal[0], whole.scal[0], rtol=1e-6, atol=0)
+            close(plans[r].scal[2], whole.scal[2], rtol=1e-6, atol=0)
+            grad_close(plans[r].dfeat, whole.dfeat[r * per:(r + 1) * per], rtol=1e-5)
+            assert torch.equal(plans[r].scal, plans[0].scal)
+    assert all(bx.epoch() == 3 and bx.timeouts() == 0 for bx in boxes)
+
+
 def test_c_abi_called_directly_with_ctypes():
     """The INTEGRATION.md stub: raw ctypes against include/slcl.h, no torch custom-op layer in between."""
     import ctypes as C
