@@ -988,6 +988,24 @@ def extra_kernels(dev, feats, labels, centres, peak):
         plan4.backward()
     add("cfg4 shape per GPU: prototype loss fwd+bwd, 16 x 32 x 224 x 224, K4", timed(proto4, iters=20),
         (12 * c5 + 24) * 16 * h5 * h5)
+    # f-1 source side at the same shape: update_class_center_iter + source loss forward + backward as ONE call
+    # (slcl.loss.mpcl_source_step), replayed as a CUDA graph; three walks over a 98 MiB map that fits in L2 (zig-zag walk
+    # order + evict_last forward: ncu counts 194 MB of DRAM reads for the step instead of 3.4 maps, profiles/README.md)
+    try:
+        from slcl.loss import MPCL as _MPCL, mpcl_source_step as _src_step
+        f4g = f4.clone().requires_grad_(True)
+        lab4m = lab4.view(16, h5, h5)
+        mp4 = _MPCL(dev, num_class=k5, temperature=CFG["temperature"], m=0.4, base_temperature=CFG["base_temperature"])
+
+        def src_step():
+            _, l4 = _src_step(f4g, lab4m, cen4, mp4, m=0.9, num_class=k5)
+            l4.backward()
+            f4g.grad = None
+        add("cfg4 shape per GPU: source step (EMA class centres + source loss fwd+bwd, one call), one CUDA graph",
+            timed_graph(src_step, iters=30), (16 * c5 + 32) * 16 * h5 * h5)
+        del f4g
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] source step: unavailable ({exc!r})", file=sys.stderr)
     del f4, lab4, sel4, cen4, plan4
     res["cfg1: prototype loss fwd+bwd, source variant, B8 C128 33x33 K5 (configs[0], the reference's CPU-runnable case)"] = \
         cfg1_line(dev, timed)
@@ -1113,6 +1131,32 @@ def p2p_kernels(dev, gen):
     out["cfg3 through the public API: sampled_supcon_loss (draw + compaction + gather + sweeps + scatter), fwd+bwd, eager"] = {
         "ms": ms, "algorithmic_flop": 8.0 * A * M * d, "achieved_TFLOPs": 8.0 * A * M * d / (ms * 1e-3) / 1e12,
         "frac_of_bf16_peak": 8.0 * A * M * d / (ms * 1e-3) / 1e12 / tf_peak, "rows_per_s": (A + M) / (ms * 1e-3)}
+    try:        # nothing in that call synchronises, so the whole public-API step can be replayed as ONE CUDA graph
+        fmap_g = fmap.detach().clone().requires_grad_(True)
+        gen_g = torch.Generator(device=dev).manual_seed(77)
+
+        def api_step_g():
+            loss_s = sampled_supcon_loss(fmap_g, lmap, A, M, 5, temperature=T, generator=gen_g)
+            loss_s.backward()
+            fmap_g.grad = None
+            return loss_s.detach()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            api_step_g()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g_api = torch.cuda.CUDAGraph()
+        g_api.register_generator_state(gen_g)
+        with torch.cuda.graph(g_api):
+            keep_api = api_step_g()          # noqa: F841
+        ms = timed(g_api.replay, iters=10)
+        out["cfg3 through the public API: the same sampled_supcon_loss step (incl. the draw) replayed as one CUDA graph"] = {
+            "ms": ms, "algorithmic_flop": 8.0 * A * M * d, "achieved_TFLOPs": 8.0 * A * M * d / (ms * 1e-3) / 1e12,
+            "frac_of_bf16_peak": 8.0 * A * M * d / (ms * 1e-3) / 1e12 / tf_peak, "rows_per_s": (A + M) / (ms * 1e-3)}
+        del g_api, keep_api, fmap_g
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] sampled_supcon_loss: graph capture unavailable ({exc!r})", file=sys.stderr)
     del fmap, lmap
     # BlockConLoss at the reference's documented shape (1, 2, 32, 224, 224), 32 x 32 tiles: 49 tiles of 2048 rows as ONE
     # block-diagonal problem (the reference and the per-tile loop launch 49 separate SupCon problems)

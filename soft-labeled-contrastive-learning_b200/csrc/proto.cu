@@ -58,6 +58,8 @@ struct ProtoArgs {
   float sel_threshold;
   int fused_target;           // forward derives label/sel itself (generate_pseudo_label fused in) and writes them out
   int keep_l2;                // the map fits in L2: load it with evict_last so the backward's read of F hits L2
+  int reverse;                // walk the pixel blocks back to front (forward kernels of L2-sized maps: zig-zag with the
+                              // class-sum sweep in front and the backward behind, each starts where its predecessor ended)
   MarginConst mc;
 };
 
@@ -115,7 +117,8 @@ __device__ __forceinline__ void centre_row(const float* sC, int c, float (&ck)[K
 // Pixel-group addressing shared by every kernel in this file.
 template <int VEC>
 __device__ __forceinline__ bool locate(const ProtoArgs& a, int64_t& pix, int64_t& offset) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bid = a.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+  int64_t g = bid * blockDim.x + threadIdx.x;
   int64_t groups_per_image = a.pixels / VEC;
   if (g >= a.batch * groups_per_image) { pix = 0; offset = 0; return false; }
   int64_t b = g / groups_per_image;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
     double l = 0.0, s = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) { l += red[0][w]; s += red[1][w]; }
-    a.partial[blockIdx.x] = make_double2(l, s);
+    a.partial[a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x] = make_double2(l, s);      // indexed by pixel range
   }
 }
 
@@ -664,6 +667,7 @@ extern "C" int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map, con
   a.labels = labels; a.soft_mask = soft_mask; a.sel = sel; a.stash = stash;
   a.partial = reinterpret_cast<double2*>(workspace);
   a.mc = make_const(params);
+  a.reverse = a.keep_l2;
 
   launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, (int)map->channels, K, params->normalize, cstate);
   SLCL_DISPATCH_K(K, plan.vec, {
@@ -702,6 +706,7 @@ extern "C" int slcl_proto_fwd_target_peer(const float* feat, const slcl_map_t* m
   a.partial = reinterpret_cast<double2*>(workspace);
   a.mc = make_const(params);
   a.fused_target = 1; a.sel_threshold = sel_threshold; a.out_label = label; a.out_sel = sel;
+  a.reverse = a.keep_l2;
   launch_pdl(prep_centres_kernel, dim3(K), dim3(kThreads), 0, stream, centres, (int)map->channels, K, 1, cstate);
   SLCL_DISPATCH_K(K, plan.vec, {
     int st = ensure_smem(proto_fwd_kernel<KK, VV>, plan.smem);

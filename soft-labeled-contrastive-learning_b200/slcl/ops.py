@@ -701,16 +701,18 @@ def _p2p_check(a: Tensor, b: Tensor, a_meta: Tensor, b_meta: Tensor, shift: Tens
 
 def self_maps(id_a: Tensor, id_b: Tensor) -> Tuple[Tensor, Tensor]:
     """(a_selfcol [A], b_selfrow [M]) int32 for the analytic p2p mode: the contrast row carrying anchor i's id
-    (-1: none) and its inverse.  Ids must be unique within each side."""
+    (-1: none) and its inverse.  Ids must be unique within each side.  No host synchronisation (no boolean-mask
+    indexing): anchors without a contrast row scatter into a dump slot."""
+    m = id_b.numel()
     sorted_b, perm = torch.sort(id_b.reshape(-1).long())
     ia = id_a.reshape(-1).long()
-    pos = torch.searchsorted(sorted_b, ia).clamp_(max=sorted_b.numel() - 1)
+    pos = torch.searchsorted(sorted_b, ia).clamp_(max=m - 1)
     found = sorted_b[pos] == ia
     selfcol = torch.where(found, perm[pos], torch.full_like(pos, -1))
-    selfrow = torch.full((id_b.numel(),), -1, dtype=torch.long, device=id_b.device)
-    anchors = torch.arange(ia.numel(), device=ia.device)
-    selfrow[selfcol[found]] = anchors[found]
-    return selfcol.to(torch.int32), selfrow.to(torch.int32)
+    selfrow = torch.full((m + 1,), -1, dtype=torch.long, device=id_b.device)
+    selfrow.index_put_((torch.where(found, selfcol, torch.full_like(selfcol, m)),),
+                       torch.arange(ia.numel(), device=ia.device))
+    return selfcol.to(torch.int32), selfrow[:m].to(torch.int32).contiguous()
 
 
 def _selfcol_check(t: Optional[Tensor], n: int, what: str):

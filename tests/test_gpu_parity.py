@@ -745,6 +745,30 @@ def test_sampler_without_host_sync_bit_exact(n, k, na, nc, rare):
     assert bool((labels[c_idx.cpu()] < k).all())
 
 
+def test_sampled_supcon_loss_whole_call_has_no_host_sync():
+    """draw + compaction + self maps + gather + sweeps + backward scatter: nothing in the public cfg3 call may synchronise
+    (torch's sync debug mode raises on .item() / .cpu() / boolean-mask indexing / nonzero)."""
+    from slcl import p2p
+    g = cases.g(4343)
+    feat = torch.randn(2, 48, 32, 32, generator=g).to(dev())
+    labels = torch.randint(0, 5, (2, 32, 32), generator=g).to(dev())
+    gen = torch.Generator(device=dev()).manual_seed(11)
+
+    def step():
+        f = feat.clone().requires_grad_(True)
+        out = p2p.sampled_supcon_loss(f, labels, 256, 1024, 5, temperature=0.7, generator=gen)
+        out.backward()
+        return out.detach(), f.grad
+    step()                                            # warm-up: allocator, lazy module state
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        out, grad = step()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.isfinite(out) and torch.isfinite(grad).all()
+
+
 def test_sampler_reports_short_maps_and_the_loss_is_nan():
     from slcl import p2p
     g = cases.g(77)
