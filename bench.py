@@ -1175,6 +1175,29 @@ def p2p_kernels(dev, gen):
     out["BlockConLoss (1,2,32,224,224) fwd+bwd through the Python API, 49 tiles batched"] = {
         "ms": ms, "algorithmic_flop": fl, "achieved_TFLOPs": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tf_peak,
         "rows_per_s": n_t * m_t / (ms * 1e-3)}
+    try:        # the same call replayed as one CUDA graph: the device time behind the host-dispatch-bound eager number
+        fbg = fb.detach().clone().requires_grad_(True)
+
+        def block_step_g():
+            loss_b = crit(fbg, lbk)
+            loss_b.backward()
+            fbg.grad = None
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            block_step_g()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g_blk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_blk):
+            block_step_g()
+        ms_g = timed(g_blk.replay, iters=20)
+        out["BlockConLoss (1,2,32,224,224) fwd+bwd, the same Python-API step replayed as one CUDA graph"] = {
+            "ms": ms_g, "algorithmic_flop": fl, "achieved_TFLOPs": fl / (ms_g * 1e-3) / 1e12,
+            "frac_of_bf16_peak": fl / (ms_g * 1e-3) / 1e12 / tf_peak, "rows_per_s": n_t * m_t / (ms_g * 1e-3)}
+        del g_blk, fbg
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] BlockConLoss: graph capture unavailable ({exc!r})", file=sys.stderr)
     crit.batched = False
     ms_loop = timed(block_step, iters=3)
     out["BlockConLoss (1,2,32,224,224) fwd+bwd, per-tile loop (49 SupCon calls, the reference's structure)"] = {

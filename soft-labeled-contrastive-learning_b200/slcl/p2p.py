@@ -90,8 +90,11 @@ class _P2PLoss(torch.autograd.Function):
         d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
                                 grad_out.reshape(1), True, True, n_class, selfcol, selfrow, state, n_batch)
         dfeat = torch.zeros_like(fm)
-        _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
-        _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
+        if same_rows:       # anchors and contrast rows are the same gathered rows: one scatter of the summed row gradients
+            _ops.scatter_rows_bwd(fm, idx_b, normalize, d_a + d_b, inv_b, dfeat)
+        else:
+            _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
+            _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
         return (dfeat,) + (None,) * 12
 
 
