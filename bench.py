@@ -441,6 +441,29 @@ def run_slcl(args):
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        # the same host-buffer step through the DROP-IN signature itself (no pipelining: copy in, mpcl_loss_calc(...)
+        # .backward(), copy out) -- what a trainer that keeps its batch on the host would see without slcl.host
+        def dropin_step():
+            f = feats_h.to(dev, non_blocking=True).requires_grad_(True)
+            lab_d = labels_h.to(dev, non_blocking=True)
+            sel_d = sel_h.to(dev, non_blocking=True)
+            loss = mpcl_loss_calc(f, lab_d, centres, mp, pixel_sel_loc=sel_d, tag="target", group=group)
+            loss.backward()
+            grad_h.copy_(f.grad, non_blocking=True)
+            loss_h.copy_(loss.detach(), non_blocking=True)
+        dropin_step()
+        barrier()
+        s3, e3 = ev(), ev()
+        s3.record()
+        for _ in range(5):
+            dropin_step()
+        e3.record()
+        barrier()
+        ms_dropin = s3.elapsed_time(e3) / 5
+        if world > 1:
+            t = torch.tensor([ms_dropin], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_dropin = float(t.item())
         h2d = feats_h.numel() * 4 + labels_h.numel() * 8 + sel_h.numel() * 4
         d2h = grad_h.numel() * 4 + 4
         # what the box's IO fabric gives at this N: plain pinned cudaMemcpyAsync of the same buffers, all ranks at once --
@@ -477,6 +500,9 @@ def run_slcl(args):
                "api": f"slcl.host.mpcl_loss_and_grad_host(pinned feats/labels/sel -> loss, pinned dF): {E2E_CHUNK}-image chunks, "
                       "H2D / kernels / D2H overlapped on 3 streams",
                "loss": float(loss_h),
+               "drop_in_signature": {"value": world * n_px / (ms_dropin * 1e-3), "ms_per_step": ms_dropin,
+                                     "api": "feats.to(device) -> slcl.loss.mpcl_loss_calc(...).backward() -> grad.cpu(), unpipelined "
+                                            "(H2D, kernels and D2H one after the other)"},
                "achieved_h2d_GBps_per_gpu": h2d * n_e2e / (ms * 1e-3) / 1e9, "achieved_d2h_GBps_per_gpu": d2h * n_e2e / (ms * 1e-3) / 1e9,
                "memcpy_ceiling_same_n": pcie, "cpu_affinity": affinity,
                "bound": "host<->device copies: the step moves %.2f GB in and %.2f GB out per GPU; compare achieved_*_GBps with "

@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(kThreads, 2) class_sums_kernel(const SumArgs a
 //   NBW warps    weight builders (round 2: they no longer touch global memory, so no load latency to hide and half
 //                as many warps): raw inputs of the stage -> sW[stage][column][pixel]; two warps per stage, teams
 //                round-robin over the stages
-//   last warp    counter (channel block 0 only): sums the weights themselves -> the class-count column
+//   last warp    counter (channel block 0 only): sums the weights themselves -> the class-count column (folding this
+//                into consumer 0 was measured in round 2: that warp becomes the straggler of every stage, 0.83 -> 0.75)
 //   consumers    (as many as the channel count needs, <= NCW): warp w owns CPW channels; lane l owns pixels 4l..4l+3
 //                of the stage; x and the weights come back from shared memory with conflict-free LDS.128;
 //                acc[CPW][KWT] in registers for the whole sweep; every channel has exactly one owner, so the block

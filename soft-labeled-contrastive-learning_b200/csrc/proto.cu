@@ -231,6 +231,22 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
       }
       Vec<VEC>::store_keep(a.out_sel + pix, selv);
     }
+    // soft positives (caller-supplied mask [N,K] row-major, :516-517): the VEC pixels of this thread own VEC*K consecutive
+    // floats -- fetched as 128-bit loads (the first version gathered them one float at a time with a stride of K)
+    float msoft[VEC * K];
+    if (a.labels == nullptr && !a.fused_target) {
+      const float* mp = a.soft_mask + pix * K;
+      if constexpr (VEC == 4) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(mp + 4 * q);
+          msoft[4 * q] = t.x; msoft[4 * q + 1] = t.y; msoft[4 * q + 2] = t.z; msoft[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < K; ++q) msoft[q] = mp[q];
+      }
+    }
     float out[K + 1][VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_FWD_MINB
       for (int k = 0; k < K; ++k) {
         cosv[k] = dot[k][v] * inv_n;
         if (a.labels != nullptr || a.fused_target) M[k] = (lab[v] == (long long)k) ? 1.0f : 0.0f;      // :513
-        else M[k] = a.soft_mask[(pix + v) * K + k];                                    // :517
+        else M[k] = msoft[v * K + k];                                                  // :517
       }
       float row = margin_row<K>(cosv, M, selv[v], inv_n, a.mc, coef);
       loss_acc += (double)(selv[v] * row);
@@ -659,7 +675,7 @@ extern "C" int slcl_proto_fwd_peer(const float* feat, const slcl_map_t* map, con
   if (K < 2 || K > kMaxK || !(params->temperature > 0.f) || !(params->base_temperature > 0.f))
     return SLCL_ERR_INVALID_ARGUMENT;
   cudaStream_t stream = (cudaStream_t)stream_;
-  Plan plan = make_plan(map, K, {feat, labels, sel, stash});
+  Plan plan = make_plan(map, K, {feat, labels, sel, stash, soft_mask});
   if (workspace_bytes < slcl_proto_workspace_bytes(plan.n_total)) return SLCL_ERR_WORKSPACE;
   if (!aligned16(workspace)) return SLCL_ERR_INVALID_ARGUMENT;
 
