@@ -350,8 +350,9 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *     so sorting the contrast rows by label pays).  bwd_state must be null.
  *     1..8 = "analytic" mode for class-index labels in [0, n_class) and UNIQUE ids, weights >= 0: the
  *     positive-pair terms are rank-n_class and are evaluated outside the tensor-core sweeps from per-class row
- *     sums, the self pair is removed afterwards with one dot product per anchor.  The ids inside the meta arrays
- *     are then unused; instead
+ *     sums, the self pair is removed afterwards with one dot product per anchor.  An anchor whose label is outside
+ *     [0, n_class) has no class table: its row loss is 0/0 and the returned loss is NaN (whatever its weight).
+ *     The ids inside the meta arrays are then unused; instead
  *       a_selfcol [A] int32: the contrast row holding anchor i's own pixel, or -1 (null: no anchor is a contrast row)
  *       b_selfrow [M] int32: its inverse (anchor whose pixel contrast row j is, or -1); both or none.
  *       bwd_state: optional caller-owned buffer of slcl_p2p_state_bytes() bytes (16-byte aligned) that the forward
@@ -363,7 +364,8 @@ int slcl_entropy_map(const float* prob, int64_t n_elems, int n_class, float* out
  *     (labels and weights only), do not depend on the sweep: they run on a side stream owned by the library (one per
  *     host thread and device, created on first use; fork/join by events, graph-capturable).  The forward on the
  *     caller's stream is the sweep plus ONE finishing launch (its last block totals the loss).
- *   n_batch: 1, or the number of equal BLOCK-DIAGONAL batches (general mode only): anchors [z A/n, (z+1) A/n) are
+ *   n_batch: 1, or the number of equal BLOCK-DIAGONAL batches (either mode; the analytic mode keeps one table of
+ *     per-class sums per batch): anchors [z A/n, (z+1) A/n) are
  *     contrasted with contrast rows [z M/n, (z+1) M/n) only -- BlockConLoss (utils/loss.py:416-466) as ONE launch per
  *     sweep instead of div_num^2 separate problems.  A/n and M/n must be multiples of 128.
  * forward : stats [A,3] = {sum_j exp(S_ij - shift_i), sum_pos S_ij * T, #pos},

@@ -547,7 +547,7 @@ p2p_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__
       if (row_ok) lab = a.row_meta[row].x;
       if (lab >= a.n_class) lab = -1;
       for (int idx = threadIdx.x - 128; idx < a.n_class * a.d; idx += 32 * kEpiWarps)
-        sTab[idx] = a.ab_sums[(size_t)(idx / a.d) * (a.d + 1) + idx % a.d];
+        sTab[idx] = a.ab_sums[((size_t)batch * a.n_class + (size_t)(idx / a.d)) * (a.d + 1) + idx % a.d];      // this batch's table
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");         // the eight epilogue warps only
     }
     if (half == 0) {
@@ -817,6 +817,41 @@ __device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* x, const __n
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// ---- row groups: LPR = 8, 16 or 32 lanes per row (the finishing kernels; LPR = d / 8 so that one 16-byte load per lane
+// covers a bf16 row, 32 / LPR rows per warp instruction).  The shuffles name only the group's lanes, so the groups of a
+// warp may diverge.
+template <int LPR>
+__device__ __forceinline__ unsigned grp_mask(int lane) {
+  return LPR == 32 ? 0xffffffffu : (((1u << (LPR & 31)) - 1u) << (lane & ~(LPR - 1)));
+}
+template <int LPR>
+__device__ __forceinline__ float grp_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+__device__ __forceinline__ void bf16x8_to_float(const uint4& r, float (&x)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    x[2 * k] = __uint_as_float(w[k] << 16);
+    x[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+  }
+}
+template <int LPR>
+__device__ __forceinline__ float grp_dot_bf16(const __nv_bfloat16* x, const __nv_bfloat16* y, int d, int lg, unsigned mask) {
+  float acc = 0.f;
+  for (int c = lg * 8; c < d; c += LPR * 8) {
+    float xa[8], ya[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + c), xa);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(y + c), ya);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(xa[k], ya[k], acc);
+  }
+  return grp_sum<LPR>(acc, mask);
+}
+inline int lanes_per_row(int d) { return d <= 64 ? 8 : (d <= 128 ? 16 : 32); }
+
 // ---- general path -----------------------------------------------------------
 // stats[i] = sum over slots of partial (deterministic order); also the per-block partial of
 // sum_i w_i * (shift_i + log(Zs_i) - P_i / n_i),  P_i = P_raw_i / T     (utils/loss.py:371-386)
@@ -999,17 +1034,18 @@ __device__ __forceinline__ void label_table_add(float* tab, float* cnt, int d, i
 // fixed-order combine of the eight warp tables of a block -> partial[block][K][d], cnt[block][K]  (after __syncthreads)
 __device__ __forceinline__ void label_tables_flush(const float* s_sum, const float* s_cnt, int n_class, int d, float* partial,
                                                    float* cnt) {
+  const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;          // blockIdx.y = block-diagonal batch
   for (int idx = threadIdx.x; idx < n_class * d; idx += 256) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_sum[(size_t)w * n_class * d + idx];
-    partial[(size_t)blockIdx.x * n_class * d + idx] = t;
+    partial[blk * n_class * d + idx] = t;
   }
   if ((int)threadIdx.x < n_class) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_cnt[w * n_class + threadIdx.x];
-    cnt[blockIdx.x * n_class + threadIdx.x] = t;
+    cnt[blk * n_class + threadIdx.x] = t;
   }
 }
 
@@ -1029,7 +1065,20 @@ __global__ void __launch_bounds__(256) p2p_label_part_kernel(const __nv_bfloat16
                                                              unsigned int* zero_ticket) {
   pdl_trigger();
   pdl_wait();
-  if (zero_ticket != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_ticket = 0u;      // (see p2p_finish_fwd_kernel)
+  if (zero_ticket != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_ticket = 0u;      // (see p2p_finish_fwd_kernel)
+  // block-diagonal batches (gridDim.y > 1): batch z owns rows [z n_rows, (z+1) n_rows) and its own [K][d+1] tables;
+  // n_rows is the per-batch row count, self columns stay global contrast-row indices
+  {
+    const size_t z = blockIdx.y;
+    rows += z * (size_t)n_rows * d;
+    meta += z * (size_t)n_rows;
+    if (kBeta) {
+      weight += z * (size_t)n_rows;
+      beta_out += z * (size_t)n_rows;
+      if (selfcol) selfcol += z * (size_t)n_rows;
+      other_sums += z * (size_t)n_class * (d + 1);
+    }
+  }
   extern __shared__ float sm_lp[];                 // [8 warps][K][d] + [8][K]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* s_sum = sm_lp;
@@ -1089,6 +1138,9 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
   pdl_trigger();
   pdl_wait();
   __shared__ float red[8][33];
+  partial += (size_t)blockIdx.y * n_blocks * n_class * d;          // blockIdx.y = block-diagonal batch
+  cnt += (size_t)blockIdx.y * n_blocks * n_class;
+  out += (size_t)blockIdx.y * n_class * (d + 1);
   const int o = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int n_out = n_class * (d + 1);
   const int idx = blockIdx.x * 32 + o;
@@ -1116,7 +1168,7 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
   }
 }
 
-// Forward finish, one warp per anchor i (fixed summation orders throughout).  The per-class sums
+// Forward finish, LPR lanes per anchor i (fixed summation orders throughout).  The per-class sums
 // label_sums[K][d + 1] (last column = class count) are read through L1 (a 5 KB table every warp shares).
 //   Zs_i   = sum_slots zs - e_self                      e_self = exp(S_i,self / T - shift_i) if anchor i is a contrast row
 //   P_raw  = a_i . Bsum[lab_i] - [labels agree] S_i,self        n_i = count[lab_i] - [labels agree]
@@ -1127,12 +1179,14 @@ __global__ void __launch_bounds__(256) p2p_label_reduce_kernel(const float* part
 // stay where the sweep wrote them and are summed by the backward finish).
 // The block that finishes last adds the per-block loss partials in index order (ticket counter `done`, zeroed by the
 // first side-stream kernel of the call and wrapped back to zero by atomicInc), so the forward ends with this launch.
-constexpr int kFinWarps = 32;          // warps (= anchors in flight) per block of the forward finish
+constexpr int kFinWarps = 8;           // warps per block of the forward finish
+template <int LPR>
 __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const float* zs_partial, int n_slots, int n_rows, const float* shift,
                                                              const float* weight, float inv_t, const __nv_bfloat16* a,
                                                              const __nv_bfloat16* b, int d, const int2* a_meta,
                                                              const int2* b_meta, const int32_t* a_selfcol,
-                                                             const float* label_sums, int n_class, float* alpha_out,
+                                                             const float* label_sums, int n_class, int rows_per_batch,
+                                                             float* alpha_out,
                                                              float* colshift_out, int n_rows_padded, float* stats,
                                                              double* loss_partial, unsigned int* done, float* loss) {
   pdl_trigger();
@@ -1142,37 +1196,40 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
     for (int r = n_rows + threadIdx.x; r < n_rows_padded; r += 32 * kFinWarps) colshift_out[r] = kShiftOff;
   __shared__ double red[kFinWarps];
   __shared__ bool s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kRpw = 32 / LPR, kFinRows = kRpw * kFinWarps;          // rows per warp, per block and pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPR, l8 = lane % LPR;
+  const unsigned om = grp_mask<LPR>(lane);
   double acc = 0.0;
-  for (int base = blockIdx.x * kFinWarps; base < n_rows; base += gridDim.x * kFinWarps) {
-    const int i = base + warp;
-    if (i >= n_rows) continue;
+  for (int base = blockIdx.x * kFinRows; base < n_rows; base += gridDim.x * kFinRows) {
+    const int i = base + warp * kRpw + grp;
+    if (i >= n_rows) continue;                      // whole groups leave together
     const __nv_bfloat16* ai = a + (size_t)i * d;
     const int lab = a_meta[i].x;
     const int sc = a_selfcol ? a_selfcol[i] : -1;
     const bool lab_ok = lab >= 0 && lab < n_class;
     float zp = 0.f;
-    for (int s = lane; s < n_slots; s += 32) zp += zs_partial[(size_t)s * n_rows + i];
-    float zs = warp_sum(zp);
+    for (int s = l8; s < n_slots; s += LPR) zp += zs_partial[(size_t)s * n_rows + i];
+    float zs = grp_sum<LPR>(zp, om);
     float praw = 0.f, n = 0.f;
     if (lab_ok) {
-      const float* bs = label_sums + (size_t)lab * (d + 1);
+      const float* bs = label_sums + ((size_t)(i / rows_per_batch) * n_class + lab) * (d + 1);      // the tables of anchor i's batch
       float t = 0.f;
-      for (int c = lane * 2; c < d; c += 64) {
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
-        t = fmaf(x.x, __ldg(bs + c), t);
-        t = fmaf(x.y, __ldg(bs + c + 1), t);
+      for (int c = l8 * 8; c < d; c += LPR * 8) {
+        float x[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(ai + c), x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t = fmaf(x[k], __ldg(bs + c + k), t);
       }
-      praw = warp_sum(t);
+      praw = grp_sum<LPR>(t, om);
       n = __ldg(bs + d);
     }
     if (sc >= 0) {
-      const float s_self = warp_dot_bf16(ai, b + (size_t)sc * d, d, lane);
+      const float s_self = grp_dot_bf16<LPR>(ai, b + (size_t)sc * d, d, l8, om);
       const float e_self = ex2_approx(fmaf(s_self, inv_t * kLog2e, -shift[i] * kLog2e));
       zs = fmaxf(zs - e_self, e_self * 1.1920929e-7f);      // round-off floor, see p2p_reduce_stats_self_kernel
-      if (lab == b_meta[sc].x) { praw -= s_self; n -= 1.f; }
+      if (lab_ok && lab == b_meta[sc].x) { praw -= s_self; n -= 1.f; }      // (a label outside [0, K): n stays 0 -> NaN)
     }
-    if (lane == 0) {
+    if (l8 == 0) {
       if (keep) {
         const float al = weight[i] * inv_t / zs;
         alpha_out[i] = al;
@@ -1182,6 +1239,13 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
       const float li = shift[i] + logf(zs) - (praw * inv_t) / n;      // n == 0 -> NaN, as 0/0 in the reference (:376-380)
       acc += (double)(weight[i] * li);
     }
+  }
+  __syncwarp();
+  {          // the group leaders of the warp, in lane order
+    double t = 0.0;
+#pragma unroll
+    for (int gl = 0; gl < 32; gl += LPR) t += __shfl_sync(0xffffffffu, acc, gl);
+    acc = t;
   }
   if (lane == 0) red[warp] = acc;
   __syncthreads();
@@ -1202,14 +1266,16 @@ __global__ void __launch_bounds__(32 * kFinWarps) p2p_finish_fwd_kernel(const fl
   }
 }
 
-// Backward finish, one warp per output row (anchors first, then contrast rows), g = dL/dloss:
+// Backward finish, eight lanes per output row (anchors first, then contrast rows), g = dL/dloss:
 //   d_a[i] = g ( alpha~_i U_i - beta~_i (Bsum[lab_i] - [labels agree] b_self) )
 //   d_b[j] = g ( sum_splits Acc_j - bf16(alpha~_i e_i,self) a_i - ABsum[lab_j] + [labels agree] beta~_i a_i ),  i = b_selfrow[j]
+template <int LPR>
 __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n_contrast, int d, int dim,
                                                              const __nv_bfloat16* a, const __nv_bfloat16* b, const int2* a_meta,
                                                              const int2* b_meta, const int32_t* a_selfcol,
                                                              const int32_t* b_selfrow, const float* label_sums,
-                                                             const float* ab_sums, int n_class, const float* alpha,
+                                                             const float* ab_sums, int n_class, int rows_per_batch_a,
+                                                             int rows_per_batch_b, const float* alpha,
                                                              const float* beta, const float* colshift, const float* shift,
                                                              float scale_log2, const float* u_partial, int n_splits_u,
                                                              const float* acc_partial, int n_splits,
@@ -1217,64 +1283,80 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
   pdl_trigger();
   pdl_wait();
   // fused_db: the dB sweep already wrote d_b = g (Acc - ABsum[lab_j]); only the self-pair term is left, and it is
-  // added here by the warp of the anchor it belongs to (ids are unique, so no two warps touch the same row)
+  // added here by the lane group of the anchor it belongs to (ids are unique, so no two groups touch the same row)
   const float g = grad_out[0];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kRpw = 32 / LPR, kStep = LPR * 8;          // rows per warp; channels per pass of a group
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / LPR, l8 = lane % LPR;
+  const unsigned om = grp_mask<LPR>(lane);
+  const bool vec = (dim & 3) == 0;          // 16-byte stores: every 4-channel group is wholly inside or outside [0, dim)
   const int r_begin = (d_a || fused_db) ? 0 : n_anchor, r_end = (d_b && !fused_db) ? n_anchor + n_contrast : n_anchor;
-  for (int r = r_begin + blockIdx.x * 8 + warp; r < r_end; r += gridDim.x * 8) {
+  for (int r = r_begin + blockIdx.x * (8 * kRpw) + warp * kRpw + grp; r < r_end; r += gridDim.x * (8 * kRpw)) {
     if (r < n_anchor) {
       const int i = r;
       const int lab = a_meta[i].x;
       const bool lab_ok = lab >= 0 && lab < n_class;
       const int sc = a_selfcol ? a_selfcol[i] : -1;
-      const bool match = sc >= 0 && lab == b_meta[sc].x;
+      const bool match = sc >= 0 && lab_ok && lab == b_meta[sc].x;
       const float al = alpha[i], be = lab_ok ? beta[i] : 0.f;
       const __nv_bfloat16* bs = b + (size_t)max(sc, 0) * d;
-      const float* bsum = label_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
+      const float* bsum = label_sums + ((size_t)(i / rows_per_batch_a) * n_class + (lab_ok ? lab : 0)) * (d + 1);
       const __nv_bfloat16* ai = a + (size_t)i * d;
-      const float s_self = sc >= 0 ? warp_dot_bf16(ai, bs, d, lane) : 0.f;
+      const float s_self = sc >= 0 ? grp_dot_bf16<LPR>(ai, bs, d, l8, om) : 0.f;
       if (fused_db && sc >= 0) {
         const float g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
         const float coef = g * ((match ? beta[i] : 0.f) - g_self);
-        for (int c = lane * 2; c < dim; c += 64) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ai + c));
-          d_b[(size_t)sc * dim + c] += coef * x.x;
-          if (c + 1 < dim) d_b[(size_t)sc * dim + c + 1] += coef * x.y;
+        for (int c = l8 * 8; c < dim; c += kStep) {
+          float x[8];
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(ai + c), x);
+          float* dst = d_b + (size_t)sc * dim + c;
+          if (vec) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (c + 4 * h < dim) {
+                float4 o = *reinterpret_cast<float4*>(dst + 4 * h);
+                o.x = fmaf(coef, x[4 * h], o.x); o.y = fmaf(coef, x[4 * h + 1], o.y);
+                o.z = fmaf(coef, x[4 * h + 2], o.z); o.w = fmaf(coef, x[4 * h + 3], o.w);
+                *reinterpret_cast<float4*>(dst + 4 * h) = o;
+              }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (c + k < dim) dst[k] = fmaf(coef, x[k], dst[k]);
+          }
         }
       }
       if (d_a == nullptr) continue;
       // U_i = sum_splits U_partial - bf16(e_self) b_self   (the sweep multiplied bf16-rounded exponentials)
       const float e_self_r = sc >= 0 ? bf16_round(ex2_approx(fmaf(s_self, scale_log2, -shift[i] * kLog2e))) : 0.f;
       const size_t split_stride = (size_t)n_anchor * d;
-      for (int c = lane * 2; c < dim; c += 64) {
+      for (int c = l8 * 8; c < dim; c += kStep) {
         const float* src = u_partial + (size_t)i * d + c;
-        float2 uu = make_float2(0.f, 0.f);
-        int s = 0;
-        for (; s + 4 <= n_splits_u; s += 4) {                 // four loads in flight, summed in split order
-          const float2 p0 = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
-          const float2 p1 = *reinterpret_cast<const float2*>(src + (size_t)(s + 1) * split_stride);
-          const float2 p2 = *reinterpret_cast<const float2*>(src + (size_t)(s + 2) * split_stride);
-          const float2 p3 = *reinterpret_cast<const float2*>(src + (size_t)(s + 3) * split_stride);
-          uu.x = (((uu.x + p0.x) + p1.x) + p2.x) + p3.x;
-          uu.y = (((uu.y + p0.y) + p1.y) + p2.y) + p3.y;
+        float uu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < n_splits_u; ++s) {                // summed in split order
+          const float4 p0 = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride);
+          const float4 p1 = *reinterpret_cast<const float4*>(src + (size_t)s * split_stride + 4);
+          uu[0] += p0.x; uu[1] += p0.y; uu[2] += p0.z; uu[3] += p0.w;
+          uu[4] += p1.x; uu[5] += p1.y; uu[6] += p1.z; uu[7] += p1.w;
         }
-        for (; s < n_splits_u; ++s) {
-          const float2 q = *reinterpret_cast<const float2*>(src + (size_t)s * split_stride);
-          uu.x += q.x; uu.y += q.y;
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (sc >= 0) bf16x8_to_float(*reinterpret_cast<const uint4*>(bs + c), x);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float u = fmaf(-e_self_r, x[k], uu[k]);
+          float pk = lab_ok ? __ldg(bsum + c + k) : 0.f;
+          if (match) pk -= x[k];
+          o[k] = g * (al * u - be * pk);
         }
-        if (sc >= 0) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
-          uu.x = fmaf(-e_self_r, x.x, uu.x); uu.y = fmaf(-e_self_r, x.y, uu.y);
+        float* dst = d_a + (size_t)i * dim + c;
+        if (vec) {
+          if (c < dim) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          if (c + 4 < dim) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (c + k < dim) dst[k] = o[k];
         }
-        float2 p = make_float2(0.f, 0.f);
-        if (lab_ok) { p.x = __ldg(bsum + c); p.y = __ldg(bsum + c + 1); }
-        if (match) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bs + c));
-          p.x -= x.x; p.y -= x.y;
-        }
-        const float ox = g * (al * uu.x - be * p.x), oy = g * (al * uu.y - be * p.y);
-        d_a[(size_t)i * dim + c] = ox;
-        if (c + 1 < dim) d_a[(size_t)i * dim + c + 1] = oy;
       }
     } else {
       const int j = r - n_anchor;
@@ -1284,24 +1366,38 @@ __global__ void __launch_bounds__(256) p2p_finish_bwd_kernel(int n_anchor, int n
       float g_self = 0.f, be_self = 0.f;
       const __nv_bfloat16* as = a + (size_t)max(i, 0) * d;
       if (i >= 0) {
-        const float s_self = warp_dot_bf16(as, b + (size_t)j * d, d, lane);
+        const float s_self = grp_dot_bf16<LPR>(as, b + (size_t)j * d, d, l8, om);
         g_self = bf16_round(ex2_approx(fmaf(s_self, scale_log2, -colshift[i])));
         if (a_meta[i].x == lab) be_self = beta[i];
       }
-      const float* absum = ab_sums + (size_t)(lab_ok ? lab : 0) * (d + 1);
-      for (int c = lane * 2; c < dim; c += 64) {
-        float2 t = make_float2(0.f, 0.f);
+      const float* absum = ab_sums + ((size_t)(j / rows_per_batch_b) * n_class + (lab_ok ? lab : 0)) * (d + 1);
+      for (int c = l8 * 8; c < dim; c += kStep) {
+        float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < n_splits; ++s) {
-          const float2 p = *reinterpret_cast<const float2*>(acc_partial + ((size_t)s * n_contrast + j) * d + c);
-          t.x += p.x; t.y += p.y;
+          const float* src = acc_partial + ((size_t)s * n_contrast + j) * d + c;
+          const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
+          t[0] += p0.x; t[1] += p0.y; t[2] += p0.z; t[3] += p0.w;
+          t[4] += p1.x; t[5] += p1.y; t[6] += p1.z; t[7] += p1.w;
         }
-        if (lab_ok) { t.x -= __ldg(absum + c); t.y -= __ldg(absum + c + 1); }
-        if (i >= 0) {
-          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(as + c));
-          t.x += (be_self - g_self) * x.x; t.y += (be_self - g_self) * x.y;
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i >= 0) bf16x8_to_float(*reinterpret_cast<const uint4*>(as + c), x);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float tk = t[k];
+          if (lab_ok) tk -= __ldg(absum + c + k);
+          tk += (be_self - g_self) * x[k];          // x = 0 without a self pair
+          o[k] = g * tk;
         }
-        d_b[(size_t)j * dim + c] = g * t.x;
-        if (c + 1 < dim) d_b[(size_t)j * dim + c + 1] = g * t.y;
+        float* dst = d_b + (size_t)j * dim + c;
+        if (vec) {
+          if (c < dim) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          if (c + 4 < dim) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (c + k < dim) dst[k] = o[k];
+        }
       }
     }
   }
@@ -1461,7 +1557,7 @@ int max_splits(int64_t n_rows) {          // upper bound of plan_sweep(n_rows, a
 P2PState carve_state(void* p, int64_t na, int d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  const size_t K = kMaxLabelClasses;
+  const size_t K = kMaxLabelClasses * (size_t)ceil_div<int64_t>(na, BM);      // per-class tables for every possible block-diagonal batch
   size_t o0 = take((size_t)max_splits(na) * na * d * sizeof(float)), o1 = take(K * (d + 1) * sizeof(float)), o2 = take(K * (d + 1) * sizeof(float));
   size_t o3 = take(align_up((size_t)na, BN) * sizeof(float)), o4 = take((size_t)na * sizeof(float)), o5 = take((size_t)na * sizeof(float));
   char* b = reinterpret_cast<char*>(p);
@@ -1498,18 +1594,20 @@ P2PWs carve(void* ws, int64_t na, int64_t m, int d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   P2PWs w;
-  w.blocks_b = (int)ceil_div<int64_t>(m, kLabelRowsPerBlock);
+  w.blocks_b = (int)(ceil_div<int64_t>(m, kLabelRowsPerBlock) + ceil_div<int64_t>(m, BM));      // + one ragged block per batch
   const size_t K = kMaxLabelClasses;
+  const size_t ab_blocks = (size_t)std::max<int64_t>(kMaxFinishBlocks, ceil_div<int64_t>(na, BM));
   size_t o[14];
-  o[0] = take((size_t)2 * sa.splits * na * 3 * sizeof(float));
+  const size_t spa = (size_t)std::max(sa.splits, max_splits(na)), spb = (size_t)std::max(sb.splits, max_splits(m));      // any batching
+  o[0] = take((size_t)2 * spa * na * 3 * sizeof(float));
   o[1] = take((size_t)align_up((size_t)na, BN) * sizeof(float4));
-  o[2] = take((size_t)sa.splits * na * d * sizeof(float));
-  o[3] = take((size_t)sb.splits * m * d * sizeof(float));
+  o[2] = take(spa * na * d * sizeof(float));
+  o[3] = take(spb * m * d * sizeof(float));
   o[4] = take((size_t)w.blocks_b * K * d * sizeof(float));
   o[5] = take((size_t)w.blocks_b * K * sizeof(float));
-  o[6] = take((size_t)kMaxFinishBlocks * K * d * sizeof(float));
-  o[7] = take((size_t)kMaxFinishBlocks * K * sizeof(float));
-  o[8] = take(K * (d + 1) * sizeof(float));
+  o[6] = take(ab_blocks * K * d * sizeof(float));
+  o[7] = take(ab_blocks * K * sizeof(float));
+  o[8] = take(K * (size_t)ceil_div<int64_t>(na, BM) * (d + 1) * sizeof(float));
   o[9] = take((size_t)na * 3 * sizeof(float));
   const int64_t n_loss_partial = ceil_div<int64_t>(na, 8) > kMaxFinishBlocks ? ceil_div<int64_t>(na, 8) : kMaxFinishBlocks;
   o[10] = take((size_t)n_loss_partial * sizeof(double));
@@ -1540,15 +1638,16 @@ bool p2p_args_ok(const void* a, const void* b, int64_t na, int64_t m, int64_t dp
          m < (int64_t)INT_MAX - BM && aligned16(a) && aligned16(b);
 }
 
-// block-diagonal batching (general sweeps only): equal batches whose row / column ranges are whole tiles
+// block-diagonal batching: equal batches whose row / column ranges are whole tiles
 bool batches_ok(int64_t na, int64_t m, int n_class, int n_batch) {
   if (n_batch == 1) return true;
-  return n_batch > 1 && n_batch <= 65535 && n_class == 0 && na % n_batch == 0 && m % n_batch == 0 && (na / n_batch) % BM == 0 &&
+  (void)n_class;
+  return n_batch > 1 && n_batch <= 65535 && na % n_batch == 0 && m % n_batch == 0 && (na / n_batch) % BM == 0 &&
          (m / n_batch) % BM == 0;
 }
 
-int finish_blocks(int64_t rows) {          // forward finish: one warp per anchor up to kMaxFinishBlocks partials
-  const int64_t want = ceil_div<int64_t>(rows, kFinWarps);
+int finish_blocks(int64_t rows, int lpr) {          // forward finish: lpr lanes per anchor up to kMaxFinishBlocks partials
+  const int64_t want = ceil_div<int64_t>(rows, (32 / lpr) * kFinWarps);
   return (int)(want < kMaxFinishBlocks ? want : kMaxFinishBlocks);
 }
 
@@ -1589,7 +1688,9 @@ Aux* aux_stream() {
 // analytic forward: [side stream: label sums of b -> beta~ and ABsum of the anchors]  ||  sweep  ->  finish (+ loss)
 int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, const int2* am, const int2* bm,
                 const int32_t* a_selfcol, int n_class, const float* shift, const float* weight, float inv_t,
-                float* stats, float* loss, const P2PState* state, const P2PWs& w, cudaStream_t stream) {
+                float* stats, float* loss, const P2PState* state, const P2PWs& w, cudaStream_t stream, int n_batch = 1) {
+  const int rpb_a = (int)(na / n_batch), rpb_b = (int)(m / n_batch);          // rows per block-diagonal batch
+  const int blocks_b = ceil_div(rpb_b, kLabelRowsPerBlock);
   const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(a);
   const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
   if (int st0 = big_smem_ok()) return st0;
@@ -1601,34 +1702,37 @@ int ana_forward(const void* a, const void* b, int64_t na, int64_t m, int d, cons
   cudaStream_t side = stream;
   if (aux != nullptr && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
     side = aux->s;
-  launch_pdl(p2p_label_part_kernel<false>, dim3(w.blocks_b), dim3(256), table_smem, side, bb, (int)m, d, bm, n_class, w.lab_partial_b,
-             w.lab_cnt_b, (const float*)nullptr, 0.f, (const int32_t*)nullptr, (const int2*)nullptr, (const float*)nullptr,
-             (float*)nullptr, w.done);
-  launch_pdl(p2p_label_reduce_kernel, dim3(n_red), dim3(256), 0, side, (const float*)w.lab_partial_b, (const float*)w.lab_cnt_b,
-             w.blocks_b, n_class, d, bsum);
+  launch_pdl(p2p_label_part_kernel<false>, dim3(blocks_b, n_batch), dim3(256), table_smem, side, bb, rpb_b, d, bm, n_class,
+             w.lab_partial_b, w.lab_cnt_b, (const float*)nullptr, 0.f, (const int32_t*)nullptr, (const int2*)nullptr,
+             (const float*)nullptr, (float*)nullptr, w.done);
+  launch_pdl(p2p_label_reduce_kernel, dim3(n_red, n_batch), dim3(256), 0, side, (const float*)w.lab_partial_b,
+             (const float*)w.lab_cnt_b, blocks_b, n_class, d, bsum);
   if (keep) {
-    const int blocks_a = (int)std::min<int64_t>(ceil_div<int64_t>(na, kLabelRowsPerBlock), (int64_t)kMaxFinishBlocks);
-    launch_pdl(p2p_label_part_kernel<true>, dim3(blocks_a), dim3(256), table_smem, side, ab, (int)na, d, am, n_class, w.ab_partial,
-               w.ab_cnt, weight, inv_t, a_selfcol, bm, (const float*)bsum, state->beta,
-               (unsigned int*)nullptr);
-    launch_pdl(p2p_label_reduce_kernel, dim3(n_red), dim3(256), 0, side, (const float*)w.ab_partial, (const float*)w.ab_cnt,
-               blocks_a, n_class, d, state->absum);
+    const int blocks_a = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(rpb_a, kLabelRowsPerBlock),
+                                                                     (int64_t)kMaxFinishBlocks / n_batch));
+    launch_pdl(p2p_label_part_kernel<true>, dim3(blocks_a, n_batch), dim3(256), table_smem, side, ab, rpb_a, d, am, n_class,
+               w.ab_partial, w.ab_cnt, weight, inv_t, a_selfcol, bm, (const float*)bsum, state->beta, (unsigned int*)nullptr);
+    launch_pdl(p2p_label_reduce_kernel, dim3(n_red, n_batch), dim3(256), 0, side, (const float*)w.ab_partial,
+               (const float*)w.ab_cnt, blocks_a, n_class, d, state->absum);
   }
   if (side != stream) cudaEventRecord(aux->join, side);
-  Sweep sw = plan_sweep(na, m);
+  Sweep sw = plan_sweep(na / n_batch, m / n_batch, n_batch);
   P2PArgs args{};
   args.row_shift = shift;
   args.stat_partial = w.stat_partial;
   args.grad_partial = keep ? state->u : w.grad_partial_a;
-  int st = keep ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream)
-                : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream);
+  int st = keep ? launch_sweep<kAnaFwdU>(a, na, b, m, d, inv_t, args, sw, stream, n_batch)
+                : launch_sweep<kAnaFwd>(a, na, b, m, d, inv_t, args, sw, stream, n_batch);
   if (side != stream) cudaStreamWaitEvent(stream, aux->join, 0);          // join even when the sweep failed to launch
   if (st != SLCL_OK) return st;
-  const int nb = finish_blocks(na);
-  launch_pdl(p2p_finish_fwd_kernel, dim3(nb), dim3(32 * kFinWarps), 0, stream, (const float*)w.stat_partial, 2 * sw.splits, (int)na,
-             shift, weight, inv_t, ab, bb, d, am, bm, a_selfcol, (const float*)bsum, n_class,
-             keep ? state->alpha : (float*)nullptr, keep ? state->colshift : (float*)nullptr, (int)align_up((size_t)na, BN), stats,
-             w.loss_partial, w.done, loss);
+  const int lpr = lanes_per_row(d), nb = finish_blocks(na, lpr);
+  auto fin = [&](auto kernel) {
+    launch_pdl(kernel, dim3(nb), dim3(32 * kFinWarps), 0, stream, (const float*)w.stat_partial, 2 * sw.splits, (int)na, shift,
+               weight, inv_t, ab, bb, d, am, bm, a_selfcol, (const float*)bsum, n_class, rpb_a,
+               keep ? state->alpha : (float*)nullptr, keep ? state->colshift : (float*)nullptr, (int)align_up((size_t)na, BN),
+               stats, w.loss_partial, w.done, loss);
+  };
+  if (lpr == 8) fin(p2p_finish_fwd_kernel<8>); else if (lpr == 16) fin(p2p_finish_fwd_kernel<16>); else fin(p2p_finish_fwd_kernel<32>);
   return SLCL_OK;
 }
 
@@ -1670,7 +1774,7 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
   if (n_class > 0) {
     P2PState st_ = carve_state(bwd_state, n_anchor, d);
     int st = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t, stats, loss,
-                         bwd_state ? &st_ : nullptr, w, stream);
+                         bwd_state ? &st_ : nullptr, w, stream, n_batch);
     if (st != SLCL_OK) return st;
     return check_launch("slcl_p2p_fwd");
   }
@@ -1725,12 +1829,12 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     if (bwd_state == nullptr) {
       // the caller did not keep the forward's state: one more forward sweep regenerates it in the workspace
       int st = ana_forward(a_bf16, b_bf16, n_anchor, n_contrast, d, am, bm, a_selfcol, n_class, shift, weight, inv_t,
-                           w.stats_scratch, reinterpret_cast<float*>(w.loss_partial) /* scratch */, &st_, w, stream);
+                           w.stats_scratch, reinterpret_cast<float*>(w.loss_partial) /* scratch */, &st_, w, stream, n_batch);
       if (st != SLCL_OK) return st;
     }
     int n_splits_b = 0, fused_db = 0;
     if (d_b) {
-      Sweep sw = plan_sweep(n_contrast, n_anchor);
+      Sweep sw = plan_sweep(n_contrast / n_batch, n_anchor / n_batch, n_batch);
       P2PArgs args{};
       args.col_shift = st_.colshift;
       args.grad_partial = w.grad_partial_b;
@@ -1740,16 +1844,21 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
         args.fused_out = d_b; args.ld_out = (int)dim; args.n_class = n_class; args.ab_sums = st_.absum; args.grad_out = grad_out;
         args.row_meta = bm;
       }
-      int st = launch_sweep<kAnaCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream);
+      int st = launch_sweep<kAnaCols>(b_bf16, n_contrast, a_bf16, n_anchor, d, inv_t, args, sw, stream, n_batch);
       if (st != SLCL_OK) return st;
       n_splits_b = sw.splits;
     }
     const int64_t rows = ((d_a || fused_db) ? n_anchor : 0) + ((d_b && !fused_db) ? n_contrast : 0);
-    launch_pdl(p2p_finish_bwd_kernel, dim3((unsigned)ceil_div<int64_t>(rows, 8)), dim3(256), 0, stream, na, (int)n_contrast, d,
-               (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, (const float*)st_.bsum, (const float*)st_.absum, n_class,
-               (const float*)st_.alpha, (const float*)st_.beta, (const float*)st_.colshift, shift, inv_t * kLog2e,
-               (const float*)st_.u, plan_sweep(n_anchor, n_contrast).splits, (const float*)w.grad_partial_b, n_splits_b, fused_db,
-               grad_out, d_a, d_b);
+    const int lpr = lanes_per_row(d);
+    auto fin = [&](auto kernel) {
+      launch_pdl(kernel, dim3((unsigned)ceil_div<int64_t>(rows, 8 * (32 / lpr))), dim3(256), 0, stream, na, (int)n_contrast, d,
+                 (int)dim, ab, bb, am, bm, a_selfcol, b_selfrow, (const float*)st_.bsum, (const float*)st_.absum, n_class,
+                 (int)(n_anchor / n_batch), (int)(n_contrast / n_batch),
+                 (const float*)st_.alpha, (const float*)st_.beta, (const float*)st_.colshift, shift, inv_t * kLog2e,
+                 (const float*)st_.u, plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch).splits,
+                 (const float*)w.grad_partial_b, n_splits_b, fused_db, grad_out, d_a, d_b);
+    };
+    if (lpr == 8) fin(p2p_finish_bwd_kernel<8>); else if (lpr == 16) fin(p2p_finish_bwd_kernel<16>); else fin(p2p_finish_bwd_kernel<32>);
     return check_launch("slcl_p2p_bwd");
   }
   launch_pdl(p2p_anchor_stat_kernel, dim3(ceil_div(na + BN, 256)), dim3(256), 0, stream, stats, shift, weight, grad_out, na,

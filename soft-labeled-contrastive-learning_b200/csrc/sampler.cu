@@ -167,6 +167,85 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* feat
   }
 }
 
+// The same gather for narrow maps (C <= 64, rows padded to 64 bf16): ONE THREAD per sampled row, so a warp's load of one
+// channel touches 32 pixels -- four sectors when the rows are neighbouring pixels (dense tiles: BlockConLoss, strided
+// grids) and never more sectors than the warp-per-row layout when they are scattered.  The row stays in registers; the
+// block's 256 x 128-byte output region is written through shared memory with coalesced 16-byte stores.
+constexpr int kDenseC = 64;
+constexpr int kDenseRows = 256;
+constexpr int kDensePitch = kDenseC + 8;          // bf16 elements: 144-byte pitch, conflict-free 16-byte accesses
+__global__ void __launch_bounds__(kDenseRows) gather_rows_dense_kernel(const float* feat, int64_t C, int64_t HW,
+                                                                       const int64_t* pixel_idx, int64_t n_rows, int normalize,
+                                                                       __nv_bfloat16* out_bf16, float* inv_norm) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kDenseRows][kDensePitch];
+  const int64_t row0 = (int64_t)blockIdx.x * kDenseRows;
+  const int64_t row = row0 + threadIdx.x;
+  const bool ok = row < n_rows;
+  const int64_t pix = ok ? pixel_idx[row] : 0;
+  const int64_t b = pix / HW, p = pix - b * HW;
+  const float* base = feat + b * C * HW + p;
+  float v[kDenseC];
+#pragma unroll
+  for (int c = 0; c < kDenseC; ++c) v[c] = (ok && c < C) ? __ldg(base + (int64_t)c * HW) : 0.f;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < kDenseC; ++c) ss = fmaf(v[c], v[c], ss);
+  const float inv_n = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  const float inv = normalize ? inv_n : 1.0f;
+  if (ok && inv_norm) inv_norm[row] = inv_n;
+#pragma unroll
+  for (int k = 0; k < kDenseC / 8; ++k) {
+    uint4 q;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * k + 2 * u] * inv, v[8 * k + 2 * u + 1] * inv);
+      w[u] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(&tile[threadIdx.x][8 * k]) = q;
+  }
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(out_bf16 + row0 * kDenseC);
+#pragma unroll
+  for (int k = 0; k < kDenseC / 8; ++k) {
+    const int q = threadIdx.x + kDenseRows * k, r = q >> 3, ch = q & 7;
+    if (row0 + r < n_rows) out[q] = *reinterpret_cast<const uint4*>(&tile[r][8 * ch]);
+  }
+}
+
+// Scatter for narrow maps, one thread per row (see gather_rows_dense_kernel): the block's row gradients come in through
+// shared memory (coalesced), every thread then owns its row, and a warp's atomic adds of one channel hit 32 pixels.
+constexpr int kScatterRows = 128;
+__global__ void __launch_bounds__(kScatterRows) scatter_rows_dense_kernel(const float* feat, int64_t C, int64_t HW,
+                                                                          const int64_t* pixel_idx, int64_t n_rows,
+                                                                          int normalize, const float* d_rows,
+                                                                          const float* inv_norm, float* dfeat) {
+  extern __shared__ float s_g[];                    // [kScatterRows][C + 1]
+  const int pitch = (int)C + 1;
+  const int64_t row0 = (int64_t)blockIdx.x * kScatterRows;
+  const int64_t n_here = min((int64_t)kScatterRows, n_rows - row0);
+  for (int64_t e = threadIdx.x; e < n_here * C; e += kScatterRows) {
+    const int r = (int)(e / C), c = (int)(e - (int64_t)r * C);
+    s_g[r * pitch + c] = d_rows[row0 * C + e];
+  }
+  __syncthreads();
+  const int64_t row = row0 + threadIdx.x;
+  if (row >= n_rows) return;
+  const int64_t pix = pixel_idx[row];
+  const int64_t b = pix / HW, p = pix - b * HW;
+  const int64_t base = b * C * HW + p;
+  const float* g = s_g + threadIdx.x * pitch;
+  if (!normalize) {
+    for (int c = 0; c < (int)C; ++c) atomicAdd(dfeat + base + (int64_t)c * HW, g[c]);
+    return;
+  }
+  const float inv = inv_norm[row];
+  float dotv = 0.f;
+  for (int c = 0; c < (int)C; ++c) dotv = fmaf(__ldg(feat + base + (int64_t)c * HW) * inv, g[c], dotv);
+  for (int c = 0; c < (int)C; ++c)
+    atomicAdd(dfeat + base + (int64_t)c * HW, (g[c] - __ldg(feat + base + (int64_t)c * HW) * inv * dotv) * inv);
+}
+
 // dx = (g - xhat (xhat . g)) * inv_norm, scattered (atomic add) into NCHW dfeat
 __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const float* feat, int64_t C, int64_t HW,
                                                                 const int64_t* pixel_idx, int64_t n_rows, int normalize,
@@ -226,6 +305,11 @@ extern "C" int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t c
   if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !pixel_idx || n_rows <= 0) return SLCL_ERR_INVALID_ARGUMENT;
   if (!rows_bf16 && !rows_f32) return SLCL_ERR_INVALID_ARGUMENT;
   if (rows_bf16 && bf16_row_stride < channels) return SLCL_ERR_INVALID_ARGUMENT;
+  if (channels <= kDenseC && rows_bf16 && !rows_f32 && bf16_row_stride == kDenseC && aligned16(rows_bf16)) {
+    gather_rows_dense_kernel<<<(int)ceil_div<int64_t>(n_rows, kDenseRows), kDenseRows, 0, (cudaStream_t)stream_>>>(
+        feat, channels, pixels, pixel_idx, n_rows, normalize, reinterpret_cast<__nv_bfloat16*>(rows_bf16), inv_norm);
+    return check_launch("slcl_gather_unit_rows");
+  }
   const int blocks = (int)ceil_div<int64_t>(n_rows, kWarps);
   gather_rows_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream_>>>(feat, channels, pixels, pixel_idx, n_rows, normalize,
                                                                     reinterpret_cast<__nv_bfloat16*>(rows_bf16),
@@ -239,6 +323,12 @@ extern "C" int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t c
   if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !pixel_idx || n_rows <= 0 || !d_rows || !dfeat)
     return SLCL_ERR_INVALID_ARGUMENT;
   if (normalize && !inv_norm) return SLCL_ERR_INVALID_ARGUMENT;
+  if (channels <= kDenseC) {
+    const size_t smem = (size_t)kScatterRows * (channels + 1) * sizeof(float);          // <= 33 KB
+    scatter_rows_dense_kernel<<<(int)ceil_div<int64_t>(n_rows, kScatterRows), kScatterRows, smem, (cudaStream_t)stream_>>>(
+        feat, channels, pixels, pixel_idx, n_rows, normalize, d_rows, inv_norm, dfeat);
+    return check_launch("slcl_scatter_rows_bwd");
+  }
   const int blocks = (int)ceil_div<int64_t>(n_rows, kWarps);
   scatter_rows_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream_>>>(feat, channels, pixels, pixel_idx, n_rows,
                                                                      normalize, d_rows, inv_norm, dfeat);

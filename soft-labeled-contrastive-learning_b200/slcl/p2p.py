@@ -25,8 +25,10 @@ class _AutoClasses:
     """Lets the STOCK signatures (``SupConLoss()``, ``LocalConLoss()``: no ``n_class`` argument) reach the analytic
     tensor-core sweeps.  Those need class-index labels in [0, n_class), n_class <= 8 -- true for every label map of the
     reference (4 or 5 classes, config.py:9) but not guaranteed by the signature.  The first labelled call of a module
-    checks the range once on the host (one synchronisation in the module's lifetime); every later call checks it on the
-    device and poisons the loss with NaN if a label ever leaves the range (no synchronisation, no silent wrong value).
+    checks the range once on the host (one synchronisation in the module's lifetime).  Should a label leave the range
+    in a later call the loss comes out NaN, never silently wrong, and at no cost: in these losses every row is an
+    anchor, an anchor whose label is outside [0, n_class) has no class table, so the finishing kernel sees n_i = 0
+    positives and its row loss is 0/0 -- which the weighted sum carries to the result whatever the row's weight.
     ``n_class=0`` in the constructor forces the general sweeps (any integer labels), ``n_class=k`` trusts the caller."""
 
     def __init__(self, n_class):
@@ -34,7 +36,7 @@ class _AutoClasses:
         self.auto = None                # decided at the first labelled call
 
     def resolve(self, labels):
-        """-> (n_class for the sweeps, device flag `labels in range` or None)"""
+        """-> (n_class for the sweeps, device flag `labels in range` or None -- None since the kernels' own NaN covers it)"""
         if self.fixed is not None:
             return int(self.fixed), None
         if labels is None:
@@ -44,7 +46,7 @@ class _AutoClasses:
             self.auto = AUTO_N_CLASS if (lo >= 0 and hi < AUTO_N_CLASS) else 0
         if self.auto == 0:
             return 0, None
-        return self.auto, (labels.min() >= 0) & (labels.max() < self.auto)
+        return self.auto, None
 
 
 def _guard(loss, in_range):
@@ -102,8 +104,8 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
              selfcol=None, selfrow=None, n_batch=1):
     """``same_rows``: anchors and contrast rows are the same gathered rows (one gather); their labels may
     still differ (ISCL compares query labels with the anchors' dominant labels).
-    ``n_batch`` > 1: block-diagonal batches -- rows [z R/n, (z+1) R/n) of both sides only see each other (general mode,
-    R/n a multiple of 128).
+    ``n_batch`` > 1: block-diagonal batches -- rows [z R/n, (z+1) R/n) of both sides only see each other (R/n a
+    multiple of 128; either mode -- the analytic sweeps keep one table of per-class sums per batch).
     ``n_class`` in 1..8: labels are class indices in [0, n_class) and ids are unique -> analytic sweeps; the
     self-pair maps are derived from the ids unless given."""
     if same_rows and n_class == 0 and n_batch == 1 and idx_a.numel() >= _SORT_MIN_ROWS:
@@ -245,11 +247,11 @@ class BlockConLoss(nn.Module):
         t = self.supconloss.temperature
         if div == 0:
             return torch.zeros((), device=dev)
-        if self.batched and features.ndim == 5 and not self.supconloss.n_class:
+        n_class, in_range = self.supconloss._classes.resolve(labels)
+        if self.batched and features.ndim == 5:
             b, v = features.shape[:2]
             if (b * v * bs * bs) % 128 == 0:
-                return self._forward_batched(features, labels, div, t)
-        n_class, in_range = self.supconloss._classes.resolve(labels)
+                return _guard(self._forward_batched(features, labels, div, t, n_class), in_range)
         losses, flags = [], []
         for i in range(div):
             for j in range(div):
@@ -264,10 +266,11 @@ class BlockConLoss(nn.Module):
         keep = torch.stack(flags).float()
         return _guard((stacked * keep).sum() / keep.sum().clamp_min(1.0), in_range)   # :445-448 (0 when every tile is skipped)
 
-    def _forward_batched(self, features, labels, div, t):
+    def _forward_batched(self, features, labels, div, t, n_class=0):
         """All div x div tiles as ONE block-diagonal problem (one launch per tensor-core sweep instead of div^2
         separate SupCon calls): rows are ordered (tile, view, image, y, x); the per-tile weighting of :445-448 /
-        :465 -- fg_i / sum_tile fg, averaged over the tiles that have foreground -- is folded into the row weights."""
+        :465 -- fg_i / sum_tile fg, averaged over the tiles that have foreground -- is folded into the row weights.
+        ``n_class`` > 0 (class-index labels): the analytic sweeps with one table of per-class sums per tile."""
         b, v, c, h, w = features.shape
         dev = features.device
         bs = self.block_size
@@ -292,7 +295,8 @@ class BlockConLoss(nn.Module):
         else:
             lab = (ids % (m_tile // v)).to(torch.int32)                               # same pixel of the tile, other views
             weight = torch.full((idx.numel(),), 1.0 / (m_tile * n_tiles), device=dev)
-        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True, n_batch=n_tiles)
+        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True,
+                        n_class=n_class if labels is not None else 0, n_batch=n_tiles)
 
 
 def _balanced_prefix(perm, lp, rank, counts, valid, per: int, total: int):

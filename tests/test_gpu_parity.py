@@ -643,6 +643,7 @@ def test_kat7_local_and_block_con_loss(api, golden):
 
 @pytest.mark.parametrize("b,v,c,hw,bs,labelled", [
     (1, 2, 32, 64, 32, True),        # 4 tiles of 2048 rows: the block-diagonal batched sweeps
+    (1, 2, 32, 224, 224 // 7, True), # 49 tiles of 2048 rows: BASELINE cfg3's map, more tiles than SMs / row tiles
     (2, 2, 24, 48, 16, True),        # 9 tiles of 1024 rows, some all-background tiles
     (1, 2, 16, 64, 32, False),       # unlabelled: other views are the positives
     (1, 2, 16, 36, 12, True),        # 288 rows per tile (not a multiple of 128): the per-tile loop
@@ -659,11 +660,14 @@ def test_block_con_loss_vs_oracle(api, b, v, c, hw, bs, labelled):
     fo = f5.clone().requires_grad_(True)
     ref = O.block_con_loss(fo, lab, 0.7, bs)
     ref.backward()
-    f = f5.to(dev()).requires_grad_(True)
-    out = loss_mod.BlockConLoss(0.7, bs)(f, lab.to(dev()) if labelled else None)
-    out.backward()
-    close(out, ref, rtol=P2P_RTOL)
-    grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
+    # stock signature (class-index labels -> the analytic sweeps, one table of class sums per tile) and n_class=0
+    # (any integer labels -> the general sweeps)
+    for n_class in ((None, 0) if labelled else (None,)):
+        f = f5.to(dev()).requires_grad_(True)
+        out = loss_mod.BlockConLoss(0.7, bs, n_class=n_class)(f, lab.to(dev()) if labelled else None)
+        out.backward()
+        close(out, ref, rtol=P2P_RTOL)
+        grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
 
 
 def test_supcon_unnormalised_features_vs_oracle(api):
