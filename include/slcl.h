@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 110            /* major*100 + minor */
+#define SLCL_VERSION 111            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -304,6 +304,11 @@ int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, in
                           const int64_t* pixel_idx, int64_t n_rows, int normalize,
                           void* rows_bf16, int64_t bf16_row_stride, float* rows_f32, float* inv_norm,
                           slcl_stream_t stream);
+/* exp shift for un-normalised rows (SupConLoss does not normalise, utils/loss.py:342-349):
+ * shift[i] = |a_i| * max_j |b_j| / temperature, from the inv_norm outputs of slcl_gather_unit_rows.
+ * n_contrast <= 2^20 (SLCL_ERR_UNSUPPORTED beyond). */
+int slcl_p2p_shift(const float* inv_norm_a, int64_t n_anchor, const float* inv_norm_b, int64_t n_contrast,
+                   float temperature, float* shift, slcl_stream_t stream);
 /* scatter-add of row gradients back into an NCHW gradient map, through the
  * normalisation backward: dx = (g - xhat (xhat.g)) * inv_norm. */
 int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,

@@ -12,6 +12,8 @@
 // selection is bit-exact by construction.
 //
 // Roofline: HBM (integer / gather work; no tensor cores).
+#include <algorithm>
+
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -246,6 +248,26 @@ __global__ void __launch_bounds__(kScatterRows) scatter_rows_dense_kernel(const 
     atomicAdd(dfeat + base + (int64_t)c * HW, (g[c] - __ldg(feat + base + (int64_t)c * HW) * inv * dotv) * inv);
 }
 
+// exp shift of un-normalised rows: shift_i = |a_i| max_j |b_j| / T >= S_ij / T (the losses are shift-invariant; the bound
+// keeps exp() in range).  Every block finds the maximum itself (inv_b is a few hundred KB, L2-resident) -- one launch, no
+// grid barrier -- and writes its slice.  min over 1/|b| = 1 / max |b|.
+__global__ void __launch_bounds__(1024) p2p_shift_kernel(const float* inv_a, int64_t na, const float* inv_b, int64_t m, float inv_t,
+                                                         float* shift) {
+  __shared__ float red[32];
+  float lo = INFINITY;
+  for (int64_t j = threadIdx.x; j < m; j += 1024) lo = fminf(lo, __ldg(inv_b + j));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lo;
+  __syncthreads();
+  lo = red[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+  const float scale = (1.0f / lo) * inv_t;
+  for (int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x; i < na; i += (int64_t)gridDim.x * 1024)
+    shift[i] = (1.0f / inv_a[i]) * scale;
+}
+
 // dx = (g - xhat (xhat . g)) * inv_norm, scattered (atomic add) into NCHW dfeat
 __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const float* feat, int64_t C, int64_t HW,
                                                                 const int64_t* pixel_idx, int64_t n_rows, int normalize,
@@ -315,6 +337,17 @@ extern "C" int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t c
                                                                     reinterpret_cast<__nv_bfloat16*>(rows_bf16),
                                                                     bf16_row_stride, rows_f32, inv_norm);
   return check_launch("slcl_gather_unit_rows");
+}
+
+extern "C" int slcl_p2p_shift(const float* inv_norm_a, int64_t n_anchor, const float* inv_norm_b, int64_t n_contrast,
+                              float temperature, float* shift, slcl_stream_t stream_) {
+  if (!inv_norm_a || !inv_norm_b || !shift || n_anchor <= 0 || n_contrast <= 0 || !(temperature > 0.f))
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_contrast > (int64_t)1 << 20) return SLCL_ERR_UNSUPPORTED;          // every block reads all of inv_norm_b
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(n_anchor, 1024), n_contrast > 65536 ? 148 : 592);
+  p2p_shift_kernel<<<blocks, 1024, 0, (cudaStream_t)stream_>>>(inv_norm_a, n_anchor, inv_norm_b, n_contrast, 1.0f / temperature,
+                                                                shift);
+  return check_launch("slcl_p2p_shift");
 }
 
 extern "C" int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t channels, int64_t pixels,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "slcl_compact_by_class": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P, _SZ, _P]),
     "slcl_gather_unit_rows": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _I64, _P, _P, _P]),
     "slcl_scatter_rows_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _P, _P, _P]),
+    "slcl_p2p_shift": (C.c_int, [_P, _I64, _P, _I64, C.c_float, _P, _P]),
     "slcl_seg_workspace_bytes": (_SZ, [_I64, _I64, C.c_int]),
     "slcl_seg_fwd": (C.c_int, [_P, _P, _I64, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
     "slcl_seg_bwd": (C.c_int, [_P, _P, _I64, C.c_int, _I64, _P, _P, _P, _P]),

@@ -657,6 +657,28 @@ def _(feat, pixel_idx, normalize, want_bf16, want_f32):
             torch.empty((r if want_f32 else 0, c), dtype=_F32, device=feat.device), feat.new_empty(r))
 
 
+@torch.library.custom_op("slcl::p2p_shift", mutates_args=(), device_types="cuda")
+def p2p_shift(inv_norm_a: Tensor, inv_norm_b: Tensor, temperature: float) -> Tensor:
+    """exp shift of un-normalised rows, shift_i = |a_i| max_j |b_j| / T (one launch instead of five torch ops)."""
+    dev = require_cuda(inv_norm_a, inv_norm_b)
+    lib = _lib.load()
+    ia, ib = inv_norm_a.contiguous(), inv_norm_b.contiguous()
+    if ia.dtype != _F32 or ib.dtype != _F32:
+        raise ValueError("inv_norm tensors must be float32")
+    if ib.numel() > (1 << 20):          # beyond the single-launch kernel's range
+        return (1.0 / ia) * ((1.0 / ib).amax() / temperature)
+    shift = torch.empty_like(ia)
+    with _guard(dev):
+        st = lib.slcl_p2p_shift(ptr(ia), ia.numel(), ptr(ib), ib.numel(), float(temperature), ptr(shift), stream_ptr(dev))
+    check(st, "slcl_p2p_shift")
+    return shift
+
+
+@p2p_shift.register_fake
+def _(inv_norm_a, inv_norm_b, temperature):
+    return torch.empty_like(inv_norm_a)
+
+
 @torch.library.custom_op("slcl::scatter_rows_bwd", mutates_args=("dfeat",), device_types="cuda")
 def scatter_rows_bwd(feat: Tensor, pixel_idx: Tensor, normalize: bool, d_rows: Tensor, inv_norm: Tensor,
                      dfeat: Tensor) -> None:

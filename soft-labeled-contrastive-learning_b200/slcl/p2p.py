@@ -73,7 +73,7 @@ class _P2PLoss(torch.autograd.Function):
         if normalize:
             shift = torch.full_like(inv_a, 1.0 / temperature)
         else:   # upper bound of S_ij: |a_i| max_j |b_j| / T
-            shift = (1.0 / inv_a) * ((1.0 / inv_b).amax() / temperature)
+            shift = _ops.p2p_shift(inv_a, inv_b, temperature)
         keep = n_class > 0 and ctx.needs_input_grad[0]
         loss, stats, state = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol, keep,
                                           n_batch)

@@ -670,6 +670,18 @@ def test_block_con_loss_vs_oracle(api, b, v, c, hw, bs, labelled):
         grad_close(f.grad, fo.grad, rtol=P2P_RTOL, floor=0.5)
 
 
+def test_p2p_shift_is_the_row_norm_bound():
+    """slcl_p2p_shift: shift_i = |a_i| max_j |b_j| / T from the gather's inv_norm outputs (one launch)."""
+    from slcl import ops
+    gen = cases.g(4242)
+    for na, m in ((1, 1), (100, 37), (5000, 70001)):
+        inv_a = (torch.rand(na, generator=gen) + 0.05).to(dev())
+        inv_b = (torch.rand(m, generator=gen) + 0.05).to(dev())
+        out = ops.p2p_shift(inv_a, inv_b, 0.7)
+        ref = (1.0 / inv_a) * ((1.0 / inv_b).amax() / 0.7)
+        torch.testing.assert_close(out, ref, rtol=1e-6, atol=0)
+
+
 def test_supcon_unnormalised_features_vs_oracle(api):
     """SupConLoss does not normalise (utils/loss.py:342-349): rows of norm ~2, T = 0.5 -> the exp shift matters."""
     loss_mod, _ = api
