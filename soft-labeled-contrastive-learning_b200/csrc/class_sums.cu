@@ -410,6 +410,11 @@ __device__ __forceinline__ float v3_pair_sum(unsigned long long v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
   return lo + hi;
 }
+__device__ __forceinline__ float2 v3_lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float v3_lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -696,7 +701,7 @@ class_sums_v3_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_
 // form the cosines against the unit centres, derive label / selection mask / loss row / backward stash exactly as
 // proto_fwd_kernel's fused-target path does (same fmaf order over the channels, so labels, masks and the stash are
 // bit-identical), write the one-hot weight row, and the consumers accumulate the class sums from the same stage.
-//   warp 0: TMA producer   warps 1..4: pixel warps (every warp on every stage)   then n_cw consumers, 1 counter
+//   warp 0: TMA producer   warps 1..8: pixel warps (teams of two, round robin over the stages)   then n_cw consumers, 1 counter
 // Needs all C channels in one stage: C <= 16 * CPW (CPW = 4 or 8).
 // ---------------------------------------------------------------------------
 struct TileArgs {
@@ -712,31 +717,40 @@ struct TileArgs {
   double2* loss_partial;      // [gridDim.x] {sum sel*row, sum sel}
   float* partial;             // class sums per block [gridDim.x][K][C+1]
   unsigned int* ticket;
-  int n_cw, n_stages;
+  int n_cw, n_stages, n_teams;
 };
-// NPW pixel warps: 4 (every warp on every stage) or 8 (two teams of four on alternating stages; the ring depth is then
-// even, so a team always meets the same slots and sees every phase of their barriers).  8 goes with <= 8 consumer warps.
-template <int K, int CPW, int NPW>
-__global__ void __launch_bounds__(32 * (2 + NPW + (NPW == 8 ? 8 : 16)), 1)
+// Stages are 64 pixels x C channels (half the class-sum kernel's tile): the pixel work is latency-bound per warp -- a
+// serial walk over the channels, then ~300 dependent instructions of margin arithmetic -- so what sets the speed is how
+// many pixel warps are in flight on DIFFERENT stages, and that takes a deep ring of small stages (with 128-pixel stages
+// C = 128 leaves room for three, and one team of pixel warps: 318 us at cfg2, every role waiting on another; an
+// explicit suspend-time hint on the mbarrier waits changed nothing, and four pixels per lane -- fewer shared loads per
+// FMA but a third of the warps -- was slower, 368 us).
+// Pixel warps come in teams of two (32 pixels per warp, one per lane); a.n_teams (2..4) teams take the stages round
+// robin, and the ring depth is a multiple of n_teams so a team always meets the same slots and sees every phase of
+// their barriers.  Consumers own CPW channels and two pixels per lane.
+constexpr int kTPx = 64;                 // pixels per stage of the fused target kernel
+constexpr int kTileTeamsMax = 4;
+constexpr int kTilePixelWarps = 2 * kTileTeamsMax;
+template <int K, int CPW, int NCWMAX>
+__global__ void __launch_bounds__(32 * (2 + kTilePixelWarps + NCWMAX), 1)
 target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs a) {
-  constexpr int kTilePixelWarps = NPW;
-  constexpr int kTeams = NPW / 4;
+  const int kTeams = a.n_teams;
   constexpr int KP = K <= 4 ? 4 : 8;
   const int C = (int)a.channels;
   const int kStages = a.n_stages;
-  const int kStageBytes = C * kV3Px * 4;
+  const int kStageBytes = C * kTPx * 4;
   extern __shared__ __align__(128) uint8_t v3_smem[];
   const uint32_t pad = (128u - (v3_smem_u32(v3_smem) & 127u)) & 127u;                       // align the carve-up to 128 bytes
   uint8_t* base = v3_smem + pad;
-  const uint32_t sX_u32 = v3_smem_u32(base);                                               // [stages][C][128]
-  const uint32_t sWt_u32 = sX_u32 + (uint32_t)(kStages * kStageBytes);                     // [stages][K][128]
-  const uint32_t sC_u32 = sWt_u32 + (uint32_t)(kStages * K * kV3Px * 4);                   // [C][KP] unit centres
-  const size_t sC_off = (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kV3Px * 4);
-  V3Bars* bars = reinterpret_cast<V3Bars*>(base + (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kV3Px * 4) +
+  const uint32_t sX_u32 = v3_smem_u32(base);                                               // [stages][C][64]
+  const uint32_t sWt_u32 = sX_u32 + (uint32_t)(kStages * kStageBytes);                     // [stages][K][64]
+  const uint32_t sC_u32 = sWt_u32 + (uint32_t)(kStages * K * kTPx * 4);                    // [C][KP] unit centres
+  const size_t sC_off = (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kTPx * 4);
+  V3Bars* bars = reinterpret_cast<V3Bars*>(base + (size_t)kStages * ((size_t)kStageBytes + (size_t)K * kTPx * 4) +
                                            (size_t)C * KP * 4);
-  __shared__ double s_red[2][8];
+  __shared__ double s_red[2][kTilePixelWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t tiles_per_image = (a.pixels + kV3Px - 1) / kV3Px;
+  const int64_t tiles_per_image = (a.pixels + kTPx - 1) / kTPx;
   const int64_t n_tiles = a.batch * tiles_per_image;
   const int64_t n_iter = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -751,7 +765,7 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_feat)) : "memory");
     for (int s = 0; s < kStages; ++s) {
       v3_mbar_init(&bars->x_full[s], 1);
-      v3_mbar_init(&bars->w_full[s], 4);
+      v3_mbar_init(&bars->w_full[s], 2);
       v3_mbar_init(&bars->empty[s], a.n_cw + 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -761,7 +775,7 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
     int64_t b; int64_t t, step, per;
     __device__ TilePos(int64_t tile0, int64_t step_, int64_t per_) : step(step_), per(per_) { b = tile0 / per_; t = tile0 - b * per_; }
     __device__ __forceinline__ void next() { t += step; if (t >= per) { const int64_t q = t / per; b += q; t -= q * per; } }
-    __device__ __forceinline__ int p0() const { return (int)(t * kV3Px); }
+    __device__ __forceinline__ int p0() const { return (int)(t * kTPx); }
   };
 
   if (warp == 0) {
@@ -777,69 +791,71 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
     }
   } else if (warp <= kTilePixelWarps) {
     // ===================== pixel warps: cosines, pseudo label, loss row, stash, one-hot weights =====================
-    const int team = (warp - 1) >> 2;
-    const int px = ((warp - 1) & 3) * 32 + lane;
+    const int team = (warp - 1) >> 1;
+    const int px = ((warp - 1) & 1) * 32 + lane;
     double loss_acc = 0.0, sel_acc = 0.0;
-    V3Pos bpos(team, kStages);
-    TilePos tp(blockIdx.x + (int64_t)team * gridDim.x, (int64_t)kTeams * gridDim.x, tiles_per_image);
-    for (int64_t it = team; it < n_iter; it += kTeams, bpos.advance(kTeams), tp.next()) {
-      const int s = bpos.slot;
-      const int p0 = tp.p0();
-      const bool inside = (int64_t)p0 + px < a.pixels;
-      v3_mbar_wait(&bars->x_full[s], (uint32_t)bpos.phase);
-      // plain C++ loads through pointers that stay in the shared window (offsets from the extern array itself), so the
-      // compiler emits LDS AND may software-pipeline them across the unrolled channel loop
-      const float* xs = reinterpret_cast<const float*>(v3_smem + pad + (size_t)s * kStageBytes) + px;
-      const float4* cs = reinterpret_cast<const float4*>(v3_smem + pad + sC_off);
-      float nrm = 0.f, dot[K];
+    if (team < kTeams) {
+      V3Pos bpos(team, kStages);
+      TilePos tp(blockIdx.x + (int64_t)team * gridDim.x, (int64_t)kTeams * gridDim.x, tiles_per_image);
+      for (int64_t it = team; it < n_iter; it += kTeams, bpos.advance(kTeams), tp.next()) {
+        const int s = bpos.slot;
+        const int p0 = tp.p0();
+        const bool inside = (int64_t)p0 + px < a.pixels;
+        v3_mbar_wait(&bars->x_full[s], (uint32_t)bpos.phase);
+        // plain C++ loads through pointers that stay in the shared window (offsets from the extern array itself), so the
+        // compiler emits LDS AND may software-pipeline them across the unrolled channel loop
+        const float* xs = reinterpret_cast<const float*>(v3_smem + pad + (size_t)s * kStageBytes) + px;
+        const float4* cs = reinterpret_cast<const float4*>(v3_smem + pad + sC_off);
+        float nrm = 0.f, dot[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) dot[k] = 0.f;
+        for (int k = 0; k < K; ++k) dot[k] = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < C; ++c) {
-        const float x = xs[c * kV3Px];
-        float ck[8];
-        { const float4 t = cs[c * (KP / 4)]; ck[0] = t.x; ck[1] = t.y; ck[2] = t.z; ck[3] = t.w; }
-        if constexpr (K > 4) { const float4 t = cs[c * (KP / 4) + 1]; ck[4] = t.x; ck[5] = t.y; ck[6] = t.z; ck[7] = t.w; }
-        nrm = fmaf(x, x, nrm);
+        for (int c = 0; c < C; ++c) {
+          const float x = xs[c * kTPx];
+          float ck[8];
+          { const float4 t = cs[c * (KP / 4)]; ck[0] = t.x; ck[1] = t.y; ck[2] = t.z; ck[3] = t.w; }
+          if constexpr (K > 4) { const float4 t = cs[c * (KP / 4) + 1]; ck[4] = t.x; ck[5] = t.y; ck[6] = t.z; ck[7] = t.w; }
+          nrm = fmaf(x, x, nrm);
 #pragma unroll
-        for (int k = 0; k < K; ++k) dot[k] = fmaf(x, ck[k], dot[k]);
+          for (int k = 0; k < K; ++k) dot[k] = fmaf(x, ck[k], dot[k]);
+        }
+        // generate_pseudo_label on the cosines (same arithmetic as pseudo_label_kernel / proto_fwd_kernel's fused path)
+        const float n = fmaxf(sqrtf(nrm), 1e-12f);
+        float t1 = -INFINITY, t2 = -INFINITY;
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float cs_ = dot[k] / n;
+          if (cs_ > t1) { t2 = t1; t1 = cs_; best = k; }
+          else if (cs_ > t2) { t2 = cs_; }
+        }
+        const float selv = (t1 - t2 > a.sel_threshold) ? 1.0f : 0.0f;
+        const float inv_n = 1.0f / n;
+        float cosv[K], M[K], coef[K + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { cosv[k] = dot[k] * inv_n; M[k] = (best == k) ? 1.0f : 0.0f; }
+        const float row = margin_row<K>(cosv, M, selv, inv_n, a.mc, coef);
+        const uint32_t wd = sWt_u32 + (uint32_t)((s * K * kTPx + px) * 4);
+        const float wsel = a.weight_by_sel ? selv : 1.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) v3_sts32(wd + (uint32_t)(k * kTPx * 4), (inside && best == k) ? wsel : 0.f);
+        if (inside) {
+          const int64_t pix = tp.b * a.pixels + p0 + px;
+          a.out_label[pix] = best;
+          a.out_sel[pix] = selv;
+#pragma unroll
+          for (int k = 0; k <= K; ++k) a.stash[(int64_t)k * a.n_total + pix] = coef[k];
+          loss_acc += (double)(selv * row);
+          sel_acc += (double)selv;
+        }
+        __syncwarp();
+        if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
       }
-      // generate_pseudo_label on the cosines (same arithmetic as pseudo_label_kernel / proto_fwd_kernel's fused path)
-      const float n = fmaxf(sqrtf(nrm), 1e-12f);
-      float t1 = -INFINITY, t2 = -INFINITY;
-      int best = 0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float cs = dot[k] / n;
-        if (cs > t1) { t2 = t1; t1 = cs; best = k; }
-        else if (cs > t2) { t2 = cs; }
-      }
-      const float selv = (t1 - t2 > a.sel_threshold) ? 1.0f : 0.0f;
-      const float inv_n = 1.0f / n;
-      float cosv[K], M[K], coef[K + 1];
-#pragma unroll
-      for (int k = 0; k < K; ++k) { cosv[k] = dot[k] * inv_n; M[k] = (best == k) ? 1.0f : 0.0f; }
-      const float row = margin_row<K>(cosv, M, selv, inv_n, a.mc, coef);
-      const uint32_t wd = sWt_u32 + (uint32_t)((s * K * kV3Px + px) * 4);
-      const float wsel = a.weight_by_sel ? selv : 1.0f;
-#pragma unroll
-      for (int k = 0; k < K; ++k) v3_sts32(wd + (uint32_t)(k * kV3Px * 4), (inside && best == k) ? wsel : 0.f);
-      if (inside) {
-        const int64_t pix = tp.b * a.pixels + p0 + px;
-        a.out_label[pix] = best;
-        a.out_sel[pix] = selv;
-#pragma unroll
-        for (int k = 0; k <= K; ++k) a.stash[(int64_t)k * a.n_total + pix] = coef[k];
-        loss_acc += (double)(selv * row);
-        sel_acc += (double)selv;
-      }
-      __syncwarp();
-      if (lane == 0) v3_mbar_arrive(&bars->w_full[s]);
     }
     loss_acc = warp_sum(loss_acc);
     sel_acc = warp_sum(sel_acc);
     if (lane == 0) { s_red[0][warp - 1] = loss_acc; s_red[1][warp - 1] = sel_acc; }
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");         // the pixel warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kTilePixelWarps) : "memory");         // the pixel warps only
     if (warp == 1 && lane == 0) {
       double l = 0.0, sv = 0.0;
 #pragma unroll
@@ -849,7 +865,7 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
   } else {
     const int cw = warp - 1 - kTilePixelWarps;
     if (cw < a.n_cw) {
-      // ===================== consumers (as class_sums_v3_kernel) =====================
+      // ===================== consumers: CPW channels per warp, two pixels per lane =====================
       float acc[CPW][K];
 #pragma unroll
       for (int q = 0; q < K; ++q)
@@ -861,20 +877,18 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
         const uint32_t par = (uint32_t)cpos.phase;
         v3_mbar_wait(&bars->x_full[s], par);
         v3_mbar_wait(&bars->w_full[s], par);
-        const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + ((cw * CPW) * kV3Px + lane * 4) * 4);
-        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kV3Px + lane * 4) * 4);
-        float4 w[K];
+        const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + ((cw * CPW) * kTPx + lane * 2) * 4);
+        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kTPx + lane * 2) * 4);
+        float2 w[K];
 #pragma unroll
-        for (int q = 0; q < K; ++q) w[q] = v3_lds128(ws + q * kV3Px * 4);
+        for (int q = 0; q < K; ++q) w[q] = v3_lds64f(ws + q * kTPx * 4);
 #pragma unroll
         for (int j = 0; j < CPW; ++j) {
-          const float4 x = v3_lds128(xs + j * kV3Px * 4);
+          const float2 x = v3_lds64f(xs + j * kTPx * 4);
 #pragma unroll
           for (int q = 0; q < K; ++q) {
             acc[j][q] = fmaf(w[q].x, x.x, acc[j][q]);
             acc[j][q] = fmaf(w[q].y, x.y, acc[j][q]);
-            acc[j][q] = fmaf(w[q].z, x.z, acc[j][q]);
-            acc[j][q] = fmaf(w[q].w, x.w, acc[j][q]);
           }
         }
         __syncwarp();
@@ -899,11 +913,11 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
       for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
         const int s = cpos.slot;
         v3_mbar_wait(&bars->w_full[s], (uint32_t)cpos.phase);
-        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kV3Px + lane * 4) * 4);
+        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kTPx + lane * 2) * 4);
 #pragma unroll
         for (int q = 0; q < K; ++q) {
-          const float4 w = v3_lds128(ws + q * kV3Px * 4);
-          cacc[q] += (w.x + w.y) + (w.z + w.w);
+          const float2 w = v3_lds64f(ws + q * kTPx * 4);
+          cacc[q] += w.x + w.y;
         }
         __syncwarp();
         if (lane == 0) v3_mbar_arrive(&bars->empty[s]);
@@ -1678,46 +1692,50 @@ TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
   TilePlan p{};
   p.ok = false;
   if (C < 1 || C > 128 || K < 2 || K > kMaxK || pixels % 4 != 0 || pixels > INT_MAX || batch > INT_MAX) return p;
-  // register tile and pixel-warp count per shape (acc[CPW][K] <= 40 registers; 8 pixel warps need <= 8 consumer warps)
-  if (C <= 32) { p.cpw = 4; p.npw = 8; }
-  else if (C <= 64 && K <= 5) { p.cpw = 8; p.npw = 8; }
-  else if (C <= 64) { p.cpw = 4; p.npw = 4; }
-  else if (K <= 5) { p.cpw = 8; p.npw = 4; }
+  // register tile per shape (acc[CPW][K] <= 40 registers)
+  if (C <= 32) p.cpw = 4;
+  else if (C <= 64 && K <= 5) p.cpw = 8;
+  else if (C <= 64) p.cpw = 4;
+  else if (K <= 5) p.cpw = 8;
   else return p;
   p.n_cw = (int)ceil_div<int64_t>(C, p.cpw);
   const int kp = K <= 4 ? 4 : 8;
-  const size_t stage = (size_t)(C + K) * kV3Px * 4;
+  const size_t stage = (size_t)(C + K) * kTPx * 4;
   const size_t fixed = 128 + (size_t)C * kp * 4 + sizeof(V3Bars) + 64;
-  int n = (int)((200 * 1024 - fixed) / stage);
+  int n = (int)((216 * 1024 - fixed) / stage);          // C = 128, K = 5: six 33 KB stages
   if (n > kV3MaxStages) n = kV3MaxStages;
-  n = n / (p.npw / 4) * (p.npw / 4);                    // a multiple of the pixel-warp teams
-  if (n < 2) return p;
+  if (n < 4) return p;
+  // teams of pixel warps: four (measured at cfg2, C = 128, six stages fit: 4 teams x 1 slot 290 us, 3 x 2 305 us,
+  // 2 x 3 344 us -- pixel warps in flight count for more than spare slots)
+  p.npw = 4;
+  { const char* e = getenv("SLCL_TILE_TEAMS"); if (e && atoi(e) >= 1 && atoi(e) <= kTileTeamsMax && atoi(e) <= n) p.npw = atoi(e); }
+  n = n / p.npw * p.npw;
   p.stages = n;
   p.smem = fixed + (size_t)n * stage;
-  const int64_t n_tiles = batch * ceil_div<int64_t>(pixels, kV3Px);
+  const int64_t n_tiles = batch * ceil_div<int64_t>(pixels, kTPx);
   p.grid = (unsigned)std::min<int64_t>(sm_count(), n_tiles);
   p.ok = true;
   return p;
 }
-template <int K, int CPW, int NPW>
+template <int K, int CPW, int NCWMAX>
 int launch_tile(const CUtensorMap& map, const TileArgs& a, const TilePlan& p, cudaStream_t stream) {
   static bool attr_set_dev[64] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(target_tile_kernel<K, CPW, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(target_tile_kernel<K, CPW, NCWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(target_tile_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
-  launch_pdl(target_tile_kernel<K, CPW, NPW>, dim3(p.grid), dim3(32 * (2 + NPW + p.n_cw)), p.smem, stream, map, a);
+  launch_pdl(target_tile_kernel<K, CPW, NCWMAX>, dim3(p.grid), dim3(32 * (2 + kTilePixelWarps + p.n_cw)), p.smem, stream, map, a);
   return SLCL_OK;
 }
 template <int K>
 int launch_tile_k(const CUtensorMap& map, const TileArgs& a, const TilePlan& p, cudaStream_t stream) {
-  if (p.cpw == 4 && p.npw == 8) return launch_tile<K, 4, 8>(map, a, p, stream);
-  if (p.cpw == 4) return launch_tile<K, 4, 4>(map, a, p, stream);
+  if (p.cpw == 4 && p.n_cw <= 8) return launch_tile<K, 4, 8>(map, a, p, stream);
+  if (p.cpw == 4) return launch_tile<K, 4, 16>(map, a, p, stream);
   if constexpr (K <= 5) {
-    if (p.npw == 8) return launch_tile<K, 8, 8>(map, a, p, stream);
-    return launch_tile<K, 8, 4>(map, a, p, stream);
+    if (p.n_cw <= 8) return launch_tile<K, 8, 8>(map, a, p, stream);
+    return launch_tile<K, 8, 16>(map, a, p, stream);
   }
   return SLCL_ERR_UNSUPPORTED;
 }
@@ -1751,7 +1769,7 @@ extern "C" int slcl_target_step(const float* feat, int64_t batch, int64_t channe
   {
     const cuuint64_t dims[3] = {(cuuint64_t)pixels, (cuuint64_t)channels, (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)pixels * 4, (cuuint64_t)pixels * channels * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kV3Px, (cuuint32_t)channels, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)kTPx, (cuuint32_t)channels, 1};
     int st = v3_encode(&map, feat, dims, strides, box);
     if (st != SLCL_OK) return st;
   }
@@ -1764,7 +1782,7 @@ extern "C" int slcl_target_step(const float* feat, int64_t batch, int64_t channe
   a.loss_partial = reinterpret_cast<double2*>(ws);
   a.partial = reinterpret_cast<float*>(ws + align_up(blocks * sizeof(double2), 256));
   a.ticket = reinterpret_cast<unsigned int*>(ws + (workspace_bytes - kTicketBytes) / 16 * 16);
-  a.n_cw = p.n_cw; a.n_stages = p.stages;
+  a.n_cw = p.n_cw; a.n_stages = p.stages; a.n_teams = p.npw;
   launch_prep_centres(centres, (int)channels, K, 1, cstate, stream);
   int st = SLCL_ERR_UNSUPPORTED;
   switch (K) {
