@@ -644,6 +644,7 @@ def test_kat7_local_and_block_con_loss(api, golden):
 @pytest.mark.parametrize("b,v,c,hw,bs,labelled", [
     (1, 2, 32, 64, 32, True),        # 4 tiles of 2048 rows: the block-diagonal batched sweeps
     (1, 2, 32, 224, 224 // 7, True), # 49 tiles of 2048 rows: BASELINE cfg3's map, more tiles than SMs / row tiles
+    (1, 2, 16, 288, 8, True),        # 1296 tiles of 128 rows: more batches than finishing blocks (one table block per tile)
     (2, 2, 24, 48, 16, True),        # 9 tiles of 1024 rows, some all-background tiles
     (1, 2, 16, 64, 32, False),       # unlabelled: other views are the positives
     (1, 2, 16, 36, 12, True),        # 288 rows per tile (not a multiple of 128): the per-tile loop
