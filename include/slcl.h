@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 111            /* major*100 + minor */
+#define SLCL_VERSION 112            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -300,6 +300,24 @@ size_t slcl_compact_workspace_bytes(int64_t n_pixels, int n_class);
 int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, int n_class,
                           int64_t* counts, int64_t* offsets, int64_t* index,
                           void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+/* Class-balanced two-phase pick of the sampler from ONE permutation `perm` [N] of the pixel indices
+ * (torch.randperm) and the label map `labels` [N]: class k contributes its first `per` pixels in permutation order
+ * (class-major output); slots a short class leaves open take the next unpicked labelled pixels in permutation order.
+ * Two quotas at once (anchors / contrast rows; per_b = 0: one): out_q [n_class * per_q] pixel indices, filled_q [1] =
+ * slots actually filled (< n_class * per_q: too few labelled pixels, the open slots hold 0).  No host synchronisation. */
+size_t slcl_sample_balanced_workspace_bytes(int64_t n_pixels, int n_class);
+int slcl_sample_balanced(const int64_t* perm, const int64_t* labels, int64_t n_pixels, int n_class,
+                         int64_t per_a, int64_t* out_a, int64_t* filled_a,
+                         int64_t per_b, int64_t* out_b, int64_t* filled_b,
+                         void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+/* Self-pair maps of the analytic pixel<->pixel mode for ids in [0, n_ids) (pixel indices), unique within each side:
+ * a_selfcol [A] = contrast row carrying anchor i's id or -1, b_selfrow [M] = its inverse.  workspace: 8 * n_ids bytes. */
+int slcl_self_maps(const int64_t* id_a, int64_t n_anchor, const int64_t* id_b, int64_t n_contrast, int64_t n_ids,
+                   int32_t* a_selfcol, int32_t* b_selfrow, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+/* {label, id} rows of slcl_p2p_fwd straight from the label map: meta [pad64(R), 2] int32 = {labels[idx[r]], idx[r]},
+ * pad rows {INT_MIN, INT_MIN}.  n_pixels <= INT_MAX. */
+int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,
+                   slcl_stream_t stream);
 int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
                           const int64_t* pixel_idx, int64_t n_rows, int normalize,
                           void* rows_bf16, int64_t bf16_row_stride, float* rows_f32, float* inv_norm,

@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <limits.h>
 #include <math.h>
 
 namespace slcl {
@@ -24,11 +25,17 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 4096;          // pixels per block (16 rounds of 256)
 constexpr int KM = SLCL_MAX_CLASSES;
+// pixels per block of the compaction kernels (a multiple of 256): 4096 for large maps, 1024 below 2M pixels so that a
+// 64K-pixel map (cfg3) still spreads over 64 blocks
+inline int compact_chunk(int64_t n) { return n >= ((int64_t)1 << 21) ? 4096 : 1024; }
 
 // phase 1: per-block class histogram -> hist[block][K]
-__global__ void __launch_bounds__(kThreads) compact_count_kernel(const int64_t* labels, int64_t n, int K, int* hist) {
+// `skip`: optional device flag -- the launch does nothing when *skip == 0 (the sampler's second-phase compactions are
+// only needed when some class is short; the decision is taken on the device so the launch sequence stays static)
+__global__ void __launch_bounds__(kThreads) compact_count_kernel(const int64_t* labels, int64_t n, int K, int* hist, int kChunk,
+                                                                 const int64_t* skip) {
+  if (skip != nullptr && *skip == 0) return;
   __shared__ int s_cnt[KM];
   if (threadIdx.x < KM) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -57,7 +64,8 @@ __global__ void __launch_bounds__(kThreads) compact_count_kernel(const int64_t* 
 
 // phase 2 (one block): counts, class offsets, and per-block start offsets (in place in hist)
 __global__ void __launch_bounds__(kThreads) compact_scan_kernel(int* hist, int n_blocks, int K, int64_t* counts,
-                                                                int64_t* offsets, int64_t* block_base) {
+                                                                int64_t* offsets, int64_t* block_base, const int64_t* skip) {
+  if (skip != nullptr && *skip == 0) return;
   __shared__ long long s_total[KM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warp k scans class k over the blocks (sequential over 32-wide strips: n_blocks is small)
@@ -85,7 +93,8 @@ __global__ void __launch_bounds__(kThreads) compact_scan_kernel(int* hist, int n
 // phase 3: stable scatter
 __global__ void __launch_bounds__(kThreads) compact_write_kernel(const int64_t* labels, int64_t n, int K,
                                                                  const int64_t* offsets, const int64_t* block_base,
-                                                                 int64_t* index) {
+                                                                 int64_t* index, int kChunk, const int64_t* skip) {
+  if (skip != nullptr && *skip == 0) return;
   __shared__ int s_warp[KM][kWarps];
   __shared__ long long s_run[KM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,6 +124,93 @@ __global__ void __launch_bounds__(kThreads) compact_write_kernel(const int64_t* 
     }
     __syncthreads();
   }
+}
+
+// ---- class-balanced two-phase pick (the sampler of SURVEY.md 8(c)-3; test-side restatement: sample_class_balanced) ----
+// lp[i] = labels[perm[i]]: the label map read in permutation order
+__global__ void __launch_bounds__(kThreads) gather_labels_kernel(const int64_t* perm, const int64_t* labels, int64_t n, int64_t* lp) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = perm[i];
+  lp[i] = (p >= 0 && p < n) ? labels[p] : -1;
+}
+
+struct PickArgs {
+  const int64_t* perm; const int64_t* counts; const int64_t* offsets; const int64_t* index;
+  int K;
+  int64_t per[2];          // picks per class of the two quotas (0 = quota unused)
+  int64_t* out[2];         // [K * per] pixel indices, class-major
+  int64_t* flag[2];        // [N] in permutation order, preset to -1: 0 marks a labelled pixel phase 1 left unpicked
+  int64_t* need[2];        // [1] slots phase 1 leaves open
+};
+// One thread per entry e of the stable class-major compaction of lp: class k, rank r within the class (in permutation
+// order).  Phase 1: the first `per` pixels of every class, class-major.
+__global__ void __launch_bounds__(kThreads) balanced_pick_kernel(const PickArgs a) {
+  __shared__ long long s_off[KM + 1], s_base[2][KM];
+  if (threadIdx.x == 0) {
+    for (int k = 0; k <= a.K; ++k) s_off[k] = a.offsets[k];
+    for (int q = 0; q < 2; ++q) {
+      long long base = 0;
+      for (int k = 0; k < a.K; ++k) { s_base[q][k] = base; base += a.counts[k] < a.per[q] ? a.counts[k] : a.per[q]; }
+      if (blockIdx.x == 0 && a.out[q] != nullptr) *a.need[q] = a.K * a.per[q] - base;
+    }
+  }
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (e >= s_off[a.K]) return;
+  int k = 0;
+  while (e >= s_off[k + 1]) ++k;
+  const int64_t r = e - s_off[k], p = a.index[e], pix = a.perm[p];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (a.out[q] == nullptr) continue;
+    if (r < a.per[q]) a.out[q][s_base[q][k] + r] = pix;
+    else a.flag[q][p] = 0;
+  }
+}
+// Phase 2: the slots a short class leaves open take the next unpicked labelled pixels in permutation order (`index2`:
+// their positions, compacted in order); slots that stay open hold 0 and `filled` < K * per tells the caller.
+__global__ void __launch_bounds__(kThreads) balanced_fill_kernel(const int64_t* perm, const int64_t* need_p, int64_t total,
+                                                                 const int64_t* counts2, const int64_t* index2, int64_t* out,
+                                                                 int64_t* filled) {
+  const int64_t need = *need_p;
+  if (need == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) *filled = total; return; }
+  const int64_t n1 = total - need, avail = counts2[0], m = need < avail ? need : avail;
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < need; r += (int64_t)gridDim.x * kThreads)
+    out[n1 + r] = r < m ? perm[index2[r]] : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *filled = n1 + m;
+}
+
+// ---- self-pair maps for ids in [0, n_ids) (pixel indices): two lookup tables instead of a sort ----
+__global__ void __launch_bounds__(kThreads) self_table_kernel(const int64_t* id_a, int64_t na, const int64_t* id_b, int64_t m,
+                                                              int64_t n_ids, int32_t* table_a, int32_t* table_b) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < na) { const int64_t v = id_a[i]; if (v >= 0 && v < n_ids) table_a[v] = (int32_t)i; }
+  if (i < m) { const int64_t v = id_b[i]; if (v >= 0 && v < n_ids) table_b[v] = (int32_t)i; }
+}
+__global__ void __launch_bounds__(kThreads) self_lookup_kernel(const int64_t* id_a, int64_t na, const int64_t* id_b, int64_t m,
+                                                               int64_t n_ids, const int32_t* table_a, const int32_t* table_b,
+                                                               int32_t* selfcol, int32_t* selfrow) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < na) { const int64_t v = id_a[i]; selfcol[i] = (v >= 0 && v < n_ids) ? table_b[v] : -1; }
+  if (i < m) { const int64_t v = id_b[i]; selfrow[i] = (v >= 0 && v < n_ids) ? table_a[v] : -1; }
+}
+
+// ---- {label, id} metadata rows of the tensor-core sweeps straight from the label map ----
+// meta[r] = {labels[idx[r]], (int)idx[r]} for r < n_rows, {INT_MIN, INT_MIN} for the pad rows up to n_pad
+__global__ void __launch_bounds__(kThreads) rows_meta_kernel(const int64_t* labels, int64_t n_pixels, const int64_t* idx,
+                                                             int64_t n_rows, int64_t n_pad, int2* meta) {
+  const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (r >= n_pad) return;
+  int2 v = make_int2(INT_MIN, INT_MIN);
+  if (r < n_rows) {
+    const int64_t p = idx[r];
+    if (p >= 0 && p < n_pixels) {
+      const long long lab = labels[p];
+      v = make_int2(lab >= INT_MIN + 2 && lab <= INT_MAX ? (int)lab : INT_MIN + 1, (int)p);
+    }
+  }
+  meta[r] = v;
 }
 
 // One warp per sampled row: gather C strided values, L2-normalise, write row-major.
@@ -280,6 +376,31 @@ __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const float* fea
   const int64_t b = pix / HW, p = pix - b * HW;
   const int64_t base = b * C * HW + p;
   const float inv = normalize ? inv_norm[row] : 1.0f;
+  // C <= 256: feature row and gradient row stay in registers -- all the sparse loads of the row are in flight at once.
+  // (The adds stay fire-and-forget reductions even where every pixel is known to occur once: a plain read-modify-write
+  // was measured slower, 88 vs 74 us per launch at cfg3 -- the load puts a second L2 round trip on every element.)
+  constexpr int kRegs = 8;
+  if (C <= 32 * kRegs) {
+    float x[kRegs], g[kRegs];
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+      const int64_t c = lane + 32 * j;
+      x[j] = (normalize && c < C) ? __ldg(feat + base + c * HW) * inv : 0.f;
+      g[j] = c < C ? __ldg(d_rows + row * C + c) : 0.f;
+    }
+    float dotv = 0.f;
+    if (normalize) {
+#pragma unroll
+      for (int j = 0; j < kRegs; ++j) dotv = fmaf(x[j], g[j], dotv);
+      dotv = warp_sum(dotv);
+    }
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+      const int64_t c = lane + 32 * j;
+      if (c < C) atomicAdd(dfeat + base + c * HW, normalize ? (g[j] - x[j] * dotv) * inv : g[j]);
+    }
+    return;
+  }
   float dotv = 0.f;
   if (normalize) {
     for (int64_t c = lane; c < C; c += 32) dotv = fmaf(feat[base + c * HW] * inv, d_rows[row * C + c], dotv);
@@ -299,9 +420,26 @@ using namespace slcl;
 
 extern "C" size_t slcl_compact_workspace_bytes(int64_t n_pixels, int n_class) {
   if (n_pixels <= 0 || n_class < 1 || n_class > KM) return 0;
-  size_t blocks = (size_t)ceil_div<int64_t>(n_pixels, kChunk);
+  size_t blocks = (size_t)ceil_div<int64_t>(n_pixels, compact_chunk(n_pixels));
   return align_up(blocks * n_class * sizeof(int), 256) + align_up(blocks * n_class * sizeof(int64_t), 256);
 }
+
+namespace slcl {
+namespace {
+// the three launches of the stable compaction; `skip` (device flag, may be null): do nothing when *skip == 0
+void launch_compact(const int64_t* labels, int64_t n_pixels, int n_class, int64_t* counts, int64_t* offsets, int64_t* index,
+                    void* workspace, const int64_t* skip, cudaStream_t stream) {
+  const int chunk = compact_chunk(n_pixels);
+  const int blocks = (int)ceil_div<int64_t>(n_pixels, chunk);
+  int* hist = reinterpret_cast<int*>(workspace);
+  int64_t* block_base =
+      reinterpret_cast<int64_t*>((char*)workspace + align_up((size_t)blocks * n_class * sizeof(int), 256));
+  compact_count_kernel<<<blocks, kThreads, 0, stream>>>(labels, n_pixels, n_class, hist, chunk, skip);
+  compact_scan_kernel<<<1, kThreads, 0, stream>>>(hist, blocks, n_class, counts, offsets, block_base, skip);
+  compact_write_kernel<<<blocks, kThreads, 0, stream>>>(labels, n_pixels, n_class, offsets, block_base, index, chunk, skip);
+}
+}  // namespace
+}  // namespace slcl
 
 extern "C" int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, int n_class, int64_t* counts,
                                      int64_t* offsets, int64_t* index, void* workspace, size_t workspace_bytes,
@@ -310,15 +448,92 @@ extern "C" int slcl_compact_by_class(const int64_t* labels, int64_t n_pixels, in
   if (n_class < 1 || n_class > KM) return SLCL_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < slcl_compact_workspace_bytes(n_pixels, n_class) || !aligned16(workspace))
     return SLCL_ERR_WORKSPACE;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int blocks = (int)ceil_div<int64_t>(n_pixels, kChunk);
-  int* hist = reinterpret_cast<int*>(workspace);
-  int64_t* block_base =
-      reinterpret_cast<int64_t*>((char*)workspace + align_up((size_t)blocks * n_class * sizeof(int), 256));
-  compact_count_kernel<<<blocks, kThreads, 0, stream>>>(labels, n_pixels, n_class, hist);
-  compact_scan_kernel<<<1, kThreads, 0, stream>>>(hist, blocks, n_class, counts, offsets, block_base);
-  compact_write_kernel<<<blocks, kThreads, 0, stream>>>(labels, n_pixels, n_class, offsets, block_base, index);
+  launch_compact(labels, n_pixels, n_class, counts, offsets, index, workspace, nullptr, (cudaStream_t)stream_);
   return check_launch("slcl_compact_by_class");
+}
+
+// workspace of slcl_sample_balanced: lp [N] | counts [K] offsets [K+1] | index [N] | flags 2 x [N] | need 2 | per quota:
+// counts2 [1] offsets2 [2] index2 [N] | compaction scratch (shared by the three compactions, they run one after the other)
+namespace slcl {
+namespace {
+struct SampleWs { int64_t *lp, *counts, *offsets, *index, *flag[2], *need, *counts2[2], *offsets2[2], *index2[2]; void* scratch; size_t total; };
+SampleWs carve_sample(void* ws, int64_t n, int K) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t nb = (size_t)n * sizeof(int64_t);
+  size_t o_lp = take(nb), o_c = take((size_t)K * 8), o_o = take((size_t)(K + 1) * 8), o_i = take(nb), o_f = take(2 * nb), o_n = take(16);
+  size_t o_c2[2], o_o2[2], o_i2[2];
+  for (int q = 0; q < 2; ++q) { o_c2[q] = take(8); o_o2[q] = take(16); o_i2[q] = take(nb); }
+  size_t o_s = take(slcl_compact_workspace_bytes(n, K > 1 ? K : 1));
+  SampleWs w{};
+  char* b = reinterpret_cast<char*>(ws);
+  w.lp = (int64_t*)(b + o_lp); w.counts = (int64_t*)(b + o_c); w.offsets = (int64_t*)(b + o_o); w.index = (int64_t*)(b + o_i);
+  w.flag[0] = (int64_t*)(b + o_f); w.flag[1] = w.flag[0] + n; w.need = (int64_t*)(b + o_n);
+  for (int q = 0; q < 2; ++q) { w.counts2[q] = (int64_t*)(b + o_c2[q]); w.offsets2[q] = (int64_t*)(b + o_o2[q]); w.index2[q] = (int64_t*)(b + o_i2[q]); }
+  w.scratch = b + o_s;
+  w.total = off;
+  return w;
+}
+}  // namespace
+}  // namespace slcl
+
+extern "C" size_t slcl_sample_balanced_workspace_bytes(int64_t n_pixels, int n_class) {
+  if (n_pixels <= 0 || n_class < 1 || n_class > KM) return 0;
+  return carve_sample(nullptr, n_pixels, n_class).total;
+}
+
+extern "C" int slcl_sample_balanced(const int64_t* perm, const int64_t* labels, int64_t n_pixels, int n_class, int64_t per_a,
+                                    int64_t* out_a, int64_t* filled_a, int64_t per_b, int64_t* out_b, int64_t* filled_b,
+                                    void* workspace, size_t workspace_bytes, slcl_stream_t stream_) {
+  if (!perm || !labels || n_pixels <= 0 || n_class < 1 || n_class > KM || per_a < 1 || !out_a || !filled_a || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (per_b < 0 || (per_b > 0 && (!out_b || !filled_b))) return SLCL_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < slcl_sample_balanced_workspace_bytes(n_pixels, n_class) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SampleWs w = carve_sample(workspace, n_pixels, n_class);
+  const int nb = (int)ceil_div<int64_t>(n_pixels, kThreads);
+  gather_labels_kernel<<<nb, kThreads, 0, stream>>>(perm, labels, n_pixels, w.lp);
+  launch_compact(w.lp, n_pixels, n_class, w.counts, w.offsets, w.index, w.scratch, nullptr, stream);
+  cudaMemsetAsync(w.flag[0], 0xFF, 2 * (size_t)n_pixels * sizeof(int64_t), stream);          // -1: not a phase-2 candidate
+  PickArgs a{};
+  a.perm = perm; a.counts = w.counts; a.offsets = w.offsets; a.index = w.index; a.K = n_class;
+  a.per[0] = per_a; a.out[0] = out_a; a.flag[0] = w.flag[0]; a.need[0] = w.need;
+  a.per[1] = per_b; a.out[1] = per_b > 0 ? out_b : nullptr; a.flag[1] = w.flag[1]; a.need[1] = w.need + 1;
+  balanced_pick_kernel<<<nb, kThreads, 0, stream>>>(a);
+  for (int q = 0; q < (per_b > 0 ? 2 : 1); ++q) {
+    const int64_t per = q == 0 ? per_a : per_b;
+    launch_compact(w.flag[q], n_pixels, 1, w.counts2[q], w.offsets2[q], w.index2[q], w.scratch, w.need + q, stream);
+    const int fb = (int)std::min<int64_t>(ceil_div<int64_t>(n_class * per, kThreads), 148);
+    balanced_fill_kernel<<<fb, kThreads, 0, stream>>>(perm, w.need + q, n_class * per, w.counts2[q], w.index2[q],
+                                                     q == 0 ? out_a : out_b, q == 0 ? filled_a : filled_b);
+  }
+  return check_launch("slcl_sample_balanced");
+}
+
+extern "C" int slcl_self_maps(const int64_t* id_a, int64_t n_anchor, const int64_t* id_b, int64_t n_contrast, int64_t n_ids,
+                              int32_t* a_selfcol, int32_t* b_selfrow, void* workspace, size_t workspace_bytes,
+                              slcl_stream_t stream_) {
+  if (!id_a || !id_b || n_anchor <= 0 || n_contrast <= 0 || n_ids <= 0 || !a_selfcol || !b_selfrow || !workspace)
+    return SLCL_ERR_INVALID_ARGUMENT;
+  if (n_anchor > INT_MAX || n_contrast > INT_MAX) return SLCL_ERR_UNSUPPORTED;
+  if (workspace_bytes < 2 * (size_t)n_ids * sizeof(int32_t) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int32_t* table_a = reinterpret_cast<int32_t*>(workspace);
+  int32_t* table_b = table_a + n_ids;
+  cudaMemsetAsync(table_a, 0xFF, 2 * (size_t)n_ids * sizeof(int32_t), stream);          // -1: id not present
+  const int nb = (int)ceil_div<int64_t>(std::max(n_anchor, n_contrast), kThreads);
+  self_table_kernel<<<nb, kThreads, 0, stream>>>(id_a, n_anchor, id_b, n_contrast, n_ids, table_a, table_b);
+  self_lookup_kernel<<<nb, kThreads, 0, stream>>>(id_a, n_anchor, id_b, n_contrast, n_ids, table_a, table_b, a_selfcol, b_selfrow);
+  return check_launch("slcl_self_maps");
+}
+
+extern "C" int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,
+                              slcl_stream_t stream_) {
+  if (!labels || n_pixels <= 0 || n_pixels > INT_MAX || !pixel_idx || n_rows <= 0 || !meta) return SLCL_ERR_INVALID_ARGUMENT;
+  const int64_t n_pad = (int64_t)align_up((size_t)n_rows, 64);
+  rows_meta_kernel<<<(int)ceil_div<int64_t>(n_pad, kThreads), kThreads, 0, (cudaStream_t)stream_>>>(
+      labels, n_pixels, pixel_idx, n_rows, n_pad, reinterpret_cast<int2*>(meta));
+  return check_launch("slcl_rows_meta");
 }
 
 extern "C" int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
@@ -367,3 +582,4 @@ extern "C" int slcl_scatter_rows_bwd(const float* feat, int64_t batch, int64_t c
                                                                      normalize, d_rows, inv_norm, dfeat);
   return check_launch("slcl_scatter_rows_bwd");
 }
+

@@ -625,6 +625,85 @@ def _(labels, n_class):
             torch.empty(labels.numel(), dtype=torch.int64, device=dev))
 
 
+@torch.library.custom_op("slcl::sample_balanced", mutates_args=(), device_types="cuda")
+def sample_balanced(perm: Tensor, labels: Tensor, n_class: int, per_a: int, per_b: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Two-phase class-balanced pick for two quotas from one permutation (slcl_sample_balanced):
+    -> (idx_a [K*per_a], filled_a [1], idx_b [K*per_b], filled_b [1]) int64."""
+    dev = require_cuda(perm, labels)
+    lib = _lib.load()
+    pm, lab = perm.reshape(-1).contiguous(), labels.reshape(-1).contiguous()
+    if pm.dtype != torch.int64 or lab.dtype != torch.int64 or pm.numel() != lab.numel():
+        raise ValueError("perm and labels must be int64 of equal length")
+    if per_a < 1 or per_b < 1:
+        raise ValueError("both quotas need at least one pick per class")
+    n = lab.numel()
+    out_a = torch.empty(n_class * per_a, dtype=torch.int64, device=dev)
+    out_b = torch.empty(n_class * per_b, dtype=torch.int64, device=dev)
+    fill_a = torch.empty(1, dtype=torch.int64, device=dev)
+    fill_b = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.slcl_sample_balanced_workspace_bytes(n, n_class), dev)
+    with _guard(dev):
+        st = lib.slcl_sample_balanced(ptr(pm), ptr(lab), n, int(n_class), int(per_a), ptr(out_a), ptr(fill_a), int(per_b), ptr(out_b),
+                                      ptr(fill_b), ptr(ws), ws.numel(), stream_ptr(dev))
+    check(st, "slcl_sample_balanced")
+    return out_a, fill_a, out_b, fill_b
+
+
+@sample_balanced.register_fake
+def _(perm, labels, n_class, per_a, per_b):
+    dev = perm.device
+    return (torch.empty(n_class * per_a, dtype=torch.int64, device=dev), torch.empty(1, dtype=torch.int64, device=dev),
+            torch.empty(n_class * per_b, dtype=torch.int64, device=dev), torch.empty(1, dtype=torch.int64, device=dev))
+
+
+@torch.library.custom_op("slcl::self_maps_bounded", mutates_args=(), device_types="cuda")
+def self_maps_bounded(id_a: Tensor, id_b: Tensor, n_ids: int) -> Tuple[Tensor, Tensor]:
+    """(a_selfcol [A], b_selfrow [M]) int32 for ids in [0, n_ids) (pixel indices), unique within each side: two lookup
+    tables instead of the sort of ``self_maps``."""
+    dev = require_cuda(id_a, id_b)
+    lib = _lib.load()
+    ia, ib = id_a.reshape(-1).contiguous(), id_b.reshape(-1).contiguous()
+    if ia.dtype != torch.int64 or ib.dtype != torch.int64:
+        raise ValueError("ids must be int64")
+    selfcol = torch.empty(ia.numel(), dtype=torch.int32, device=dev)
+    selfrow = torch.empty(ib.numel(), dtype=torch.int32, device=dev)
+    ws = _ws(8 * int(n_ids), dev)
+    with _guard(dev):
+        st = lib.slcl_self_maps(ptr(ia), ia.numel(), ptr(ib), ib.numel(), int(n_ids), ptr(selfcol), ptr(selfrow), ptr(ws), ws.numel(),
+                                stream_ptr(dev))
+    check(st, "slcl_self_maps")
+    return selfcol, selfrow
+
+
+@self_maps_bounded.register_fake
+def _(id_a, id_b, n_ids):
+    return (torch.empty(id_a.numel(), dtype=torch.int32, device=id_a.device),
+            torch.empty(id_b.numel(), dtype=torch.int32, device=id_b.device))
+
+
+@torch.library.custom_op("slcl::rows_meta", mutates_args=(), device_types="cuda")
+def rows_meta(labels: Tensor, pixel_idx: Tensor) -> Tensor:
+    """{label, id = pixel index} int32 pairs of the sampled rows, padded to a multiple of 64 rows with INT_MIN -- what
+    ``pad_meta(labels[idx], idx)`` builds, in one launch."""
+    dev = require_cuda(labels, pixel_idx)
+    lib = _lib.load()
+    lab, idx = labels.reshape(-1).contiguous(), pixel_idx.reshape(-1).contiguous()
+    if lab.dtype != torch.int64 or idx.dtype != torch.int64:
+        raise ValueError("labels and pixel_idx must be int64")
+    n = idx.numel()
+    meta = torch.empty(((n + 63) // 64 * 64, 2), dtype=torch.int32, device=dev)
+    with _guard(dev):
+        st = lib.slcl_rows_meta(ptr(lab), lab.numel(), ptr(idx), n, ptr(meta), stream_ptr(dev))
+    check(st, "slcl_rows_meta")
+    return meta
+
+
+@rows_meta.register_fake
+def _(labels, pixel_idx):
+    n = pixel_idx.numel()
+    return torch.empty(((n + 63) // 64 * 64, 2), dtype=torch.int32, device=labels.device)
+
+
 @torch.library.custom_op("slcl::gather_unit_rows", mutates_args=(), device_types="cuda")
 def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16: bool,
                      want_f32: bool) -> Tuple[Tensor, Tensor, Tensor]:

@@ -101,13 +101,16 @@ class _P2PLoss(torch.autograd.Function):
 
 
 def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False, n_class=0,
-             selfcol=None, selfrow=None, n_batch=1):
+             selfcol=None, selfrow=None, n_batch=1, metas=None, id_bound=None):
     """``same_rows``: anchors and contrast rows are the same gathered rows (one gather); their labels may
     still differ (ISCL compares query labels with the anchors' dominant labels).
     ``n_batch`` > 1: block-diagonal batches -- rows [z R/n, (z+1) R/n) of both sides only see each other (R/n a
     multiple of 128; either mode -- the analytic sweeps keep one table of per-class sums per batch).
     ``n_class`` in 1..8: labels are class indices in [0, n_class) and ids are unique -> analytic sweeps; the
-    self-pair maps are derived from the ids unless given."""
+    self-pair maps are derived from the ids unless given.
+    ``metas``: the {label, id} rows (``ops.rows_meta`` / ``ops.pad_meta``) when the caller has built them already
+    (``lab_*`` are then unused); ``id_bound``: the ids are int64 in [0, id_bound) (pixel indices) -> the self-pair maps
+    come from two lookup tables instead of a sort."""
     if same_rows and n_class == 0 and n_batch == 1 and idx_a.numel() >= _SORT_MIN_ROWS:
         # General labels over ONE large row set (SupCon family, ISCL): the sums are order-invariant, so gather the rows
         # sorted by contrast label -- label-uniform column tiles take the sweeps' fast path -- and hand the kernels the
@@ -122,12 +125,17 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
         weight = weight[order]
         id_a = id_b = torch.arange(n, device=feat.device, dtype=torch.int32)
         selfcol = selfrow = id_a
-    meta_a = ops.pad_meta(lab_a, id_a)
-    meta_b = meta_a if (same_rows and lab_b is lab_a) else ops.pad_meta(lab_b, id_b)
+    if metas is not None:
+        meta_a, meta_b = metas
+    else:
+        meta_a = ops.pad_meta(lab_a, id_a)
+        meta_b = meta_a if (same_rows and lab_b is lab_a) else ops.pad_meta(lab_b, id_b)
     if n_class > 0 and selfcol is None:
         if same_rows:
             selfcol = torch.arange(idx_a.numel(), device=feat.device, dtype=torch.int32)
             selfrow = selfcol
+        elif id_bound is not None:
+            selfcol, selfrow = _ops.self_maps_bounded(id_a, id_b, int(id_bound))
         else:
             selfcol, selfrow = ops.self_maps(id_a, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
@@ -299,24 +307,6 @@ class BlockConLoss(nn.Module):
                         n_class=n_class if labels is not None else 0, n_batch=n_tiles)
 
 
-def _balanced_prefix(perm, lp, rank, counts, valid, per: int, total: int):
-    """Pixels of ``perm`` chosen by the two-phase rule of ``sample_class_balanced`` (all on the device, no host sync):
-    returns (picks [total], n_filled 0-d)."""
-    k = counts.numel()
-    take = counts.clamp(max=per)                                   # phase-1 picks per class
-    n1 = take.sum()
-    base = torch.cumsum(take, 0) - take                            # class-major output offsets
-    p1 = rank < per                                                # rank = huge for pixels outside [0, K)
-    dest1 = base[lp.clamp(0, k - 1)] + rank
-    u = valid & ~p1
-    r2 = torch.cumsum(u, 0) - 1
-    p2 = u & (r2 < total - n1)
-    dest = torch.where(p1, dest1, torch.where(p2, n1 + r2, torch.full_like(r2, total)))      # slot `total` = dump
-    out = torch.zeros(total + 1, dtype=torch.int64, device=perm.device)
-    out.index_put_((dest,), perm)
-    return out[:total], n1 + torch.minimum(u.sum(), total - n1)
-
-
 def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
                           generator: Optional[torch.Generator] = None, return_counts: bool = False):
     """Class-balanced sampler (north_star item 1), with NO host synchronisation.
@@ -334,20 +324,12 @@ def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, 
     dev = lab.device
     gen_dev = generator.device if generator is not None else dev
     perm = torch.randperm(n, generator=generator, device=gen_dev).to(dev)
-    lp = lab[perm]
-    counts, offsets, index = _ops.compact_by_class(lp, n_class)
-    pos = torch.arange(n, device=dev)
-    n_valid = offsets[n_class]
-    cls = torch.searchsorted(offsets[1:].contiguous(), pos, right=True).clamp(max=n_class - 1)
-    rank_sorted = pos - offsets[cls]
-    rank = torch.full((n + 1,), 1 << 60, dtype=torch.int64, device=dev)
-    rank.index_put_((torch.where(pos < n_valid, index, torch.full_like(index, n)),), rank_sorted)
-    rank = rank[:n]
-    valid = (lp >= 0) & (lp < n_class)
     per_a = -(-n_anchor // n_class)
     per_c = -(-n_contrast // n_class)
-    c_idx, c_fill = _balanced_prefix(perm, lp, rank, counts, valid, per_c, per_c * n_class)
-    a_idx, a_fill = _balanced_prefix(perm, lp, rank, counts, valid, per_a, per_a * n_class)
+    # labels in permutation order -> stable per-class compaction -> phase-1 prefix per class -> phase-2 fill, both quotas:
+    # one C-ABI call (slcl_sample_balanced), ~13 launches where the torch formulation of the same rule took ~60
+    a_idx, a_fill, c_idx, c_fill = _ops.sample_balanced(perm, lab, n_class, per_a, per_c)
+    a_fill, c_fill = a_fill[0], c_fill[0]
     if return_counts:
         return a_idx, c_idx, a_fill, c_fill
     return a_idx, c_idx
@@ -366,13 +348,14 @@ def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int,
         anchor_idx, contrast_idx, a_fill, c_fill = sample_class_balanced(labels, n_anchor, n_contrast, n_class, generator,
                                                                           return_counts=True)
         short = (a_fill < anchor_idx.numel()) | (c_fill < contrast_idx.numel())
-    lab = labels.reshape(-1)
-    la, lb = lab[anchor_idx], lab[contrast_idx]
-    fg = (la != 0).float()
+    lab = labels.reshape(-1).long()
+    anchor_idx, contrast_idx = anchor_idx.reshape(-1).long(), contrast_idx.reshape(-1).long()
+    meta_a, meta_b = _ops.rows_meta(lab, anchor_idx), _ops.rows_meta(lab, contrast_idx)          # {label, pixel index}
+    fg = (meta_a[:anchor_idx.numel(), 0] != 0).float()
     weight = fg / fg.sum()
     # analytic sweeps need class-index labels (true here) and unique picks (distinct pixels of one permutation are)
-    loss = p2p_loss(feat, anchor_idx, contrast_idx, la, lb, anchor_idx, contrast_idx, weight, temperature, normalize=True,
-                    n_class=n_class if (analytic and n_class <= 8) else 0)
+    loss = p2p_loss(feat, anchor_idx, contrast_idx, None, None, anchor_idx, contrast_idx, weight, temperature, normalize=True,
+                    n_class=n_class if (analytic and n_class <= 8) else 0, metas=(meta_a, meta_b), id_bound=lab.numel())
     if short is not None:
         loss = torch.where(short, torch.full_like(loss, float("nan")), loss)
     return loss

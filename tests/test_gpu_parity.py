@@ -430,6 +430,20 @@ def test_gather_unit_rows_vs_oracle():
     grad_close(dfeat, fo.grad)
 
 
+def test_scatter_rows_wide_map_distinct_and_repeated_rows():
+    """C = 256 (the warp-per-row kernel, rows held in registers): distinct pixels and pixels that occur several times."""
+    gen = cases.g(78)
+    feat = torch.randn(2, 256, 6, 5, generator=gen)
+    for idx in (torch.randperm(60, generator=gen)[:37], torch.randint(0, 60, (90,), generator=gen)):
+        fo = feat.clone().requires_grad_(True)
+        g_rows = torch.randn(idx.numel(), 256, generator=gen)
+        (O.gather_unit_rows(fo, idx) * g_rows).sum().backward()
+        _, _, inv = torch.ops.slcl.gather_unit_rows(feat.to(dev()), idx.to(dev()), True, True, False)
+        dfeat = torch.zeros_like(feat, device=dev())
+        torch.ops.slcl.scatter_rows_bwd(feat.to(dev()), idx.to(dev()), True, g_rows.to(dev()), inv, dfeat)
+        grad_close(dfeat, fo.grad)
+
+
 # ---------------------------------------------------------------------------
 # size-independent properties at full size (cfg2 / cfg4 shapes)
 # ---------------------------------------------------------------------------
