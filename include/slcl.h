@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 112            /* major*100 + minor */
+#define SLCL_VERSION 113            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -311,9 +311,19 @@ int slcl_sample_balanced(const int64_t* perm, const int64_t* labels, int64_t n_p
                          int64_t per_b, int64_t* out_b, int64_t* filled_b,
                          void* workspace, size_t workspace_bytes, slcl_stream_t stream);
 /* Self-pair maps of the analytic pixel<->pixel mode for ids in [0, n_ids) (pixel indices), unique within each side:
- * a_selfcol [A] = contrast row carrying anchor i's id or -1, b_selfrow [M] = its inverse.  workspace: 8 * n_ids bytes. */
+ * a_selfcol [A] = contrast row carrying anchor i's id or -1, b_selfrow [M] = its inverse.  row_of_id [2, n_ids] int32
+ * (caller-owned) receives the two lookup tables they are read from: row_of_id[0][id] = anchor row holding id or -1,
+ * row_of_id[1][id] = contrast row -- for pixel ids exactly the maps slcl_scatter_rows_by_map wants. */
 int slcl_self_maps(const int64_t* id_a, int64_t n_anchor, const int64_t* id_b, int64_t n_contrast, int64_t n_ids,
-                   int32_t* a_selfcol, int32_t* b_selfrow, void* workspace, size_t workspace_bytes, slcl_stream_t stream);
+                   int32_t* a_selfcol, int32_t* b_selfrow, int32_t* row_of_id, slcl_stream_t stream);
+/* Backward of slcl_gather_unit_rows driven from the pixel side (same arithmetic as slcl_scatter_rows_bwd): row_of_pixel_s
+ * [batch * pixels] int32 = the row of set s gathered from that pixel, or -1; every element of dfeat is WRITTEN (zeros
+ * where no row holds the pixel), coalesced, without atomics -- the faster route when the rows cover a good share of
+ * the map.  Set b is optional (all three pointers null); the two sets are summed. */
+int slcl_scatter_rows_by_map(const float* feat, int64_t batch, int64_t channels, int64_t pixels, int normalize,
+                             const int32_t* row_of_pixel_a, const float* d_rows_a, const float* inv_norm_a,
+                             const int32_t* row_of_pixel_b, const float* d_rows_b, const float* inv_norm_b,
+                             float* dfeat, slcl_stream_t stream);
 /* {label, id} rows of slcl_p2p_fwd straight from the label map: meta [pad64(R), 2] int32 = {labels[idx[r]], idx[r]},
  * pad rows {INT_MIN, INT_MIN}.  n_pixels <= INT_MAX. */
 int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,

@@ -413,6 +413,67 @@ __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const float* fea
   }
 }
 
+// Backward of the gather driven from the PIXEL side: map_s[pixel] = row of set s that holds the pixel, or -1.  Threads
+// own pixels and walk channels, so loads of the feature map and stores of the gradient map are coalesced and EVERY
+// element of dfeat is written exactly once (zeros where no row holds the pixel): no pre-zeroed map, no atomics, no
+// 4-byte accesses scattered over 32-byte sectors.  Pays off when the sampled rows cover a good share of the map
+// (cfg3: 20 480 rows of 65 536 pixels touch ~95 % of the map's sectors anyway).  Up to two row sets (anchors and
+// contrast rows) are summed on the fly.
+__global__ void __launch_bounds__(kThreads) scatter_by_map_kernel(const float* feat, int64_t C, int64_t HW, int64_t n_pix,
+                                                                  int normalize, const int32_t* map0, const float* d0,
+                                                                  const float* inv0, const int32_t* map1, const float* d1,
+                                                                  const float* inv1, float* dfeat) {
+  // block = 32 consecutive pixels (lane) x 8 channel groups (warp): a warp's load / store of one channel is one full
+  // line, a thread's slice of its gradient row is contiguous, and 8 x more threads share the serial channel walk
+  __shared__ float s_dot[2][kWarps][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t p = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = p < n_pix;
+  const int64_t pc = live ? p : n_pix - 1;
+  const int64_t b = pc / HW, q = pc - b * HW;
+  const int64_t base = b * C * HW + q;
+  const int r0 = live ? map0[pc] : -1;
+  const int r1 = (live && map1 != nullptr) ? map1[pc] : -1;
+  const bool any = r0 >= 0 || r1 >= 0;
+  const int cg = (int)((C + kWarps - 1) / kWarps);
+  const int c_begin = grp * cg, c_end = (int)min((int64_t)(grp + 1) * cg, C);
+  if (!__any_sync(0xffffffffu, any)) {                 // (the same 32 pixels in every warp of the block: uniform exit)
+    if (live)
+      for (int c = c_begin; c < c_end; ++c) dfeat[base + (int64_t)c * HW] = 0.f;
+    return;
+  }
+  const float* g0 = r0 >= 0 ? d0 + (int64_t)r0 * C : nullptr;
+  const float* g1 = r1 >= 0 ? d1 + (int64_t)r1 * C : nullptr;
+  const float i0 = (normalize && r0 >= 0) ? inv0[r0] : 1.f;
+  const float i1 = (normalize && r1 >= 0) ? inv1[r1] : 1.f;
+  float dot0 = 0.f, dot1 = 0.f;
+  if (normalize) {
+    float t0 = 0.f, t1 = 0.f;
+    if (any) {
+#pragma unroll 8
+      for (int c = c_begin; c < c_end; ++c) {
+        const float x = __ldg(feat + base + (int64_t)c * HW);
+        if (g0) t0 = fmaf(x * i0, __ldg(g0 + c), t0);
+        if (g1) t1 = fmaf(x * i1, __ldg(g1 + c), t1);
+      }
+    }
+    s_dot[0][grp][lane] = t0; s_dot[1][grp][lane] = t1;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { dot0 += s_dot[0][w][lane]; dot1 += s_dot[1][w][lane]; }      // fixed order
+  }
+#pragma unroll 8
+  for (int c = c_begin; c < c_end; ++c) {              // all lanes together: full-line stores, zeros where nothing was sampled
+    float v = 0.f;
+    if (any) {
+      const float x = normalize ? __ldg(feat + base + (int64_t)c * HW) : 0.f;
+      if (g0) { const float g = __ldg(g0 + c); v += normalize ? (g - x * i0 * dot0) * i0 : g; }
+      if (g1) { const float g = __ldg(g1 + c); v += normalize ? (g - x * i1 * dot1) * i1 : g; }
+    }
+    if (live) dfeat[base + (int64_t)c * HW] = v;
+  }
+}
+
 }  // namespace
 }  // namespace slcl
 
@@ -511,20 +572,31 @@ extern "C" int slcl_sample_balanced(const int64_t* perm, const int64_t* labels, 
 }
 
 extern "C" int slcl_self_maps(const int64_t* id_a, int64_t n_anchor, const int64_t* id_b, int64_t n_contrast, int64_t n_ids,
-                              int32_t* a_selfcol, int32_t* b_selfrow, void* workspace, size_t workspace_bytes,
-                              slcl_stream_t stream_) {
-  if (!id_a || !id_b || n_anchor <= 0 || n_contrast <= 0 || n_ids <= 0 || !a_selfcol || !b_selfrow || !workspace)
+                              int32_t* a_selfcol, int32_t* b_selfrow, int32_t* row_of_id, slcl_stream_t stream_) {
+  if (!id_a || !id_b || n_anchor <= 0 || n_contrast <= 0 || n_ids <= 0 || !a_selfcol || !b_selfrow || !row_of_id)
     return SLCL_ERR_INVALID_ARGUMENT;
   if (n_anchor > INT_MAX || n_contrast > INT_MAX) return SLCL_ERR_UNSUPPORTED;
-  if (workspace_bytes < 2 * (size_t)n_ids * sizeof(int32_t) || !aligned16(workspace)) return SLCL_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  int32_t* table_a = reinterpret_cast<int32_t*>(workspace);
+  int32_t* table_a = row_of_id;
   int32_t* table_b = table_a + n_ids;
   cudaMemsetAsync(table_a, 0xFF, 2 * (size_t)n_ids * sizeof(int32_t), stream);          // -1: id not present
   const int nb = (int)ceil_div<int64_t>(std::max(n_anchor, n_contrast), kThreads);
   self_table_kernel<<<nb, kThreads, 0, stream>>>(id_a, n_anchor, id_b, n_contrast, n_ids, table_a, table_b);
   self_lookup_kernel<<<nb, kThreads, 0, stream>>>(id_a, n_anchor, id_b, n_contrast, n_ids, table_a, table_b, a_selfcol, b_selfrow);
   return check_launch("slcl_self_maps");
+}
+
+extern "C" int slcl_scatter_rows_by_map(const float* feat, int64_t batch, int64_t channels, int64_t pixels, int normalize,
+                                        const int32_t* row_of_pixel_a, const float* d_rows_a, const float* inv_norm_a,
+                                        const int32_t* row_of_pixel_b, const float* d_rows_b, const float* inv_norm_b,
+                                        float* dfeat, slcl_stream_t stream_) {
+  if (!feat || batch <= 0 || channels <= 0 || pixels <= 0 || !row_of_pixel_a || !d_rows_a || !dfeat) return SLCL_ERR_INVALID_ARGUMENT;
+  if ((row_of_pixel_b == nullptr) != (d_rows_b == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (normalize && (!inv_norm_a || (row_of_pixel_b && !inv_norm_b))) return SLCL_ERR_INVALID_ARGUMENT;
+  const int64_t n_pix = batch * pixels;
+  scatter_by_map_kernel<<<(unsigned)ceil_div<int64_t>(n_pix, 32), kThreads, 0, (cudaStream_t)stream_>>>(
+      feat, channels, pixels, n_pix, normalize, row_of_pixel_a, d_rows_a, inv_norm_a, row_of_pixel_b, d_rows_b, inv_norm_b, dfeat);
+  return check_launch("slcl_scatter_rows_by_map");
 }
 
 extern "C" int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,

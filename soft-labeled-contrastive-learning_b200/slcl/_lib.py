@@ -91,7 +91,8 @@ SIGNATURES = {
     "slcl_compact_by_class": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, _P, _SZ, _P]),
     "slcl_sample_balanced_workspace_bytes": (_SZ, [_I64, C.c_int]),
     "slcl_sample_balanced": (C.c_int, [_P, _P, _I64, C.c_int, _I64, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
-    "slcl_self_maps": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "slcl_self_maps": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P, _P, _P]),
+    "slcl_scatter_rows_by_map": (C.c_int, [_P, _I64, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "slcl_rows_meta": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "slcl_gather_unit_rows": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _I64, _P, _P, _P]),
     "slcl_scatter_rows_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _P, _P, _P]),

@@ -657,9 +657,10 @@ def _(perm, labels, n_class, per_a, per_b):
 
 
 @torch.library.custom_op("slcl::self_maps_bounded", mutates_args=(), device_types="cuda")
-def self_maps_bounded(id_a: Tensor, id_b: Tensor, n_ids: int) -> Tuple[Tensor, Tensor]:
-    """(a_selfcol [A], b_selfrow [M]) int32 for ids in [0, n_ids) (pixel indices), unique within each side: two lookup
-    tables instead of the sort of ``self_maps``."""
+def self_maps_bounded(id_a: Tensor, id_b: Tensor, n_ids: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(a_selfcol [A], b_selfrow [M], row_of_id [2, n_ids]) int32 for ids in [0, n_ids) (pixel indices), unique within
+    each side: two lookup tables instead of the sort of ``self_maps``; the tables come back too (row_of_id[0][id] =
+    anchor row holding id or -1, row_of_id[1] likewise for the contrast rows)."""
     dev = require_cuda(id_a, id_b)
     lib = _lib.load()
     ia, ib = id_a.reshape(-1).contiguous(), id_b.reshape(-1).contiguous()
@@ -667,18 +668,55 @@ def self_maps_bounded(id_a: Tensor, id_b: Tensor, n_ids: int) -> Tuple[Tensor, T
         raise ValueError("ids must be int64")
     selfcol = torch.empty(ia.numel(), dtype=torch.int32, device=dev)
     selfrow = torch.empty(ib.numel(), dtype=torch.int32, device=dev)
-    ws = _ws(8 * int(n_ids), dev)
+    tables = torch.empty((2, int(n_ids)), dtype=torch.int32, device=dev)
     with _guard(dev):
-        st = lib.slcl_self_maps(ptr(ia), ia.numel(), ptr(ib), ib.numel(), int(n_ids), ptr(selfcol), ptr(selfrow), ptr(ws), ws.numel(),
+        st = lib.slcl_self_maps(ptr(ia), ia.numel(), ptr(ib), ib.numel(), int(n_ids), ptr(selfcol), ptr(selfrow), ptr(tables),
                                 stream_ptr(dev))
     check(st, "slcl_self_maps")
-    return selfcol, selfrow
+    return selfcol, selfrow, tables
 
 
 @self_maps_bounded.register_fake
 def _(id_a, id_b, n_ids):
-    return (torch.empty(id_a.numel(), dtype=torch.int32, device=id_a.device),
-            torch.empty(id_b.numel(), dtype=torch.int32, device=id_b.device))
+    dev = id_a.device
+    return (torch.empty(id_a.numel(), dtype=torch.int32, device=dev), torch.empty(id_b.numel(), dtype=torch.int32, device=dev),
+            torch.empty((2, n_ids), dtype=torch.int32, device=dev))
+
+
+@torch.library.custom_op("slcl::scatter_rows_by_map", mutates_args=(), device_types="cuda")
+def scatter_rows_by_map(feat: Tensor, normalize: bool, map_a: Tensor, d_a: Tensor, inv_a: Tensor,
+                        map_b: Optional[Tensor], d_b: Optional[Tensor], inv_b: Optional[Tensor]) -> Tensor:
+    """dfeat (every element written) from row gradients and pixel -> row maps (slcl_scatter_rows_by_map)."""
+    dev = require_cuda(feat, map_a, d_a, inv_a)
+    lib = _lib.load()
+    if not feat.is_contiguous() or feat.dim() != 4 or feat.dtype != _F32:
+        raise ValueError("feat must be a contiguous float32 NCHW map")
+    b, c, h, w = feat.shape
+    n = b * h * w
+
+    def chk(m, d, what):
+        if m.dtype != torch.int32 or m.numel() != n or not m.is_contiguous():
+            raise ValueError(f"{what}: the pixel -> row map must be contiguous int32 [{n}]")
+        if d.dtype != _F32 or d.dim() != 2 or d.shape[1] != c or not d.is_contiguous():
+            raise ValueError(f"{what}: row gradients must be contiguous float32 [rows, {c}]")
+    chk(map_a, d_a, "set a")
+    two = map_b is not None
+    if two:
+        if d_b is None or inv_b is None:
+            raise ValueError("set b needs its map, its row gradients and its inverse norms")
+        chk(map_b, d_b, "set b")
+    dfeat = torch.empty_like(feat)
+    with _guard(dev):
+        st = lib.slcl_scatter_rows_by_map(ptr(feat), b, c, h * w, int(normalize), ptr(map_a), ptr(d_a), ptr(inv_a.contiguous()),
+                                          ptr(map_b) if two else None, ptr(d_b) if two else None,
+                                          ptr(inv_b.contiguous()) if two else None, ptr(dfeat), stream_ptr(dev))
+    check(st, "slcl_scatter_rows_by_map")
+    return dfeat
+
+
+@scatter_rows_by_map.register_fake
+def _(feat, normalize, map_a, d_a, inv_a, map_b, d_b, inv_b):
+    return torch.empty_like(feat)
 
 
 @torch.library.custom_op("slcl::rows_meta", mutates_args=(), device_types="cuda")

@@ -62,7 +62,7 @@ class _P2PLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, idx_a, idx_b, meta_a, meta_b, weight, temperature, normalize, same_rows, n_class, selfcol,
-                selfrow, n_batch):
+                selfrow, n_batch, rowmaps):
         fm = feat.detach().contiguous()
         c = fm.shape[1]
         b_bf16, _, inv_b = _ops.gather_unit_rows(fm, idx_b, normalize, True, False)
@@ -78,26 +78,31 @@ class _P2PLoss(torch.autograd.Function):
         loss, stats, state = _ops.p2p_fwd(a_bf16, b_bf16, meta_a, meta_b, shift, weight, temperature, n_class, selfcol, keep,
                                           n_batch)
         ctx.save_for_backward(fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state,
-                              selfcol, selfrow)
+                              selfcol, selfrow, rowmaps)
         ctx.cfg = (temperature, normalize, same_rows, c, n_class, n_batch)
         return loss[0]
 
     @staticmethod
     def backward(ctx, grad_out):
         (fm, idx_a, idx_b, meta_a, meta_b, weight, a_bf16, b_bf16, inv_a, inv_b, shift, stats, state, selfcol,
-         selfrow) = ctx.saved_tensors
+         selfrow, rowmaps) = ctx.saved_tensors
         temperature, normalize, same_rows, c, n_class, n_batch = ctx.cfg
         if not ctx.needs_input_grad[0]:
-            return (None,) * 13
+            return (None,) * 14
         d_a, d_b = _ops.p2p_bwd(a_bf16, b_bf16, c, meta_a, meta_b, shift, weight, temperature, stats,
                                 grad_out.reshape(1), True, True, n_class, selfcol, selfrow, state, n_batch)
+        if rowmaps is not None and not same_rows:
+            # pixel -> row maps at hand and the rows cover a good share of the map: write the whole gradient map from the
+            # pixel side (coalesced, no atomics, no zero-fill) instead of scattering 4-byte elements
+            dfeat = _ops.scatter_rows_by_map(fm, normalize, rowmaps[0], d_a.contiguous(), inv_a, rowmaps[1], d_b.contiguous(), inv_b)
+            return (dfeat,) + (None,) * 13
         dfeat = torch.zeros_like(fm)
         if same_rows:       # anchors and contrast rows are the same gathered rows: one scatter of the summed row gradients
             _ops.scatter_rows_bwd(fm, idx_b, normalize, d_a + d_b, inv_b, dfeat)
         else:
             _ops.scatter_rows_bwd(fm, idx_a, normalize, d_a, inv_a, dfeat)
             _ops.scatter_rows_bwd(fm, idx_b, normalize, d_b, inv_b, dfeat)
-        return (dfeat,) + (None,) * 12
+        return (dfeat,) + (None,) * 13
 
 
 def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, normalize, same_rows=False, n_class=0,
@@ -125,6 +130,7 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
         weight = weight[order]
         id_a = id_b = torch.arange(n, device=feat.device, dtype=torch.int32)
         selfcol = selfrow = id_a
+    rowmaps = None
     if metas is not None:
         meta_a, meta_b = metas
     else:
@@ -135,11 +141,15 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
             selfcol = torch.arange(idx_a.numel(), device=feat.device, dtype=torch.int32)
             selfrow = selfcol
         elif id_bound is not None:
-            selfcol, selfrow = _ops.self_maps_bounded(id_a, id_b, int(id_bound))
+            selfcol, selfrow, tables = _ops.self_maps_bounded(id_a, id_b, int(id_bound))
+            n_pix = feat.shape[0] * feat.shape[2] * feat.shape[3]
+            if id_a is idx_a and id_b is idx_b and int(id_bound) == n_pix and (idx_a.numel() + idx_b.numel()) * 4 >= n_pix:
+                rowmaps = tables          # the ids ARE the pixel indices: the tables are pixel -> row maps
         else:
             selfcol, selfrow = ops.self_maps(id_a, id_b)
     return _P2PLoss.apply(feat, idx_a.contiguous(), idx_b.contiguous(), meta_a, meta_b, weight.float().contiguous(),
-                          float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow, int(n_batch))
+                          float(temperature), bool(normalize), bool(same_rows), int(n_class), selfcol, selfrow, int(n_batch),
+                          rowmaps)
 
 
 _INDEX_CACHE = {}          # row-index tensors per geometry: pure functions of the shapes, rebuilt ~20 small torch ops a call

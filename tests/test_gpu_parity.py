@@ -430,6 +430,44 @@ def test_gather_unit_rows_vs_oracle():
     grad_close(dfeat, fo.grad)
 
 
+@pytest.mark.parametrize("normalize", [True, False])
+def test_scatter_rows_by_map_equals_the_sparse_scatter(normalize):
+    """slcl_scatter_rows_by_map (pixel-side backward of the gather: every element of dfeat written once, two row sets
+    summed) against two slcl_scatter_rows_bwd launches into a zeroed map; the sets overlap like anchors / contrast rows."""
+    from slcl import ops
+    gen = cases.g(79)
+    feat = torch.randn(3, 48, 10, 7, generator=gen).to(dev())
+    n = 3 * 10 * 7
+    perm = torch.randperm(n, generator=gen)
+    idx_b, idx_a = perm[:120].to(dev()), perm[60:150].to(dev())                     # 60 pixels in both sets, 60 / 30 in one only
+    _, _, inv_a = torch.ops.slcl.gather_unit_rows(feat, idx_a, True, True, False)
+    _, _, inv_b = torch.ops.slcl.gather_unit_rows(feat, idx_b, True, True, False)
+    d_a = torch.randn(idx_a.numel(), 48, generator=gen).to(dev())
+    d_b = torch.randn(idx_b.numel(), 48, generator=gen).to(dev())
+    want = torch.zeros_like(feat)
+    torch.ops.slcl.scatter_rows_bwd(feat, idx_a, normalize, d_a, inv_a, want)
+    torch.ops.slcl.scatter_rows_bwd(feat, idx_b, normalize, d_b, inv_b, want)
+    selfcol, selfrow, tables = ops.self_maps_bounded(idx_a, idx_b, n)
+    # the self maps agree with the sort-based construction, and the tables are the pixel -> row maps
+    sc2, sr2 = ops.self_maps(idx_a, idx_b)
+    assert torch.equal(selfcol, sc2) and torch.equal(selfrow, sr2)
+    assert torch.equal(tables[0][idx_a].long(), torch.arange(idx_a.numel(), device=dev()))
+    got = ops.scatter_rows_by_map(feat, normalize, tables[0], d_a, inv_a, tables[1], d_b, inv_b)
+    grad_close(got, want)
+    one = ops.scatter_rows_by_map(feat, normalize, tables[1], d_b, inv_b, None, None, None)
+    want1 = torch.zeros_like(feat)
+    torch.ops.slcl.scatter_rows_bwd(feat, idx_b, normalize, d_b, inv_b, want1)
+    grad_close(one, want1)
+
+
+def test_rows_meta_equals_pad_meta():
+    from slcl import ops
+    gen = cases.g(80)
+    labels = torch.randint(-1, 6, (500,), generator=gen).to(dev())
+    idx = torch.randperm(500, generator=gen)[:130].to(dev())
+    assert torch.equal(ops.rows_meta(labels, idx), ops.pad_meta(labels[idx], idx))
+
+
 def test_scatter_rows_wide_map_distinct_and_repeated_rows():
     """C = 256 (the warp-per-row kernel, rows held in registers): distinct pixels and pixels that occur several times."""
     gen = cases.g(78)
