@@ -62,6 +62,18 @@ def test_argument_validation_without_gpu():
     assert lib.slcl_centroids_fwd(None, 1, 1, 1, None, None, 0, 0.0, None, 1, 4, None, 0.9, None, None, None, None, None, 0,
                                   None) == -1
     assert lib.slcl_p2p_workspace_bytes(4096, 16384, 256) > 0
+    # sampler bookkeeping / row plumbing added in round 2
+    assert lib.slcl_sample_balanced_workspace_bytes(65536, 5) > 0 and lib.slcl_sample_balanced_workspace_bytes(65536, 0) == 0
+    assert lib.slcl_sample_balanced(None, None, 100, 4, 8, None, None, 8, None, None, None, 0, None) == -1
+    assert lib.slcl_sample_balanced(16, 16, 100, 4, 0, 16, 16, 8, 16, 16, 16, 1 << 20, None) == -1      # per_a must be >= 1
+    assert lib.slcl_sample_balanced(16, 16, 100, 4, 8, 16, 16, 8, None, None, 16, 1 << 20, None) == -1   # quota b without outputs
+    assert lib.slcl_sample_balanced(16, 16, 100, 4, 8, 16, 16, 8, 16, 16, 16, 64, None) == -3            # workspace too small
+    assert lib.slcl_self_maps(None, 10, None, 10, 100, None, None, None, None) == -1
+    assert lib.slcl_rows_meta(None, 100, None, 10, None, None) == -1
+    assert lib.slcl_scatter_rows_by_map(None, 1, 8, 16, 1, None, None, None, None, None, None, None, None) == -1
+    assert lib.slcl_scatter_rows_by_map(16, 1, 8, 16, 1, 16, 16, 16, 16, None, None, 16, None) == -1      # half of set b
+    assert lib.slcl_p2p_shift(None, 10, None, 10, 0.7, None, None) == -1
+    assert lib.slcl_p2p_shift(16, 10, 16, 10, 0.0, 16, None) == -1                                        # temperature > 0
 
 
 def test_reference_signatures_are_kept():
