@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 113            /* major*100 + minor */
+#define SLCL_VERSION 114            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -328,6 +328,13 @@ int slcl_scatter_rows_by_map(const float* feat, int64_t batch, int64_t channels,
  * pad rows {INT_MIN, INT_MIN}.  n_pixels <= INT_MAX. */
 int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,
                    slcl_stream_t stream);
+/* Row weights of the SupCon family from the metadata rows (label != 0 = foreground): the rows are n_tiles equal tiles
+ * of rows_per_tile rows; weight[r] = fg_r / (foreground rows of r's tile) / (tiles that have foreground) --
+ * utils/loss.py:382-384 for one problem (n_tiles = 1), :445-448 folded into the rows for BlockConLoss.  zero_if_empty:
+ * tiles (or a whole problem) without foreground weigh 0 (:405-407, :439-440); otherwise 0/0 stays NaN as in SupConLoss.
+ * tile_fg [n_tiles] fp32 receives the per-tile foreground counts. */
+int slcl_tile_weights(const int32_t* meta, int64_t n_tiles, int64_t rows_per_tile, int zero_if_empty, float* tile_fg,
+                      float* weight, slcl_stream_t stream);
 int slcl_gather_unit_rows(const float* feat, int64_t batch, int64_t channels, int64_t pixels,
                           const int64_t* pixel_idx, int64_t n_rows, int normalize,
                           void* rows_bf16, int64_t bf16_row_stride, float* rows_f32, float* inv_norm,

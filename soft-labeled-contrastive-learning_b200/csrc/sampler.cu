@@ -213,6 +213,55 @@ __global__ void __launch_bounds__(kThreads) rows_meta_kernel(const int64_t* labe
   meta[r] = v;
 }
 
+// ---- row weights of the SupCon family from the metadata rows: fg_r / sum_tile fg / #tiles with foreground ----
+// (utils/loss.py:382-384 for one problem; :445-448 / :465 folded into the rows for BlockConLoss' tiles.)
+// pass 1: tile_fg[t] = number of rows of tile t whose label is not 0 (background); one block per tile, fixed order
+__global__ void __launch_bounds__(kThreads) tile_fg_kernel(const int2* meta, int64_t rows_per_tile, float* tile_fg) {
+  __shared__ int red[kWarps];
+  const int2* m = meta + (int64_t)blockIdx.x * rows_per_tile;
+  int cnt = 0;
+  for (int64_t r = threadIdx.x; r < rows_per_tile; r += kThreads) cnt += m[r].x != 0 ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kWarps; ++w) t += red[w];
+    tile_fg[blockIdx.x] = (float)t;
+  }
+}
+// pass 2: weight_r = fg_r / tile_fg / n_keep, n_keep = tiles with foreground (every block counts them itself).
+// zero_if_empty: a tile (or the whole problem) without foreground contributes 0 (LocalConLoss / BlockConLoss early-outs);
+// otherwise the division is left as it is (0/0 = NaN, what SupConLoss returns there).
+__global__ void __launch_bounds__(kThreads) tile_weight_kernel(const int2* meta, int64_t n_tiles, int64_t rows_per_tile,
+                                                               const float* tile_fg, int zero_if_empty, float* weight) {
+  __shared__ int red[kWarps];
+  __shared__ float s_keep;
+  int cnt = 0;
+  for (int64_t t = threadIdx.x; t < n_tiles; t += kThreads) cnt += tile_fg[t] > 0.f ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kWarps; ++w) t += red[w];
+    s_keep = (float)t;
+  }
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (r >= n_tiles * rows_per_tile) return;
+  const float fg = meta[r].x != 0 ? 1.f : 0.f;
+  float tf = tile_fg[r / rows_per_tile], keep = s_keep;
+  if (zero_if_empty) {
+    const float k = tf > 0.f ? 1.f : 0.f;
+    weight[r] = fg / fmaxf(tf, 1.f) * k / fmaxf(keep, 1.f);
+  } else {
+    weight[r] = n_tiles == 1 ? fg / tf : fg / tf / keep;
+  }
+}
+
 // One warp per sampled row: gather C strided values, L2-normalise, write row-major.
 __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* feat, int64_t C, int64_t HW,
                                                                const int64_t* pixel_idx, int64_t n_rows, int normalize,
@@ -597,6 +646,17 @@ extern "C" int slcl_scatter_rows_by_map(const float* feat, int64_t batch, int64_
   scatter_by_map_kernel<<<(unsigned)ceil_div<int64_t>(n_pix, 32), kThreads, 0, (cudaStream_t)stream_>>>(
       feat, channels, pixels, n_pix, normalize, row_of_pixel_a, d_rows_a, inv_norm_a, row_of_pixel_b, d_rows_b, inv_norm_b, dfeat);
   return check_launch("slcl_scatter_rows_by_map");
+}
+
+extern "C" int slcl_tile_weights(const int32_t* meta, int64_t n_tiles, int64_t rows_per_tile, int zero_if_empty, float* tile_fg,
+                                 float* weight, slcl_stream_t stream_) {
+  if (!meta || n_tiles <= 0 || n_tiles > INT_MAX || rows_per_tile <= 0 || !tile_fg || !weight) return SLCL_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int2* m = reinterpret_cast<const int2*>(meta);
+  tile_fg_kernel<<<(unsigned)n_tiles, kThreads, 0, stream>>>(m, rows_per_tile, tile_fg);
+  tile_weight_kernel<<<(unsigned)ceil_div<int64_t>(n_tiles * rows_per_tile, kThreads), kThreads, 0, stream>>>(
+      m, n_tiles, rows_per_tile, tile_fg, zero_if_empty, weight);
+  return check_launch("slcl_tile_weights");
 }
 
 extern "C" int slcl_rows_meta(const int64_t* labels, int64_t n_pixels, const int64_t* pixel_idx, int64_t n_rows, int32_t* meta,

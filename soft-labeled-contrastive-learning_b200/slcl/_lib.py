@@ -93,6 +93,7 @@ SIGNATURES = {
     "slcl_sample_balanced": (C.c_int, [_P, _P, _I64, C.c_int, _I64, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "slcl_self_maps": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P, _P, _P]),
     "slcl_scatter_rows_by_map": (C.c_int, [_P, _I64, _I64, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "slcl_tile_weights": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P, _P]),
     "slcl_rows_meta": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "slcl_gather_unit_rows": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _I64, _P, _P, _P]),
     "slcl_scatter_rows_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.c_int, _P, _P, _P, _P]),

@@ -742,6 +742,31 @@ def _(labels, pixel_idx):
     return torch.empty(((n + 63) // 64 * 64, 2), dtype=torch.int32, device=labels.device)
 
 
+@torch.library.custom_op("slcl::tile_weights", mutates_args=(), device_types="cuda")
+def tile_weights(meta: Tensor, n_rows: int, n_tiles: int, zero_if_empty: bool) -> Tuple[Tensor, Tensor]:
+    """Row weights fg_r / (foreground rows of r's tile) / (tiles with foreground) from the first ``n_rows`` metadata
+    rows of ``rows_meta`` / ``pad_meta`` (label != 0 = foreground), split into ``n_tiles`` equal tiles
+    (slcl_tile_weights) -> (weight [n_rows], tile_fg [n_tiles])."""
+    dev = require_cuda(meta)
+    lib = _lib.load()
+    if meta.dtype != torch.int32 or meta.dim() != 2 or meta.shape[1] != 2 or not meta.is_contiguous():
+        raise ValueError("meta must be contiguous int32 [rows_padded, 2]")
+    if n_tiles < 1 or n_rows < 1 or n_rows % n_tiles or n_rows > meta.shape[0]:
+        raise ValueError("n_rows must be a positive multiple of n_tiles within the metadata rows")
+    weight = torch.empty(n_rows, dtype=_F32, device=dev)
+    tile_fg = torch.empty(n_tiles, dtype=_F32, device=dev)
+    with _guard(dev):
+        st = lib.slcl_tile_weights(ptr(meta), int(n_tiles), n_rows // n_tiles, int(zero_if_empty), ptr(tile_fg), ptr(weight),
+                                   stream_ptr(dev))
+    check(st, "slcl_tile_weights")
+    return weight, tile_fg
+
+
+@tile_weights.register_fake
+def _(meta, n_rows, n_tiles, zero_if_empty):
+    return (torch.empty(n_rows, dtype=_F32, device=meta.device), torch.empty(n_tiles, dtype=_F32, device=meta.device))
+
+
 @torch.library.custom_op("slcl::gather_unit_rows", mutates_args=(), device_types="cuda")
 def gather_unit_rows(feat: Tensor, pixel_idx: Tensor, normalize: bool, want_bf16: bool,
                      want_f32: bool) -> Tuple[Tensor, Tensor, Tensor]:

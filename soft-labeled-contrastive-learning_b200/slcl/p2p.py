@@ -190,18 +190,18 @@ def _supcon(features, labels, temperature, ys, xs, zero_if_no_foreground=False, 
         ids = torch.arange(idx.numel(), device=dev, dtype=torch.int32)
     m = idx.numel()
     if labels is not None:
-        lab_map = labels.reshape(-1)
-        lab = lab_map[idx].to(torch.int32)                                          # :352-353
-        fg = (lab != 0).float()                                                     # :356-358
-        denom = fg.sum()
-        if zero_if_no_foreground:      # LocalConLoss / BlockConLoss early-out (:405-407, :439-440), without a host sync
-            denom = denom.clamp_min(1.0)
-        weight = fg / denom                                                         # :382-384
-    else:
-        lab = (ids % (m // v)).to(torch.int32)                                      # :360-361 same pixel, other views
-        weight = torch.full((m,), 1.0 / m, device=dev)                              # :386
-    return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True,
-                    n_class=n_class if labels is not None else 0)
+        # {label, pixel index} rows and the foreground weights fg / sum fg (:352-358, :382-384) in three launches;
+        # zero_if_no_foreground: LocalConLoss / BlockConLoss early-out (:405-407, :439-440), without a host sync
+        meta = _ops.rows_meta(labels.reshape(-1).long(), idx)
+        weight, _ = _ops.tile_weights(meta, m, 1, bool(zero_if_no_foreground))
+        if n_class > 0:
+            return p2p_loss(fmap, idx, idx, None, None, ids, ids, weight, temperature, normalize=False, same_rows=True,
+                            n_class=n_class, metas=(meta, meta))
+        lab = meta[:m, 0]                 # general sweeps: p2p_loss may sort the rows by label and rebuilds the metadata
+        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True, n_class=0)
+    lab = (ids % (m // v)).to(torch.int32)                                          # :360-361 same pixel, other views
+    weight = torch.full((m,), 1.0 / m, device=dev)                                  # :386
+    return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, temperature, normalize=False, same_rows=True, n_class=0)
 
 
 class SupConLoss(nn.Module):
@@ -305,16 +305,13 @@ class BlockConLoss(nn.Module):
         idx, ids = _cached(("blocks", b, v, h, w, bs, div, str(dev)), build)
         n_tiles, m_tile = div * div, b * v * bs * bs
         if labels is not None:
-            lab = labels.reshape(-1)[idx].to(torch.int32)
-            fg = (lab != 0).float().view(n_tiles, m_tile)
-            tile_fg = fg.sum(1, keepdim=True)
-            keep = (tile_fg > 0).float()
-            weight = (fg / tile_fg.clamp_min(1.0) * keep / keep.sum().clamp_min(1.0)).reshape(-1)
-        else:
-            lab = (ids % (m_tile // v)).to(torch.int32)                               # same pixel of the tile, other views
-            weight = torch.full((idx.numel(),), 1.0 / (m_tile * n_tiles), device=dev)
-        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True,
-                        n_class=n_class if labels is not None else 0, n_batch=n_tiles)
+            meta = _ops.rows_meta(labels.reshape(-1).long(), idx)
+            weight, _ = _ops.tile_weights(meta, idx.numel(), n_tiles, True)
+            return p2p_loss(fmap, idx, idx, None, None, ids, ids, weight, t, normalize=False, same_rows=True,
+                            n_class=n_class, n_batch=n_tiles, metas=(meta, meta))
+        lab = (ids % (m_tile // v)).to(torch.int32)                                   # same pixel of the tile, other views
+        weight = torch.full((idx.numel(),), 1.0 / (m_tile * n_tiles), device=dev)
+        return p2p_loss(fmap, idx, idx, lab, lab, ids, ids, weight, t, normalize=False, same_rows=True, n_batch=n_tiles)
 
 
 def sample_class_balanced(labels: torch.Tensor, n_anchor: int, n_contrast: int, n_class: int,
@@ -361,8 +358,7 @@ def sampled_supcon_loss(feat: torch.Tensor, labels: torch.Tensor, n_anchor: int,
     lab = labels.reshape(-1).long()
     anchor_idx, contrast_idx = anchor_idx.reshape(-1).long(), contrast_idx.reshape(-1).long()
     meta_a, meta_b = _ops.rows_meta(lab, anchor_idx), _ops.rows_meta(lab, contrast_idx)          # {label, pixel index}
-    fg = (meta_a[:anchor_idx.numel(), 0] != 0).float()
-    weight = fg / fg.sum()
+    weight, _ = _ops.tile_weights(meta_a, anchor_idx.numel(), 1, False)          # fg / sum fg over the anchors
     # analytic sweeps need class-index labels (true here) and unique picks (distinct pixels of one permutation are)
     loss = p2p_loss(feat, anchor_idx, contrast_idx, None, None, anchor_idx, contrast_idx, weight, temperature, normalize=True,
                     n_class=n_class if (analytic and n_class <= 8) else 0, metas=(meta_a, meta_b), id_bound=lab.numel())

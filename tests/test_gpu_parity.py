@@ -460,6 +460,28 @@ def test_scatter_rows_by_map_equals_the_sparse_scatter(normalize):
     grad_close(one, want1)
 
 
+def test_tile_weights_equal_the_torch_formula():
+    """slcl_tile_weights: fg / (foreground of the tile) / (tiles with foreground), utils/loss.py:382-384 and :445-448."""
+    from slcl import ops
+    gen = cases.g(81)
+    n_tiles, per = 7, 96
+    lab = torch.randint(0, 4, (n_tiles * per,), generator=gen)
+    lab[2 * per:3 * per] = 0                                              # one all-background tile
+    meta = ops.pad_meta(lab.to(dev()), torch.arange(n_tiles * per, device=dev()))
+    w, tile_fg = ops.tile_weights(meta, n_tiles * per, n_tiles, True)
+    fg = (lab != 0).float().view(n_tiles, per)
+    tf = fg.sum(1, keepdim=True)
+    keep = (tf > 0).float()
+    want = (fg / tf.clamp_min(1.0) * keep / keep.sum().clamp_min(1.0)).reshape(-1)
+    torch.testing.assert_close(w.cpu(), want, rtol=1e-6, atol=0)
+    assert torch.equal(tile_fg.cpu(), tf.reshape(-1))
+    w1, _ = ops.tile_weights(meta, n_tiles * per, 1, False)               # one problem: fg / sum fg
+    torch.testing.assert_close(w1.cpu(), (fg / fg.sum()).reshape(-1), rtol=1e-6, atol=0)
+    zero = ops.pad_meta(torch.zeros(64, dtype=torch.int64, device=dev()), torch.arange(64, device=dev()))
+    assert torch.isnan(ops.tile_weights(zero, 64, 1, False)[0]).all()     # SupConLoss: 0/0, as the reference
+    assert float(ops.tile_weights(zero, 64, 1, True)[0].abs().sum()) == 0.0
+
+
 def test_rows_meta_equals_pad_meta():
     from slcl import ops
     gen = cases.g(80)
