@@ -1444,14 +1444,32 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t d, int box_r
 
 struct Sweep { int row_tiles, splits, cols_per_split, cluster; };
 
-Sweep plan_sweep(int64_t n_rows, int64_t n_cols, int n_batch = 1) {          // sizes are per batch
+Sweep plan_sweep(int64_t n_rows, int64_t n_cols, int n_batch = 1, bool tail_split = false) {          // sizes are per batch
   Sweep s;
   s.row_tiles = (int)ceil_div<int64_t>(n_rows, BM);
   int col_tiles = (int)ceil_div<int64_t>(n_cols, BN);
-  int want = max(1, sm_count() / (s.row_tiles * n_batch));      // fill the SMs: batches x row tiles x column splits ~ #SMs
+  const int n_sm = sm_count(), R = s.row_tiles * n_batch;
+  int want = max(1, n_sm / R);      // fill the SMs: batches x row tiles x column splits ~ #SMs
   s.splits = min(want, col_tiles);
   int tiles_per_split = ceil_div(col_tiles, s.splits);
   s.splits = ceil_div(col_tiles, tiles_per_split);
+  // Uneven tail: R x want CTAs leave SMs idle (cfg3: 32 x 4 = 128 of 148).  One more, SHORT split per row tile puts them to
+  // work: the long CTAs (launched first: blockIdx.y < want) shrink from ceil(T / want) to tp column tiles, the R short ones
+  // take the remaining T - want tp tiles each and run on the (n_sm - R want) free SMs, in rounds.  tp is the smallest
+  // value for which the rounds of short CTAs end before the long ones (kFixed ~ set-up + drain of a CTA in tile-steps).
+  // Measured at cfg3: general sweeps 160 -> 155 us; the ANALYTIC forward gets slower (48 -> 52 us, 70 -> 76 us with U):
+  // its table kernels run on the side stream and want those idle SMs, and a fifth split adds partial traffic -- so only
+  // the general sweeps ask for it (tail_split).
+  static const bool uneven = [] { const char* e = getenv("SLCL_P2P_UNEVEN"); return !(e && atoi(e) == 0); }();
+  constexpr int kFixed = 7;
+  if (tail_split && uneven && want >= 2 && s.splits == want && R * want < n_sm && col_tiles > 2 * want) {
+    const int free_sms = n_sm - R * want, rounds = ceil_div(R, free_sms);
+    for (int tp = ceil_div(col_tiles, want + 1); tp < tiles_per_split; ++tp) {
+      const int tail = col_tiles - want * tp;
+      if (tail < 1) break;
+      if (rounds * (tail + kFixed) <= tp + kFixed) { tiles_per_split = tp; s.splits = want + 1; break; }
+    }
+  }
   s.cols_per_split = tiles_per_split * BN;
   // Cluster size of the multicast variant (1, 2 or 4 CTAs along the row tiles share every column tile).
   s.cluster = 1;
@@ -1551,8 +1569,8 @@ struct P2PState {
   float* beta;       // [Na]
   size_t total;
 };
-int max_splits(int64_t n_rows) {          // upper bound of plan_sweep(n_rows, any).splits
-  return max(1, sm_count() / (int)ceil_div<int64_t>(n_rows, BM));
+int max_splits(int64_t n_rows) {          // upper bound of plan_sweep(n_rows, any).splits (+1: the uneven tail split)
+  return max(1, sm_count() / (int)ceil_div<int64_t>(n_rows, BM)) + 1;
 }
 P2PState carve_state(void* p, int64_t na, int d) {
   size_t off = 0;
@@ -1778,7 +1796,7 @@ extern "C" int slcl_p2p_fwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     if (st != SLCL_OK) return st;
     return check_launch("slcl_p2p_fwd");
   }
-  Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
+  Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch, true);
   P2PArgs args{};
   args.row_meta = am; args.col_meta = bm; args.row_shift = shift; args.stat_partial = w.stat_partial;
   args.self_by_id = a_selfcol == nullptr;
@@ -1873,7 +1891,7 @@ extern "C" int slcl_p2p_bwd(const void* a_bf16, const void* b_bf16, int64_t n_an
     gself = w.gself;
   }
   if (d_a) {
-    Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch);
+    Sweep sw = plan_sweep(n_anchor / n_batch, n_contrast / n_batch, n_batch, true);
     P2PArgs args{};
     args.row_meta = am; args.col_meta = bm; args.row_stat = w.anchor_stat; args.grad_partial = w.grad_partial_a;
     args.self_by_id = by_id;
