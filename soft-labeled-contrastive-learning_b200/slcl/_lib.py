@@ -155,7 +155,8 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
-_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # the handle without building a Stream object
+_raw_stream = None if os.environ.get("SLCL_STREAM_OBJECT") else getattr(torch._C, "_cuda_getCurrentRawStream", None)
+# (the handle without building a Stream object; SLCL_STREAM_OBJECT=1 forces the public-API route)
 
 
 def stream_ptr(device: torch.device) -> int:
