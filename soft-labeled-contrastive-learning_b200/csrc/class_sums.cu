@@ -729,11 +729,12 @@ struct TileArgs {
 // robin, and the ring depth is a multiple of n_teams so a team always meets the same slots and sees every phase of
 // their barriers.  Consumers own CPW channels and two pixels per lane.
 constexpr int kTPx = 64;                 // pixels per stage of the fused target kernel
-constexpr int kTileTeamsMax = 4;
-constexpr int kTilePixelWarps = 2 * kTileTeamsMax;
+// Up to 6 teams (12 pixel warps) next to <= 8 consumer warps (C <= 64 at CPW = 8, C <= 32 at CPW = 4), 4 teams next to 16.
+__host__ __device__ constexpr int tile_teams_max(int ncw_max) { return ncw_max <= 8 ? 6 : 4; }
 template <int K, int CPW, int NCWMAX>
-__global__ void __launch_bounds__(32 * (2 + kTilePixelWarps + NCWMAX), 1)
+__global__ void __launch_bounds__(32 * (2 + 2 * tile_teams_max(NCWMAX) + NCWMAX), 1)
 target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs a) {
+  constexpr int kTilePixelWarps = 2 * tile_teams_max(NCWMAX);
   const int kTeams = a.n_teams;
   constexpr int KP = K <= 4 ? 4 : 8;
   const int C = (int)a.channels;
@@ -1708,7 +1709,8 @@ TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
   // teams of pixel warps: four (measured at cfg2, C = 128, six stages fit: 4 teams x 1 slot 290 us, 3 x 2 305 us,
   // 2 x 3 344 us -- pixel warps in flight count for more than spare slots)
   p.npw = 4;
-  { const char* e = getenv("SLCL_TILE_TEAMS"); if (e && atoi(e) >= 1 && atoi(e) <= kTileTeamsMax && atoi(e) <= n) p.npw = atoi(e); }
+  if (p.n_cw <= 8 && n >= 6) p.npw = 6;          // room for 12 pixel warps next to 8 consumers (and 6 divides the 12-deep ring)
+  { const char* e = getenv("SLCL_TILE_TEAMS"); if (e && atoi(e) >= 1 && atoi(e) <= tile_teams_max(p.n_cw <= 8 ? 8 : 16) && atoi(e) <= n) p.npw = atoi(e); }
   n = n / p.npw * p.npw;
   p.stages = n;
   p.smem = fixed + (size_t)n * stage;
@@ -1726,7 +1728,7 @@ int launch_tile(const CUtensorMap& map, const TileArgs& a, const TilePlan& p, cu
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(target_tile_kernel)"); return SLCL_ERR_CUDA; }
     attr_set = true;
   }
-  launch_pdl(target_tile_kernel<K, CPW, NCWMAX>, dim3(p.grid), dim3(32 * (2 + kTilePixelWarps + p.n_cw)), p.smem, stream, map, a);
+  launch_pdl(target_tile_kernel<K, CPW, NCWMAX>, dim3(p.grid), dim3(32 * (2 + 2 * tile_teams_max(NCWMAX) + p.n_cw)), p.smem, stream, map, a);
   return SLCL_OK;
 }
 template <int K>
