@@ -717,7 +717,7 @@ struct TileArgs {
   double2* loss_partial;      // [gridDim.x] {sum sel*row, sum sel}
   float* partial;             // class sums per block [gridDim.x][K][C+1]
   unsigned int* ticket;
-  int n_cw, n_stages, n_teams;
+  int n_cw, n_stages, n_teams, wide;
 };
 // Stages are 64 pixels x C channels (half the class-sum kernel's tile): the pixel work is latency-bound per warp -- a
 // serial walk over the channels, then ~300 dependent instructions of margin arithmetic -- so what sets the speed is how
@@ -866,30 +866,53 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
   } else {
     const int cw = warp - 1 - kTilePixelWarps;
     if (cw < a.n_cw) {
-      // ===================== consumers: CPW channels per warp, two pixels per lane =====================
+      // ===================== consumers =====================
+      // a.wide == 0: CPW channels per warp, two pixels per lane.  a.wide == 1 (C > 64): 2 x CPW channels per warp -- each
+      // half warp owns CPW of them and four pixels per lane -- so 8 consumer warps cover 128 channels and leave room
+      // for six teams of pixel warps; the consumers have the slack (they wait most of the time), the pixel warps do not.
       float acc[CPW][K];
 #pragma unroll
       for (int q = 0; q < K; ++q)
 #pragma unroll
         for (int j = 0; j < CPW; ++j) acc[j][q] = 0.f;
+      const int half = lane >> 4, l16 = lane & 15;
+      const int c_first = a.wide ? cw * 2 * CPW + half * CPW : cw * CPW;
+      const uint32_t px_off = (uint32_t)((a.wide ? l16 * 4 : lane * 2) * 4);
       V3Pos cpos(0, kStages);
       for (int64_t it = 0; it < n_iter; ++it, cpos.advance(1)) {
         const int s = cpos.slot;
         const uint32_t par = (uint32_t)cpos.phase;
         v3_mbar_wait(&bars->x_full[s], par);
         v3_mbar_wait(&bars->w_full[s], par);
-        const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + ((cw * CPW) * kTPx + lane * 2) * 4);
-        const uint32_t ws = sWt_u32 + (uint32_t)((s * K * kTPx + lane * 2) * 4);
-        float2 w[K];
+        const uint32_t xs = sX_u32 + (uint32_t)(s * kStageBytes + c_first * kTPx * 4) + px_off;
+        const uint32_t ws = sWt_u32 + (uint32_t)(s * K * kTPx * 4) + px_off;
+        if (a.wide) {
+          float4 w[K];
 #pragma unroll
-        for (int q = 0; q < K; ++q) w[q] = v3_lds64f(ws + q * kTPx * 4);
+          for (int q = 0; q < K; ++q) w[q] = v3_lds128(ws + q * kTPx * 4);
 #pragma unroll
-        for (int j = 0; j < CPW; ++j) {
-          const float2 x = v3_lds64f(xs + j * kTPx * 4);
+          for (int j = 0; j < CPW; ++j) {
+            const float4 x = v3_lds128(xs + j * kTPx * 4);
 #pragma unroll
-          for (int q = 0; q < K; ++q) {
-            acc[j][q] = fmaf(w[q].x, x.x, acc[j][q]);
-            acc[j][q] = fmaf(w[q].y, x.y, acc[j][q]);
+            for (int q = 0; q < K; ++q) {
+              acc[j][q] = fmaf(w[q].x, x.x, acc[j][q]);
+              acc[j][q] = fmaf(w[q].y, x.y, acc[j][q]);
+              acc[j][q] = fmaf(w[q].z, x.z, acc[j][q]);
+              acc[j][q] = fmaf(w[q].w, x.w, acc[j][q]);
+            }
+          }
+        } else {
+          float2 w[K];
+#pragma unroll
+          for (int q = 0; q < K; ++q) w[q] = v3_lds64f(ws + q * kTPx * 4);
+#pragma unroll
+          for (int j = 0; j < CPW; ++j) {
+            const float2 x = v3_lds64f(xs + j * kTPx * 4);
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+              acc[j][q] = fmaf(w[q].x, x.x, acc[j][q]);
+              acc[j][q] = fmaf(w[q].y, x.y, acc[j][q]);
+            }
           }
         }
         __syncwarp();
@@ -898,11 +921,18 @@ target_tile_kernel(const __grid_constant__ CUtensorMap map_feat, const TileArgs 
       float* out = a.partial + (int64_t)blockIdx.x * K * (C + 1);
 #pragma unroll
       for (int j = 0; j < CPW; ++j) {
-        const int c = cw * CPW + j;
+        const int c = c_first + j;
 #pragma unroll
         for (int q = 0; q < K; ++q) {
-          const float r = warp_sum(acc[j][q]);
-          if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
+          float r = acc[j][q];
+          if (a.wide) {          // the two halves hold different channels: reduce within 16 lanes
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (l16 == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
+          } else {
+            r = warp_sum(r);
+            if (lane == 0 && c < C) out[(int64_t)q * (C + 1) + c] = r;
+          }
         }
       }
     } else if (cw == a.n_cw) {
@@ -1688,7 +1718,7 @@ void launch_prep_centres(const float* centres, int C, int K, int normalize, floa
 void launch_proto_finalize(const void* partial, int n_blocks, int64_t n_total, int has_sel, float* scal,
                            const slcl_peer_t* peer, cudaStream_t stream);
 namespace {
-struct TilePlan { bool ok; int cpw, n_cw, npw, stages; unsigned grid; size_t smem; };
+struct TilePlan { bool ok; int cpw, n_cw, npw, stages, wide; unsigned grid; size_t smem; };
 TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
   TilePlan p{};
   p.ok = false;
@@ -1699,7 +1729,8 @@ TilePlan plan_tile(int64_t batch, int64_t C, int64_t pixels, int K) {
   else if (C <= 64) p.cpw = 4;
   else if (K <= 5) p.cpw = 8;
   else return p;
-  p.n_cw = (int)ceil_div<int64_t>(C, p.cpw);
+  p.wide = (C > 64 && p.cpw == 8 && !getenv("SLCL_TILE_NARROW")) ? 1 : 0;          // consumer warps of 2 x CPW channels
+  p.n_cw = (int)ceil_div<int64_t>(C, p.cpw * (p.wide ? 2 : 1));
   const int kp = K <= 4 ? 4 : 8;
   const size_t stage = (size_t)(C + K) * kTPx * 4;
   const size_t fixed = 128 + (size_t)C * kp * 4 + sizeof(V3Bars) + 64;
@@ -1784,7 +1815,7 @@ extern "C" int slcl_target_step(const float* feat, int64_t batch, int64_t channe
   a.loss_partial = reinterpret_cast<double2*>(ws);
   a.partial = reinterpret_cast<float*>(ws + align_up(blocks * sizeof(double2), 256));
   a.ticket = reinterpret_cast<unsigned int*>(ws + (workspace_bytes - kTicketBytes) / 16 * 16);
-  a.n_cw = p.n_cw; a.n_stages = p.stages; a.n_teams = p.npw;
+  a.n_cw = p.n_cw; a.n_stages = p.stages; a.n_teams = p.npw; a.wide = p.wide;
   launch_prep_centres(centres, (int)channels, K, 1, cstate, stream);
   int st = SLCL_ERR_UNSUPPORTED;
   switch (K) {
