@@ -1,3 +1,5 @@
+"""Host-side cost of one custom-op call through torch.ops.slcl vs the eager dispatch shortcut (slcl.ops.dispatch).
+"""
 import sys, time, torch
 sys.path.insert(0, 'soft-labeled-contrastive-learning_b200')
 from slcl import ops, functional as SF

@@ -1,3 +1,6 @@
+"""Fused target step at one shape with SLCL_TILE_TEAMS from the environment (team-count scaling of the pixel warps):
+    SLCL_TILE_TEAMS=4 python tools/target_step_teams.py B C H K
+"""
 import os, sys, torch
 ROOT = "/root/repo"
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "soft-labeled-contrastive-learning_b200"))
