@@ -35,6 +35,44 @@ def test_library_exports_every_declared_symbol():
     assert lib.slcl_compact_workspace_bytes(10000, 4) > 0
 
 
+def test_ctypes_table_matches_the_header_prototypes():
+    """Every prototype of include/slcl.h against slcl/_lib.py: the same number of parameters, pointers where the header
+    has pointers, 64-bit integers / size_t / float / double / int where it has those (an ABI drift would otherwise only
+    show up as a crash on the GPU box)."""
+    import ctypes as C
+    from slcl import _lib
+    txt = open(os.path.join(ROOT, "include", "slcl.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = []
+    for name in _lib.SIGNATURES:
+        m = re.search(r"\b" + name + r"\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+        assert m, f"no prototype of {name} in include/slcl.h"
+        protos.append((name, m.group(1)))
+
+    def kind(decl):
+        decl = " ".join(decl.split())
+        if "*" in decl or decl.startswith("slcl_stream_t"):
+            return "ptr"
+        for key, name in (("int64_t", "i64"), ("size_t", "size"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+            if re.search(r"\b" + key + r"\b", decl):
+                return name
+        raise AssertionError(f"unparsed parameter {decl!r}")
+
+    ckind = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int64: "i64", C.c_size_t: "size", C.c_double: "f64", C.c_float: "f32",
+             C.c_int: "i32"}
+    for name, params in protos:
+        params = params.strip()
+        want = [] if params in ("", "void") else [kind(p) for p in params.split(",")]
+        restype, argtypes = _lib.SIGNATURES[name]
+        got = []
+        for a in argtypes:
+            if a in ckind:
+                got.append(ckind[a])
+            else:          # POINTER(struct) and friends
+                got.append("ptr")
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+
+
 def test_argument_validation_without_gpu():
     """Validation happens before any launch, so it can be exercised on a GPU-less host."""
     from slcl import _lib
