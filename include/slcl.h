@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SLCL_VERSION 114            /* major*100 + minor */
+#define SLCL_VERSION 115            /* major*100 + minor */
 #define SLCL_MAX_CLASSES 8          /* K <= 8 (reference uses 4; MPCL defaults to 5) */
 #define SLCL_MAX_WEIGHT_COLS 16     /* partitions * classes <= 16 for class sums */
 
@@ -178,6 +178,12 @@ int slcl_target_step(const float* feat, int64_t batch, int64_t channels, int64_t
 int slcl_proto_bwd(const float* feat, const slcl_map_t* map,
                    const float* stash, const float* cstate, const float* scal, const float* grad_out,
                    const slcl_proto_params_t* params, float* dfeat, slcl_stream_t stream);
+/* Gradients of the same loss w.r.t. the two inputs no reference caller differentiates (utils/loss.py:516-517, :558-565):
+ * dmask [N,K] = d loss / d soft_mask (needs soft_mask), dsel [N] = d loss / d pixel_sel_loc (needs sel); either may be
+ * null.  A pass of its own over `feat` (cosines recomputed) with the forward's cstate and scal; dL/dloss = *grad_out. */
+int slcl_proto_bwd_aux(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
+                       const float* sel, const float* cstate, const float* scal, const float* grad_out,
+                       const slcl_proto_params_t* params, float* dmask, float* dsel, slcl_stream_t stream);
 
 /* Backward w.r.t. the raw centres [K,C] (only when they require grad; both
  * reference callers pass detached centres, trainer/Trainer_MPSCL.py:139,145). */

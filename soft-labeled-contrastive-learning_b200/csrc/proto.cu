@@ -493,6 +493,45 @@ __global__ void __launch_bounds__(kThreads, (K <= 5 && VEC == 4) ? SLCL_BWD_MINB
 }
 
 // ---------------------------------------------------------------------------
+// auxiliary backward: d loss / d soft mask [N,K] and d loss / d pixel_sel_loc [N]  (utils/loss.py:516-517, :558-565 take
+// both as tensors; no reference caller differentiates them, so this is a pass of its own that recomputes the cosines
+// instead of widening the stash of the hot path)
+//   dmask_ik = g coef sel_i dl_i/dM_ik          dsel_i = g coef (l_i - L)        coef = scal[1], L = scal[0]
+// ---------------------------------------------------------------------------
+template <int K, int VEC>
+__global__ void __launch_bounds__(kThreads) proto_aux_bwd_kernel(const ProtoArgs a, const float* scal, const float* grad_out,
+                                                                 float* dmask, float* dsel) {
+  extern __shared__ __align__(16) float sC[];
+  const int C = (int)a.channels;
+  load_centres_smem<K>(sC, a.cstate, C);
+  __syncthreads();
+  int64_t pix, off;
+  if (!locate<VEC>(a, pix, off)) return;
+  float nrm[VEC], dot[K][VEC];
+  channel_pass<K, VEC>(a.feat + off, a.sc, C, sC, nrm, dot, l2_policy(false));
+  const float gc = grad_out[0] * scal[1], loss = scal[0];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const float n = a.mc.normalize ? fmaxf(sqrtf(nrm[v]), 1e-12f) : 1.0f;
+    const float inv_n = 1.0f / n;
+    const float selv = a.sel != nullptr ? a.sel[pix + v] : 1.0f;
+    float cosv[K], M[K], dM[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      cosv[k] = dot[k][v] * inv_n;
+      if (a.labels != nullptr) M[k] = (a.labels[pix + v] == (long long)k) ? 1.0f : 0.0f;
+      else M[k] = a.soft_mask[(pix + v) * K + k];
+    }
+    const float row = margin_row_aux<K>(cosv, M, a.mc, dM);
+    if (dsel != nullptr) dsel[pix + v] = gc * (row - loss);
+    if (dmask != nullptr) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) dmask[(pix + v) * K + k] = gc * selv * dM[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // pseudo labels: argmax_k cos and (top1 - top2 > th)
 // ---------------------------------------------------------------------------
 template <int K, int VEC>
@@ -785,6 +824,28 @@ extern "C" int slcl_proto_bwd_peer(const float* feat, const slcl_map_t* map, con
                grad_out, dfeat, peer_ctx(peer), has_sel);
   })
   return check_launch("slcl_proto_bwd");
+}
+
+extern "C" int slcl_proto_bwd_aux(const float* feat, const slcl_map_t* map, const int64_t* labels, const float* soft_mask,
+                                  const float* sel, const float* cstate, const float* scal, const float* grad_out,
+                                  const slcl_proto_params_t* params, float* dmask, float* dsel, slcl_stream_t stream_) {
+  if (!feat || !validate_map(map) || !cstate || !scal || !grad_out || !params || (!dmask && !dsel)) return SLCL_ERR_INVALID_ARGUMENT;
+  if ((labels == nullptr) == (soft_mask == nullptr)) return SLCL_ERR_INVALID_ARGUMENT;
+  if (dmask && !soft_mask) return SLCL_ERR_INVALID_ARGUMENT;          // the one-hot mask of `labels` is not an input
+  if (dsel && !sel) return SLCL_ERR_INVALID_ARGUMENT;
+  const int K = params->n_class;
+  if (K < 2 || K > kMaxK) return SLCL_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan plan = make_plan(map, K, {feat});
+  ProtoArgs a = base_args(feat, map, cstate);
+  a.labels = labels; a.soft_mask = soft_mask; a.sel = sel;
+  a.mc = make_const(params);
+  SLCL_DISPATCH_K(K, plan.vec, {
+    int st = ensure_smem(proto_aux_bwd_kernel<KK, VV>, plan.smem);
+    if (st != SLCL_OK) return st;
+    proto_aux_bwd_kernel<KK, VV><<<plan.n_blocks, kThreads, plan.smem, stream>>>(a, scal, grad_out, dmask, dsel);
+  })
+  return check_launch("slcl_proto_bwd_aux");
 }
 
 extern "C" int slcl_proto_bwd(const float* feat, const slcl_map_t* map, const float* stash, const float* cstate,

@@ -69,6 +69,52 @@ __device__ __forceinline__ float margin_row(const float (&cosv)[K], const float 
   return -mc.scale * row;
 }
 
+// The same pixel for the two inputs no reference caller differentiates: returns the row loss l and
+//   dM[k] = dl / dM_k = -(T/T_b) [ (z_k - lse) + (marg'_k - plain'_k) (M_k - p_k sum_j M_j) ],   p_k = exp(z_k) / (s + 1e-4)
+// (M enters through z_k = plain'_k (1 - M_k) + marg'_k M_k, :550-554, and through the weights of :562; plain' / marg' are
+// the max-shifted logits, whose shifts are detached, :531 / :545).  Same expressions as margin_row up to `lse`.
+template <int K>
+__device__ __forceinline__ float margin_row_aux(const float (&cosv)[K], const float (&M)[K], const MarginConst& mc,
+                                                float (&dM)[K]) {
+  float plain[K], marg[K];
+  float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float cs = cosv[k];
+    plain[k] = cs * mc.inv_t;
+    const float u = 1.0f - cs * cs;
+    const float uc = fminf(fmaxf(u, 1e-4f), 1.0f);
+    const float rs = rsqrtf(uc);
+    const float sine = uc * rs;
+    const float phi = cs * mc.cos_m - sine * mc.sin_m;
+    const bool on = mc.easy ? (cs > 0.f) : (cs > mc.th);
+    const float ph = on ? phi : (mc.easy ? cs : cs - mc.mm);
+    marg[k] = ph * mc.inv_t;
+    m1 = fmaxf(m1, plain[k]);
+    m2 = fmaxf(m2, marg[k]);
+  }
+  float z[K], ez[K];
+  float s = 0.f, sum_m = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    z[k] = (plain[k] - m1) * (1.0f - M[k]) + (marg[k] - m2) * M[k];
+    ez[k] = expf(z[k]);
+    s += ez[k];
+    sum_m += M[k];
+  }
+  const float den = s + 1e-4f;
+  const float lse = logf(den);
+  const float inv_den = 1.0f / den;
+  float row = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    row += M[k] * (z[k] - lse);
+    const float delta = (marg[k] - m2) - (plain[k] - m1);
+    dM[k] = -mc.scale * ((z[k] - lse) + delta * (M[k] - ez[k] * inv_den * sum_m));
+  }
+  return -mc.scale * row;
+}
+
 
 // host side: the constants of one MPCL instance (utils/loss.py:475-480)
 inline MarginConst make_margin_const(const slcl_proto_params_t* p) {

@@ -73,6 +73,7 @@ SIGNATURES = {
     "slcl_centroids_fwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, C.c_int, C.c_float, _P, C.c_int, C.c_int, _P, C.c_float,
                                      _P, _P, _P, C.POINTER(PeerT), _P, _SZ, _P]),
     "slcl_proto_bwd": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P]),
+    "slcl_proto_bwd_aux": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _P]),
     "slcl_proto_bwd_centres_workspace_bytes": (_SZ, [_I64, _I64, C.c_int]),
     "slcl_proto_bwd_centres": (C.c_int, [_P, C.POINTER(MapT), _P, _P, _P, _P, C.POINTER(ProtoParamsT), _P, _P, _SZ, _P]),
     "slcl_pseudo_label": (C.c_int, [_P, C.POINTER(MapT), _P, C.c_int, C.c_float, _P, _P, _P, _SZ, _P]),

@@ -50,26 +50,33 @@ class _ProtoLoss(torch.autograd.Function):
                                              n_class, temperature, base_temperature, margin, easy_margin, normalize,
                                              *_peer_args(group))
         _exchange_loss_pair(scal, sel is not None, group)
-        ctx.save_for_backward(feat, stash, cstate, scal)
-        ctx.cfg = (rows_layout, n_class, normalize)
         ctx.soft = soft_mask is not None and soft_mask.requires_grad
         ctx.sel_grad = sel is not None and sel.requires_grad
+        aux = ctx.soft or ctx.sel_grad          # (no reference caller differentiates these two: keep them only when asked)
+        ctx.save_for_backward(feat, stash, cstate, scal, labels if aux else None, soft_mask if aux else None,
+                              sel if aux else None)
+        ctx.cfg = (rows_layout, n_class, normalize, temperature, base_temperature, margin, easy_margin)
         return scal[0]
 
     @staticmethod
     def backward(ctx, grad_out):
-        feat, stash, cstate, scal = ctx.saved_tensors
-        rows_layout, n_class, normalize = ctx.cfg
-        if ctx.soft or ctx.sel_grad:
-            raise NotImplementedError("slcl MPCL: gradients w.r.t. `mask` / `pixel_sel_loc` are not provided "
-                                      "(both reference callers pass constants)")
+        feat, stash, cstate, scal, labels, soft_mask, sel = ctx.saved_tensors
+        rows_layout, n_class, normalize, temperature, base_temperature, margin, easy_margin = ctx.cfg
         g = grad_out.reshape(1)
-        dfeat = dcen = None
+        dfeat = dcen = dmask = dsel = None
         if ctx.needs_input_grad[0]:
             dfeat = _ops.proto_bwd(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
         if ctx.needs_input_grad[4]:
             dcen = _ops.proto_bwd_centres(feat.detach(), stash, cstate, scal, g, rows_layout, n_class, normalize)
-        return dfeat, None, None, None, dcen, None, None, None, None, None, None, None, None
+        if ctx.soft or ctx.sel_grad:          # utils/loss.py:516-517 / :558-565 as differentiable inputs: one more pass over feat
+            dm, ds = _ops.proto_bwd_aux(feat.detach(), labels, None if soft_mask is None else soft_mask.detach(),
+                                        None if sel is None else sel.detach(), cstate, scal, g, rows_layout, n_class,
+                                        temperature, base_temperature, margin, easy_margin, normalize, ctx.soft, ctx.sel_grad)
+            if ctx.soft:
+                dmask = dm.reshape(soft_mask.shape).to(soft_mask.dtype)
+            if ctx.sel_grad:
+                dsel = ds.reshape(sel.shape).to(sel.dtype)
+        return dfeat, None, dmask, dsel, dcen, None, None, None, None, None, None, None, None
 
 
 class _ProtoTargetStep(torch.autograd.Function):

@@ -275,6 +275,44 @@ def _(feat, stash, cstate, scal, grad_out, rows_layout, n_class, normalize):
     return torch.empty_like(feat)
 
 
+@torch.library.custom_op("slcl::proto_bwd_aux", mutates_args=(), device_types="cuda")
+def proto_bwd_aux(feat: Tensor, labels: Optional[Tensor], soft_mask: Optional[Tensor], sel: Optional[Tensor], cstate: Tensor,
+                  scal: Tensor, grad_out: Tensor, rows_layout: bool, n_class: int, temperature: float, base_temperature: float,
+                  margin: float, easy_margin: bool, normalize: bool, want_dmask: bool, want_dsel: bool) -> Tuple[Tensor, Tensor]:
+    """-> (d loss / d soft_mask [N,K], d loss / d pixel_sel_loc [N]); an output that is not wanted comes back empty."""
+    dev = require_cuda(feat, labels, soft_mask, sel, cstate, scal, grad_out)
+    lib = _lib.load()
+    feat_c, m = _feat_map(feat, rows_layout)
+    n = m.batch * m.pixels
+    if labels is not None:
+        labels = labels.contiguous()
+    if soft_mask is not None:
+        soft_mask = soft_mask.to(_F32).contiguous()
+    if sel is not None:
+        sel = sel.to(_F32).contiguous()
+    if want_dmask and soft_mask is None:
+        raise ValueError("d/d mask needs the soft mask")
+    if want_dsel and sel is None:
+        raise ValueError("d/d pixel_sel_loc needs pixel_sel_loc")
+    dmask = torch.empty((n, n_class) if want_dmask else (0, n_class), dtype=_F32, device=dev)
+    dsel = torch.empty(n if want_dsel else 0, dtype=_F32, device=dev)
+    grad_out = grad_out.to(_F32).contiguous()
+    p = _params(n_class, temperature, base_temperature, margin, easy_margin, normalize)
+    with _guard(dev):
+        st = lib.slcl_proto_bwd_aux(ptr(feat_c), C.byref(m), ptr(labels), ptr(soft_mask), ptr(sel), ptr(cstate), ptr(scal),
+                                    ptr(grad_out), C.byref(p), ptr(dmask) if want_dmask else None,
+                                    ptr(dsel) if want_dsel else None, stream_ptr(dev))
+    check(st, "slcl_proto_bwd_aux")
+    return dmask, dsel
+
+
+@proto_bwd_aux.register_fake
+def _(feat, labels, soft_mask, sel, cstate, scal, grad_out, rows_layout, n_class, temperature, base_temperature, margin,
+      easy_margin, normalize, want_dmask, want_dsel):
+    n = feat.shape[0] if rows_layout else feat.shape[0] * feat.shape[2] * feat.shape[3]
+    return feat.new_empty((n if want_dmask else 0, n_class)), feat.new_empty(n if want_dsel else 0)
+
+
 @torch.library.custom_op("slcl::proto_bwd_centres", mutates_args=(), device_types="cuda")
 def proto_bwd_centres(feat: Tensor, stash: Tensor, cstate: Tensor, scal: Tensor, grad_out: Tensor, rows_layout: bool,
                       n_class: int, normalize: bool) -> Tensor:

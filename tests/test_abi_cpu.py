@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libslcl.so lacks {name}"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
-    assert lib.slcl_version() == 114
+    assert lib.slcl_version() == 115
     assert lib.slcl_strerror(0) == b"ok"
     assert b"invalid" in lib.slcl_strerror(-1)
     assert lib.slcl_proto_workspace_bytes(1 << 20) >= (1 << 20) // 256 * 16

@@ -101,6 +101,44 @@ def test_kat8_direct_mpcl_forward_soft_mask(api, golden):
     grad_close(unit.grad, golden["kat8_dunit"])
 
 
+@pytest.mark.parametrize("n,c,k,m,with_sel", [(300, 32, 4, .4, True), (257, 48, 5, .2, False), (64, 128, 3, .3, True)])
+def test_mpcl_gradients_into_soft_mask_and_pixel_sel_loc(api, n, c, k, m, with_sel):
+    """utils/loss.py:516-517 / :558-565 take `mask` and `pixel_sel_loc` as tensors; autograd of the reference's formula
+    (the restatement) gives their gradients, slcl_proto_bwd_aux must match -- next to the usual d/d features."""
+    loss_mod, _ = api
+    gen = cases.g(300 + n)
+    unit = F.normalize(torch.randn(n, c, generator=gen), dim=1)
+    cen = F.normalize(torch.randn(k, c, generator=gen), dim=1).t().contiguous()
+    mask = torch.softmax(2 * torch.randn(n, k, generator=gen), dim=1)
+    sel = torch.rand(n, generator=gen) if with_sel else None
+    spec = O.MarginSpec(num_class=k, temperature=.1, m=m, base_temperature=1.0)
+    uo, mo = unit.clone().requires_grad_(True), mask.clone().requires_grad_(True)
+    so = sel.clone().requires_grad_(True) if with_sel else None
+    ref = O.mpcl_forward(spec, uo.unsqueeze(1), None, cen, pixel_sel_loc=so, mask=mo)
+    ref.backward()
+    ud, md = unit.to(dev()).requires_grad_(True), mask.to(dev()).requires_grad_(True)
+    sd = sel.to(dev()).requires_grad_(True) if with_sel else None
+    mp = loss_mod.MPCL(dev(), num_class=k, temperature=.1, base_temperature=1, m=m)
+    out = mp(ud.unsqueeze(1), None, cen.to(dev()), pixel_sel_loc=sd, mask=md)
+    out.backward()
+    close(out, ref)
+    grad_close(ud.grad, uo.grad)
+    grad_close(md.grad, mo.grad)
+    if with_sel:
+        grad_close(sd.grad, so.grad)
+    # hard labels: only pixel_sel_loc can ask for a gradient
+    if with_sel:
+        lab = torch.randint(0, k, (n,), generator=gen)
+        so2 = sel.clone().requires_grad_(True)
+        ref2 = O.mpcl_forward(spec, unit.unsqueeze(1), lab, cen, pixel_sel_loc=so2)
+        ref2.backward()
+        sd2 = sel.to(dev()).requires_grad_(True)
+        out2 = mp(unit.to(dev()).unsqueeze(1), lab.to(dev()), cen.to(dev()), pixel_sel_loc=sd2)
+        out2.backward()
+        close(out2, ref2)
+        grad_close(sd2.grad, so2.grad)
+
+
 def test_kat9_cfg1_geometry_label_downsample(api, golden):
     """33x33 map (HW = 1089, odd: scalar path), labels 256 -> 33, K = 5, C = 128."""
     loss_mod, _ = api
