@@ -46,7 +46,11 @@ class MPCL(nn.Module):
         if labels is not None and mask is not None:                     # :502-503
             raise ValueError('Cannot define both `labels` and `mask`')
         if features.shape[1] != 1:
-            raise NotImplementedError("slcl MPCL supports n_views == 1 (the only use in the reference trainers)")
+            # the reference cannot run this either: mask.repeat(anchor_count, contrast_count) (:548) is [V*N, V*K] against
+            # [V*N, K] logits, a RuntimeError from the broadcast at :552 -- same exception type, raised before any work
+            raise RuntimeError(f"MPCL: n_views = {features.shape[1]} > 1 -- the size of tensor a ({self.num_class}) must match "
+                               f"the size of tensor b ({features.shape[1] * self.num_class}) at non-singleton dimension 1 "
+                               "(utils/loss.py:548-552); only n_views == 1 is defined")
         n = features.shape[0]
         if labels is None and mask is None:                             # :504-505  (eye(N) positives)
             if n != self.num_class:

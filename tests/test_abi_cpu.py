@@ -173,6 +173,8 @@ def test_mpcl_error_behaviour_matches_reference():
         m(torch.randn(4, 1, 8), torch.zeros(4), torch.randn(8, 4), mask=torch.ones(4, 4))
     with pytest.raises(ValueError):
         m(torch.randn(4, 1, 8), torch.zeros(5), torch.randn(8, 4))
+    with pytest.raises(RuntimeError):          # n_views > 1: the reference fails in the broadcast at utils/loss.py:552
+        m(torch.randn(4, 2, 8), torch.zeros(4), torch.randn(8, 4))
 
 
 def test_class_centre_state_layout(tmp_path):

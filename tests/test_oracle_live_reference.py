@@ -72,6 +72,39 @@ def test_soft_mask_forward(ref, seed):
     same(O.mpcl_forward(O.MarginSpec(k, 0.07, 0.5, 0.07), unit, None, cen, mask=mask), want)
 
 
+@pytest.mark.parametrize("seed", [24, 25])
+def test_soft_mask_and_pixel_sel_loc_gradients(ref, seed):
+    """The reference takes `mask` and `pixel_sel_loc` as tensors (utils/loss.py:516-517, :558-565): its autograd gives
+    their gradients, and the restatement -- which the GPU test of slcl_proto_bwd_aux is checked against -- must agree."""
+    gen = g(seed)
+    n, c, k = 120, 16, 4
+    unit = F.normalize(torch.randn(n, c, generator=gen), dim=1).unsqueeze(1)
+    cen = F.normalize(torch.randn(k, c, generator=gen), dim=1).t().contiguous()
+    mask = torch.softmax(2 * torch.randn(n, k, generator=gen), 1)
+    sel = torch.rand(n, generator=gen)
+    mr, sr = mask.clone().requires_grad_(True), sel.clone().requires_grad_(True)
+    with ref_loader.host_tensors():
+        want = ref.MPCL("cpu", num_class=k, temperature=0.1, m=0.4, base_temperature=1.0)(unit, None, cen, pixel_sel_loc=sr, mask=mr)
+        want.backward()
+    mo, so = mask.clone().requires_grad_(True), sel.clone().requires_grad_(True)
+    got = O.mpcl_forward(O.MarginSpec(k, 0.1, 0.4, 1.0), unit, None, cen, pixel_sel_loc=so, mask=mo)
+    got.backward()
+    same(got, want)
+    same(mo.grad, mr.grad, atol=1e-9)
+    same(so.grad, sr.grad, atol=1e-9)
+
+
+def test_more_than_one_view_fails_in_the_reference_too(ref):
+    """MPCL with n_views > 1: mask.repeat(anchor_count, contrast_count) (utils/loss.py:548) makes a [V N, V K] mask
+    against [V N, K] logits -- a RuntimeError in the reference; the product raises the same type up front."""
+    gen = g(26)
+    feats = F.normalize(torch.randn(6, 2, 8, generator=gen), dim=2)
+    cen = F.normalize(torch.randn(8, 4, generator=gen), dim=0)
+    with ref_loader.host_tensors():
+        with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+            ref.MPCL("cpu", num_class=4)(feats, torch.randint(0, 4, (6,), generator=gen), cen)
+
+
 @pytest.mark.parametrize("seed,k,drop", [(31, 4, None), (32, 4, 2), (33, 5, 0)])
 def test_ema_class_centres_with_empty_class(ref, seed, k, drop):
     gen = g(seed)
