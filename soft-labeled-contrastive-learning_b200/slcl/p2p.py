@@ -116,7 +116,7 @@ def p2p_loss(feat, idx_a, idx_b, lab_a, lab_b, id_a, id_b, weight, temperature, 
     ``metas``: the {label, id} rows (``ops.rows_meta`` / ``ops.pad_meta``) when the caller has built them already
     (``lab_*`` are then unused); ``id_bound``: the ids are int64 in [0, id_bound) (pixel indices) -> the self-pair maps
     come from two lookup tables instead of a sort."""
-    if same_rows and n_class == 0 and n_batch == 1 and idx_a.numel() >= _SORT_MIN_ROWS:
+    if same_rows and n_class == 0 and n_batch == 1 and metas is None and idx_a.numel() >= _SORT_MIN_ROWS:
         # General labels over ONE large row set (SupCon family, ISCL): the sums are order-invariant, so gather the rows
         # sorted by contrast label -- label-uniform column tiles take the sweeps' fast path -- and hand the kernels the
         # self maps (row i is its own contrast row), which takes the id tests out of the sweeps.  (Small or batched

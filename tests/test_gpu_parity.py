@@ -757,6 +757,7 @@ def test_kat7_local_and_block_con_loss(api, golden):
     (1, 2, 32, 64, 32, True),        # 4 tiles of 2048 rows: the block-diagonal batched sweeps
     (1, 2, 32, 224, 224 // 7, True), # 49 tiles of 2048 rows: BASELINE cfg3's map, more tiles than SMs / row tiles
     (1, 2, 16, 288, 8, True),        # 1296 tiles of 128 rows: more batches than finishing blocks (one table block per tile)
+    (1, 2, 16, 64, 64, True),        # ONE tile of 8192 rows: n_batch = 1 with prebuilt metadata (no label sort in the general mode)
     (2, 2, 24, 48, 16, True),        # 9 tiles of 1024 rows, some all-background tiles
     (1, 2, 16, 64, 32, False),       # unlabelled: other views are the positives
     (1, 2, 16, 36, 12, True),        # 288 rows per tile (not a multiple of 128): the per-tile loop
@@ -768,7 +769,7 @@ def test_block_con_loss_vs_oracle(api, b, v, c, hw, bs, labelled):
     gen = cases.g(800 + hw + bs)
     f5 = F.normalize(torch.randn(b, v, c, hw, hw, generator=gen), dim=2)
     lab = torch.randint(0, 4, (b, v, hw, hw), generator=gen) if labelled else None
-    if labelled:
+    if labelled and hw // bs > 1:
         lab[..., :bs, :bs] = 0                                          # one all-background tile: skipped (:439-440)
     fo = f5.clone().requires_grad_(True)
     ref = O.block_con_loss(fo, lab, 0.7, bs)
